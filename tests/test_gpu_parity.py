@@ -1,0 +1,284 @@
+"""GPU parity tests: the CUDA path through the C ABI vs the CPU oracle / golden fixtures.
+
+Tolerances are the north star's: FP32 path logits <= 1e-4 max-abs, gradients <= 1e-3
+relative, TF32 path logits <= 1e-2 with argmax agreement wherever the oracle's top-2
+margin exceeds 2e-2, bit-exact integer work, identical greedy sequences.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import wavenet_oracle as O
+from tests.util import make_cfg, make_net, rel_err
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+LOGIT_TOL_FP32 = 1e-4
+GRAD_TOL = 1e-3
+LOGIT_TOL_TF32 = 1e-2
+
+
+def load_gold(name):
+    with np.load(os.path.join(GOLD, name)) as f:
+        return {k: f[k] for k in f.files}
+
+
+def split_gold(gd, prefix):
+    return {k[len(prefix):]: v for k, v in gd.items() if k.startswith(prefix)}
+
+
+def dev(a, dtype=torch.int32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dtype=dtype)
+
+
+def run_train_step(net, x, tgt, T):
+    """train.py:58-80 through the reference-named methods; returns logits(B,Q,1,T), loss."""
+    out = net.forward_causal_block(x)
+    out, skip = net.forward_residual_block(out)
+    W = out.data.shape[3]
+    if W - T >= 1:
+        skip = net.slice_1d(skip, W - T)
+    logits = net.forward_softmax_block(skip, apply_softmax=False)
+    loss = net.cross_entropy(logits, tgt)
+    return logits, loss
+
+
+# ---- golden fixtures: forward, loss, gradients, one optimiser step -------------------------------
+@pytest.mark.parametrize("name,T", [("tiny_k2", 20), ("tiny_k3_bias", 61), ("odd", 33)])
+def test_train_step_matches_golden(name, T):
+    cfg = make_cfg(name)
+    gd = load_gold("train_%s.npz" % name)
+    net = make_net(cfg, split_gold(gd, "w:"))
+    logits, loss = run_train_step(net, gd["x"], gd["target"], T)
+    got = logits.data.detach().cpu().numpy()[:, :, 0, :]
+    assert got.shape == gd["logits"].shape
+    assert np.abs(got - gd["logits"]).max() < LOGIT_TOL_FP32
+    assert abs(float(loss.data) - float(gd["loss"])) < 1e-5
+    net.update_laerning_rate(1e-3)
+    net.backward()
+    g = net.get_grads()
+    for k, v in split_gold(gd, "g:").items():
+        if np.abs(v).max() == 0:
+            assert np.abs(g[k]).max() == 0, k
+        else:
+            assert rel_err(g[k], v) < GRAD_TOL, (k, rel_err(g[k], v))
+    net.update()
+    assert abs(float(net._norm[0]) - float(gd["norm"])) < 1e-4 * max(1.0, float(gd["norm"]))
+    w2 = net.get_weights()
+    for k, v in split_gold(gd, "u:").items():
+        assert np.abs(w2[k] - v).max() < 2e-5, k
+
+
+# ---- seeded inputs vs the oracle at the reference's configurations ------------------------------------
+@pytest.mark.parametrize("name,B,W,T", [("A", 2, 700, 700), ("B", 1, 600, 343), ("C_small", 2, 1000, 1000),
+                                        ("C", 1, 4200, 1129)])
+def test_forward_backward_matches_oracle(name, B, W, T):
+    cfg = make_cfg(name)
+    rng = np.random.default_rng(1234)
+    w = O.init_weights(cfg, rng, np.float64)
+    x = np.random.default_rng(0).integers(0, cfg.quantization_steps, (B, W)).astype(np.int32)
+    tgt = np.random.default_rng(1).integers(0, cfg.quantization_steps, (B, T)).astype(np.int32)
+    fw = O.forward_loss(cfg, w, x, tgt, train_width=T, dtype=np.float64)
+    g_ref = O.backward(cfg, fw)
+    net = make_net(cfg, w)
+    logits, loss = run_train_step(net, x, tgt, T)
+    got = logits.data.detach().cpu().numpy()[:, :, 0, :]
+    assert np.abs(got - fw["logits"]).max() < LOGIT_TOL_FP32
+    assert abs(float(loss.data) - float(fw["loss"])) < 1e-5
+    net.backward()
+    g = net.get_grads()
+    for k, v in g_ref.items():
+        if np.abs(v).max() == 0:
+            assert np.abs(g[k]).max() == 0, k
+        else:
+            assert rel_err(g[k], v) < GRAD_TOL, (k, rel_err(g[k], v))
+
+
+def test_block_outputs_and_one_hot_input():
+    cfg = make_cfg("tiny_k3_bias")
+    rng = np.random.default_rng(5)
+    w = O.init_weights(cfg, rng, np.float64, bias_scale=0.3)
+    x = rng.integers(0, 6, (2, 45)).astype(np.int32)
+    fw = O.forward_loss(cfg, w, x, None, dtype=np.float64)
+    net = make_net(cfg, w)
+    onehot = O.onehot_pixel_image(x, 6)                        # the reference's input format
+    c = net.forward_causal_block(onehot)
+    assert tuple(c.data.shape) == (2, 5, 1, 45)
+    assert np.abs(c.data.cpu().numpy()[:, :, 0, :] - fw["causal"]).max() < 1e-5
+    out, skip = net.forward_residual_block(c)
+    assert np.abs(out.data.cpu().numpy()[:, :, 0, :] - fw["out"]).max() < 1e-5
+    assert np.abs(skip.data.cpu().numpy()[:, :, 0, :] - fw["sum_skip"]).max() < 1e-5
+    probs = net.forward_one_step(onehot, apply_softmax=True, as_numpy=True)
+    want = O.softmax_axis1(fw["logits"])
+    assert probs.shape == (2, 6, 1, 45) and np.abs(probs[:, :, 0, :] - want).max() < 1e-5
+    # foreign (numpy) inputs to the later blocks are accepted like Chainer accepts raw arrays
+    out2, skip2 = net.forward_residual_block(fw["causal"][:, :, None, :].astype(np.float32))
+    assert np.abs(skip2.data.cpu().numpy()[:, :, 0, :] - fw["sum_skip"]).max() < 1e-5
+    y = net.forward_softmax_block(fw["sum_skip"][:, :, None, -7:].astype(np.float32), apply_softmax=False)
+    assert np.abs(y.data.cpu().numpy()[:, :, 0, :] - fw["logits"][:, :, -7:]).max() < 1e-5
+    with pytest.raises(Exception, match="width"):
+        net.cross_entropy(y, np.zeros((2, 6), np.int32))
+
+
+def test_full_size_properties_config_c():
+    """BASELINE config 2 shape (32 x 16000): size-independent properties instead of the oracle."""
+    cfg = make_cfg("C")
+    w = O.init_weights(cfg, np.random.default_rng(1234), np.float32)
+    net = make_net(cfg, w)
+    B, W = 32, 16000
+    x = np.random.default_rng(0).integers(0, 256, (B, W)).astype(np.int32)
+    tgt = np.concatenate([x[:, 1:], np.random.default_rng(2).integers(0, 256, (B, 1)).astype(np.int32)], axis=1)
+    xd, td = dev(x), dev(tgt)
+    net._bind(B, W)
+    logits = torch.empty((B, W, 256), dtype=torch.float32, device="cuda")
+    from wavenet_b200.wavenet import _ptr, _stream
+    from wavenet_b200._lib import check
+    check(net._libh.wn_forward_loss(net._h, _ptr(net._params), _ptr(xd), _ptr(td), W, _ptr(net._loss), _ptr(logits),
+                                    _stream()))
+    loss_full = float(net._loss[0])
+    assert abs(loss_full - np.log(256)) < 0.5                  # random init: near-uniform predictions
+    # (1) batch items are independent and causal: row 5 alone, truncated to 6000 samples, reproduces its prefix...
+    sub = 6000
+    fw = O.forward_loss(cfg, w, x[5:6, :sub], None, dtype=np.float32)   # oracle on one short clip (seconds)
+    # ...except where the zero prefix (Q1) depends on the width: compare beyond the receptive field of those zeros
+    zp_full = [O.zero_prefix(W, 2 ** i, 2) for i in range(10)]
+    zp_sub = [O.zero_prefix(sub, 2 ** i, 2) for i in range(10)]
+    got = logits[5, :sub].detach().cpu().numpy().T
+    if zp_full == zp_sub:
+        assert np.abs(got - fw["logits"][0]).max() < LOGIT_TOL_FP32
+    else:
+        lo = 3 * 1023 + max(max(zp_full), max(zp_sub)) + 2
+        assert np.abs(got[:, lo:] - fw["logits"][0][:, lo:]).max() < LOGIT_TOL_FP32
+    # (2) loss is the mean of per-row losses: recompute from the returned logits
+    lg = logits.double()
+    lse = torch.logsumexp(lg, dim=2)
+    picked = torch.gather(lg, 2, td.long().unsqueeze(2)).squeeze(2)
+    assert abs(float((lse - picked).mean()) - loss_full) < 1e-5
+    # (3) gradient of the mean loss w.r.t. the last head bias == mean(softmax - onehot)
+    net.backward()
+    g = net.get_grads()["softmax_1/b"]
+    sm = torch.softmax(lg, dim=2)
+    want = (sm.sum(dim=(0, 1)) - torch.bincount(td.flatten().long(), minlength=256).double()) / (B * W)
+    assert rel_err(g, want.cpu().numpy()) < GRAD_TOL
+
+
+def test_adam_multi_step_matches_oracle():
+    cfg = make_cfg("odd")
+    rng = np.random.default_rng(8)
+    w = O.init_weights(cfg, rng, np.float64)
+    net = make_net(cfg, w)
+    net.update_laerning_rate(1e-3)
+    w_ref = {k: v.copy() for k, v in w.items()}
+    st = O.new_adam_state(w_ref)
+    for step in range(4):
+        x = rng.integers(0, 37, (2, 40)).astype(np.int32)
+        tgt = rng.integers(0, 37, (2, 25)).astype(np.int32)
+        fw = O.forward_loss(cfg, w_ref, x, tgt, train_width=25, dtype=np.float64)
+        g_ref = O.backward(cfg, fw)
+        O.clip_and_adam(cfg, w_ref, g_ref, st, lr=1e-3)
+        loss = net.train_step(dev(x), dev(tgt), train_width=25)
+        assert abs(float(loss[0]) - float(fw["loss"])) < 1e-4
+    assert net.optimizer.t == 4
+    w_got = net.get_weights()
+    for k in w_ref:
+        assert np.abs(w_got[k] - w_ref[k]).max() < 5e-5, k
+
+
+# ---- generation ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["tiny_k2", "tiny_k3_bias"])
+@pytest.mark.parametrize("act", ["reference", "relu"])
+def test_greedy_generation_matches_golden(name, act):
+    cfg = make_cfg(name)
+    gd = load_gold("gen_%s.npz" % name)
+    net = make_net(cfg, split_gold(gd, "w:"), faster=True, head_act=act)
+    n, steps = gd["greedy_" + act].shape
+    got = net.generate(gd["window"], steps, mode="greedy").cpu().numpy()
+    assert np.array_equal(got, gd["greedy_" + act])
+
+
+@pytest.mark.parametrize("n", [1, 3])
+def test_greedy_1000_steps_config_c(n):
+    """North star: identical greedy-decoded sequences for 1,000 steps (config C)."""
+    cfg = make_cfg("C")
+    w = O.init_weights(cfg, np.random.default_rng(1234), np.float64)
+    Win = O.input_width(cfg)
+    if n == 1:
+        window = np.full((1, Win), 127, dtype=np.int32)                 # generate.py:21
+    else:
+        window = np.random.default_rng(0).integers(0, 256, (n, Win)).astype(np.int32)
+    ring = O.RingGenerator(cfg, w, n, head_act="reference", dtype=np.float64)
+    want = ring.generate_greedy(window, 1000)
+    net = make_net(cfg, w, faster=True, head_act="reference")
+    got = net.generate(window, 1000, mode="greedy").cpu().numpy()
+    assert np.array_equal(got, want)
+
+
+def test_forward_one_step_api_matches_literal_generator():
+    """_forward_one_step as generate.py:24-35 drives it, vs the literal rolled-window restatement."""
+    cfg = make_cfg("tiny_k2")
+    rng = np.random.default_rng(3)
+    w = O.init_weights(cfg, rng, np.float64, bias_scale=0.1)
+    Win = O.input_width(cfg)
+    lit = O.LiteralFastGenerator(cfg, w, np.float64)
+    net = make_net(cfg, w, faster=True)
+    seq = [127 % 6] * Win
+    for step in range(15):
+        window = np.array(seq[-Win:], dtype=np.int32).reshape(1, -1)
+        onehot = O.onehot_pixel_image(window, 6)
+        want = lit._forward_one_step(onehot, apply_softmax=True)[0, :, 0, -1]
+        got = net._forward_one_step(onehot, apply_softmax=True, as_numpy=True)
+        assert got.shape == (1, 6, 1, 1)
+        assert np.abs(got[0, :, 0, -1] - want).max() < 1e-5, step
+        seq.append(int(np.argmax(want)))
+    net.prev_causal_outputs = None          # cache reset as in _tests_/faster_generation/generate.py:44
+    got = net._forward_one_step(O.onehot_pixel_image(np.array(seq[:Win]).reshape(1, -1), 6), as_numpy=True)
+    lit2 = O.LiteralFastGenerator(cfg, w, np.float64)
+    want = lit2._forward_one_step(O.onehot_pixel_image(np.array(seq[:Win]).reshape(1, -1), 6))[0, :, 0, -1]
+    assert np.abs(got[0, :, 0, 0] - want).max() < 1e-5
+
+
+def test_sampling_follows_softmax_distribution():
+    cfg = make_cfg("tiny_k2")
+    w = O.init_weights(cfg, np.random.default_rng(4), np.float64)
+    Win = O.input_width(cfg)
+    n = 4096
+    window = np.tile(np.arange(Win, dtype=np.int32) % 6, (n, 1))
+    net = make_net(cfg, w, faster=True)
+    out = net.generate(window, 1, mode="sample", seed=123).cpu().numpy()[:, 0]
+    ring = O.RingGenerator(cfg, w, 1, dtype=np.float64)
+    p = O.softmax_axis1(ring.prime(window[:1])[:, :, None])[0, :, 0]
+    freq = np.bincount(out, minlength=6) / n
+    assert np.abs(freq - p).max() < 4 * np.sqrt(0.25 / n) + 1e-3
+    out2 = net.generate(window, 1, mode="sample", seed=123).cpu().numpy()[:, 0]
+    assert np.array_equal(out, out2)         # counter-based RNG: same seed, same draw
+
+
+# ---- data.py on device ---------------------------------------------------------------------------------------
+def test_mulaw_device_kernels_bit_exact():
+    from oracle import data_oracle as D
+    from wavenet_b200 import _lib
+    from wavenet_b200.wavenet import _ptr, _stream
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    sig = np.concatenate([rng.uniform(-1.2, 1.2, 100000), [0.0, 1.0, -1.0, 0.5, -0.5]])
+    want = D.mulaw_quantize(sig)
+    sd = torch.from_numpy(sig).cuda()
+    q = torch.empty(sig.size, dtype=torch.int32, device="cuda")
+    _lib.check(lib.wn_mulaw_encode(_ptr(sd), sig.size, 256, _ptr(q), _stream()))
+    got = q.cpu().numpy()
+    # log() differs by <= 1 ulp between libm and CUDA: allow mismatches only exactly at bin edges
+    bad = got != want
+    assert bad.mean() < 1e-4
+    assert np.all(np.abs(got[bad] - want[bad]) <= 1)
+    qa = torch.arange(256, dtype=torch.int32, device="cuda")
+    out = torch.empty(256, dtype=torch.float64, device="cuda")
+    _lib.check(lib.wn_mulaw_decode(_ptr(qa), 256, 256, 32768.0, _ptr(out), _stream()))
+    n = (np.arange(256) / 256.0 - 0.5) * 2.0
+    ref = np.sign(n) * (256.0 ** np.abs(n)) / 255.0 * 32768.0
+    assert np.allclose(out.cpu().numpy(), ref, rtol=1e-12)
+    assert np.array_equal(out.cpu().numpy().astype(np.int16)[1:], D.decode(np.arange(256))[1:, 0])

@@ -1,0 +1,52 @@
+"""Shared helpers for the parity tests."""
+import numpy as np
+
+from oracle import wavenet_oracle as O
+
+
+def make_cfg(name):
+    if name == "tiny_k2":
+        return O.OracleParams(quantization_steps=6, causal_conv_channels=[4], residual_conv_channels=[3, 3, 3],
+                              residual_num_blocks=2, softmax_conv_channels=[5, 6])
+    if name == "tiny_k3_bias":
+        return O.OracleParams(quantization_steps=6, causal_conv_channels=[4, 5], causal_conv_filter_width=3,
+                              causal_conv_no_bias=False, residual_conv_filter_width=3,
+                              residual_conv_dilation_no_bias=False, residual_conv_projection_no_bias=False,
+                              residual_conv_channels=[3, 2, 3], residual_num_blocks=2,
+                              softmax_conv_channels=[5, 7, 6])
+    if name == "odd":   # channel counts that are not multiples of anything
+        return O.OracleParams(quantization_steps=37, causal_conv_channels=[19], residual_conv_channels=[13, 11, 13, 7],
+                              residual_num_blocks=2, softmax_conv_channels=[23, 37], weight_decay=0.01)
+    if name == "A":     # Params() defaults, wavenet.py:102-146
+        return O.OracleParams()
+    if name == "B":     # train_audio/model.py:24-43
+        return O.config_B()
+    if name == "C":     # BASELINE.json configs 2-5
+        return O.config_C()
+    if name == "C_small":  # config C channel widths, 2 blocks of 6 layers (d=1..32)
+        return O.OracleParams(causal_conv_channels=[64], residual_conv_channels=[64] * 6, residual_num_blocks=2,
+                              softmax_conv_channels=[256, 256, 256])
+    raise KeyError(name)
+
+
+def to_product_params(cfg):
+    from wavenet_b200.wavenet import Params
+    p = Params()
+    for k in p.to_dict():
+        setattr(p, k, getattr(cfg, k))
+    return p
+
+
+def make_net(cfg, w, faster=False, **kw):
+    from wavenet_b200.wavenet import WaveNet
+    from wavenet_b200.faster_wavenet import FasterWaveNet
+    net = (FasterWaveNet if faster else WaveNet)(to_product_params(cfg), seed=0, **kw)
+    net.set_weights(w)
+    net.to_gpu()
+    return net
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))

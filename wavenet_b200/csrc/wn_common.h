@@ -1,0 +1,175 @@
+// Internal definitions shared by the translation units of libwavenet_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/wavenet_b200.h"
+
+void wn_set_error(const char* fmt, ...);
+void wn_count_launch();
+
+#define WN_CHECK_CUDA(expr)                                                               \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      wn_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return WN_ECUDA;                                                                    \
+    }                                                                                     \
+  } while (0)
+
+#define WN_CHECK_LAUNCH()                                                               \
+  do {                                                                                  \
+    wn_count_launch();                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess) {                                                            \
+      wn_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return WN_ECUDA;                                                                  \
+    }                                                                                   \
+  } while (0)
+
+#define WN_REQUIRE(cond, code, ...) \
+  do {                              \
+    if (!(cond)) {                  \
+      wn_set_error(__VA_ARGS__);    \
+      return (code);                \
+    }                               \
+  } while (0)
+
+#define WN_TRY(expr)        \
+  do {                      \
+    int _r = (expr);        \
+    if (_r != WN_OK) return _r; \
+  } while (0)
+
+// ---- parameter table ---------------------------------------------------------------
+struct ConvParam {
+  int64_t w_off = -1;  // offset (floats) of W (out, in, taps) -- Chainer (O,C,1,k)/(O,C,k,1) share this element order
+  int64_t b_off = -1;  // offset of bias or -1
+  int out_ch = 0, in_ch = 0, taps = 1;
+};
+
+struct ResLayer {
+  ConvParam wf, wg, proj, skip;
+  int dilation = 1;
+  int G = 0;
+};
+
+// ---- training tape (offsets in floats into the bound workspace) ------------------
+struct Tape {
+  int B = 0, W = 0;
+  int64_t P = 0;
+  int64_t emb = 0, demb = 0;          // [kc][Q][R0] transposed first causal filter / its gradient
+  std::vector<int64_t> cx;            // causal layer outputs [P][C_i]
+  std::vector<int64_t> x;             // x[l]: input of residual layer l, x[L]: final output   [P][R]
+  std::vector<int64_t> tfsg;          // [P][2G]  tanh | sigmoid
+  std::vector<int64_t> z;             // [P][G]
+  int64_t skip = 0;                   // [P][S]
+  std::vector<int64_t> hbuf;          // head activations h[i] (i>=1) [B*T][c_i]; logits = last
+  int64_t dlogits = 0;                // [B*T][Q]
+  int64_t dh[2] = {0, 0};             // [B*T][max head width]
+  int64_t dout[2] = {0, 0};           // [P][R]
+  int64_t dz = 0;                     // [P][Gmax]
+  int64_t dafg = 0;                   // [P][2Gmax]
+  int64_t dcx[2] = {0, 0};            // [P][max causal width] (only when n_causal > 1)
+  int64_t loss_acc = 0;               // 2 doubles
+  int64_t total = 0;
+};
+
+enum Phase { PH_NONE = 0, PH_CAUSAL = 1, PH_RESIDUAL = 2, PH_HEAD = 3, PH_LOSS = 4 };
+
+struct wn_handle {
+  wn_config cfg;
+  int prec = WN_PREC_FP32;
+  std::vector<wn_param_desc> descs;
+  int64_t flat_size = 0, param_elems = 0;
+  std::vector<ConvParam> causal;
+  std::vector<ResLayer> layers;  // residual_num_blocks * n_res_layers
+  std::vector<ConvParam> head;
+  int R = 0, S = 0, Q = 0;
+  // bound workspace
+  float* ws = nullptr;
+  int64_t ws_bytes = 0;
+  Tape tape;
+  int phase = PH_NONE;
+  bool causal_from_idx = false;   // gradient can reach the causal stack
+  bool residual_external = false;
+  bool head_external = false;
+  const int32_t* x_idx = nullptr;  // device pointer given to the causal phase (must stay alive until backward)
+  int T = 0;                       // columns seen by head/loss
+  int sm_count = 148;
+};
+
+// ---- SIMT fp32 kernels (wn_simt.cu) ---------------------------------------------
+struct GemmArgs {
+  const float* A;
+  int lda;
+  int K;
+  int ntaps;
+  int shift[4];       // A row = in_row - shift[tap] (negative shift = look ahead)
+  int64_t M;          // output rows
+  int rows_out;       // output rows per sequence
+  int rows_in;        // A rows per sequence
+  int in_off;         // t_in = t_out + in_off
+  int a_relu;         // apply max(.,0) to A elements
+  const float* Wt;    // w(n, tap, k) = Wt[n*sn + k*sk + tap*st]
+  int64_t sn, sk, st;
+  int N;
+  const float* bias;  // [N] or null
+  int zp;             // rows with t_out < zp are forced to 0 (after bias)
+  const float* Rsd;   // residual added after the mask, or null
+  int ldr;
+  const float* mask_src;  // multiply by (mask_src[mrow][n] > 0), or null;
+  int ldm;                //   mrow = seq*mask_rows_in + t_out + mask_in_off
+  int mask_rows_in;
+  int mask_in_off;
+  int accumulate;     // Y += result
+  float* Y;
+  int ldy;
+};
+int simt_gemm(const GemmArgs& g, cudaStream_t s);
+
+struct WgradArgs {
+  const float* dY;    // [M][ldd], N columns used
+  int ldd;
+  int N;
+  int dy_rows_out;    // dY row mapping (same scheme as A): rows of the iteration space per sequence
+  int dy_rows_in;
+  int dy_in_off;
+  const float* A;
+  int lda;
+  int K;
+  int ntaps;
+  int shift[4];
+  int64_t M;          // iteration rows
+  int rows_out, rows_in, in_off;   // A row mapping
+  int a_relu;
+  float* dW;          // dW(n, tap, k) += ... at dW[n*sn + k*sk + tap*st]
+  int64_t sn, sk, st;
+  float* dbias;       // [N] += column sums of dY, or null
+};
+int simt_wgrad(const WgradArgs& g, int sm_count, cudaStream_t s);
+
+int simt_embed_prepare(const float* Wc, float* emb, int R, int Q, int kc, cudaStream_t s);
+int simt_embed_forward(const float* emb, const float* bias, const int32_t* idx, float* out, int B, int W, int R, int Q,
+                       int kc, cudaStream_t s);
+int simt_embed_backward(const float* dout, const int32_t* idx, float* demb, float* dWc, float* dbias, int B, int W,
+                        int R, int Q, int kc, cudaStream_t s);
+int simt_gate_forward(float* afg, float* z, int64_t P, int G, cudaStream_t s);
+int simt_gate_backward(const float* tfsg, const float* dz, float* dafg, int64_t P, int W, int G, int zp,
+                       cudaStream_t s);
+int simt_softmax_rows(const float* in, float* out, int64_t rows, int Q, cudaStream_t s);
+int simt_cross_entropy(const float* logits, const int32_t* target, int64_t rows, int Q, double* acc, float* loss,
+                       float* dlogits, cudaStream_t s);
+int simt_onehot_to_index(const float* onehot, int B, int Q, int W, int32_t* idx, cudaStream_t s);
+
+// ---- optimiser (wn_optim.cu) ---------------------------------------------------
+int optim_clip_adam(float* params, float* grads, float* m, float* v, int64_t n, int t, float lr, float beta1,
+                    float beta2, float eps, float wd, float clip, float grad_scale, double* scratch, float* norm_out,
+                    int sm_count, cudaStream_t s);
+
+// ---- tcgen05 TF32 kernels (wn_tc.cu) ---------------------------------------------
+bool tc_layer_supported(const wn_handle* h);
+int tc_forward_residual(wn_handle* h, const float* params, cudaStream_t s);

@@ -1,0 +1,688 @@
+// Incremental generator: FasterWaveNet._forward_one_step (faster_wavenet.py:50-113)
+// and the sampling loop of train_audio/generate.py:24-43 as ONE persistent kernel.
+//
+// The reference keeps, per layer, a full receptive-field-wide window moved with
+// xp.roll (faster_wavenet.py:72,90,94) and runs the head over the whole window
+// (faster_wavenet.py:105-113) although only the last column is consumed
+// (generate.py:38).  Here each layer keeps a (k-1)*d deep ring of its own input,
+// only the last column is computed, sampling happens on device and the loop over
+// audio samples never returns to the host.  Arithmetic is exact fp32 (FFMA) so
+// greedy sequences can match the oracle.
+#include <string.h>
+
+#include "wn_common.h"
+
+struct GenLayerOff {
+  int64_t wa, ba, wb, bb, ring;  // offsets (floats) into the state buffer
+  int G, dilation, ring_len;
+};
+
+struct GenLayout {
+  int n = 0, Q = 0, R = 0, S = 0, k = 0, kc = 0, n_causal = 0, n_head = 0, L = 0;
+  int causal_ch[WN_MAX_CAUSAL];
+  int head_ch[WN_MAX_HEAD];
+  int64_t emb = 0, emb_b = 0;
+  int64_t cw[WN_MAX_CAUSAL], cb[WN_MAX_CAUSAL], chist[WN_MAX_CAUSAL];  // causal layers >= 1
+  int64_t hw[WN_MAX_HEAD], hb[WN_MAX_HEAD];
+  int64_t idx_hist = 0;     // int32 [n][kc-1]
+  int64_t cur_logits = 0;   // [n][Q]
+  int64_t layers_dev = 0;   // GenLayerOff[L] copied to device (as raw bytes)
+  int64_t total = 0;
+  int maxw = 0;             // widest vector anywhere (for smem sizing)
+};
+
+struct wn_gen {
+  wn_handle* h = nullptr;
+  int head_act = 1;
+  GenLayout lay;
+  std::vector<GenLayerOff> layers;
+  float* state = nullptr;
+  int64_t state_bytes = 0;
+  bool primed = false;
+  int64_t t = 0;         // absolute time of the next sample
+  int64_t steps_done = 0;  // incremental steps since priming (head_act==1: ELU once > 0 ... always for steps)
+};
+
+namespace {
+
+constexpr int GT = 256;  // threads per CTA
+
+inline int64_t align_up64(int64_t v) { return (v + 63) / 64 * 64; }
+
+// dst[(tap*C + c)*ldn + noff + o] = W[o][c][tap]
+__global__ void gen_transpose_conv(const float* __restrict__ W, float* __restrict__ dst, int O, int C, int taps, int ldn,
+                                   int noff) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= O * C * taps) return;
+  const int o = i % O, c = (i / O) % C, tap = i / (O * C);
+  dst[((int64_t)tap * C + c) * ldn + noff + o] = W[((int64_t)o * C + c) * taps + tap];
+}
+
+__global__ void gen_copy_bias(const float* __restrict__ b, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = b ? b[i] : 0.f;
+}
+
+// ring[stream][slot][c] <- x[stream][tau][c] for the last ring_len window positions, slot = tau mod ring_len
+__global__ void gen_fill_ring(const float* __restrict__ x, float* __restrict__ ring, int n, int Win, int C, int len,
+                              int linear) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n * len * C) return;
+  const int c = (int)(i % C);
+  const int j = (int)((i / C) % len);
+  const int sidx = (int)(i / ((int64_t)C * len));
+  const int tau = Win - len + j;
+  const float v = tau >= 0 ? x[((int64_t)sidx * Win + tau) * C + c] : 0.f;
+  const int slot = linear ? j : ((tau % len) + len) % len;   // linear: oldest first
+  ring[((int64_t)sidx * len + slot) * C + c] = v;
+}
+
+__global__ void gen_fill_idx_hist(const int32_t* __restrict__ window, int32_t* __restrict__ hist, int n, int Win,
+                                  int kc1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * kc1) return;
+  const int sidx = i / kc1, j = i % kc1;
+  const int tau = Win - kc1 + j;
+  hist[i] = tau >= 0 ? window[(int64_t)sidx * Win + tau] : -1;
+}
+
+struct GenArgs {
+  float* state;
+  GenLayout lay;
+  const GenLayerOff* layers;
+  int n_steps;
+  int mode;            // WN_GEN_GREEDY / WN_GEN_SAMPLE
+  int sample_first;    // 1: draw each step's input from cur_logits (run); 0: inputs forced (step API)
+  const int32_t* forced;  // [n] when !sample_first
+  uint64_t seed;
+  int64_t t0;          // absolute time of the first processed sample
+  int head_elu;        // ELU head (reference incremental steps) vs ReLU
+  int32_t* out;        // [n][n_steps] or null
+  float* probs;        // [n][Q] or null (written after the last step)
+  int apply_softmax;
+};
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__device__ __forceinline__ float gumbel(uint64_t seed, uint64_t stream, uint64_t t, uint32_t q) {
+  const uint64_t h = splitmix64(seed ^ splitmix64(stream * 0x100000001B3ull + t) ^ ((uint64_t)q << 32 | q));
+  const float u = ((float)(h >> 40) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+  return -logf(-logf(u));
+}
+
+// out[s][o] (+)= sum_kk Wt[kk][o] * xin[s][kk]; all GT threads cooperate; K split across
+// thread groups when N is small.  part: smem scratch of >= GT*NS floats.
+template <int NS>
+__device__ __forceinline__ void matvec(const float* __restrict__ Wt, int K, int N, const float* xin, int ldx,
+                                       float* part, float* out, int ldo, const float* __restrict__ bias,
+                                       const float* addin, int lda) {
+  const int tid = threadIdx.x;
+  if (N <= GT) {
+    const int ksplit = GT / N;  // >= 1
+    const int Kc = (K + ksplit - 1) / ksplit;
+    const int ks = tid / N, o = tid - ks * N;
+    float acc[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) acc[s] = 0.f;
+    if (ks < ksplit) {
+      const int kb = ks * Kc, ke = min(K, kb + Kc);
+      const float* wp = Wt + (int64_t)kb * N + o;
+#pragma unroll 8
+      for (int kk = kb; kk < ke; ++kk) {
+        const float w = __ldg(wp);
+        wp += N;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) acc[s] = fmaf(w, xin[s * ldx + kk], acc[s]);
+      }
+#pragma unroll
+      for (int s = 0; s < NS; ++s) part[(ks * NS + s) * N + o] = acc[s];
+    }
+    __syncthreads();
+    for (int i = tid; i < NS * N; i += GT) {
+      const int s = i / N, oo = i - s * N;
+      float v = bias ? bias[oo] : 0.f;
+      for (int q = 0; q < ksplit; ++q) v += part[(q * NS + s) * N + oo];
+      if (addin) v += addin[s * lda + oo];
+      out[s * ldo + oo] = v;
+    }
+    __syncthreads();
+  } else {
+    for (int o = tid; o < N; o += GT) {
+      float acc[NS];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) acc[s] = 0.f;
+      const float* wp = Wt + o;
+#pragma unroll 8
+      for (int kk = 0; kk < K; ++kk) {
+        const float w = __ldg(wp);
+        wp += N;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) acc[s] = fmaf(w, xin[s * ldx + kk], acc[s]);
+      }
+      const float b = bias ? bias[o] : 0.f;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) out[s * ldo + o] = acc[s] + b + (addin ? addin[s * lda + o] : 0.f);
+    }
+    __syncthreads();
+  }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(GT) gen_kernel(GenArgs a) {
+  extern __shared__ float sm[];
+  const GenLayout& L = a.lay;
+  const int tid = threadIdx.x;
+  const int s0 = blockIdx.x * NS;  // first stream of this CTA
+  const int maxw = L.maxw;
+  // smem carve-up
+  float* xv = sm;                       // [NS][maxw] current trunk vector
+  float* xin = xv + NS * maxw;          // [NS][k*maxw] conv input (past taps | current)
+  float* av = xin + NS * L.k * maxw + NS * L.kc * maxw;  // [NS][2*maxw] pre-activations / z
+  float* zv = av + NS * 2 * maxw;       // [NS][maxw]
+  float* skipv = zv + NS * maxw;        // [NS][maxw] skip accumulator / head ping
+  float* hv = skipv + NS * maxw;        // [NS][maxw] head pong
+  float* part = hv + NS * maxw;         // [GT*NS] + spare
+  __shared__ int s_sample[NS];
+  __shared__ float s_redv[GT / 32];
+  __shared__ int s_redi[GT / 32];
+
+  float* st = a.state;
+  int32_t* idx_hist = (int32_t*)(st + L.idx_hist);
+  float* cur_logits = st + L.cur_logits;
+  const int kc1 = L.kc - 1;
+
+  for (int step = 0; step < a.n_steps; ++step) {
+    const int64_t t = a.t0 + step;
+    // ---- 1. choose this step's input sample --------------------------------------
+    for (int s = 0; s < NS; ++s) {
+      const int stream = s0 + s;
+      if (stream >= L.n) {
+        if (tid == 0) s_sample[s] = 0;
+        continue;
+      }
+      if (!a.sample_first) {
+        if (tid == 0) s_sample[s] = a.forced[stream];
+        continue;
+      }
+      // argmax over Q of logits (+ Gumbel noise when sampling); ties -> lowest index (np.argmax)
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int q = tid; q < L.Q; q += GT) {
+        float v = cur_logits[(int64_t)stream * L.Q + q];
+        if (a.mode == WN_GEN_SAMPLE) v += gumbel(a.seed, (uint64_t)stream, (uint64_t)t, (uint32_t)q);
+        if (v > bv || (v == bv && q < bi)) {
+          bv = v;
+          bi = q;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) {
+          bv = ov;
+          bi = oi;
+        }
+      }
+      if ((tid & 31) == 0) {
+        s_redv[tid >> 5] = bv;
+        s_redi[tid >> 5] = bi;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        for (int w = 1; w < GT / 32; ++w)
+          if (s_redv[w] > bv || (s_redv[w] == bv && s_redi[w] < bi)) {
+            bv = s_redv[w];
+            bi = s_redi[w];
+          }
+        s_sample[s] = bi;
+        if (a.out) a.out[(int64_t)stream * a.n_steps + step] = bi;
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+
+    // ---- 2. causal stack (wavenet.py:281-286 on one-hot taps == table gather) -----
+    {
+      const int R0 = L.causal_ch[0];
+      const float* emb = st + L.emb;
+      const float* eb = st + L.emb_b;
+      for (int i = tid; i < NS * R0; i += GT) {
+        const int s = i / R0, r = i - s * R0;
+        const int stream = s0 + s;
+        float v = eb[r];
+        if (stream < L.n) {
+          for (int j = 0; j < L.kc; ++j) {
+            const int q = j == kc1 ? s_sample[s] : idx_hist[(int64_t)stream * kc1 + j];
+            if (q >= 0) v += emb[((int64_t)j * L.Q + q) * R0 + r];
+          }
+        }
+        xv[s * maxw + r] = v;
+      }
+      __syncthreads();
+      if (kc1 > 0)
+        for (int i = tid; i < NS; i += GT) {
+          const int stream = s0 + i;
+          if (stream < L.n) {
+            for (int j = 0; j + 1 < kc1; ++j) idx_hist[(int64_t)stream * kc1 + j] = idx_hist[(int64_t)stream * kc1 + j + 1];
+            idx_hist[(int64_t)stream * kc1 + kc1 - 1] = s_sample[i];
+          }
+        }
+      for (int ci = 1; ci < L.n_causal; ++ci) {
+        const int Cin = L.causal_ch[ci - 1], Cout = L.causal_ch[ci];
+        float* hist = st + L.chist[ci];  // [n][kc-1][Cin], oldest first
+        float* cin = xin;                // [NS][kc*Cin]
+        for (int i = tid; i < NS * L.kc * Cin; i += GT) {
+          const int s = i / (L.kc * Cin), rem = i - s * L.kc * Cin;
+          const int j = rem / Cin, c = rem - j * Cin;
+          const int stream = s0 + s;
+          float v = 0.f;
+          if (stream < L.n) v = j == kc1 ? xv[s * maxw + c] : hist[((int64_t)stream * kc1 + j) * Cin + c];
+          cin[s * (L.kc * maxw) + j * Cin + c] = v;
+        }
+        __syncthreads();
+        for (int i = tid; i < NS * kc1 * Cin; i += GT) {  // slide history
+          const int s = i / (kc1 * Cin), rem = i - s * kc1 * Cin;
+          const int stream = s0 + s;
+          if (stream < L.n) hist[(int64_t)stream * kc1 * Cin + rem] = cin[s * (L.kc * maxw) + Cin + rem];
+        }
+        matvec<NS>(st + L.cw[ci], L.kc * Cin, Cout, cin, L.kc * maxw, part, xv, maxw, st + L.cb[ci], nullptr, 0);
+      }
+    }
+
+    // ---- 3. residual layers (ResidualConvLayer._forward, wavenet.py:350-356) -------
+    const int R = L.R;
+    for (int i = tid; i < NS * L.S; i += GT) skipv[(i / L.S) * maxw + (i % L.S)] = 0.f;
+    for (int l = 0; l < L.L; ++l) {
+      const GenLayerOff ly = a.layers[l];
+      const int len = ly.ring_len;
+      float* ring = st + ly.ring;  // [n][len][R]
+      const int kR = L.k * R;
+      // gather taps: xin[s][tap*R + c], tap k-1 = current sample (wavenet.py:288-290)
+      for (int i = tid; i < NS * kR; i += GT) {
+        const int s = i / kR, rem = i - s * kR;
+        const int tap = rem / R, c = rem - tap * R;
+        const int stream = s0 + s;
+        float v = 0.f;
+        if (stream < L.n) {
+          if (tap == L.k - 1) {
+            v = xv[s * maxw + c];
+          } else {
+            const int64_t tau = t - (int64_t)(L.k - 1 - tap) * ly.dilation;
+            const int slot = (int)(((tau % len) + len) % len);
+            v = ring[((int64_t)stream * len + slot) * R + c];
+          }
+        }
+        xin[s * (L.k * maxw) + rem] = v;
+      }
+      __syncthreads();
+      if (len > 0)
+        for (int i = tid; i < NS * R; i += GT) {  // push x[t] into the ring (roll, faster_wavenet.py:90-91)
+          const int s = i / R, c = i - s * R;
+          const int stream = s0 + s;
+          if (stream < L.n) ring[((int64_t)stream * len + (int)(t % len)) * R + c] = xv[s * maxw + c];
+        }
+      const int G = ly.G;
+      matvec<NS>(st + ly.wa, kR, 2 * G, xin, L.k * maxw, part, av, 2 * maxw, st + ly.ba, nullptr, 0);
+      for (int i = tid; i < NS * G; i += GT) {  // z = tanh(a_f) * sigmoid(a_g), wavenet.py:351
+        const int s = i / G, g = i - s * G;
+        const float f = av[s * 2 * maxw + g], gg = av[s * 2 * maxw + G + g];
+        zv[s * maxw + g] = tanhf(f) * (1.f / (1.f + expf(-gg)));
+      }
+      __syncthreads();
+      // [x_next | skip] = WB^T z + b (+ x | + skip_acc)
+      // proj and skip share one [G][R+S] matrix; addin differs, so run them as two calls on column ranges
+      matvec<NS>(st + ly.wb, G, R + L.S, zv, maxw, part, av, 2 * maxw, st + ly.bb, nullptr, 0);
+      for (int i = tid; i < NS * (R + L.S); i += GT) {
+        const int s = i / (R + L.S), o = i - s * (R + L.S);
+        const float v = av[s * 2 * maxw + o];
+        if (o < R)
+          xv[s * maxw + o] += v;                 // output = projection_block + x, wavenet.py:354
+        else
+          skipv[s * maxw + (o - R)] += v;        // sum_skip_connections += z, faster_wavenet.py:100
+      }
+      __syncthreads();
+    }
+
+    // ---- 4. head (faster_wavenet.py:105-113: ELU; wavenet.py:584-593: ReLU) --------
+    float* hin = skipv;
+    float* hout = hv;
+    for (int hi = 0; hi < L.n_head; ++hi) {
+      const int Cin = L.head_ch[hi], Cout = L.head_ch[hi + 1];
+      for (int i = tid; i < NS * Cin; i += GT) {
+        const int s = i / Cin, c = i - s * Cin;
+        const float v = hin[s * maxw + c];
+        hin[s * maxw + c] = a.head_elu ? (v > 0.f ? v : expm1f(v)) : fmaxf(v, 0.f);
+      }
+      __syncthreads();
+      matvec<NS>(st + L.hw[hi], Cin, Cout, hin, maxw, part, hout, maxw, st + L.hb[hi], nullptr, 0);
+      float* tmp = hin;
+      hin = hout;
+      hout = tmp;
+    }
+    // hin now holds the logits for the next sample
+    for (int i = tid; i < NS * L.Q; i += GT) {
+      const int s = i / L.Q, q = i - s * L.Q;
+      const int stream = s0 + s;
+      if (stream < L.n) cur_logits[(int64_t)stream * L.Q + q] = hin[s * maxw + q];
+    }
+    __syncthreads();
+  }
+
+  if (a.probs) {
+    for (int s = 0; s < NS; ++s) {
+      const int stream = s0 + s;
+      if (stream >= L.n) continue;
+      const float* lg = cur_logits + (int64_t)stream * L.Q;
+      if (!a.apply_softmax) {
+        for (int q = tid; q < L.Q; q += GT) a.probs[(int64_t)stream * L.Q + q] = lg[q];
+        continue;
+      }
+      float m = -INFINITY;
+      for (int q = tid; q < L.Q; q += GT) m = fmaxf(m, lg[q]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if ((tid & 31) == 0) s_redv[tid >> 5] = m;
+      __syncthreads();
+      m = s_redv[0];
+      for (int w = 1; w < GT / 32; ++w) m = fmaxf(m, s_redv[w]);
+      __syncthreads();
+      float sum = 0.f;
+      for (int q = tid; q < L.Q; q += GT) sum += expf(lg[q] - m);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if ((tid & 31) == 0) s_redv[tid >> 5] = sum;
+      __syncthreads();
+      sum = 0.f;
+      for (int w = 0; w < GT / 32; ++w) sum += s_redv[w];
+      __syncthreads();
+      for (int q = tid; q < L.Q; q += GT) a.probs[(int64_t)stream * L.Q + q] = expf(lg[q] - m) / sum;
+    }
+  }
+}
+
+size_t gen_smem_bytes(const GenLayout& L, int NS) {
+  const size_t maxw = L.maxw;
+  size_t f = NS * maxw                               // xv
+             + NS * (L.k + L.kc) * maxw              // xin
+             + NS * 2 * maxw                         // av
+             + NS * maxw * 3                         // zv, skipv, hv
+             + (size_t)GT * NS + 64;                 // part
+  return f * sizeof(float);
+}
+
+template <int NS>
+int launch_gen(const GenArgs& a, cudaStream_t s) {
+  const size_t smem = gen_smem_bytes(a.lay, NS);
+  WN_REQUIRE(smem <= 227 * 1024, WN_EINVAL, "generator: network too wide for shared memory (%zu bytes)", smem);
+  WN_CHECK_CUDA(cudaFuncSetAttribute(gen_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (a.lay.n + NS - 1) / NS;
+  gen_kernel<NS><<<grid, GT, smem, s>>>(a);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+int pick_ns(const wn_gen* g) {
+  // streams per CTA: spread over the SMs first, then stack streams to amortise weight reads
+  const int n = g->lay.n, sms = g->h->sm_count;
+  if (n <= sms) return 1;
+  if (n <= 2 * sms) return 2;
+  return 4;
+}
+
+int run_gen(wn_gen* g, GenArgs& a, cudaStream_t s) {
+  const int ns = pick_ns(g);
+  if (ns == 1) return launch_gen<1>(a, s);
+  if (ns == 2) return launch_gen<2>(a, s);
+  return launch_gen<4>(a, s);
+}
+
+}  // namespace
+
+extern "C" int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen** out) {
+  WN_REQUIRE(h && out, WN_EINVAL, "null argument");
+  WN_REQUIRE(n_streams >= 1, WN_EINVAL, "n_streams must be >= 1");
+  WN_REQUIRE(head_act == 0 || head_act == 1, WN_EINVAL, "head_act must be 0 (relu) or 1 (reference)");
+  wn_gen* g = new wn_gen();
+  g->h = h;
+  g->head_act = head_act;
+  GenLayout& L = g->lay;
+  const wn_config& c = h->cfg;
+  L.n = n_streams;
+  L.Q = h->Q;
+  L.R = h->R;
+  L.S = h->S;
+  L.k = c.residual_filter_width;
+  L.kc = c.causal_filter_width;
+  L.n_causal = c.n_causal;
+  L.n_head = (int)h->head.size();
+  L.L = (int)h->layers.size();
+  int maxw = h->Q > h->S ? h->Q : h->S;
+  for (int i = 0; i < c.n_causal; ++i) {
+    L.causal_ch[i] = c.causal_channels[i];
+    maxw = maxw > c.causal_channels[i] ? maxw : c.causal_channels[i];
+  }
+  for (int i = 0; i < c.n_softmax; ++i) {
+    L.head_ch[i] = c.softmax_channels[i];
+    maxw = maxw > c.softmax_channels[i] ? maxw : c.softmax_channels[i];
+  }
+  int64_t off = 0;
+  auto take = [&](int64_t nfl) {
+    int64_t o = off;
+    off = align_up64(off + nfl);
+    return o;
+  };
+  L.emb = take((int64_t)L.kc * L.Q * L.causal_ch[0]);
+  L.emb_b = take(L.causal_ch[0]);
+  for (int i = 1; i < c.n_causal; ++i) {
+    L.cw[i] = take((int64_t)L.kc * L.causal_ch[i - 1] * L.causal_ch[i]);
+    L.cb[i] = take(L.causal_ch[i]);
+    L.chist[i] = take((int64_t)n_streams * (L.kc - 1) * L.causal_ch[i - 1] + 1);
+  }
+  for (int l = 0; l < L.L; ++l) {
+    const ResLayer& ly = h->layers[l];
+    GenLayerOff o;
+    o.G = ly.G;
+    o.dilation = ly.dilation;
+    o.ring_len = (L.k - 1) * ly.dilation;
+    o.wa = take((int64_t)L.k * L.R * 2 * ly.G);
+    o.ba = take(2 * ly.G);
+    o.wb = take((int64_t)ly.G * (L.R + L.S));
+    o.bb = take(L.R + L.S);
+    o.ring = take((int64_t)n_streams * o.ring_len * L.R + 1);
+    g->layers.push_back(o);
+    maxw = maxw > 2 * ly.G ? maxw : 2 * ly.G;
+    maxw = maxw > L.R + L.S ? maxw : L.R + L.S;
+  }
+  for (int i = 0; i < L.n_head; ++i) {
+    L.hw[i] = take((int64_t)L.head_ch[i] * L.head_ch[i + 1]);
+    L.hb[i] = take(L.head_ch[i + 1]);
+  }
+  L.idx_hist = take((int64_t)n_streams * (L.kc - 1) + 1);
+  L.cur_logits = take((int64_t)n_streams * L.Q);
+  L.layers_dev = take((int64_t)(sizeof(GenLayerOff) * L.L + 3) / 4);
+  L.maxw = (maxw + 3) / 4 * 4;
+  L.total = off;
+  *out = g;
+  return WN_OK;
+}
+
+extern "C" int wn_gen_destroy(wn_gen* g) {
+  delete g;
+  return WN_OK;
+}
+
+extern "C" int64_t wn_gen_state_bytes(const wn_gen* g) { return g ? g->lay.total * (int64_t)sizeof(float) : WN_EINVAL; }
+
+extern "C" int wn_gen_bind_state(wn_gen* g, void* state, int64_t bytes) {
+  WN_REQUIRE(g && state, WN_EINVAL, "null argument");
+  WN_REQUIRE(bytes >= g->lay.total * (int64_t)sizeof(float), WN_ENOMEM, "generator state too small");
+  WN_REQUIRE(((uintptr_t)state & 255) == 0, WN_EINVAL, "generator state must be 256-byte aligned");
+  g->state = (float*)state;
+  g->state_bytes = bytes;
+  g->primed = false;
+  return WN_OK;
+}
+
+extern "C" int wn_gen_prime(wn_gen* g, const float* params, const int32_t* window, float* probs_opt, wn_stream_t st) {
+  WN_REQUIRE(g && params && window, WN_EINVAL, "null argument");
+  WN_REQUIRE(g->state, WN_ESTATE, "no generator state bound");
+  wn_handle* h = g->h;
+  const GenLayout& L = g->lay;
+  const int Win = wn_input_width(h);
+  WN_REQUIRE(h->ws && h->tape.B == L.n && h->tape.W == Win, WN_ESTATE,
+             "wn_gen_prime: bind a training workspace for (B=%d, W=%d) first", L.n, Win);
+  cudaStream_t s = (cudaStream_t)st;
+  // full pass over the window (faster_wavenet.py:13-47); the priming head is ReLU (Q2)
+  WN_TRY(wn_forward_causal_block(h, params, window, nullptr, st));
+  WN_TRY(wn_forward_residual_block(h, params, nullptr, nullptr, nullptr, st));
+  WN_TRY(wn_forward_softmax_block(h, params, nullptr, 1, 1, probs_opt, st));
+  float* S = g->state;
+  const Tape& t = h->tape;
+  WN_CHECK_CUDA(cudaMemcpyAsync(S + L.cur_logits, h->ws + t.hbuf.back(), sizeof(float) * L.n * L.Q,
+                                cudaMemcpyDeviceToDevice, s));
+  auto nb = [](int64_t n) { return (unsigned)((n + 255) / 256); };
+  // generator-layout weights
+  const wn_config& c = h->cfg;
+  WN_CHECK_CUDA(cudaMemcpyAsync(S + L.emb, h->ws + t.emb, sizeof(float) * L.kc * L.Q * L.causal_ch[0],
+                                cudaMemcpyDeviceToDevice, s));
+  gen_copy_bias<<<nb(L.causal_ch[0]), 256, 0, s>>>(h->causal[0].b_off >= 0 ? params + h->causal[0].b_off : nullptr,
+                                                   S + L.emb_b, L.causal_ch[0]);
+  for (int i = 1; i < c.n_causal; ++i) {
+    const ConvParam& cp = h->causal[i];
+    gen_transpose_conv<<<nb((int64_t)cp.out_ch * cp.in_ch * cp.taps), 256, 0, s>>>(params + cp.w_off, S + L.cw[i],
+                                                                                    cp.out_ch, cp.in_ch, cp.taps,
+                                                                                    cp.out_ch, 0);
+    gen_copy_bias<<<nb(cp.out_ch), 256, 0, s>>>(cp.b_off >= 0 ? params + cp.b_off : nullptr, S + L.cb[i], cp.out_ch);
+    if (L.kc > 1)
+      gen_fill_ring<<<nb((int64_t)L.n * (L.kc - 1) * cp.in_ch), 256, 0, s>>>(h->ws + t.cx[i - 1], S + L.chist[i], L.n,
+                                                                              Win, cp.in_ch, L.kc - 1, 1);
+  }
+  for (int l = 0; l < L.L; ++l) {
+    const ResLayer& ly = h->layers[l];
+    const GenLayerOff& o = g->layers[l];
+    const int64_t nw = (int64_t)ly.G * L.R * L.k;
+    gen_transpose_conv<<<nb(nw), 256, 0, s>>>(params + ly.wf.w_off, S + o.wa, ly.G, L.R, L.k, 2 * ly.G, 0);
+    gen_transpose_conv<<<nb(nw), 256, 0, s>>>(params + ly.wg.w_off, S + o.wa, ly.G, L.R, L.k, 2 * ly.G, ly.G);
+    gen_copy_bias<<<nb(ly.G), 256, 0, s>>>(ly.wf.b_off >= 0 ? params + ly.wf.b_off : nullptr, S + o.ba, ly.G);
+    gen_copy_bias<<<nb(ly.G), 256, 0, s>>>(ly.wg.b_off >= 0 ? params + ly.wg.b_off : nullptr, S + o.ba + ly.G, ly.G);
+    gen_transpose_conv<<<nb((int64_t)L.R * ly.G), 256, 0, s>>>(params + ly.proj.w_off, S + o.wb, L.R, ly.G, 1,
+                                                                L.R + L.S, 0);
+    gen_transpose_conv<<<nb((int64_t)L.S * ly.G), 256, 0, s>>>(params + ly.skip.w_off, S + o.wb, L.S, ly.G, 1,
+                                                                L.R + L.S, L.R);
+    gen_copy_bias<<<nb(L.R), 256, 0, s>>>(ly.proj.b_off >= 0 ? params + ly.proj.b_off : nullptr, S + o.bb, L.R);
+    gen_copy_bias<<<nb(L.S), 256, 0, s>>>(ly.skip.b_off >= 0 ? params + ly.skip.b_off : nullptr, S + o.bb + L.R, L.S);
+    if (o.ring_len > 0)
+      gen_fill_ring<<<nb((int64_t)L.n * o.ring_len * L.R), 256, 0, s>>>(h->ws + t.x[l], S + o.ring, L.n, Win, L.R,
+                                                                         o.ring_len, 0);
+  }
+  for (int i = 0; i < L.n_head; ++i) {
+    const ConvParam& cp = h->head[i];
+    gen_transpose_conv<<<nb((int64_t)cp.out_ch * cp.in_ch), 256, 0, s>>>(params + cp.w_off, S + L.hw[i], cp.out_ch,
+                                                                          cp.in_ch, 1, cp.out_ch, 0);
+    gen_copy_bias<<<nb(cp.out_ch), 256, 0, s>>>(cp.b_off >= 0 ? params + cp.b_off : nullptr, S + L.hb[i], cp.out_ch);
+  }
+  if (L.kc > 1)
+    gen_fill_idx_hist<<<nb((int64_t)L.n * (L.kc - 1)), 256, 0, s>>>(window, (int32_t*)(S + L.idx_hist), L.n, Win,
+                                                                    L.kc - 1);
+  WN_CHECK_LAUNCH();
+  WN_CHECK_CUDA(cudaMemcpyAsync(S + L.layers_dev, g->layers.data(), sizeof(GenLayerOff) * L.L, cudaMemcpyHostToDevice,
+                                s));
+  g->primed = true;
+  g->t = Win;
+  g->steps_done = 0;
+  return WN_OK;
+}
+
+static void fill_args(wn_gen* g, GenArgs* a) {
+  memset(a, 0, sizeof(*a));
+  a->state = g->state;
+  a->lay = g->lay;
+  a->layers = (const GenLayerOff*)(g->state + g->lay.layers_dev);
+  a->t0 = g->t;
+  a->head_elu = g->head_act == 1;
+}
+
+extern "C" int wn_gen_step(wn_gen* g, const float* params, const int32_t* x_new, int apply_softmax, float* probs,
+                           wn_stream_t st) {
+  (void)params;
+  WN_REQUIRE(g && x_new, WN_EINVAL, "null argument");
+  WN_REQUIRE(g->primed, WN_ESTATE, "wn_gen_step: call wn_gen_prime first");
+  GenArgs a;
+  fill_args(g, &a);
+  a.n_steps = 1;
+  a.sample_first = 0;
+  a.forced = x_new;
+  a.probs = probs;
+  a.apply_softmax = apply_softmax;
+  WN_TRY(run_gen(g, a, (cudaStream_t)st));
+  g->t += 1;
+  g->steps_done += 1;
+  return WN_OK;
+}
+
+extern "C" int wn_gen_run(wn_gen* g, const float* params, int n_steps, int mode, uint64_t seed, int32_t* out,
+                          wn_stream_t st) {
+  (void)params;
+  WN_REQUIRE(g && out, WN_EINVAL, "null argument");
+  WN_REQUIRE(g->primed, WN_ESTATE, "wn_gen_run: call wn_gen_prime first");
+  WN_REQUIRE(n_steps >= 1, WN_EINVAL, "n_steps must be >= 1");
+  WN_REQUIRE(mode == WN_GEN_GREEDY || mode == WN_GEN_SAMPLE, WN_EINVAL, "unknown sampling mode");
+  GenArgs a;
+  fill_args(g, &a);
+  a.n_steps = n_steps;
+  a.mode = mode;
+  a.sample_first = 1;
+  a.seed = seed;
+  a.out = out;
+  WN_TRY(run_gen(g, a, (cudaStream_t)st));
+  g->t += n_steps;
+  g->steps_done += n_steps;
+  return WN_OK;
+}
+
+// ---- data.py on device -------------------------------------------------------------
+namespace {
+__global__ void mulaw_encode_kernel(const double* __restrict__ sig, int64_t n, int Q, int32_t* __restrict__ q) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double mu = (double)(Q - 1);
+  const double x = sig[i];
+  const double sgn = x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : 0.0);
+  const double y = sgn * log(1.0 + mu * fabs(x)) / log(1.0 + mu);   // data.py:20
+  double c = y * 0.5 + 0.5;
+  c = c < 0.0 ? 0.0 : (c > 1.0 ? 1.0 : c);
+  q[i] = (int32_t)(c * mu);                                            // truncation, data.py:23
+}
+__global__ void mulaw_decode_kernel(const int32_t* __restrict__ q, int64_t n, int Q, double scale,
+                                    double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double nrm = ((double)q[i] / (double)Q - 0.5) * 2.0;           // data.py:39
+  const double mu = (double)(Q - 1);
+  const double sgn = nrm > 0.0 ? 1.0 : (nrm < 0.0 ? -1.0 : 0.0);
+  out[i] = sgn * pow(1.0 + mu, fabs(nrm)) / mu * scale;               // data.py:43,54
+}
+}  // namespace
+
+extern "C" int wn_mulaw_encode(const double* signal, int64_t n, int quantization_steps, int32_t* q, wn_stream_t s) {
+  WN_REQUIRE(signal && q && n >= 0, WN_EINVAL, "bad argument");
+  if (n == 0) return WN_OK;
+  mulaw_encode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)s>>>(signal, n, quantization_steps, q);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+extern "C" int wn_mulaw_decode(const int32_t* q, int64_t n, int quantization_steps, double scale, double* out,
+                               wn_stream_t s) {
+  WN_REQUIRE(q && out && n >= 0, WN_EINVAL, "bad argument");
+  if (n == 0) return WN_OK;
+  mulaw_decode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)s>>>(q, n, quantization_steps, scale, out);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
