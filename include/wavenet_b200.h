@@ -91,6 +91,8 @@ int wn_create(const wn_config* cfg, wn_handle** out);
 int wn_destroy(wn_handle* h);
 int wn_set_precision(wn_handle* h, int prec);
 int wn_get_precision(const wn_handle* h);
+/* 1 when the residual stack of this network runs on the tcgen05 path under the current precision */
+int wn_tc_active(const wn_handle* h);
 
 /* Flat parameter layout (replaces chain.add_link registration, wavenet.py:461-472). */
 int64_t wn_flat_size(const wn_handle* h);      /* floats, including alignment padding */

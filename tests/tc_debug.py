@@ -1,0 +1,34 @@
+"""Manual diagnostic (not a pytest): TF32 tensor-core path vs the exact-fp32 SIMT path, stage by stage."""
+import sys, os
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import wavenet_oracle as O
+from tests.util import make_cfg, make_net
+
+name = sys.argv[1] if len(sys.argv) > 1 else "C_small"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+W = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
+cfg = make_cfg(name)
+w = O.init_weights(cfg, np.random.default_rng(1234), np.float64)
+x = np.random.default_rng(0).integers(0, 256, (B, W)).astype(np.int32)
+res = {}
+for prec in ("fp32", "tf32"):
+    net = make_net(cfg, w)
+    net.set_precision(prec)
+    print(prec, "tc_active =", net._libh.wn_tc_active(net._h), flush=True)
+    c = net.forward_causal_block(x)
+    out, skip = net.forward_residual_block(c)
+    torch.cuda.synchronize()
+    print(prec, "residual done", flush=True)
+    logits = net.forward_softmax_block(skip, apply_softmax=False)
+    torch.cuda.synchronize()
+    res[prec] = (out.data.cpu().numpy(), skip.data.cpu().numpy(), logits.data.cpu().numpy())
+for i, nm in enumerate(("out", "skip", "logits")):
+    a, b = res["fp32"][i], res["tf32"][i]
+    err = np.abs(a - b)
+    print("%-7s max|fp32| %.3e  max err %.3e  mean err %.3e  worst t=%d" % (nm, np.abs(a).max(), err.max(), err.mean(),
+          int(np.unravel_index(err.argmax(), err.shape)[3])))
+    # error profile along time (first 8 blocks of 128)
+    prof = [err[..., k * 128:(k + 1) * 128].max() for k in range(min(8, (W + 127) // 128))]
+    print("        per-128 max err:", " ".join("%.1e" % p for p in prof))

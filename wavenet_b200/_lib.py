@@ -57,6 +57,7 @@ SIGNATURES = {
     "wn_destroy": (_I, [_P]),
     "wn_set_precision": (_I, [_P, _I]),
     "wn_get_precision": (_I, [_P]),
+    "wn_tc_active": (_I, [_P]),
     "wn_flat_size": (_L, [_P]),
     "wn_param_elems": (_L, [_P]),
     "wn_num_params": (_I, [_P]),

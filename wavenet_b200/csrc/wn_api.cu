@@ -216,6 +216,17 @@ static void plan_tape(const wn_handle* h, int B, int W, Tape* t) {
     t->dcx[1] = take(P * cmax);
   }
   t->loss_acc = take(16);
+  {
+    int gm = 0;
+    for (int l = 0; l < L; ++l) gm = gm > h->layers[l].G ? gm : h->layers[l].G;
+    const int kk = c.residual_filter_width;
+    t->tc_tab = take((int64_t)L * 8);
+    t->tc_w1 = take((int64_t)L * 2 * gm * kk * h->R);
+    t->tc_w2 = take((int64_t)L * h->R * gm);
+    t->tc_ws = take((int64_t)L * h->S * gm);
+    t->tc_wh.clear();
+    for (int i = 0; i + 1 < c.n_softmax; ++i) t->tc_wh.push_back(take((int64_t)c.softmax_channels[i] * c.softmax_channels[i + 1]));
+  }
   t->total = off;
 }
 
@@ -238,6 +249,7 @@ extern "C" int wn_bind_workspace(wn_handle* h, void* ws, int64_t bytes, int B, i
   h->ws_bytes = bytes;
   h->tape = t;
   h->phase = PH_NONE;
+  h->tc_tab_uploaded = false;
   return WN_OK;
 }
 
@@ -350,10 +362,13 @@ extern "C" int wn_forward_residual_block(wn_handle* h, const float* params, cons
   } else {
     WN_REQUIRE(h->phase >= PH_CAUSAL, WN_ESTATE, "forward_residual_block: no causal output on the tape");
   }
-  if (h->prec == WN_PREC_TF32 && tc_layer_supported(h))
+  if (h->prec == WN_PREC_TF32 && tc_layer_supported(h)) {
     WN_TRY(tc_forward_residual(h, params, s));
-  else
+    h->tape_has_tfsg = false;
+  } else {
     WN_TRY(residual_forward_simt(h, params, s));
+    h->tape_has_tfsg = true;
+  }
   const int L = (int)h->layers.size();
   if (out) WN_CHECK_CUDA(cudaMemcpyAsync(out, WS(t.x[L]), sizeof(float) * t.P * h->R, cudaMemcpyDeviceToDevice, s));
   if (sum_skip)
@@ -380,7 +395,9 @@ extern "C" int wn_forward_softmax_block(wn_handle* h, const float* params, const
   }
   h->T = T;
   const int nh = (int)h->head.size();
-  for (int i = 0; i < nh; ++i) {  // ReLU -> 1x1 conv per head layer (wavenet.py:587-590)
+  const bool tc_head = h->prec == WN_PREC_TF32 && tc_head_supported(h) && h->S % 32 == 0;
+  if (tc_head) WN_TRY(tc_forward_head(h, params, T, h->head_external, s));
+  for (int i = 0; i < nh && !tc_head; ++i) {  // ReLU -> 1x1 conv per head layer (wavenet.py:587-590)
     const ConvParam& cp = h->head[i];
     GemmArgs g = base_gemm(rows, T);
     if (i == 0) {
@@ -566,6 +583,11 @@ extern "C" int wn_backward(wn_handle* h, const float* params, float* grads, wn_s
       wg.dbias = ly.skip.b_off >= 0 ? grads + ly.skip.b_off : nullptr;
       WN_TRY(simt_wgrad(wg, h->sm_count, s));
     }
+    if (!h->tape_has_tfsg) {  // tensor-core forward keeps only x and z: recompute tanh | sigmoid from x[l]
+      WN_TRY(conv_forward(h, params, ly.wf, WS(t.x[l]), h->R, ly.dilation, zp, WS(t.tfsg[l]), 2 * G, s));
+      WN_TRY(conv_forward(h, params, ly.wg, WS(t.x[l]), h->R, ly.dilation, zp, WS(t.tfsg[l]) + G, 2 * G, s));
+      WN_TRY(simt_gate_forward(WS(t.tfsg[l]), WS(t.dafg), P, G, s));   // z recomputed into scratch (dafg)
+    }
     WN_TRY(simt_gate_backward(WS(t.tfsg[l]), WS(t.dz), WS(t.dafg), P, W, G, zp, s));
     float* dnew = WS(t.dout[dt]);
     for (int part = 0; part < 2; ++part) {
@@ -663,6 +685,10 @@ extern "C" int wn_forward_loss(wn_handle* h, const float* params, const int32_t*
   WN_TRY(wn_forward_softmax_block(h, params, nullptr, T, 0, logits_opt, st));
   if (target) WN_TRY(wn_cross_entropy(h, target, loss, st));
   return WN_OK;
+}
+
+extern "C" int wn_tc_active(const wn_handle* h) {
+  return h && h->prec == WN_PREC_TF32 && tc_layer_supported(h) ? 1 : 0;
 }
 
 extern "C" int64_t wn_optim_scratch_bytes(const wn_handle* h) { return h ? 256 : WN_EINVAL; }

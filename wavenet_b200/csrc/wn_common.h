@@ -75,6 +75,9 @@ struct Tape {
   int64_t dafg = 0;                   // [P][2Gmax]
   int64_t dcx[2] = {0, 0};            // [P][max causal width] (only when n_causal > 1)
   int64_t loss_acc = 0;               // 2 doubles
+  // tensor-core path: TF32-rounded, K-major weight copies (rebuilt every forward)
+  int64_t tc_tab = 0, tc_w1 = 0, tc_w2 = 0, tc_ws = 0;
+  std::vector<int64_t> tc_wh;
   int64_t total = 0;
 };
 
@@ -100,6 +103,8 @@ struct wn_handle {
   const int32_t* x_idx = nullptr;  // device pointer given to the causal phase (must stay alive until backward)
   int T = 0;                       // columns seen by head/loss
   int sm_count = 148;
+  bool tc_tab_uploaded = false;
+  bool tape_has_tfsg = false;      // false after a tensor-core forward (backward recomputes the gates)
 };
 
 // ---- SIMT fp32 kernels (wn_simt.cu) ---------------------------------------------
@@ -172,4 +177,6 @@ int optim_clip_adam(float* params, float* grads, float* m, float* v, int64_t n, 
 
 // ---- tcgen05 TF32 kernels (wn_tc.cu) ---------------------------------------------
 bool tc_layer_supported(const wn_handle* h);
+bool tc_head_supported(const wn_handle* h);
 int tc_forward_residual(wn_handle* h, const float* params, cudaStream_t s);
+int tc_forward_head(wn_handle* h, const float* params, int T, bool external, cudaStream_t s);

@@ -538,10 +538,15 @@ extern "C" int wn_gen_prime(wn_gen* g, const float* params, const int32_t* windo
   WN_REQUIRE(h->ws && h->tape.B == L.n && h->tape.W == Win, WN_ESTATE,
              "wn_gen_prime: bind a training workspace for (B=%d, W=%d) first", L.n, Win);
   cudaStream_t s = (cudaStream_t)st;
-  // full pass over the window (faster_wavenet.py:13-47); the priming head is ReLU (Q2)
-  WN_TRY(wn_forward_causal_block(h, params, window, nullptr, st));
-  WN_TRY(wn_forward_residual_block(h, params, nullptr, nullptr, nullptr, st));
-  WN_TRY(wn_forward_softmax_block(h, params, nullptr, 1, 1, probs_opt, st));
+  // full pass over the window (faster_wavenet.py:13-47); the priming head is ReLU (Q2).
+  // Generation is always exact fp32 so greedy sequences match the reference arithmetic.
+  const int saved_prec = h->prec;
+  h->prec = WN_PREC_FP32;
+  int rc = wn_forward_causal_block(h, params, window, nullptr, st);
+  if (rc == WN_OK) rc = wn_forward_residual_block(h, params, nullptr, nullptr, nullptr, st);
+  if (rc == WN_OK) rc = wn_forward_softmax_block(h, params, nullptr, 1, 1, probs_opt, st);
+  h->prec = saved_prec;
+  WN_TRY(rc);
   float* S = g->state;
   const Tape& t = h->tape;
   WN_CHECK_CUDA(cudaMemcpyAsync(S + L.cur_logits, h->ws + t.hbuf.back(), sizeof(float) * L.n * L.Q,
