@@ -282,3 +282,61 @@ def test_mulaw_device_kernels_bit_exact():
     ref = np.sign(n) * (256.0 ** np.abs(n)) / 255.0 * 32768.0
     assert np.allclose(out.cpu().numpy(), ref, rtol=1e-12)
     assert np.array_equal(out.cpu().numpy().astype(np.int16)[1:], D.decode(np.arange(256))[1:, 0])
+
+
+# ---- TF32 tensor-core path (tcgen05) ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name,B,W,T", [("C_small", 2, 1000, 1000), ("C", 2, 4200, 1129), ("C", 1, 3071, 1)])
+def test_tf32_path_matches_oracle(name, B, W, T):
+    """North star: logits within 1e-2 with argmax agreement in the TF32 path.  Argmax must agree wherever
+    the oracle's top-2 margin exceeds 2e-2 (closer calls are below the stated logit tolerance)."""
+    cfg = make_cfg(name)
+    w = O.init_weights(cfg, np.random.default_rng(1234), np.float64)
+    x = np.random.default_rng(0).integers(0, 256, (B, W)).astype(np.int32)
+    tgt = np.random.default_rng(1).integers(0, 256, (B, T)).astype(np.int32)
+    fw = O.forward_loss(cfg, w, x, tgt, train_width=T, dtype=np.float64)
+    g_ref = O.backward(cfg, fw)
+    net = make_net(cfg, w)
+    net.set_precision("tf32")
+    assert net._libh.wn_tc_active(net._h) == 1, "tcgen05 path must be the one that runs"
+    logits, loss = run_train_step(net, x, tgt, T)
+    got = logits.data.detach().cpu().numpy()[:, :, 0, :]
+    ref = fw["logits"]
+    assert np.abs(got - ref).max() < LOGIT_TOL_TF32
+    srt = np.sort(ref, axis=1)
+    margin = srt[:, -1, :] - srt[:, -2, :]
+    agree = got.argmax(axis=1) == ref.argmax(axis=1)
+    assert np.all(agree[margin > 2 * LOGIT_TOL_TF32])
+    assert agree.mean() > 0.98
+    assert abs(float(loss.data) - float(fw["loss"])) < 1e-3
+    # gradients: tensor-core forward + exact-fp32 backward kernels on the TF32 tape
+    net.backward()
+    g = net.get_grads()
+    for k, v in g_ref.items():
+        if np.abs(v).max() == 0:
+            assert np.abs(g[k]).max() == 0, k
+        else:
+            assert rel_err(g[k], v) < 2e-2, (k, rel_err(g[k], v))
+
+
+def test_tf32_full_size_agrees_with_fp32_path():
+    """BASELINE config 2 shape: TF32 and FP32 GPU paths agree on the loss and logits at 32 x 16000."""
+    cfg = make_cfg("C")
+    w = O.init_weights(cfg, np.random.default_rng(1234), np.float32)
+    B, W = 32, 16000
+    x = np.random.default_rng(0).integers(0, 256, (B, W + 1)).astype(np.int32)
+    xd, td = dev(x[:, :W]), dev(x[:, 1:])
+    from wavenet_b200.wavenet import _ptr, _stream
+    from wavenet_b200._lib import check
+    outs = {}
+    for prec in ("fp32", "tf32"):
+        net = make_net(cfg, w)
+        net.set_precision(prec)
+        net._bind(B, W)
+        logits = torch.empty((B, W, 256), dtype=torch.float32, device="cuda")
+        check(net._libh.wn_forward_loss(net._h, _ptr(net._params), _ptr(xd), _ptr(td), W, _ptr(net._loss),
+                                        _ptr(logits), _stream()))
+        outs[prec] = (float(net._loss[0]), logits)
+        del net
+    assert abs(outs["fp32"][0] - outs["tf32"][0]) < 1e-3
+    err = (outs["fp32"][1] - outs["tf32"][1]).abs().max().item()
+    assert err < LOGIT_TOL_TF32, err
