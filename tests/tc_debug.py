@@ -32,3 +32,31 @@ for i, nm in enumerate(("out", "skip", "logits")):
     # error profile along time (first 8 blocks of 128)
     prof = [err[..., k * 128:(k + 1) * 128].max() for k in range(min(8, (W + 127) // 128))]
     print("        per-128 max err:", " ".join("%.1e" % p for p in prof))
+
+# ---- gradients: tensor-core backward vs fp32 SIMT backward vs fp64 oracle ----
+T = W
+tgt = np.random.default_rng(1).integers(0, 256, (B, T)).astype(np.int32)
+fw = O.forward_loss(cfg, w, x, tgt, train_width=T, dtype=np.float64)
+g_ref = O.backward(cfg, fw)
+from tests.util import rel_err
+grads = {}
+for prec in ("fp32", "tf32"):
+    net = make_net(cfg, w)
+    net.set_precision(prec)
+    logits = net.forward_one_step(x, apply_softmax=False)
+    loss = net.cross_entropy(logits, tgt)
+    net.backward()
+    torch.cuda.synchronize()
+    grads[prec] = net.get_grads()
+    print(prec, "loss", float(loss.data), "oracle", float(fw["loss"]))
+worst = []
+for k, v in g_ref.items():
+    if np.abs(v).max() == 0:
+        worst.append((0.0, k, float(np.abs(grads["tf32"][k]).max())))
+        continue
+    worst.append((rel_err(grads["tf32"][k], v), k, rel_err(grads["fp32"][k], v)))
+worst.sort(reverse=True)
+print("worst tf32 grad rel errs (tf32, name, fp32):")
+for e in worst[:12]:
+    print("  %.3e  %-44s %.3e" % e)
+print("median tf32 rel err %.3e" % np.median([e[0] for e in worst]))

@@ -224,8 +224,15 @@ static void plan_tape(const wn_handle* h, int B, int W, Tape* t) {
     t->tc_w1 = take((int64_t)L * 2 * gm * kk * h->R);
     t->tc_w2 = take((int64_t)L * h->R * gm);
     t->tc_ws = take((int64_t)L * h->S * gm);
+    t->tc_w1t = take((int64_t)L * 2 * gm * kk * h->R);
+    t->tc_wpt = take((int64_t)L * h->R * gm);
+    t->tc_wst = take((int64_t)L * h->S * gm);
     t->tc_wh.clear();
-    for (int i = 0; i + 1 < c.n_softmax; ++i) t->tc_wh.push_back(take((int64_t)c.softmax_channels[i] * c.softmax_channels[i + 1]));
+    t->tc_wht.clear();
+    for (int i = 0; i + 1 < c.n_softmax; ++i) {
+      t->tc_wh.push_back(take((int64_t)c.softmax_channels[i] * c.softmax_channels[i + 1]));
+      t->tc_wht.push_back(take((int64_t)c.softmax_channels[i] * c.softmax_channels[i + 1]));
+    }
   }
   t->total = off;
 }
@@ -364,10 +371,12 @@ extern "C" int wn_forward_residual_block(wn_handle* h, const float* params, cons
   }
   if (h->prec == WN_PREC_TF32 && tc_layer_supported(h)) {
     WN_TRY(tc_forward_residual(h, params, s));
-    h->tape_has_tfsg = false;
+    h->tape_has_tfsg = h->save_gates;
+    h->tape_tc = true;
   } else {
     WN_TRY(residual_forward_simt(h, params, s));
     h->tape_has_tfsg = true;
+    h->tape_tc = false;
   }
   const int L = (int)h->layers.size();
   if (out) WN_CHECK_CUDA(cudaMemcpyAsync(out, WS(t.x[L]), sizeof(float) * t.P * h->R, cudaMemcpyDeviceToDevice, s));
@@ -397,6 +406,7 @@ extern "C" int wn_forward_softmax_block(wn_handle* h, const float* params, const
   const int nh = (int)h->head.size();
   const bool tc_head = h->prec == WN_PREC_TF32 && tc_head_supported(h) && h->S % 32 == 0;
   if (tc_head) WN_TRY(tc_forward_head(h, params, T, h->head_external, s));
+  h->head_tc = tc_head;
   for (int i = 0; i < nh && !tc_head; ++i) {  // ReLU -> 1x1 conv per head layer (wavenet.py:587-590)
     const ConvParam& cp = h->head[i];
     GemmArgs g = base_gemm(rows, T);
@@ -453,6 +463,54 @@ static WgradArgs base_wgrad(int64_t M, int rows) {
   return g;
 }
 
+// ---- causal stack (backward of wavenet.py:565-570) ----
+static int causal_backward(wn_handle* h, const float* params, float* grads, const float* dout, cudaStream_t s) {
+  if (!h->causal_from_idx) return WN_OK;
+  const Tape& t = h->tape;
+  const wn_config& c = h->cfg;
+  const int W = t.W;
+  const int64_t P = t.P;
+  const float* dcur = dout;
+  int ct = 0;
+  for (int i = c.n_causal - 1; i >= 1; --i) {
+    const ConvParam& cp = h->causal[i];
+    WgradArgs wg = base_wgrad(P, W);
+    wg.dY = dcur;
+    wg.ldd = cp.out_ch;
+    wg.N = cp.out_ch;
+    wg.A = WS(t.cx[i - 1]);
+    wg.lda = cp.in_ch;
+    wg.K = cp.in_ch;
+    wg.ntaps = cp.taps;
+    for (int j = 0; j < cp.taps; ++j) wg.shift[j] = cp.taps - 1 - j;
+    wg.dW = grads + cp.w_off;
+    wg.sn = (int64_t)cp.in_ch * cp.taps;
+    wg.sk = cp.taps;
+    wg.st = 1;
+    wg.dbias = cp.b_off >= 0 ? grads + cp.b_off : nullptr;
+    WN_TRY(simt_wgrad(wg, h->sm_count, s));
+    GemmArgs g = base_gemm(P, W);
+    g.A = dcur;
+    g.lda = cp.out_ch;
+    g.K = cp.out_ch;
+    g.ntaps = cp.taps;
+    for (int j = 0; j < cp.taps; ++j) g.shift[j] = -(cp.taps - 1 - j);
+    g.Wt = PRM(cp.w_off);
+    g.sn = cp.taps;
+    g.sk = (int64_t)cp.in_ch * cp.taps;
+    g.st = 1;
+    g.N = cp.in_ch;
+    g.Y = WS(t.dcx[ct]);
+    g.ldy = cp.in_ch;
+    WN_TRY(simt_gemm(g, s));
+    dcur = WS(t.dcx[ct]);
+    ct ^= 1;
+  }
+  const ConvParam& c0 = h->causal[0];
+  return simt_embed_backward(dcur, h->x_idx, WS(t.demb), grads + c0.w_off, c0.b_off >= 0 ? grads + c0.b_off : nullptr,
+                             t.B, W, c0.out_ch, h->Q, c.causal_filter_width, s);
+}
+
 extern "C" int wn_backward(wn_handle* h, const float* params, float* grads, wn_stream_t st) {
   WN_REQUIRE(h && params && grads, WN_EINVAL, "null argument");
   WN_REQUIRE(h->phase == PH_LOSS, WN_ESTATE, "backward: run forward and cross_entropy first");
@@ -463,6 +521,11 @@ extern "C" int wn_backward(wn_handle* h, const float* params, float* grads, wn_s
   const int64_t P = t.P, rows = (int64_t)t.B * T;
   const int nh = (int)h->head.size();
   WN_CHECK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * h->flat_size, s));
+  if (h->prec == WN_PREC_TF32 && h->tape_tc && h->head_tc && h->tape_has_tfsg) {
+    WN_TRY(tc_backward(h, params, grads, s));
+    if (h->head_external) return WN_OK;
+    return causal_backward(h, params, grads, h->bwd_dout, s);
+  }
 
   // ---- head (backward of wavenet.py:584-593) ----
   const float* d = WS(t.dlogits);
@@ -633,49 +696,7 @@ extern "C" int wn_backward(wn_handle* h, const float* params, float* grads, wn_s
     dout = dnew;
     dt ^= 1;
   }
-  if (!h->causal_from_idx) return WN_OK;
-
-  // ---- causal stack (backward of wavenet.py:565-570) ----
-  const float* dcur = dout;
-  int ct = 0;
-  for (int i = c.n_causal - 1; i >= 1; --i) {
-    const ConvParam& cp = h->causal[i];
-    WgradArgs wg = base_wgrad(P, W);
-    wg.dY = dcur;
-    wg.ldd = cp.out_ch;
-    wg.N = cp.out_ch;
-    wg.A = WS(t.cx[i - 1]);
-    wg.lda = cp.in_ch;
-    wg.K = cp.in_ch;
-    wg.ntaps = cp.taps;
-    for (int j = 0; j < cp.taps; ++j) wg.shift[j] = cp.taps - 1 - j;
-    wg.dW = grads + cp.w_off;
-    wg.sn = (int64_t)cp.in_ch * cp.taps;
-    wg.sk = cp.taps;
-    wg.st = 1;
-    wg.dbias = cp.b_off >= 0 ? grads + cp.b_off : nullptr;
-    WN_TRY(simt_wgrad(wg, h->sm_count, s));
-    GemmArgs g = base_gemm(P, W);
-    g.A = dcur;
-    g.lda = cp.out_ch;
-    g.K = cp.out_ch;
-    g.ntaps = cp.taps;
-    for (int j = 0; j < cp.taps; ++j) g.shift[j] = -(cp.taps - 1 - j);
-    g.Wt = PRM(cp.w_off);
-    g.sn = cp.taps;
-    g.sk = (int64_t)cp.in_ch * cp.taps;
-    g.st = 1;
-    g.N = cp.in_ch;
-    g.Y = WS(t.dcx[ct]);
-    g.ldy = cp.in_ch;
-    WN_TRY(simt_gemm(g, s));
-    dcur = WS(t.dcx[ct]);
-    ct ^= 1;
-  }
-  const ConvParam& c0 = h->causal[0];
-  WN_TRY(simt_embed_backward(dcur, h->x_idx, WS(t.demb), grads + c0.w_off, c0.b_off >= 0 ? grads + c0.b_off : nullptr,
-                             t.B, W, c0.out_ch, h->Q, c.causal_filter_width, s));
-  return WN_OK;
+  return causal_backward(h, params, grads, dout, s);
 }
 
 extern "C" int wn_forward_loss(wn_handle* h, const float* params, const int32_t* x, const int32_t* target, int T,

@@ -76,8 +76,8 @@ struct Tape {
   int64_t dcx[2] = {0, 0};            // [P][max causal width] (only when n_causal > 1)
   int64_t loss_acc = 0;               // 2 doubles
   // tensor-core path: TF32-rounded, K-major weight copies (rebuilt every forward)
-  int64_t tc_tab = 0, tc_w1 = 0, tc_w2 = 0, tc_ws = 0;
-  std::vector<int64_t> tc_wh;
+  int64_t tc_tab = 0, tc_w1 = 0, tc_w2 = 0, tc_ws = 0, tc_w1t = 0, tc_wpt = 0, tc_wst = 0;
+  std::vector<int64_t> tc_wh, tc_wht;
   int64_t total = 0;
 };
 
@@ -104,7 +104,11 @@ struct wn_handle {
   int T = 0;                       // columns seen by head/loss
   int sm_count = 148;
   bool tc_tab_uploaded = false;
-  bool tape_has_tfsg = false;      // false after a tensor-core forward (backward recomputes the gates)
+  bool tape_has_tfsg = false;      // tanh | sigmoid of every layer are on the tape
+  bool head_tc = false;            // head activations on the tape came from the tensor-core head
+  bool tape_tc = false;            // tape written by the tensor-core forward (stored head activations are post-ReLU)
+  bool save_gates = true;          // tensor-core forward also stores tanh | sigmoid (needed by backward)
+  const float* bwd_dout = nullptr; // gradient w.r.t. the causal output after the residual backward
 };
 
 // ---- SIMT fp32 kernels (wn_simt.cu) ---------------------------------------------
@@ -180,3 +184,5 @@ bool tc_layer_supported(const wn_handle* h);
 bool tc_head_supported(const wn_handle* h);
 int tc_forward_residual(wn_handle* h, const float* params, cudaStream_t s);
 int tc_forward_head(wn_handle* h, const float* params, int T, bool external, cudaStream_t s);
+int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s);
+int simt_colsum(const float* a, int64_t rows, int C, float* out, cudaStream_t s);

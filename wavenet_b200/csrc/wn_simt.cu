@@ -413,6 +413,13 @@ int simt_embed_backward(const float* dout, const int32_t* idx, float* demb, floa
   return WN_OK;
 }
 
+int simt_colsum(const float* a, int64_t rows, int C, float* out, cudaStream_t s) {
+  dim3 grid(blocks_for(C, 32), 64), block(32, 8);
+  colsum_kernel<<<grid, block, 0, s>>>(a, rows, C, out);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
 int simt_gate_forward(float* afg, float* z, int64_t P, int G, cudaStream_t s) {
   gate_forward_kernel<<<blocks_for(P * G, 256), 256, 0, s>>>(afg, z, P, G);
   WN_CHECK_LAUNCH();

@@ -12,6 +12,7 @@
 //                    skip sum  sum_l Ws_l z_l  (ONE GEMM with K = 64*L instead of L read-modify-write
 //                    passes over the 256-channel skip tensor, wavenet.py:579) and for the head convs.
 #include <cuda.h>
+#include <string.h>
 
 #include "wn_common.h"
 #include "wn_tc.cuh"
@@ -34,7 +35,8 @@ struct TcTabEntry {
 };
 
 __global__ void tc_prep_kernel(const float* __restrict__ params, const TcTabEntry* __restrict__ tab, float* __restrict__ w1,
-                               float* __restrict__ w2, float* __restrict__ wsc, int L, int R, int G, int S, int k) {
+                               float* __restrict__ w2, float* __restrict__ wsc, float* __restrict__ w1t,
+                               float* __restrict__ wpt, float* __restrict__ wst, int L, int R, int G, int S, int k) {
   const int l = blockIdx.y;
   const TcTabEntry e = tab[l];
   const int n1 = 2 * G * k * R, n2 = R * G, n3 = S * G;
@@ -43,16 +45,33 @@ __global__ void tc_prep_kernel(const float* __restrict__ params, const TcTabEntr
       const int n = i / (k * R), kk = i % (k * R);
       const int tap = kk / R, c = kk % R;
       const float* src = n < G ? params + e.wf : params + e.wg;
-      w1[(int64_t)l * n1 + i] = tf32_rna(src[((int64_t)(n % G) * R + c) * k + tap]);
+      const float v = tf32_rna(src[((int64_t)(n % G) * R + c) * k + tap]);
+      w1[(int64_t)l * n1 + i] = v;
+      // backward data-gradient operand: w1t[c][slab*2G + n], slab 0 = current tap (k-1), slab 1 = past tap
+      const int slab = (k - 1) - tap;
+      w1t[(int64_t)l * n1 + (int64_t)c * (k * 2 * G) + slab * 2 * G + n] = v;
     } else if (i < n1 + n2) {
       const int j = i - n1;
-      w2[(int64_t)l * n2 + j] = tf32_rna(params[e.wp + j]);
+      const float v = tf32_rna(params[e.wp + j]);
+      w2[(int64_t)l * n2 + j] = v;
+      const int r = j / G, g = j % G;
+      wpt[(int64_t)l * n2 + (int64_t)g * R + r] = v;
     } else {
       const int j = i - n1 - n2;
       const int sidx = j / G, g = j % G;
-      wsc[(int64_t)sidx * (L * G) + (int64_t)l * G + g] = tf32_rna(params[e.ws + j]);
+      const float v = tf32_rna(params[e.ws + j]);
+      wsc[(int64_t)sidx * (L * G) + (int64_t)l * G + g] = v;
+      wst[(int64_t)l * n3 + (int64_t)g * S + sidx] = v;
     }
   }
+}
+
+// dst[i][o] = tf32(src[o][i])
+__global__ void tc_transpose_round_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int I) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)O * I) return;
+  const int o = (int)(idx / I), i = (int)(idx % I);
+  dst[(int64_t)i * O + o] = tf32_rna(src[idx]);
 }
 
 __global__ void tc_round_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
@@ -89,6 +108,7 @@ __device__ __forceinline__ float tanh_fast(float x) {
 struct LayerArgs {
   float* x_out;            // [B][W][64]
   float* z_out;            // [B][W][64]
+  float* tfsg_out;         // [B][W][128] tanh | sigmoid for backward, or null
   const float* bias_fg;    // [128] or null
   const float* bias_p;     // [64] or null
   int W, d, zp, tiles_per_seq, num_tiles;
@@ -207,6 +227,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       mbar_wait(d1_full(s), ph);
       tcgen05_fence_after();
       uint32_t f[32], g[32];
+      float fsave[32];
       tmem_ld32(trow + s * 128 + half * 32, f);
       tmem_ld32(trow + s * 128 + 64 + half * 32, g);
       tmem_ld_wait();
@@ -218,18 +239,32 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           af += a.bias_fg[half * 32 + i];
           ag += a.bias_fg[64 + half * 32 + i];
         }
-        const float zz = tanh_fast(af) * (0.5f * tanh_fast(0.5f * ag) + 0.5f);
-        f[i] = __float_as_uint(live ? tf32_rna(zz) : 0.f);
+        const float tf = tanh_fast(af), sg = 0.5f * tanh_fast(0.5f * ag) + 0.5f;
+        g[i] = __float_as_uint(live ? sg : 0.5f);          // masked rows look like tanh(0) | sigmoid(0)
+        fsave[i] = live ? tf : 0.f;
+        f[i] = __float_as_uint(tf32_rna(fsave[i] * sg));
       }
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint4 v = make_uint4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
-        *reinterpret_cast<uint4*>(as_g + half * SUB_A + sw128_off(row, c)) = v;   // A operand of GEMM 2
-        if (valid) *reinterpret_cast<uint4*>(a.z_out + grow + 4 * c) = v;
-      }
+      for (int c = 0; c < 8; ++c)   // A operand of GEMM 2 first: the MMA warp is waiting for it
+        *reinterpret_cast<uint4*>(as_g + half * SUB_A + sw128_off(row, c)) =
+            make_uint4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
       fence_proxy_async();
       tcgen05_fence_before();
       mbar_arrive(z_full(s));
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(a.z_out + grow + 4 * c) = make_uint4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
+        if (a.tfsg_out) {
+          float* trow_g = a.tfsg_out + ((int64_t)b * a.W + t) * 128 + half * 32;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            *reinterpret_cast<float4*>(trow_g + 4 * c) =
+                make_float4(fsave[4 * c], fsave[4 * c + 1], fsave[4 * c + 2], fsave[4 * c + 3]);
+            *reinterpret_cast<uint4*>(trow_g + 64 + 4 * c) = make_uint4(g[4 * c], g[4 * c + 1], g[4 * c + 2], g[4 * c + 3]);
+          }
+        }
+      }
       // ---- epilogue 2: projection + residual ----
       mbar_wait(d2_full(s), ph);
       tcgen05_fence_after();
@@ -261,15 +296,22 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------
+// Y[(b,t)][n] = epi( sum_slab  A[slab_idx][b][t + slab_row_off][:] . Wt[n][slab*K ...] )
+constexpr int MAX_SLABS = 32;
 struct GemmTcArgs {
   float* Y;                // [num_seq * rows_out][ldy]
   int ldy;
   const float* bias;       // [N] or null
   int N;                   // valid output columns (<= BN)
-  int relu, round_out;
-  int rows_out;            // output rows per sequence (T)
-  int a_row_off;           // first A row of a sequence that is used (W - T)
-  int slabs, ksub;         // K = slabs * ksub * 32
+  int relu, round_out, accumulate;
+  const float* Rsd;        // residual added to the result (same rows as Y), or null
+  int ldr;
+  const float* mask;       // result zeroed where mask[(b, mask_row_off + t)][n] <= 0, or null
+  int ldm, mask_rows_in, mask_row_off;
+  int rows_out;            // output rows per sequence
+  int nslab, ksub;         // K = nslab * ksub * 32
+  int slab_row_off[MAX_SLABS];
+  int slab_idx[MAX_SLABS];
   int tiles_per_seq, num_tiles;
 };
 
@@ -279,7 +321,6 @@ struct GemmCfg {
   static constexpr int STAGES = (200 * 1024) / STAGE > 6 ? 6 : (200 * 1024) / STAGE;
   static constexpr int BAR = STAGES * STAGE;
   static constexpr int SMEM = BAR + 256 + 1024;
-  static constexpr int ACC = 2;   // TMEM accumulator buffers (2 x BN <= 512 columns)
 };
 
 template <int BN>
@@ -315,7 +356,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int n_local = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int ksteps = a.slabs * a.ksub;
+  const int ksteps = a.nslab * a.ksub;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -323,13 +364,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       for (int j = 0; j < n_local; ++j) {
         const int tile = blockIdx.x + j * gridDim.x;
         const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM;
-        for (int sl = 0; sl < a.slabs; ++sl)
+        for (int sl = 0; sl < a.nslab; ++sl)
           for (int ks = 0; ks < a.ksub; ++ks, ++it) {
             const int s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
             mbar_wait(empty(s), ph ^ 1);
             const uint32_t st = base + s * Cfg::STAGE;
             mbar_arrive_expect_tx(full(s), Cfg::STAGE);
-            tma_load_4d(st, &tm_a, full(s), ks * SUBK, a.a_row_off + t0, b, sl);
+            tma_load_4d(st, &tm_a, full(s), ks * SUBK, a.slab_row_off[sl] + t0, b, a.slab_idx[sl]);
             tma_load_2d(st + SUB_A, &tm_b, full(s), (sl * a.ksub + ks) * SUBK, 0);
           }
       }
@@ -365,7 +406,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int ab = j & 1, aph = (j >> 1) & 1;
       const int b = tile / a.tiles_per_seq, t = (tile % a.tiles_per_seq) * TM + row;
       const bool valid = t < a.rows_out;
-      float* yrow = a.Y + ((int64_t)b * a.rows_out + t) * a.ldy;
+      const int64_t orow = (int64_t)b * a.rows_out + t;
+      float* yrow = a.Y + orow * a.ldy;
+      const float* rrow = a.Rsd ? a.Rsd + orow * a.ldr : nullptr;
+      const float* mrow = a.mask ? a.mask + ((int64_t)b * a.mask_rows_in + a.mask_row_off + t) * a.ldm : nullptr;
       mbar_wait(acc_full(ab), aph);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -377,16 +421,37 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         if (valid && c0 < a.N) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            float o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float x = __uint_as_float(v[4 * c + e]);
-              if (a.bias) x += a.bias[c0 + 4 * c + e];
-              if (a.relu) x = fmaxf(x, 0.f);
-              if (a.round_out) x = tf32_rna(x);
-              o[e] = x;
+            float o[4] = {__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
+                          __uint_as_float(v[4 * c + 3])};
+            const int cc = c0 + 4 * c;
+            if (a.bias) {
+              const float4 bb = *reinterpret_cast<const float4*>(a.bias + cc);
+              o[0] += bb.x, o[1] += bb.y, o[2] += bb.z, o[3] += bb.w;
             }
-            *reinterpret_cast<float4*>(yrow + c0 + 4 * c) = make_float4(o[0], o[1], o[2], o[3]);
+            if (a.relu) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+            }
+            if (rrow) {
+              const float4 rr = *reinterpret_cast<const float4*>(rrow + cc);
+              o[0] += rr.x, o[1] += rr.y, o[2] += rr.z, o[3] += rr.w;
+            }
+            if (mrow) {
+              const float4 mm = *reinterpret_cast<const float4*>(mrow + cc);
+              o[0] = mm.x > 0.f ? o[0] : 0.f;
+              o[1] = mm.y > 0.f ? o[1] : 0.f;
+              o[2] = mm.z > 0.f ? o[2] : 0.f;
+              o[3] = mm.w > 0.f ? o[3] : 0.f;
+            }
+            if (a.accumulate) {
+              const float4 yy = *reinterpret_cast<const float4*>(yrow + cc);
+              o[0] += yy.x, o[1] += yy.y, o[2] += yy.z, o[3] += yy.w;
+            }
+            if (a.round_out) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o[e] = tf32_rna(o[e]);
+            }
+            *reinterpret_cast<float4*>(yrow + cc) = make_float4(o[0], o[1], o[2], o[3]);
           }
         }
       }
@@ -397,6 +462,138 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
+// Weight gradient: D[128 x NB] = sum over positions  dY[p][a_c0 + m] * X_slab[p + off_slab][c]
+// The reduction dimension (positions) is the row index of both operands in memory, so both are
+// MN-major UMMA operands: TMA deposits [32 positions x 32 channels] sub-tiles (128-byte rows,
+// SWIZZLE_128B); one K=8 MMA step consumes one 8-row swizzle group, sub-tiles 4096 B apart (LBO).
+struct WgradTcArgs {
+  int rows_it, num_seq;    // iteration rows per sequence
+  int a_row_off, a_c0;
+  int nb_slab, nb_sub;     // B slabs (taps) and 32-channel sub-tiles per slab
+  int b_row_off[2];
+  int slab_tap[2];
+  float* dW0;              // rows [0, m_split)
+  float* dW1;              // rows [m_split, m_valid)
+  int m_split, m_valid;
+  int64_t sn, sk, st;      // element (m, slab, c) -> + m*sn + c*sk + slab_tap[slab]*st
+  int chunks_per_seq, num_chunks;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+constexpr int WG_KC = 32;                 // positions per pipeline stage
+constexpr int WG_SUB = WG_KC * 128;       // bytes of a [32 x 32] sub-tile
+
+template <int NB>
+struct WgradCfg {
+  static constexpr int STAGE = 4 * WG_SUB + (NB / 32) * WG_SUB;
+  static constexpr int STAGES = 4;
+  static constexpr int BAR = STAGES * STAGE;
+  static constexpr int SMEM = BAR + 256 + 1024;
+};
+
+template <int NB>
+__global__ void __launch_bounds__(L_THREADS, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const WgradTcArgs a) {
+  using Cfg = WgradCfg<NB>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + Cfg::BAR;
+  auto full = [&](int s) { return bar0 + 8 * s; };
+  auto empty = [&](int s) { return bar0 + 64 + 8 * s; };
+  const uint32_t acc_full = bar0 + 128;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + Cfg::BAR + 192);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tm_a);
+    prefetch_tmap(&tm_b);
+  }
+  if (warp == 1) tmem_alloc<256>(smem_u32((const void*)tmem_slot));
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // contiguous chunk range per CTA
+  const int per = (a.num_chunks + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int c_begin = (int)blockIdx.x * per;
+  const int c_end = min(a.num_chunks, c_begin + per);
+  const int n_local = c_end - c_begin;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < n_local; ++it) {
+        const int chunk = c_begin + it;
+        const int b = chunk / a.chunks_per_seq, t0 = (chunk % a.chunks_per_seq) * WG_KC;
+        const int s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
+        mbar_wait(empty(s), ph ^ 1);
+        const uint32_t st = base + s * Cfg::STAGE;
+        mbar_arrive_expect_tx(full(s), Cfg::STAGE);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tma_load_4d(st + i * WG_SUB, &tm_a, full(s), a.a_c0 + i * SUBK, a.a_row_off + t0, b, 0);
+        for (int sl = 0; sl < a.nb_slab; ++sl)
+          for (int i = 0; i < a.nb_sub; ++i)
+            tma_load_4d(st + (4 + sl * a.nb_sub + i) * WG_SUB, &tm_b, full(s), i * SUBK, a.b_row_off[sl] + t0, b, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_local > 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(128, NB) | (1u << 15) | (1u << 16);   // both operands MN-major
+      for (int it = 0; it < n_local; ++it) {
+        const int s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
+        mbar_wait(full(s), ph);
+        tcgen05_fence_after();
+        const uint32_t st = base + s * Cfg::STAGE;
+#pragma unroll
+        for (int k8 = 0; k8 < WG_KC / 8; ++k8)
+          umma_tf32(tmem, umma_desc_mn_sw128(st + k8 * 1024, WG_SUB), umma_desc_mn_sw128(st + 4 * WG_SUB + k8 * 1024, WG_SUB),
+                    idesc, (it | k8) > 0);
+        umma_commit(empty(s));
+      }
+      umma_commit(acc_full);
+    }
+  } else if (n_local > 0) {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int m = q * 32 + lane;
+    constexpr int CH = NB / 64;
+    mbar_wait(acc_full, 0);
+    tcgen05_fence_after();
+    const int nb = a.nb_sub * 32;   // channels per slab
+#pragma unroll 1
+    for (int ch = 0; ch < CH; ++ch) {
+      const int c0 = (half * CH + ch) * 32;
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      if (m < a.m_valid) {
+        float* wrow = m < a.m_split ? a.dW0 + (int64_t)m * a.sn : a.dW1 + (int64_t)(m - a.m_split) * a.sn;
+        const int sl = c0 / nb, cbase = c0 % nb;
+        wrow += (int64_t)a.slab_tap[sl] * a.st;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(wrow + (int64_t)(cbase + i) * a.sk, __uint_as_float(v[i]));
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -460,34 +657,116 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcArgs& 
   return WN_OK;
 }
 
+template <int NB>
+int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, const WgradTcArgs& g, int sm_count, cudaStream_t s) {
+  using Cfg = WgradCfg<NB>;
+  static bool attr = false;
+  if (!attr) {
+    WN_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr = true;
+  }
+  const int grid = g.num_chunks < sm_count ? g.num_chunks : sm_count;
+  tc_wgrad_kernel<NB><<<grid, L_THREADS, Cfg::SMEM, s>>>(ta, tb, g);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
 }  // namespace
 
-// Y[(b, t)][0..N) = epi( sum_slab A_slab[b][a_row_off + t][:] . Wt[:, slab*K .. ]^T ),  Wt is [N][slabs*K] (TF32-rounded)
-int tc_gemm(const wn_handle* h, const float* A, int K, int rows_in, int num_seq, int slabs, int64_t slab_stride,
-            int a_row_off, int rows_out, const float* Wt, int N, const float* bias, int relu, int round_out, float* Y,
-            int ldy, cudaStream_t s) {
-  WN_REQUIRE(K % SUBK == 0 && N % 32 == 0 && N <= 256, WN_EINVAL, "tc_gemm: unsupported shape K=%d N=%d", K, N);
+// One operand of a slab GEMM: rows of sequence b are A[slab][b][row_off + t][0..K)
+struct TcOperand {
+  const float* ptr;
+  int K;            // channels (row length, contiguous)
+  int rows_in;      // rows per sequence in memory
+  int num_seq;
+  int nslab;        // number of equally spaced slabs behind ptr (1 for a plain tensor)
+  int64_t slab_stride;
+};
+
+struct TcEpilogue {
+  const float* bias = nullptr;
+  int relu = 0, round_out = 0, accumulate = 0;
+  const float* Rsd = nullptr;
+  int ldr = 0;
+  const float* mask = nullptr;
+  int ldm = 0, mask_rows_in = 0, mask_row_off = 0;
+};
+
+// Y[(b, t)][0..N) = epi( sum_s A[slab_idx[s]][b][t + row_off[s]][:] . Wt[:, s*K ..]^T ),  Wt is [N][ns*K] (TF32-rounded)
+int tc_gemm(const wn_handle* h, const TcOperand& A, int ns, const int* slab_idx, const int* row_off, int rows_out,
+            const float* Wt, int N, const TcEpilogue& e, float* Y, int ldy, cudaStream_t s) {
+  WN_REQUIRE(A.K % SUBK == 0 && N % 32 == 0 && N <= 256 && ns <= MAX_SLABS, WN_EINVAL,
+             "tc_gemm: unsupported shape K=%d N=%d slabs=%d", A.K, N, ns);
   CUtensorMap ta, tb;
-  if (slabs == 1) slab_stride = (int64_t)rows_in * num_seq * K;
-  WN_TRY(make_map_4d(&ta, A, K, rows_in, num_seq, slabs, K, (uint64_t)rows_in * K, slab_stride, TM));
+  const int64_t sstride = A.nslab > 1 ? A.slab_stride : (int64_t)A.rows_in * A.num_seq * A.K;
+  WN_TRY(make_map_4d(&ta, A.ptr, A.K, A.rows_in, A.num_seq, A.nslab, A.K, (uint64_t)A.rows_in * A.K, sstride, TM));
   const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-  WN_TRY(make_map_2d(&tb, Wt, (uint64_t)slabs * K, N, (uint64_t)slabs * K, BN));
+  WN_TRY(make_map_2d(&tb, Wt, (uint64_t)ns * A.K, N, (uint64_t)ns * A.K, BN));
   GemmTcArgs g;
+  memset(&g, 0, sizeof(g));
   g.Y = Y;
   g.ldy = ldy;
-  g.bias = bias;
+  g.bias = e.bias;
   g.N = N;
-  g.relu = relu;
-  g.round_out = round_out;
+  g.relu = e.relu;
+  g.round_out = e.round_out;
+  g.accumulate = e.accumulate;
+  g.Rsd = e.Rsd;
+  g.ldr = e.ldr;
+  g.mask = e.mask;
+  g.ldm = e.ldm;
+  g.mask_rows_in = e.mask_rows_in;
+  g.mask_row_off = e.mask_row_off;
   g.rows_out = rows_out;
-  g.a_row_off = a_row_off;
-  g.slabs = slabs;
-  g.ksub = K / SUBK;
+  g.nslab = ns;
+  g.ksub = A.K / SUBK;
+  for (int i = 0; i < ns; ++i) {
+    g.slab_row_off[i] = row_off ? row_off[i] : 0;
+    g.slab_idx[i] = slab_idx ? slab_idx[i] : 0;
+  }
   g.tiles_per_seq = (rows_out + TM - 1) / TM;
-  g.num_tiles = g.tiles_per_seq * num_seq;
+  g.num_tiles = g.tiles_per_seq * A.num_seq;
   if (BN == 64) return launch_gemm<64>(ta, tb, g, h->sm_count, s);
   if (BN == 128) return launch_gemm<128>(ta, tb, g, h->sm_count, s);
   return launch_gemm<256>(ta, tb, g, h->sm_count, s);
+}
+
+// dW(m, tap, c) += sum_{b,t} dY[b][a_row_off + t][a_c0 + m] * X[b][b_row_off[s] + t][c]   for m < m_valid (<= 128)
+int tc_wgrad(const wn_handle* h, const TcOperand& dY, int a_row_off, int a_c0, int m_valid, const TcOperand& X, int nb_slab,
+             const int* b_row_off, const int* slab_tap, int rows_it, float* dW0, float* dW1, int m_split, int64_t sn,
+             int64_t sk, int64_t st, cudaStream_t s) {
+  const int NB = nb_slab * X.K;
+  WN_REQUIRE(X.K % 32 == 0 && (NB == 64 || NB == 128 || NB == 256) && nb_slab <= 2, WN_EINVAL,
+             "tc_wgrad: unsupported shape X.K=%d slabs=%d", X.K, nb_slab);
+  CUtensorMap ta, tb;
+  WN_TRY(make_map_4d(&ta, dY.ptr, dY.K, dY.rows_in, dY.num_seq, 1, dY.K, (uint64_t)dY.rows_in * dY.K,
+                     (uint64_t)dY.rows_in * dY.num_seq * dY.K, WG_KC));
+  WN_TRY(make_map_4d(&tb, X.ptr, X.K, X.rows_in, X.num_seq, 1, X.K, (uint64_t)X.rows_in * X.K,
+                     (uint64_t)X.rows_in * X.num_seq * X.K, WG_KC));
+  WgradTcArgs g;
+  memset(&g, 0, sizeof(g));
+  g.rows_it = rows_it;
+  g.num_seq = dY.num_seq;
+  g.a_row_off = a_row_off;
+  g.a_c0 = a_c0;
+  g.nb_slab = nb_slab;
+  g.nb_sub = X.K / 32;
+  for (int i = 0; i < nb_slab; ++i) {
+    g.b_row_off[i] = b_row_off[i];
+    g.slab_tap[i] = slab_tap[i];
+  }
+  g.dW0 = dW0;
+  g.dW1 = dW1;
+  g.m_split = m_split;
+  g.m_valid = m_valid;
+  g.sn = sn;
+  g.sk = sk;
+  g.st = st;
+  g.chunks_per_seq = (rows_it + WG_KC - 1) / WG_KC;
+  g.num_chunks = g.chunks_per_seq * dY.num_seq;
+  if (NB == 64) return launch_wgrad<64>(ta, tb, g, h->sm_count, s);
+  if (NB == 128) return launch_wgrad<128>(ta, tb, g, h->sm_count, s);
+  return launch_wgrad<256>(ta, tb, g, h->sm_count, s);
 }
 
 bool tc_layer_supported(const wn_handle* h) {
@@ -500,8 +779,8 @@ bool tc_layer_supported(const wn_handle* h) {
 
 bool tc_head_supported(const wn_handle* h) {
   for (const ConvParam& c : h->head)
-    if (c.in_ch % 32 != 0 || c.out_ch % 32 != 0 || c.out_ch > 256) return false;
-  return get_encode() != nullptr;
+    if (c.in_ch % 32 != 0 || c.out_ch % 32 != 0 || c.out_ch > 256 || c.in_ch > 256) return false;
+  return h->S % 32 == 0 && get_encode() != nullptr;
 }
 
 int tc_prepare_weights(wn_handle* h, const float* params, cudaStream_t s) {
@@ -521,7 +800,8 @@ int tc_prepare_weights(wn_handle* h, const float* params, cudaStream_t s) {
   }
   dim3 grid(16, L);
   tc_prep_kernel<<<grid, 256, 0, s>>>(params, (const TcTabEntry*)(h->ws + t.tc_tab), h->ws + t.tc_w1, h->ws + t.tc_w2,
-                                      h->ws + t.tc_ws, L, h->R, 64, h->S, 2);
+                                      h->ws + t.tc_ws, h->ws + t.tc_w1t, h->ws + t.tc_wpt, h->ws + t.tc_wst, L, h->R, 64,
+                                      h->S, 2);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
@@ -541,7 +821,6 @@ int tc_forward_residual(wn_handle* h, const float* params, cudaStream_t s) {
   const int grid = num_tiles < h->sm_count ? num_tiles : h->sm_count;
   for (int l = 0; l < L; ++l) {
     const ResLayer& ly = h->layers[l];
-    WN_REQUIRE(ly.wf.b_off < 0 && ly.proj.b_off < 0, WN_EINVAL, "tc layer kernel: bias path goes through SIMT");
     CUtensorMap tx, tw1, tw2;
     WN_TRY(make_map_4d(&tx, h->ws + t.x[l], R, t.W, t.B, 1, R, (uint64_t)t.W * R, (uint64_t)t.P * R, TM));
     WN_TRY(make_map_2d(&tw1, h->ws + t.tc_w1 + (int64_t)l * 2 * G * 2 * R, 2 * R, 2 * G, 2 * R, 128));
@@ -549,6 +828,7 @@ int tc_forward_residual(wn_handle* h, const float* params, cudaStream_t s) {
     LayerArgs a;
     a.x_out = h->ws + t.x[l + 1];
     a.z_out = h->ws + t.z[l];
+    a.tfsg_out = h->save_gates ? h->ws + t.tfsg[l] : nullptr;
     a.bias_fg = nullptr;
     a.bias_p = nullptr;
     a.W = t.W;
@@ -563,12 +843,19 @@ int tc_forward_residual(wn_handle* h, const float* params, cudaStream_t s) {
   const int64_t zstride = L > 1 ? t.z[1] - t.z[0] : 0;
   for (int l = 1; l < L; ++l)
     WN_REQUIRE(t.z[l] - t.z[l - 1] == zstride, WN_EINVAL, "z slabs are not equally spaced");
-  return tc_gemm(h, h->ws + t.z[0], G, t.W, t.B, L, zstride, 0, t.W, h->ws + t.tc_ws, h->S, nullptr, 0, 0,
-                 h->ws + t.skip, h->S, s);
+  WN_REQUIRE(L <= MAX_SLABS, WN_EINVAL, "too many layers for the skip GEMM");
+  int idx[MAX_SLABS], off[MAX_SLABS];
+  for (int l = 0; l < L; ++l) {
+    idx[l] = l;
+    off[l] = 0;
+  }
+  TcOperand A{h->ws + t.z[0], G, t.W, t.B, L, zstride};
+  TcEpilogue e;
+  return tc_gemm(h, A, L, idx, off, t.W, h->ws + t.tc_ws, h->S, e, h->ws + t.skip, h->S, s);
 }
 
 // ReLU -> 1x1 conv per head layer (wavenet.py:587-590) on tensor cores.  Stored activations are
-// post-ReLU (ReLU is idempotent, so the SIMT backward's a_relu / mask logic sees the same values).
+// post-ReLU (ReLU is idempotent, so mask / a_relu logic in backward sees the same values).
 int tc_forward_head(wn_handle* h, const float* params, int T, bool external, cudaStream_t s) {
   const Tape& t = h->tape;
   const int nh = (int)h->head.size();
@@ -584,12 +871,108 @@ int tc_forward_head(wn_handle* h, const float* params, int T, bool external, cud
     const int64_t n = (int64_t)cp.out_ch * cp.in_ch;
     tc_round_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(params + cp.w_off, h->ws + t.tc_wh[i], n);
     WN_CHECK_LAUNCH();
-    const float* A = i == 0 ? h->ws + t.skip : h->ws + t.hbuf[i - 1];
-    const int rin = i == 0 ? rows_in0 : T, off = i == 0 ? off0 : 0;
     const bool last = i == nh - 1;
-    WN_TRY(tc_gemm(h, A, cp.in_ch, rin, t.B, 1, 0, off, T, h->ws + t.tc_wh[i], cp.out_ch,
-                   cp.b_off >= 0 ? params + cp.b_off : nullptr, last ? 0 : 1, last ? 0 : 1, h->ws + t.hbuf[i], cp.out_ch,
-                   s));
+    TcOperand A{i == 0 ? h->ws + t.skip : h->ws + t.hbuf[i - 1], cp.in_ch, i == 0 ? rows_in0 : T, t.B, 1, 0};
+    const int off = i == 0 ? off0 : 0;
+    TcEpilogue e;
+    e.bias = cp.b_off >= 0 ? params + cp.b_off : nullptr;
+    e.relu = last ? 0 : 1;
+    e.round_out = last ? 0 : 1;
+    WN_TRY(tc_gemm(h, A, 1, nullptr, &off, T, h->ws + t.tc_wh[i], cp.out_ch, e, h->ws + t.hbuf[i], cp.out_ch, s));
   }
+  return WN_OK;
+}
+
+// Backward of head + residual stack on tensor cores (gate derivative and embedding scatter stay SIMT).
+// Requires a tape written by tc_forward_residual(save_gates) and tc_forward_head.
+int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s) {
+  const Tape& t = h->tape;
+  const int T = h->T, W = t.W, B = t.B;
+  const int64_t P = t.P;
+  const int nh = (int)h->head.size();
+  const int L = (int)h->layers.size();
+  const int R = 64, G = 64, S = h->S;
+  float* ws = h->ws;
+  const int zero = 0;
+  // ---- head ----
+  const float* d = ws + t.dlogits;
+  int tog = 0;
+  for (int i = nh - 1; i >= 0; --i) {
+    const ConvParam& cp = h->head[i];
+    const bool first = i == 0;
+    const int rin = first ? (h->head_external ? T : W) : T;
+    const int aoff = first ? (h->head_external ? 0 : W - T) : 0;
+    const float* Ain = first ? ws + t.skip : ws + t.hbuf[i - 1];
+    TcOperand dY{d, cp.out_ch, T, B, 1, 0};
+    TcOperand X{Ain, cp.in_ch, rin, B, 1, 0};
+    const int tap0 = 0;
+    for (int m0 = 0; m0 < cp.out_ch; m0 += 128) {
+      const int mv = cp.out_ch - m0 < 128 ? cp.out_ch - m0 : 128;
+      WN_TRY(tc_wgrad(h, dY, 0, m0, mv, X, 1, &aoff, &tap0, T, grads + cp.w_off + (int64_t)m0 * cp.in_ch, nullptr, 128,
+                      cp.in_ch, 1, 0, s));
+    }
+    if (cp.b_off >= 0) WN_TRY(simt_colsum(d, (int64_t)B * T, cp.out_ch, grads + cp.b_off, s));
+    if (first && h->head_external) return WN_OK;
+    // d_prev = (d . W) masked by the stored (post-ReLU) input
+    const int64_t n = (int64_t)cp.out_ch * cp.in_ch;
+    tc_transpose_round_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(params + cp.w_off, ws + t.tc_wht[i], cp.out_ch,
+                                                                         cp.in_ch);
+    WN_CHECK_LAUNCH();
+    TcEpilogue e;
+    e.mask = Ain;
+    e.ldm = cp.in_ch;
+    e.mask_rows_in = rin;
+    e.mask_row_off = aoff;
+    WN_TRY(tc_gemm(h, dY, 1, nullptr, &zero, T, ws + t.tc_wht[i], cp.in_ch, e, ws + t.dh[tog], cp.in_ch, s));
+    d = ws + t.dh[tog];
+    tog ^= 1;
+  }
+  const float* dskip = d;   // [B*T][S]
+  TcOperand DS{dskip, S, T, B, 1, 0};
+  // ---- residual layers ----
+  int dt = 0;
+  const float* dout = nullptr;
+  for (int l = L - 1; l >= 0; --l) {
+    const ResLayer& ly = h->layers[l];
+    const int zp = wn_zero_prefix(W, ly.dilation, 2);
+    TcOperand Z{ws + t.z[l], G, W, B, 1, 0};
+    const int tap0 = 0, wt = W - T, nwt = -(W - T);
+    if (dout) {
+      TcOperand DO{dout, R, W, B, 1, 0};
+      TcEpilogue e;
+      WN_TRY(tc_gemm(h, DO, 1, nullptr, &zero, W, ws + t.tc_wpt + (int64_t)l * G * R, G, e, ws + t.dz, G, s));
+      WN_TRY(tc_wgrad(h, DO, 0, 0, R, Z, 1, &zero, &tap0, W, grads + ly.proj.w_off, nullptr, 128, G, 1, 0, s));
+    }
+    {
+      TcEpilogue e;
+      e.accumulate = dout != nullptr;
+      WN_TRY(tc_gemm(h, DS, 1, nullptr, &nwt, W, ws + t.tc_wst + (int64_t)l * G * S, G, e, ws + t.dz, G, s));
+      for (int m0 = 0; m0 < S; m0 += 128) {
+        const int mv = S - m0 < 128 ? S - m0 : 128;
+        WN_TRY(tc_wgrad(h, DS, 0, m0, mv, Z, 1, &wt, &tap0, T, grads + ly.skip.w_off + (int64_t)m0 * G, nullptr, 128, G, 1,
+                        0, s));
+      }
+    }
+    WN_TRY(simt_gate_backward(ws + t.tfsg[l], ws + t.dz, ws + t.dafg, P, W, G, zp, s));
+    TcOperand DA{ws + t.dafg, 2 * G, W, B, 1, 0};
+    {
+      TcOperand X{ws + t.x[l], R, W, B, 1, 0};
+      const int boff[2] = {-ly.dilation, 0};
+      const int taps[2] = {0, 1};
+      WN_TRY(tc_wgrad(h, DA, 0, 0, 2 * G, X, 2, boff, taps, W, grads + ly.wf.w_off, grads + ly.wg.w_off, G, 2 * R, 2, 1, s));
+    }
+    {
+      float* dnew = ws + t.dout[dt];
+      const int roff[2] = {0, ly.dilation};
+      const int sidx[2] = {0, 0};
+      TcEpilogue e;
+      e.Rsd = dout;
+      e.ldr = R;
+      WN_TRY(tc_gemm(h, DA, 2, sidx, roff, W, ws + t.tc_w1t + (int64_t)l * R * 4 * G, R, e, dnew, R, s));
+      dout = dnew;
+      dt ^= 1;
+    }
+  }
+  h->bwd_dout = dout;
   return WN_OK;
 }
