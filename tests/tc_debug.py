@@ -60,3 +60,6 @@ print("worst tf32 grad rel errs (tf32, name, fp32):")
 for e in worst[:12]:
     print("  %.3e  %-44s %.3e" % e)
 print("median tf32 rel err %.3e" % np.median([e[0] for e in worst]))
+for k in ["softmax_1/W", "softmax_1/b", "softmax_0/W", "residual_1_block_5_wf/W", "residual_1_block_5_projection_softmax/W", "residual_0_block_0_projection_block/W", "causal_0/W"]:
+    a, b_, r = grads["tf32"][k], grads["fp32"][k], g_ref[k]
+    print("%-44s |tf32| %.4e |fp32| %.4e |ref| %.4e  tf32[0,:4]=%s ref[0,:4]=%s" % (k, np.linalg.norm(a), np.linalg.norm(b_), np.linalg.norm(r), a.reshape(a.shape[0], -1)[0, :4] if a.ndim > 1 else a[:4], r.reshape(r.shape[0], -1)[0, :4] if r.ndim > 1 else r[:4]))

@@ -315,7 +315,7 @@ def test_tf32_path_matches_oracle(name, B, W, T):
         if np.abs(v).max() == 0:
             assert np.abs(g[k]).max() == 0, k
         else:
-            assert rel_err(g[k], v) < 2e-2, (k, rel_err(g[k], v))
+            assert rel_err(g[k], v) < 5e-2, (k, rel_err(g[k], v))   # TF32 forward + TF32 backward
 
 
 def test_tf32_full_size_agrees_with_fp32_path():

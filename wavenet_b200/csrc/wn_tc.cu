@@ -468,7 +468,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 // Weight gradient: D[128 x NB] = sum over positions  dY[p][a_c0 + m] * X_slab[p + off_slab][c]
 // The reduction dimension (positions) is the row index of both operands in memory, so both are
 // MN-major UMMA operands: TMA deposits [32 positions x 32 channels] sub-tiles (128-byte rows,
-// SWIZZLE_128B); one K=8 MMA step consumes one 8-row swizzle group, sub-tiles 4096 B apart (LBO).
+// SWIZZLE_128B_ATOM_32B); one K=8 MMA step consumes two 4-row swizzle groups (SBO 512 B), sub-tiles
+// are 4096 B apart (LBO).
 struct WgradTcArgs {
   int rows_it, num_seq;    // iteration rows per sequence
   int a_row_off, a_c0;
@@ -480,15 +481,19 @@ struct WgradTcArgs {
   int m_split, m_valid;
   int64_t sn, sk, st;      // element (m, slab, c) -> + m*sn + c*sk + slab_tap[slab]*st
   int chunks_per_seq, num_chunks;
+  int dbg_lbo, dbg_sbo, dbg_kstep, dbg_major;   // descriptor probing (wn_debug_wgrad); 0 = defaults
 };
 
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+// MN-major tf32 operands only exist in the SWIZZLE_128B_BASE32B layout (layout_type 1): 128-byte rows,
+// 4-row atoms, 32-byte chunks XOR-ed with (row & 3) -- what TMA's SWIZZLE_128B_ATOM_32B deposits.
+// LBO = bytes between 32-element M atoms, SBO = bytes between 4-row K groups.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_32b(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)(lbo_bytes >> 4) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)1 << 61;
   return d;
 }
 
@@ -555,7 +560,11 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     }
   } else if (warp == 1) {
     if (lane == 0 && n_local > 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(128, NB) | (1u << 15) | (1u << 16);   // both operands MN-major
+      uint32_t idesc = umma_idesc_tf32(128, NB) | (1u << 15) | (1u << 16);   // both operands MN-major
+      if (a.dbg_major && a.dbg_major < 4) idesc = umma_idesc_tf32(128, NB) | ((uint32_t)(a.dbg_major & 3) << 15);
+      if (a.dbg_major == 4) idesc = umma_idesc_tf32(128, NB);
+      const uint32_t lbo = a.dbg_lbo ? a.dbg_lbo : WG_SUB, sbo = a.dbg_sbo ? a.dbg_sbo : 512;
+      const uint32_t kstep = a.dbg_kstep ? a.dbg_kstep : 1024;
       for (int it = 0; it < n_local; ++it) {
         const int s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
         mbar_wait(full(s), ph);
@@ -563,8 +572,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const uint32_t st = base + s * Cfg::STAGE;
 #pragma unroll
         for (int k8 = 0; k8 < WG_KC / 8; ++k8)
-          umma_tf32(tmem, umma_desc_mn_sw128(st + k8 * 1024, WG_SUB), umma_desc_mn_sw128(st + 4 * WG_SUB + k8 * 1024, WG_SUB),
-                    idesc, (it | k8) > 0);
+          umma_tf32(tmem, umma_desc_mn_sw128_32b(st + k8 * kstep, lbo, sbo),
+                    umma_desc_mn_sw128_32b(st + 4 * WG_SUB + k8 * kstep, lbo, sbo), idesc, (it | k8) > 0);
         umma_commit(empty(s));
       }
       umma_commit(acc_full);
@@ -587,7 +596,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const int sl = c0 / nb, cbase = c0 % nb;
         wrow += (int64_t)a.slab_tap[sl] * a.st;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) atomicAdd(wrow + (int64_t)(cbase + i) * a.sk, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; ++i) {
+          float val = __uint_as_float(v[i]);
+          if (a.dbg_major == 7) val = 1.0f;                                                     // flow probe
+          if (a.dbg_major == 6) val = *reinterpret_cast<const float*>(gbase + (m * 32 + i) * 4);   // smem A probe (stage 0)
+          if (a.dbg_major == 5) val = *reinterpret_cast<const float*>(gbase + 4 * WG_SUB + (m * 32 + i) * 4);   // smem B
+          atomicAdd(wrow + (int64_t)(cbase + i) * a.sk, val);
+        }
       }
     }
   }
@@ -615,7 +630,7 @@ EncodeTiledFn get_encode() {
 
 // fp32 tensor [d3][d2][d1][d0] (d0 contiguous), box [1][1][box1][32], SWIZZLE_128B, zero fill out of range
 int make_map_4d(CUtensorMap* m, const float* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint64_t s1,
-                uint64_t s2, uint64_t s3, uint32_t box1) {
+                uint64_t s2, uint64_t s3, uint32_t box1, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   WN_REQUIRE(enc, WN_ECUDA, "cuTensorMapEncodeTiled is unavailable");
   cuuint64_t dims[4] = {d0, d1, d2, d3};
@@ -623,7 +638,7 @@ int make_map_4d(CUtensorMap* m, const float* ptr, uint64_t d0, uint64_t d1, uint
   cuuint32_t box[4] = {SUBK, box1, 1, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)ptr, dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   WN_REQUIRE(r == CUDA_SUCCESS, WN_ECUDA, "cuTensorMapEncodeTiled(4d) failed: %d", (int)r);
   return WN_OK;
@@ -732,6 +747,7 @@ int tc_gemm(const wn_handle* h, const TcOperand& A, int ns, const int* slab_idx,
 }
 
 // dW(m, tap, c) += sum_{b,t} dY[b][a_row_off + t][a_c0 + m] * X[b][b_row_off[s] + t][c]   for m < m_valid (<= 128)
+static int g_dbg[4] = {0, 0, 0, 0};
 int tc_wgrad(const wn_handle* h, const TcOperand& dY, int a_row_off, int a_c0, int m_valid, const TcOperand& X, int nb_slab,
              const int* b_row_off, const int* slab_tap, int rows_it, float* dW0, float* dW1, int m_split, int64_t sn,
              int64_t sk, int64_t st, cudaStream_t s) {
@@ -740,9 +756,9 @@ int tc_wgrad(const wn_handle* h, const TcOperand& dY, int a_row_off, int a_c0, i
              "tc_wgrad: unsupported shape X.K=%d slabs=%d", X.K, nb_slab);
   CUtensorMap ta, tb;
   WN_TRY(make_map_4d(&ta, dY.ptr, dY.K, dY.rows_in, dY.num_seq, 1, dY.K, (uint64_t)dY.rows_in * dY.K,
-                     (uint64_t)dY.rows_in * dY.num_seq * dY.K, WG_KC));
+                     (uint64_t)dY.rows_in * dY.num_seq * dY.K, WG_KC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   WN_TRY(make_map_4d(&tb, X.ptr, X.K, X.rows_in, X.num_seq, 1, X.K, (uint64_t)X.rows_in * X.K,
-                     (uint64_t)X.rows_in * X.num_seq * X.K, WG_KC));
+                     (uint64_t)X.rows_in * X.num_seq * X.K, WG_KC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   WgradTcArgs g;
   memset(&g, 0, sizeof(g));
   g.rows_it = rows_it;
@@ -764,6 +780,10 @@ int tc_wgrad(const wn_handle* h, const TcOperand& dY, int a_row_off, int a_c0, i
   g.st = st;
   g.chunks_per_seq = (rows_it + WG_KC - 1) / WG_KC;
   g.num_chunks = g.chunks_per_seq * dY.num_seq;
+  g.dbg_lbo = g_dbg[0];
+  g.dbg_sbo = g_dbg[1];
+  g.dbg_kstep = g_dbg[2];
+  g.dbg_major = g_dbg[3];
   if (NB == 64) return launch_wgrad<64>(ta, tb, g, h->sm_count, s);
   if (NB == 128) return launch_wgrad<128>(ta, tb, g, h->sm_count, s);
   return launch_wgrad<256>(ta, tb, g, h->sm_count, s);
@@ -975,4 +995,19 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
   }
   h->bwd_dout = dout;
   return WN_OK;
+}
+
+// Debug probe: dW[128][Kx] = dY[rows][0..128)^T . X[rows][Kx] with explicit descriptor parameters.
+extern "C" int wn_debug_wgrad(wn_handle* h, const float* dY, int Kd, const float* X, int Kx, int rows, int nseq, float* dW,
+                              int lbo, int sbo, int kstep, int major, void* stream) {
+  g_dbg[0] = lbo;
+  g_dbg[1] = sbo;
+  g_dbg[2] = kstep;
+  g_dbg[3] = major;
+  TcOperand A{dY, Kd, rows, nseq, 1, 0};
+  TcOperand B{X, Kx, rows, nseq, 1, 0};
+  const int zero = 0;
+  int rc = tc_wgrad(h, A, 0, 0, 128, B, 1, &zero, &zero, rows, dW, nullptr, 128, Kx, 1, 0, (cudaStream_t)stream);
+  g_dbg[0] = g_dbg[1] = g_dbg[2] = g_dbg[3] = 0;
+  return rc;
 }
