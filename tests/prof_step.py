@@ -1,0 +1,15 @@
+import sys, os
+sys.path.insert(0, '/root/repo')
+import numpy as np, torch
+from oracle import wavenet_oracle as O
+from bench import config_c, synth_batch
+from wavenet_b200.faster_wavenet import FasterWaveNet
+B, W = 32, 16000
+net = FasterWaveNet(config_c(), seed=0)
+net.set_weights(O.init_weights(O.config_C(), np.random.default_rng(1234), np.float32))
+net.to_gpu(0); net.set_precision("tf32"); net.update_laerning_rate(1e-3)
+x, t = synth_batch(0, B, W)
+xd, td = torch.from_numpy(x).cuda(), torch.from_numpy(t).cuda()
+for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
+    net.train_step(xd, td)
+torch.cuda.synchronize()

@@ -1,0 +1,25 @@
+# -*- coding: utf-8 -*-
+"""Command line of the reference's train_audio/args.py:5-19 (module-level singleton `args`)."""
+import argparse
+
+parser = argparse.ArgumentParser()
+parser.add_argument("-g", "--gpu_device", type=int, default=0)
+parser.add_argument("-w", "--wav-dir", type=str, default="wav")
+parser.add_argument("-m", "--model-dir", type=str, default="model")
+
+# generation
+parser.add_argument("-o", "--output_dir", type=str, default="generated_audio")
+parser.add_argument("-s", "--seconds", type=float, default=1.0)
+parser.add_argument("--lr", type=float, default=0.001, help="learning_rate")
+# live flag of the reference is --fast (args.py:14); its README says --use_faster_wavenet (README.md:44)
+parser.add_argument("--fast", "--use_faster_wavenet", dest="fast", action="store_true", default=False)
+
+# seed
+parser.add_argument("--seed", type=int, default=None)
+
+# B200 backend extras (not in the reference)
+parser.add_argument("--precision", type=str, default="tf32", choices=["tf32", "fp32"],
+                    help="tf32: tcgen05 tensor-core path; fp32: exact SIMT parity path")
+parser.add_argument("--greedy", action="store_true", default=False, help="argmax decoding instead of sampling")
+
+args = parser.parse_args()

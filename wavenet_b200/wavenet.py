@@ -17,6 +17,7 @@ import torch
 
 from . import _lib
 from ._lib import check
+from .dist import allreduce_sum_
 
 
 # --------------------------------------------------------------------------
@@ -463,10 +464,7 @@ class WaveNet(object):
     def update(self):
         """Hooks + Adam (wavenet.py:477-480, Chainer GradientMethod.update)."""
         p, opt = self.params, self.optimizer
-        grad_scale = 1.0
-        if self.data_parallel and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-            torch.distributed.all_reduce(self._grads)
-            grad_scale = 1.0 / torch.distributed.get_world_size()
+        grad_scale = allreduce_sum_(self._grads) if self.data_parallel else 1.0
         opt.t += 1
         check(self._libh.wn_clip_adam_step(self._h, _ptr(self._params), _ptr(self._grads), _ptr(self._m), _ptr(self._v),
                                            opt.t, opt.alpha, opt.beta1, opt.beta2, opt.eps, float(p.weight_decay),
