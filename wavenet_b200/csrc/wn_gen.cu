@@ -11,6 +11,9 @@
 #include <string.h>
 
 #include "wn_common.h"
+#include "wn_tc.cuh"
+
+static const int GT_HOST = 256;   // consumer threads per CTA (must equal GT below)
 
 struct GenLayerOff {
   int64_t wa, ba, wb, bb, ring;  // offsets (floats) into the state buffer
@@ -27,8 +30,15 @@ struct GenLayout {
   int64_t idx_hist = 0;     // int32 [n][kc-1]
   int64_t cur_logits = 0;   // [n][Q]
   int64_t layers_dev = 0;   // GenLayerOff[L] copied to device (as raw bytes)
+  int64_t chunks_dev = 0;   // GenChunk[] streaming schedule
   int64_t total = 0;
   int maxw = 0;             // widest vector anywhere (for smem sizing)
+};
+
+struct GenChunk {
+  uint64_t off;     // byte offset from the state base (16-byte aligned)
+  uint32_t bytes;
+  uint32_t pad;
 };
 
 struct wn_gen {
@@ -40,12 +50,26 @@ struct wn_gen {
   int64_t state_bytes = 0;
   bool primed = false;
   int64_t t = 0;         // absolute time of the next sample
-  int64_t steps_done = 0;  // incremental steps since priming (head_act==1: ELU once > 0 ... always for steps)
+  int64_t steps_done = 0;  // incremental steps since priming
+  bool stream_ok = false;             // every matrix fits the streamed (cp.async.bulk ring) matvec
+  std::vector<GenChunk> chunks;       // per-step streaming schedule
 };
 
 namespace {
 
-constexpr int GT = 256;  // threads per CTA
+constexpr int GT = 256;  // consumer threads per CTA (the streaming variant adds one producer warp)
+constexpr int RING_STAGES = 8;
+constexpr int RING_STAGE_BYTES = 16384;
+
+// barrier among the GT consumer threads only (the producer warp never joins)
+__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// consumer-side view of the weight ring
+struct StreamCtx {
+  uint32_t full0, empty0;   // smem addresses of the barrier arrays
+  const float* ring;        // generic pointer to stage 0
+  uint32_t it;              // chunks consumed so far
+};
 
 inline int64_t align_up64(int64_t v) { return (v + 63) / 64 * 64; }
 
@@ -90,6 +114,8 @@ struct GenArgs {
   float* state;
   GenLayout lay;
   const GenLayerOff* layers;
+  const GenChunk* chunks;   // per-step weight streaming schedule (STREAM kernels)
+  int n_chunks;
   int n_steps;
   int mode;            // WN_GEN_GREEDY / WN_GEN_SAMPLE
   int sample_first;    // 1: draw each step's input from cur_logits (run); 0: inputs forced (step API)
@@ -142,7 +168,7 @@ __device__ __forceinline__ void matvec(const float* __restrict__ Wt, int K, int 
 #pragma unroll
       for (int s = 0; s < NS; ++s) part[(ks * NS + s) * N + o] = acc[s];
     }
-    __syncthreads();
+    csync();
     for (int i = tid; i < NS * N; i += GT) {
       const int s = i / N, oo = i - s * N;
       float v = bias ? bias[oo] : 0.f;
@@ -150,7 +176,7 @@ __device__ __forceinline__ void matvec(const float* __restrict__ Wt, int K, int 
       if (addin) v += addin[s * lda + oo];
       out[s * ldo + oo] = v;
     }
-    __syncthreads();
+    csync();
   } else {
     for (int o = tid; o < N; o += GT) {
       float acc[NS];
@@ -168,12 +194,66 @@ __device__ __forceinline__ void matvec(const float* __restrict__ Wt, int K, int 
 #pragma unroll
       for (int s = 0; s < NS; ++s) out[s * ldo + o] = acc[s] + b + (addin ? addin[s * lda + o] : 0.f);
     }
-    __syncthreads();
+    csync();
   }
 }
 
+// Streamed matvec: the [K][N] matrix arrives in row chunks through the shared-memory ring (cp.async.bulk
+// issued by the producer warp in consumption order).  Each thread owns 4 consecutive outputs (LDS.128) for a
+// 4-row slice of every chunk; slices are reduced through `part` at the end.  Requires N%4==0, N<=1024, K%4==0.
 template <int NS>
-__global__ void __launch_bounds__(GT) gen_kernel(GenArgs a) {
+__device__ __forceinline__ void matvec_stream(StreamCtx& cx, int K, int N, const float* xin, int ldx, float* part,
+                                              float* out, int ldo, const float* __restrict__ bias) {
+  const int tid = threadIdx.x;
+  const int NV = N >> 2;
+  const int nsl = GT / NV;
+  const int rpc = nsl << 2;
+  const int sl = tid / NV, o4 = tid - sl * NV;
+  const bool active = sl < nsl;
+  float acc[NS][4];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0.f;
+  for (int r0 = 0; r0 < K; r0 += rpc) {
+    const uint32_t stage = cx.it % RING_STAGES, parity = (cx.it / RING_STAGES) & 1;
+    tc::mbar_wait(cx.full0 + 8 * stage, parity);
+    const int rows = min(rpc, K - r0);
+    if (active && sl * 4 < rows) {
+      const float* w = cx.ring + stage * (RING_STAGE_BYTES / 4) + (sl * 4) * N + o4 * 4;
+      const float* xp = xin + r0 + sl * 4;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float4 wv = *reinterpret_cast<const float4*>(w + r * N);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const float x = xp[s * ldx + r];
+          acc[s][0] = fmaf(wv.x, x, acc[s][0]);
+          acc[s][1] = fmaf(wv.y, x, acc[s][1]);
+          acc[s][2] = fmaf(wv.z, x, acc[s][2]);
+          acc[s][3] = fmaf(wv.w, x, acc[s][3]);
+        }
+      }
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) tc::mbar_arrive(cx.empty0 + 8 * stage);
+    ++cx.it;
+  }
+  if (active) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      *reinterpret_cast<float4*>(part + (sl * NS + s) * N + o4 * 4) = make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
+  }
+  csync();
+  for (int i = tid; i < NS * N; i += GT) {
+    const int s = i / N, oo = i - s * N;
+    float v = bias ? bias[oo] : 0.f;
+    for (int q = 0; q < nsl; ++q) v += part[(q * NS + s) * N + oo];
+    out[s * ldo + oo] = v;
+  }
+  csync();
+}
+
+template <int NS, bool STREAM>
+__global__ void __launch_bounds__(GT + (STREAM ? 32 : 0)) gen_kernel(GenArgs a) {
   extern __shared__ float sm[];
   const GenLayout& L = a.lay;
   const int tid = threadIdx.x;
@@ -186,8 +266,46 @@ __global__ void __launch_bounds__(GT) gen_kernel(GenArgs a) {
   float* zv = av + NS * 2 * maxw;       // [NS][maxw]
   float* skipv = zv + NS * maxw;        // [NS][maxw] skip accumulator / head ping
   float* hv = skipv + NS * maxw;        // [NS][maxw] head pong
-  float* part = hv + NS * maxw;         // [GT*NS] + spare
+  float* part = hv + NS * maxw;         // [1024*NS]
   __shared__ int s_sample[NS];
+  __shared__ __align__(8) uint64_t s_bars[2 * RING_STAGES];
+  StreamCtx cx;
+  cx.it = 0;
+  if (STREAM) {
+    uint8_t* ring_g = reinterpret_cast<uint8_t*>(part + 1024 * NS);
+    ring_g += (128 - (tc::smem_u32(ring_g) & 127)) & 127;
+    cx.ring = reinterpret_cast<const float*>(ring_g);
+    cx.full0 = tc::smem_u32(&s_bars[0]);
+    cx.empty0 = tc::smem_u32(&s_bars[RING_STAGES]);
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < RING_STAGES; ++i) {
+        tc::mbar_init(cx.full0 + 8 * i, 1);
+        tc::mbar_init(cx.empty0 + 8 * i, GT / 32);
+      }
+      tc::fence_barrier_init();
+    }
+    __syncthreads();   // all 288 threads, once
+    if (threadIdx.x >= GT) {
+      // ---- producer warp: stream every step's weights in consumption order ----
+      if (threadIdx.x == GT) {
+        const uint8_t* sbase = reinterpret_cast<const uint8_t*>(a.state);
+        const uint32_t ring_s = tc::smem_u32(ring_g);
+        uint32_t it = 0;
+        for (int step = 0; step < a.n_steps; ++step)
+          for (int c = 0; c < a.n_chunks; ++c, ++it) {
+            const GenChunk ch = a.chunks[c];
+            const uint32_t stage = it % RING_STAGES;
+            tc::mbar_wait(cx.empty0 + 8 * stage, ((it / RING_STAGES) & 1) ^ 1);
+            tc::mbar_arrive_expect_tx(cx.full0 + 8 * stage, ch.bytes);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             ring_s + stage * RING_STAGE_BYTES),
+                         "l"(reinterpret_cast<uint64_t>(sbase + ch.off)), "r"(ch.bytes), "r"(cx.full0 + 8 * stage)
+                         : "memory");
+          }
+      }
+      return;
+    }
+  }
   __shared__ float s_redv[GT / 32];
   __shared__ int s_redi[GT / 32];
 
@@ -233,7 +351,7 @@ __global__ void __launch_bounds__(GT) gen_kernel(GenArgs a) {
         s_redv[tid >> 5] = bv;
         s_redi[tid >> 5] = bi;
       }
-      __syncthreads();
+      csync();
       if (tid == 0) {
         for (int w = 1; w < GT / 32; ++w)
           if (s_redv[w] > bv || (s_redv[w] == bv && s_redi[w] < bi)) {
@@ -243,9 +361,9 @@ __global__ void __launch_bounds__(GT) gen_kernel(GenArgs a) {
         s_sample[s] = bi;
         if (a.out) a.out[(int64_t)stream * a.n_steps + step] = bi;
       }
-      __syncthreads();
+      csync();
     }
-    __syncthreads();
+    csync();
 
     // ---- 2. causal stack (wavenet.py:281-286 on one-hot taps == table gather) -----
     {
@@ -264,7 +382,7 @@ __global__ void __launch_bounds__(GT) gen_kernel(GenArgs a) {
         }
         xv[s * maxw + r] = v;
       }
-      __syncthreads();
+      csync();
       if (kc1 > 0)
         for (int i = tid; i < NS; i += GT) {
           const int stream = s0 + i;
@@ -285,13 +403,14 @@ __global__ void __launch_bounds__(GT) gen_kernel(GenArgs a) {
           if (stream < L.n) v = j == kc1 ? xv[s * maxw + c] : hist[((int64_t)stream * kc1 + j) * Cin + c];
           cin[s * (L.kc * maxw) + j * Cin + c] = v;
         }
-        __syncthreads();
+        csync();
         for (int i = tid; i < NS * kc1 * Cin; i += GT) {  // slide history
           const int s = i / (kc1 * Cin), rem = i - s * kc1 * Cin;
           const int stream = s0 + s;
           if (stream < L.n) hist[(int64_t)stream * kc1 * Cin + rem] = cin[s * (L.kc * maxw) + Cin + rem];
         }
-        matvec<NS>(st + L.cw[ci], L.kc * Cin, Cout, cin, L.kc * maxw, part, xv, maxw, st + L.cb[ci], nullptr, 0);
+        if (STREAM) matvec_stream<NS>(cx, L.kc * Cin, Cout, cin, L.kc * maxw, part, xv, maxw, st + L.cb[ci]);
+        else matvec<NS>(st + L.cw[ci], L.kc * Cin, Cout, cin, L.kc * maxw, part, xv, maxw, st + L.cb[ci], nullptr, 0);
       }
     }
 
@@ -320,7 +439,7 @@ __global__ void __launch_bounds__(GT) gen_kernel(GenArgs a) {
         }
         xin[s * (L.k * maxw) + rem] = v;
       }
-      __syncthreads();
+      csync();
       if (len > 0)
         for (int i = tid; i < NS * R; i += GT) {  // push x[t] into the ring (roll, faster_wavenet.py:90-91)
           const int s = i / R, c = i - s * R;
@@ -328,16 +447,18 @@ __global__ void __launch_bounds__(GT) gen_kernel(GenArgs a) {
           if (stream < L.n) ring[((int64_t)stream * len + (int)(t % len)) * R + c] = xv[s * maxw + c];
         }
       const int G = ly.G;
-      matvec<NS>(st + ly.wa, kR, 2 * G, xin, L.k * maxw, part, av, 2 * maxw, st + ly.ba, nullptr, 0);
+      if (STREAM) matvec_stream<NS>(cx, kR, 2 * G, xin, L.k * maxw, part, av, 2 * maxw, st + ly.ba);
+      else matvec<NS>(st + ly.wa, kR, 2 * G, xin, L.k * maxw, part, av, 2 * maxw, st + ly.ba, nullptr, 0);
       for (int i = tid; i < NS * G; i += GT) {  // z = tanh(a_f) * sigmoid(a_g), wavenet.py:351
         const int s = i / G, g = i - s * G;
         const float f = av[s * 2 * maxw + g], gg = av[s * 2 * maxw + G + g];
         zv[s * maxw + g] = tanhf(f) * (1.f / (1.f + expf(-gg)));
       }
-      __syncthreads();
+      csync();
       // [x_next | skip] = WB^T z + b (+ x | + skip_acc)
       // proj and skip share one [G][R+S] matrix; addin differs, so run them as two calls on column ranges
-      matvec<NS>(st + ly.wb, G, R + L.S, zv, maxw, part, av, 2 * maxw, st + ly.bb, nullptr, 0);
+      if (STREAM) matvec_stream<NS>(cx, G, R + L.S, zv, maxw, part, av, 2 * maxw, st + ly.bb);
+      else matvec<NS>(st + ly.wb, G, R + L.S, zv, maxw, part, av, 2 * maxw, st + ly.bb, nullptr, 0);
       for (int i = tid; i < NS * (R + L.S); i += GT) {
         const int s = i / (R + L.S), o = i - s * (R + L.S);
         const float v = av[s * 2 * maxw + o];
@@ -346,7 +467,7 @@ __global__ void __launch_bounds__(GT) gen_kernel(GenArgs a) {
         else
           skipv[s * maxw + (o - R)] += v;        // sum_skip_connections += z, faster_wavenet.py:100
       }
-      __syncthreads();
+      csync();
     }
 
     // ---- 4. head (faster_wavenet.py:105-113: ELU; wavenet.py:584-593: ReLU) --------
@@ -359,8 +480,9 @@ __global__ void __launch_bounds__(GT) gen_kernel(GenArgs a) {
         const float v = hin[s * maxw + c];
         hin[s * maxw + c] = a.head_elu ? (v > 0.f ? v : expm1f(v)) : fmaxf(v, 0.f);
       }
-      __syncthreads();
-      matvec<NS>(st + L.hw[hi], Cin, Cout, hin, maxw, part, hout, maxw, st + L.hb[hi], nullptr, 0);
+      csync();
+      if (STREAM) matvec_stream<NS>(cx, Cin, Cout, hin, maxw, part, hout, maxw, st + L.hb[hi]);
+      else matvec<NS>(st + L.hw[hi], Cin, Cout, hin, maxw, part, hout, maxw, st + L.hb[hi], nullptr, 0);
       float* tmp = hin;
       hin = hout;
       hout = tmp;
@@ -371,7 +493,7 @@ __global__ void __launch_bounds__(GT) gen_kernel(GenArgs a) {
       const int stream = s0 + s;
       if (stream < L.n) cur_logits[(int64_t)stream * L.Q + q] = hin[s * maxw + q];
     }
-    __syncthreads();
+    csync();
   }
 
   if (a.probs) {
@@ -388,41 +510,41 @@ __global__ void __launch_bounds__(GT) gen_kernel(GenArgs a) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
       if ((tid & 31) == 0) s_redv[tid >> 5] = m;
-      __syncthreads();
+      csync();
       m = s_redv[0];
       for (int w = 1; w < GT / 32; ++w) m = fmaxf(m, s_redv[w]);
-      __syncthreads();
+      csync();
       float sum = 0.f;
       for (int q = tid; q < L.Q; q += GT) sum += expf(lg[q] - m);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
       if ((tid & 31) == 0) s_redv[tid >> 5] = sum;
-      __syncthreads();
+      csync();
       sum = 0.f;
       for (int w = 0; w < GT / 32; ++w) sum += s_redv[w];
-      __syncthreads();
+      csync();
       for (int q = tid; q < L.Q; q += GT) a.probs[(int64_t)stream * L.Q + q] = expf(lg[q] - m) / sum;
     }
   }
 }
 
-size_t gen_smem_bytes(const GenLayout& L, int NS) {
+size_t gen_smem_bytes(const GenLayout& L, int NS, bool stream) {
   const size_t maxw = L.maxw;
   size_t f = NS * maxw                               // xv
              + NS * (L.k + L.kc) * maxw              // xin
              + NS * 2 * maxw                         // av
              + NS * maxw * 3                         // zv, skipv, hv
-             + (size_t)GT * NS + 64;                 // part
-  return f * sizeof(float);
+             + (size_t)1024 * NS + 64;               // part
+  return f * sizeof(float) + (stream ? RING_STAGES * RING_STAGE_BYTES + 128 : 0);
 }
 
-template <int NS>
+template <int NS, bool STREAM>
 int launch_gen(const GenArgs& a, cudaStream_t s) {
-  const size_t smem = gen_smem_bytes(a.lay, NS);
+  const size_t smem = gen_smem_bytes(a.lay, NS, STREAM);
   WN_REQUIRE(smem <= 227 * 1024, WN_EINVAL, "generator: network too wide for shared memory (%zu bytes)", smem);
-  WN_CHECK_CUDA(cudaFuncSetAttribute(gen_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  WN_CHECK_CUDA(cudaFuncSetAttribute(gen_kernel<NS, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (a.lay.n + NS - 1) / NS;
-  gen_kernel<NS><<<grid, GT, smem, s>>>(a);
+  gen_kernel<NS, STREAM><<<grid, GT + (STREAM ? 32 : 0), smem, s>>>(a);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
@@ -437,9 +559,14 @@ int pick_ns(const wn_gen* g) {
 
 int run_gen(wn_gen* g, GenArgs& a, cudaStream_t s) {
   const int ns = pick_ns(g);
-  if (ns == 1) return launch_gen<1>(a, s);
-  if (ns == 2) return launch_gen<2>(a, s);
-  return launch_gen<4>(a, s);
+  if (g->stream_ok && gen_smem_bytes(g->lay, ns, true) <= 227 * 1024) {
+    if (ns == 1) return launch_gen<1, true>(a, s);
+    if (ns == 2) return launch_gen<2, true>(a, s);
+    return launch_gen<4, true>(a, s);
+  }
+  if (ns == 1) return launch_gen<1, false>(a, s);
+  if (ns == 2) return launch_gen<2, false>(a, s);
+  return launch_gen<4, false>(a, s);
 }
 
 }  // namespace
@@ -506,6 +633,30 @@ extern "C" int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen**
   L.idx_hist = take((int64_t)n_streams * (L.kc - 1) + 1);
   L.cur_logits = take((int64_t)n_streams * L.Q);
   L.layers_dev = take((int64_t)(sizeof(GenLayerOff) * L.L + 3) / 4);
+  // streaming schedule: every matrix of one step, in consumption order, cut into row chunks of <= 16 KB
+  g->stream_ok = true;
+  auto add_matrix = [&](int64_t off_floats, int K, int N) {
+    if (N % 4 != 0 || K % 4 != 0 || N > 1024) {
+      g->stream_ok = false;
+      return;
+    }
+    const int rpc = 4 * (GT_HOST / (N / 4));
+    for (int r0 = 0; r0 < K; r0 += rpc) {
+      const int rows = K - r0 < rpc ? K - r0 : rpc;
+      GenChunk c;
+      c.off = (uint64_t)(off_floats + (int64_t)r0 * N) * 4;
+      c.bytes = (uint32_t)(rows * N * 4);
+      c.pad = 0;
+      g->chunks.push_back(c);
+    }
+  };
+  for (int i = 1; i < c.n_causal; ++i) add_matrix(L.cw[i], L.kc * L.causal_ch[i - 1], L.causal_ch[i]);
+  for (int l = 0; l < L.L; ++l) {
+    add_matrix(g->layers[l].wa, L.k * L.R, 2 * g->layers[l].G);
+    add_matrix(g->layers[l].wb, g->layers[l].G, L.R + L.S);
+  }
+  for (int i = 0; i < L.n_head; ++i) add_matrix(L.hw[i], L.head_ch[i], L.head_ch[i + 1]);
+  L.chunks_dev = take((int64_t)(sizeof(GenChunk) * g->chunks.size() + 3) / 4 + 4);
   L.maxw = (maxw + 3) / 4 * 4;
   L.total = off;
   *out = g;
@@ -598,6 +749,9 @@ extern "C" int wn_gen_prime(wn_gen* g, const float* params, const int32_t* windo
   WN_CHECK_LAUNCH();
   WN_CHECK_CUDA(cudaMemcpyAsync(S + L.layers_dev, g->layers.data(), sizeof(GenLayerOff) * L.L, cudaMemcpyHostToDevice,
                                 s));
+  if (!g->chunks.empty())
+    WN_CHECK_CUDA(cudaMemcpyAsync(S + L.chunks_dev, g->chunks.data(), sizeof(GenChunk) * g->chunks.size(),
+                                  cudaMemcpyHostToDevice, s));
   g->primed = true;
   g->t = Win;
   g->steps_done = 0;
@@ -609,6 +763,8 @@ static void fill_args(wn_gen* g, GenArgs* a) {
   a->state = g->state;
   a->lay = g->lay;
   a->layers = (const GenLayerOff*)(g->state + g->lay.layers_dev);
+  a->chunks = (const GenChunk*)(g->state + g->lay.chunks_dev);
+  a->n_chunks = (int)g->chunks.size();
   a->t0 = g->t;
   a->head_elu = g->head_act == 1;
 }
