@@ -13,11 +13,12 @@
 #include "wn_common.h"
 #include "wn_tc.cuh"
 
-static const int GT_HOST = 256;   // consumer threads per CTA (must equal GT below)
+static const int GT_HOST = 512;   // consumer threads per CTA (must equal GT below)
 
 struct GenLayerOff {
   int64_t wa, ba, wb, bb, ring;  // offsets (floats) into the state buffer
   int G, dilation, ring_len;
+  int has_ba, has_bb, pad;         // biases present (absent ones are not even loaded)
 };
 
 struct GenLayout {
@@ -27,6 +28,7 @@ struct GenLayout {
   int64_t emb = 0, emb_b = 0;
   int64_t cw[WN_MAX_CAUSAL], cb[WN_MAX_CAUSAL], chist[WN_MAX_CAUSAL];  // causal layers >= 1
   int64_t hw[WN_MAX_HEAD], hb[WN_MAX_HEAD];
+  int has_hb = 0, has_cb = 0;
   int64_t idx_hist = 0;     // int32 [n][kc-1]
   int64_t cur_logits = 0;   // [n][Q]
   int64_t layers_dev = 0;   // GenLayerOff[L] copied to device (as raw bytes)
@@ -57,12 +59,14 @@ struct wn_gen {
 
 namespace {
 
-constexpr int GT = 256;  // consumer threads per CTA (the streaming variant adds one producer warp)
-constexpr int RING_STAGES = 8;
-constexpr int RING_STAGE_BYTES = 16384;
+constexpr int GT = 512;  // consumer threads per CTA (the streaming variant adds one producer warp)
+constexpr int RING_STAGES = 4;
+constexpr int RING_STAGE_BYTES = 32768;
+constexpr int RING_GROUPS = 1;      // 4*nsl-row groups per chunk
+constexpr int MAX_CHUNKS = 512;     // schedule entries kept in shared memory
 
 // barrier among the GT consumer threads only (the producer warp never joins)
-__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // consumer-side view of the weight ring
 struct StreamCtx {
@@ -198,12 +202,15 @@ __device__ __forceinline__ void matvec(const float* __restrict__ Wt, int K, int 
   }
 }
 
-// Streamed matvec: the [K][N] matrix arrives in row chunks through the shared-memory ring (cp.async.bulk
-// issued by the producer warp in consumption order).  Each thread owns 4 consecutive outputs (LDS.128) for a
-// 4-row slice of every chunk; slices are reduced through `part` at the end.  Requires N%4==0, N<=1024, K%4==0.
+// Streamed matvec (partials only): the [K][N] matrix arrives in row chunks through the shared-memory ring
+// (cp.async.bulk issued by the producer warp in consumption order).  Each thread owns 4 consecutive outputs
+// (LDS.128) for a 4-row slice of every row group; slice partial sums land in part[(slice*NS + s)*N + o] and the
+// CALLER reduces them after a csync (so it can fuse its own epilogue).  Input rows [0,Ksplit) come from xa, the
+// rest from xb (past taps | current sample) -- no gather pass.  Requires N%4==0, N<=1024, K%4==0, Ksplit%4==0.
+// Returns the number of slices.
 template <int NS>
-__device__ __forceinline__ void matvec_stream(StreamCtx& cx, int K, int N, const float* xin, int ldx, float* part,
-                                              float* out, int ldo, const float* __restrict__ bias) {
+__device__ __forceinline__ int matvec_stream(StreamCtx& cx, int K, int N, const float* xa, int lda, const float* xb,
+                                             int ldb, int Ksplit, float* part) {
   const int tid = threadIdx.x;
   const int NV = N >> 2;
   const int nsl = GT / NV;
@@ -213,23 +220,34 @@ __device__ __forceinline__ void matvec_stream(StreamCtx& cx, int K, int N, const
   float acc[NS][4];
 #pragma unroll
   for (int s = 0; s < NS; ++s) acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0.f;
-  for (int r0 = 0; r0 < K; r0 += rpc) {
+  for (int r0 = 0; r0 < K; r0 += RING_GROUPS * rpc) {
     const uint32_t stage = cx.it % RING_STAGES, parity = (cx.it / RING_STAGES) & 1;
     tc::mbar_wait(cx.full0 + 8 * stage, parity);
-    const int rows = min(rpc, K - r0);
-    if (active && sl * 4 < rows) {
-      const float* w = cx.ring + stage * (RING_STAGE_BYTES / 4) + (sl * 4) * N + o4 * 4;
-      const float* xp = xin + r0 + sl * 4;
+    const int rows = min(RING_GROUPS * rpc, K - r0);
+    if (active) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const float4 wv = *reinterpret_cast<const float4*>(w + r * N);
+      for (int gp = 0; gp < RING_GROUPS; ++gp) {
+        const int rr = gp * rpc + sl * 4;
+        if (rr < rows) {
+          const float* w = cx.ring + stage * (RING_STAGE_BYTES / 4) + rr * N + o4 * 4;
+          const int kk = r0 + rr;
+          const float* xp = kk < Ksplit ? xa + kk : xb + (kk - Ksplit);
+          const int ld = kk < Ksplit ? lda : ldb;
+          float4 wv[4];
 #pragma unroll
-        for (int s = 0; s < NS; ++s) {
-          const float x = xp[s * ldx + r];
-          acc[s][0] = fmaf(wv.x, x, acc[s][0]);
-          acc[s][1] = fmaf(wv.y, x, acc[s][1]);
-          acc[s][2] = fmaf(wv.z, x, acc[s][2]);
-          acc[s][3] = fmaf(wv.w, x, acc[s][3]);
+          for (int r = 0; r < 4; ++r) wv[r] = *reinterpret_cast<const float4*>(w + r * N);
+#pragma unroll
+          for (int s = 0; s < NS; ++s) {
+            const float4 x = *reinterpret_cast<const float4*>(xp + s * ld);
+            acc[s][0] = fmaf(wv[0].x, x.x, acc[s][0]); acc[s][1] = fmaf(wv[0].y, x.x, acc[s][1]);
+            acc[s][2] = fmaf(wv[0].z, x.x, acc[s][2]); acc[s][3] = fmaf(wv[0].w, x.x, acc[s][3]);
+            acc[s][0] = fmaf(wv[1].x, x.y, acc[s][0]); acc[s][1] = fmaf(wv[1].y, x.y, acc[s][1]);
+            acc[s][2] = fmaf(wv[1].z, x.y, acc[s][2]); acc[s][3] = fmaf(wv[1].w, x.y, acc[s][3]);
+            acc[s][0] = fmaf(wv[2].x, x.z, acc[s][0]); acc[s][1] = fmaf(wv[2].y, x.z, acc[s][1]);
+            acc[s][2] = fmaf(wv[2].z, x.z, acc[s][2]); acc[s][3] = fmaf(wv[2].w, x.z, acc[s][3]);
+            acc[s][0] = fmaf(wv[3].x, x.w, acc[s][0]); acc[s][1] = fmaf(wv[3].y, x.w, acc[s][1]);
+            acc[s][2] = fmaf(wv[3].z, x.w, acc[s][2]); acc[s][3] = fmaf(wv[3].w, x.w, acc[s][3]);
+          }
         }
       }
     }
@@ -242,14 +260,7 @@ __device__ __forceinline__ void matvec_stream(StreamCtx& cx, int K, int N, const
     for (int s = 0; s < NS; ++s)
       *reinterpret_cast<float4*>(part + (sl * NS + s) * N + o4 * 4) = make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
   }
-  csync();
-  for (int i = tid; i < NS * N; i += GT) {
-    const int s = i / N, oo = i - s * N;
-    float v = bias ? bias[oo] : 0.f;
-    for (int q = 0; q < nsl; ++q) v += part[(q * NS + s) * N + oo];
-    out[s * ldo + oo] = v;
-  }
-  csync();
+  return nsl;
 }
 
 template <int NS, bool STREAM>
@@ -266,13 +277,17 @@ __global__ void __launch_bounds__(GT + (STREAM ? 32 : 0)) gen_kernel(GenArgs a) 
   float* zv = av + NS * 2 * maxw;       // [NS][maxw]
   float* skipv = zv + NS * maxw;        // [NS][maxw] skip accumulator / head ping
   float* hv = skipv + NS * maxw;        // [NS][maxw] head pong
-  float* part = hv + NS * maxw;         // [1024*NS]
+  float* part = hv + NS * maxw;         // [4*GT*NS]
+  float* xpast = part + 4 * GT * NS;      // [NS][L][(k-1)R] past taps of every layer (STREAM only)
+  __shared__ GenLayerOff s_layers[STREAM ? 128 : 1];
   __shared__ int s_sample[NS];
   __shared__ __align__(8) uint64_t s_bars[2 * RING_STAGES];
+  __shared__ GenChunk s_sched[STREAM ? MAX_CHUNKS : 1];
   StreamCtx cx;
   cx.it = 0;
   if (STREAM) {
-    uint8_t* ring_g = reinterpret_cast<uint8_t*>(part + 1024 * NS);
+    uint8_t* ring_g = reinterpret_cast<uint8_t*>(xpast + NS * L.L * (L.k - 1) * L.R);
+    for (int i = threadIdx.x; i < L.L; i += blockDim.x) s_layers[i] = a.layers[i];
     ring_g += (128 - (tc::smem_u32(ring_g) & 127)) & 127;
     cx.ring = reinterpret_cast<const float*>(ring_g);
     cx.full0 = tc::smem_u32(&s_bars[0]);
@@ -284,6 +299,7 @@ __global__ void __launch_bounds__(GT + (STREAM ? 32 : 0)) gen_kernel(GenArgs a) 
       }
       tc::fence_barrier_init();
     }
+    for (int i = threadIdx.x; i < a.n_chunks; i += blockDim.x) s_sched[i] = a.chunks[i];
     __syncthreads();   // all 288 threads, once
     if (threadIdx.x >= GT) {
       // ---- producer warp: stream every step's weights in consumption order ----
@@ -293,7 +309,7 @@ __global__ void __launch_bounds__(GT + (STREAM ? 32 : 0)) gen_kernel(GenArgs a) 
         uint32_t it = 0;
         for (int step = 0; step < a.n_steps; ++step)
           for (int c = 0; c < a.n_chunks; ++c, ++it) {
-            const GenChunk ch = a.chunks[c];
+            const GenChunk ch = s_sched[c];
             const uint32_t stage = it % RING_STAGES;
             tc::mbar_wait(cx.empty0 + 8 * stage, ((it / RING_STAGES) & 1) ^ 1);
             tc::mbar_arrive_expect_tx(cx.full0 + 8 * stage, ch.bytes);
@@ -409,83 +425,178 @@ __global__ void __launch_bounds__(GT + (STREAM ? 32 : 0)) gen_kernel(GenArgs a) 
           const int stream = s0 + s;
           if (stream < L.n) hist[(int64_t)stream * kc1 * Cin + rem] = cin[s * (L.kc * maxw) + Cin + rem];
         }
-        if (STREAM) matvec_stream<NS>(cx, L.kc * Cin, Cout, cin, L.kc * maxw, part, xv, maxw, st + L.cb[ci]);
-        else matvec<NS>(st + L.cw[ci], L.kc * Cin, Cout, cin, L.kc * maxw, part, xv, maxw, st + L.cb[ci], nullptr, 0);
+        if (STREAM) {
+          const int nsc = matvec_stream<NS>(cx, L.kc * Cin, Cout, cin, L.kc * maxw, cin, L.kc * maxw, L.kc * Cin, part);
+          csync();
+          for (int i = tid; i < NS * Cout; i += GT) {
+            const int s = i / Cout, o = i - s * Cout;
+            float v = L.has_cb ? st[L.cb[ci] + o] : 0.f;
+            for (int q = 0; q < nsc; ++q) v += part[(q * NS + s) * Cout + o];
+            xv[s * maxw + o] = v;
+          }
+          csync();
+        } else matvec<NS>(st + L.cw[ci], L.kc * Cin, Cout, cin, L.kc * maxw, part, xv, maxw, st + L.cb[ci], nullptr, 0);
       }
     }
 
-    // ---- 3. residual layers (ResidualConvLayer._forward, wavenet.py:350-356) -------
-    const int R = L.R;
-    for (int i = tid; i < NS * L.S; i += GT) skipv[(i / L.S) * maxw + (i % L.S)] = 0.f;
-    for (int l = 0; l < L.L; ++l) {
-      const GenLayerOff ly = a.layers[l];
-      const int len = ly.ring_len;
-      float* ring = st + ly.ring;  // [n][len][R]
-      const int kR = L.k * R;
-      // gather taps: xin[s][tap*R + c], tap k-1 = current sample (wavenet.py:288-290)
-      for (int i = tid; i < NS * kR; i += GT) {
-        const int s = i / kR, rem = i - s * kR;
-        const int tap = rem / R, c = rem - tap * R;
-        const int stream = s0 + s;
-        float v = 0.f;
-        if (stream < L.n) {
-          if (tap == L.k - 1) {
-            v = xv[s * maxw + c];
-          } else {
+    float* hin;
+    float* hout;
+    if constexpr (STREAM) {
+      // ---- 3s. residual layers, streamed weights (ResidualConvLayer._forward, wavenet.py:350-356) ----
+      const int R = L.R, S = L.S;
+      const int pastw = (L.k - 1) * R;                 // past-tap floats per layer per stream
+      // all past taps x_l[t-(k-1-tap)d] of this step are already in the rings: fetch them in one go
+      {
+        const int per = pastw >> 2;                    // float4 per (stream, layer)
+        for (int i = tid; i < NS * L.L * per; i += GT) {
+          const int v4 = i % per, sl_ = i / per;
+          const int l = sl_ % L.L, s = sl_ / L.L;
+          const int stream = s0 + s;
+          const GenLayerOff& ly = s_layers[l];
+          const int tap = (v4 * 4) / R, c = v4 * 4 - tap * R;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (stream < L.n) {
+            const int len = ly.ring_len;
             const int64_t tau = t - (int64_t)(L.k - 1 - tap) * ly.dilation;
             const int slot = (int)(((tau % len) + len) % len);
-            v = ring[((int64_t)stream * len + slot) * R + c];
+            v = *reinterpret_cast<const float4*>(st + ly.ring + ((int64_t)stream * len + slot) * R + c);
           }
+          *reinterpret_cast<float4*>(xpast + (s * L.L + l) * pastw + v4 * 4) = v;
         }
-        xin[s * (L.k * maxw) + rem] = v;
       }
+      for (int i = tid; i < NS * S; i += GT) skipv[(i / S) * maxw + (i % S)] = 0.f;
       csync();
-      if (len > 0)
-        for (int i = tid; i < NS * R; i += GT) {  // push x[t] into the ring (roll, faster_wavenet.py:90-91)
+      for (int l = 0; l < L.L; ++l) {
+        const GenLayerOff& ly = s_layers[l];
+        const int len = ly.ring_len, G = ly.G;
+        for (int i = tid; i < NS * R; i += GT) {        // push x[t] into the ring (roll, faster_wavenet.py:90-91)
           const int s = i / R, c = i - s * R;
           const int stream = s0 + s;
-          if (stream < L.n) ring[((int64_t)stream * len + (int)(t % len)) * R + c] = xv[s * maxw + c];
+          if (stream < L.n) st[ly.ring + ((int64_t)stream * len + (int)(t % len)) * R + c] = xv[s * maxw + c];
         }
-      const int G = ly.G;
-      if (STREAM) matvec_stream<NS>(cx, kR, 2 * G, xin, L.k * maxw, part, av, 2 * maxw, st + ly.ba);
-      else matvec<NS>(st + ly.wa, kR, 2 * G, xin, L.k * maxw, part, av, 2 * maxw, st + ly.ba, nullptr, 0);
-      for (int i = tid; i < NS * G; i += GT) {  // z = tanh(a_f) * sigmoid(a_g), wavenet.py:351
-        const int s = i / G, g = i - s * G;
-        const float f = av[s * 2 * maxw + g], gg = av[s * 2 * maxw + G + g];
-        zv[s * maxw + g] = tanhf(f) * (1.f / (1.f + expf(-gg)));
+        const int nsa = matvec_stream<NS>(cx, L.k * R, 2 * G, xpast + l * pastw, L.L * pastw, xv, maxw, pastw, part);
+        csync();
+        for (int i = tid; i < NS * G; i += GT) {        // reduce slices + gate (wavenet.py:351)
+          const int s = i / G, g = i - s * G;
+          float f = ly.has_ba ? st[ly.ba + g] : 0.f, gg = ly.has_ba ? st[ly.ba + G + g] : 0.f;
+          for (int q = 0; q < nsa; ++q) {
+            f += part[(q * NS + s) * 2 * G + g];
+            gg += part[(q * NS + s) * 2 * G + G + g];
+          }
+          zv[s * maxw + g] = tanhf(f) * (1.f / (1.f + expf(-gg)));
+        }
+        csync();
+        const int N2 = R + S;
+        const int nsb = matvec_stream<NS>(cx, G, N2, zv, maxw, zv, maxw, G, part);
+        csync();
+        for (int i = tid; i < NS * N2; i += GT) {       // reduce slices + residual / skip accumulation
+          const int s = i / N2, o = i - s * N2;
+          float v = ly.has_bb ? st[ly.bb + o] : 0.f;
+          for (int q = 0; q < nsb; ++q) v += part[(q * NS + s) * N2 + o];
+          if (o < R)
+            xv[s * maxw + o] += v;                      // output = projection_block + x, wavenet.py:354
+          else
+            skipv[s * maxw + (o - R)] += v;             // sum_skip_connections += z, faster_wavenet.py:100
+        }
+        csync();
       }
-      csync();
-      // [x_next | skip] = WB^T z + b (+ x | + skip_acc)
-      // proj and skip share one [G][R+S] matrix; addin differs, so run them as two calls on column ranges
-      if (STREAM) matvec_stream<NS>(cx, G, R + L.S, zv, maxw, part, av, 2 * maxw, st + ly.bb);
-      else matvec<NS>(st + ly.wb, G, R + L.S, zv, maxw, part, av, 2 * maxw, st + ly.bb, nullptr, 0);
-      for (int i = tid; i < NS * (R + L.S); i += GT) {
-        const int s = i / (R + L.S), o = i - s * (R + L.S);
-        const float v = av[s * 2 * maxw + o];
-        if (o < R)
-          xv[s * maxw + o] += v;                 // output = projection_block + x, wavenet.py:354
-        else
-          skipv[s * maxw + (o - R)] += v;        // sum_skip_connections += z, faster_wavenet.py:100
-      }
-      csync();
-    }
-
-    // ---- 4. head (faster_wavenet.py:105-113: ELU; wavenet.py:584-593: ReLU) --------
-    float* hin = skipv;
-    float* hout = hv;
-    for (int hi = 0; hi < L.n_head; ++hi) {
-      const int Cin = L.head_ch[hi], Cout = L.head_ch[hi + 1];
-      for (int i = tid; i < NS * Cin; i += GT) {
-        const int s = i / Cin, c = i - s * Cin;
+      // ---- 4s. head (faster_wavenet.py:105-113: ELU; wavenet.py:584-593: ReLU) ----
+      hin = skipv;
+      hout = hv;
+      for (int i = tid; i < NS * S; i += GT) {
+        const int s = i / S, c = i - s * S;
         const float v = hin[s * maxw + c];
         hin[s * maxw + c] = a.head_elu ? (v > 0.f ? v : expm1f(v)) : fmaxf(v, 0.f);
       }
       csync();
-      if (STREAM) matvec_stream<NS>(cx, Cin, Cout, hin, maxw, part, hout, maxw, st + L.hb[hi]);
-      else matvec<NS>(st + L.hw[hi], Cin, Cout, hin, maxw, part, hout, maxw, st + L.hb[hi], nullptr, 0);
-      float* tmp = hin;
-      hin = hout;
-      hout = tmp;
+      for (int hi = 0; hi < L.n_head; ++hi) {
+        const int Cin = L.head_ch[hi], Cout = L.head_ch[hi + 1];
+        const int nsh = matvec_stream<NS>(cx, Cin, Cout, hin, maxw, hin, maxw, Cin, part);
+        csync();
+        const bool last = hi == L.n_head - 1;
+        for (int i = tid; i < NS * Cout; i += GT) {
+          const int s = i / Cout, o = i - s * Cout;
+          float v = L.has_hb ? st[L.hb[hi] + o] : 0.f;
+          for (int q = 0; q < nsh; ++q) v += part[(q * NS + s) * Cout + o];
+          if (!last) v = a.head_elu ? (v > 0.f ? v : expm1f(v)) : fmaxf(v, 0.f);   // activation of the next layer
+          hout[s * maxw + o] = v;
+        }
+        csync();
+        float* tmp = hin;
+        hin = hout;
+        hout = tmp;
+      }
+    } else {
+      // ---- 3. residual layers (ResidualConvLayer._forward, wavenet.py:350-356) -------
+      const int R = L.R;
+      for (int i = tid; i < NS * L.S; i += GT) skipv[(i / L.S) * maxw + (i % L.S)] = 0.f;
+      for (int l = 0; l < L.L; ++l) {
+        const GenLayerOff ly = a.layers[l];
+        const int len = ly.ring_len;
+        float* ring = st + ly.ring;  // [n][len][R]
+        const int kR = L.k * R;
+        // gather taps: xin[s][tap*R + c], tap k-1 = current sample (wavenet.py:288-290)
+        for (int i = tid; i < NS * kR; i += GT) {
+          const int s = i / kR, rem = i - s * kR;
+          const int tap = rem / R, c = rem - tap * R;
+          const int stream = s0 + s;
+          float v = 0.f;
+          if (stream < L.n) {
+            if (tap == L.k - 1) {
+              v = xv[s * maxw + c];
+            } else {
+              const int64_t tau = t - (int64_t)(L.k - 1 - tap) * ly.dilation;
+              const int slot = (int)(((tau % len) + len) % len);
+              v = ring[((int64_t)stream * len + slot) * R + c];
+            }
+          }
+          xin[s * (L.k * maxw) + rem] = v;
+        }
+        csync();
+        if (len > 0)
+          for (int i = tid; i < NS * R; i += GT) {  // push x[t] into the ring (roll, faster_wavenet.py:90-91)
+            const int s = i / R, c = i - s * R;
+            const int stream = s0 + s;
+            if (stream < L.n) ring[((int64_t)stream * len + (int)(t % len)) * R + c] = xv[s * maxw + c];
+          }
+        const int G = ly.G;
+        matvec<NS>(st + ly.wa, kR, 2 * G, xin, L.k * maxw, part, av, 2 * maxw, st + ly.ba, nullptr, 0);
+        for (int i = tid; i < NS * G; i += GT) {  // z = tanh(a_f) * sigmoid(a_g), wavenet.py:351
+          const int s = i / G, g = i - s * G;
+          const float f = av[s * 2 * maxw + g], gg = av[s * 2 * maxw + G + g];
+          zv[s * maxw + g] = tanhf(f) * (1.f / (1.f + expf(-gg)));
+        }
+        csync();
+        // [x_next | skip] = WB^T z + b (+ x | + skip_acc)
+        // proj and skip share one [G][R+S] matrix; addin differs, so run them as two calls on column ranges
+        matvec<NS>(st + ly.wb, G, R + L.S, zv, maxw, part, av, 2 * maxw, st + ly.bb, nullptr, 0);
+        for (int i = tid; i < NS * (R + L.S); i += GT) {
+          const int s = i / (R + L.S), o = i - s * (R + L.S);
+          const float v = av[s * 2 * maxw + o];
+          if (o < R)
+            xv[s * maxw + o] += v;                 // output = projection_block + x, wavenet.py:354
+          else
+            skipv[s * maxw + (o - R)] += v;        // sum_skip_connections += z, faster_wavenet.py:100
+        }
+        csync();
+      }
+
+      // ---- 4. head (faster_wavenet.py:105-113: ELU; wavenet.py:584-593: ReLU) --------
+      hin = skipv;
+      hout = hv;
+      for (int hi = 0; hi < L.n_head; ++hi) {
+        const int Cin = L.head_ch[hi], Cout = L.head_ch[hi + 1];
+        for (int i = tid; i < NS * Cin; i += GT) {
+          const int s = i / Cin, c = i - s * Cin;
+          const float v = hin[s * maxw + c];
+          hin[s * maxw + c] = a.head_elu ? (v > 0.f ? v : expm1f(v)) : fmaxf(v, 0.f);
+        }
+        csync();
+        matvec<NS>(st + L.hw[hi], Cin, Cout, hin, maxw, part, hout, maxw, st + L.hb[hi], nullptr, 0);
+        float* tmp = hin;
+        hin = hout;
+        hout = tmp;
+      }
     }
     // hin now holds the logits for the next sample
     for (int i = tid; i < NS * L.Q; i += GT) {
@@ -534,7 +645,8 @@ size_t gen_smem_bytes(const GenLayout& L, int NS, bool stream) {
              + NS * (L.k + L.kc) * maxw              // xin
              + NS * 2 * maxw                         // av
              + NS * maxw * 3                         // zv, skipv, hv
-             + (size_t)1024 * NS + 64;               // part
+             + (size_t)4 * GT * NS + 64;             // part
+  if (stream) f += (size_t)NS * L.L * (L.k - 1) * L.R;   // xpast
   return f * sizeof(float) + (stream ? RING_STAGES * RING_STAGE_BYTES + 128 : 0);
 }
 
@@ -559,7 +671,7 @@ int pick_ns(const wn_gen* g) {
 
 int run_gen(wn_gen* g, GenArgs& a, cudaStream_t s) {
   const int ns = pick_ns(g);
-  if (g->stream_ok && gen_smem_bytes(g->lay, ns, true) <= 227 * 1024) {
+  if (g->stream_ok && gen_smem_bytes(g->lay, ns, true) <= 208 * 1024) {   // + ~16 KB static (schedule, layer table)
     if (ns == 1) return launch_gen<1, true>(a, s);
     if (ns == 2) return launch_gen<2, true>(a, s);
     return launch_gen<4, true>(a, s);
@@ -589,6 +701,8 @@ extern "C" int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen**
   L.n_causal = c.n_causal;
   L.n_head = (int)h->head.size();
   L.L = (int)h->layers.size();
+  L.has_hb = !c.softmax_no_bias;
+  L.has_cb = !c.causal_no_bias;
   int maxw = h->Q > h->S ? h->Q : h->S;
   for (int i = 0; i < c.n_causal; ++i) {
     L.causal_ch[i] = c.causal_channels[i];
@@ -617,6 +731,9 @@ extern "C" int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen**
     o.G = ly.G;
     o.dilation = ly.dilation;
     o.ring_len = (L.k - 1) * ly.dilation;
+    o.has_ba = ly.wf.b_off >= 0;
+    o.has_bb = ly.proj.b_off >= 0;
+    o.pad = 0;
     o.wa = take((int64_t)L.k * L.R * 2 * ly.G);
     o.ba = take(2 * ly.G);
     o.wb = take((int64_t)ly.G * (L.R + L.S));
@@ -636,11 +753,11 @@ extern "C" int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen**
   // streaming schedule: every matrix of one step, in consumption order, cut into row chunks of <= 16 KB
   g->stream_ok = true;
   auto add_matrix = [&](int64_t off_floats, int K, int N) {
-    if (N % 4 != 0 || K % 4 != 0 || N > 1024) {
+    if (N % 4 != 0 || K % 4 != 0 || N > 2048) {
       g->stream_ok = false;
       return;
     }
-    const int rpc = 4 * (GT_HOST / (N / 4));
+    const int rpc = 1 * 4 * (GT_HOST / (N / 4));   // RING_GROUPS groups of 4*nsl rows
     for (int r0 = 0; r0 < K; r0 += rpc) {
       const int rows = K - r0 < rpc ? K - r0 : rpc;
       GenChunk c;
@@ -656,6 +773,7 @@ extern "C" int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen**
     add_matrix(g->layers[l].wb, g->layers[l].G, L.R + L.S);
   }
   for (int i = 0; i < L.n_head; ++i) add_matrix(L.hw[i], L.head_ch[i], L.head_ch[i + 1]);
+  if (g->chunks.size() > 512 || L.L > 128 || L.R % 4 != 0) g->stream_ok = false;   // MAX_CHUNKS, s_layers, float4 taps
   L.chunks_dev = take((int64_t)(sizeof(GenChunk) * g->chunks.size() + 3) / 4 + 4);
   L.maxw = (maxw + 3) / 4 * 4;
   L.total = off;
