@@ -209,6 +209,7 @@ static void plan_tape(const wn_handle* h, int B, int W, Tape* t) {
   t->dout[1] = take(P * h->R);
   t->dz = take(P * gmax);
   t->dafg = take(P * 2 * gmax);
+  t->dzs = take((int64_t)L * P * gmax);
   int cmax = 0;
   for (int i = 0; i < c.n_causal; ++i) cmax = cmax > c.causal_channels[i] ? cmax : c.causal_channels[i];
   if (c.n_causal > 1) {

@@ -73,6 +73,7 @@ struct Tape {
   int64_t dout[2] = {0, 0};           // [P][R]
   int64_t dz = 0;                     // [P][Gmax]
   int64_t dafg = 0;                   // [P][2Gmax]
+  int64_t dzs = 0;                    // [L][P][Gmax]  dskip . Ws_l for every layer (tensor-core backward)
   int64_t dcx[2] = {0, 0};            // [P][max causal width] (only when n_causal > 1)
   int64_t loss_acc = 0;               // 2 doubles
   // tensor-core path: TF32-rounded, K-major weight copies (rebuilt every forward)

@@ -313,6 +313,12 @@ struct GemmTcArgs {
   int slab_row_off[MAX_SLABS];
   int slab_idx[MAX_SLABS];
   int tiles_per_seq, num_tiles;
+  int y_slab_cols;         // >0: column block c goes to Y + (c / y_slab_cols) * y_slab_stride, column c % y_slab_cols
+  int64_t y_slab_stride;
+  // gate-backward epilogue (N == G): result is dz; writes da_f | da_g into dafg[row][0..2G) instead of Y
+  const float* gate_tfsg;  // [rows][2G] tanh | sigmoid, or null
+  float* gate_dafg;
+  int gate_zp;
 };
 
 template <int BN>
@@ -419,6 +425,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * BN + c0, v);
         tmem_ld_wait();
         if (valid && c0 < a.N) {
+          float* ydst = yrow + c0;
+          if (a.y_slab_cols > 0) ydst = a.Y + (int64_t)(c0 / a.y_slab_cols) * a.y_slab_stride + orow * a.ldy + (c0 % a.y_slab_cols);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             float o[4] = {__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
@@ -443,15 +451,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               o[2] = mm.z > 0.f ? o[2] : 0.f;
               o[3] = mm.w > 0.f ? o[3] : 0.f;
             }
+            if (a.gate_tfsg) {
+              // dz -> (da_f, da_g) = dz*sg*(1-tf^2), dz*tf*sg*(1-sg); rows inside the zero prefix get none (Q1)
+              const float* trow = a.gate_tfsg + orow * (2 * a.N);
+              const float4 tf = *reinterpret_cast<const float4*>(trow + cc);
+              const float4 sg = *reinterpret_cast<const float4*>(trow + a.N + cc);
+              const float live = t >= a.gate_zp ? 1.f : 0.f;
+              float4 df, dg;
+              df.x = live * o[0] * sg.x * (1.f - tf.x * tf.x), dg.x = live * o[0] * tf.x * sg.x * (1.f - sg.x);
+              df.y = live * o[1] * sg.y * (1.f - tf.y * tf.y), dg.y = live * o[1] * tf.y * sg.y * (1.f - sg.y);
+              df.z = live * o[2] * sg.z * (1.f - tf.z * tf.z), dg.z = live * o[2] * tf.z * sg.z * (1.f - sg.z);
+              df.w = live * o[3] * sg.w * (1.f - tf.w * tf.w), dg.w = live * o[3] * tf.w * sg.w * (1.f - sg.w);
+              float* drow = a.gate_dafg + orow * (2 * a.N);
+              *reinterpret_cast<float4*>(drow + cc) = df;
+              *reinterpret_cast<float4*>(drow + a.N + cc) = dg;
+              continue;
+            }
             if (a.accumulate) {
-              const float4 yy = *reinterpret_cast<const float4*>(yrow + cc);
+              const float4 yy = *reinterpret_cast<const float4*>(ydst + 4 * c);
               o[0] += yy.x, o[1] += yy.y, o[2] += yy.z, o[3] += yy.w;
             }
             if (a.round_out) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) o[e] = tf32_rna(o[e]);
             }
-            *reinterpret_cast<float4*>(yrow + cc) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(ydst + 4 * c) = make_float4(o[0], o[1], o[2], o[3]);
           }
         }
       }
@@ -473,13 +497,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 struct WgradTcArgs {
   int rows_it, num_seq;    // iteration rows per sequence
   int a_row_off, a_c0;
-  int nb_slab, nb_sub;     // B slabs (taps) and 32-channel sub-tiles per slab
-  int b_row_off[2];
-  int slab_tap[2];
-  float* dW0;              // rows [0, m_split)
-  float* dW1;              // rows [m_split, m_valid)
+  int nb_slab, nb_sub;     // B slabs (taps or layers) and 32-channel sub-tiles per slab
+  int b_row_off[4];
+  int b_slab_idx[4];       // 4-D map coordinate of each slab
+  float* dW0[4];           // per slab: rows [0, m_split)
+  float* dW1[4];           // per slab: rows [m_split, m_valid)
   int m_split, m_valid;
-  int64_t sn, sk, st;      // element (m, slab, c) -> + m*sn + c*sk + slab_tap[slab]*st
+  int64_t sn, sk;          // element (m, slab, c) -> dW[slab] + m*sn + c*sk
   int chunks_per_seq, num_chunks;
   int dbg_lbo, dbg_sbo, dbg_kstep, dbg_major;   // descriptor probing (wn_debug_wgrad); 0 = defaults
 };
@@ -555,7 +579,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         for (int i = 0; i < 4; ++i) tma_load_4d(st + i * WG_SUB, &tm_a, full(s), a.a_c0 + i * SUBK, a.a_row_off + t0, b, 0);
         for (int sl = 0; sl < a.nb_slab; ++sl)
           for (int i = 0; i < a.nb_sub; ++i)
-            tma_load_4d(st + (4 + sl * a.nb_sub + i) * WG_SUB, &tm_b, full(s), i * SUBK, a.b_row_off[sl] + t0, b, 0);
+            tma_load_4d(st + (4 + sl * a.nb_sub + i) * WG_SUB, &tm_b, full(s), i * SUBK, a.b_row_off[sl] + t0, b,
+                        a.b_slab_idx[sl]);
       }
     }
   } else if (warp == 1) {
@@ -592,9 +617,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
       tmem_ld_wait();
       if (m < a.m_valid) {
-        float* wrow = m < a.m_split ? a.dW0 + (int64_t)m * a.sn : a.dW1 + (int64_t)(m - a.m_split) * a.sn;
         const int sl = c0 / nb, cbase = c0 % nb;
-        wrow += (int64_t)a.slab_tap[sl] * a.st;
+        float* wrow = m < a.m_split ? a.dW0[sl] + (int64_t)m * a.sn : a.dW1[sl] + (int64_t)(m - a.m_split) * a.sn;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           float val = __uint_as_float(v[i]);
@@ -705,6 +729,11 @@ struct TcEpilogue {
   int ldr = 0;
   const float* mask = nullptr;
   int ldm = 0, mask_rows_in = 0, mask_row_off = 0;
+  int y_slab_cols = 0;
+  int64_t y_slab_stride = 0;
+  const float* gate_tfsg = nullptr;
+  float* gate_dafg = nullptr;
+  int gate_zp = 0;
 };
 
 // Y[(b, t)][0..N) = epi( sum_s A[slab_idx[s]][b][t + row_off[s]][:] . Wt[:, s*K ..]^T ),  Wt is [N][ns*K] (TF32-rounded)
@@ -732,6 +761,11 @@ int tc_gemm(const wn_handle* h, const TcOperand& A, int ns, const int* slab_idx,
   g.ldm = e.ldm;
   g.mask_rows_in = e.mask_rows_in;
   g.mask_row_off = e.mask_row_off;
+  g.y_slab_cols = e.y_slab_cols;
+  g.y_slab_stride = e.y_slab_stride;
+  g.gate_tfsg = e.gate_tfsg;
+  g.gate_dafg = e.gate_dafg;
+  g.gate_zp = e.gate_zp;
   g.rows_out = rows_out;
   g.nslab = ns;
   g.ksub = A.K / SUBK;
@@ -746,19 +780,20 @@ int tc_gemm(const wn_handle* h, const TcOperand& A, int ns, const int* slab_idx,
   return launch_gemm<256>(ta, tb, g, h->sm_count, s);
 }
 
-// dW(m, tap, c) += sum_{b,t} dY[b][a_row_off + t][a_c0 + m] * X[b][b_row_off[s] + t][c]   for m < m_valid (<= 128)
+// dW[slab](m, c) += sum_{b,t} dY[b][a_row_off + t][a_c0 + m] * X[slab_idx[s]][b][b_row_off[s] + t][c]   for m < m_valid (<= 128)
 static int g_dbg[4] = {0, 0, 0, 0};
 int tc_wgrad(const wn_handle* h, const TcOperand& dY, int a_row_off, int a_c0, int m_valid, const TcOperand& X, int nb_slab,
-             const int* b_row_off, const int* slab_tap, int rows_it, float* dW0, float* dW1, int m_split, int64_t sn,
-             int64_t sk, int64_t st, cudaStream_t s) {
+             const int* b_row_off, const int* b_slab_idx, float* const* dW0, float* const* dW1, int m_split, int rows_it,
+             int64_t sn, int64_t sk, cudaStream_t s) {
   const int NB = nb_slab * X.K;
-  WN_REQUIRE(X.K % 32 == 0 && (NB == 64 || NB == 128 || NB == 256) && nb_slab <= 2, WN_EINVAL,
+  WN_REQUIRE(X.K % 32 == 0 && (NB == 64 || NB == 128 || NB == 256) && nb_slab <= 4, WN_EINVAL,
              "tc_wgrad: unsupported shape X.K=%d slabs=%d", X.K, nb_slab);
   CUtensorMap ta, tb;
   WN_TRY(make_map_4d(&ta, dY.ptr, dY.K, dY.rows_in, dY.num_seq, 1, dY.K, (uint64_t)dY.rows_in * dY.K,
                      (uint64_t)dY.rows_in * dY.num_seq * dY.K, WG_KC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-  WN_TRY(make_map_4d(&tb, X.ptr, X.K, X.rows_in, X.num_seq, 1, X.K, (uint64_t)X.rows_in * X.K,
-                     (uint64_t)X.rows_in * X.num_seq * X.K, WG_KC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  const int64_t xstride = X.nslab > 1 ? X.slab_stride : (int64_t)X.rows_in * X.num_seq * X.K;
+  WN_TRY(make_map_4d(&tb, X.ptr, X.K, X.rows_in, X.num_seq, X.nslab, X.K, (uint64_t)X.rows_in * X.K, xstride, WG_KC,
+                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   WgradTcArgs g;
   memset(&g, 0, sizeof(g));
   g.rows_it = rows_it;
@@ -769,15 +804,14 @@ int tc_wgrad(const wn_handle* h, const TcOperand& dY, int a_row_off, int a_c0, i
   g.nb_sub = X.K / 32;
   for (int i = 0; i < nb_slab; ++i) {
     g.b_row_off[i] = b_row_off[i];
-    g.slab_tap[i] = slab_tap[i];
+    g.b_slab_idx[i] = b_slab_idx ? b_slab_idx[i] : 0;
+    g.dW0[i] = dW0[i];
+    g.dW1[i] = dW1 ? dW1[i] : nullptr;
   }
-  g.dW0 = dW0;
-  g.dW1 = dW1;
   g.m_split = m_split;
   g.m_valid = m_valid;
   g.sn = sn;
   g.sk = sk;
-  g.st = st;
   g.chunks_per_seq = (rows_it + WG_KC - 1) / WG_KC;
   g.num_chunks = g.chunks_per_seq * dY.num_seq;
   g.dbg_lbo = g_dbg[0];
@@ -903,7 +937,7 @@ int tc_forward_head(wn_handle* h, const float* params, int T, bool external, cud
   return WN_OK;
 }
 
-// Backward of head + residual stack on tensor cores (gate derivative and embedding scatter stay SIMT).
+// Backward of head + residual stack on tensor cores (embedding scatter stays SIMT).
 // Requires a tape written by tc_forward_residual(save_gates) and tc_forward_head.
 int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s) {
   const Tape& t = h->tape;
@@ -925,11 +959,10 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
     const float* Ain = first ? ws + t.skip : ws + t.hbuf[i - 1];
     TcOperand dY{d, cp.out_ch, T, B, 1, 0};
     TcOperand X{Ain, cp.in_ch, rin, B, 1, 0};
-    const int tap0 = 0;
     for (int m0 = 0; m0 < cp.out_ch; m0 += 128) {
       const int mv = cp.out_ch - m0 < 128 ? cp.out_ch - m0 : 128;
-      WN_TRY(tc_wgrad(h, dY, 0, m0, mv, X, 1, &aoff, &tap0, T, grads + cp.w_off + (int64_t)m0 * cp.in_ch, nullptr, 128,
-                      cp.in_ch, 1, 0, s));
+      float* dw = grads + cp.w_off + (int64_t)m0 * cp.in_ch;
+      WN_TRY(tc_wgrad(h, dY, 0, m0, mv, X, 1, &aoff, nullptr, &dw, nullptr, 128, T, cp.in_ch, 1, s));
     }
     if (cp.b_off >= 0) WN_TRY(simt_colsum(d, (int64_t)B * T, cp.out_ch, grads + cp.b_off, s));
     if (first && h->head_external) return WN_OK;
@@ -949,37 +982,72 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
   }
   const float* dskip = d;   // [B*T][S]
   TcOperand DS{dskip, S, T, B, 1, 0};
+  const int wt = W - T, nwt = -(W - T);
+  const int64_t zstride = L > 1 ? t.z[1] - t.z[0] : (int64_t)P * G;
+  // ---- skip path for ALL layers at once (mirror of the forward skip GEMM) ----
+  //  dzs[l] = dskip . Ws_l   : GEMMs with N = 4 layers x 64, each column block written to its layer slab
+  //  dWs_l  = dskip^T . z_l  : wgrad with the B operand gathered from 4 z slabs per launch
+  for (int l0 = 0; l0 < L; l0 += 4) {
+    const int nl = L - l0 < 4 ? L - l0 : 4;
+    TcEpilogue e;
+    e.y_slab_cols = G;
+    e.y_slab_stride = (int64_t)P * G;
+    WN_TRY(tc_gemm(h, DS, 1, nullptr, &nwt, W, ws + t.tc_wst + (int64_t)l0 * G * S, nl * G, e,
+                   ws + t.dzs + (int64_t)l0 * P * G, G, s));
+    if (nl == 3) continue;   // NB must be 64/128/256: handled below layer by layer
+    TcOperand Z{ws + t.z[0], G, W, B, L, zstride};
+    int boff[4], bidx[4];
+    float* dws[4];
+    for (int m0 = 0; m0 < S; m0 += 128) {
+      const int mv = S - m0 < 128 ? S - m0 : 128;
+      for (int j = 0; j < nl; ++j) {
+        boff[j] = wt;
+        bidx[j] = l0 + j;
+        dws[j] = grads + h->layers[l0 + j].skip.w_off + (int64_t)m0 * G;
+      }
+      WN_TRY(tc_wgrad(h, DS, 0, m0, mv, Z, nl, boff, bidx, dws, nullptr, 128, T, G, 1, s));
+    }
+  }
+  if (L % 4 == 3) {
+    for (int l = L - 3; l < L; ++l) {
+      TcOperand Z{ws + t.z[l], G, W, B, 1, 0};
+      for (int m0 = 0; m0 < S; m0 += 128) {
+        const int mv = S - m0 < 128 ? S - m0 : 128;
+        float* dw = grads + h->layers[l].skip.w_off + (int64_t)m0 * G;
+        WN_TRY(tc_wgrad(h, DS, 0, m0, mv, Z, 1, &wt, nullptr, &dw, nullptr, 128, T, G, 1, s));
+      }
+    }
+  }
   // ---- residual layers ----
   int dt = 0;
   const float* dout = nullptr;
   for (int l = L - 1; l >= 0; --l) {
     const ResLayer& ly = h->layers[l];
     const int zp = wn_zero_prefix(W, ly.dilation, 2);
-    TcOperand Z{ws + t.z[l], G, W, B, 1, 0};
-    const int tap0 = 0, wt = W - T, nwt = -(W - T);
+    const float* dzs = ws + t.dzs + (int64_t)l * P * G;
     if (dout) {
+      // dz = dout . Wp + dzs_l, gate derivative fused into the epilogue -> dafg
       TcOperand DO{dout, R, W, B, 1, 0};
       TcEpilogue e;
+      e.Rsd = dzs;
+      e.ldr = G;
+      e.gate_tfsg = ws + t.tfsg[l];
+      e.gate_dafg = ws + t.dafg;
+      e.gate_zp = zp;
       WN_TRY(tc_gemm(h, DO, 1, nullptr, &zero, W, ws + t.tc_wpt + (int64_t)l * G * R, G, e, ws + t.dz, G, s));
-      WN_TRY(tc_wgrad(h, DO, 0, 0, R, Z, 1, &zero, &tap0, W, grads + ly.proj.w_off, nullptr, 128, G, 1, 0, s));
+      TcOperand Z{ws + t.z[l], G, W, B, 1, 0};
+      float* dw = grads + ly.proj.w_off;
+      WN_TRY(tc_wgrad(h, DO, 0, 0, R, Z, 1, &zero, nullptr, &dw, nullptr, 128, W, G, 1, s));
+    } else {
+      WN_TRY(simt_gate_backward(ws + t.tfsg[l], dzs, ws + t.dafg, P, W, G, zp, s));
     }
-    {
-      TcEpilogue e;
-      e.accumulate = dout != nullptr;
-      WN_TRY(tc_gemm(h, DS, 1, nullptr, &nwt, W, ws + t.tc_wst + (int64_t)l * G * S, G, e, ws + t.dz, G, s));
-      for (int m0 = 0; m0 < S; m0 += 128) {
-        const int mv = S - m0 < 128 ? S - m0 : 128;
-        WN_TRY(tc_wgrad(h, DS, 0, m0, mv, Z, 1, &wt, &tap0, T, grads + ly.skip.w_off + (int64_t)m0 * G, nullptr, 128, G, 1,
-                        0, s));
-      }
-    }
-    WN_TRY(simt_gate_backward(ws + t.tfsg[l], ws + t.dz, ws + t.dafg, P, W, G, zp, s));
     TcOperand DA{ws + t.dafg, 2 * G, W, B, 1, 0};
     {
       TcOperand X{ws + t.x[l], R, W, B, 1, 0};
       const int boff[2] = {-ly.dilation, 0};
-      const int taps[2] = {0, 1};
-      WN_TRY(tc_wgrad(h, DA, 0, 0, 2 * G, X, 2, boff, taps, W, grads + ly.wf.w_off, grads + ly.wg.w_off, G, 2 * R, 2, 1, s));
+      float* d0[2] = {grads + ly.wf.w_off + 0, grads + ly.wf.w_off + 1};   // (o, c, tap): tap is the fastest index
+      float* d1[2] = {grads + ly.wg.w_off + 0, grads + ly.wg.w_off + 1};
+      WN_TRY(tc_wgrad(h, DA, 0, 0, 2 * G, X, 2, boff, nullptr, d0, d1, G, W, 2 * R, 2, s));
     }
     {
       float* dnew = ws + t.dout[dt];
@@ -1007,7 +1075,7 @@ extern "C" int wn_debug_wgrad(wn_handle* h, const float* dY, int Kd, const float
   TcOperand A{dY, Kd, rows, nseq, 1, 0};
   TcOperand B{X, Kx, rows, nseq, 1, 0};
   const int zero = 0;
-  int rc = tc_wgrad(h, A, 0, 0, 128, B, 1, &zero, &zero, rows, dW, nullptr, 128, Kx, 1, 0, (cudaStream_t)stream);
+  int rc = tc_wgrad(h, A, 0, 0, 128, B, 1, &zero, nullptr, &dW, nullptr, 128, rows, Kx, 1, (cudaStream_t)stream);
   g_dbg[0] = g_dbg[1] = g_dbg[2] = g_dbg[3] = 0;
   return rc;
 }
