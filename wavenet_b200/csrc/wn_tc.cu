@@ -326,7 +326,8 @@ struct GemmCfg {
   static constexpr int STAGE = SUB_A + BN * 128;
   static constexpr int STAGES = (200 * 1024) / STAGE > 6 ? 6 : (200 * 1024) / STAGE;
   static constexpr int BAR = STAGES * STAGE;
-  static constexpr int SMEM = BAR + 256 + 1024;
+  static constexpr int STG = BAR + 256;            // 8 epilogue warps x 4 KB transpose buffers
+  static constexpr int SMEM = STG + 8 * 4096 + 1024;
 };
 
 template <int BN>
@@ -405,17 +406,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
   } else {
     const int q = warp & 3, half = (warp - 2) >> 2;
-    const int row = q * 32 + lane;
     constexpr int CH = BN / 64;   // 32-column chunks per warp
+    uint8_t* stg = gbase + Cfg::STG + (warp - 2) * 4096;   // [32 rows][128 B], 16-byte chunks XOR-swizzled by row
+    const int cc4 = (lane & 7) * 4;                         // column (within the 32-col block) this lane owns when coalesced
     for (int j = 0; j < n_local; ++j) {
       const int tile = blockIdx.x + j * gridDim.x;
       const int ab = j & 1, aph = (j >> 1) & 1;
-      const int b = tile / a.tiles_per_seq, t = (tile % a.tiles_per_seq) * TM + row;
-      const bool valid = t < a.rows_out;
-      const int64_t orow = (int64_t)b * a.rows_out + t;
-      float* yrow = a.Y + orow * a.ldy;
-      const float* rrow = a.Rsd ? a.Rsd + orow * a.ldr : nullptr;
-      const float* mrow = a.mask ? a.mask + ((int64_t)b * a.mask_rows_in + a.mask_row_off + t) * a.ldm : nullptr;
+      const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM + q * 32;
       mbar_wait(acc_full(ab), aph);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -424,60 +421,95 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * BN + c0, v);
         tmem_ld_wait();
-        if (valid && c0 < a.N) {
-          float* ydst = yrow + c0;
-          if (a.y_slab_cols > 0) ydst = a.Y + (int64_t)(c0 / a.y_slab_cols) * a.y_slab_stride + orow * a.ldy + (c0 % a.y_slab_cols);
+        if (c0 >= a.N) continue;
+        // row-per-lane -> smem -> 4 full 128-byte rows per instruction (coalesced global traffic)
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float o[4] = {__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
-                          __uint_as_float(v[4 * c + 3])};
-            const int cc = c0 + 4 * c;
-            if (a.bias) {
-              const float4 bb = *reinterpret_cast<const float4*>(a.bias + cc);
-              o[0] += bb.x, o[1] += bb.y, o[2] += bb.z, o[3] += bb.w;
-            }
-            if (a.relu) {
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+              make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        __syncwarp();
+        const int col = c0 + cc4;
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.bias) bb = *reinterpret_cast<const float4*>(a.bias + col);
+        float* ybase = a.Y;
+        int ycol = col;
+        if (a.y_slab_cols > 0) {
+          ybase += (int64_t)(c0 / a.y_slab_cols) * a.y_slab_stride;
+          ycol = col % a.y_slab_cols;
+        }
+        // phase 1: issue every global load of this 32x32 block (memory-level parallelism), phase 2: math + stores.
+        // Mode-specific branches keep only the needed register arrays alive (no spills).
+        const int rsub = lane >> 3;
+        const uint8_t* srow = stg + (((lane & 7)) << 4);
+        if (a.gate_tfsg) {
+          float4 r4[8], tf4[8], sg4[8];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
-            }
-            if (rrow) {
-              const float4 rr = *reinterpret_cast<const float4*>(rrow + cc);
-              o[0] += rr.x, o[1] += rr.y, o[2] += rr.z, o[3] += rr.w;
-            }
-            if (mrow) {
-              const float4 mm = *reinterpret_cast<const float4*>(mrow + cc);
-              o[0] = mm.x > 0.f ? o[0] : 0.f;
-              o[1] = mm.y > 0.f ? o[1] : 0.f;
-              o[2] = mm.z > 0.f ? o[2] : 0.f;
-              o[3] = mm.w > 0.f ? o[3] : 0.f;
-            }
-            if (a.gate_tfsg) {
-              // dz -> (da_f, da_g) = dz*sg*(1-tf^2), dz*tf*sg*(1-sg); rows inside the zero prefix get none (Q1)
-              const float* trow = a.gate_tfsg + orow * (2 * a.N);
-              const float4 tf = *reinterpret_cast<const float4*>(trow + cc);
-              const float4 sg = *reinterpret_cast<const float4*>(trow + a.N + cc);
-              const float live = t >= a.gate_zp ? 1.f : 0.f;
-              float4 df, dg;
-              df.x = live * o[0] * sg.x * (1.f - tf.x * tf.x), dg.x = live * o[0] * tf.x * sg.x * (1.f - sg.x);
-              df.y = live * o[1] * sg.y * (1.f - tf.y * tf.y), dg.y = live * o[1] * tf.y * sg.y * (1.f - sg.y);
-              df.z = live * o[2] * sg.z * (1.f - tf.z * tf.z), dg.z = live * o[2] * tf.z * sg.z * (1.f - sg.z);
-              df.w = live * o[3] * sg.w * (1.f - tf.w * tf.w), dg.w = live * o[3] * tf.w * sg.w * (1.f - sg.w);
-              float* drow = a.gate_dafg + orow * (2 * a.N);
-              *reinterpret_cast<float4*>(drow + cc) = df;
-              *reinterpret_cast<float4*>(drow + a.N + cc) = dg;
-              continue;
-            }
-            if (a.accumulate) {
-              const float4 yy = *reinterpret_cast<const float4*>(ydst + 4 * c);
-              o[0] += yy.x, o[1] += yy.y, o[2] += yy.z, o[3] += yy.w;
-            }
-            if (a.round_out) {
+          for (int jj = 0; jj < 8; ++jj) {
+            const int t = min(t0 + jj * 4 + rsub, a.rows_out - 1);
+            const int64_t orow = (int64_t)b * a.rows_out + t;
+            r4[jj] = *reinterpret_cast<const float4*>(a.Rsd + orow * a.ldr + col);
+            const float* trow = a.gate_tfsg + orow * (2 * a.N);
+            tf4[jj] = *reinterpret_cast<const float4*>(trow + col);
+            sg4[jj] = *reinterpret_cast<const float4*>(trow + a.N + col);
+          }
 #pragma unroll
-              for (int e = 0; e < 4; ++e) o[e] = tf32_rna(o[e]);
+          for (int jj = 0; jj < 8; ++jj) {
+            const int rr = jj * 4 + rsub;
+            const int t = t0 + rr;
+            if (t >= a.rows_out) continue;
+            const int64_t orow = (int64_t)b * a.rows_out + t;
+            float4 o = *reinterpret_cast<const float4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+            o.x += r4[jj].x, o.y += r4[jj].y, o.z += r4[jj].z, o.w += r4[jj].w;
+            // dz -> (da_f, da_g) = dz*sg*(1-tf^2), dz*tf*sg*(1-sg); rows inside the zero prefix get none (Q1)
+            const float4 tf = tf4[jj], sg = sg4[jj];
+            const float live = t >= a.gate_zp ? 1.f : 0.f;
+            float4 df, dg;
+            df.x = live * o.x * sg.x * (1.f - tf.x * tf.x), dg.x = live * o.x * tf.x * sg.x * (1.f - sg.x);
+            df.y = live * o.y * sg.y * (1.f - tf.y * tf.y), dg.y = live * o.y * tf.y * sg.y * (1.f - sg.y);
+            df.z = live * o.z * sg.z * (1.f - tf.z * tf.z), dg.z = live * o.z * tf.z * sg.z * (1.f - sg.z);
+            df.w = live * o.w * sg.w * (1.f - tf.w * tf.w), dg.w = live * o.w * tf.w * sg.w * (1.f - sg.w);
+            float* drow = a.gate_dafg + orow * (2 * a.N);
+            *reinterpret_cast<float4*>(drow + col) = df;
+            *reinterpret_cast<float4*>(drow + a.N + col) = dg;
+          }
+        } else {
+          float4 r4[8], x4[8];   // x4: ReLU mask source or previous Y (never both)
+          const bool has_aux = a.mask != nullptr || a.accumulate;
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int t = min(t0 + jj * 4 + rsub, a.rows_out - 1);
+            const int64_t orow = (int64_t)b * a.rows_out + t;
+            if (a.Rsd) r4[jj] = *reinterpret_cast<const float4*>(a.Rsd + orow * a.ldr + col);
+            if (has_aux) {
+              const float* ap = a.mask ? a.mask + ((int64_t)b * a.mask_rows_in + a.mask_row_off + t) * a.ldm + col
+                                       : ybase + orow * a.ldy + ycol;
+              x4[jj] = *reinterpret_cast<const float4*>(ap);
             }
-            *reinterpret_cast<float4*>(ydst + 4 * c) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int rr = jj * 4 + rsub;
+            const int t = t0 + rr;
+            if (t >= a.rows_out) continue;
+            const int64_t orow = (int64_t)b * a.rows_out + t;
+            float4 o = *reinterpret_cast<const float4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+            o.x += bb.x, o.y += bb.y, o.z += bb.z, o.w += bb.w;
+            if (a.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+            if (a.Rsd) o.x += r4[jj].x, o.y += r4[jj].y, o.z += r4[jj].z, o.w += r4[jj].w;
+            if (a.mask) {
+              o.x = x4[jj].x > 0.f ? o.x : 0.f;
+              o.y = x4[jj].y > 0.f ? o.y : 0.f;
+              o.z = x4[jj].z > 0.f ? o.z : 0.f;
+              o.w = x4[jj].w > 0.f ? o.w : 0.f;
+            } else if (a.accumulate) {
+              o.x += x4[jj].x, o.y += x4[jj].y, o.z += x4[jj].z, o.w += x4[jj].w;
+            }
+            if (a.round_out) o.x = tf32_rna(o.x), o.y = tf32_rna(o.y), o.z = tf32_rna(o.z), o.w = tf32_rna(o.w);
+            *reinterpret_cast<float4*>(ybase + orow * a.ldy + ycol) = o;
           }
         }
+        (void)srow;
+        __syncwarp();
       }
       tcgen05_fence_before();
       mbar_arrive(acc_empty(ab));
