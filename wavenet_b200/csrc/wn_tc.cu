@@ -104,6 +104,31 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return y;
 }
 
+// Coalesced store of a 32-row x 32-column fp32 block held row-per-lane (lane r owns row r): the block goes
+// through a 2 KB per-warp XOR-swizzled staging buffer, 16 rows at a time, so that every STG.128 covers four
+// complete 128-byte rows instead of 32 partial sectors.
+__device__ __forceinline__ void store_block_coalesced(uint8_t* stg, const uint32_t (&v)[32], float* gblock, int64_t ld,
+                                                      int rows_valid, int lane) {
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    if ((lane >> 4) == hh) {
+      const int r = lane & 15;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(stg + r * 128 + ((c ^ (r & 7)) << 4)) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int rr = jj * 4 + (lane >> 3);
+      const int row = hh * 16 + rr;
+      const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+      if (row < rows_valid) *reinterpret_cast<uint4*>(gblock + (int64_t)row * ld + (lane & 7) * 4) = val;
+    }
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 struct LayerArgs {
   float* x_out;            // [B][W][64]
@@ -118,7 +143,8 @@ constexpr int L_B1 = 0;                       // 4 sub-tiles [128 x 32]  (64 KB)
 constexpr int L_B2 = 65536;                   // 2 sub-tiles [64 x 32]   (16 KB)
 constexpr int L_A = 81920;                    // 2 stages x 4 sub-tiles  (128 KB); Z aliases sub-tiles 0,1
 constexpr int L_BAR = L_A + 2 * 65536;        // barriers
-constexpr int L_SMEM = L_BAR + 256;
+constexpr int L_STG = L_BAR + 256;            // 8 epilogue warps x 2 KB store-transpose buffers
+constexpr int L_SMEM = L_STG + 8 * 2048;
 constexpr int L_THREADS = 64 + 256;           // producer warp, MMA warp, 8 epilogue warps
 
 __global__ void __launch_bounds__(L_THREADS, 1)
@@ -215,12 +241,12 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     const int q = warp & 3;               // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;     // which 32 of the 64 channels this warp handles
     const int row = q * 32 + lane;
+    uint8_t* stg = gbase + L_STG + (warp - 2) * 2048;
     for (int j = 0; j < n_local; ++j) {
       const int tile = blockIdx.x + j * gridDim.x;
       const int s = j & 1, ph = (j >> 1) & 1;
       const int b = tile / a.tiles_per_seq, t = (tile % a.tiles_per_seq) * TM + row;
       const bool valid = t < a.W;
-      const int64_t grow = ((int64_t)b * a.W + t) * 64 + half * 32;
       uint8_t* as_g = gbase + L_A + s * 65536;
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
       // ---- epilogue 1: gate ----
@@ -251,18 +277,19 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       fence_proxy_async();
       tcgen05_fence_before();
       mbar_arrive(z_full(s));
-      if (valid) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(a.z_out + grow + 4 * c) = make_uint4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
+      {
+        // global stores of this warp's 32x32 blocks (z, tanh, sigmoid), coalesced through the staging buffer
+        const int t_w0 = (tile % a.tiles_per_seq) * TM + q * 32;           // first row of the warp's block
+        const int rows_valid = a.W - t_w0;                                 // may be <= 0 or > 32
+        const int64_t gblk = ((int64_t)b * a.W + t_w0) * 64 + half * 32;
+        store_block_coalesced(stg, f, a.z_out + gblk, 64, rows_valid, lane);
         if (a.tfsg_out) {
-          float* trow_g = a.tfsg_out + ((int64_t)b * a.W + t) * 128 + half * 32;
+          float* tblk = a.tfsg_out + ((int64_t)b * a.W + t_w0) * 128 + half * 32;
+          uint32_t fs[32];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            *reinterpret_cast<float4*>(trow_g + 4 * c) =
-                make_float4(fsave[4 * c], fsave[4 * c + 1], fsave[4 * c + 2], fsave[4 * c + 3]);
-            *reinterpret_cast<uint4*>(trow_g + 64 + 4 * c) = make_uint4(g[4 * c], g[4 * c + 1], g[4 * c + 2], g[4 * c + 3]);
-          }
+          for (int i = 0; i < 32; ++i) fs[i] = __float_as_uint(fsave[i]);
+          store_block_coalesced(stg, fs, tblk, 128, rows_valid, lane);
+          store_block_coalesced(stg, g, tblk + 64, 128, rows_valid, lane);
         }
       }
       // ---- epilogue 2: projection + residual ----
@@ -284,10 +311,18 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           o.z += a.bias_p[half * 32 + 4 * c + 2];
           o.w += a.bias_p[half * 32 + 4 * c + 3];
         }
-        if (valid) *reinterpret_cast<float4*>(a.x_out + grow + 4 * c) = o;
+        g[4 * c] = __float_as_uint(o.x);
+        g[4 * c + 1] = __float_as_uint(o.y);
+        g[4 * c + 2] = __float_as_uint(o.z);
+        g[4 * c + 3] = __float_as_uint(o.w);
       }
+      // the stage (x(t) rows just read) can go back to the producer before the global stores are issued
       tcgen05_fence_before();
       mbar_arrive(a_empty(s));
+      {
+        const int t_w0 = (tile % a.tiles_per_seq) * TM + q * 32;
+        store_block_coalesced(stg, g, a.x_out + ((int64_t)b * a.W + t_w0) * 64 + half * 32, 64, a.W - t_w0, lane);
+      }
     }
   }
   tcgen05_fence_before();
