@@ -372,12 +372,13 @@ extern "C" int wn_forward_residual_block(wn_handle* h, const float* params, cons
   }
   if (h->prec == WN_PREC_TF32 && tc_layer_supported(h)) {
     WN_TRY(tc_forward_residual(h, params, s));
-    h->tape_has_tfsg = h->save_gates;
+    h->tape_has_tfsg = false;      // tensor-core tapes keep (z, sigmoid) only; the SIMT backward would recompute
     h->tape_tc = true;
   } else {
     WN_TRY(residual_forward_simt(h, params, s));
     h->tape_has_tfsg = true;
     h->tape_tc = false;
+    h->skip_is_relu = false;
   }
   const int L = (int)h->layers.size();
   if (out) WN_CHECK_CUDA(cudaMemcpyAsync(out, WS(t.x[L]), sizeof(float) * t.P * h->R, cudaMemcpyDeviceToDevice, s));
@@ -522,7 +523,7 @@ extern "C" int wn_backward(wn_handle* h, const float* params, float* grads, wn_s
   const int64_t P = t.P, rows = (int64_t)t.B * T;
   const int nh = (int)h->head.size();
   WN_CHECK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * h->flat_size, s));
-  if (h->prec == WN_PREC_TF32 && h->tape_tc && h->head_tc && h->tape_has_tfsg) {
+  if (h->prec == WN_PREC_TF32 && h->tape_tc && h->head_tc && h->save_gates) {
     WN_TRY(tc_backward(h, params, grads, s));
     if (h->head_external) return WN_OK;
     return causal_backward(h, params, grads, h->bwd_dout, s);
@@ -703,7 +704,10 @@ extern "C" int wn_backward(wn_handle* h, const float* params, float* grads, wn_s
 extern "C" int wn_forward_loss(wn_handle* h, const float* params, const int32_t* x, const int32_t* target, int T,
                                float* loss, float* logits_opt, wn_stream_t st) {
   WN_TRY(wn_forward_causal_block(h, params, x, nullptr, st));
-  WN_TRY(wn_forward_residual_block(h, params, nullptr, nullptr, nullptr, st));
+  h->fuse_head_relu = 1;
+  int rc = wn_forward_residual_block(h, params, nullptr, nullptr, nullptr, st);
+  h->fuse_head_relu = 0;
+  WN_TRY(rc);
   WN_TRY(wn_forward_softmax_block(h, params, nullptr, T, 0, logits_opt, st));
   if (target) WN_TRY(wn_cross_entropy(h, target, loss, st));
   return WN_OK;

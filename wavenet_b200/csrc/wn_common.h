@@ -108,6 +108,8 @@ struct wn_handle {
   bool tape_has_tfsg = false;      // tanh | sigmoid of every layer are on the tape
   bool head_tc = false;            // head activations on the tape came from the tensor-core head
   bool tape_tc = false;            // tape written by the tensor-core forward (stored head activations are post-ReLU)
+  int fuse_head_relu = 0;          // set by wn_forward_loss: nobody reads the raw skip sum, ReLU it in the skip GEMM
+  bool skip_is_relu = false;
   bool save_gates = true;          // tensor-core forward also stores tanh | sigmoid (needed by backward)
   const float* bwd_dout = nullptr; // gradient w.r.t. the causal output after the residual backward
 };
@@ -187,3 +189,5 @@ int tc_forward_residual(wn_handle* h, const float* params, cudaStream_t s);
 int tc_forward_head(wn_handle* h, const float* params, int T, bool external, cudaStream_t s);
 int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s);
 int simt_colsum(const float* a, int64_t rows, int C, float* out, cudaStream_t s);
+int simt_gate_backward_zs(const float* z, const float* sg, const float* dz, float* dafg, int64_t P, int W, int G, int zp,
+                          cudaStream_t s);

@@ -271,6 +271,26 @@ __global__ void gate_backward_kernel(const float* __restrict__ tfsg, const float
   dafg[p * 2 * G + G + gch] = dg;
 }
 
+// same derivative from (z, sigmoid) as stored by the tensor-core forward: tanh = z / sigmoid
+__global__ void gate_backward_zs_kernel(const float* __restrict__ z, const float* __restrict__ sg,
+                                        const float* __restrict__ dz, float* __restrict__ dafg, int64_t P, int W, int G,
+                                        int zp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * G) return;
+  const int64_t p = i / G;
+  const int gch = (int)(i - p * G);
+  const int t = (int)(p % W);
+  const float zz = z[i], s = sg[i], d = dz[i];
+  float df = d * (s - zz * zz / s);
+  float dg = d * zz * (1.f - s);
+  if (t < zp) {
+    df = 0.f;
+    dg = 0.f;
+  }
+  dafg[p * 2 * G + gch] = df;
+  dafg[p * 2 * G + G + gch] = dg;
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -429,6 +449,13 @@ int simt_gate_forward(float* afg, float* z, int64_t P, int G, cudaStream_t s) {
 int simt_gate_backward(const float* tfsg, const float* dz, float* dafg, int64_t P, int W, int G, int zp,
                        cudaStream_t s) {
   gate_backward_kernel<<<blocks_for(P * G, 256), 256, 0, s>>>(tfsg, dz, dafg, P, W, G, zp);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+int simt_gate_backward_zs(const float* z, const float* sg, const float* dz, float* dafg, int64_t P, int W, int G, int zp,
+                          cudaStream_t s) {
+  gate_backward_zs_kernel<<<blocks_for(P * G, 256), 256, 0, s>>>(z, sg, dz, dafg, P, W, G, zp);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }

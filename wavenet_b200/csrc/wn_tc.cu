@@ -133,7 +133,7 @@ __device__ __forceinline__ void store_block_coalesced(uint8_t* stg, const uint32
 struct LayerArgs {
   float* x_out;            // [B][W][64]
   float* z_out;            // [B][W][64]
-  float* tfsg_out;         // [B][W][128] tanh | sigmoid for backward, or null
+  float* sg_out;           // [B][W][64] sigmoid (backward rebuilds tanh = z / sigmoid), or null
   const float* bias_fg;    // [128] or null
   const float* bias_p;     // [64] or null
   int W, d, zp, tiles_per_seq, num_tiles;
@@ -253,7 +253,6 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       mbar_wait(d1_full(s), ph);
       tcgen05_fence_after();
       uint32_t f[32], g[32];
-      float fsave[32];
       tmem_ld32(trow + s * 128 + half * 32, f);
       tmem_ld32(trow + s * 128 + 64 + half * 32, g);
       tmem_ld_wait();
@@ -267,8 +266,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         }
         const float tf = tanh_fast(af), sg = 0.5f * tanh_fast(0.5f * ag) + 0.5f;
         g[i] = __float_as_uint(live ? sg : 0.5f);          // masked rows look like tanh(0) | sigmoid(0)
-        fsave[i] = live ? tf : 0.f;
-        f[i] = __float_as_uint(tf32_rna(fsave[i] * sg));
+        f[i] = __float_as_uint(tf32_rna((live ? tf : 0.f) * sg));
       }
 #pragma unroll
       for (int c = 0; c < 8; ++c)   // A operand of GEMM 2 first: the MMA warp is waiting for it
@@ -283,14 +281,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         const int rows_valid = a.W - t_w0;                                 // may be <= 0 or > 32
         const int64_t gblk = ((int64_t)b * a.W + t_w0) * 64 + half * 32;
         store_block_coalesced(stg, f, a.z_out + gblk, 64, rows_valid, lane);
-        if (a.tfsg_out) {
-          float* tblk = a.tfsg_out + ((int64_t)b * a.W + t_w0) * 128 + half * 32;
-          uint32_t fs[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) fs[i] = __float_as_uint(fsave[i]);
-          store_block_coalesced(stg, fs, tblk, 128, rows_valid, lane);
-          store_block_coalesced(stg, g, tblk + 64, 128, rows_valid, lane);
-        }
+        if (a.sg_out) store_block_coalesced(stg, g, a.sg_out + gblk, 64, rows_valid, lane);
       }
       // ---- epilogue 2: projection + residual ----
       mbar_wait(d2_full(s), ph);
@@ -351,7 +342,8 @@ struct GemmTcArgs {
   int y_slab_cols;         // >0: column block c goes to Y + (c / y_slab_cols) * y_slab_stride, column c % y_slab_cols
   int64_t y_slab_stride;
   // gate-backward epilogue (N == G): result is dz; writes da_f | da_g into dafg[row][0..2G) instead of Y
-  const float* gate_tfsg;  // [rows][2G] tanh | sigmoid, or null
+  const float* gate_sg;    // [rows][G] sigmoid, or null
+  const float* gate_z;     // [rows][G] z = tanh * sigmoid
   float* gate_dafg;
   int gate_zp;
 };
@@ -476,16 +468,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         // Mode-specific branches keep only the needed register arrays alive (no spills).
         const int rsub = lane >> 3;
         const uint8_t* srow = stg + (((lane & 7)) << 4);
-        if (a.gate_tfsg) {
-          float4 r4[8], tf4[8], sg4[8];
+        if (a.gate_sg) {
+          float4 r4[8], z4[8], sg4[8];
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
             const int t = min(t0 + jj * 4 + rsub, a.rows_out - 1);
             const int64_t orow = (int64_t)b * a.rows_out + t;
             r4[jj] = *reinterpret_cast<const float4*>(a.Rsd + orow * a.ldr + col);
-            const float* trow = a.gate_tfsg + orow * (2 * a.N);
-            tf4[jj] = *reinterpret_cast<const float4*>(trow + col);
-            sg4[jj] = *reinterpret_cast<const float4*>(trow + a.N + col);
+            z4[jj] = *reinterpret_cast<const float4*>(a.gate_z + orow * a.N + col);
+            sg4[jj] = *reinterpret_cast<const float4*>(a.gate_sg + orow * a.N + col);
           }
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
@@ -495,14 +486,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             const int64_t orow = (int64_t)b * a.rows_out + t;
             float4 o = *reinterpret_cast<const float4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
             o.x += r4[jj].x, o.y += r4[jj].y, o.z += r4[jj].z, o.w += r4[jj].w;
-            // dz -> (da_f, da_g) = dz*sg*(1-tf^2), dz*tf*sg*(1-sg); rows inside the zero prefix get none (Q1)
-            const float4 tf = tf4[jj], sg = sg4[jj];
+            // with z = tanh*sg:  da_f = dz*sg*(1-tanh^2) = dz*(sg - z*z/sg),  da_g = dz*tanh*sg*(1-sg) = dz*z*(1-sg);
+            // rows inside the zero prefix get none (Q1)
+            const float4 z = z4[jj], sg = sg4[jj];
             const float live = t >= a.gate_zp ? 1.f : 0.f;
             float4 df, dg;
-            df.x = live * o.x * sg.x * (1.f - tf.x * tf.x), dg.x = live * o.x * tf.x * sg.x * (1.f - sg.x);
-            df.y = live * o.y * sg.y * (1.f - tf.y * tf.y), dg.y = live * o.y * tf.y * sg.y * (1.f - sg.y);
-            df.z = live * o.z * sg.z * (1.f - tf.z * tf.z), dg.z = live * o.z * tf.z * sg.z * (1.f - sg.z);
-            df.w = live * o.w * sg.w * (1.f - tf.w * tf.w), dg.w = live * o.w * tf.w * sg.w * (1.f - sg.w);
+            df.x = live * o.x * (sg.x - __fdividef(z.x * z.x, sg.x)), dg.x = live * o.x * z.x * (1.f - sg.x);
+            df.y = live * o.y * (sg.y - __fdividef(z.y * z.y, sg.y)), dg.y = live * o.y * z.y * (1.f - sg.y);
+            df.z = live * o.z * (sg.z - __fdividef(z.z * z.z, sg.z)), dg.z = live * o.z * z.z * (1.f - sg.z);
+            df.w = live * o.w * (sg.w - __fdividef(z.w * z.w, sg.w)), dg.w = live * o.w * z.w * (1.f - sg.w);
             float* drow = a.gate_dafg + orow * (2 * a.N);
             *reinterpret_cast<float4*>(drow + col) = df;
             *reinterpret_cast<float4*>(drow + a.N + col) = dg;
@@ -588,13 +580,13 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128_32b(uint32_t smem_addr, u
   return d;
 }
 
-constexpr int WG_KC = 32;                 // positions per pipeline stage
+constexpr int WG_KC = 64;                 // positions per pipeline stage
 constexpr int WG_SUB = WG_KC * 128;       // bytes of a [32 x 32] sub-tile
 
 template <int NB>
 struct WgradCfg {
   static constexpr int STAGE = 4 * WG_SUB + (NB / 32) * WG_SUB;
-  static constexpr int STAGES = 4;
+  static constexpr int STAGES = (200 * 1024) / STAGE > 4 ? 4 : (200 * 1024) / STAGE;
   static constexpr int BAR = STAGES * STAGE;
   static constexpr int SMEM = BAR + 256 + 1024;
 };
@@ -798,7 +790,8 @@ struct TcEpilogue {
   int ldm = 0, mask_rows_in = 0, mask_row_off = 0;
   int y_slab_cols = 0;
   int64_t y_slab_stride = 0;
-  const float* gate_tfsg = nullptr;
+  const float* gate_sg = nullptr;
+  const float* gate_z = nullptr;
   float* gate_dafg = nullptr;
   int gate_zp = 0;
 };
@@ -830,7 +823,8 @@ int tc_gemm(const wn_handle* h, const TcOperand& A, int ns, const int* slab_idx,
   g.mask_row_off = e.mask_row_off;
   g.y_slab_cols = e.y_slab_cols;
   g.y_slab_stride = e.y_slab_stride;
-  g.gate_tfsg = e.gate_tfsg;
+  g.gate_sg = e.gate_sg;
+  g.gate_z = e.gate_z;
   g.gate_dafg = e.gate_dafg;
   g.gate_zp = e.gate_zp;
   g.rows_out = rows_out;
@@ -949,7 +943,7 @@ int tc_forward_residual(wn_handle* h, const float* params, cudaStream_t s) {
     LayerArgs a;
     a.x_out = h->ws + t.x[l + 1];
     a.z_out = h->ws + t.z[l];
-    a.tfsg_out = h->save_gates ? h->ws + t.tfsg[l] : nullptr;
+    a.sg_out = h->save_gates ? h->ws + t.tfsg[l] : nullptr;   // TC tapes keep sigmoid only, row stride G
     a.bias_fg = nullptr;
     a.bias_p = nullptr;
     a.W = t.W;
@@ -972,6 +966,9 @@ int tc_forward_residual(wn_handle* h, const float* params, cudaStream_t s) {
   }
   TcOperand A{h->ws + t.z[0], G, t.W, t.B, L, zstride};
   TcEpilogue e;
+  e.relu = h->fuse_head_relu;        // fused train path: the head's first ReLU (wavenet.py:588) rides on this epilogue
+  e.round_out = h->fuse_head_relu;
+  h->skip_is_relu = h->fuse_head_relu != 0;
   return tc_gemm(h, A, L, idx, off, t.W, h->ws + t.tc_ws, h->S, e, h->ws + t.skip, h->S, s);
 }
 
@@ -982,7 +979,7 @@ int tc_forward_head(wn_handle* h, const float* params, int T, bool external, cud
   const int nh = (int)h->head.size();
   const int64_t rows = (int64_t)t.B * T;
   const int rows_in0 = external ? T : t.W, off0 = external ? 0 : t.W - T;
-  {
+  if (!h->skip_is_relu || external) {
     const int64_t n = rows * (h->S / 4);
     tc_relu_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->ws + t.skip, h->S, rows_in0, off0, T, rows);
     WN_CHECK_LAUNCH();
@@ -1098,7 +1095,8 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
       TcEpilogue e;
       e.Rsd = dzs;
       e.ldr = G;
-      e.gate_tfsg = ws + t.tfsg[l];
+      e.gate_sg = ws + t.tfsg[l];
+      e.gate_z = ws + t.z[l];
       e.gate_dafg = ws + t.dafg;
       e.gate_zp = zp;
       WN_TRY(tc_gemm(h, DO, 1, nullptr, &zero, W, ws + t.tc_wpt + (int64_t)l * G * R, G, e, ws + t.dz, G, s));
@@ -1106,7 +1104,7 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
       float* dw = grads + ly.proj.w_off;
       WN_TRY(tc_wgrad(h, DO, 0, 0, R, Z, 1, &zero, nullptr, &dw, nullptr, 128, W, G, 1, s));
     } else {
-      WN_TRY(simt_gate_backward(ws + t.tfsg[l], dzs, ws + t.dafg, P, W, G, zp, s));
+      WN_TRY(simt_gate_backward_zs(ws + t.z[l], ws + t.tfsg[l], dzs, ws + t.dafg, P, W, G, zp, s));
     }
     TcOperand DA{ws + t.dafg, 2 * G, W, B, 1, 0};
     {
