@@ -145,6 +145,11 @@ int wn_clip_adam_step(wn_handle* h, float* params, float* grads, float* m, float
                       float beta2, float eps, float weight_decay, float clip, float grad_scale, void* scratch,
                       float* norm_out, wn_stream_t s);
 
+/* Profiling hooks used by bench.py's roofline leg: ONE launch of the fused residual-layer kernel (layer l)
+ * or of the skip-sum GEMM on the bound tape; need a preceding TF32 wn_forward_residual_block. */
+int wn_tc_layer_forward(wn_handle* h, int layer, wn_stream_t s);
+int wn_tc_skip_gemm(wn_handle* h, wn_stream_t s);
+
 /* ---- incremental generation (faster_wavenet.py) ----------------------------
  * n_streams independent utterances (the reference hard-codes one, wavenet.py:286).
  * head_act: 0 = ReLU always; 1 = reference (ReLU on the priming call,

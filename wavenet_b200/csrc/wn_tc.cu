@@ -921,6 +921,9 @@ int tc_prepare_weights(wn_handle* h, const float* params, cudaStream_t s) {
   return WN_OK;
 }
 
+int tc_layer_launch(wn_handle* h, int l, cudaStream_t s);
+int tc_skip_gemm(wn_handle* h, cudaStream_t s);
+
 int tc_forward_residual(wn_handle* h, const float* params, cudaStream_t s) {
   const Tape& t = h->tape;
   const int L = (int)h->layers.size();
@@ -931,10 +934,18 @@ int tc_forward_residual(wn_handle* h, const float* params, cudaStream_t s) {
     WN_CHECK_CUDA(cudaFuncSetAttribute(tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM + 1024));
     attr = true;
   }
+  for (int l = 0; l < L; ++l) WN_TRY(tc_layer_launch(h, l, s));
+  // sum_skip = sum_l Ws_l z_l as one GEMM over K = L*G (z buffers are equally spaced slabs)
+  return tc_skip_gemm(h, s);
+}
+
+int tc_layer_launch(wn_handle* h, int l, cudaStream_t s) {
+  const Tape& t = h->tape;
+  const int R = 64, G = 64;
   const int tiles_per_seq = (t.W + TM - 1) / TM;
   const int num_tiles = tiles_per_seq * t.B;
   const int grid = num_tiles < h->sm_count ? num_tiles : h->sm_count;
-  for (int l = 0; l < L; ++l) {
+  {
     const ResLayer& ly = h->layers[l];
     CUtensorMap tx, tw1, tw2;
     WN_TRY(make_map_4d(&tx, h->ws + t.x[l], R, t.W, t.B, 1, R, (uint64_t)t.W * R, (uint64_t)t.P * R, TM));
@@ -954,7 +965,13 @@ int tc_forward_residual(wn_handle* h, const float* params, cudaStream_t s) {
     tc_layer_kernel<<<grid, L_THREADS, L_SMEM + 1024, s>>>(tx, tw1, tw2, a);
     WN_CHECK_LAUNCH();
   }
-  // sum_skip = sum_l Ws_l z_l as one GEMM over K = L*G (z buffers are equally spaced slabs)
+  return WN_OK;
+}
+
+int tc_skip_gemm(wn_handle* h, cudaStream_t s) {
+  const Tape& t = h->tape;
+  const int L = (int)h->layers.size();
+  const int G = 64;
   const int64_t zstride = L > 1 ? t.z[1] - t.z[0] : 0;
   for (int l = 1; l < L; ++l)
     WN_REQUIRE(t.z[l] - t.z[l - 1] == zstride, WN_EINVAL, "z slabs are not equally spaced");
@@ -1143,4 +1160,16 @@ extern "C" int wn_debug_wgrad(wn_handle* h, const float* dY, int Kd, const float
   int rc = tc_wgrad(h, A, 0, 0, 128, B, 1, &zero, nullptr, &dW, nullptr, 128, rows, Kx, 1, (cudaStream_t)stream);
   g_dbg[0] = g_dbg[1] = g_dbg[2] = g_dbg[3] = 0;
   return rc;
+}
+
+// Profiling hooks (bench.py roofline): one launch of the fused residual-layer kernel / of the skip GEMM on
+// the bound tape.  Require a previous wn_forward_residual_block under WN_PREC_TF32 (weights prepared).
+extern "C" int wn_tc_layer_forward(wn_handle* h, int layer, void* stream) {
+  WN_REQUIRE(h && h->ws && h->tape_tc, WN_ESTATE, "wn_tc_layer_forward: run a TF32 forward first");
+  WN_REQUIRE(layer >= 0 && layer < (int)h->layers.size(), WN_EINVAL, "bad layer index");
+  return tc_layer_launch(h, layer, (cudaStream_t)stream);
+}
+extern "C" int wn_tc_skip_gemm(wn_handle* h, void* stream) {
+  WN_REQUIRE(h && h->ws && h->tape_tc, WN_ESTATE, "wn_tc_skip_gemm: run a TF32 forward first");
+  return tc_skip_gemm(h, (cudaStream_t)stream);
 }
