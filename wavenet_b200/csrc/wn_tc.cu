@@ -564,7 +564,6 @@ struct WgradTcArgs {
   int m_split, m_valid;
   int64_t sn, sk;          // element (m, slab, c) -> dW[slab] + m*sn + c*sk
   int chunks_per_seq, num_chunks;
-  int dbg_lbo, dbg_sbo, dbg_kstep, dbg_major;   // descriptor probing (wn_debug_wgrad); 0 = defaults
 };
 
 // MN-major tf32 operands only exist in the SWIZZLE_128B_BASE32B layout (layout_type 1): 128-byte rows,
@@ -644,11 +643,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     }
   } else if (warp == 1) {
     if (lane == 0 && n_local > 0) {
-      uint32_t idesc = umma_idesc_tf32(128, NB) | (1u << 15) | (1u << 16);   // both operands MN-major
-      if (a.dbg_major && a.dbg_major < 4) idesc = umma_idesc_tf32(128, NB) | ((uint32_t)(a.dbg_major & 3) << 15);
-      if (a.dbg_major == 4) idesc = umma_idesc_tf32(128, NB);
-      const uint32_t lbo = a.dbg_lbo ? a.dbg_lbo : WG_SUB, sbo = a.dbg_sbo ? a.dbg_sbo : 512;
-      const uint32_t kstep = a.dbg_kstep ? a.dbg_kstep : 1024;
+      constexpr uint32_t idesc = umma_idesc_tf32(128, NB) | (1u << 15) | (1u << 16);   // both operands MN-major
+      constexpr uint32_t lbo = WG_SUB, sbo = 512, kstep = 1024;
       for (int it = 0; it < n_local; ++it) {
         const int s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
         mbar_wait(full(s), ph);
@@ -680,11 +676,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         float* wrow = m < a.m_split ? a.dW0[sl] + (int64_t)m * a.sn : a.dW1[sl] + (int64_t)(m - a.m_split) * a.sn;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float val = __uint_as_float(v[i]);
-          if (a.dbg_major == 7) val = 1.0f;                                                     // flow probe
-          if (a.dbg_major == 6) val = *reinterpret_cast<const float*>(gbase + (m * 32 + i) * 4);   // smem A probe (stage 0)
-          if (a.dbg_major == 5) val = *reinterpret_cast<const float*>(gbase + 4 * WG_SUB + (m * 32 + i) * 4);   // smem B
-          atomicAdd(wrow + (int64_t)(cbase + i) * a.sk, val);
+          atomicAdd(wrow + (int64_t)(cbase + i) * a.sk, __uint_as_float(v[i]));
         }
       }
     }
@@ -842,7 +834,6 @@ int tc_gemm(const wn_handle* h, const TcOperand& A, int ns, const int* slab_idx,
 }
 
 // dW[slab](m, c) += sum_{b,t} dY[b][a_row_off + t][a_c0 + m] * X[slab_idx[s]][b][b_row_off[s] + t][c]   for m < m_valid (<= 128)
-static int g_dbg[4] = {0, 0, 0, 0};
 int tc_wgrad(const wn_handle* h, const TcOperand& dY, int a_row_off, int a_c0, int m_valid, const TcOperand& X, int nb_slab,
              const int* b_row_off, const int* b_slab_idx, float* const* dW0, float* const* dW1, int m_split, int rows_it,
              int64_t sn, int64_t sk, cudaStream_t s) {
@@ -875,10 +866,6 @@ int tc_wgrad(const wn_handle* h, const TcOperand& dY, int a_row_off, int a_c0, i
   g.sk = sk;
   g.chunks_per_seq = (rows_it + WG_KC - 1) / WG_KC;
   g.num_chunks = g.chunks_per_seq * dY.num_seq;
-  g.dbg_lbo = g_dbg[0];
-  g.dbg_sbo = g_dbg[1];
-  g.dbg_kstep = g_dbg[2];
-  g.dbg_major = g_dbg[3];
   if (NB == 64) return launch_wgrad<64>(ta, tb, g, h->sm_count, s);
   if (NB == 128) return launch_wgrad<128>(ta, tb, g, h->sm_count, s);
   return launch_wgrad<256>(ta, tb, g, h->sm_count, s);
@@ -1145,21 +1132,6 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
   }
   h->bwd_dout = dout;
   return WN_OK;
-}
-
-// Debug probe: dW[128][Kx] = dY[rows][0..128)^T . X[rows][Kx] with explicit descriptor parameters.
-extern "C" int wn_debug_wgrad(wn_handle* h, const float* dY, int Kd, const float* X, int Kx, int rows, int nseq, float* dW,
-                              int lbo, int sbo, int kstep, int major, void* stream) {
-  g_dbg[0] = lbo;
-  g_dbg[1] = sbo;
-  g_dbg[2] = kstep;
-  g_dbg[3] = major;
-  TcOperand A{dY, Kd, rows, nseq, 1, 0};
-  TcOperand B{X, Kx, rows, nseq, 1, 0};
-  const int zero = 0;
-  int rc = tc_wgrad(h, A, 0, 0, 128, B, 1, &zero, nullptr, &dW, nullptr, 128, rows, Kx, 1, (cudaStream_t)stream);
-  g_dbg[0] = g_dbg[1] = g_dbg[2] = g_dbg[3] = 0;
-  return rc;
 }
 
 // Profiling hooks (bench.py roofline): one launch of the fused residual-layer kernel / of the skip GEMM on
