@@ -33,6 +33,8 @@ struct GenLayout {
   int64_t cur_logits = 0;   // [n][Q]
   int64_t layers_dev = 0;   // GenLayerOff[L] copied to device (as raw bytes)
   int64_t chunks_dev = 0;   // GenChunk[] streaming schedule
+  int64_t chunks3_dev = 0;  // GenChunk[] schedule of the packed (v3) weights
+  int64_t wpk = 0;          // packed weights (v3)
   int64_t total = 0;
   int maxw = 0;             // widest vector anywhere (for smem sizing)
 };
@@ -55,6 +57,10 @@ struct wn_gen {
   int64_t steps_done = 0;  // incremental steps since priming
   bool stream_ok = false;             // every matrix fits the streamed (cp.async.bulk ring) matvec
   std::vector<GenChunk> chunks;       // per-step streaming schedule
+  bool v3_ok = false;                 // network tiles exactly over 16 warps (config C): packed-weight kernel
+  std::vector<GenChunk> chunks3;      // schedule over the packed weights
+  struct Pack3 { int64_t src, dst; int K, N, chunkK, mode; };
+  std::vector<Pack3> packs3;
 };
 
 namespace {
@@ -639,6 +645,381 @@ __global__ void __launch_bounds__(GT + (STREAM ? 32 : 0)) gen_kernel(GenArgs a) 
   }
 }
 
+
+// =============================================================================================
+// Generator v3: specialised for networks whose matvecs tile exactly over 16 warps
+// (2G = 128, R + S = 320, head widths 256 -- BASELINE config C).  Differences from the generic
+// streamed kernel above:
+//   * weights are pre-packed so that lane j of warp w reads ITS rows of ITS outputs with consecutive
+//     LDS.128 (conflict-free), lanes split K, and partial sums are combined with a shuffle
+//     reduce-scatter -- no shared-memory partials, no barrier between matvec and epilogue;
+//   * the gate runs inside the warp that produced a_f/a_g, the skip accumulators stay in registers
+//     for the whole step; two block barriers per layer remain (z visible, x visible).
+constexpr int V3_STAGE_BYTES = 40960;
+constexpr int V3_STAGES = 4;
+
+// acc[s] += sum over this lane's rows of ITS output: per chunk NQ float4 of packed weights (4 consecutive rows of
+// one output each) against NQ float4 of the input vector.  f4_off/q_stride locate the lane's float4s inside a
+// chunk; rows [0,Ksplit) of the input come from xa, the rest from xb.
+template <int NS, int NQ>
+__device__ __forceinline__ void mv4(StreamCtx& cx, int nchunks, int f4_off, int q_stride, int chunkK, int row0,
+                                    bool active, const float* xa, int lda, const float* xb, int ldb, int Ksplit,
+                                    float (&acc)[NS]) {
+  const int lane = threadIdx.x & 31;
+  for (int c = 0; c < nchunks; ++c) {
+    const uint32_t stage = cx.it % V3_STAGES, parity = (cx.it / V3_STAGES) & 1;
+    tc::mbar_wait(cx.full0 + 8 * stage, parity);
+    if (active) {
+      const float4* wp = reinterpret_cast<const float4*>(cx.ring + stage * (V3_STAGE_BYTES / 4)) + f4_off;
+      const int kk = c * chunkK + row0;
+      const float* xp = kk < Ksplit ? xa + kk : xb + (kk - Ksplit);
+      const int ld = kk < Ksplit ? lda : ldb;
+      float4 wv[NQ];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) wv[q] = wp[q * q_stride];
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const float4 x = *reinterpret_cast<const float4*>(xp + s * ld + q * 4);
+          acc[s] = fmaf(wv[q].x, x.x, acc[s]);
+          acc[s] = fmaf(wv[q].y, x.y, acc[s]);
+          acc[s] = fmaf(wv[q].z, x.z, acc[s]);
+          acc[s] = fmaf(wv[q].w, x.w, acc[s]);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(cx.empty0 + 8 * stage);
+    ++cx.it;
+  }
+}
+
+__device__ __forceinline__ float head_act(float v, int elu) { return elu ? (v > 0.f ? v : expm1f(v)) : fmaxf(v, 0.f); }
+
+template <int NS>
+__global__ void __launch_bounds__(GT + 32) gen_kernel_v3(GenArgs a) {
+  extern __shared__ float sm[];
+  const GenLayout& L = a.lay;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s0 = blockIdx.x * NS;
+  const int R = L.R, Q = L.Q;
+  const int pastw = (L.k - 1) * R;
+  // smem carve-up (floats)
+  float* xv = sm;                               // [NS][R]
+  float* zv = xv + NS * R;                      // [NS][128] (G <= 64 used)
+  float* xpast = zv + NS * 128;                 // [NS][L][pastw]
+  float* hA = xpast + NS * L.L * pastw;         // [NS][256]
+  float* hB = hA + NS * 256;                    // [NS][256]
+  float* hbias = hB + NS * 256;                 // [n_head][256]
+  uint8_t* ring_g = reinterpret_cast<uint8_t*>(hbias + L.n_head * 256);
+  ring_g += (128 - (tc::smem_u32(ring_g) & 127)) & 127;
+  __shared__ int s_sample[NS];
+  __shared__ __align__(8) uint64_t s_bars[2 * V3_STAGES];
+  __shared__ GenChunk s_sched[MAX_CHUNKS];
+  __shared__ GenLayerOff s_layers[128];
+  __shared__ float s_redv[GT / 32];
+  __shared__ int s_redi[GT / 32];
+  StreamCtx cx;
+  cx.it = 0;
+  cx.ring = reinterpret_cast<const float*>(ring_g);
+  cx.full0 = tc::smem_u32(&s_bars[0]);
+  cx.empty0 = tc::smem_u32(&s_bars[V3_STAGES]);
+  float* st = a.state;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < V3_STAGES; ++i) {
+      tc::mbar_init(cx.full0 + 8 * i, 1);
+      tc::mbar_init(cx.empty0 + 8 * i, GT / 32);
+    }
+    tc::fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < a.n_chunks; i += blockDim.x) s_sched[i] = a.chunks[i];
+  for (int i = threadIdx.x; i < L.L; i += blockDim.x) s_layers[i] = a.layers[i];
+  for (int i = threadIdx.x; i < L.n_head * 256; i += blockDim.x) hbias[i] = L.has_hb ? st[L.hb[i / 256] + (i % 256)] : 0.f;
+  float* cur_logits = st + L.cur_logits;
+  for (int i = threadIdx.x; i < NS * Q; i += blockDim.x) {
+    const int stream = s0 + i / Q;
+    hA[i] = stream < L.n ? cur_logits[(int64_t)stream * Q + (i % Q)] : 0.f;   // logits of the next sample
+  }
+  __syncthreads();
+  if (threadIdx.x >= GT) {
+    if (threadIdx.x == GT) {   // producer: stream the packed weights of every step in consumption order
+      const uint8_t* sbase = reinterpret_cast<const uint8_t*>(a.state);
+      const uint32_t ring_s = tc::smem_u32(ring_g);
+      uint32_t it = 0;
+      for (int step = 0; step < a.n_steps; ++step)
+        for (int c = 0; c < a.n_chunks; ++c, ++it) {
+          const GenChunk ch = s_sched[c];
+          const uint32_t stage = it % V3_STAGES;
+          tc::mbar_wait(cx.empty0 + 8 * stage, ((it / V3_STAGES) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(cx.full0 + 8 * stage, ch.bytes);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           ring_s + stage * V3_STAGE_BYTES),
+                       "l"(reinterpret_cast<uint64_t>(sbase + ch.off)), "r"(ch.bytes), "r"(cx.full0 + 8 * stage)
+                       : "memory");
+        }
+    }
+    return;
+  }
+  int32_t* idx_hist = (int32_t*)(st + L.idx_hist);
+  const int kc1 = L.kc - 1;
+  float* lg = hA;                       // logits of the next sample live in smem between steps
+  // lane roles: WA  -> output ol = lane&7 of the warp's 8 (4 a_f + 4 a_g), K slice sl = lane>>3 (16 rows per chunk)
+  //             WB  -> thread tid owns output tid (< R+S), all 32 rows of a chunk
+  //             head-> output ol = lane&15 of the warp's 16, K slice lane>>4 (16 rows per chunk)
+  const int olA = lane & 7, slA = lane >> 3;
+  const int olH = lane & 15, slH = lane >> 4;
+  const bool actB = tid < R + 256;
+
+  for (int step = 0; step < a.n_steps; ++step) {
+    const int64_t t = a.t0 + step;
+    // ---- 1. sample (argmax, optionally Gumbel-perturbed; ties -> lowest index) ----
+    for (int s = 0; s < NS; ++s) {
+      const int stream = s0 + s;
+      if (!a.sample_first || stream >= L.n) {
+        if (tid == 0) s_sample[s] = (stream < L.n && !a.sample_first) ? a.forced[stream] : 0;
+        continue;
+      }
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int q = tid; q < Q; q += GT) {
+        float v = lg[s * 256 + q];
+        if (a.mode == WN_GEN_SAMPLE) v += gumbel(a.seed, (uint64_t)stream, (uint64_t)t, (uint32_t)q);
+        if (v > bv || (v == bv && q < bi)) {
+          bv = v;
+          bi = q;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) {
+          bv = ov;
+          bi = oi;
+        }
+      }
+      if (lane == 0) {
+        s_redv[warp] = bv;
+        s_redi[warp] = bi;
+      }
+      csync();
+      if (tid == 0) {
+        for (int w = 1; w < GT / 32; ++w)
+          if (s_redv[w] > bv || (s_redv[w] == bv && s_redi[w] < bi)) {
+            bv = s_redv[w];
+            bi = s_redi[w];
+          }
+        s_sample[s] = bi;
+        if (a.out) a.out[(int64_t)stream * a.n_steps + step] = bi;
+      }
+      csync();
+    }
+    // ---- 2. past taps of every layer (already in the rings) + embedding of the new sample ----
+    {
+      const int per = pastw >> 2;
+      for (int i = tid; i < NS * L.L * per; i += GT) {
+        const int v4 = i % per, sl_ = i / per;
+        const int l = sl_ % L.L, s = sl_ / L.L;
+        const int stream = s0 + s;
+        const GenLayerOff& ly = s_layers[l];
+        const int tap = (v4 * 4) / R, c = v4 * 4 - tap * R;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (stream < L.n) {
+          const int len = ly.ring_len;
+          const int64_t tau = t - (int64_t)(L.k - 1 - tap) * ly.dilation;
+          const int slot = (int)(((tau % len) + len) % len);
+          v = *reinterpret_cast<const float4*>(st + ly.ring + ((int64_t)stream * len + slot) * R + c);
+        }
+        *reinterpret_cast<float4*>(xpast + (s * L.L + l) * pastw + v4 * 4) = v;
+      }
+    }
+    csync();   // s_sample visible
+    {
+      const float* emb = st + L.emb;
+      const float* eb = st + L.emb_b;
+      for (int i = tid; i < NS * R; i += GT) {
+        const int s = i / R, r = i - s * R;
+        const int stream = s0 + s;
+        float v = L.has_cb ? eb[r] : 0.f;
+        if (stream < L.n)
+          for (int j = 0; j < L.kc; ++j) {
+            const int q = j == kc1 ? s_sample[s] : idx_hist[(int64_t)stream * kc1 + j];
+            if (q >= 0) v += emb[((int64_t)j * Q + q) * R + r];
+          }
+        xv[s * R + r] = v;
+      }
+    }
+    csync();
+    if (kc1 > 0 && tid < NS) {
+      const int stream = s0 + tid;
+      if (stream < L.n) {
+        for (int j = 0; j + 1 < kc1; ++j) idx_hist[(int64_t)stream * kc1 + j] = idx_hist[(int64_t)stream * kc1 + j + 1];
+        idx_hist[(int64_t)stream * kc1 + kc1 - 1] = s_sample[tid];
+      }
+    }
+    // ---- 3. residual layers ----
+    float skr[NS];   // this thread's skip-sum channel (tid - R) stays in a register for the whole step
+#pragma unroll
+    for (int s = 0; s < NS; ++s) skr[s] = 0.f;
+    for (int l = 0; l < L.L; ++l) {
+      const GenLayerOff& ly = s_layers[l];
+      const int len = ly.ring_len, G = ly.G;
+      for (int i = tid; i < NS * R; i += GT) {   // x[t] into the ring (roll, faster_wavenet.py:90-91)
+        const int s = i / R, c = i - s * R;
+        const int stream = s0 + s;
+        if (stream < L.n) st[ly.ring + ((int64_t)stream * len + (int)(t % len)) * R + c] = xv[s * R + c];
+      }
+      {
+        float acc[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) acc[s] = 0.f;
+        mv4<NS, 4>(cx, (L.k * R) / 64, (warp * 4) * 32 + lane, 32, 64, slA * 16, true, xpast + l * pastw, L.L * pastw, xv,
+                   R, pastw, acc);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          float v = acc[s];
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);           // every lane: full a_f / a_g of its output
+          const float other = __shfl_xor_sync(0xffffffffu, v, 4);   // ol<4 holds a_f, ol+4 the matching a_g
+          if (slA == 0 && olA < 4) {
+            const int ch = 4 * warp + olA;
+            float f = v, gg = other;
+            if (ly.has_ba) {
+              f += st[ly.ba + ch];
+              gg += st[ly.ba + G + ch];
+            }
+            zv[s * 128 + ch] = tanhf(f) * (1.f / (1.f + expf(-gg)));   // wavenet.py:351
+          }
+        }
+      }
+      csync();
+      {
+        float acc[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) acc[s] = 0.f;
+        mv4<NS, 8>(cx, G / 32, tid, R + 256, 32, 0, actB, zv, 128, zv, 128, G, acc);
+        if (actB) {
+          const float bb = ly.has_bb ? st[ly.bb + tid] : 0.f;
+#pragma unroll
+          for (int s = 0; s < NS; ++s) {
+            if (tid < R)
+              xv[s * R + tid] += acc[s] + bb;      // output = projection_block + x, wavenet.py:354
+            else
+              skr[s] += acc[s] + bb;               // sum_skip_connections += z, faster_wavenet.py:100
+          }
+        }
+      }
+      csync();
+    }
+    // ---- 4. head (faster_wavenet.py:105-113: ELU on incremental steps; ReLU variant) ----
+    if (actB && tid >= R) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) hB[s * 256 + (tid - R)] = head_act(skr[s], a.head_elu);
+    }
+    csync();
+    float* hin = hB;
+    float* hout = hA;
+    for (int hi = 0; hi < L.n_head; ++hi) {
+      float acc[NS];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) acc[s] = 0.f;
+      mv4<NS, 4>(cx, L.head_ch[hi] / 32, (warp * 4) * 32 + lane, 32, 32, slH * 16, true, hin, 256, hin, 256, L.head_ch[hi],
+                 acc);
+      const bool last = hi == L.n_head - 1;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        float v = acc[s] + __shfl_xor_sync(0xffffffffu, acc[s], 16);
+        if (slH == 0) {
+          const int o = 16 * warp + olH;
+          v += hbias[hi * 256 + o];
+          if (!last) v = head_act(v, a.head_elu);
+          hout[s * 256 + o] = v;
+        }
+      }
+      csync();
+      float* tmp = hin;
+      hin = hout;
+      hout = tmp;
+    }
+    lg = hin;   // logits for the next sample
+  }
+  // ---- epilogue: publish logits (and probabilities for the step API) ----
+  for (int i = tid; i < NS * Q; i += GT) {
+    const int s = i / Q, q = i - s * Q;
+    const int stream = s0 + s;
+    if (stream < L.n) cur_logits[(int64_t)stream * Q + q] = lg[s * 256 + q];
+  }
+  if (a.probs) {
+    for (int s = 0; s < NS; ++s) {
+      const int stream = s0 + s;
+      if (stream >= L.n) continue;
+      const float* lgs = lg + s * 256;
+      if (!a.apply_softmax) {
+        for (int q = tid; q < Q; q += GT) a.probs[(int64_t)stream * Q + q] = lgs[q];
+        continue;
+      }
+      float m = -INFINITY;
+      for (int q = tid; q < Q; q += GT) m = fmaxf(m, lgs[q]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) s_redv[warp] = m;
+      csync();
+      m = s_redv[0];
+      for (int w = 1; w < GT / 32; ++w) m = fmaxf(m, s_redv[w]);
+      csync();
+      float sum = 0.f;
+      for (int q = tid; q < Q; q += GT) sum += expf(lgs[q] - m);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) s_redv[warp] = sum;
+      csync();
+      sum = 0.f;
+      for (int w = 0; w < GT / 32; ++w) sum += s_redv[w];
+      csync();
+      for (int q = tid; q < Q; q += GT) a.probs[(int64_t)stream * Q + q] = expf(lgs[q] - m) / sum;
+    }
+  }
+}
+
+// dst (packed so that every lane reads consecutive float4s) <- src [K][N].  One float4 = 4 consecutive rows of one
+// output.  mode 1 (gated conv, 8 outputs/warp = 4 a_f + 4 a_g, 4 K slices/warp), mode 2 (one output per thread),
+// mode 3 (16 outputs/warp, 2 K slices/warp).
+__global__ void gen_pack_v3(const float* __restrict__ src, float* __restrict__ dst, int K, int N, int chunkK, int mode) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= K * N) return;
+  const int k = idx / N, n = idx % N;
+  const int c = k / chunkK, kr = k % chunkK, comp = kr & 3;
+  int64_t f4;
+  if (mode == 1) {
+    const int G = N / 2, ch = n < G ? n : n - G;
+    const int w = ch / 4, ol = (n < G ? 0 : 4) + ch % 4;
+    const int sl = kr / 16, q = (kr % 16) / 4;
+    f4 = (int64_t)(w * 4 + q) * 32 + sl * 8 + ol;
+  } else if (mode == 2) {
+    f4 = (int64_t)(kr / 4) * N + n;
+  } else {
+    const int w = n / 16, ol = n % 16;
+    const int sl = kr / 16, q = (kr % 16) / 4;
+    f4 = (int64_t)(w * 4 + q) * 32 + sl * 16 + ol;
+  }
+  dst[(int64_t)c * chunkK * N + f4 * 4 + comp] = src[idx];
+}
+
+size_t gen_smem_bytes_v3(const GenLayout& L, int NS) {
+  size_t f = (size_t)NS * L.R + NS * 128 + (size_t)NS * L.L * (L.k - 1) * L.R + 2 * NS * 256 + L.n_head * 256 + 64;
+  return f * sizeof(float) + V3_STAGES * V3_STAGE_BYTES + 128;
+}
+
+template <int NS>
+int launch_gen_v3(const GenArgs& a, cudaStream_t s) {
+  const size_t smem = gen_smem_bytes_v3(a.lay, NS);
+  WN_CHECK_CUDA(cudaFuncSetAttribute(gen_kernel_v3<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (a.lay.n + NS - 1) / NS;
+  gen_kernel_v3<NS><<<grid, GT + 32, smem, s>>>(a);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
 size_t gen_smem_bytes(const GenLayout& L, int NS, bool stream) {
   const size_t maxw = L.maxw;
   size_t f = NS * maxw                               // xv
@@ -671,6 +1052,12 @@ int pick_ns(const wn_gen* g) {
 
 int run_gen(wn_gen* g, GenArgs& a, cudaStream_t s) {
   const int ns = pick_ns(g);
+  if (g->v3_ok && gen_smem_bytes_v3(g->lay, ns > 2 ? 2 : ns) <= 200 * 1024) {
+    a.chunks = (const GenChunk*)(g->state + g->lay.chunks3_dev);
+    a.n_chunks = (int)g->chunks3.size();
+    if (ns == 1) return launch_gen_v3<1>(a, s);
+    return launch_gen_v3<2>(a, s);
+  }
   if (g->stream_ok && gen_smem_bytes(g->lay, ns, true) <= 208 * 1024) {   // + ~16 KB static (schedule, layer table)
     if (ns == 1) return launch_gen<1, true>(a, s);
     if (ns == 2) return launch_gen<2, true>(a, s);
@@ -775,6 +1162,36 @@ extern "C" int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen**
   for (int i = 0; i < L.n_head; ++i) add_matrix(L.hw[i], L.head_ch[i], L.head_ch[i + 1]);
   if (g->chunks.size() > 512 || L.L > 128 || L.R % 4 != 0) g->stream_ok = false;   // MAX_CHUNKS, s_layers, float4 taps
   L.chunks_dev = take((int64_t)(sizeof(GenChunk) * g->chunks.size() + 3) / 4 + 4);
+  // v3 (packed weights, warp-shuffle reductions): needs 2G = 128, R + S = 320, head widths 256, one causal layer
+  g->v3_ok = c.n_causal == 1 && L.R + L.S == 320 && L.S == 256 && L.R % 4 == 0 && (L.k * L.R) % 64 == 0 && ((L.k - 1) * L.R) % 2 == 0 &&
+             L.L <= 128 && L.Q == 256;
+  for (int l = 0; l < L.L && g->v3_ok; ++l) g->v3_ok = g->layers[l].G == 64;
+  for (int i = 0; i < L.n_head && g->v3_ok; ++i) g->v3_ok = L.head_ch[i + 1] == 256 && L.head_ch[i] % 32 == 0 && L.head_ch[i] <= 256;
+  if (g->v3_ok) {
+    int64_t pk = 0;
+    auto add3 = [&](int64_t src, int K, int N, int chunkK, int mode) {
+      wn_gen::Pack3 p{src, pk, K, N, chunkK, mode};
+      g->packs3.push_back(p);
+      for (int r0 = 0; r0 < K; r0 += chunkK) {
+        GenChunk ch;
+        ch.off = (uint64_t)(pk + (int64_t)r0 * N) * 4;   // relative to wpk, fixed up below
+        ch.bytes = (uint32_t)(chunkK * N * 4);
+        ch.pad = 0;
+        g->chunks3.push_back(ch);
+      }
+      pk += (int64_t)K * N;
+    };
+    for (int l = 0; l < L.L; ++l) {
+      add3(g->layers[l].wa, L.k * L.R, 128, 64, 1);
+      add3(g->layers[l].wb, g->layers[l].G, 320, 32, 2);
+    }
+    for (int i = 0; i < L.n_head; ++i) add3(L.hw[i], L.head_ch[i], 256, 32, 3);
+    L.wpk = take(pk);
+    for (auto& ch : g->chunks3) ch.off += (uint64_t)L.wpk * 4;
+    for (auto& p : g->packs3) p.dst += L.wpk;
+    if (g->chunks3.size() > 512) g->v3_ok = false;
+    L.chunks3_dev = take((int64_t)(sizeof(GenChunk) * g->chunks3.size() + 3) / 4 + 4);
+  }
   L.maxw = (maxw + 3) / 4 * 4;
   L.total = off;
   *out = g;
@@ -870,6 +1287,14 @@ extern "C" int wn_gen_prime(wn_gen* g, const float* params, const int32_t* windo
   if (!g->chunks.empty())
     WN_CHECK_CUDA(cudaMemcpyAsync(S + L.chunks_dev, g->chunks.data(), sizeof(GenChunk) * g->chunks.size(),
                                   cudaMemcpyHostToDevice, s));
+  if (g->v3_ok) {
+    for (const auto& p : g->packs3) {
+      gen_pack_v3<<<nb((int64_t)p.K * p.N), 256, 0, s>>>(S + p.src, S + p.dst, p.K, p.N, p.chunkK, p.mode);
+      WN_CHECK_LAUNCH();
+    }
+    WN_CHECK_CUDA(cudaMemcpyAsync(S + L.chunks3_dev, g->chunks3.data(), sizeof(GenChunk) * g->chunks3.size(),
+                                  cudaMemcpyHostToDevice, s));
+  }
   g->primed = true;
   g->t = Win;
   g->steps_done = 0;
