@@ -8,6 +8,7 @@
 // only the last column is computed, sampling happens on device and the loop over
 // audio samples never returns to the host.  Arithmetic is exact fp32 (FFMA) so
 // greedy sequences can match the oracle.
+#include <stdlib.h>
 #include <string.h>
 
 #include "wn_common.h"
@@ -655,8 +656,8 @@ __global__ void __launch_bounds__(GT + (STREAM ? 32 : 0)) gen_kernel(GenArgs a) 
 //     reduce-scatter -- no shared-memory partials, no barrier between matvec and epilogue;
 //   * the gate runs inside the warp that produced a_f/a_g, the skip accumulators stay in registers
 //     for the whole step; two block barriers per layer remain (z visible, x visible).
-constexpr int V3_STAGE_BYTES = 40960;
-constexpr int V3_STAGES = 4;
+constexpr int V3_STAGE_BYTES = 81920;   // one whole per-layer matrix per stage (WA 64 KB, WB 80 KB)
+constexpr int V3_STAGES = 2;
 
 // acc[s] += sum over this lane's rows of ITS output: per chunk NQ float4 of packed weights (4 consecutive rows of
 // one output each) against NQ float4 of the input vector.  f4_off/q_stride locate the lane's float4s inside a
@@ -674,19 +675,22 @@ __device__ __forceinline__ void mv4(StreamCtx& cx, int nchunks, int f4_off, int 
       const int kk = c * chunkK + row0;
       const float* xp = kk < Ksplit ? xa + kk : xb + (kk - Ksplit);
       const int ld = kk < Ksplit ? lda : ldb;
-      float4 wv[NQ];
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) wv[q] = wp[q * q_stride];
+      for (int q0 = 0; q0 < NQ; q0 += 4) {
+        float4 wv[4];
 #pragma unroll
-      for (int s = 0; s < NS; ++s)
+        for (int q = 0; q < 4; ++q) wv[q] = wp[(q0 + q) * q_stride];
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-          const float4 x = *reinterpret_cast<const float4*>(xp + s * ld + q * 4);
-          acc[s] = fmaf(wv[q].x, x.x, acc[s]);
-          acc[s] = fmaf(wv[q].y, x.y, acc[s]);
-          acc[s] = fmaf(wv[q].z, x.z, acc[s]);
-          acc[s] = fmaf(wv[q].w, x.w, acc[s]);
-        }
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 x = *reinterpret_cast<const float4*>(xp + s * ld + (q0 + q) * 4);
+            acc[s] = fmaf(wv[q].x, x.x, acc[s]);
+            acc[s] = fmaf(wv[q].y, x.y, acc[s]);
+            acc[s] = fmaf(wv[q].z, x.z, acc[s]);
+            acc[s] = fmaf(wv[q].w, x.w, acc[s]);
+          }
+      }
     }
     __syncwarp();
     if (lane == 0) tc::mbar_arrive(cx.empty0 + 8 * stage);
@@ -873,8 +877,8 @@ __global__ void __launch_bounds__(GT + 32) gen_kernel_v3(GenArgs a) {
         float acc[NS];
 #pragma unroll
         for (int s = 0; s < NS; ++s) acc[s] = 0.f;
-        mv4<NS, 4>(cx, (L.k * R) / 64, (warp * 4) * 32 + lane, 32, 64, slA * 16, true, xpast + l * pastw, L.L * pastw, xv,
-                   R, pastw, acc);
+        mv4<NS, 8>(cx, 1, (warp * 8) * 32 + lane, 32, L.k * R, slA * 32, true, xpast + l * pastw, L.L * pastw, xv, R, pastw,
+                   acc);
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
           float v = acc[s];
@@ -897,7 +901,7 @@ __global__ void __launch_bounds__(GT + 32) gen_kernel_v3(GenArgs a) {
         float acc[NS];
 #pragma unroll
         for (int s = 0; s < NS; ++s) acc[s] = 0.f;
-        mv4<NS, 8>(cx, G / 32, tid, R + 256, 32, 0, actB, zv, 128, zv, 128, G, acc);
+        mv4<NS, 16>(cx, 1, tid, R + 256, G, 0, actB, zv, 128, zv, 128, G, acc);
         if (actB) {
           const float bb = ly.has_bb ? st[ly.bb + tid] : 0.f;
 #pragma unroll
@@ -923,7 +927,7 @@ __global__ void __launch_bounds__(GT + 32) gen_kernel_v3(GenArgs a) {
       float acc[NS];
 #pragma unroll
       for (int s = 0; s < NS; ++s) acc[s] = 0.f;
-      mv4<NS, 4>(cx, L.head_ch[hi] / 32, (warp * 4) * 32 + lane, 32, 32, slH * 16, true, hin, 256, hin, 256, L.head_ch[hi],
+      mv4<NS, 8>(cx, L.head_ch[hi] / 64, (warp * 8) * 32 + lane, 32, 64, slH * 32, true, hin, 256, hin, 256, L.head_ch[hi],
                  acc);
       const bool last = hi == L.n_head - 1;
 #pragma unroll
@@ -990,17 +994,19 @@ __global__ void gen_pack_v3(const float* __restrict__ src, float* __restrict__ d
   const int k = idx / N, n = idx % N;
   const int c = k / chunkK, kr = k % chunkK, comp = kr & 3;
   int64_t f4;
-  if (mode == 1) {
+  if (mode == 1) {          // 4 K slices per warp, 8 outputs per warp (4 a_f + 4 a_g)
     const int G = N / 2, ch = n < G ? n : n - G;
     const int w = ch / 4, ol = (n < G ? 0 : 4) + ch % 4;
-    const int sl = kr / 16, q = (kr % 16) / 4;
-    f4 = (int64_t)(w * 4 + q) * 32 + sl * 8 + ol;
-  } else if (mode == 2) {
+    const int rps = chunkK / 4, nq = rps / 4;
+    const int sl = kr / rps, q = (kr % rps) / 4;
+    f4 = (int64_t)(w * nq + q) * 32 + sl * 8 + ol;
+  } else if (mode == 2) {   // one output per thread
     f4 = (int64_t)(kr / 4) * N + n;
-  } else {
+  } else {                  // 2 K slices per warp, 16 outputs per warp
     const int w = n / 16, ol = n % 16;
-    const int sl = kr / 16, q = (kr % 16) / 4;
-    f4 = (int64_t)(w * 4 + q) * 32 + sl * 16 + ol;
+    const int rps = chunkK / 2, nq = rps / 4;
+    const int sl = kr / rps, q = (kr % rps) / 4;
+    f4 = (int64_t)(w * nq + q) * 32 + sl * 16 + ol;
   }
   dst[(int64_t)c * chunkK * N + f4 * 4 + comp] = src[idx];
 }
@@ -1052,11 +1058,16 @@ int pick_ns(const wn_gen* g) {
 
 int run_gen(wn_gen* g, GenArgs& a, cudaStream_t s) {
   const int ns = pick_ns(g);
-  if (g->v3_ok && gen_smem_bytes_v3(g->lay, ns > 2 ? 2 : ns) <= 200 * 1024) {
+  if (g->v3_ok) {
+    int ns3 = ns;
+    if (const char* e = getenv("WN_GEN_NS")) ns3 = atoi(e);
+    if (ns3 != 1 && ns3 != 2 && ns3 != 4) ns3 = 2;
+    while (ns3 > 1 && gen_smem_bytes_v3(g->lay, ns3) > 208 * 1024) ns3 /= 2;
     a.chunks = (const GenChunk*)(g->state + g->lay.chunks3_dev);
     a.n_chunks = (int)g->chunks3.size();
-    if (ns == 1) return launch_gen_v3<1>(a, s);
-    return launch_gen_v3<2>(a, s);
+    if (ns3 == 1) return launch_gen_v3<1>(a, s);
+    if (ns3 == 2) return launch_gen_v3<2>(a, s);
+    return launch_gen_v3<4>(a, s);
   }
   if (g->stream_ok && gen_smem_bytes(g->lay, ns, true) <= 208 * 1024) {   // + ~16 KB static (schedule, layer table)
     if (ns == 1) return launch_gen<1, true>(a, s);
@@ -1163,10 +1174,10 @@ extern "C" int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen**
   if (g->chunks.size() > 512 || L.L > 128 || L.R % 4 != 0) g->stream_ok = false;   // MAX_CHUNKS, s_layers, float4 taps
   L.chunks_dev = take((int64_t)(sizeof(GenChunk) * g->chunks.size() + 3) / 4 + 4);
   // v3 (packed weights, warp-shuffle reductions): needs 2G = 128, R + S = 320, head widths 256, one causal layer
-  g->v3_ok = c.n_causal == 1 && L.R + L.S == 320 && L.S == 256 && L.R % 4 == 0 && (L.k * L.R) % 64 == 0 && ((L.k - 1) * L.R) % 2 == 0 &&
+  g->v3_ok = c.n_causal == 1 && L.R + L.S == 320 && L.S == 256 && L.R % 4 == 0 && L.k * L.R == 128 && ((L.k - 1) * L.R) % 32 == 0 &&
              L.L <= 128 && L.Q == 256;
   for (int l = 0; l < L.L && g->v3_ok; ++l) g->v3_ok = g->layers[l].G == 64;
-  for (int i = 0; i < L.n_head && g->v3_ok; ++i) g->v3_ok = L.head_ch[i + 1] == 256 && L.head_ch[i] % 32 == 0 && L.head_ch[i] <= 256;
+  for (int i = 0; i < L.n_head && g->v3_ok; ++i) g->v3_ok = L.head_ch[i + 1] == 256 && L.head_ch[i] % 64 == 0 && L.head_ch[i] <= 256;
   if (g->v3_ok) {
     int64_t pk = 0;
     auto add3 = [&](int64_t src, int K, int N, int chunkK, int mode) {
@@ -1182,10 +1193,10 @@ extern "C" int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen**
       pk += (int64_t)K * N;
     };
     for (int l = 0; l < L.L; ++l) {
-      add3(g->layers[l].wa, L.k * L.R, 128, 64, 1);
-      add3(g->layers[l].wb, g->layers[l].G, 320, 32, 2);
+      add3(g->layers[l].wa, L.k * L.R, 128, L.k * L.R, 1);     // whole matrix = one chunk (64 KB)
+      add3(g->layers[l].wb, g->layers[l].G, 320, g->layers[l].G, 2);   // 80 KB
     }
-    for (int i = 0; i < L.n_head; ++i) add3(L.hw[i], L.head_ch[i], 256, 32, 3);
+    for (int i = 0; i < L.n_head; ++i) add3(L.hw[i], L.head_ch[i], 256, 64, 3);   // 64 KB chunks
     L.wpk = take(pk);
     for (auto& ch : g->chunks3) ch.off += (uint64_t)L.wpk * 4;
     for (auto& p : g->packs3) p.dst += L.wpk;
