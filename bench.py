@@ -353,8 +353,16 @@ def main():
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 gms = float(t[0])
             total_streams = n * world if n_total > 1 else 1
-            gen["batch_%d" % n_total] = {"samples_per_s": total_streams * steps / (gms / 1e3), "streams": total_streams,
-                                         "steps": steps, "us_per_step": 1e3 * gms / steps}
+            us = 1e3 * gms / steps
+            sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+            n_ctas = -(-n // (1 if n <= 148 else 2))
+            gen["batch_%d" % n_total] = {
+                "samples_per_s": total_streams * steps / (gms / 1e3), "streams": total_streams, "steps": steps,
+                "us_per_step": us, "cycles_per_sample_per_stream": us * sm_mhz,
+                # every CTA streams the 5.08 MB fp32 weight set once per step through its cp.async.bulk ring
+                "weight_stream_gbs_per_sm": 1270272 * 4 / (us * 1e-6) / 1e9,
+                "weight_stream_gbs_all_ctas": n_ctas * world * 1270272 * 4 / (us * 1e-6) / 1e9,
+                "bound": "dependency-chain latency (30 layers x 2 block barriers + head per sample)"}
         line["fast_gen"] = gen
 
     # ---- CPU baseline (rank 0, N == 1 only) -----------------------------------------------------
