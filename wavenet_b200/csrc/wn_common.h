@@ -107,6 +107,7 @@ struct wn_handle {
   bool tc_tab_uploaded = false;
   bool tape_has_tfsg = false;      // tanh | sigmoid of every layer are on the tape
   bool head_tc = false;            // head activations on the tape came from the tensor-core head
+  bool tape_gates_zs = false;      // tensor-core tape stores (z, sigmoid) [fused kernel] instead of (tanh | sigmoid)
   bool tape_tc = false;            // tape written by the tensor-core forward (stored head activations are post-ReLU)
   int fuse_head_relu = 0;          // set by wn_forward_loss: nobody reads the raw skip sum, ReLU it in the skip GEMM
   bool skip_is_relu = false;
@@ -184,6 +185,7 @@ int optim_clip_adam(float* params, float* grads, float* m, float* v, int64_t n, 
 
 // ---- tcgen05 TF32 kernels (wn_tc.cu) ---------------------------------------------
 bool tc_layer_supported(const wn_handle* h);
+bool tc_fused_supported(const wn_handle* h);
 bool tc_head_supported(const wn_handle* h);
 int tc_forward_residual(wn_handle* h, const float* params, cudaStream_t s);
 int tc_forward_head(wn_handle* h, const float* params, int T, bool external, cudaStream_t s);

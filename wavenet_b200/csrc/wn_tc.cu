@@ -342,10 +342,11 @@ struct GemmTcArgs {
   int y_slab_cols;         // >0: column block c goes to Y + (c / y_slab_cols) * y_slab_stride, column c % y_slab_cols
   int64_t y_slab_stride;
   // gate-backward epilogue (N == G): result is dz; writes da_f | da_g into dafg[row][0..2G) instead of Y
-  const float* gate_sg;    // [rows][G] sigmoid, or null
+  const float* gate_sg;    // [rows][gate_sg_ld] sigmoid, or null
   const float* gate_z;     // [rows][G] z = tanh * sigmoid
   float* gate_dafg;
-  int gate_zp;
+  int gate_zp, gate_sg_ld;
+  int zero_rows_below;     // output rows with t < this are forced to 0 (quirk Q1 zero prefix)
 };
 
 template <int BN>
@@ -476,7 +477,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             const int64_t orow = (int64_t)b * a.rows_out + t;
             r4[jj] = *reinterpret_cast<const float4*>(a.Rsd + orow * a.ldr + col);
             z4[jj] = *reinterpret_cast<const float4*>(a.gate_z + orow * a.N + col);
-            sg4[jj] = *reinterpret_cast<const float4*>(a.gate_sg + orow * a.N + col);
+            sg4[jj] = *reinterpret_cast<const float4*>(a.gate_sg + orow * a.gate_sg_ld + col);
           }
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
@@ -522,6 +523,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             float4 o = *reinterpret_cast<const float4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
             o.x += bb.x, o.y += bb.y, o.z += bb.z, o.w += bb.w;
             if (a.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+            if (t < a.zero_rows_below) o = make_float4(0.f, 0.f, 0.f, 0.f);
             if (a.Rsd) o.x += r4[jj].x, o.y += r4[jj].y, o.z += r4[jj].z, o.w += r4[jj].w;
             if (a.mask) {
               o.x = x4[jj].x > 0.f ? o.x : 0.f;
@@ -785,7 +787,8 @@ struct TcEpilogue {
   const float* gate_sg = nullptr;
   const float* gate_z = nullptr;
   float* gate_dafg = nullptr;
-  int gate_zp = 0;
+  int gate_zp = 0, gate_sg_ld = 0;
+  int zero_rows_below = 0;
 };
 
 // Y[(b, t)][0..N) = epi( sum_s A[slab_idx[s]][b][t + row_off[s]][:] . Wt[:, s*K ..]^T ),  Wt is [N][ns*K] (TF32-rounded)
@@ -819,6 +822,8 @@ int tc_gemm(const wn_handle* h, const TcOperand& A, int ns, const int* slab_idx,
   g.gate_z = e.gate_z;
   g.gate_dafg = e.gate_dafg;
   g.gate_zp = e.gate_zp;
+  g.gate_sg_ld = e.gate_sg_ld ? e.gate_sg_ld : N;
+  g.zero_rows_below = e.zero_rows_below;
   g.rows_out = rows_out;
   g.nslab = ns;
   g.ksub = A.K / SUBK;
@@ -871,7 +876,8 @@ int tc_wgrad(const wn_handle* h, const TcOperand& dY, int a_row_off, int a_c0, i
   return launch_wgrad<256>(ta, tb, g, h->sm_count, s);
 }
 
-bool tc_layer_supported(const wn_handle* h) {
+// fused layer kernel: the benchmark shape (R = G = 64, k = 2, no biases)
+bool tc_fused_supported(const wn_handle* h) {
   if (h->R != 64 || h->cfg.residual_filter_width != 2) return false;
   for (const ResLayer& l : h->layers)
     if (l.G != 64 || l.wf.b_off >= 0 || l.proj.b_off >= 0) return false;
@@ -879,9 +885,21 @@ bool tc_layer_supported(const wn_handle* h) {
   return get_encode() != nullptr;
 }
 
+// any network whose channel counts are multiples of 32 and fit one N tile: layers run as slab GEMMs
+// (gate on SIMT), e.g. the reference default R=256/G=128 (train_audio/model.py:24-43) or Params() defaults
+bool tc_layer_supported(const wn_handle* h) {
+  if (tc_fused_supported(h)) return true;
+  if (h->cfg.residual_filter_width != 2 || h->R % 32 != 0 || h->R > 256 || h->S % 32 != 0 || h->S > 256) return false;
+  const int G = h->layers[0].G;
+  if (G % 32 != 0 || 2 * G > 256 || (int)h->layers.size() > MAX_SLABS) return false;
+  for (const ResLayer& l : h->layers)
+    if (l.G != G || l.wf.b_off >= 0 || l.proj.b_off >= 0) return false;
+  return get_encode() != nullptr;
+}
+
 bool tc_head_supported(const wn_handle* h) {
   for (const ConvParam& c : h->head)
-    if (c.in_ch % 32 != 0 || c.out_ch % 32 != 0 || c.out_ch > 256 || c.in_ch > 256) return false;
+    if ((c.in_ch != 64 && c.in_ch != 128 && c.in_ch != 256) || c.out_ch % 32 != 0 || c.out_ch > 256) return false;
   return h->S % 32 == 0 && get_encode() != nullptr;
 }
 
@@ -902,8 +920,8 @@ int tc_prepare_weights(wn_handle* h, const float* params, cudaStream_t s) {
   }
   dim3 grid(16, L);
   tc_prep_kernel<<<grid, 256, 0, s>>>(params, (const TcTabEntry*)(h->ws + t.tc_tab), h->ws + t.tc_w1, h->ws + t.tc_w2,
-                                      h->ws + t.tc_ws, h->ws + t.tc_w1t, h->ws + t.tc_wpt, h->ws + t.tc_wst, L, h->R, 64,
-                                      h->S, 2);
+                                      h->ws + t.tc_ws, h->ws + t.tc_w1t, h->ws + t.tc_wpt, h->ws + t.tc_wst, L, h->R,
+                                      h->layers[0].G, h->S, 2);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
@@ -914,14 +932,38 @@ int tc_skip_gemm(wn_handle* h, cudaStream_t s);
 int tc_forward_residual(wn_handle* h, const float* params, cudaStream_t s) {
   const Tape& t = h->tape;
   const int L = (int)h->layers.size();
-  const int R = 64, G = 64;
   WN_TRY(tc_prepare_weights(h, params, s));
-  static bool attr = false;
-  if (!attr) {
-    WN_CHECK_CUDA(cudaFuncSetAttribute(tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM + 1024));
-    attr = true;
+  if (tc_fused_supported(h)) {
+    static bool attr = false;
+    if (!attr) {
+      WN_CHECK_CUDA(cudaFuncSetAttribute(tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM + 1024));
+      attr = true;
+    }
+    for (int l = 0; l < L; ++l) WN_TRY(tc_layer_launch(h, l, s));
+    h->tape_gates_zs = true;     // tape keeps (z, sigmoid)
+  } else {
+    // generic shapes: a = [x(t-d) | x(t)] . W1^T as a 2-slab GEMM (zero prefix in the epilogue), SIMT gate,
+    // projection GEMM with the residual in the epilogue
+    const int R = h->R, G = h->layers[0].G;
+    for (int l = 0; l < L; ++l) {
+      const ResLayer& ly = h->layers[l];
+      TcOperand X{h->ws + t.x[l], R, t.W, t.B, 1, 0};
+      const int sidx[2] = {0, 0};
+      const int roff[2] = {-ly.dilation, 0};
+      TcEpilogue e;
+      e.zero_rows_below = wn_zero_prefix(t.W, ly.dilation, 2);
+      WN_TRY(tc_gemm(h, X, 2, sidx, roff, t.W, h->ws + t.tc_w1 + (int64_t)l * 2 * G * 2 * R, 2 * G, e, h->ws + t.tfsg[l],
+                     2 * G, s));
+      WN_TRY(simt_gate_forward(h->ws + t.tfsg[l], h->ws + t.z[l], t.P, G, s));
+      TcOperand Z{h->ws + t.z[l], G, t.W, t.B, 1, 0};
+      const int zero = 0;
+      TcEpilogue e2;
+      e2.Rsd = h->ws + t.x[l];
+      e2.ldr = R;
+      WN_TRY(tc_gemm(h, Z, 1, nullptr, &zero, t.W, h->ws + t.tc_w2 + (int64_t)l * R * G, R, e2, h->ws + t.x[l + 1], R, s));
+    }
+    h->tape_gates_zs = false;    // tape keeps (tanh | sigmoid) like the SIMT path
   }
-  for (int l = 0; l < L; ++l) WN_TRY(tc_layer_launch(h, l, s));
   // sum_skip = sum_l Ws_l z_l as one GEMM over K = L*G (z buffers are equally spaced slabs)
   return tc_skip_gemm(h, s);
 }
@@ -958,7 +1000,7 @@ int tc_layer_launch(wn_handle* h, int l, cudaStream_t s) {
 int tc_skip_gemm(wn_handle* h, cudaStream_t s) {
   const Tape& t = h->tape;
   const int L = (int)h->layers.size();
-  const int G = 64;
+  const int G = h->layers[0].G;
   const int64_t zstride = L > 1 ? t.z[1] - t.z[0] : 0;
   for (int l = 1; l < L; ++l)
     WN_REQUIRE(t.z[l] - t.z[l - 1] == zstride, WN_EINVAL, "z slabs are not equally spaced");
@@ -1013,7 +1055,7 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
   const int64_t P = t.P;
   const int nh = (int)h->head.size();
   const int L = (int)h->layers.size();
-  const int R = 64, G = 64, S = h->S;
+  const int R = h->R, G = h->layers[0].G, S = h->S;
   float* ws = h->ws;
   const int zero = 0;
   // ---- head ----
@@ -1052,39 +1094,92 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
   TcOperand DS{dskip, S, T, B, 1, 0};
   const int wt = W - T, nwt = -(W - T);
   const int64_t zstride = L > 1 ? t.z[1] - t.z[0] : (int64_t)P * G;
-  // ---- skip path for ALL layers at once (mirror of the forward skip GEMM) ----
-  //  dzs[l] = dskip . Ws_l   : GEMMs with N = 4 layers x 64, each column block written to its layer slab
-  //  dWs_l  = dskip^T . z_l  : wgrad with the B operand gathered from 4 z slabs per launch
-  for (int l0 = 0; l0 < L; l0 += 4) {
-    const int nl = L - l0 < 4 ? L - l0 : 4;
-    TcEpilogue e;
-    e.y_slab_cols = G;
-    e.y_slab_stride = (int64_t)P * G;
-    WN_TRY(tc_gemm(h, DS, 1, nullptr, &nwt, W, ws + t.tc_wst + (int64_t)l0 * G * S, nl * G, e,
-                   ws + t.dzs + (int64_t)l0 * P * G, G, s));
-    if (nl == 3) continue;   // NB must be 64/128/256: handled below layer by layer
-    TcOperand Z{ws + t.z[0], G, W, B, L, zstride};
-    int boff[4], bidx[4];
-    float* dws[4];
-    for (int m0 = 0; m0 < S; m0 += 128) {
-      const int mv = S - m0 < 128 ? S - m0 : 128;
-      for (int j = 0; j < nl; ++j) {
-        boff[j] = wt;
-        bidx[j] = l0 + j;
-        dws[j] = grads + h->layers[l0 + j].skip.w_off + (int64_t)m0 * G;
+  auto nb_ok = [](int nb) { return nb == 64 || nb == 128 || nb == 256; };
+  // generic weight-gradient helper: dW(m, c) += dY[.., m]^T X[.., c] over M in 128-row halves; rows below `split`
+  // go to dWa, the rest to dWb (wf | wg); falls back to the SIMT kernel when the tile shape is not MMA-friendly
+  auto wgrad_any = [&](const TcOperand& dY, int a_row_off, int Mtot, int split, const TcOperand& X, int x_row_off,
+                       int rows_it, float* dWa, float* dWb, int64_t sn, int64_t sk) -> int {
+    if (!nb_ok(X.K)) {
+      WgradArgs wg;
+      memset(&wg, 0, sizeof(wg));
+      for (int part = 0; part < (dWb ? 2 : 1); ++part) {
+        const int m0 = part == 0 ? 0 : split, m1 = part == 0 ? (dWb ? split : Mtot) : Mtot;
+        wg.dY = dY.ptr + m0;
+        wg.ldd = dY.K;
+        wg.N = m1 - m0;
+        wg.dy_rows_out = rows_it;
+        wg.dy_rows_in = dY.rows_in;
+        wg.dy_in_off = a_row_off;
+        wg.A = X.ptr;
+        wg.lda = X.K;
+        wg.K = X.K;
+        wg.ntaps = 1;
+        wg.shift[0] = 0;
+        wg.M = (int64_t)dY.num_seq * rows_it;
+        wg.rows_out = rows_it;
+        wg.rows_in = X.rows_in;
+        wg.in_off = x_row_off;
+        wg.dW = part == 0 ? dWa : dWb;
+        wg.sn = sn;
+        wg.sk = sk;
+        wg.st = 0;
+        WN_TRY(simt_wgrad(wg, h->sm_count, s));
       }
-      WN_TRY(tc_wgrad(h, DS, 0, m0, mv, Z, nl, boff, bidx, dws, nullptr, 128, T, G, 1, s));
+      return WN_OK;
     }
-  }
-  if (L % 4 == 3) {
-    for (int l = L - 3; l < L; ++l) {
-      TcOperand Z{ws + t.z[l], G, W, B, 1, 0};
+    for (int m0 = 0; m0 < Mtot; m0 += 128) {
+      const int mv = Mtot - m0 < 128 ? Mtot - m0 : 128;
+      float* d0;
+      float* d1 = nullptr;
+      int msplit = 128;
+      if (!dWb || m0 + mv <= split) {
+        d0 = dWa + (int64_t)m0 * sn;
+      } else if (m0 >= split) {
+        d0 = dWb + (int64_t)(m0 - split) * sn;
+      } else {
+        d0 = dWa + (int64_t)m0 * sn;
+        d1 = dWb;
+        msplit = split - m0;
+      }
+      WN_TRY(tc_wgrad(h, dY, a_row_off, m0, mv, X, 1, &x_row_off, nullptr, &d0, d1 ? &d1 : nullptr, msplit, rows_it, sn, sk, s));
+    }
+    return WN_OK;
+  };
+  // ---- skip path for ALL layers at once (mirror of the forward skip GEMM) ----
+  //  dzs[l] = dskip . Ws_l   : GEMMs with N = nl layers x G, each column block written to its layer slab
+  //  dWs_l  = dskip^T . z_l  : wgrad with the B operand gathered from nl z slabs per launch
+  int nl_max = 256 / G;
+  if (nl_max > 4) nl_max = 4;
+  for (int l0 = 0; l0 < L;) {
+    int nl = L - l0 < nl_max ? L - l0 : nl_max;
+    while (nl > 1 && !nb_ok(nl * G)) --nl;
+    {
+      TcEpilogue e;
+      e.y_slab_cols = G;
+      e.y_slab_stride = (int64_t)P * G;
+      WN_TRY(tc_gemm(h, DS, 1, nullptr, &nwt, W, ws + t.tc_wst + (int64_t)l0 * G * S, nl * G, e,
+                     ws + t.dzs + (int64_t)l0 * P * G, G, s));
+    }
+    if (nb_ok(nl * G)) {
+      TcOperand Z{ws + t.z[0], G, W, B, L, zstride};
+      int boff[4], bidx[4];
+      float* dws[4];
       for (int m0 = 0; m0 < S; m0 += 128) {
         const int mv = S - m0 < 128 ? S - m0 : 128;
-        float* dw = grads + h->layers[l].skip.w_off + (int64_t)m0 * G;
-        WN_TRY(tc_wgrad(h, DS, 0, m0, mv, Z, 1, &wt, nullptr, &dw, nullptr, 128, T, G, 1, s));
+        for (int j = 0; j < nl; ++j) {
+          boff[j] = wt;
+          bidx[j] = l0 + j;
+          dws[j] = grads + h->layers[l0 + j].skip.w_off + (int64_t)m0 * G;
+        }
+        WN_TRY(tc_wgrad(h, DS, 0, m0, mv, Z, nl, boff, bidx, dws, nullptr, 128, T, G, 1, s));
+      }
+    } else {
+      for (int j = 0; j < nl; ++j) {
+        TcOperand Z{ws + t.z[l0 + j], G, W, B, 1, 0};
+        WN_TRY(wgrad_any(DS, 0, S, S, Z, wt, T, grads + h->layers[l0 + j].skip.w_off, nullptr, G, 1));
       }
     }
+    l0 += nl;
   }
   // ---- residual layers ----
   int dt = 0;
@@ -1093,30 +1188,56 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
     const ResLayer& ly = h->layers[l];
     const int zp = wn_zero_prefix(W, ly.dilation, 2);
     const float* dzs = ws + t.dzs + (int64_t)l * P * G;
+    const float* sg = h->tape_gates_zs ? ws + t.tfsg[l] : ws + t.tfsg[l] + G;
+    const int sg_ld = h->tape_gates_zs ? G : 2 * G;
+    TcOperand Z{ws + t.z[l], G, W, B, 1, 0};
     if (dout) {
       // dz = dout . Wp + dzs_l, gate derivative fused into the epilogue -> dafg
       TcOperand DO{dout, R, W, B, 1, 0};
       TcEpilogue e;
       e.Rsd = dzs;
       e.ldr = G;
-      e.gate_sg = ws + t.tfsg[l];
+      e.gate_sg = sg;
+      e.gate_sg_ld = sg_ld;
       e.gate_z = ws + t.z[l];
       e.gate_dafg = ws + t.dafg;
       e.gate_zp = zp;
       WN_TRY(tc_gemm(h, DO, 1, nullptr, &zero, W, ws + t.tc_wpt + (int64_t)l * G * R, G, e, ws + t.dz, G, s));
-      TcOperand Z{ws + t.z[l], G, W, B, 1, 0};
-      float* dw = grads + ly.proj.w_off;
-      WN_TRY(tc_wgrad(h, DO, 0, 0, R, Z, 1, &zero, nullptr, &dw, nullptr, 128, W, G, 1, s));
-    } else {
+      WN_TRY(wgrad_any(DO, 0, R, R, Z, 0, W, grads + ly.proj.w_off, nullptr, G, 1));
+    } else if (h->tape_gates_zs) {
       WN_TRY(simt_gate_backward_zs(ws + t.z[l], ws + t.tfsg[l], dzs, ws + t.dafg, P, W, G, zp, s));
+    } else {
+      WN_TRY(simt_gate_backward(ws + t.tfsg[l], dzs, ws + t.dafg, P, W, G, zp, s));
     }
     TcOperand DA{ws + t.dafg, 2 * G, W, B, 1, 0};
     {
+      // dW_{f,g}(o, c, tap) += da[t][o] * x[t - (1-tap) d][c]; taps share a launch while 2R fits one N tile
       TcOperand X{ws + t.x[l], R, W, B, 1, 0};
-      const int boff[2] = {-ly.dilation, 0};
-      float* d0[2] = {grads + ly.wf.w_off + 0, grads + ly.wf.w_off + 1};   // (o, c, tap): tap is the fastest index
-      float* d1[2] = {grads + ly.wg.w_off + 0, grads + ly.wg.w_off + 1};
-      WN_TRY(tc_wgrad(h, DA, 0, 0, 2 * G, X, 2, boff, nullptr, d0, d1, G, W, 2 * R, 2, s));
+      if (nb_ok(2 * R)) {
+        const int boff[2] = {-ly.dilation, 0};
+        for (int m0 = 0; m0 < 2 * G; m0 += 128) {
+          const int mv = 2 * G - m0 < 128 ? 2 * G - m0 : 128;
+          float* d0[2];
+          float* d1[2] = {nullptr, nullptr};
+          int msplit = 128;
+          for (int tap = 0; tap < 2; ++tap) {
+            if (m0 + mv <= G) {
+              d0[tap] = grads + ly.wf.w_off + (int64_t)m0 * 2 * R + tap;
+            } else if (m0 >= G) {
+              d0[tap] = grads + ly.wg.w_off + (int64_t)(m0 - G) * 2 * R + tap;
+            } else {
+              d0[tap] = grads + ly.wf.w_off + (int64_t)m0 * 2 * R + tap;
+              d1[tap] = grads + ly.wg.w_off + tap;
+              msplit = G - m0;
+            }
+          }
+          WN_TRY(tc_wgrad(h, DA, 0, m0, mv, X, 2, boff, nullptr, d0, d1[0] ? d1 : nullptr, msplit, W, 2 * R, 2, s));
+        }
+      } else {
+        for (int tap = 0; tap < 2; ++tap)
+          WN_TRY(wgrad_any(DA, 0, 2 * G, G, X, tap == 0 ? -ly.dilation : 0, W, grads + ly.wf.w_off + tap,
+                           grads + ly.wg.w_off + tap, 2 * R, 2));
+      }
     }
     {
       float* dnew = ws + t.dout[dt];
