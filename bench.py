@@ -378,6 +378,33 @@ def main():
                 "bound": "dependency-chain latency (30 layers x 2 block barriers + head per sample)"}
         line["fast_gen"] = gen
 
+    # ---- BASELINE config 1 shape on the GPU: reference default network (train_audio/model.py:24-43), one train.py
+    # step on a 1 s 16 kHz clip, batch 1 (the CPU leg below times the same arithmetic on the host) ----
+    if rank == 0 and world == 1:
+        from wavenet_b200.wavenet import Params
+        pb = Params()
+        pb.causal_conv_channels = [256]
+        pb.residual_conv_channels = [128] * 8
+        pb.residual_num_blocks = 1
+        pb.softmax_conv_channels = [256, 256]
+        netb = WaveNet(pb, seed=0)
+        netb.to_gpu(local_rank)
+        netb.set_precision(args.precision)
+        netb.update_laerning_rate(1e-3)
+        xb_h, tb_h = synth_batch(0, 1, 16000)
+        tw = 16000 - 257
+        xb = torch.from_numpy(xb_h).cuda()
+        tb = torch.from_numpy(np.ascontiguousarray(tb_h[:, 16000 - tw:])).cuda()
+        stepb = lambda: netb.train_step(xb, tb, train_width=tw)
+        for _ in range(3):
+            stepb()
+        msb = timed(stepb, 10)
+        line["config1_reference_default_net"] = {
+            "workload": "R256/G128 x 8 layers, batch 1 x 16000, train_width 15743, fwd+bwd+clip+Adam",
+            "ms_per_step": msb, "samples_per_s": 16000 / (msb / 1e3),
+            "tc_active": bool(lib.wn_tc_active(netb._h)), "tflops": 3 * 3276800 * 16000 / (msb / 1e3) / 1e12}
+        del netb
+
     # ---- CPU baseline (rank 0, N == 1 only) -----------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1

@@ -174,6 +174,13 @@ int wn_gen_step(wn_gen* g, const float* params, const int32_t* x_new, int apply_
  * incremental steps, each feeding its own sample back.  out[n][n_steps]. */
 int wn_gen_run(wn_gen* g, const float* params, int n_steps, int mode, uint64_t seed, int32_t* out, wn_stream_t s);
 
+/* create_batch of train_audio/train.py:14-22 on a device-resident quantised signal: for every start index
+ * (host-drawn with np.random.randint exactly like the reference, then uploaded: B ints) gathers
+ *   x[n]   = signal[start : start + input_width + target_width]
+ *   tgt[n] = signal[start + input_width + 1 : start + input_width + target_width + 1]. */
+int wn_crop_batch(const int32_t* signal, int64_t signal_len, const int32_t* starts, int B, int input_width,
+                  int target_width, int32_t* x, int32_t* tgt, wn_stream_t s);
+
 /* ---- data.py helpers on device ----------------------------------------------
  * onehot_pixel_image inverse: argmax over Q of a (B,Q,1,W) one-hot -> int32. */
 int wn_onehot_to_index(const float* onehot_bq1w, int B, int Q, int W, int32_t* idx, wn_stream_t s);

@@ -357,3 +357,18 @@ def test_streamed_generator_many_streams(n):
     # fp32 vs fp64 can flip an argmax on a near tie; a flipped stream then diverges: allow a tiny fraction
     bad_streams = mism.any(axis=1).mean()
     assert bad_streams <= 0.01, bad_streams
+
+
+def test_device_crop_batch_matches_reference_create_batch():
+    """train_audio/train.py:14-22 restated vs wn_crop_batch with the same np.random stream."""
+    rng = np.random.default_rng(0)
+    signal = rng.integers(0, 256, 5000).astype(np.int32)
+    iw, tw, B = 257, 300, 7
+    np.random.seed(3)
+    idx = np.random.randint(0, signal.size - tw - iw - 1, size=B)
+    want_x = np.stack([signal[s:s + iw + tw] for s in idx])
+    want_t = np.stack([signal[s + iw + 1:s + iw + tw + 1] for s in idx])
+    cfg = make_cfg("tiny_k2")
+    net = make_net(cfg, O.init_weights(cfg, np.random.default_rng(0), np.float64))
+    x, t = net.create_batch(dev(signal), idx, iw, tw)
+    assert np.array_equal(x.cpu().numpy(), want_x) and np.array_equal(t.cpu().numpy(), want_t)

@@ -47,8 +47,12 @@ def train_audio(filename, batch_size=16, train_width=16, repeat=1000):
     sum_loss = 0
     signals = np.insert(signals, 0, np.full((input_width,), 127, dtype=np.int32), axis=0)
 
+    import torch
+    signals_dev = torch.from_numpy(np.ascontiguousarray(signals, dtype=np.int32)).cuda()   # resident for the whole file
     for batch_index in range(0, repeat):
-        input_batch, target_batch = create_batch(signals, batch_size, input_width, train_width)
+        # same np.random stream as create_batch (train.py:15); the gather itself runs on the device
+        indecis = np.random.randint(0, signals.size - train_width - input_width - 1, size=batch_size)
+        input_batch, target_batch = wavenet.create_batch(signals_dev, indecis, input_width, train_width)
         output = wavenet.forward_causal_block(input_batch)
         output, sum_skip_connections = wavenet.forward_residual_block(output)
         output = wavenet.slice_1d(output, output.data.shape[3] - train_width)

@@ -84,6 +84,7 @@ SIGNATURES = {
     "wn_gen_prime": (_I, [_P, _P, _P, _P, _P]),
     "wn_gen_step": (_I, [_P, _P, _P, _I, _P, _P]),
     "wn_gen_run": (_I, [_P, _P, _I, _I, C.c_uint64, _P, _P]),
+    "wn_crop_batch": (_I, [_P, _L, _P, _I, _I, _I, _P, _P, _P]),
     "wn_onehot_to_index": (_I, [_P, _I, _I, _I, _P, _P]),
     "wn_mulaw_encode": (_I, [_P, _L, _I, _P, _P]),
     "wn_mulaw_decode": (_I, [_P, _L, _I, C.c_double, _P, _P]),

@@ -1363,6 +1363,34 @@ extern "C" int wn_gen_run(wn_gen* g, const float* params, int n_steps, int mode,
 
 // ---- data.py on device -------------------------------------------------------------
 namespace {
+__global__ void crop_batch_kernel(const int32_t* __restrict__ signal, int64_t len, const int32_t* __restrict__ starts,
+                                  int B, int iw, int tw, int32_t* __restrict__ x, int32_t* __restrict__ tgt) {
+  const int n = blockIdx.y;
+  const int64_t st = starts[n];
+  const int wx = iw + tw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wx + tw; i += gridDim.x * blockDim.x) {
+    if (i < wx) {
+      const int64_t p = st + i;
+      x[(int64_t)n * wx + i] = p < len ? signal[p] : 127;
+    } else {
+      const int j = i - wx;
+      const int64_t p = st + iw + 1 + j;
+      tgt[(int64_t)n * tw + j] = p < len ? signal[p] : 127;
+    }
+  }
+}
+}  // namespace
+
+extern "C" int wn_crop_batch(const int32_t* signal, int64_t signal_len, const int32_t* starts, int B, int input_width,
+                             int target_width, int32_t* x, int32_t* tgt, wn_stream_t s) {
+  WN_REQUIRE(signal && starts && x && tgt && B >= 1 && input_width >= 0 && target_width >= 1, WN_EINVAL, "bad argument");
+  dim3 grid((unsigned)((input_width + 2 * target_width + 255) / 256), (unsigned)B);
+  crop_batch_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(signal, signal_len, starts, B, input_width, target_width, x, tgt);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+namespace {
 __global__ void mulaw_encode_kernel(const double* __restrict__ sig, int64_t n, int Q, int32_t* __restrict__ q) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

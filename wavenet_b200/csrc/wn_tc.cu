@@ -581,21 +581,23 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128_32b(uint32_t smem_addr, u
   return d;
 }
 
-constexpr int WG_KC = 64;                 // positions per pipeline stage
-constexpr int WG_SUB = WG_KC * 128;       // bytes of a [32 x 32] sub-tile
-
-template <int NB>
+// MH = number of 128-row halves of dY handled per CTA (2 lets a 256-channel gradient read X only once)
+template <int NB, int MH>
 struct WgradCfg {
-  static constexpr int STAGE = 4 * WG_SUB + (NB / 32) * WG_SUB;
+  static constexpr int KC = MH == 2 ? 32 : 64;          // positions per pipeline stage
+  static constexpr int SUB = KC * 128;                  // bytes of a [KC x 32] sub-tile
+  static constexpr int STAGE = (4 * MH + NB / 32) * SUB;
   static constexpr int STAGES = (200 * 1024) / STAGE > 4 ? 4 : (200 * 1024) / STAGE;
   static constexpr int BAR = STAGES * STAGE;
   static constexpr int SMEM = BAR + 256 + 1024;
+  static constexpr int TMEM_COLS = MH * NB > 256 ? 512 : 256;
 };
 
-template <int NB>
+template <int NB, int MH>
 __global__ void __launch_bounds__(L_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const WgradTcArgs a) {
-  using Cfg = WgradCfg<NB>;
+  using Cfg = WgradCfg<NB, MH>;
+  constexpr int KC = Cfg::KC, SUB = Cfg::SUB;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -615,7 +617,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     prefetch_tmap(&tm_a);
     prefetch_tmap(&tm_b);
   }
-  if (warp == 1) tmem_alloc<256>(smem_u32((const void*)tmem_slot));
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32((const void*)tmem_slot));
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -630,62 +632,67 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     if (lane == 0) {
       for (int it = 0; it < n_local; ++it) {
         const int chunk = c_begin + it;
-        const int b = chunk / a.chunks_per_seq, t0 = (chunk % a.chunks_per_seq) * WG_KC;
+        const int b = chunk / a.chunks_per_seq, t0 = (chunk % a.chunks_per_seq) * KC;
         const int s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
         mbar_wait(empty(s), ph ^ 1);
         const uint32_t st = base + s * Cfg::STAGE;
         mbar_arrive_expect_tx(full(s), Cfg::STAGE);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) tma_load_4d(st + i * WG_SUB, &tm_a, full(s), a.a_c0 + i * SUBK, a.a_row_off + t0, b, 0);
+        for (int i = 0; i < 4 * MH; ++i) tma_load_4d(st + i * SUB, &tm_a, full(s), a.a_c0 + i * SUBK, a.a_row_off + t0, b, 0);
         for (int sl = 0; sl < a.nb_slab; ++sl)
           for (int i = 0; i < a.nb_sub; ++i)
-            tma_load_4d(st + (4 + sl * a.nb_sub + i) * WG_SUB, &tm_b, full(s), i * SUBK, a.b_row_off[sl] + t0, b,
+            tma_load_4d(st + (4 * MH + sl * a.nb_sub + i) * SUB, &tm_b, full(s), i * SUBK, a.b_row_off[sl] + t0, b,
                         a.b_slab_idx[sl]);
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && n_local > 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(128, NB) | (1u << 15) | (1u << 16);   // both operands MN-major
-      constexpr uint32_t lbo = WG_SUB, sbo = 512, kstep = 1024;
+      constexpr uint32_t lbo = SUB, sbo = 512, kstep = 1024;
       for (int it = 0; it < n_local; ++it) {
         const int s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
         mbar_wait(full(s), ph);
         tcgen05_fence_after();
         const uint32_t st = base + s * Cfg::STAGE;
 #pragma unroll
-        for (int k8 = 0; k8 < WG_KC / 8; ++k8)
-          umma_tf32(tmem, umma_desc_mn_sw128_32b(st + k8 * kstep, lbo, sbo),
-                    umma_desc_mn_sw128_32b(st + 4 * WG_SUB + k8 * kstep, lbo, sbo), idesc, (it | k8) > 0);
+        for (int k8 = 0; k8 < KC / 8; ++k8) {
+          const uint64_t bdesc = umma_desc_mn_sw128_32b(st + 4 * MH * SUB + k8 * kstep, lbo, sbo);
+#pragma unroll
+          for (int mh = 0; mh < MH; ++mh)
+            umma_tf32(tmem + mh * NB, umma_desc_mn_sw128_32b(st + 4 * mh * SUB + k8 * kstep, lbo, sbo), bdesc, idesc,
+                      (it | k8) > 0);
+        }
         umma_commit(empty(s));
       }
       umma_commit(acc_full);
     }
   } else if (n_local > 0) {
     const int q = warp & 3, half = (warp - 2) >> 2;
-    const int m = q * 32 + lane;
     constexpr int CH = NB / 64;
     mbar_wait(acc_full, 0);
     tcgen05_fence_after();
     const int nb = a.nb_sub * 32;   // channels per slab
 #pragma unroll 1
-    for (int ch = 0; ch < CH; ++ch) {
-      const int c0 = (half * CH + ch) * 32;
-      uint32_t v[32];
-      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
-      tmem_ld_wait();
-      if (m < a.m_valid) {
-        const int sl = c0 / nb, cbase = c0 % nb;
-        float* wrow = m < a.m_split ? a.dW0[sl] + (int64_t)m * a.sn : a.dW1[sl] + (int64_t)(m - a.m_split) * a.sn;
+    for (int mh = 0; mh < MH; ++mh) {
+      const int m = mh * 128 + q * 32 + lane;
+#pragma unroll 1
+      for (int ch = 0; ch < CH; ++ch) {
+        const int c0 = (half * CH + ch) * 32;
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + mh * NB + c0, v);
+        tmem_ld_wait();
+        if (m < a.m_valid) {
+          const int sl = c0 / nb, cbase = c0 % nb;
+          float* wrow = m < a.m_split ? a.dW0[sl] + (int64_t)m * a.sn : a.dW1[sl] + (int64_t)(m - a.m_split) * a.sn;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          atomicAdd(wrow + (int64_t)(cbase + i) * a.sk, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) atomicAdd(wrow + (int64_t)(cbase + i) * a.sk, __uint_as_float(v[i]));
         }
       }
     }
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<256>(tmem);
+  if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -749,16 +756,16 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcArgs& 
   return WN_OK;
 }
 
-template <int NB>
+template <int NB, int MH>
 int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, const WgradTcArgs& g, int sm_count, cudaStream_t s) {
-  using Cfg = WgradCfg<NB>;
+  using Cfg = WgradCfg<NB, MH>;
   static bool attr = false;
   if (!attr) {
-    WN_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    WN_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<NB, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr = true;
   }
   const int grid = g.num_chunks < sm_count ? g.num_chunks : sm_count;
-  tc_wgrad_kernel<NB><<<grid, L_THREADS, Cfg::SMEM, s>>>(ta, tb, g);
+  tc_wgrad_kernel<NB, MH><<<grid, L_THREADS, Cfg::SMEM, s>>>(ta, tb, g);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
@@ -843,8 +850,10 @@ int tc_wgrad(const wn_handle* h, const TcOperand& dY, int a_row_off, int a_c0, i
              const int* b_row_off, const int* b_slab_idx, float* const* dW0, float* const* dW1, int m_split, int rows_it,
              int64_t sn, int64_t sk, cudaStream_t s) {
   const int NB = nb_slab * X.K;
-  WN_REQUIRE(X.K % 32 == 0 && (NB == 64 || NB == 128 || NB == 256) && nb_slab <= 4, WN_EINVAL,
-             "tc_wgrad: unsupported shape X.K=%d slabs=%d", X.K, nb_slab);
+  WN_REQUIRE(X.K % 32 == 0 && (NB == 64 || NB == 128 || NB == 256) && nb_slab <= 4 && m_valid <= 256, WN_EINVAL,
+             "tc_wgrad: unsupported shape X.K=%d slabs=%d M=%d", X.K, nb_slab, m_valid);
+  const int MH = m_valid > 128 ? 2 : 1;
+  const int WG_KC = MH == 2 ? 32 : 64;
   CUtensorMap ta, tb;
   WN_TRY(make_map_4d(&ta, dY.ptr, dY.K, dY.rows_in, dY.num_seq, 1, dY.K, (uint64_t)dY.rows_in * dY.K,
                      (uint64_t)dY.rows_in * dY.num_seq * dY.K, WG_KC, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
@@ -871,9 +880,14 @@ int tc_wgrad(const wn_handle* h, const TcOperand& dY, int a_row_off, int a_c0, i
   g.sk = sk;
   g.chunks_per_seq = (rows_it + WG_KC - 1) / WG_KC;
   g.num_chunks = g.chunks_per_seq * dY.num_seq;
-  if (NB == 64) return launch_wgrad<64>(ta, tb, g, h->sm_count, s);
-  if (NB == 128) return launch_wgrad<128>(ta, tb, g, h->sm_count, s);
-  return launch_wgrad<256>(ta, tb, g, h->sm_count, s);
+  if (MH == 1) {
+    if (NB == 64) return launch_wgrad<64, 1>(ta, tb, g, h->sm_count, s);
+    if (NB == 128) return launch_wgrad<128, 1>(ta, tb, g, h->sm_count, s);
+    return launch_wgrad<256, 1>(ta, tb, g, h->sm_count, s);
+  }
+  if (NB == 64) return launch_wgrad<64, 2>(ta, tb, g, h->sm_count, s);
+  if (NB == 128) return launch_wgrad<128, 2>(ta, tb, g, h->sm_count, s);
+  return launch_wgrad<256, 2>(ta, tb, g, h->sm_count, s);
 }
 
 // fused layer kernel: the benchmark shape (R = G = 64, k = 2, no biases)
@@ -1069,10 +1083,10 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
     const float* Ain = first ? ws + t.skip : ws + t.hbuf[i - 1];
     TcOperand dY{d, cp.out_ch, T, B, 1, 0};
     TcOperand X{Ain, cp.in_ch, rin, B, 1, 0};
-    for (int m0 = 0; m0 < cp.out_ch; m0 += 128) {
-      const int mv = cp.out_ch - m0 < 128 ? cp.out_ch - m0 : 128;
+    for (int m0 = 0; m0 < cp.out_ch; m0 += 256) {
+      const int mv = cp.out_ch - m0 < 256 ? cp.out_ch - m0 : 256;
       float* dw = grads + cp.w_off + (int64_t)m0 * cp.in_ch;
-      WN_TRY(tc_wgrad(h, dY, 0, m0, mv, X, 1, &aoff, nullptr, &dw, nullptr, 128, T, cp.in_ch, 1, s));
+      WN_TRY(tc_wgrad(h, dY, 0, m0, mv, X, 1, &aoff, nullptr, &dw, nullptr, 256, T, cp.in_ch, 1, s));
     }
     if (cp.b_off >= 0) WN_TRY(simt_colsum(d, (int64_t)B * T, cp.out_ch, grads + cp.b_off, s));
     if (first && h->head_external) return WN_OK;
@@ -1127,11 +1141,11 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
       }
       return WN_OK;
     }
-    for (int m0 = 0; m0 < Mtot; m0 += 128) {
-      const int mv = Mtot - m0 < 128 ? Mtot - m0 : 128;
+    for (int m0 = 0; m0 < Mtot; m0 += 256) {
+      const int mv = Mtot - m0 < 256 ? Mtot - m0 : 256;
       float* d0;
       float* d1 = nullptr;
-      int msplit = 128;
+      int msplit = 256;
       if (!dWb || m0 + mv <= split) {
         d0 = dWa + (int64_t)m0 * sn;
       } else if (m0 >= split) {
@@ -1164,14 +1178,14 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
       TcOperand Z{ws + t.z[0], G, W, B, L, zstride};
       int boff[4], bidx[4];
       float* dws[4];
-      for (int m0 = 0; m0 < S; m0 += 128) {
-        const int mv = S - m0 < 128 ? S - m0 : 128;
+      for (int m0 = 0; m0 < S; m0 += 256) {
+        const int mv = S - m0 < 256 ? S - m0 : 256;
         for (int j = 0; j < nl; ++j) {
           boff[j] = wt;
           bidx[j] = l0 + j;
           dws[j] = grads + h->layers[l0 + j].skip.w_off + (int64_t)m0 * G;
         }
-        WN_TRY(tc_wgrad(h, DS, 0, m0, mv, Z, nl, boff, bidx, dws, nullptr, 128, T, G, 1, s));
+        WN_TRY(tc_wgrad(h, DS, 0, m0, mv, Z, nl, boff, bidx, dws, nullptr, 256, T, G, 1, s));
       }
     } else {
       for (int j = 0; j < nl; ++j) {
@@ -1215,11 +1229,11 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
       TcOperand X{ws + t.x[l], R, W, B, 1, 0};
       if (nb_ok(2 * R)) {
         const int boff[2] = {-ly.dilation, 0};
-        for (int m0 = 0; m0 < 2 * G; m0 += 128) {
-          const int mv = 2 * G - m0 < 128 ? 2 * G - m0 : 128;
+        for (int m0 = 0; m0 < 2 * G; m0 += 256) {
+          const int mv = 2 * G - m0 < 256 ? 2 * G - m0 : 256;
           float* d0[2];
           float* d1[2] = {nullptr, nullptr};
-          int msplit = 128;
+          int msplit = 256;
           for (int tap = 0; tap < 2; ++tap) {
             if (m0 + mv <= G) {
               d0[tap] = grads + ly.wf.w_off + (int64_t)m0 * 2 * R + tap;

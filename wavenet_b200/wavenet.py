@@ -477,6 +477,19 @@ class WaveNet(object):
         self.backward()
         self.update()
 
+    def create_batch(self, signal, starts, input_width, target_width):
+        """train_audio/train.py:14-22 on the device.  `signal`: int32 cuda tensor (the silence-padded quantised
+        clip, uploaded once per file); `starts`: the host-drawn crop indices (np.random.randint as in the
+        reference).  Returns (input_batch (B, iw+tw), target_batch (B, tw)) int32 cuda tensors."""
+        self._need_gpu()
+        st = torch.as_tensor(np.asarray(starts, dtype=np.int32)).to(self._device, non_blocking=True)
+        B = int(st.shape[0])
+        x = torch.empty((B, input_width + target_width), dtype=torch.int32, device=self._device)
+        t = torch.empty((B, target_width), dtype=torch.int32, device=self._device)
+        check(self._libh.wn_crop_batch(_ptr(signal), int(signal.numel()), _ptr(st), B, int(input_width), int(target_width),
+                                       _ptr(x), _ptr(t), _stream()))
+        return x, t
+
     def train_step(self, x_idx, target, train_width=None):
         """One fused train.py:58-80 step on int32 device tensors; returns the loss tensor (no sync)."""
         self._need_gpu()
