@@ -182,20 +182,33 @@ __global__ void embed_prepare_kernel(const float* __restrict__ Wc, float* __rest
 __global__ void embed_forward_kernel(const float* __restrict__ emb, const float* __restrict__ bias,
                                      const int32_t* __restrict__ idx, float* __restrict__ out, int64_t P, int W, int R,
                                      int Q, int kc) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P * R) return;
-  const int r = (int)(i % R);
-  const int64_t p = i / R;
-  const int t = (int)(p % W);
-  float v = bias ? bias[r] : 0.f;
-  for (int j = 0; j < kc; ++j) {
-    const int s = kc - 1 - j;
-    if (t - s >= 0) {
-      const int q = idx[p - s];
-      v += emb[((int64_t)j * Q + q) * R + r];
+  // one thread per (position, 4 channels) when R % 4 == 0 (float4 path), else per element; 32-bit index math
+  const bool vec = (R & 3) == 0;
+  const uint32_t rv = vec ? R >> 2 : R;
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (uint64_t)P * rv) return;
+  const uint32_t p = (uint32_t)(i / rv);
+  const uint32_t r = (uint32_t)(i - (uint64_t)p * rv) * (vec ? 4 : 1);
+  const int t = (int)(p % (uint32_t)W);
+  if (vec) {
+    float4 v = bias ? *reinterpret_cast<const float4*>(bias + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < kc; ++j) {
+      const int s = kc - 1 - j;
+      if (t - s >= 0) {
+        const int q = idx[p - s];
+        const float4 e = *reinterpret_cast<const float4*>(emb + ((int64_t)j * Q + q) * R + r);
+        v.x += e.x, v.y += e.y, v.z += e.z, v.w += e.w;
+      }
     }
+    *reinterpret_cast<float4*>(out + (int64_t)p * R + r) = v;
+  } else {
+    float v = bias ? bias[r] : 0.f;
+    for (int j = 0; j < kc; ++j) {
+      const int s = kc - 1 - j;
+      if (t - s >= 0) v += emb[((int64_t)j * Q + idx[p - s]) * R + r];
+    }
+    out[(int64_t)p * R + r] = v;
   }
-  out[i] = v;
 }
 
 __global__ void embed_backward_kernel(const float* __restrict__ dout, const int32_t* __restrict__ idx,
@@ -412,7 +425,7 @@ int simt_embed_prepare(const float* Wc, float* emb, int R, int Q, int kc, cudaSt
 int simt_embed_forward(const float* emb, const float* bias, const int32_t* idx, float* out, int B, int W, int R, int Q,
                        int kc, cudaStream_t s) {
   const int64_t P = (int64_t)B * W;
-  embed_forward_kernel<<<blocks_for(P * R, 256), 256, 0, s>>>(emb, bias, idx, out, P, W, R, Q, kc);
+  embed_forward_kernel<<<blocks_for((R & 3) == 0 ? P * (R / 4) : P * R, 256), 256, 0, s>>>(emb, bias, idx, out, P, W, R, Q, kc);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
