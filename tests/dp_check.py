@@ -31,7 +31,8 @@ for prec in ("fp32", "tf32"):
     if rank == 0:
         print("%s: replicas identical=%s  max|dp - single|=%.3e" % (prec, ok, diff), flush=True)
     # TF32: atomics + different batch split change rounding; Adam(lr=1e-3) turns tiny gradient differences into +-lr moves
-    assert ok and diff < (2e-6 if prec == "fp32" else 5e-3), (ok, diff)
+    # fp32: all-reduce summation order differs from the single-process atomics order (6e-5 seen at 8 ranks)
+    assert ok and diff < (2e-4 if prec == "fp32" else 5e-3), (ok, diff)
 dist.destroy_process_group()
 if rank == 0:
     print("DP CHECK OK")

@@ -12,6 +12,7 @@
 //                    skip sum  sum_l Ws_l z_l  (ONE GEMM with K = 64*L instead of L read-modify-write
 //                    passes over the 256-channel skip tensor, wavenet.py:579) and for the head convs.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "wn_common.h"
@@ -1164,6 +1165,7 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
   //  dWs_l  = dskip^T . z_l  : wgrad with the B operand gathered from nl z slabs per launch
   int nl_max = 256 / G;
   if (nl_max > 4) nl_max = 4;
+  if (const char* ev = getenv("WN_DZS_NL")) nl_max = atoi(ev) > 0 && atoi(ev) < nl_max ? atoi(ev) : nl_max;
   for (int l0 = 0; l0 < L;) {
     int nl = L - l0 < nl_max ? L - l0 : nl_max;
     while (nl > 1 && !nb_ok(nl * G)) --nl;
