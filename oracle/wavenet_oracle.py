@@ -665,8 +665,9 @@ class RingGenerator(object):
         k, kc = p.residual_conv_filter_width, p.causal_conv_filter_width
         nc = len(p.causal_conv_channels)
         # history needed by the next step: the last (k-1)*d columns of every conv input
-        self.idx_hist = window_idx[:, -(kc - 1):].copy() if kc > 1 else window_idx[:, :0].copy()
-        self.causal_hist = [fw["c_cache"][i][:, :, -(kc - 1):].copy() for i in range(1, nc)]
+        self.idx_hist = window_idx[:, window_idx.shape[1] - (kc - 1):].copy()
+        Wn = window_idx.shape[1]
+        self.causal_hist = [fw["c_cache"][i][:, :, Wn - (kc - 1):].copy() for i in range(1, nc)]   # empty when kc == 1
         self.rings = []
         for li, (j, i, d, base) in enumerate(_layers(p)):
             x = fw["r_cache"][li][0]

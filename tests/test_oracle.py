@@ -268,3 +268,21 @@ def test_mulaw_quirks():
     np.testing.assert_allclose(st, raw[:, 0] / 32768.0)
     mono = D.normalize(raw[:, 0])
     assert list(mono) == [0, -1, 0]
+
+
+@pytest.mark.parametrize("kc,nc", [(1, 2), (3, 2), (2, 3)])
+def test_ring_generator_multi_causal_layers_match_full_window(kc, nc):
+    # found by the randomised GPU sweep: with causal_conv_filter_width == 1 the history slice must be empty
+    p = tiny_params(causal_conv_filter_width=kc, causal_conv_channels=[4, 5, 3][:nc])
+    rng = np.random.default_rng(21)
+    w = O.init_weights(p, rng, np.float64)
+    Win = O.input_width(p)
+    windows = rng.integers(0, 6, (2, Win))
+    got = O.RingGenerator(p, w, 2, head_act="relu", dtype=np.float64).generate_greedy(windows, 8)
+    seqs = [list(r) for r in windows]
+    for s in range(8):
+        win = np.array([q[-Win:] for q in seqs])
+        nxt = np.argmax(O.forward_loss(p, w, win, None, dtype=np.float64)["logits"][:, :, -1], axis=1)
+        assert np.all(nxt == got[:, s]), s
+        for i in range(2):
+            seqs[i].append(int(nxt[i]))
