@@ -84,6 +84,8 @@ const char* wn_last_error(void);
 int wn_version(void);
 /* number of kernels this library has launched in this process (reset!=0: read and zero) */
 int64_t wn_launch_count(int reset);
+/* a CUDA-graph replay re-launches kernels this library recorded at capture time: the caller adds them here */
+int64_t wn_launch_count_add(int64_t n);
 
 /* WaveNet.__init__ / create_network (wavenet.py:371-455): validates the
  * hyper-parameters (Params.check, wavenet.py:167-173) and builds the layout. */

@@ -53,6 +53,7 @@ SIGNATURES = {
     "wn_last_error": (C.c_char_p, []),
     "wn_version": (_I, []),
     "wn_launch_count": (_L, [_I]),
+    "wn_launch_count_add": (_L, [_L]),
     "wn_create": (_I, [C.POINTER(wn_config), C.POINTER(_P)]),
     "wn_destroy": (_I, [_P]),
     "wn_set_precision": (_I, [_P, _I]),

@@ -22,6 +22,7 @@ extern "C" int64_t wn_launch_count(int reset) {
   return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
+extern "C" int64_t wn_launch_count_add(int64_t n) { return g_launches.fetch_add(n) + n; }
 extern "C" const char* wn_last_error(void) { return g_err; }
 extern "C" int wn_version(void) { return 100; }
 

@@ -490,16 +490,61 @@ class WaveNet(object):
                                        _ptr(x), _ptr(t), _stream()))
         return x, t
 
+    def _fwd_bwd(self, x_idx, target, T):
+        check(self._libh.wn_forward_loss(self._h, _ptr(self._params), _ptr(x_idx), _ptr(target), T, _ptr(self._loss),
+                                         None, _stream()))
+        self.backward()
+
     def train_step(self, x_idx, target, train_width=None):
-        """One fused train.py:58-80 step on int32 device tensors; returns the loss tensor (no sync)."""
+        """One fused train.py:58-80 step on int32 device tensors; returns the loss tensor (no sync).
+
+        The ~200 launches of forward + loss + backward are captured once per (B, W, T) shape into a CUDA graph
+        and replayed (launch-bound shapes such as the reference's 16 x 757 batches gain most); the optimiser
+        hooks + Adam stay outside because their step size changes every call.  Set `use_cuda_graph = False`
+        to launch eagerly."""
         self._need_gpu()
         B, W = x_idx.shape
         self._bind(B, W)
         T = W if train_width is None else train_width
-        self._keep["idx"], self._keep["tgt"] = x_idx, target
-        check(self._libh.wn_forward_loss(self._h, _ptr(self._params), _ptr(x_idx), _ptr(target), T, _ptr(self._loss),
-                                         None, _stream()))
-        self.backward()
+        key = (B, W, T, int(self._libh.wn_get_precision(self._h)))
+        if not getattr(self, "use_cuda_graph", True):
+            self._keep["idx"], self._keep["tgt"] = x_idx, target
+            self._fwd_bwd(x_idx, target, T)
+        else:
+            g = self._graphs.get(key) if hasattr(self, "_graphs") else None
+            if not hasattr(self, "_graphs"):
+                self._graphs = {}
+            if g is None:
+                # static input buffers + one eager warm-up (one-time uploads / attribute calls), then capture
+                sx, st = torch.empty_like(x_idx), torch.empty_like(target)
+                sx.copy_(x_idx)
+                st.copy_(target)
+                self._fwd_bwd(sx, st, T)
+                graph = None
+                try:
+                    torch.cuda.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    n0 = int(self._libh.wn_launch_count(0))
+                    with torch.cuda.graph(graph):
+                        self._fwd_bwd(sx, st, T)
+                    self._graph_launches = int(self._libh.wn_launch_count(0)) - n0   # kernels recorded in the graph
+                    self._libh.wn_launch_count_add(-self._graph_launches)            # capture itself launched nothing
+                except Exception:
+                    graph = None                      # capture unsupported here: stay eager
+                    torch.cuda.synchronize()
+                self._graphs = {key: (graph, sx, st)}     # one shape at a time (the tape is re-bound on shape change)
+                if graph is None:
+                    self.update()
+                    return self._loss
+                g = self._graphs[key]
+            graph, sx, st = g
+            if graph is None:
+                self._fwd_bwd(x_idx, target, T)
+            else:
+                sx.copy_(x_idx, non_blocking=True)
+                st.copy_(target, non_blocking=True)
+                graph.replay()
+                self._libh.wn_launch_count_add(self._graph_launches)
         self.update()
         return self._loss
 
