@@ -551,6 +551,152 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------
+// A-resident slab GEMM for wide outputs: Y[(b,t)][0..Ntot) = A[b][t + row_off][0..K) . Wt[Ntot][K]^T with K <= 256.
+// The 128 x K A tile is loaded ONCE per 128-row tile and stays in shared memory while the kernel walks the
+// 256-column output groups (B streamed through a 2-stage ring from L2).  Used for dzs = dskip . [Ws_0 .. Ws_L-1]:
+// dskip is read from HBM once instead of once per group of four layers.
+struct GemmAresArgs {
+  float* Y;
+  int ldy;                 // row stride inside a slab
+  int y_slab_cols;         // columns per output slab (G)
+  int64_t y_slab_stride;
+  int Ntot, ngroups;       // output columns, ceil(Ntot / 256)
+  int ksub;                // K / 32  (<= 8)
+  int rows_out, a_row_off;
+  int tiles_per_seq, num_tiles;
+};
+
+constexpr int AR_A = 0;                        // up to 8 sub-tiles [128 x 32]  (128 KB)
+constexpr int AR_B = 131072;                   // 2 stages x [256 x 32]          (64 KB)
+constexpr int AR_BAR = AR_B + 2 * 32768;
+constexpr int AR_STG = AR_BAR + 256;           // 8 x 4 KB transpose buffers
+constexpr int AR_SMEM = AR_STG + 8 * 4096 + 1024;
+
+__global__ void __launch_bounds__(L_THREADS, 1)
+tc_gemm_ares_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                    const GemmAresArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + AR_BAR;
+  const uint32_t a_full = bar0, a_empty = bar0 + 8;
+  auto b_full = [&](int s) { return bar0 + 16 + 8 * s; };
+  auto b_empty = [&](int s) { return bar0 + 32 + 8 * s; };
+  auto acc_full = [&](int s) { return bar0 + 48 + 8 * s; };
+  auto acc_empty = [&](int s) { return bar0 + 64 + 8 * s; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + AR_BAR + 128);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), 256);
+    }
+    fence_barrier_init();
+    prefetch_tmap(&tm_a);
+    prefetch_tmap(&tm_b);
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32((const void*)tmem_slot));
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int n_local = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int j = 0; j < n_local; ++j) {
+        const int tile = blockIdx.x + j * gridDim.x;
+        const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM;
+        mbar_wait(a_empty, (j & 1) ^ 1);
+        mbar_arrive_expect_tx(a_full, a.ksub * SUB_A);
+        for (int ks = 0; ks < a.ksub; ++ks) tma_load_4d(base + AR_A + ks * SUB_A, &tm_a, a_full, ks * SUBK, a.a_row_off + t0, b, 0);
+        for (int ng = 0; ng < a.ngroups; ++ng)
+          for (int ks = 0; ks < a.ksub; ++ks, ++it) {
+            const int s = it & 1, ph = (it >> 1) & 1;
+            mbar_wait(b_empty(s), ph ^ 1);
+            mbar_arrive_expect_tx(b_full(s), 32768);
+            tma_load_2d(base + AR_B + s * 32768, &tm_b, b_full(s), ks * SUBK, ng * 256);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(128, 256);
+      int it = 0, ia = 0;
+      for (int j = 0; j < n_local; ++j) {
+        mbar_wait(a_full, j & 1);
+        tcgen05_fence_after();
+        for (int ng = 0; ng < a.ngroups; ++ng, ++ia) {
+          const int ab = ia & 1, aph = (ia >> 1) & 1;
+          mbar_wait(acc_empty(ab), aph ^ 1);
+          tcgen05_fence_after();
+          for (int ks = 0; ks < a.ksub; ++ks, ++it) {
+            const int s = it & 1, ph = (it >> 1) & 1;
+            mbar_wait(b_full(s), ph);
+            tcgen05_fence_after();
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              umma_tf32(tmem + ab * 256, umma_desc_k_sw128(base + AR_A + ks * SUB_A + k4 * 32),
+                        umma_desc_k_sw128(base + AR_B + s * 32768 + k4 * 32), idesc, (ks | k4) > 0);
+            umma_commit(b_empty(s));
+          }
+          umma_commit(acc_full(ab));
+        }
+        umma_commit(a_empty);   // every MMA that reads this A tile has completed when this fires
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    uint8_t* stg = gbase + AR_STG + (warp - 2) * 4096;
+    const int cc4 = (lane & 7) * 4, rsub = lane >> 3;
+    int ia = 0;
+    for (int j = 0; j < n_local; ++j) {
+      const int tile = blockIdx.x + j * gridDim.x;
+      const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM + q * 32;
+      for (int ng = 0; ng < a.ngroups; ++ng, ++ia) {
+        const int ab = ia & 1, aph = (ia >> 1) & 1;
+        mbar_wait(acc_full(ab), aph);
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          const int c0 = (half * 4 + ch) * 32;
+          uint32_t v[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * 256 + c0, v);
+          tmem_ld_wait();
+          const int gc = ng * 256 + c0;          // first global output column of this block
+          if (gc >= a.Ntot) continue;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          __syncwarp();
+          float* ybase = a.Y + (int64_t)((gc + cc4) / a.y_slab_cols) * a.y_slab_stride + ((gc + cc4) % a.y_slab_cols);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int rr = jj * 4 + rsub;
+            const int t = t0 + rr;
+            if (t >= a.rows_out) continue;
+            const uint4 o = *reinterpret_cast<const uint4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+            *reinterpret_cast<uint4*>(ybase + ((int64_t)b * a.rows_out + t) * a.ldy) = o;
+          }
+          __syncwarp();
+        }
+        tcgen05_fence_before();
+        mbar_arrive(acc_empty(ab));
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
 // Weight gradient: D[128 x NB] = sum over positions  dY[p][a_c0 + m] * X_slab[p + off_slab][c]
 // The reduction dimension (positions) is the row index of both operands in memory, so both are
 // MN-major UMMA operands: TMA deposits [32 positions x 32 channels] sub-tiles (128-byte rows,
@@ -891,6 +1037,39 @@ int tc_wgrad(const wn_handle* h, const TcOperand& dY, int a_row_off, int a_c0, i
   return launch_wgrad<256, 2>(ta, tb, g, h->sm_count, s);
 }
 
+// Y slabs <- A . Wt^T with the A tile resident (see tc_gemm_ares_kernel); requires K <= 256, K % 32 == 0
+int tc_gemm_ares(const wn_handle* h, const TcOperand& A, int row_off, int rows_out, const float* Wt, int Ntot, float* Y,
+                 int ldy, int y_slab_cols, int64_t y_slab_stride, cudaStream_t s) {
+  WN_REQUIRE(A.K % SUBK == 0 && A.K <= 256 && y_slab_cols % 32 == 0 && A.nslab == 1, WN_EINVAL,
+             "tc_gemm_ares: unsupported shape K=%d", A.K);
+  CUtensorMap ta, tb;
+  WN_TRY(make_map_4d(&ta, A.ptr, A.K, A.rows_in, A.num_seq, 1, A.K, (uint64_t)A.rows_in * A.K,
+                     (uint64_t)A.rows_in * A.num_seq * A.K, TM));
+  WN_TRY(make_map_2d(&tb, Wt, A.K, Ntot, A.K, 256));
+  GemmAresArgs g;
+  memset(&g, 0, sizeof(g));
+  g.Y = Y;
+  g.ldy = ldy;
+  g.y_slab_cols = y_slab_cols;
+  g.y_slab_stride = y_slab_stride;
+  g.Ntot = Ntot;
+  g.ngroups = (Ntot + 255) / 256;
+  g.ksub = A.K / SUBK;
+  g.rows_out = rows_out;
+  g.a_row_off = row_off;
+  g.tiles_per_seq = (rows_out + TM - 1) / TM;
+  g.num_tiles = g.tiles_per_seq * A.num_seq;
+  static bool attr = false;
+  if (!attr) {
+    WN_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_ares_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_SMEM));
+    attr = true;
+  }
+  const int grid = g.num_tiles < h->sm_count ? g.num_tiles : h->sm_count;
+  tc_gemm_ares_kernel<<<grid, L_THREADS, AR_SMEM, s>>>(ta, tb, g);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
 // fused layer kernel: the benchmark shape (R = G = 64, k = 2, no biases)
 bool tc_fused_supported(const wn_handle* h) {
   if (h->R != 64 || h->cfg.residual_filter_width != 2) return false;
@@ -1163,13 +1342,16 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
   // ---- skip path for ALL layers at once (mirror of the forward skip GEMM) ----
   //  dzs[l] = dskip . Ws_l   : GEMMs with N = nl layers x G, each column block written to its layer slab
   //  dWs_l  = dskip^T . z_l  : wgrad with the B operand gathered from nl z slabs per launch
+  const bool ares = S <= 256 && getenv("WN_NO_ARES") == nullptr;
+  if (ares)   // all L slabs of dzs in one pass over dskip
+    WN_TRY(tc_gemm_ares(h, DS, nwt, W, ws + t.tc_wst, L * G, ws + t.dzs, G, G, (int64_t)P * G, s));
   int nl_max = 256 / G;
   if (nl_max > 4) nl_max = 4;
   if (const char* ev = getenv("WN_DZS_NL")) nl_max = atoi(ev) > 0 && atoi(ev) < nl_max ? atoi(ev) : nl_max;
   for (int l0 = 0; l0 < L;) {
     int nl = L - l0 < nl_max ? L - l0 : nl_max;
     while (nl > 1 && !nb_ok(nl * G)) --nl;
-    {
+    if (!ares) {
       TcEpilogue e;
       e.y_slab_cols = G;
       e.y_slab_stride = (int64_t)P * G;
