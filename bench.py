@@ -99,7 +99,7 @@ def synth_batch(rank, B, W):
 
 
 # --------------------------------------------------------------------------------------
-def cpu_train_sample(threads, B=1, W=2048, reps=1):
+def cpu_train_sample(threads, B=1, W=16000, reps=2):
     """One train step of config C on the CPU oracle (the reference's arithmetic restated in
     NumPy: one-hot input, pad copies, im2col+tensordot convs forward; einsum backward; clip+Adam)."""
     from oracle import wavenet_oracle as O
@@ -126,7 +126,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    B, W = 1, 2048
+    B, W = 1, 8192
     times = []
     from oracle import wavenet_oracle as O
     cfg = O.config_C()
@@ -410,7 +410,7 @@ def main():
         threads = os.cpu_count() or 1
         v, secs = cpu_train_sample(threads)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "one config-C train step on 1 x 2048 samples (%.1f s), NumPy oracle in "
+                                "sample": "best of 2 config-C train steps on 1 x 16000 samples (%.1f s each), NumPy oracle in "
                                           "reference-literal mode, BLAS threads = all host cores" % secs}
     if rank == 0:
         print(json.dumps(line))

@@ -135,8 +135,6 @@ struct LayerArgs {
   float* x_out;            // [B][W][64]
   float* z_out;            // [B][W][64]
   float* sg_out;           // [B][W][64] sigmoid (backward rebuilds tanh = z / sigmoid), or null
-  const float* bias_fg;    // [128] or null
-  const float* bias_p;     // [64] or null
   int W, d, zp, tiles_per_seq, num_tiles;
 };
 
@@ -261,10 +259,6 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         float af = __uint_as_float(f[i]), ag = __uint_as_float(g[i]);
-        if (a.bias_fg) {
-          af += a.bias_fg[half * 32 + i];
-          ag += a.bias_fg[64 + half * 32 + i];
-        }
         const float tf = tanh_fast(af), sg = 0.5f * tanh_fast(0.5f * ag) + 0.5f;
         g[i] = __float_as_uint(live ? sg : 0.5f);          // masked rows look like tanh(0) | sigmoid(0)
         f[i] = __float_as_uint(tf32_rna((live ? tf : 0.f) * sg));
@@ -297,12 +291,6 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         o.y = __uint_as_float(g[4 * c + 1]) + xv.y;
         o.z = __uint_as_float(g[4 * c + 2]) + xv.z;
         o.w = __uint_as_float(g[4 * c + 3]) + xv.w;
-        if (a.bias_p) {
-          o.x += a.bias_p[half * 32 + 4 * c];
-          o.y += a.bias_p[half * 32 + 4 * c + 1];
-          o.z += a.bias_p[half * 32 + 4 * c + 2];
-          o.w += a.bias_p[half * 32 + 4 * c + 3];
-        }
         g[4 * c] = __float_as_uint(o.x);
         g[4 * c + 1] = __float_as_uint(o.y);
         g[4 * c + 2] = __float_as_uint(o.z);
@@ -359,7 +347,10 @@ struct GemmCfg {
   static constexpr int SMEM = STG + 8 * 4096 + 1024;
 };
 
-template <int BN>
+// MODE selects the epilogue at compile time (runtime-predicated feature code costs issue slots in the 8 epilogue warps,
+// which are the critical resource of these HBM-bound kernels): 0 = generic (runtime flags), 1 = dz + gate derivative,
+// 2 = Y = acc + Rsd only (the per-layer dx GEMM).
+template <int BN, int MODE>
 __global__ void __launch_bounds__(L_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmTcArgs a) {
   using Cfg = GemmCfg<BN>;
@@ -458,19 +449,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         __syncwarp();
         const int col = c0 + cc4;
-        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.bias) bb = *reinterpret_cast<const float4*>(a.bias + col);
-        float* ybase = a.Y;
-        int ycol = col;
-        if (a.y_slab_cols > 0) {
-          ybase += (int64_t)(c0 / a.y_slab_cols) * a.y_slab_stride;
-          ycol = col % a.y_slab_cols;
-        }
         // phase 1: issue every global load of this 32x32 block (memory-level parallelism), phase 2: math + stores.
         // Mode-specific branches keep only the needed register arrays alive (no spills).
         const int rsub = lane >> 3;
-        const uint8_t* srow = stg + (((lane & 7)) << 4);
-        if (a.gate_sg) {
+        if constexpr (MODE == 2) {
+          float4 r4[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int t = min(t0 + jj * 4 + rsub, a.rows_out - 1);
+            r4[jj] = *reinterpret_cast<const float4*>(a.Rsd + ((int64_t)b * a.rows_out + t) * a.ldr + col);
+          }
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int rr = jj * 4 + rsub;
+            const int t = t0 + rr;
+            if (t >= a.rows_out) continue;
+            float4 o = *reinterpret_cast<const float4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+            o.x += r4[jj].x, o.y += r4[jj].y, o.z += r4[jj].z, o.w += r4[jj].w;
+            *reinterpret_cast<float4*>(a.Y + ((int64_t)b * a.rows_out + t) * a.ldy + col) = o;
+          }
+        } else if constexpr (MODE == 1) {
           float4 r4[8], z4[8], sg4[8];
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
@@ -502,6 +500,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             *reinterpret_cast<float4*>(drow + a.N + col) = dg;
           }
         } else {
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.bias) bb = *reinterpret_cast<const float4*>(a.bias + col);
+          float* ybase = a.Y;
+          int ycol = col;
+          if (a.y_slab_cols > 0) {
+            ybase += (int64_t)(c0 / a.y_slab_cols) * a.y_slab_stride;
+            ycol = col % a.y_slab_cols;
+          }
           float4 r4[8], x4[8];   // x4: ReLU mask source or previous Y (never both)
           const bool has_aux = a.mask != nullptr || a.accumulate;
 #pragma unroll
@@ -538,7 +544,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             *reinterpret_cast<float4*>(ybase + orow * a.ldy + ycol) = o;
           }
         }
-        (void)srow;
         __syncwarp();
       }
       tcgen05_fence_before();
@@ -889,18 +894,27 @@ int make_map_2d(CUtensorMap* m, const float* ptr, uint64_t d0, uint64_t d1, uint
   return WN_OK;
 }
 
-template <int BN>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcArgs& g, int sm_count, cudaStream_t s) {
+template <int BN, int MODE>
+int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcArgs& g, int sm_count, cudaStream_t s) {
   using Cfg = GemmCfg<BN>;
   static bool attr = false;
   if (!attr) {
-    WN_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    WN_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr = true;
   }
   const int grid = g.num_tiles < sm_count ? g.num_tiles : sm_count;
-  tc_gemm_kernel<BN><<<grid, L_THREADS, Cfg::SMEM, s>>>(ta, tb, g);
+  tc_gemm_kernel<BN, MODE><<<grid, L_THREADS, Cfg::SMEM, s>>>(ta, tb, g);
   WN_CHECK_LAUNCH();
   return WN_OK;
+}
+
+template <int BN>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcArgs& g, int sm_count, cudaStream_t s) {
+  if (g.gate_sg) return launch_gemm_mode<BN, 1>(ta, tb, g, sm_count, s);
+  const bool rsd_only = g.Rsd && !g.bias && !g.relu && !g.round_out && !g.accumulate && !g.mask && g.y_slab_cols == 0 &&
+                        g.zero_rows_below <= 0 && g.N == BN;
+  if (rsd_only) return launch_gemm_mode<BN, 2>(ta, tb, g, sm_count, s);
+  return launch_gemm_mode<BN, 0>(ta, tb, g, sm_count, s);
 }
 
 template <int NB, int MH>
@@ -1178,8 +1192,6 @@ int tc_layer_launch(wn_handle* h, int l, cudaStream_t s) {
     a.x_out = h->ws + t.x[l + 1];
     a.z_out = h->ws + t.z[l];
     a.sg_out = h->save_gates ? h->ws + t.tfsg[l] : nullptr;   // TC tapes keep sigmoid only, row stride G
-    a.bias_fg = nullptr;
-    a.bias_p = nullptr;
     a.W = t.W;
     a.d = ly.dilation;
     a.zp = wn_zero_prefix(t.W, ly.dilation, 2);
