@@ -718,6 +718,7 @@ struct WgradTcArgs {
   int m_split, m_valid;
   int64_t sn, sk;          // element (m, slab, c) -> dW[slab] + m*sn + c*sk
   int chunks_per_seq, num_chunks;
+  int red_mode;            // 0 scalar atomics, 1 rows contiguous (sk == 1), 2 two taps interleaved (sk == 2); 1/2 need 16-B alignment
 };
 
 // MN-major tf32 operands only exist in the SWIZZLE_128B_BASE32B layout (layout_type 1): 128-byte rows,
@@ -824,20 +825,81 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     mbar_wait(acc_full, 0);
     tcgen05_fence_after();
     const int nb = a.nb_sub * 32;   // channels per slab
+    // Every MMA has retired, so the pipeline stages are free: each epilogue warp turns its row-per-lane TMEM
+    // blocks into column-per-lane order through 8 KB of that memory and issues 16-byte vector reductions that
+    // cover whole 128/256-byte rows of dW (a strided scalar atomic per element costs 8x the L2 transactions).
+    uint8_t* stg = gbase + (warp - 2) * 8192;
+    auto row_ptr = [&](int m, int sl) {
+      return m < a.m_split ? a.dW0[sl] + (int64_t)m * a.sn : a.dW1[sl] + (int64_t)(m - a.m_split) * a.sn;
+    };
+    if (a.red_mode == 2) {
+      // two taps interleaved in memory (sk == 2, dW[1] == dW[0] + 1): this warp owns channels [cw, cw+32) of both taps
 #pragma unroll 1
-    for (int mh = 0; mh < MH; ++mh) {
-      const int m = mh * 128 + q * 32 + lane;
+      for (int mh = 0; mh < MH; ++mh) {
 #pragma unroll 1
-      for (int ch = 0; ch < CH; ++ch) {
-        const int c0 = (half * CH + ch) * 32;
-        uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + mh * NB + c0, v);
-        tmem_ld_wait();
-        if (m < a.m_valid) {
-          const int sl = c0 / nb, cbase = c0 % nb;
-          float* wrow = m < a.m_split ? a.dW0[sl] + (int64_t)m * a.sn : a.dW1[sl] + (int64_t)(m - a.m_split) * a.sn;
+        for (int ch = 0; ch < nb / 64; ++ch) {
+          const int cw = (half * (nb / 64) + ch) * 32;
+          uint32_t v0[32], v1[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + mh * NB + cw, v0);
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + mh * NB + nb + cw, v1);
+          tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) atomicAdd(wrow + (int64_t)(cbase + i) * a.sk, __uint_as_float(v[i]));
+          for (int k = 0; k < 16; ++k)
+            *reinterpret_cast<uint4*>(stg + lane * 256 + ((k ^ (lane & 7)) << 4)) =
+                make_uint4(v0[2 * k], v1[2 * k], v0[2 * k + 1], v1[2 * k + 1]);
+          __syncwarp();
+#pragma unroll 4
+          for (int jj = 0; jj < 16; ++jj) {
+            const int rr = jj * 2 + (lane >> 4), kk = lane & 15;
+            const int m = mh * 128 + q * 32 + rr;
+            const float4 o = *reinterpret_cast<const float4*>(stg + rr * 256 + ((kk ^ (rr & 7)) << 4));
+            if (m < a.m_valid) red_add_v4(row_ptr(m, 0) + (int64_t)cw * 2 + kk * 4, o);
+          }
+          __syncwarp();
+        }
+      }
+    } else if (a.red_mode == 1) {
+      // contiguous channels (sk == 1)
+#pragma unroll 1
+      for (int mh = 0; mh < MH; ++mh) {
+#pragma unroll 1
+        for (int ch = 0; ch < CH; ++ch) {
+          const int c0 = (half * CH + ch) * 32;
+          uint32_t v[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + mh * NB + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          __syncwarp();
+          const int sl = c0 / nb, cbase = c0 % nb;
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int rr = jj * 4 + (lane >> 3), kk = lane & 7;
+            const int m = mh * 128 + q * 32 + rr;
+            const float4 o = *reinterpret_cast<const float4*>(stg + rr * 128 + ((kk ^ (rr & 7)) << 4));
+            if (m < a.m_valid) red_add_v4(row_ptr(m, sl) + cbase + kk * 4, o);
+          }
+          __syncwarp();
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int mh = 0; mh < MH; ++mh) {
+        const int m = mh * 128 + q * 32 + lane;
+#pragma unroll 1
+        for (int ch = 0; ch < CH; ++ch) {
+          const int c0 = (half * CH + ch) * 32;
+          uint32_t v[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + mh * NB + c0, v);
+          tmem_ld_wait();
+          if (m < a.m_valid) {
+            const int sl = c0 / nb, cbase = c0 % nb;
+            float* wrow = row_ptr(m, sl);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(wrow + (int64_t)(cbase + i) * a.sk, __uint_as_float(v[i]));
+          }
         }
       }
     }
@@ -1041,6 +1103,17 @@ int tc_wgrad(const wn_handle* h, const TcOperand& dY, int a_row_off, int a_c0, i
   g.sk = sk;
   g.chunks_per_seq = (rows_it + WG_KC - 1) / WG_KC;
   g.num_chunks = g.chunks_per_seq * dY.num_seq;
+  {
+    bool aligned = sn % 4 == 0;
+    for (int i = 0; i < nb_slab; ++i) {
+      aligned = aligned && ((uintptr_t)g.dW0[i] & 15) == 0;
+      if (g.dW1[i]) aligned = aligned && ((uintptr_t)g.dW1[i] & 15) == 0;
+    }
+    const bool taps2 = nb_slab == 2 && sk == 2 && X.K % 64 == 0 && g.dW0[1] == g.dW0[0] + 1 &&
+                       (!g.dW1[0] || g.dW1[1] == g.dW1[0] + 1) && sn % 4 == 0 && ((uintptr_t)g.dW0[0] & 15) == 0 &&
+                       (!g.dW1[0] || ((uintptr_t)g.dW1[0] & 15) == 0);
+    g.red_mode = (sk == 1 && aligned) ? 1 : (taps2 ? 2 : 0);
+  }
   if (MH == 1) {
     if (NB == 64) return launch_wgrad<64, 1>(ta, tb, g, h->sm_count, s);
     if (NB == 128) return launch_wgrad<128, 1>(ta, tb, g, h->sm_count, s);

@@ -137,6 +137,11 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 // byte offset of 16-byte chunk `c` (0..7) of row `r` inside a [rows x 128 B] SWIZZLE_128B tile
 __device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
+// 16-byte vector reduction (sm_90+): four fp32 adds in one L2 transaction
+__device__ __forceinline__ void red_add_v4(float* p, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t o;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(o) : "f"(x));
