@@ -146,9 +146,17 @@ constexpr int L_STG = L_BAR + 256;            // 8 epilogue warps x 2 KB store-t
 constexpr int L_SMEM = L_STG + 8 * 2048;
 constexpr int L_THREADS = 64 + 256;           // producer warp, MMA warp, 8 epilogue warps
 
+// Developer trace (make EXTRA=-DWN_LAYER_TRACE, tests/trace_layer.py): clock64 stamps of CTA 0's pipeline events.
+#ifdef WN_LAYER_TRACE
+__device__ long long g_trace[64 * 32];
+#define TR(j, e) do { if (blockIdx.x == 0 && (j) < 64) g_trace[(j) * 32 + (e)] = clock64(); } while (0)
+#else
+#define TR(j, e) do { } while (0)
+#endif
 __global__ void __launch_bounds__(L_THREADS, 1)
 tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
-                const __grid_constant__ CUtensorMap tm_w2, const LayerArgs a) {
+                const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_z,
+                const __grid_constant__ CUtensorMap tm_sg, const LayerArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -156,7 +164,6 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   // barrier slots (8 bytes each)
   const uint32_t b_full = bar0;
   auto a_full = [&](int s) { return bar0 + 8 + 8 * s; };
-  auto a_empty = [&](int s) { return bar0 + 24 + 8 * s; };
   auto d1_full = [&](int s) { return bar0 + 40 + 8 * s; };
   auto z_full = [&](int s) { return bar0 + 56 + 8 * s; };
   auto d2_full = [&](int s) { return bar0 + 72 + 8 * s; };
@@ -167,7 +174,6 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     mbar_init(b_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(a_full(s), 1);
-      mbar_init(a_empty(s), 256);
       mbar_init(d1_full(s), 1);
       mbar_init(z_full(s), 256);
       mbar_init(d2_full(s), 1);
@@ -176,6 +182,8 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     prefetch_tmap(&tm_x);
     prefetch_tmap(&tm_w1);
     prefetch_tmap(&tm_w2);
+    prefetch_tmap(&tm_z);
+    prefetch_tmap(&tm_sg);
   }
   if (warp == 1) tmem_alloc<512>(smem_u32((const void*)tmem_slot));
   tcgen05_fence_before();
@@ -186,54 +194,101 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
+      // The producer thread also writes z and sigmoid back: both tiles sit in the stage in the 128B-swizzled layout
+      // TMA understands (z = A operand of GEMM 2 in sub-tiles 0,1; sigmoid replaces x(t) in sub-tiles 2,3 once the
+      // residual is in registers), so each is one pair of bulk tensor stores instead of a register -> smem ->
+      // register -> global transpose in the epilogue warps.
       mbar_arrive_expect_tx(b_full, 81920);
       for (int j = 0; j < 4; ++j) tma_load_2d(base + L_B1 + j * SUB_A, &tm_w1, b_full, j * SUBK, 0);
       for (int j = 0; j < 2; ++j) tma_load_2d(base + L_B2 + j * 8192, &tm_w2, b_full, j * SUBK, 0);
-      for (int j = 0; j < n_local; ++j) {
-        const int tile = blockIdx.x + j * gridDim.x;
-        const int s = j & 1, ph = (j >> 1) & 1;
-        mbar_wait(a_empty(s), ph ^ 1);
-        const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM;
+      for (int j = 0; j <= n_local; ++j) {
+        const int s = j & 1;
         const uint32_t as = base + L_A + s * 65536;
-        mbar_arrive_expect_tx(a_full(s), 65536);
-        tma_load_4d(as + 0 * SUB_A, &tm_x, a_full(s), 0, t0 - a.d, b, 0);
-        tma_load_4d(as + 1 * SUB_A, &tm_x, a_full(s), SUBK, t0 - a.d, b, 0);
-        tma_load_4d(as + 2 * SUB_A, &tm_x, a_full(s), 0, t0, b, 0);
-        tma_load_4d(as + 3 * SUB_A, &tm_x, a_full(s), SUBK, t0, b, 0);
+        if (j >= 2) {
+          // tile j-2 used this stage.  Its last reader is GEMM 2 (z in sub-tiles 0,1); the residual was taken into
+          // registers before z_full.  Also wait until the bulk stores of z / sigmoid have finished READING the stage.
+          mbar_wait(d2_full(s), ((j - 2) >> 1) & 1);
+          TR(j, 0);
+          bulk_wait_group_read0();
+          TR(j, 1);
+        }
+        if (j < n_local) {
+          const int tile = blockIdx.x + j * gridDim.x;
+          const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM;
+          mbar_arrive_expect_tx(a_full(s), 65536);
+          tma_load_4d(as + 0 * SUB_A, &tm_x, a_full(s), 0, t0 - a.d, b, 0);
+          tma_load_4d(as + 1 * SUB_A, &tm_x, a_full(s), SUBK, t0 - a.d, b, 0);
+          tma_load_4d(as + 2 * SUB_A, &tm_x, a_full(s), 0, t0, b, 0);
+          tma_load_4d(as + 3 * SUB_A, &tm_x, a_full(s), SUBK, t0, b, 0);
+          TR(j, 2);
+        }
+        if (j >= 1) {
+          const int jj = j - 1, s1 = jj & 1, tile = blockIdx.x + jj * gridDim.x;
+          const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM;
+          const uint32_t zs = base + L_A + s1 * 65536;
+          mbar_wait(z_full(s1), (jj >> 1) & 1);
+          TR(j, 3);
+          tma_store_4d(&tm_z, zs + 0 * SUB_A, 0, t0, b, 0);
+          tma_store_4d(&tm_z, zs + 1 * SUB_A, SUBK, t0, b, 0);
+          if (a.sg_out) {
+            tma_store_4d(&tm_sg, zs + 2 * SUB_A, 0, t0, b, 0);
+            tma_store_4d(&tm_sg, zs + 3 * SUB_A, SUBK, t0, b, 0);
+          }
+          bulk_commit_group();
+        }
       }
+      bulk_wait_group0();
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc1 = umma_idesc_tf32(128, 128);
       constexpr uint32_t idesc2 = umma_idesc_tf32(128, 64);
       mbar_wait(b_full, 0);
-      auto issue1 = [&](int j) {
-        const int s = j & 1, ph = (j >> 1) & 1;
-        mbar_wait(a_full(s), ph);
-        tcgen05_fence_after();
-        const uint32_t as = base + L_A + s * 65536;
+      // Two independent in-order streams share this thread: GEMM 1 of tile j1 (needs the TMA load) and GEMM 2 of
+      // tile j2 (needs z from the epilogue warps).  Poll both barriers and issue whichever is ready: waiting for
+      // the next tile's load before GEMM 2 of the current tile would stall the epilogue warps on d2_full.
+      const uint64_t db1 = umma_desc_k_sw128(base + L_B1), db2 = umma_desc_k_sw128(base + L_B2);
+      int j1 = 0, j2 = 0;
+      uint32_t spins = 0;
+      while (j2 < n_local) {
+        bool progressed = false;
+        if (j2 < j1 && mbar_try_wait(z_full(j2 & 1), (j2 >> 1) & 1)) {
+          const int s = j2 & 1;
+          TR(j2, 6);
+          tcgen05_fence_after();
+          const uint64_t da = umma_desc_k_sw128(base + L_A + s * 65536);
 #pragma unroll
-        for (int ks = 0; ks < 16; ++ks) {
-          const uint32_t off = (ks >> 2) * SUB_A + (ks & 3) * 32;
-          umma_tf32(tmem + s * 128, umma_desc_k_sw128(as + off), umma_desc_k_sw128(base + L_B1 + off), idesc1, ks > 0);
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t offa = (ks >> 2) * SUB_A + (ks & 3) * 32;
+            const uint32_t offb = (ks >> 2) * 8192 + (ks & 3) * 32;
+            umma_tf32(tmem + 256 + s * 64, da + (offa >> 4), db2 + (offb >> 4), idesc2, ks > 0);
+          }
+          umma_commit(d2_full(s));
+          ++j2;
+          progressed = true;
         }
-        umma_commit(d1_full(s));
-      };
-      if (n_local > 0) issue1(0);
-      for (int j = 0; j < n_local; ++j) {
-        if (j + 1 < n_local) issue1(j + 1);
-        const int s = j & 1, ph = (j >> 1) & 1;
-        mbar_wait(z_full(s), ph);
-        tcgen05_fence_after();
-        const uint32_t as = base + L_A + s * 65536;
+        // GEMM 1 of tile j1 overwrites the accumulator epilogue 1 of tile j1-2 read: allowed once z_full(j1-2) was seen
+        if (j1 < n_local && j1 <= j2 + 1 && mbar_try_wait(a_full(j1 & 1), (j1 >> 1) & 1)) {
+          const int s = j1 & 1;
+          TR(j1, 4);
+          tcgen05_fence_after();
+          const uint64_t da = umma_desc_k_sw128(base + L_A + s * 65536);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t offa = (ks >> 2) * SUB_A + (ks & 3) * 32;
-          const uint32_t offb = (ks >> 2) * 8192 + (ks & 3) * 32;
-          umma_tf32(tmem + 256 + s * 64, umma_desc_k_sw128(as + offa), umma_desc_k_sw128(base + L_B2 + offb), idesc2,
-                    ks > 0);
+          for (int ks = 0; ks < 16; ++ks) {
+            const uint32_t off = (ks >> 2) * SUB_A + (ks & 3) * 32;
+            umma_tf32(tmem + s * 128, da + (off >> 4), db1 + (off >> 4), idesc1, ks > 0);
+          }
+          umma_commit(d1_full(s));
+          TR(j1, 5);
+          ++j1;
+          progressed = true;
         }
-        umma_commit(d2_full(s));
+        if (progressed) {
+          spins = 0;
+        } else if (++spins > (1u << 26)) {
+          printf("wavenet_b200: layer kernel MMA warp timeout (block %d, j1 %d, j2 %d)\n", (int)blockIdx.x, j1, j2);
+          __trap();
+        }
       }
     }
   } else {
@@ -250,10 +305,15 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
       // ---- epilogue 1: gate ----
       mbar_wait(d1_full(s), ph);
+      if (threadIdx.x == 64) TR(j, 8);
       tcgen05_fence_after();
       uint32_t f[32], g[32];
       tmem_ld32(trow + s * 128 + half * 32, f);
       tmem_ld32(trow + s * 128 + 64 + half * 32, g);
+      // residual x(t) of this thread's row: into registers now, so that the stage is free as soon as GEMM 2 is done
+      float4 xr[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) xr[c] = *reinterpret_cast<const float4*>(as_g + (2 + half) * SUB_A + sw128_off(row, c));
       tmem_ld_wait();
       const bool live = valid && t >= a.zp;
 #pragma unroll
@@ -264,45 +324,38 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         f[i] = __float_as_uint(tf32_rna((live ? tf : 0.f) * sg));
       }
 #pragma unroll
-      for (int c = 0; c < 8; ++c)   // A operand of GEMM 2 first: the MMA warp is waiting for it
+      for (int c = 0; c < 8; ++c)   // z: A operand of GEMM 2 and source of the z bulk store
         *reinterpret_cast<uint4*>(as_g + half * SUB_A + sw128_off(row, c)) =
             make_uint4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
+      if (a.sg_out) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)   // sigmoid over x(t) (already in xr): source of the sigmoid bulk store
+          *reinterpret_cast<uint4*>(as_g + (2 + half) * SUB_A + sw128_off(row, c)) =
+              make_uint4(g[4 * c], g[4 * c + 1], g[4 * c + 2], g[4 * c + 3]);
+      }
       fence_proxy_async();
       tcgen05_fence_before();
       mbar_arrive(z_full(s));
-      {
-        // global stores of this warp's 32x32 blocks (z, tanh, sigmoid), coalesced through the staging buffer
-        const int t_w0 = (tile % a.tiles_per_seq) * TM + q * 32;           // first row of the warp's block
-        const int rows_valid = a.W - t_w0;                                 // may be <= 0 or > 32
-        const int64_t gblk = ((int64_t)b * a.W + t_w0) * 64 + half * 32;
-        store_block_coalesced(stg, f, a.z_out + gblk, 64, rows_valid, lane);
-        if (a.sg_out) store_block_coalesced(stg, g, a.sg_out + gblk, 64, rows_valid, lane);
-      }
+      if (threadIdx.x == 64) TR(j, 9);
       // ---- epilogue 2: projection + residual ----
       mbar_wait(d2_full(s), ph);
+      if (threadIdx.x == 64) TR(j, 10);
       tcgen05_fence_after();
       tmem_ld32(trow + 256 + s * 64 + half * 32, g);
       tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        const float4 xv = *reinterpret_cast<const float4*>(as_g + (2 + half) * SUB_A + sw128_off(row, c));
-        float4 o;
-        o.x = __uint_as_float(g[4 * c]) + xv.x;
-        o.y = __uint_as_float(g[4 * c + 1]) + xv.y;
-        o.z = __uint_as_float(g[4 * c + 2]) + xv.z;
-        o.w = __uint_as_float(g[4 * c + 3]) + xv.w;
-        g[4 * c] = __float_as_uint(o.x);
-        g[4 * c + 1] = __float_as_uint(o.y);
-        g[4 * c + 2] = __float_as_uint(o.z);
-        g[4 * c + 3] = __float_as_uint(o.w);
+        g[4 * c] = __float_as_uint(__uint_as_float(g[4 * c]) + xr[c].x);
+        g[4 * c + 1] = __float_as_uint(__uint_as_float(g[4 * c + 1]) + xr[c].y);
+        g[4 * c + 2] = __float_as_uint(__uint_as_float(g[4 * c + 2]) + xr[c].z);
+        g[4 * c + 3] = __float_as_uint(__uint_as_float(g[4 * c + 3]) + xr[c].w);
       }
-      // the stage (x(t) rows just read) can go back to the producer before the global stores are issued
       tcgen05_fence_before();
-      mbar_arrive(a_empty(s));
       {
-        const int t_w0 = (tile % a.tiles_per_seq) * TM + q * 32;
+        const int t_w0 = (tile % a.tiles_per_seq) * TM + q * 32;           // first row of the warp's block
         store_block_coalesced(stg, g, a.x_out + ((int64_t)b * a.W + t_w0) * 64 + half * 32, 64, a.W - t_w0, lane);
       }
+      if (threadIdx.x == 64) TR(j, 11);
     }
   }
   tcgen05_fence_before();
@@ -1257,8 +1310,10 @@ int tc_layer_launch(wn_handle* h, int l, cudaStream_t s) {
   const int grid = num_tiles < h->sm_count ? num_tiles : h->sm_count;
   {
     const ResLayer& ly = h->layers[l];
-    CUtensorMap tx, tw1, tw2;
+    CUtensorMap tx, tw1, tw2, tz, tsg;
     WN_TRY(make_map_4d(&tx, h->ws + t.x[l], R, t.W, t.B, 1, R, (uint64_t)t.W * R, (uint64_t)t.P * R, TM));
+    WN_TRY(make_map_4d(&tz, h->ws + t.z[l], G, t.W, t.B, 1, G, (uint64_t)t.W * G, (uint64_t)t.P * G, TM));
+    WN_TRY(make_map_4d(&tsg, h->ws + t.tfsg[l], G, t.W, t.B, 1, G, (uint64_t)t.W * G, (uint64_t)t.P * G, TM));
     WN_TRY(make_map_2d(&tw1, h->ws + t.tc_w1 + (int64_t)l * 2 * G * 2 * R, 2 * R, 2 * G, 2 * R, 128));
     WN_TRY(make_map_2d(&tw2, h->ws + t.tc_w2 + (int64_t)l * R * G, G, R, G, 64));
     LayerArgs a;
@@ -1270,7 +1325,7 @@ int tc_layer_launch(wn_handle* h, int l, cudaStream_t s) {
     a.zp = wn_zero_prefix(t.W, ly.dilation, 2);
     a.tiles_per_seq = tiles_per_seq;
     a.num_tiles = num_tiles;
-    tc_layer_kernel<<<grid, L_THREADS, L_SMEM + 1024, s>>>(tx, tw1, tw2, a);
+    tc_layer_kernel<<<grid, L_THREADS, L_SMEM + 1024, s>>>(tx, tw1, tw2, tz, tsg, a);
     WN_CHECK_LAUNCH();
   }
   return WN_OK;
@@ -1545,6 +1600,11 @@ extern "C" int wn_tc_layer_forward(wn_handle* h, int layer, void* stream) {
   WN_REQUIRE(layer >= 0 && layer < (int)h->layers.size(), WN_EINVAL, "bad layer index");
   return tc_layer_launch(h, layer, (cudaStream_t)stream);
 }
+#ifdef WN_LAYER_TRACE
+extern "C" int wn_debug_layer_trace(long long* out) {
+  return cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 64 * 32) == cudaSuccess ? 0 : -1;
+}
+#endif
 extern "C" int wn_tc_skip_gemm(wn_handle* h, void* stream) {
   WN_REQUIRE(h && h->ws && h->tape_tc, WN_ESTATE, "wn_tc_skip_gemm: run a TF32 forward first");
   return tc_skip_gemm(h, (cudaStream_t)stream);
