@@ -381,6 +381,8 @@ struct GemmTcArgs {
   int slab_row_off[MAX_SLABS];
   int slab_idx[MAX_SLABS];
   int tiles_per_seq, num_tiles;
+  int ngroups;             // BN-column groups of the output (N > BN): tile = row_tile * ngroups + group, so CTAs that run
+                           // at the same time share the A rows through L2 (A is read from HBM once, not once per group)
   int y_slab_cols;         // >0: column block c goes to Y + (c / y_slab_cols) * y_slab_stride, column c % y_slab_cols
   int64_t y_slab_stride;
   // gate-backward epilogue (N == G): result is dz; writes da_f | da_g into dafg[row][0..2G) instead of Y
@@ -443,7 +445,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       int it = 0;
       for (int j = 0; j < n_local; ++j) {
         const int tile = blockIdx.x + j * gridDim.x;
-        const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM;
+        const int grp = tile % a.ngroups, rt = tile / a.ngroups;
+        const int b = rt / a.tiles_per_seq, t0 = (rt % a.tiles_per_seq) * TM;
         for (int sl = 0; sl < a.nslab; ++sl)
           for (int ks = 0; ks < a.ksub; ++ks, ++it) {
             const int s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
@@ -451,7 +454,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             const uint32_t st = base + s * Cfg::STAGE;
             mbar_arrive_expect_tx(full(s), Cfg::STAGE);
             tma_load_4d(st, &tm_a, full(s), ks * SUBK, a.slab_row_off[sl] + t0, b, a.slab_idx[sl]);
-            tma_load_2d(st + SUB_A, &tm_b, full(s), (sl * a.ksub + ks) * SUBK, 0);
+            tma_load_2d(st + SUB_A, &tm_b, full(s), (sl * a.ksub + ks) * SUBK, grp * BN);
           }
       }
     }
@@ -485,14 +488,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     for (int j = 0; j < n_local; ++j) {
       const int tile = blockIdx.x + j * gridDim.x;
       const int ab = j & 1, aph = (j >> 1) & 1;
-      const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM + q * 32;
+      const int grp = MODE == 0 ? tile % a.ngroups : 0, rt = MODE == 0 ? tile / a.ngroups : tile;
+      const int b = rt / a.tiles_per_seq, t0 = (rt % a.tiles_per_seq) * TM + q * 32;
       mbar_wait(acc_full(ab), aph);
       tcgen05_fence_after();
 #pragma unroll 1
       for (int ch = 0; ch < CH; ++ch) {
-        const int c0 = (half * CH + ch) * 32;
+        const int ct = (half * CH + ch) * 32;          // column inside the TMEM tile
+        const int c0 = grp * BN + ct;                  // output column
         uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * BN + c0, v);
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * BN + ct, v);
         tmem_ld_wait();
         if (c0 >= a.N) continue;
         // row-per-lane -> smem -> 4 full 128-byte rows per instruction (coalesced global traffic)
@@ -765,9 +770,12 @@ struct WgradTcArgs {
   int a_row_off, a_c0;
   int nb_slab, nb_sub;     // B slabs (taps or layers) and 32-channel sub-tiles per slab
   int b_row_off[4];
-  int b_slab_idx[4];       // 4-D map coordinate of each slab
-  float* dW0[4];           // per slab: rows [0, m_split)
-  float* dW1[4];           // per slab: rows [m_split, m_valid)
+  // Slab groups: CTA c works on group c % ngroups over the chunk range c / ngroups, so the CTAs that run at the same
+  // time read the same dY rows for different B slabs (dY comes from HBM once, the other groups hit L2).
+  int ngroups;
+  int b_slab_idx[8][4];    // per group: 4-D map coordinate of each slab (< 0: padding slab, loaded but not reduced)
+  float* dW0[8][4];        // per group and slab: rows [0, m_split)
+  float* dW1[4];           // group 0 only, per slab: rows [m_split, m_valid)
   int m_split, m_valid;
   int64_t sn, sk;          // element (m, slab, c) -> dW[slab] + m*sn + c*sk
   int chunks_per_seq, num_chunks;
@@ -828,9 +836,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
-  // contiguous chunk range per CTA
-  const int per = (a.num_chunks + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int c_begin = (int)blockIdx.x * per;
+  // contiguous chunk range per CTA (per group of CTAs when the B slabs are grouped)
+  const int grp = (int)blockIdx.x % a.ngroups, nrange = (int)gridDim.x / a.ngroups;
+  const int per = (a.num_chunks + nrange - 1) / nrange;
+  const int c_begin = ((int)blockIdx.x / a.ngroups) * per;
   const int c_end = min(a.num_chunks, c_begin + per);
   const int n_local = c_end - c_begin;
 
@@ -848,7 +857,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         for (int sl = 0; sl < a.nb_slab; ++sl)
           for (int i = 0; i < a.nb_sub; ++i)
             tma_load_4d(st + (4 * MH + sl * a.nb_sub + i) * SUB, &tm_b, full(s), i * SUBK, a.b_row_off[sl] + t0, b,
-                        a.b_slab_idx[sl]);
+                        max(a.b_slab_idx[grp][sl], 0));
       }
     }
   } else if (warp == 1) {
@@ -883,7 +892,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     // cover whole 128/256-byte rows of dW (a strided scalar atomic per element costs 8x the L2 transactions).
     uint8_t* stg = gbase + (warp - 2) * 8192;
     auto row_ptr = [&](int m, int sl) {
-      return m < a.m_split ? a.dW0[sl] + (int64_t)m * a.sn : a.dW1[sl] + (int64_t)(m - a.m_split) * a.sn;
+      return m < a.m_split ? a.dW0[grp][sl] + (int64_t)m * a.sn : a.dW1[sl] + (int64_t)(m - a.m_split) * a.sn;
     };
     if (a.red_mode == 2) {
       // two taps interleaved in memory (sk == 2, dW[1] == dW[0] + 1): this warp owns channels [cw, cw+32) of both taps
@@ -927,12 +936,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
           __syncwarp();
           const int sl = c0 / nb, cbase = c0 % nb;
+          const bool slab_ok = a.b_slab_idx[grp][sl] >= 0;
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
             const int rr = jj * 4 + (lane >> 3), kk = lane & 7;
             const int m = mh * 128 + q * 32 + rr;
             const float4 o = *reinterpret_cast<const float4*>(stg + rr * 128 + ((kk ^ (rr & 7)) << 4));
-            if (m < a.m_valid) red_add_v4(row_ptr(m, sl) + cbase + kk * 4, o);
+            if (m < a.m_valid && slab_ok) red_add_v4(row_ptr(m, sl) + cbase + kk * 4, o);
           }
           __syncwarp();
         }
@@ -947,8 +957,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           uint32_t v[32];
           tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + mh * NB + c0, v);
           tmem_ld_wait();
-          if (m < a.m_valid) {
-            const int sl = c0 / nb, cbase = c0 % nb;
+          const int sl = c0 / nb, cbase = c0 % nb;
+          if (m < a.m_valid && a.b_slab_idx[grp][sl] >= 0) {
             float* wrow = row_ptr(m, sl);
 #pragma unroll
             for (int i = 0; i < 32; ++i) atomicAdd(wrow + (int64_t)(cbase + i) * a.sk, __uint_as_float(v[i]));
@@ -1040,7 +1050,8 @@ int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, const WgradTcArgs
     WN_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<NB, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr = true;
   }
-  const int grid = g.num_chunks < sm_count ? g.num_chunks : sm_count;
+  int grid = g.num_chunks * g.ngroups < sm_count ? g.num_chunks * g.ngroups : sm_count;
+  grid -= grid % g.ngroups;
   tc_wgrad_kernel<NB, MH><<<grid, L_THREADS, Cfg::SMEM, s>>>(ta, tb, g);
   WN_CHECK_LAUNCH();
   return WN_OK;
@@ -1077,7 +1088,8 @@ struct TcEpilogue {
 // Y[(b, t)][0..N) = epi( sum_s A[slab_idx[s]][b][t + row_off[s]][:] . Wt[:, s*K ..]^T ),  Wt is [N][ns*K] (TF32-rounded)
 int tc_gemm(const wn_handle* h, const TcOperand& A, int ns, const int* slab_idx, const int* row_off, int rows_out,
             const float* Wt, int N, const TcEpilogue& e, float* Y, int ldy, cudaStream_t s) {
-  WN_REQUIRE(A.K % SUBK == 0 && N % 32 == 0 && N <= 256 && ns <= MAX_SLABS, WN_EINVAL,
+  const bool plain = !e.gate_sg && !e.Rsd && !e.mask && !e.accumulate;   // wide outputs: column groups (MODE 0 only)
+  WN_REQUIRE(A.K % SUBK == 0 && N % 32 == 0 && (N <= 256 || plain) && ns <= MAX_SLABS, WN_EINVAL,
              "tc_gemm: unsupported shape K=%d N=%d slabs=%d", A.K, N, ns);
   CUtensorMap ta, tb;
   const int64_t sstride = A.nslab > 1 ? A.slab_stride : (int64_t)A.rows_in * A.num_seq * A.K;
@@ -1115,7 +1127,8 @@ int tc_gemm(const wn_handle* h, const TcOperand& A, int ns, const int* slab_idx,
     g.slab_idx[i] = slab_idx ? slab_idx[i] : 0;
   }
   g.tiles_per_seq = (rows_out + TM - 1) / TM;
-  g.num_tiles = g.tiles_per_seq * A.num_seq;
+  g.ngroups = (N + BN - 1) / BN;
+  g.num_tiles = g.tiles_per_seq * A.num_seq * g.ngroups;
   if (BN == 64) return launch_gemm<64>(ta, tb, g, h->sm_count, s);
   if (BN == 128) return launch_gemm<128>(ta, tb, g, h->sm_count, s);
   return launch_gemm<256>(ta, tb, g, h->sm_count, s);
@@ -1124,10 +1137,12 @@ int tc_gemm(const wn_handle* h, const TcOperand& A, int ns, const int* slab_idx,
 // dW[slab](m, c) += sum_{b,t} dY[b][a_row_off + t][a_c0 + m] * X[slab_idx[s]][b][b_row_off[s] + t][c]   for m < m_valid (<= 128)
 int tc_wgrad(const wn_handle* h, const TcOperand& dY, int a_row_off, int a_c0, int m_valid, const TcOperand& X, int nb_slab,
              const int* b_row_off, const int* b_slab_idx, float* const* dW0, float* const* dW1, int m_split, int rows_it,
-             int64_t sn, int64_t sk, cudaStream_t s) {
+             int64_t sn, int64_t sk, cudaStream_t s, int ngroups = 1) {
+  // ngroups > 1: b_slab_idx and dW0 hold ngroups x nb_slab entries (group-major); a negative slab index pads a group
   const int NB = nb_slab * X.K;
-  WN_REQUIRE(X.K % 32 == 0 && (NB == 64 || NB == 128 || NB == 256) && nb_slab <= 4 && m_valid <= 256, WN_EINVAL,
-             "tc_wgrad: unsupported shape X.K=%d slabs=%d M=%d", X.K, nb_slab, m_valid);
+  WN_REQUIRE(X.K % 32 == 0 && (NB == 64 || NB == 128 || NB == 256) && nb_slab <= 4 && m_valid <= 256 && ngroups >= 1 &&
+                 ngroups <= 8 && (ngroups == 1 || !dW1),
+             WN_EINVAL, "tc_wgrad: unsupported shape X.K=%d slabs=%d M=%d groups=%d", X.K, nb_slab, m_valid, ngroups);
   const int MH = m_valid > 128 ? 2 : 1;
   const int WG_KC = MH == 2 ? 32 : 64;
   CUtensorMap ta, tb;
@@ -1144,11 +1159,17 @@ int tc_wgrad(const wn_handle* h, const TcOperand& dY, int a_row_off, int a_c0, i
   g.a_c0 = a_c0;
   g.nb_slab = nb_slab;
   g.nb_sub = X.K / 32;
+  g.ngroups = ngroups;
+  bool aligned = sn % 4 == 0;
   for (int i = 0; i < nb_slab; ++i) {
     g.b_row_off[i] = b_row_off[i];
-    g.b_slab_idx[i] = b_slab_idx ? b_slab_idx[i] : 0;
-    g.dW0[i] = dW0[i];
     g.dW1[i] = dW1 ? dW1[i] : nullptr;
+    if (g.dW1[i]) aligned = aligned && ((uintptr_t)g.dW1[i] & 15) == 0;
+    for (int gr = 0; gr < ngroups; ++gr) {
+      g.b_slab_idx[gr][i] = b_slab_idx ? b_slab_idx[gr * nb_slab + i] : 0;
+      g.dW0[gr][i] = dW0[gr * nb_slab + i];
+      if (g.b_slab_idx[gr][i] >= 0) aligned = aligned && ((uintptr_t)g.dW0[gr][i] & 15) == 0;
+    }
   }
   g.m_split = m_split;
   g.m_valid = m_valid;
@@ -1157,13 +1178,8 @@ int tc_wgrad(const wn_handle* h, const TcOperand& dY, int a_row_off, int a_c0, i
   g.chunks_per_seq = (rows_it + WG_KC - 1) / WG_KC;
   g.num_chunks = g.chunks_per_seq * dY.num_seq;
   {
-    bool aligned = sn % 4 == 0;
-    for (int i = 0; i < nb_slab; ++i) {
-      aligned = aligned && ((uintptr_t)g.dW0[i] & 15) == 0;
-      if (g.dW1[i]) aligned = aligned && ((uintptr_t)g.dW1[i] & 15) == 0;
-    }
-    const bool taps2 = nb_slab == 2 && sk == 2 && X.K % 64 == 0 && g.dW0[1] == g.dW0[0] + 1 &&
-                       (!g.dW1[0] || g.dW1[1] == g.dW1[0] + 1) && sn % 4 == 0 && ((uintptr_t)g.dW0[0] & 15) == 0 &&
+    const bool taps2 = ngroups == 1 && nb_slab == 2 && sk == 2 && X.K % 64 == 0 && g.dW0[0][1] == g.dW0[0][0] + 1 &&
+                       (!g.dW1[0] || g.dW1[1] == g.dW1[0] + 1) && sn % 4 == 0 && ((uintptr_t)g.dW0[0][0] & 15) == 0 &&
                        (!g.dW1[0] || ((uintptr_t)g.dW1[0] & 15) == 0);
     g.red_mode = (sk == 1 && aligned) ? 1 : (taps2 ? 2 : 0);
   }
@@ -1482,16 +1498,42 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
   // ---- skip path for ALL layers at once (mirror of the forward skip GEMM) ----
   //  dzs[l] = dskip . Ws_l   : GEMMs with N = nl layers x G, each column block written to its layer slab
   //  dWs_l  = dskip^T . z_l  : wgrad with the B operand gathered from nl z slabs per launch
-  const bool ares = S <= 256 && getenv("WN_NO_ARES") == nullptr;
-  if (ares)   // all L slabs of dzs in one pass over dskip
+  // all L slabs of dzs from one launch: 256-column groups of [Ws_0 .. Ws_L-1] interleaved per row tile, so dskip
+  // comes from HBM once.  (WN_DZS_ARES=1 selects the A-resident kernel, WN_DZS_SPLIT=1 one launch per group.)
+  const bool ares = S <= 256 && getenv("WN_DZS_ARES") != nullptr;
+  const bool grouped = !ares && getenv("WN_DZS_SPLIT") == nullptr && 256 % G == 0;
+  if (ares) {
     WN_TRY(tc_gemm_ares(h, DS, nwt, W, ws + t.tc_wst, L * G, ws + t.dzs, G, G, (int64_t)P * G, s));
+  } else if (grouped) {
+    TcEpilogue e;
+    e.y_slab_cols = G;
+    e.y_slab_stride = (int64_t)P * G;
+    WN_TRY(tc_gemm(h, DS, 1, nullptr, &nwt, W, ws + t.tc_wst, L * G, e, ws + t.dzs, G, s));
+  }
   int nl_max = 256 / G;
   if (nl_max > 4) nl_max = 4;
   if (const char* ev = getenv("WN_DZS_NL")) nl_max = atoi(ev) > 0 && atoi(ev) < nl_max ? atoi(ev) : nl_max;
-  for (int l0 = 0; l0 < L;) {
+  // dWs for all layers from one launch when the layers fit 8 groups of nl_max slabs (dskip read from HBM once)
+  const int ngr = (L + nl_max - 1) / nl_max;
+  const bool dws_grouped = nb_ok(nl_max * G) && nl_max > 1 && ngr > 1 && ngr <= 8 && S <= 256 && (grouped || ares) &&
+                           getenv("WN_DWS_SPLIT") == nullptr;
+  if (dws_grouped) {
+    TcOperand Z{ws + t.z[0], G, W, B, L, zstride};
+    int boff[4], bidx[32];
+    float* dws[32];
+    for (int j = 0; j < nl_max; ++j) boff[j] = wt;
+    for (int gr = 0; gr < ngr; ++gr)
+      for (int j = 0; j < nl_max; ++j) {
+        const int l = gr * nl_max + j;
+        bidx[gr * nl_max + j] = l < L ? l : -1;
+        dws[gr * nl_max + j] = l < L ? grads + h->layers[l].skip.w_off : nullptr;
+      }
+    WN_TRY(tc_wgrad(h, DS, 0, 0, S, Z, nl_max, boff, bidx, dws, nullptr, 256, T, G, 1, s, ngr));
+  }
+  for (int l0 = 0; l0 < L && !(dws_grouped && (grouped || ares));) {
     int nl = L - l0 < nl_max ? L - l0 : nl_max;
     while (nl > 1 && !nb_ok(nl * G)) --nl;
-    if (!ares) {
+    if (!ares && !grouped) {
       TcEpilogue e;
       e.y_slab_cols = G;
       e.y_slab_stride = (int64_t)P * G;
