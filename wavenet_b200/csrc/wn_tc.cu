@@ -973,6 +973,207 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------
+// Backward of one residual layer's gate + projection for the fused shape (R = G = 64), one pass over the tile:
+//   dz   = dout . Wp + dzs_l                       (K-major GEMM, N = 64)
+//   dafg = gate derivative of dz (z, sigmoid)      (epilogue, as tc_gemm_kernel MODE 1)
+//   dWp += dout^T . z                              (MN-major GEMM over the same 128 rows, accumulated in TMEM for the
+//                                                   whole CTA and reduced into the gradient buffer at the end)
+// dout and z are already on their way through L2 for the first two, so folding dWp in removes the separate
+// weight-gradient pass (a second HBM read of dout and z for every layer).
+struct GateBwdArgs {
+  const float* dzs;        // [rows][64]
+  const float* z;          // [rows][64]
+  const float* sg;         // [rows][sg_ld]
+  float* dafg;             // [rows][128]
+  float* dWp;              // [64 o][64 c]
+  int sg_ld, zp;
+  int rows_out, tiles_per_seq, num_tiles;
+};
+constexpr int GB_STAGE = SUB_A + 64 * 128;     // dout [128 x 32] + Wp^T [64 x 32]
+constexpr int GB_STAGES = 4;
+constexpr int GB_MN = GB_STAGES * GB_STAGE;    // dout^T atoms 0,1 | zero atoms 2,3 | z atoms 0,1  (6 x 16 KB)
+constexpr int GB_BAR = GB_MN + 6 * SUB_A;
+constexpr int GB_STG = GB_BAR + 256;
+constexpr int GB_SMEM = GB_STG + 8 * 4096 + 1024;
+
+__global__ void __launch_bounds__(L_THREADS, 1)
+tc_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                   const __grid_constant__ CUtensorMap tm_a_mn, const __grid_constant__ CUtensorMap tm_z_mn,
+                   const GateBwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + GB_BAR;
+  auto full = [&](int s) { return bar0 + 8 * s; };
+  auto empty = [&](int s) { return bar0 + 64 + 8 * s; };
+  auto acc_full = [&](int s) { return bar0 + 128 + 8 * s; };
+  auto acc_empty = [&](int s) { return bar0 + 144 + 8 * s; };
+  const uint32_t mn_full = bar0 + 160, mn_empty = bar0 + 168, wg_full = bar0 + 176;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + GB_BAR + 192);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < GB_STAGES; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), 256);
+    }
+    mbar_init(mn_full, 1);
+    mbar_init(mn_empty, 1);
+    mbar_init(wg_full, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tm_a);
+    prefetch_tmap(&tm_b);
+    prefetch_tmap(&tm_a_mn);
+    prefetch_tmap(&tm_z_mn);
+  }
+  // channels 64..127 of the M = 128 weight-gradient MMA: two zero atoms, written once
+  for (int i = threadIdx.x; i < 2 * SUB_A / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(gbase + GB_MN + 2 * SUB_A)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  if (warp == 1) tmem_alloc<256>(smem_u32((const void*)tmem_slot));
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int n_local = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int j = 0; j < n_local; ++j) {
+        const int tile = blockIdx.x + j * gridDim.x;
+        const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM;
+        for (int ks = 0; ks < 2; ++ks, ++it) {
+          const int s = it % GB_STAGES, ph = (it / GB_STAGES) & 1;
+          mbar_wait(empty(s), ph ^ 1);
+          const uint32_t st = base + s * GB_STAGE;
+          mbar_arrive_expect_tx(full(s), GB_STAGE);
+          tma_load_4d(st, &tm_a, full(s), ks * SUBK, t0, b, 0);
+          tma_load_2d(st + SUB_A, &tm_b, full(s), ks * SUBK, 0);
+        }
+        // MN-major copies of the same rows for the weight gradient (single buffer: freed by the MMA warp)
+        mbar_wait(mn_empty, (j & 1) ^ 1);
+        mbar_arrive_expect_tx(mn_full, 4 * SUB_A);
+        tma_load_4d(base + GB_MN + 0 * SUB_A, &tm_a_mn, mn_full, 0, t0, b, 0);
+        tma_load_4d(base + GB_MN + 1 * SUB_A, &tm_a_mn, mn_full, SUBK, t0, b, 0);
+        tma_load_4d(base + GB_MN + 4 * SUB_A, &tm_z_mn, mn_full, 0, t0, b, 0);
+        tma_load_4d(base + GB_MN + 5 * SUB_A, &tm_z_mn, mn_full, SUBK, t0, b, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(128, 64);
+      constexpr uint32_t idesc_mn = umma_idesc_tf32(128, 64) | (1u << 15) | (1u << 16);
+      int it = 0;
+      for (int j = 0; j < n_local; ++j) {
+        const int ab = j & 1, aph = (j >> 1) & 1;
+        mbar_wait(acc_empty(ab), aph ^ 1);
+        tcgen05_fence_after();
+        for (int kk = 0; kk < 2; ++kk, ++it) {
+          const int s = it % GB_STAGES, ph = (it / GB_STAGES) & 1;
+          mbar_wait(full(s), ph);
+          tcgen05_fence_after();
+          const uint32_t st = base + s * GB_STAGE;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma_tf32(tmem + ab * 64, umma_desc_k_sw128(st + k4 * 32), umma_desc_k_sw128(st + SUB_A + k4 * 32), idesc,
+                      (kk | k4) > 0);
+          umma_commit(empty(s));
+        }
+        umma_commit(acc_full(ab));
+        mbar_wait(mn_full, j & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int k8 = 0; k8 < TM / 8; ++k8)
+          umma_tf32(tmem + 128, umma_desc_mn_sw128_32b(base + GB_MN + k8 * 1024, SUB_A, 512),
+                    umma_desc_mn_sw128_32b(base + GB_MN + 4 * SUB_A + k8 * 1024, SUB_A, 512), idesc_mn, (j | k8) > 0);
+        umma_commit(mn_empty);
+      }
+      umma_commit(wg_full);
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    uint8_t* stg = gbase + GB_STG + (warp - 2) * 4096;
+    const int cc4 = (lane & 7) * 4, rsub = lane >> 3;
+    const int c0 = half * 32, col = c0 + cc4;
+    for (int j = 0; j < n_local; ++j) {
+      const int tile = blockIdx.x + j * gridDim.x;
+      const int ab = j & 1, aph = (j >> 1) & 1;
+      const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM + q * 32;
+      // the three epilogue inputs do not depend on the accumulator: issue their loads before waiting for it
+      float4 r4[8], z4[8], sg4[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int t = min(t0 + jj * 4 + rsub, a.rows_out - 1);
+        const int64_t orow = (int64_t)b * a.rows_out + t;
+        r4[jj] = *reinterpret_cast<const float4*>(a.dzs + orow * 64 + col);
+        z4[jj] = *reinterpret_cast<const float4*>(a.z + orow * 64 + col);
+        sg4[jj] = *reinterpret_cast<const float4*>(a.sg + orow * a.sg_ld + col);
+      }
+      mbar_wait(acc_full(ab), aph);
+      tcgen05_fence_after();
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * 64 + c0, v);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      mbar_arrive(acc_empty(ab));
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+            make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int rr = jj * 4 + rsub;
+        const int t = t0 + rr;
+        if (t >= a.rows_out) continue;
+        const int64_t orow = (int64_t)b * a.rows_out + t;
+        float4 o = *reinterpret_cast<const float4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+        o.x += r4[jj].x, o.y += r4[jj].y, o.z += r4[jj].z, o.w += r4[jj].w;
+        // with z = tanh*sg:  da_f = dz*sg*(1-tanh^2) = dz*(sg - z*z/sg),  da_g = dz*tanh*sg*(1-sg) = dz*z*(1-sg);
+        // rows inside the zero prefix get none (Q1)
+        const float4 z = z4[jj], sg = sg4[jj];
+        const float live = t >= a.zp ? 1.f : 0.f;
+        float4 df, dg;
+        df.x = live * o.x * (sg.x - __fdividef(z.x * z.x, sg.x)), dg.x = live * o.x * z.x * (1.f - sg.x);
+        df.y = live * o.y * (sg.y - __fdividef(z.y * z.y, sg.y)), dg.y = live * o.y * z.y * (1.f - sg.y);
+        df.z = live * o.z * (sg.z - __fdividef(z.z * z.z, sg.z)), dg.z = live * o.z * z.z * (1.f - sg.z);
+        df.w = live * o.w * (sg.w - __fdividef(z.w * z.w, sg.w)), dg.w = live * o.w * z.w * (1.f - sg.w);
+        float* drow = a.dafg + orow * 128;
+        *reinterpret_cast<float4*>(drow + col) = df;
+        *reinterpret_cast<float4*>(drow + 64 + col) = dg;
+      }
+      __syncwarp();
+    }
+    if (n_local > 0 && q < 2) {
+      // dWp rows (projection output channels) live in TMEM lanes 0..63
+      mbar_wait(wg_full, 0);
+      tcgen05_fence_after();
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 128 + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+            make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int rr = jj * 4 + rsub;
+        const float4 o = *reinterpret_cast<const float4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+        red_add_v4(a.dWp + (int64_t)(q * 32 + rr) * 64 + col, o);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1222,6 +1423,38 @@ int tc_gemm_ares(const wn_handle* h, const TcOperand& A, int row_off, int rows_o
   }
   const int grid = g.num_tiles < h->sm_count ? g.num_tiles : h->sm_count;
   tc_gemm_ares_kernel<<<grid, L_THREADS, AR_SMEM, s>>>(ta, tb, g);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+// dz GEMM + gate derivative + dWp in one pass (fused shape R = G = 64); dWp must be 16-byte aligned
+int tc_gate_bwd(const wn_handle* h, const float* dout, const float* wpt, const float* dzs, const float* z, const float* sg,
+                int sg_ld, float* dafg, float* dWp, int zp, int rows, int num_seq, cudaStream_t s) {
+  CUtensorMap ta, tb, tam, tzm;
+  const uint64_t seq = (uint64_t)rows * 64, all = seq * num_seq;
+  WN_TRY(make_map_4d(&ta, dout, 64, rows, num_seq, 1, 64, seq, all, TM));
+  WN_TRY(make_map_2d(&tb, wpt, 64, 64, 64, 64));
+  WN_TRY(make_map_4d(&tam, dout, 64, rows, num_seq, 1, 64, seq, all, TM, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  WN_TRY(make_map_4d(&tzm, z, 64, rows, num_seq, 1, 64, seq, all, TM, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  GateBwdArgs g;
+  memset(&g, 0, sizeof(g));
+  g.dzs = dzs;
+  g.z = z;
+  g.sg = sg;
+  g.sg_ld = sg_ld;
+  g.dafg = dafg;
+  g.dWp = dWp;
+  g.zp = zp;
+  g.rows_out = rows;
+  g.tiles_per_seq = (rows + TM - 1) / TM;
+  g.num_tiles = g.tiles_per_seq * num_seq;
+  static bool attr = false;
+  if (!attr) {
+    WN_CHECK_CUDA(cudaFuncSetAttribute(tc_gate_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM));
+    attr = true;
+  }
+  const int grid = g.num_tiles < h->sm_count ? g.num_tiles : h->sm_count;
+  tc_gate_bwd_kernel<<<grid, L_THREADS, GB_SMEM, s>>>(ta, tb, tam, tzm, g);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
@@ -1582,8 +1815,13 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
       e.gate_z = ws + t.z[l];
       e.gate_dafg = ws + t.dafg;
       e.gate_zp = zp;
-      WN_TRY(tc_gemm(h, DO, 1, nullptr, &zero, W, ws + t.tc_wpt + (int64_t)l * G * R, G, e, ws + t.dz, G, s));
-      WN_TRY(wgrad_any(DO, 0, R, R, Z, 0, W, grads + ly.proj.w_off, nullptr, G, 1));
+      float* dwp = grads + ly.proj.w_off;
+      if (R == 64 && G == 64 && ((uintptr_t)dwp & 15) == 0 && getenv("WN_NO_GATE_FUSE") == nullptr) {
+        WN_TRY(tc_gate_bwd(h, dout, ws + t.tc_wpt + (int64_t)l * G * R, dzs, ws + t.z[l], sg, sg_ld, ws + t.dafg, dwp, zp, W, B, s));
+      } else {
+        WN_TRY(tc_gemm(h, DO, 1, nullptr, &zero, W, ws + t.tc_wpt + (int64_t)l * G * R, G, e, ws + t.dz, G, s));
+        WN_TRY(wgrad_any(DO, 0, R, R, Z, 0, W, grads + ly.proj.w_off, nullptr, G, 1));
+      }
     } else if (h->tape_gates_zs) {
       WN_TRY(simt_gate_backward_zs(ws + t.z[l], ws + t.tfsg[l], dzs, ws + t.dafg, P, W, G, zp, s));
     } else {
