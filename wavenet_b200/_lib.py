@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwavenet_b200.so")
+LIB_PATH = os.environ.get("WN_LIB_PATH") or os.path.join(_HERE, "libwavenet_b200.so")   # override: A/B builds
 
 WN_MAX_CAUSAL, WN_MAX_LAYERS, WN_MAX_HEAD, WN_NAME_LEN = 8, 32, 8, 64
 WN_PREC_FP32, WN_PREC_TF32 = 0, 1

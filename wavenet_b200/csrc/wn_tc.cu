@@ -136,6 +136,7 @@ struct LayerArgs {
   float* z_out;            // [B][W][64]
   float* sg_out;           // [B][W][64] sigmoid (backward rebuilds tanh = z / sigmoid), or null
   int W, d, zp, tiles_per_seq, num_tiles;
+  int reverse;             // walk the tiles from the last to the first
 };
 
 constexpr int L_B1 = 0;                       // 4 sub-tiles [128 x 32]  (64 KB)
@@ -191,6 +192,12 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int n_local = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // Serpentine order: odd layers walk the tiles from the end, so a layer starts with the rows the previous layer wrote
+  // last (still in L2) instead of the rows it wrote first (long evicted).
+  auto tile_of = [&](int j) {
+    const int i = (int)blockIdx.x + j * (int)gridDim.x;
+    return a.reverse ? a.num_tiles - 1 - i : i;
+  };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -213,7 +220,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           TR(j, 1);
         }
         if (j < n_local) {
-          const int tile = blockIdx.x + j * gridDim.x;
+          const int tile = tile_of(j);
           const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM;
           mbar_arrive_expect_tx(a_full(s), 65536);
           tma_load_4d(as + 0 * SUB_A, &tm_x, a_full(s), 0, t0 - a.d, b, 0);
@@ -223,7 +230,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           TR(j, 2);
         }
         if (j >= 1) {
-          const int jj = j - 1, s1 = jj & 1, tile = blockIdx.x + jj * gridDim.x;
+          const int jj = j - 1, s1 = jj & 1, tile = tile_of(jj);
           const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM;
           const uint32_t zs = base + L_A + s1 * 65536;
           mbar_wait(z_full(s1), (jj >> 1) & 1);
@@ -297,7 +304,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     const int row = q * 32 + lane;
     uint8_t* stg = gbase + L_STG + (warp - 2) * 2048;
     for (int j = 0; j < n_local; ++j) {
-      const int tile = blockIdx.x + j * gridDim.x;
+      const int tile = tile_of(j);
       const int s = j & 1, ph = (j >> 1) & 1;
       const int b = tile / a.tiles_per_seq, t = (tile % a.tiles_per_seq) * TM + row;
       const bool valid = t < a.W;
@@ -391,6 +398,7 @@ struct GemmTcArgs {
   float* gate_dafg;
   int gate_zp, gate_sg_ld;
   int zero_rows_below;     // output rows with t < this are forced to 0 (quirk Q1 zero prefix)
+  int reverse;             // walk the tiles from the last to the first (serpentine hand-off through L2)
 };
 
 template <int BN>
@@ -444,7 +452,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     if (lane == 0) {
       int it = 0;
       for (int j = 0; j < n_local; ++j) {
-        const int tile = blockIdx.x + j * gridDim.x;
+        const int tile = a.reverse ? a.num_tiles - 1 - ((int)blockIdx.x + j * (int)gridDim.x) : (int)blockIdx.x + j * (int)gridDim.x;
         const int grp = tile % a.ngroups, rt = tile / a.ngroups;
         const int b = rt / a.tiles_per_seq, t0 = (rt % a.tiles_per_seq) * TM;
         for (int sl = 0; sl < a.nslab; ++sl)
@@ -486,7 +494,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     uint8_t* stg = gbase + Cfg::STG + (warp - 2) * 4096;   // [32 rows][128 B], 16-byte chunks XOR-swizzled by row
     const int cc4 = (lane & 7) * 4;                         // column (within the 32-col block) this lane owns when coalesced
     for (int j = 0; j < n_local; ++j) {
-      const int tile = blockIdx.x + j * gridDim.x;
+      const int tile = a.reverse ? a.num_tiles - 1 - ((int)blockIdx.x + j * (int)gridDim.x) : (int)blockIdx.x + j * (int)gridDim.x;
       const int ab = j & 1, aph = (j >> 1) & 1;
       const int grp = MODE == 0 ? tile % a.ngroups : 0, rt = MODE == 0 ? tile / a.ngroups : tile;
       const int b = rt / a.tiles_per_seq, t0 = (rt % a.tiles_per_seq) * TM + q * 32;
@@ -779,6 +787,8 @@ struct WgradTcArgs {
   int m_split, m_valid;
   int64_t sn, sk;          // element (m, slab, c) -> dW[slab] + m*sn + c*sk
   int chunks_per_seq, num_chunks;
+  int reverse;             // walk the chunks from the last to the first
+  int run;                 // consecutive chunks per CTA visit (0: one contiguous range per CTA)
   int red_mode;            // 0 scalar atomics, 1 rows contiguous (sk == 1), 2 two taps interleaved (sk == 2); 1/2 need 16-B alignment
 };
 
@@ -838,15 +848,27 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const uint32_t tmem = *tmem_slot;
   // contiguous chunk range per CTA (per group of CTAs when the B slabs are grouped)
   const int grp = (int)blockIdx.x % a.ngroups, nrange = (int)gridDim.x / a.ngroups;
-  const int per = (a.num_chunks + nrange - 1) / nrange;
-  const int c_begin = ((int)blockIdx.x / a.ngroups) * per;
-  const int c_end = min(a.num_chunks, c_begin + per);
-  const int n_local = c_end - c_begin;
+  // chunk order: the CTAs of one group interleave runs of WG_RUN consecutive chunks (DRAM/L2 locality inside a run, and
+  // the whole grid sweeps the rows front to back -- or back to front (serpentine hand-off through L2))
+  const int WG_RUN = a.run;      // 0: one contiguous range per CTA
+  const int r0 = (int)blockIdx.x / a.ngroups;
+  int n_local, c_begin = 0;
+  if (WG_RUN > 0) {
+    const int nruns = (a.num_chunks + WG_RUN - 1) / WG_RUN;
+    const int my_runs = r0 < nruns ? (nruns - r0 + nrange - 1) / nrange : 0;
+    n_local = my_runs * WG_RUN;
+    if (my_runs > 0 && r0 + (my_runs - 1) * nrange == nruns - 1) n_local -= nruns * WG_RUN - a.num_chunks;   // partial last run
+  } else {
+    const int per = (a.num_chunks + nrange - 1) / nrange;
+    c_begin = r0 * per;
+    n_local = max(0, min(a.num_chunks, c_begin + per) - c_begin);
+  }
 
   if (warp == 0) {
     if (lane == 0) {
       for (int it = 0; it < n_local; ++it) {
-        const int chunk = c_begin + it;
+        const int fwd = WG_RUN > 0 ? (r0 + (it / WG_RUN) * nrange) * WG_RUN + it % WG_RUN : c_begin + it;
+        const int chunk = a.reverse ? a.num_chunks - 1 - fwd : fwd;
         const int b = chunk / a.chunks_per_seq, t0 = (chunk % a.chunks_per_seq) * KC;
         const int s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
         mbar_wait(empty(s), ph ^ 1);
@@ -988,6 +1010,7 @@ struct GateBwdArgs {
   float* dWp;              // [64 o][64 c]
   int sg_ld, zp;
   int rows_out, tiles_per_seq, num_tiles;
+  int reverse;
 };
 constexpr int GB_STAGE = SUB_A + 64 * 128;     // dout [128 x 32] + Wp^T [64 x 32]
 constexpr int GB_STAGES = 4;
@@ -1039,12 +1062,16 @@ tc_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int n_local = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_of = [&](int j) {
+    const int i = (int)blockIdx.x + j * (int)gridDim.x;
+    return a.reverse ? a.num_tiles - 1 - i : i;
+  };
 
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
       for (int j = 0; j < n_local; ++j) {
-        const int tile = blockIdx.x + j * gridDim.x;
+        const int tile = tile_of(j);
         const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM;
         for (int ks = 0; ks < 2; ++ks, ++it) {
           const int s = it % GB_STAGES, ph = (it / GB_STAGES) & 1;
@@ -1100,7 +1127,7 @@ tc_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     const int cc4 = (lane & 7) * 4, rsub = lane >> 3;
     const int c0 = half * 32, col = c0 + cc4;
     for (int j = 0; j < n_local; ++j) {
-      const int tile = blockIdx.x + j * gridDim.x;
+      const int tile = tile_of(j);
       const int ab = j & 1, aph = (j >> 1) & 1;
       const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM + q * 32;
       // the three epilogue inputs do not depend on the accumulator: issue their loads before waiting for it
@@ -1284,6 +1311,7 @@ struct TcEpilogue {
   float* gate_dafg = nullptr;
   int gate_zp = 0, gate_sg_ld = 0;
   int zero_rows_below = 0;
+  int reverse = 0;
 };
 
 // Y[(b, t)][0..N) = epi( sum_s A[slab_idx[s]][b][t + row_off[s]][:] . Wt[:, s*K ..]^T ),  Wt is [N][ns*K] (TF32-rounded)
@@ -1320,6 +1348,7 @@ int tc_gemm(const wn_handle* h, const TcOperand& A, int ns, const int* slab_idx,
   g.gate_zp = e.gate_zp;
   g.gate_sg_ld = e.gate_sg_ld ? e.gate_sg_ld : N;
   g.zero_rows_below = e.zero_rows_below;
+  g.reverse = e.reverse;
   g.rows_out = rows_out;
   g.nslab = ns;
   g.ksub = A.K / SUBK;
@@ -1338,7 +1367,7 @@ int tc_gemm(const wn_handle* h, const TcOperand& A, int ns, const int* slab_idx,
 // dW[slab](m, c) += sum_{b,t} dY[b][a_row_off + t][a_c0 + m] * X[slab_idx[s]][b][b_row_off[s] + t][c]   for m < m_valid (<= 128)
 int tc_wgrad(const wn_handle* h, const TcOperand& dY, int a_row_off, int a_c0, int m_valid, const TcOperand& X, int nb_slab,
              const int* b_row_off, const int* b_slab_idx, float* const* dW0, float* const* dW1, int m_split, int rows_it,
-             int64_t sn, int64_t sk, cudaStream_t s, int ngroups = 1) {
+             int64_t sn, int64_t sk, cudaStream_t s, int ngroups = 1, int reverse = 0) {
   // ngroups > 1: b_slab_idx and dW0 hold ngroups x nb_slab entries (group-major); a negative slab index pads a group
   const int NB = nb_slab * X.K;
   WN_REQUIRE(X.K % 32 == 0 && (NB == 64 || NB == 128 || NB == 256) && nb_slab <= 4 && m_valid <= 256 && ngroups >= 1 &&
@@ -1361,6 +1390,11 @@ int tc_wgrad(const wn_handle* h, const TcOperand& dY, int a_row_off, int a_c0, i
   g.nb_slab = nb_slab;
   g.nb_sub = X.K / 32;
   g.ngroups = ngroups;
+  g.reverse = reverse;
+  {
+    static const int run_env = getenv("WN_WG_RUN") ? atoi(getenv("WN_WG_RUN")) : 8;
+    g.run = run_env;
+  }
   bool aligned = sn % 4 == 0;
   for (int i = 0; i < nb_slab; ++i) {
     g.b_row_off[i] = b_row_off[i];
@@ -1429,7 +1463,7 @@ int tc_gemm_ares(const wn_handle* h, const TcOperand& A, int row_off, int rows_o
 
 // dz GEMM + gate derivative + dWp in one pass (fused shape R = G = 64); dWp must be 16-byte aligned
 int tc_gate_bwd(const wn_handle* h, const float* dout, const float* wpt, const float* dzs, const float* z, const float* sg,
-                int sg_ld, float* dafg, float* dWp, int zp, int rows, int num_seq, cudaStream_t s) {
+                int sg_ld, float* dafg, float* dWp, int zp, int rows, int num_seq, int reverse, cudaStream_t s) {
   CUtensorMap ta, tb, tam, tzm;
   const uint64_t seq = (uint64_t)rows * 64, all = seq * num_seq;
   WN_TRY(make_map_4d(&ta, dout, 64, rows, num_seq, 1, 64, seq, all, TM));
@@ -1445,6 +1479,7 @@ int tc_gate_bwd(const wn_handle* h, const float* dout, const float* wpt, const f
   g.dafg = dafg;
   g.dWp = dWp;
   g.zp = zp;
+  g.reverse = reverse;
   g.rows_out = rows;
   g.tiles_per_seq = (rows + TM - 1) / TM;
   g.num_tiles = g.tiles_per_seq * num_seq;
@@ -1574,6 +1609,7 @@ int tc_layer_launch(wn_handle* h, int l, cudaStream_t s) {
     a.zp = wn_zero_prefix(t.W, ly.dilation, 2);
     a.tiles_per_seq = tiles_per_seq;
     a.num_tiles = num_tiles;
+    a.reverse = getenv("WN_NO_SERP") ? 0 : (l & 1);
     tc_layer_kernel<<<grid, L_THREADS, L_SMEM + 1024, s>>>(tx, tw1, tw2, tz, tsg, a);
     WN_CHECK_LAUNCH();
   }
@@ -1795,11 +1831,15 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
     l0 += nl;
   }
   // ---- residual layers ----
+  const bool serp = getenv("WN_NO_SERP") == nullptr;
   int dt = 0;
   const float* dout = nullptr;
   for (int l = L - 1; l >= 0; --l) {
     const ResLayer& ly = h->layers[l];
     const int zp = wn_zero_prefix(W, ly.dilation, 2);
+    // serpentine hand-off: consecutive kernels walk the rows in opposite directions, so each one starts on the part
+    // of its input the previous kernel touched last (still in L2): gate D -> dW1 !D -> dx D -> next layer's gate !D
+    const int dir = serp ? (l & 1) : 0, ndir = serp ? !(l & 1) : 0;
     const float* dzs = ws + t.dzs + (int64_t)l * P * G;
     const float* sg = h->tape_gates_zs ? ws + t.tfsg[l] : ws + t.tfsg[l] + G;
     const int sg_ld = h->tape_gates_zs ? G : 2 * G;
@@ -1815,9 +1855,10 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
       e.gate_z = ws + t.z[l];
       e.gate_dafg = ws + t.dafg;
       e.gate_zp = zp;
+      e.reverse = dir;
       float* dwp = grads + ly.proj.w_off;
       if (R == 64 && G == 64 && ((uintptr_t)dwp & 15) == 0 && getenv("WN_NO_GATE_FUSE") == nullptr) {
-        WN_TRY(tc_gate_bwd(h, dout, ws + t.tc_wpt + (int64_t)l * G * R, dzs, ws + t.z[l], sg, sg_ld, ws + t.dafg, dwp, zp, W, B, s));
+        WN_TRY(tc_gate_bwd(h, dout, ws + t.tc_wpt + (int64_t)l * G * R, dzs, ws + t.z[l], sg, sg_ld, ws + t.dafg, dwp, zp, W, B, dir, s));
       } else {
         WN_TRY(tc_gemm(h, DO, 1, nullptr, &zero, W, ws + t.tc_wpt + (int64_t)l * G * R, G, e, ws + t.dz, G, s));
         WN_TRY(wgrad_any(DO, 0, R, R, Z, 0, W, grads + ly.proj.w_off, nullptr, G, 1));
@@ -1849,7 +1890,7 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
               msplit = G - m0;
             }
           }
-          WN_TRY(tc_wgrad(h, DA, 0, m0, mv, X, 2, boff, nullptr, d0, d1[0] ? d1 : nullptr, msplit, W, 2 * R, 2, s));
+          WN_TRY(tc_wgrad(h, DA, 0, m0, mv, X, 2, boff, nullptr, d0, d1[0] ? d1 : nullptr, msplit, W, 2 * R, 2, s, 1, ndir));
         }
       } else {
         for (int tap = 0; tap < 2; ++tap)
@@ -1864,6 +1905,7 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
       TcEpilogue e;
       e.Rsd = dout;
       e.ldr = R;
+      e.reverse = dir;
       WN_TRY(tc_gemm(h, DA, 2, sidx, roff, W, ws + t.tc_w1t + (int64_t)l * R * 4 * G, R, e, dnew, R, s));
       dout = dnew;
       dt ^= 1;
