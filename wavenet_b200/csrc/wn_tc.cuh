@@ -45,6 +45,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// ---- programmatic dependent launch --------------------------------------------------------
+// launch_dependents: the next kernel in the stream may be scheduled onto SMs as this grid's CTAs retire (its prologue --
+// barrier init, TMEM allocation, descriptor prefetch -- then overlaps our tail);  wait: blocks until the previous grid
+// has completed and its memory is visible.  Every global access of a kernel launched with the attribute comes after
+// pdl_wait().  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- proxies / fences ---------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
