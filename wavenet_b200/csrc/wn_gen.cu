@@ -1313,7 +1313,7 @@ extern "C" int wn_gen_prime(wn_gen* g, const float* params, const int32_t* windo
 }
 
 static void fill_args(wn_gen* g, GenArgs* a) {
-  memset(a, 0, sizeof(*a));
+  *a = GenArgs{};
   a->state = g->state;
   a->lay = g->lay;
   a->layers = (const GenLayerOff*)(g->state + g->lay.layers_dev);

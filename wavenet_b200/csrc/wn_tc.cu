@@ -1261,8 +1261,7 @@ int make_map_2d(CUtensorMap* m, const float* ptr, uint64_t d0, uint64_t d1, uint
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args&&... args) {
   static const bool pdl = getenv("WN_PDL") != nullptr;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3((unsigned)block);
   cfg.dynamicSmemBytes = smem;
