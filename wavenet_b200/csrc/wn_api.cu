@@ -218,6 +218,7 @@ static void plan_tape(const wn_handle* h, int B, int W, Tape* t) {
     t->dcx[1] = take(P * cmax);
   }
   t->loss_acc = take(16);
+  t->ce_colsum = take(c.quantization_steps > 256 ? c.quantization_steps : 256);
   {
     int gm = 0;
     for (int l = 0; l < L; ++l) gm = gm > h->layers[l].G ? gm : h->layers[l].G;
@@ -259,6 +260,7 @@ extern "C" int wn_bind_workspace(wn_handle* h, void* ws, int64_t bytes, int B, i
   h->tape = t;
   h->phase = PH_NONE;
   h->tc_tab_uploaded = false;
+  h->ce_colsum_valid = false;
   return WN_OK;
 }
 
@@ -451,7 +453,8 @@ extern "C" int wn_cross_entropy(wn_handle* h, const int32_t* target, float* loss
   cudaStream_t s = (cudaStream_t)st;
   const Tape& t = h->tape;
   const int64_t rows = (int64_t)t.B * h->T;
-  WN_TRY(simt_cross_entropy(WS(t.hbuf.back()), target, rows, h->Q, (double*)WS(t.loss_acc), loss, WS(t.dlogits), s));
+  WN_TRY(simt_cross_entropy(WS(t.hbuf.back()), target, rows, h->Q, (double*)WS(t.loss_acc), loss, WS(t.dlogits),
+                            WS(t.ce_colsum), &h->ce_colsum_valid, h->sm_count, s));
   h->phase = PH_LOSS;
   return WN_OK;
 }

@@ -76,6 +76,7 @@ struct Tape {
   int64_t dzs = 0;                    // [L][P][Gmax]  dskip . Ws_l for every layer (tensor-core backward)
   int64_t dcx[2] = {0, 0};            // [P][max causal width] (only when n_causal > 1)
   int64_t loss_acc = 0;               // 2 doubles
+  int64_t ce_colsum = 0;              // [Q] column sums of dlogits (bias gradient of the last head conv), by the CE kernel
   // tensor-core path: TF32-rounded, K-major weight copies (rebuilt every forward)
   int64_t tc_tab = 0, tc_w1 = 0, tc_w2 = 0, tc_ws = 0, tc_w1t = 0, tc_wpt = 0, tc_wst = 0;
   std::vector<int64_t> tc_wh, tc_wht;
@@ -113,6 +114,7 @@ struct wn_handle {
   bool skip_is_relu = false;
   bool save_gates = true;          // tensor-core forward also stores tanh | sigmoid (needed by backward)
   const float* bwd_dout = nullptr; // gradient w.r.t. the causal output after the residual backward
+  bool ce_colsum_valid = false;    // tape.ce_colsum matches tape.dlogits (set by wn_cross_entropy)
 };
 
 // ---- SIMT fp32 kernels (wn_simt.cu) ---------------------------------------------
@@ -175,7 +177,8 @@ int simt_gate_backward(const float* tfsg, const float* dz, float* dafg, int64_t 
                        cudaStream_t s);
 int simt_softmax_rows(const float* in, float* out, int64_t rows, int Q, cudaStream_t s);
 int simt_cross_entropy(const float* logits, const int32_t* target, int64_t rows, int Q, double* acc, float* loss,
-                       float* dlogits, cudaStream_t s);
+                       float* dlogits, float* colsum, bool* colsum_written, int sm_count, cudaStream_t s);
+int simt_add_vec(const float* src, float* dst, int n, cudaStream_t s);
 int simt_onehot_to_index(const float* onehot, int B, int Q, int W, int32_t* idx, cudaStream_t s);
 
 // ---- optimiser (wn_optim.cu) ---------------------------------------------------

@@ -232,6 +232,37 @@ __global__ void embed_unprepare_kernel(const float* __restrict__ demb, float* __
   dWc[((int64_t)r * Q + q) * kc + j] += demb[i];
 }
 
+// Same scatter with a per-block copy of the whole table in shared memory (kc*Q*R floats <= 200 KB): shared-memory
+// atomics absorb the 2*P*R updates, each block then adds its table to global memory once.
+__global__ void __launch_bounds__(1024) embed_backward_smem_kernel(const float* __restrict__ dout,
+                                                                   const int32_t* __restrict__ idx,
+                                                                   float* __restrict__ demb, int64_t P, int W, int R, int Q,
+                                                                   int kc) {
+  extern __shared__ float tab[];
+  const int n = kc * Q * R;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) tab[i] = 0.f;
+  __syncthreads();
+  const int rv = R >> 2;   // R % 4 == 0
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P * rv; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / rv;
+    const int r = (int)(i - p * rv) * 4;
+    const int t = (int)(p % W);
+    const float4 v = *reinterpret_cast<const float4*>(dout + p * R + r);
+    for (int j = 0; j < kc; ++j) {
+      const int s = kc - 1 - j;
+      if (t - s >= 0) {
+        float* e = tab + (j * Q + idx[p - s]) * R + r;
+        atomicAdd(e, v.x), atomicAdd(e + 1, v.y), atomicAdd(e + 2, v.z), atomicAdd(e + 3, v.w);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = tab[i];
+    if (v != 0.f) atomicAdd(demb + i, v);
+  }
+}
+
 __global__ void colsum_kernel(const float* __restrict__ a, int64_t rows, int C, float* __restrict__ out) {
   // grid.x over column blocks of 32, grid.y over row splits; block (32, 8)
   const int c = blockIdx.x * 32 + threadIdx.x;
@@ -288,20 +319,24 @@ __global__ void gate_backward_kernel(const float* __restrict__ tfsg, const float
 __global__ void gate_backward_zs_kernel(const float* __restrict__ z, const float* __restrict__ sg,
                                         const float* __restrict__ dz, float* __restrict__ dafg, int64_t P, int W, int G,
                                         int zp) {
+  // one thread per (position, 4 channels); G % 4 == 0 is guaranteed by the tensor-core layouts that store (z, sigmoid)
+  const int gv = G >> 2;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P * G) return;
-  const int64_t p = i / G;
-  const int gch = (int)(i - p * G);
+  if (i >= P * gv) return;
+  const int64_t p = i / gv;
+  const int g4 = (int)(i - p * gv) * 4;
   const int t = (int)(p % W);
-  const float zz = z[i], s = sg[i], d = dz[i];
-  float df = d * (s - zz * zz / s);
-  float dg = d * zz * (1.f - s);
-  if (t < zp) {
-    df = 0.f;
-    dg = 0.f;
-  }
-  dafg[p * 2 * G + gch] = df;
-  dafg[p * 2 * G + G + gch] = dg;
+  const float4 zz = *reinterpret_cast<const float4*>(z + p * G + g4);
+  const float4 s = *reinterpret_cast<const float4*>(sg + p * G + g4);
+  const float4 d = *reinterpret_cast<const float4*>(dz + p * G + g4);
+  float4 df, dg;
+  df.x = d.x * (s.x - zz.x * zz.x / s.x), dg.x = d.x * zz.x * (1.f - s.x);
+  df.y = d.y * (s.y - zz.y * zz.y / s.y), dg.y = d.y * zz.y * (1.f - s.y);
+  df.z = d.z * (s.z - zz.z * zz.z / s.z), dg.z = d.z * zz.z * (1.f - s.z);
+  df.w = d.w * (s.w - zz.w * zz.w / s.w), dg.w = d.w * zz.w * (1.f - s.w);
+  if (t < zp) df = dg = make_float4(0.f, 0.f, 0.f, 0.f);
+  *reinterpret_cast<float4*>(dafg + p * 2 * G + g4) = df;
+  *reinterpret_cast<float4*>(dafg + p * 2 * G + G + g4) = dg;
 }
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -434,7 +469,20 @@ int simt_embed_backward(const float* dout, const int32_t* idx, float* demb, floa
                         int R, int Q, int kc, cudaStream_t s) {
   const int64_t P = (int64_t)B * W;
   WN_CHECK_CUDA(cudaMemsetAsync(demb, 0, sizeof(float) * R * Q * kc, s));
-  embed_backward_kernel<<<blocks_for(P * R, 256), 256, 0, s>>>(dout, idx, demb, P, W, R, Q, kc);
+  const size_t tab_bytes = sizeof(float) * R * Q * kc;
+  if (R % 4 == 0 && tab_bytes <= 200 * 1024 && P * R >= (int64_t)1 << 22) {
+    static bool attr = false;
+    if (!attr) {
+      WN_CHECK_CUDA(cudaFuncSetAttribute(embed_backward_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+    int dev = 0, sms = 0;
+    WN_CHECK_CUDA(cudaGetDevice(&dev));
+    WN_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    embed_backward_smem_kernel<<<sms, 1024, tab_bytes, s>>>(dout, idx, demb, P, W, R, Q, kc);
+  } else {
+    embed_backward_kernel<<<blocks_for(P * R, 256), 256, 0, s>>>(dout, idx, demb, P, W, R, Q, kc);
+  }
   WN_CHECK_LAUNCH();
   embed_unprepare_kernel<<<blocks_for((int64_t)R * Q * kc, 256), 256, 0, s>>>(demb, dWc, R, Q, kc);
   WN_CHECK_LAUNCH();
@@ -468,7 +516,8 @@ int simt_gate_backward(const float* tfsg, const float* dz, float* dafg, int64_t 
 
 int simt_gate_backward_zs(const float* z, const float* sg, const float* dz, float* dafg, int64_t P, int W, int G, int zp,
                           cudaStream_t s) {
-  gate_backward_zs_kernel<<<blocks_for(P * G, 256), 256, 0, s>>>(z, sg, dz, dafg, P, W, G, zp);
+  WN_REQUIRE(G % 4 == 0, WN_EINVAL, "gate_backward_zs: G must be a multiple of 4");
+  gate_backward_zs_kernel<<<blocks_for(P * (G / 4), 256), 256, 0, s>>>(z, sg, dz, dafg, P, W, G, zp);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
@@ -479,10 +528,93 @@ int simt_softmax_rows(const float* in, float* out, int64_t rows, int Q, cudaStre
   return WN_OK;
 }
 
+// Q == 256 fast path: one warp per row, the row stays in registers (one read of the logits), grid-stride over rows;
+// also accumulates the column sums of dlogits (= bias gradient of the last head conv, wavenet.py:577-586 backward)
+// so the backward pass does not have to read dlogits again for them.
+__global__ void __launch_bounds__(256) cross_entropy256_kernel(const float* __restrict__ logits,
+                                                               const int32_t* __restrict__ target, int64_t rows,
+                                                               double* __restrict__ acc, float* __restrict__ dlogits,
+                                                               float* __restrict__ colsum) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __shared__ double part[8];
+  __shared__ float cs[8][256];
+  double my = 0.0;
+  float c[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float invn = 1.f / (float)rows;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + wid; row < rows; row += (int64_t)gridDim.x * 8) {
+    const float4* x = reinterpret_cast<const float4*>(logits + row * 256);
+    const float4 a = x[lane], b = x[32 + lane];
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float m = v[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, v[i]);
+    m = warp_max(m);
+    float e[8], sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      e[i] = expf(v[i] - m);
+      sum += e[i];
+    }
+    sum = warp_sum(sum);
+    const int tg = target[row];
+    const float inv = 1.f / sum;
+    float xt = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int q = (i < 4 ? 0 : 128) + lane * 4 + (i & 3);
+      float d = e[i] * inv;
+      if (q == tg) {
+        d -= 1.f;
+        xt = v[i];
+      }
+      e[i] = d * invn;
+      c[i] += e[i];
+    }
+    xt = warp_sum(xt);
+    float4* o = reinterpret_cast<float4*>(dlogits + row * 256);
+    o[lane] = make_float4(e[0], e[1], e[2], e[3]);
+    o[32 + lane] = make_float4(e[4], e[5], e[6], e[7]);
+    if (lane == 0) my += (double)(m + logf(sum)) - (double)xt;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) cs[wid][(i < 4 ? 0 : 128) + lane * 4 + (i & 3)] = c[i];
+  if (lane == 0) part[wid] = my;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += cs[w][threadIdx.x];
+  atomicAdd(colsum + threadIdx.x, t);
+  if (threadIdx.x == 0) {
+    double tt = 0.0;
+    for (int i = 0; i < 8; ++i) tt += part[i];
+    atomicAdd(acc, tt);
+  }
+}
+
+__global__ void add_vec_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
+int simt_add_vec(const float* src, float* dst, int n, cudaStream_t s) {
+  add_vec_kernel<<<blocks_for(n, 256), 256, 0, s>>>(src, dst, n);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
 int simt_cross_entropy(const float* logits, const int32_t* target, int64_t rows, int Q, double* acc, float* loss,
-                       float* dlogits, cudaStream_t s) {
+                       float* dlogits, float* colsum, bool* colsum_written, int sm_count, cudaStream_t s) {
   WN_CHECK_CUDA(cudaMemsetAsync(acc, 0, 2 * sizeof(double), s));
-  cross_entropy_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(logits, target, rows, Q, acc, dlogits);
+  const bool fast = Q == 256 && colsum && (((uintptr_t)logits | (uintptr_t)dlogits) & 15) == 0;
+  if (colsum_written) *colsum_written = fast;
+  if (fast) {
+    WN_CHECK_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * 256, s));
+    const int64_t want = blocks_for(rows, 8);
+    const int grid = (int)(want < (int64_t)sm_count * 8 ? want : (int64_t)sm_count * 8);
+    cross_entropy256_kernel<<<grid, 256, 0, s>>>(logits, target, rows, acc, dlogits, colsum);
+  } else {
+    cross_entropy_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(logits, target, rows, Q, acc, dlogits);
+  }
   WN_CHECK_LAUNCH();
   loss_finalize_kernel<<<1, 1, 0, s>>>(acc, rows, loss);
   WN_CHECK_LAUNCH();

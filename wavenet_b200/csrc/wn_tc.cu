@@ -401,6 +401,7 @@ struct GemmTcArgs {
   int gate_zp, gate_sg_ld;
   int zero_rows_below;     // output rows with t < this are forced to 0 (quirk Q1 zero prefix)
   int reverse;             // walk the tiles from the last to the first (serpentine hand-off through L2)
+  float* colsum_out;       // MODE 0: += column sums of the stored result (bias gradient of the producing conv), or null
 };
 
 template <int BN>
@@ -497,6 +498,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     constexpr int CH = BN / 64;   // 32-column chunks per warp
     uint8_t* stg = gbase + Cfg::STG + (warp - 2) * 4096;   // [32 rows][128 B], 16-byte chunks XOR-swizzled by row
     const int cc4 = (lane & 7) * 4;                         // column (within the 32-col block) this lane owns when coalesced
+    float4 csum[CH];                                        // MODE 0 + colsum_out: this lane's columns summed over its rows
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) csum[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int j = 0; j < n_local; ++j) {
       const int tile = a.reverse ? a.num_tiles - 1 - ((int)blockIdx.x + j * (int)gridDim.x) : (int)blockIdx.x + j * (int)gridDim.x;
       const int ab = j & 1, aph = (j >> 1) & 1;
@@ -504,7 +508,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int b = rt / a.tiles_per_seq, t0 = (rt % a.tiles_per_seq) * TM + q * 32;
       mbar_wait(acc_full(ab), aph);
       tcgen05_fence_after();
-#pragma unroll 1
+#pragma unroll
       for (int ch = 0; ch < CH; ++ch) {
         const int ct = (half * CH + ch) * 32;          // column inside the TMEM tile
         const int c0 = grp * BN + ct;                  // output column
@@ -612,12 +616,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             }
             if (a.round_out) o.x = tf32_rna(o.x), o.y = tf32_rna(o.y), o.z = tf32_rna(o.z), o.w = tf32_rna(o.w);
             *reinterpret_cast<float4*>(ybase + orow * a.ldy + ycol) = o;
+            if (a.colsum_out) csum[ch].x += o.x, csum[ch].y += o.y, csum[ch].z += o.z, csum[ch].w += o.w;
           }
         }
         __syncwarp();
       }
       tcgen05_fence_before();
       mbar_arrive(acc_empty(ab));
+    }
+    if (MODE == 0 && a.colsum_out && a.ngroups == 1) {
+      // lanes l, l+8, l+16, l+24 own the same four columns (different rows): fold them, one atomic set per warp
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) {
+        float4 v = csum[ch];
+#pragma unroll
+        for (int o = 8; o < 32; o <<= 1) {
+          v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+          v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+          v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
+          v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+        }
+        const int c0 = (half * CH + ch) * 32;
+        if (lane < 8 && c0 < a.N) {
+          float* o = a.colsum_out + c0 + cc4;
+          atomicAdd(o, v.x), atomicAdd(o + 1, v.y), atomicAdd(o + 2, v.z), atomicAdd(o + 3, v.w);
+        }
+      }
     }
   }
   tcgen05_fence_before();
@@ -1339,6 +1363,7 @@ struct TcEpilogue {
   int gate_zp = 0, gate_sg_ld = 0;
   int zero_rows_below = 0;
   int reverse = 0;
+  float* colsum_out = nullptr;
 };
 
 // Y[(b, t)][0..N) = epi( sum_s A[slab_idx[s]][b][t + row_off[s]][:] . Wt[:, s*K ..]^T ),  Wt is [N][ns*K] (TF32-rounded)
@@ -1376,6 +1401,7 @@ int tc_gemm(const wn_handle* h, const TcOperand& A, int ns, const int* slab_idx,
   g.gate_sg_ld = e.gate_sg_ld ? e.gate_sg_ld : N;
   g.zero_rows_below = e.zero_rows_below;
   g.reverse = e.reverse;
+  g.colsum_out = e.colsum_out;
   g.rows_out = rows_out;
   g.nslab = ns;
   g.ksub = A.K / SUBK;
@@ -1707,6 +1733,7 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
   // ---- head ----
   const float* d = ws + t.dlogits;
   int tog = 0;
+  bool bias_done = false;
   for (int i = nh - 1; i >= 0; --i) {
     const ConvParam& cp = h->head[i];
     const bool first = i == 0;
@@ -1720,7 +1747,15 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
       float* dw = grads + cp.w_off + (int64_t)m0 * cp.in_ch;
       WN_TRY(tc_wgrad(h, dY, 0, m0, mv, X, 1, &aoff, nullptr, &dw, nullptr, 256, T, cp.in_ch, 1, s));
     }
-    if (cp.b_off >= 0) WN_TRY(simt_colsum(d, (int64_t)B * T, cp.out_ch, grads + cp.b_off, s));
+    // bias gradient = column sums of d: taken from the CE kernel (last conv) or from the epilogue of the GEMM that
+    // produced d (previous iteration) when available, else one more pass over d
+    if (cp.b_off >= 0 && !bias_done) {
+      if (i == nh - 1 && h->ce_colsum_valid && d == ws + t.dlogits)
+        WN_TRY(simt_add_vec(ws + t.ce_colsum, grads + cp.b_off, cp.out_ch, s));
+      else
+        WN_TRY(simt_colsum(d, (int64_t)B * T, cp.out_ch, grads + cp.b_off, s));
+    }
+    bias_done = false;
     if (first && h->head_external) return WN_OK;
     // d_prev = (d . W) masked by the stored (post-ReLU) input
     const int64_t n = (int64_t)cp.out_ch * cp.in_ch;
@@ -1732,6 +1767,10 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
     e.ldm = cp.in_ch;
     e.mask_rows_in = rin;
     e.mask_row_off = aoff;
+    if (i > 0 && h->head[i - 1].b_off >= 0 && cp.in_ch <= 256) {
+      e.colsum_out = grads + h->head[i - 1].b_off;   // d of the next iteration is this GEMM's output
+      bias_done = true;
+    }
     WN_TRY(tc_gemm(h, dY, 1, nullptr, &zero, T, ws + t.tc_wht[i], cp.in_ch, e, ws + t.dh[tog], cp.in_ch, s));
     d = ws + t.dh[tog];
     tog ^= 1;
