@@ -194,5 +194,5 @@ int tc_forward_residual(wn_handle* h, const float* params, cudaStream_t s);
 int tc_forward_head(wn_handle* h, const float* params, int T, bool external, cudaStream_t s);
 int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s);
 int simt_colsum(const float* a, int64_t rows, int C, float* out, cudaStream_t s);
-int simt_gate_backward_zs(const float* z, const float* sg, const float* dz, float* dafg, int64_t P, int W, int G, int zp,
+int simt_gate_backward_zs(const float* z, const float* sg, int sg_half, const float* dz, float* dafg, int64_t P, int W, int G, int zp,
                           cudaStream_t s);

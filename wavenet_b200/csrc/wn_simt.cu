@@ -1,5 +1,6 @@
 // Exact-fp32 SIMT kernels: the parity path (WN_PREC_FP32) and every shape the
 // tcgen05 path does not specialise.  All activations are channels-last fp32.
+#include <cuda_fp16.h>
 #include "wn_common.h"
 
 namespace {
@@ -316,7 +317,7 @@ __global__ void gate_backward_kernel(const float* __restrict__ tfsg, const float
 }
 
 // same derivative from (z, sigmoid) as stored by the tensor-core forward: tanh = z / sigmoid
-__global__ void gate_backward_zs_kernel(const float* __restrict__ z, const float* __restrict__ sg,
+__global__ void gate_backward_zs_kernel(const float* __restrict__ z, const float* __restrict__ sg, int sg_half,
                                         const float* __restrict__ dz, float* __restrict__ dafg, int64_t P, int W, int G,
                                         int zp) {
   // one thread per (position, 4 channels); G % 4 == 0 is guaranteed by the tensor-core layouts that store (z, sigmoid)
@@ -327,7 +328,15 @@ __global__ void gate_backward_zs_kernel(const float* __restrict__ z, const float
   const int g4 = (int)(i - p * gv) * 4;
   const int t = (int)(p % W);
   const float4 zz = *reinterpret_cast<const float4*>(z + p * G + g4);
-  const float4 s = *reinterpret_cast<const float4*>(sg + p * G + g4);
+  float4 s;
+  if (sg_half) {   // fp16 sigmoid tape written by the fused tensor-core layer kernel
+    const uint2 raw = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(sg) + p * G + g4);
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    s = make_float4(lo.x, lo.y, hi.x, hi.y);
+  } else {
+    s = *reinterpret_cast<const float4*>(sg + p * G + g4);
+  }
   const float4 d = *reinterpret_cast<const float4*>(dz + p * G + g4);
   float4 df, dg;
   df.x = d.x * (s.x - zz.x * zz.x / s.x), dg.x = d.x * zz.x * (1.f - s.x);
@@ -514,10 +523,10 @@ int simt_gate_backward(const float* tfsg, const float* dz, float* dafg, int64_t 
   return WN_OK;
 }
 
-int simt_gate_backward_zs(const float* z, const float* sg, const float* dz, float* dafg, int64_t P, int W, int G, int zp,
+int simt_gate_backward_zs(const float* z, const float* sg, int sg_half, const float* dz, float* dafg, int64_t P, int W, int G, int zp,
                           cudaStream_t s) {
   WN_REQUIRE(G % 4 == 0, WN_EINVAL, "gate_backward_zs: G must be a multiple of 4");
-  gate_backward_zs_kernel<<<blocks_for(P * (G / 4), 256), 256, 0, s>>>(z, sg, dz, dafg, P, W, G, zp);
+  gate_backward_zs_kernel<<<blocks_for(P * (G / 4), 256), 256, 0, s>>>(z, sg, sg_half, dz, dafg, P, W, G, zp);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }

@@ -12,6 +12,7 @@
 //                    skip sum  sum_l Ws_l z_l  (ONE GEMM with K = 64*L instead of L read-modify-write
 //                    passes over the 256-channel skip tensor, wavenet.py:579) and for the head convs.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -99,6 +100,18 @@ __global__ void tc_relu_rows_kernel(float* __restrict__ a, int C, int rows_per_s
   *p = v;
 }
 
+// four consecutive sigmoid values of the tape: fp32, or fp16 when the fused layer kernel wrote them (the 10-bit
+// mantissa equals what the TF32 MMAs keep of every other operand)
+__device__ __forceinline__ float4 load_sg4(const float* sg, int64_t elem, int is_half) {
+  if (is_half) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(sg) + elem);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return *reinterpret_cast<const float4*>(sg + elem);
+}
+
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -134,7 +147,7 @@ __device__ __forceinline__ void store_block_coalesced(uint8_t* stg, const uint32
 struct LayerArgs {
   float* x_out;            // [B][W][64]
   float* z_out;            // [B][W][64]
-  float* sg_out;           // [B][W][64] sigmoid (backward rebuilds tanh = z / sigmoid), or null
+  float* sg_out;           // [B][W][64] fp16 sigmoid (backward rebuilds tanh = z / sigmoid), or null
   int W, d, zp, tiles_per_seq, num_tiles;
   int reverse;             // walk the tiles from the last to the first
 };
@@ -239,10 +252,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           TR(j, 3);
           tma_store_4d(&tm_z, zs + 0 * SUB_A, 0, t0, b, 0);
           tma_store_4d(&tm_z, zs + 1 * SUB_A, SUBK, t0, b, 0);
-          if (a.sg_out) {
-            tma_store_4d(&tm_sg, zs + 2 * SUB_A, 0, t0, b, 0);
-            tma_store_4d(&tm_sg, zs + 3 * SUB_A, SUBK, t0, b, 0);
-          }
+          if (a.sg_out) tma_store_4d(&tm_sg, zs + 2 * SUB_A, 0, t0, b, 0);   // fp16 [128 x 64]
           bulk_commit_group();
         }
       }
@@ -324,6 +334,9 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 #pragma unroll
       for (int c = 0; c < 8; ++c) xr[c] = *reinterpret_cast<const float4*>(as_g + (2 + half) * SUB_A + sw128_off(row, c));
       tmem_ld_wait();
+      // the fp16 sigmoid tile below covers sub-tile 2 for BOTH channel halves: the partner warp (same rows, other half)
+      // must have taken its residual before either of us overwrites it
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
       const bool live = valid && t >= a.zp;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -337,10 +350,18 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         *reinterpret_cast<uint4*>(as_g + half * SUB_A + sw128_off(row, c)) =
             make_uint4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
       if (a.sg_out) {
+        // sigmoid as fp16, one [128 x 64] tile of 128-byte rows over x(t) (already in xr): source of its bulk store
 #pragma unroll
-        for (int c = 0; c < 8; ++c)   // sigmoid over x(t) (already in xr): source of the sigmoid bulk store
-          *reinterpret_cast<uint4*>(as_g + (2 + half) * SUB_A + sw128_off(row, c)) =
-              make_uint4(g[4 * c], g[4 * c + 1], g[4 * c + 2], g[4 * c + 3]);
+        for (int c = 0; c < 4; ++c) {
+          uint4 pk;
+          __half2 h0 = __floats2half2_rn(__uint_as_float(g[8 * c]), __uint_as_float(g[8 * c + 1]));
+          __half2 h1 = __floats2half2_rn(__uint_as_float(g[8 * c + 2]), __uint_as_float(g[8 * c + 3]));
+          __half2 h2 = __floats2half2_rn(__uint_as_float(g[8 * c + 4]), __uint_as_float(g[8 * c + 5]));
+          __half2 h3 = __floats2half2_rn(__uint_as_float(g[8 * c + 6]), __uint_as_float(g[8 * c + 7]));
+          pk.x = *reinterpret_cast<uint32_t*>(&h0), pk.y = *reinterpret_cast<uint32_t*>(&h1);
+          pk.z = *reinterpret_cast<uint32_t*>(&h2), pk.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(as_g + 2 * SUB_A + sw128_off(row, half * 4 + c)) = pk;
+        }
       }
       fence_proxy_async();
       tcgen05_fence_before();
@@ -398,7 +419,7 @@ struct GemmTcArgs {
   const float* gate_sg;    // [rows][gate_sg_ld] sigmoid, or null
   const float* gate_z;     // [rows][G] z = tanh * sigmoid
   float* gate_dafg;
-  int gate_zp, gate_sg_ld;
+  int gate_zp, gate_sg_ld, gate_sg_half;   // gate_sg_half: the sigmoid tape is fp16 (ld in elements)
   int zero_rows_below;     // output rows with t < this are forced to 0 (quirk Q1 zero prefix)
   int reverse;             // walk the tiles from the last to the first (serpentine hand-off through L2)
   float* colsum_out;       // MODE 0: += column sums of the stored result (bias gradient of the producing conv), or null
@@ -550,7 +571,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             const int64_t orow = (int64_t)b * a.rows_out + t;
             r4[jj] = *reinterpret_cast<const float4*>(a.Rsd + orow * a.ldr + col);
             z4[jj] = *reinterpret_cast<const float4*>(a.gate_z + orow * a.N + col);
-            sg4[jj] = *reinterpret_cast<const float4*>(a.gate_sg + orow * a.gate_sg_ld + col);
+            sg4[jj] = load_sg4(a.gate_sg, orow * a.gate_sg_ld + col, a.gate_sg_half);
           }
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
@@ -1038,7 +1059,7 @@ struct GateBwdArgs {
   const float* sg;         // [rows][sg_ld]
   float* dafg;             // [rows][128]
   float* dWp;              // [64 o][64 c]
-  int sg_ld, zp;
+  int sg_ld, sg_half, zp;  // sg_half: sigmoid tape is fp16 (ld in elements)
   int rows_out, tiles_per_seq, num_tiles;
   int reverse;
 };
@@ -1170,7 +1191,7 @@ tc_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         const int64_t orow = (int64_t)b * a.rows_out + t;
         r4[jj] = *reinterpret_cast<const float4*>(a.dzs + orow * 64 + col);
         z4[jj] = *reinterpret_cast<const float4*>(a.z + orow * 64 + col);
-        sg4[jj] = *reinterpret_cast<const float4*>(a.sg + orow * a.sg_ld + col);
+        sg4[jj] = load_sg4(a.sg, orow * a.sg_ld + col, a.sg_half);
       }
       mbar_wait(acc_full(ab), aph);
       tcgen05_fence_after();
@@ -1262,6 +1283,22 @@ int make_map_4d(CUtensorMap* m, const float* ptr, uint64_t d0, uint64_t d1, uint
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   WN_REQUIRE(r == CUDA_SUCCESS, WN_ECUDA, "cuTensorMapEncodeTiled(4d) failed: %d", (int)r);
+  return WN_OK;
+}
+
+// fp16 tensor [d2][d1][d0 = 64] viewed 4-D, box [1][1][box1][64] (128-byte rows), SWIZZLE_128B
+int make_map_4d_f16(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
+                    uint32_t box1) {
+  EncodeTiledFn enc = get_encode();
+  WN_REQUIRE(enc, WN_ECUDA, "cuTensorMapEncodeTiled is unavailable");
+  WN_REQUIRE(d0 == 64, WN_EINVAL, "fp16 tile maps are 64 channels wide");
+  cuuint64_t dims[4] = {d0, d1, d2, 1};
+  cuuint64_t strides[3] = {s1 * 2, s2 * 2, s2 * d2 * 2};
+  cuuint32_t box[4] = {64, box1, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  WN_REQUIRE(r == CUDA_SUCCESS, WN_ECUDA, "cuTensorMapEncodeTiled(f16) failed: %d", (int)r);
   return WN_OK;
 }
 
@@ -1360,7 +1397,7 @@ struct TcEpilogue {
   const float* gate_sg = nullptr;
   const float* gate_z = nullptr;
   float* gate_dafg = nullptr;
-  int gate_zp = 0, gate_sg_ld = 0;
+  int gate_zp = 0, gate_sg_ld = 0, gate_sg_half = 0;
   int zero_rows_below = 0;
   int reverse = 0;
   float* colsum_out = nullptr;
@@ -1399,6 +1436,7 @@ int tc_gemm(const wn_handle* h, const TcOperand& A, int ns, const int* slab_idx,
   g.gate_dafg = e.gate_dafg;
   g.gate_zp = e.gate_zp;
   g.gate_sg_ld = e.gate_sg_ld ? e.gate_sg_ld : N;
+  g.gate_sg_half = e.gate_sg_half;
   g.zero_rows_below = e.zero_rows_below;
   g.reverse = e.reverse;
   g.colsum_out = e.colsum_out;
@@ -1516,7 +1554,7 @@ int tc_gemm_ares(const wn_handle* h, const TcOperand& A, int row_off, int rows_o
 
 // dz GEMM + gate derivative + dWp in one pass (fused shape R = G = 64); dWp must be 16-byte aligned
 int tc_gate_bwd(const wn_handle* h, const float* dout, const float* wpt, const float* dzs, const float* z, const float* sg,
-                int sg_ld, float* dafg, float* dWp, int zp, int rows, int num_seq, int reverse, cudaStream_t s) {
+                int sg_ld, int sg_half, float* dafg, float* dWp, int zp, int rows, int num_seq, int reverse, cudaStream_t s) {
   CUtensorMap ta, tb, tam, tzm;
   const uint64_t seq = (uint64_t)rows * 64, all = seq * num_seq;
   WN_TRY(make_map_4d(&ta, dout, 64, rows, num_seq, 1, 64, seq, all, TM));
@@ -1529,6 +1567,7 @@ int tc_gate_bwd(const wn_handle* h, const float* dout, const float* wpt, const f
   g.z = z;
   g.sg = sg;
   g.sg_ld = sg_ld;
+  g.sg_half = sg_half;
   g.dafg = dafg;
   g.dWp = dWp;
   g.zp = zp;
@@ -1650,7 +1689,7 @@ int tc_layer_launch(wn_handle* h, int l, cudaStream_t s) {
     CUtensorMap tx, tw1, tw2, tz, tsg;
     WN_TRY(make_map_4d(&tx, h->ws + t.x[l], R, t.W, t.B, 1, R, (uint64_t)t.W * R, (uint64_t)t.P * R, TM));
     WN_TRY(make_map_4d(&tz, h->ws + t.z[l], G, t.W, t.B, 1, G, (uint64_t)t.W * G, (uint64_t)t.P * G, TM));
-    WN_TRY(make_map_4d(&tsg, h->ws + t.tfsg[l], G, t.W, t.B, 1, G, (uint64_t)t.W * G, (uint64_t)t.P * G, TM));
+    WN_TRY(make_map_4d_f16(&tsg, h->ws + t.tfsg[l], G, t.W, t.B, G, (uint64_t)t.W * G, TM));
     WN_TRY(make_map_2d(&tw1, h->ws + t.tc_w1 + (int64_t)l * 2 * G * 2 * R, 2 * R, 2 * G, 2 * R, 128));
     WN_TRY(make_map_2d(&tw2, h->ws + t.tc_w2 + (int64_t)l * R * G, G, R, G, 64));
     LayerArgs a;
@@ -1909,6 +1948,7 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
     const float* dzs = ws + t.dzs + (int64_t)l * P * G;
     const float* sg = h->tape_gates_zs ? ws + t.tfsg[l] : ws + t.tfsg[l] + G;
     const int sg_ld = h->tape_gates_zs ? G : 2 * G;
+    const int sg_half = h->tape_gates_zs ? 1 : 0;   // the fused layer kernel stores sigmoid as fp16
     TcOperand Z{ws + t.z[l], G, W, B, 1, 0};
     if (dout) {
       // dz = dout . Wp + dzs_l, gate derivative fused into the epilogue -> dafg
@@ -1918,19 +1958,20 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
       e.ldr = G;
       e.gate_sg = sg;
       e.gate_sg_ld = sg_ld;
+      e.gate_sg_half = sg_half;
       e.gate_z = ws + t.z[l];
       e.gate_dafg = ws + t.dafg;
       e.gate_zp = zp;
       e.reverse = dir;
       float* dwp = grads + ly.proj.w_off;
       if (R == 64 && G == 64 && ((uintptr_t)dwp & 15) == 0 && getenv("WN_NO_GATE_FUSE") == nullptr) {
-        WN_TRY(tc_gate_bwd(h, dout, ws + t.tc_wpt + (int64_t)l * G * R, dzs, ws + t.z[l], sg, sg_ld, ws + t.dafg, dwp, zp, W, B, dir, s));
+        WN_TRY(tc_gate_bwd(h, dout, ws + t.tc_wpt + (int64_t)l * G * R, dzs, ws + t.z[l], sg, sg_ld, sg_half, ws + t.dafg, dwp, zp, W, B, dir, s));
       } else {
         WN_TRY(tc_gemm(h, DO, 1, nullptr, &zero, W, ws + t.tc_wpt + (int64_t)l * G * R, G, e, ws + t.dz, G, s));
         WN_TRY(wgrad_any(DO, 0, R, R, Z, 0, W, grads + ly.proj.w_off, nullptr, G, 1));
       }
     } else if (h->tape_gates_zs) {
-      WN_TRY(simt_gate_backward_zs(ws + t.z[l], ws + t.tfsg[l], dzs, ws + t.dafg, P, W, G, zp, s));
+      WN_TRY(simt_gate_backward_zs(ws + t.z[l], ws + t.tfsg[l], 1, dzs, ws + t.dafg, P, W, G, zp, s));
     } else {
       WN_TRY(simt_gate_backward(ws + t.tfsg[l], dzs, ws + t.dafg, P, W, G, zp, s));
     }
