@@ -436,7 +436,7 @@ struct GemmCfg {
 
 // MODE selects the epilogue at compile time (runtime-predicated feature code costs issue slots in the 8 epilogue warps,
 // which are the critical resource of these HBM-bound kernels): 0 = generic (runtime flags), 1 = dz + gate derivative,
-// 2 = Y = acc + Rsd only (the per-layer dx GEMM).
+// 2 = Y = acc + Rsd only (the per-layer dx GEMM), 3 = generic + column sums of the result (bias gradient).
 template <int BN, int MODE>
 __global__ void __launch_bounds__(L_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmTcArgs a) {
@@ -519,17 +519,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     constexpr int CH = BN / 64;   // 32-column chunks per warp
     uint8_t* stg = gbase + Cfg::STG + (warp - 2) * 4096;   // [32 rows][128 B], 16-byte chunks XOR-swizzled by row
     const int cc4 = (lane & 7) * 4;                         // column (within the 32-col block) this lane owns when coalesced
-    float4 csum[CH];                                        // MODE 0 + colsum_out: this lane's columns summed over its rows
-#pragma unroll
-    for (int ch = 0; ch < CH; ++ch) csum[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // MODE 3 (= MODE 0 + colsum_out): this lane's columns summed over its rows, one accumulator per 32-column chunk
+    // (named registers selected by a predicate chain: the chunk loop stays rolled, unrolling it costs I-cache misses)
+    float4 cs0 = make_float4(0.f, 0.f, 0.f, 0.f), cs1 = cs0, cs2 = cs0, cs3 = cs0;
+    static_assert(CH <= 4, "column-sum accumulators cover four chunks per warp");
     for (int j = 0; j < n_local; ++j) {
       const int tile = a.reverse ? a.num_tiles - 1 - ((int)blockIdx.x + j * (int)gridDim.x) : (int)blockIdx.x + j * (int)gridDim.x;
       const int ab = j & 1, aph = (j >> 1) & 1;
-      const int grp = MODE == 0 ? tile % a.ngroups : 0, rt = MODE == 0 ? tile / a.ngroups : tile;
+      const int grp = (MODE == 0 || MODE == 3) ? tile % a.ngroups : 0, rt = (MODE == 0 || MODE == 3) ? tile / a.ngroups : tile;
       const int b = rt / a.tiles_per_seq, t0 = (rt % a.tiles_per_seq) * TM + q * 32;
       mbar_wait(acc_full(ab), aph);
       tcgen05_fence_after();
-#pragma unroll
+#pragma unroll 1
       for (int ch = 0; ch < CH; ++ch) {
         const int ct = (half * CH + ch) * 32;          // column inside the TMEM tile
         const int c0 = grp * BN + ct;                  // output column
@@ -637,7 +638,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             }
             if (a.round_out) o.x = tf32_rna(o.x), o.y = tf32_rna(o.y), o.z = tf32_rna(o.z), o.w = tf32_rna(o.w);
             *reinterpret_cast<float4*>(ybase + orow * a.ldy + ycol) = o;
-            if (a.colsum_out) csum[ch].x += o.x, csum[ch].y += o.y, csum[ch].z += o.z, csum[ch].w += o.w;
+            if constexpr (MODE == 3) {
+              float4& c = ch == 0 ? cs0 : (ch == 1 ? cs1 : (ch == 2 ? cs2 : cs3));
+              c.x += o.x, c.y += o.y, c.z += o.z, c.w += o.w;
+            }
           }
         }
         __syncwarp();
@@ -645,11 +649,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       tcgen05_fence_before();
       mbar_arrive(acc_empty(ab));
     }
-    if (MODE == 0 && a.colsum_out && a.ngroups == 1) {
+    if constexpr (MODE == 3) {
       // lanes l, l+8, l+16, l+24 own the same four columns (different rows): fold them, one atomic set per warp
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch) {
-        float4 v = csum[ch];
+        float4 v = ch == 0 ? cs0 : (ch == 1 ? cs1 : (ch == 2 ? cs2 : cs3));
 #pragma unroll
         for (int o = 8; o < 32; o <<= 1) {
           v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
@@ -1355,6 +1359,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcArgs& 
   const bool rsd_only = g.Rsd && !g.bias && !g.relu && !g.round_out && !g.accumulate && !g.mask && g.y_slab_cols == 0 &&
                         g.zero_rows_below <= 0 && g.N == BN;
   if (rsd_only) return launch_gemm_mode<BN, 2>(ta, tb, g, sm_count, s);
+  if (g.colsum_out && g.ngroups == 1) return launch_gemm_mode<BN, 3>(ta, tb, g, sm_count, s);
   return launch_gemm_mode<BN, 0>(ta, tb, g, sm_count, s);
 }
 
