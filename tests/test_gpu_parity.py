@@ -453,19 +453,23 @@ def test_random_shapes_tf32(seed):
             assert rel_err(g[k_], v) < 6e-2, (k_, rel_err(g[k_], v), bool(net._libh.wn_tc_active(net._h)))
 
 
-def test_tf32_backward_alone_is_tf32_accurate():
+@pytest.mark.parametrize("name,B,W,T", [("C_small", 2, 1000, 1000), ("C", 3, 2171, 977), ("C", 1, 3200, 3200)])
+def test_tf32_backward_alone_is_tf32_accurate(name, B, W, T):
     """Isolates the tensor-core BACKWARD: same TF32 forward tape, tcgen05 backward vs the exact-fp32 SIMT backward.
     (Against the fp64 oracle the TF32 path shows ~3.5e-2 on gradients, but the exact-fp32 backward run on the same
     TF32 tape shows the same 3.5e-2: at random init the gradient is a small difference of large terms, so the
-    7e-4 forward error is amplified ~50x -- conditioning, not backward arithmetic.)"""
+    7e-4 forward error is amplified ~50x -- conditioning, not backward arithmetic.)  The ragged full-depth case
+    (width not a multiple of the 128-row tile, T < W, odd batch) exercises the fused gate-backward + dWp kernel, the
+    grouped dzs / dWs launches, the serpentine tile order and the TMA-store clipping of the fused layer kernel."""
     from wavenet_b200 import _lib
-    cfg = make_cfg("C_small")
+    cfg = make_cfg(name)
     w = O.init_weights(cfg, np.random.default_rng(1234), np.float64)
-    x = np.random.default_rng(0).integers(0, 256, (2, 1000)).astype(np.int32)
-    tgt = np.random.default_rng(1).integers(0, 256, (2, 1000)).astype(np.int32)
+    x = np.random.default_rng(0).integers(0, 256, (B, W)).astype(np.int32)
+    tgt = np.random.default_rng(1).integers(0, 256, (B, T)).astype(np.int32)
     net = make_net(cfg, w)
     net.set_precision("tf32")
-    loss = net.cross_entropy(net.forward_one_step(x, apply_softmax=False), tgt)
+    run_train_step(net, x, tgt, T)
+    assert net._libh.wn_tc_active(net._h) == 1
     net.backward()
     g_tc = net.get_grads()
     _lib.check(net._libh.wn_set_precision(net._h, _lib.WN_PREC_FP32))   # same tape, SIMT backward
@@ -474,3 +478,5 @@ def test_tf32_backward_alone_is_tf32_accurate():
     for k, v in g_simt.items():
         if np.abs(v).max() > 0:
             assert rel_err(g_tc[k], v) < 1e-2, (k, rel_err(g_tc[k], v))
+        else:
+            assert np.abs(g_tc[k]).max() == 0, k
