@@ -274,21 +274,32 @@ def main():
     n_layers = 30
     tc_active = eff_prec == "tf32"
     if tc_active:
-        # dominant kernel of the step: the fused residual-layer kernel (30 launches per forward pass),
-        # timed alone with CUDA events on the launching stream
+        # dominant kernel of the step by time share: the fused gate-backward kernel (dz GEMM + gate derivative + dWp,
+        # 29 launches per step), timed alone with CUDA events on the launching stream; the fused forward layer kernel
+        # (30 launches) is reported next to it
+        def read_traffic(name):
+            tpath = os.path.join(ROOT, "profiles", name)
+            if os.path.isfile(tpath):
+                with open(tpath) as f:
+                    return json.load(f).get("dram_bytes_per_launch")
+            return None
+        scratch = torch.zeros_like(net._grads)
+        def gates_only():
+            for l in range(n_layers - 1):
+                _lib.check(lib.wn_tc_gate_backward_layer(net._h, l, _ptr(scratch), _stream()))
+        gates_only()
+        gate_ms = timed(gates_only, args.steps) / (n_layers - 1)
+        gate_bytes = (3 * 64 * 4 + 64 * 2 + 128 * 4) * B * W    # read dout, dzs, z (fp32) + sigmoid (fp16); write dafg
+        gate_achieved = gate_bytes / (gate_ms / 1e3) / 1e9
         def layers_only():
             for l in range(n_layers):
                 _lib.check(lib.wn_tc_layer_forward(net._h, l, _stream()))
         layers_only()
         lay_ms = timed(layers_only, args.steps) / n_layers
-        bytes_per_pos = 4 * 64 * 4          # read x(t) once, write x_out, z, sigmoid (x(t-d) re-read hits L2)
+        bytes_per_pos = 3 * 64 * 4 + 64 * 2   # read x(t) once, write x_out, z (fp32) and sigmoid (fp16); x(t-d) re-read hits L2
         alg_bytes = bytes_per_pos * B * W
         achieved = alg_bytes / (lay_ms / 1e3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_ncu_tc_layer_kernel.json")
-        if os.path.isfile(tpath):
-            with open(tpath) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+        traffic = read_traffic("r01_ncu_tc_layer_kernel.json")
         # second kernel family: the skip-sum GEMM (K = 64 x 30 layers, N = 256) is the tensor-bound one
         def skip_only():
             _lib.check(lib.wn_tc_skip_gemm(net._h, _stream()))
@@ -297,16 +308,23 @@ def main():
         skip_flops = 2 * 64 * n_layers * 256 * B * W
         skip_tf = skip_flops / (skip_ms / 1e3) / 1e12
         layer_flops = 2 * (128 * 128 + 64 * 64) * B * W
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
-                    "kernel": "tc_layer_kernel (fused residual layer forward), %.1f us per launch" % (1e3 * lay_ms),
-                    "algorithmic_bytes_per_launch": alg_bytes,
+        gate_flops = 2 * (64 * 64 + 64 * 64) * B * W
+        roofline = {"bound": "hbm", "achieved": gate_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": gate_achieved / peaks["hbm_gbs"], "traffic": read_traffic("r01_ncu_tc_gate_bwd_kernel.json"),
+                    "kernel": "tc_gate_bwd_kernel (dz GEMM + gate derivative + dWp, one residual layer), %.1f us per launch"
+                              % (1e3 * gate_ms),
+                    "algorithmic_bytes_per_launch": gate_bytes,
                     "peak_source": "%s HBM copy bandwidth" % peaks["source"],
-                    "tensor": {"achieved_tflops": layer_flops / (lay_ms / 1e3) / 1e12,
+                    "tensor": {"achieved_tflops": gate_flops / (gate_ms / 1e3) / 1e12,
                                "peak_tflops": peaks["bf16_sustained"] / 2.0,
                                "note": "kind::tf32 peak taken as half of the measured bf16 sustained figure; "
-                                       "per-layer GEMMs (K=128/64) are HBM-bound, see DESIGN.md section 5"},
-                    "residual_stack_forward_ms": res_ms}
+                                       "per-layer GEMMs (K=128/64) are HBM-bound, see DESIGN.md section 5"}}
+        roofline_layer = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+                          "kernel": "tc_layer_kernel (fused residual layer forward), %.1f us per launch" % (1e3 * lay_ms),
+                          "algorithmic_bytes_per_launch": alg_bytes,
+                          "tensor_achieved_tflops": layer_flops / (lay_ms / 1e3) / 1e12,
+                          "residual_stack_forward_ms": res_ms}
         roofline_tensor = {"bound": "tensor", "achieved": skip_tf, "peak": peaks["bf16_burst"] / 2.0, "unit": "TFLOP/s",
                            "frac": skip_tf / (peaks["bf16_burst"] / 2.0), "frac_of_nominal_tf32_1100": skip_tf / 1100.0,
                            "kernel": "tc_gemm_kernel<256> skip sum (K=1920, N=256), %.1f us per launch" % (1e3 * skip_ms),
@@ -329,6 +347,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(x_h.nbytes + t_h.nbytes),
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+        "roofline_layer": roofline_layer if tc_active else None,
         "roofline_tensor": roofline_tensor if tc_active else None,
         "train_tflops": 3 * FWD_FLOP_PER_POS * B * W * world / (ms / 1e3) / 1e12,
         "fwd_loss": {"ms": fwd_ms, "samples_per_s": B * W * world / (fwd_ms / 1e3),

@@ -151,6 +151,9 @@ int wn_clip_adam_step(wn_handle* h, float* params, float* grads, float* m, float
  * or of the skip-sum GEMM on the bound tape; need a preceding TF32 wn_forward_residual_block. */
 int wn_tc_layer_forward(wn_handle* h, int layer, wn_stream_t s);
 int wn_tc_skip_gemm(wn_handle* h, wn_stream_t s);
+/* ONE launch of the fused gate-backward kernel of layer l (dz GEMM + gate derivative + dWp) on the buffers a
+ * preceding TF32 wn_backward left on the tape; grads_scratch (flat-size floats) receives the dWp accumulation. */
+int wn_tc_gate_backward_layer(wn_handle* h, int layer, float* grads_scratch, wn_stream_t s);
 
 /* ---- incremental generation (faster_wavenet.py) ----------------------------
  * n_streams independent utterances (the reference hard-codes one, wavenet.py:286).

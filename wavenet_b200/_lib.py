@@ -76,6 +76,7 @@ SIGNATURES = {
     "wn_forward_loss": (_I, [_P, _P, _P, _P, _I, _P, _P, _P]),
     "wn_tc_layer_forward": (_I, [_P, _I, _P]),
     "wn_tc_skip_gemm": (_I, [_P, _P]),
+    "wn_tc_gate_backward_layer": (_I, [_P, _I, _P, _P]),
     "wn_optim_scratch_bytes": (_L, [_P]),
     "wn_clip_adam_step": (_I, [_P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _F, _F, _F, _P, _P, _P]),
     "wn_gen_create": (_I, [_P, _I, _I, C.POINTER(_P)]),

@@ -2034,6 +2034,19 @@ extern "C" int wn_tc_layer_forward(wn_handle* h, int layer, void* stream) {
   WN_REQUIRE(layer >= 0 && layer < (int)h->layers.size(), WN_EINVAL, "bad layer index");
   return tc_layer_launch(h, layer, (cudaStream_t)stream);
 }
+extern "C" int wn_tc_gate_backward_layer(wn_handle* h, int layer, float* grads, void* stream) {
+  WN_REQUIRE(h && h->ws && h->tape_tc && h->tape_gates_zs && grads, WN_ESTATE,
+             "wn_tc_gate_backward_layer: run a TF32 forward + backward of the fused shape first");
+  WN_REQUIRE(layer >= 0 && layer + 1 < (int)h->layers.size() && h->R == 64 && h->layers[layer].G == 64, WN_EINVAL,
+             "bad layer index / shape");
+  const Tape& t = h->tape;
+  const ResLayer& ly = h->layers[layer];
+  float* dwp = grads + ly.proj.w_off;
+  WN_REQUIRE(((uintptr_t)dwp & 15) == 0, WN_EINVAL, "grads_scratch must be 16-byte aligned");
+  return tc_gate_bwd(h, h->ws + t.dout[0], h->ws + t.tc_wpt + (int64_t)layer * 64 * 64, h->ws + t.dzs + (int64_t)layer * t.P * 64,
+                     h->ws + t.z[layer], h->ws + t.tfsg[layer], 64, 1, h->ws + t.dafg, dwp, wn_zero_prefix(t.W, ly.dilation, 2),
+                     t.W, t.B, 0, (cudaStream_t)stream);
+}
 #ifdef WN_LAYER_TRACE
 extern "C" int wn_debug_layer_trace(long long* out) {
   return cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 64 * 32) == cudaSuccess ? 0 : -1;
