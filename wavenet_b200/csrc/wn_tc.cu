@@ -243,6 +243,14 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           tma_load_4d(as + 2 * SUB_A, &tm_x, a_full(s), 0, t0, b, 0);
           tma_load_4d(as + 3 * SUB_A, &tm_x, a_full(s), SUBK, t0, b, 0);
           TR(j, 2);
+          if (j + 2 < n_local) {
+            // the load of tile j+2 cannot be issued before this stage drains: pull its rows into L2 now so that it
+            // costs an L2 hit instead of a DRAM round trip on the stage's critical path
+            const int tp = tile_of(j + 2);
+            const int bp = tp / a.tiles_per_seq, tp0 = (tp % a.tiles_per_seq) * TM;
+            tma_prefetch_4d(&tm_x, 0, tp0, bp, 0);
+            tma_prefetch_4d(&tm_x, SUBK, tp0, bp, 0);
+          }
         }
         if (j >= 1) {
           const int jj = j - 1, s1 = jj & 1, tile = tile_of(jj);
@@ -261,53 +269,25 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc1 = umma_idesc_tf32(128, 128);
-      constexpr uint32_t idesc2 = umma_idesc_tf32(128, 64);
       mbar_wait(b_full, 0);
-      // Two independent in-order streams share this thread: GEMM 1 of tile j1 (needs the TMA load) and GEMM 2 of
-      // tile j2 (needs z from the epilogue warps).  Poll both barriers and issue whichever is ready: waiting for
-      // the next tile's load before GEMM 2 of the current tile would stall the epilogue warps on d2_full.
-      const uint64_t db1 = umma_desc_k_sw128(base + L_B1), db2 = umma_desc_k_sw128(base + L_B2);
-      int j1 = 0, j2 = 0;
-      uint32_t spins = 0;
-      while (j2 < n_local) {
-        bool progressed = false;
-        if (j2 < j1 && mbar_try_wait(z_full(j2 & 1), (j2 >> 1) & 1)) {
-          const int s = j2 & 1;
-          TR(j2, 6);
-          tcgen05_fence_after();
-          const uint64_t da = umma_desc_k_sw128(base + L_A + s * 65536);
+      // GEMM 1 stream only: GEMM 2 of a tile is issued by an epilogue thread the moment z is complete (waiting here
+      // for the next tile's load before GEMM 2 of the current tile would stall the epilogue warps on d2_full).
+      const uint64_t db1 = umma_desc_k_sw128(base + L_B1);
+      for (int j1 = 0; j1 < n_local; ++j1) {
+        const int s = j1 & 1;
+        // GEMM 1 of tile j1 overwrites the accumulator that epilogue 1 of tile j1-2 read: wait for its z_full
+        if (j1 >= 2) mbar_wait(z_full(s), ((j1 - 2) >> 1) & 1);
+        mbar_wait(a_full(s), (j1 >> 1) & 1);
+        TR(j1, 4);
+        tcgen05_fence_after();
+        const uint64_t da = umma_desc_k_sw128(base + L_A + s * 65536);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t offa = (ks >> 2) * SUB_A + (ks & 3) * 32;
-            const uint32_t offb = (ks >> 2) * 8192 + (ks & 3) * 32;
-            umma_tf32(tmem + 256 + s * 64, da + (offa >> 4), db2 + (offb >> 4), idesc2, ks > 0);
-          }
-          umma_commit(d2_full(s));
-          ++j2;
-          progressed = true;
+        for (int ks = 0; ks < 16; ++ks) {
+          const uint32_t off = (ks >> 2) * SUB_A + (ks & 3) * 32;
+          umma_tf32(tmem + s * 128, da + (off >> 4), db1 + (off >> 4), idesc1, ks > 0);
         }
-        // GEMM 1 of tile j1 overwrites the accumulator epilogue 1 of tile j1-2 read: allowed once z_full(j1-2) was seen
-        if (j1 < n_local && j1 <= j2 + 1 && mbar_try_wait(a_full(j1 & 1), (j1 >> 1) & 1)) {
-          const int s = j1 & 1;
-          TR(j1, 4);
-          tcgen05_fence_after();
-          const uint64_t da = umma_desc_k_sw128(base + L_A + s * 65536);
-#pragma unroll
-          for (int ks = 0; ks < 16; ++ks) {
-            const uint32_t off = (ks >> 2) * SUB_A + (ks & 3) * 32;
-            umma_tf32(tmem + s * 128, da + (off >> 4), db1 + (off >> 4), idesc1, ks > 0);
-          }
-          umma_commit(d1_full(s));
-          TR(j1, 5);
-          ++j1;
-          progressed = true;
-        }
-        if (progressed) {
-          spins = 0;
-        } else if (++spins > (1u << 26)) {
-          printf("wavenet_b200: layer kernel MMA warp timeout (block %d, j1 %d, j2 %d)\n", (int)blockIdx.x, j1, j2);
-          __trap();
-        }
+        umma_commit(d1_full(s));
+        TR(j1, 5);
       }
     }
   } else {
@@ -315,6 +295,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     const int half = (warp - 2) >> 2;     // which 32 of the 64 channels this warp handles
     const int row = q * 32 + lane;
     uint8_t* stg = gbase + L_STG + (warp - 2) * 2048;
+    if (threadIdx.x == 64) mbar_wait(b_full, 0);   // W2 resident before this thread issues the first GEMM 2
     for (int j = 0; j < n_local; ++j) {
       const int tile = tile_of(j);
       const int s = j & 1, ph = (j >> 1) & 1;
@@ -367,6 +348,22 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       tcgen05_fence_before();
       mbar_arrive(z_full(s));
       if (threadIdx.x == 64) TR(j, 9);
+      if (threadIdx.x == 64) {
+        // one epilogue thread issues GEMM 2 as soon as every row of z is in shared memory
+        constexpr uint32_t idesc2 = umma_idesc_tf32(128, 64);
+        mbar_wait(z_full(s), ph);
+        tcgen05_fence_after();
+        const uint64_t da = umma_desc_k_sw128(base + L_A + s * 65536), db2 = umma_desc_k_sw128(base + L_B2);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t offa = (ks >> 2) * SUB_A + (ks & 3) * 32;
+          const uint32_t offb = (ks >> 2) * 8192 + (ks & 3) * 32;
+          umma_tf32(tmem + 256 + s * 64, da + (offa >> 4), db2 + (offb >> 4), idesc2, ks > 0);
+        }
+        umma_commit(d2_full(s));
+        TR(j, 6);
+      }
+      __syncwarp();
       // ---- epilogue 2: projection + residual ----
       mbar_wait(d2_full(s), ph);
       if (threadIdx.x == 64) TR(j, 10);
