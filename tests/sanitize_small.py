@@ -21,6 +21,13 @@ for name, B, W in (("tiny_k3_bias", 2, 45), ("C_small", 2, 300)):
     print(name, "gen", out[0, :6].tolist(), flush=True)
 cfg = make_cfg("C")
 w = O.init_weights(cfg, np.random.default_rng(0), np.float32)
+# full-depth config C, ragged width, T < W: fused layer kernel (TMA stores), fused gate-backward, grouped dzs/dWs
+x = torch.from_numpy(np.random.default_rng(1).integers(0, 256, (3, 1301)).astype(np.int32)).cuda()
+net = make_net(cfg, w); net.set_precision("tf32")
+for _ in range(2):
+    loss = net.train_step(x[:, :1300].contiguous(), x[:, 1:].contiguous()[:, -900:].contiguous(), train_width=900)
+torch.cuda.synchronize()
+print("C tf32 train", float(loss[0]), flush=True)
 gnet = make_net(cfg, w, faster=True)
 win = np.random.default_rng(2).integers(0, 256, (2, O.input_width(cfg))).astype(np.int32)
 print("C gen v3", gnet.generate(win, 6, mode="greedy")[0].tolist(), flush=True)
