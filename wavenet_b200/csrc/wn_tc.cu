@@ -1255,6 +1255,243 @@ tc_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
+// Backward of one residual layer's dilated conv for the fused shape (R = G = 64, two taps), one pass over dafg:
+//   dx[t]  = dout[t] + dafg[t] . W1(tap 1) + dafg[t+d] . W1(tap 0)       (K-major GEMM, K = 2 x 128, N = 64)
+//   dW_f/g(o, c, tap) += sum_t dafg[t][o] * x[t - (1-tap) d][c]             (MN-major GEMM over the same rows, M = 128, N = 2 x 64)
+// dafg is read from HBM once (the MN-major copy of the rows the dx GEMM just loaded comes from L2) instead of once per
+// kernel; the weight-gradient accumulator stays in TMEM for the CTA's whole range and is reduced at the end.
+struct DxwArgs {
+  const float* rsd;        // dout of the layer above, [rows][64]
+  float* Y;                // new dout, [rows][64]
+  float* dWf;              // (o, c, tap) with row stride 128: rows [0, 64) of the accumulator
+  float* dWg;              // rows [64, 128)
+  int d;
+  int rows_out, tiles_per_seq, num_tiles;
+  int reverse;
+};
+constexpr int DX_STAGE = SUB_A + 64 * 128;     // dafg [128 x 32] + W1t [64 x 32]
+constexpr int DX_STAGES = 4;
+constexpr int DX_MN = DX_STAGES * DX_STAGE;    // one 64-row MN-major chunk: dafg atoms 0..3 | x(t-d) atoms 0,1 | x(t) atoms 0,1
+constexpr int DX_MN_SUB = 64 * 128;
+constexpr int DX_BAR = DX_MN + 8 * DX_MN_SUB;
+constexpr int DX_STG = DX_BAR + 256;
+constexpr int DX_SMEM = DX_STG + 8 * 4096 + 1024;
+
+__global__ void __launch_bounds__(L_THREADS, 1)
+tc_dxw_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+              const __grid_constant__ CUtensorMap tm_a_mn, const __grid_constant__ CUtensorMap tm_x_mn, const DxwArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + DX_BAR;
+  auto full = [&](int s) { return bar0 + 8 * s; };
+  auto empty = [&](int s) { return bar0 + 32 + 8 * s; };
+  auto acc_full = [&](int s) { return bar0 + 64 + 8 * s; };
+  auto acc_empty = [&](int s) { return bar0 + 80 + 8 * s; };
+  const uint32_t mn_full = bar0 + 96, mn_empty = bar0 + 104, wg_full = bar0 + 112;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + DX_BAR + 192);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < DX_STAGES; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), 256);
+    }
+    mbar_init(mn_full, 1);
+    mbar_init(mn_empty, 1);
+    mbar_init(wg_full, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tm_a);
+    prefetch_tmap(&tm_b);
+    prefetch_tmap(&tm_a_mn);
+    prefetch_tmap(&tm_x_mn);
+  }
+  if (warp == 1) tmem_alloc<256>(smem_u32((const void*)tmem_slot));
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint32_t tmem = *tmem_slot;
+  const int n_local = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_of = [&](int j) {
+    const int i = (int)blockIdx.x + j * (int)gridDim.x;
+    return a.reverse ? a.num_tiles - 1 - i : i;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // two load streams, polled so that neither blocks the other: K-major k-steps (8 per tile through the ring) and the
+      // single-buffered MN-major 64-row chunks (2 per tile).  A chunk is requested only after the K-major loads of its
+      // tile are out (its dafg rows are then on their way into L2), and the x rows of the NEXT chunk are prefetched
+      // into L2 because their load cannot start before the MMA thread releases the buffer.
+      int uk = 0, um = 0;
+      uint32_t spins = 0;
+      auto chunk_coords = [&](int u, int& b, int& tc0) {
+        const int tile = tile_of(u >> 1);
+        b = tile / a.tiles_per_seq;
+        tc0 = (tile % a.tiles_per_seq) * TM + (u & 1) * 64;
+      };
+      while (uk < 8 * n_local || um < 2 * n_local) {
+        bool progressed = false;
+        if (uk < 8 * n_local) {
+          const int s = uk % DX_STAGES, ph = (uk / DX_STAGES) & 1;
+          if (mbar_try_wait(empty(s), ph ^ 1)) {
+            const int tile = tile_of(uk >> 3), sl = (uk >> 2) & 1, ks = uk & 3;
+            const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM;
+            const uint32_t st = base + s * DX_STAGE;
+            mbar_arrive_expect_tx(full(s), DX_STAGE);
+            tma_load_4d(st, &tm_a, full(s), ks * SUBK, t0 + (sl ? a.d : 0), b, 0);
+            tma_load_2d(st + SUB_A, &tm_b, full(s), (sl * 4 + ks) * SUBK, 0);
+            ++uk;
+            progressed = true;
+          }
+        }
+        if (um < 2 * n_local && (um >> 1) * 8 + 4 <= uk && mbar_try_wait(mn_empty, (um & 1) ^ 1)) {
+          int b, tc0;
+          chunk_coords(um, b, tc0);
+          const uint32_t st = base + DX_MN;
+          mbar_arrive_expect_tx(mn_full, 8 * DX_MN_SUB);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tma_load_4d(st + i * DX_MN_SUB, &tm_a_mn, mn_full, i * SUBK, tc0, b, 0);
+          tma_load_4d(st + 4 * DX_MN_SUB, &tm_x_mn, mn_full, 0, tc0 - a.d, b, 0);
+          tma_load_4d(st + 5 * DX_MN_SUB, &tm_x_mn, mn_full, SUBK, tc0 - a.d, b, 0);
+          tma_load_4d(st + 6 * DX_MN_SUB, &tm_x_mn, mn_full, 0, tc0, b, 0);
+          tma_load_4d(st + 7 * DX_MN_SUB, &tm_x_mn, mn_full, SUBK, tc0, b, 0);
+          if (um + 1 < 2 * n_local) {
+            int bn, tn0;
+            chunk_coords(um + 1, bn, tn0);
+            tma_prefetch_4d(&tm_x_mn, 0, tn0, bn, 0);
+            tma_prefetch_4d(&tm_x_mn, SUBK, tn0, bn, 0);
+          }
+          ++um;
+          progressed = true;
+        }
+        if (progressed) {
+          spins = 0;
+        } else if (++spins > (1u << 26)) {
+          printf("wavenet_b200: dxw producer timeout (block %d, uk %d, um %d)\n", (int)blockIdx.x, uk, um);
+          __trap();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(128, 64);
+      constexpr uint32_t idesc_mn = umma_idesc_tf32(128, 128) | (1u << 15) | (1u << 16);
+      // two MMA streams, polled: the dx GEMM (k-step units) and the weight gradient (64-row chunk units)
+      int uk = 0, um = 0;
+      uint32_t spins = 0;
+      while (uk < 8 * n_local || um < 2 * n_local) {
+        bool progressed = false;
+        if (uk < 8 * n_local) {
+          const int j = uk >> 3, kk = uk & 7, ab = j & 1, aph = (j >> 1) & 1;
+          const int s = uk % DX_STAGES, ph = (uk / DX_STAGES) & 1;
+          if ((kk > 0 || mbar_try_wait(acc_empty(ab), aph ^ 1)) && mbar_try_wait(full(s), ph)) {
+            tcgen05_fence_after();
+            const uint32_t st = base + s * DX_STAGE;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              umma_tf32(tmem + ab * 64, umma_desc_k_sw128(st + k4 * 32), umma_desc_k_sw128(st + SUB_A + k4 * 32), idesc,
+                        (kk | k4) > 0);
+            umma_commit(empty(s));
+            if (kk == 7) umma_commit(acc_full(ab));
+            ++uk;
+            progressed = true;
+          }
+        }
+        if (um < 2 * n_local && mbar_try_wait(mn_full, um & 1)) {
+          tcgen05_fence_after();
+#pragma unroll
+          for (int k8 = 0; k8 < 8; ++k8)
+            umma_tf32(tmem + 128, umma_desc_mn_sw128_32b(base + DX_MN + k8 * 1024, DX_MN_SUB, 512),
+                      umma_desc_mn_sw128_32b(base + DX_MN + 4 * DX_MN_SUB + k8 * 1024, DX_MN_SUB, 512), idesc_mn,
+                      (um | k8) > 0);
+          umma_commit(mn_empty);
+          ++um;
+          progressed = true;
+        }
+        if (progressed) {
+          spins = 0;
+        } else if (++spins > (1u << 26)) {
+          printf("wavenet_b200: dxw MMA timeout (block %d, uk %d, um %d)\n", (int)blockIdx.x, uk, um);
+          __trap();
+        }
+      }
+      umma_commit(wg_full);
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    uint8_t* stg = gbase + DX_STG + (warp - 2) * 4096;
+    const int cc4 = (lane & 7) * 4, rsub = lane >> 3;
+    const int c0 = half * 32, col = c0 + cc4;
+    for (int j = 0; j < n_local; ++j) {
+      const int tile = tile_of(j);
+      const int ab = j & 1, aph = (j >> 1) & 1;
+      const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM + q * 32;
+      float4 r4[8];      // residual gradient: independent of the accumulator, so loaded before waiting for it
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int t = min(t0 + jj * 4 + rsub, a.rows_out - 1);
+        r4[jj] = *reinterpret_cast<const float4*>(a.rsd + ((int64_t)b * a.rows_out + t) * 64 + col);
+      }
+      mbar_wait(acc_full(ab), aph);
+      tcgen05_fence_after();
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * 64 + c0, v);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      mbar_arrive(acc_empty(ab));
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+            make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int rr = jj * 4 + rsub;
+        const int t = t0 + rr;
+        if (t >= a.rows_out) continue;
+        float4 o = *reinterpret_cast<const float4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+        o.x += r4[jj].x, o.y += r4[jj].y, o.z += r4[jj].z, o.w += r4[jj].w;
+        *reinterpret_cast<float4*>(a.Y + ((int64_t)b * a.rows_out + t) * 64 + col) = o;
+      }
+      __syncwarp();
+    }
+    if (n_local > 0) {
+      // dW_f | dW_g: TMEM lanes = gate channel, columns = tap*64 + c.  Both taps of 32 input channels are interleaved in
+      // shared memory (the gradient layout is (o, c, tap)) and reduced with 16-byte vector REDs over whole 256-byte rows.
+      mbar_wait(wg_full, 0);
+      tcgen05_fence_after();
+      uint8_t* stg2 = gbase + (warp - 2) * 8192;          // every MMA has retired: the K-major ring is free
+      uint32_t v0[32], v1[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 128 + c0, v0);
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 128 + 64 + c0, v1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        *reinterpret_cast<uint4*>(stg2 + lane * 256 + ((k ^ (lane & 7)) << 4)) =
+            make_uint4(v0[2 * k], v1[2 * k], v0[2 * k + 1], v1[2 * k + 1]);
+      __syncwarp();
+#pragma unroll 4
+      for (int jj = 0; jj < 16; ++jj) {
+        const int rr = jj * 2 + (lane >> 4), kk = lane & 15;
+        const int m = q * 32 + rr;
+        const float4 o = *reinterpret_cast<const float4*>(stg2 + rr * 256 + ((kk ^ (rr & 7)) << 4));
+        float* rowp = m < 64 ? a.dWf + (int64_t)m * 128 : a.dWg + (int64_t)(m - 64) * 128;
+        red_add_v4(rowp + c0 * 2 + kk * 4, o);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1584,6 +1821,37 @@ int tc_gate_bwd(const wn_handle* h, const float* dout, const float* wpt, const f
   }
   const int grid = g.num_tiles < h->sm_count ? g.num_tiles : h->sm_count;
   WN_CHECK_CUDA(launch_pdl(tc_gate_bwd_kernel, grid, L_THREADS, GB_SMEM, s, ta, tb, tam, tzm, g));
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+// dx GEMM + dW_f/dW_g in one pass over dafg (fused shape R = G = 64, two taps); gradient pointers 16-byte aligned
+int tc_dxw(const wn_handle* h, const float* dafg, const float* w1t, const float* rsd, const float* x, float* Y, float* dWf,
+           float* dWg, int d, int rows, int num_seq, int reverse, cudaStream_t s) {
+  CUtensorMap ta, tb, tam, txm;
+  const uint64_t seqa = (uint64_t)rows * 128, alla = seqa * num_seq, seqx = (uint64_t)rows * 64, allx = seqx * num_seq;
+  WN_TRY(make_map_4d(&ta, dafg, 128, rows, num_seq, 1, 128, seqa, alla, TM));
+  WN_TRY(make_map_2d(&tb, w1t, 256, 64, 256, 64));
+  WN_TRY(make_map_4d(&tam, dafg, 128, rows, num_seq, 1, 128, seqa, alla, 64, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  WN_TRY(make_map_4d(&txm, x, 64, rows, num_seq, 1, 64, seqx, allx, 64, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  DxwArgs g;
+  memset(&g, 0, sizeof(g));
+  g.rsd = rsd;
+  g.Y = Y;
+  g.dWf = dWf;
+  g.dWg = dWg;
+  g.d = d;
+  g.reverse = reverse;
+  g.rows_out = rows;
+  g.tiles_per_seq = (rows + TM - 1) / TM;
+  g.num_tiles = g.tiles_per_seq * num_seq;
+  static bool attr = false;
+  if (!attr) {
+    WN_CHECK_CUDA(cudaFuncSetAttribute(tc_dxw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DX_SMEM));
+    attr = true;
+  }
+  const int grid = g.num_tiles < h->sm_count ? g.num_tiles : h->sm_count;
+  WN_CHECK_CUDA(launch_pdl(tc_dxw_kernel, grid, L_THREADS, DX_SMEM, s, ta, tb, tam, txm, g));
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
@@ -1946,7 +2214,12 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
     const int zp = wn_zero_prefix(W, ly.dilation, 2);
     // serpentine hand-off: consecutive kernels walk the rows in opposite directions, so each one starts on the part
     // of its input the previous kernel touched last (still in L2): gate D -> dW1 !D -> dx D -> next layer's gate !D
-    const int dir = serp ? (l & 1) : 0, ndir = serp ? !(l & 1) : 0;
+    // (with the fused dx + dW1 kernel there are two kernels per layer: gate forwards, dxw backwards)
+    float* dwf = grads + ly.wf.w_off;
+    float* dwg = grads + ly.wg.w_off;
+    const bool fuse_dxw = dout != nullptr && R == 64 && G == 64 && h->cfg.residual_filter_width == 2 &&
+                          (((uintptr_t)dwf | (uintptr_t)dwg) & 15) == 0 && getenv("WN_NO_DXW_FUSE") == nullptr;
+    const int dir = serp ? (fuse_dxw ? 0 : (l & 1)) : 0, ndir = serp ? !dir : 0;
     const float* dzs = ws + t.dzs + (int64_t)l * P * G;
     const float* sg = h->tape_gates_zs ? ws + t.tfsg[l] : ws + t.tfsg[l] + G;
     const int sg_ld = h->tape_gates_zs ? G : 2 * G;
@@ -1978,6 +2251,14 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
       WN_TRY(simt_gate_backward(ws + t.tfsg[l], dzs, ws + t.dafg, P, W, G, zp, s));
     }
     TcOperand DA{ws + t.dafg, 2 * G, W, B, 1, 0};
+    if (fuse_dxw) {
+      float* dnew = ws + t.dout[dt];
+      WN_TRY(tc_dxw(h, ws + t.dafg, ws + t.tc_w1t + (int64_t)l * R * 4 * G, dout, ws + t.x[l], dnew, dwf, dwg, ly.dilation, W,
+                    B, ndir, s));
+      dout = dnew;
+      dt ^= 1;
+      continue;
+    }
     {
       // dW_{f,g}(o, c, tap) += da[t][o] * x[t - (1-tap) d][c]; taps share a launch while 2R fits one N tile
       TcOperand X{ws + t.x[l], R, W, B, 1, 0};
