@@ -428,7 +428,7 @@ struct GemmCfg {
   static constexpr int STAGES = (200 * 1024) / STAGE > 6 ? 6 : (200 * 1024) / STAGE;
   static constexpr int BAR = STAGES * STAGE;
   static constexpr int STG = BAR + 256;            // 8 epilogue warps x 4 KB transpose buffers
-  static constexpr int SMEM = STG + 8 * 4096 + 1024;
+  static constexpr int SMEM = STG + 8 * 4096 + 1024 + 1024;   // + BN floats of column sums (MODE 3)
 };
 
 // MODE selects the epilogue at compile time (runtime-predicated feature code costs issue slots in the 8 epilogue warps,
@@ -462,6 +462,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     prefetch_tmap(&tm_b);
   }
   if (warp == 1) tmem_alloc<512>(smem_u32((const void*)tmem_slot));
+  if constexpr (MODE == 3) {
+    if (threadIdx.x < BN) reinterpret_cast<float*>(gbase + Cfg::STG + 8 * 4096)[threadIdx.x] = 0.f;
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -516,10 +519,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     constexpr int CH = BN / 64;   // 32-column chunks per warp
     uint8_t* stg = gbase + Cfg::STG + (warp - 2) * 4096;   // [32 rows][128 B], 16-byte chunks XOR-swizzled by row
     const int cc4 = (lane & 7) * 4;                         // column (within the 32-col block) this lane owns when coalesced
-    // MODE 3 (= MODE 0 + colsum_out): this lane's columns summed over its rows, one accumulator per 32-column chunk
-    // (named registers selected by a predicate chain: the chunk loop stays rolled, unrolling it costs I-cache misses)
-    float4 cs0 = make_float4(0.f, 0.f, 0.f, 0.f), cs1 = cs0, cs2 = cs0, cs3 = cs0;
-    static_assert(CH <= 4, "column-sum accumulators cover four chunks per warp");
+    // MODE 3 (= MODE 0 + colsum_out): column sums of the stored result accumulate in a BN-float shared-memory array
+    // (per-warp partial sums folded with shuffles, shared-memory atomics), flushed to global memory once per CTA
+    float* cs_smem = reinterpret_cast<float*>(gbase + Cfg::STG + 8 * 4096);
     for (int j = 0; j < n_local; ++j) {
       const int tile = a.reverse ? a.num_tiles - 1 - ((int)blockIdx.x + j * (int)gridDim.x) : (int)blockIdx.x + j * (int)gridDim.x;
       const int ab = j & 1, aph = (j >> 1) & 1;
@@ -602,6 +604,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             ycol = col % a.y_slab_cols;
           }
           float4 r4[8], x4[8];   // x4: ReLU mask source or previous Y (never both)
+          float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
           const bool has_aux = a.mask != nullptr || a.accumulate;
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
@@ -635,9 +638,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             }
             if (a.round_out) o.x = tf32_rna(o.x), o.y = tf32_rna(o.y), o.z = tf32_rna(o.z), o.w = tf32_rna(o.w);
             *reinterpret_cast<float4*>(ybase + orow * a.ldy + ycol) = o;
-            if constexpr (MODE == 3) {
-              float4& c = ch == 0 ? cs0 : (ch == 1 ? cs1 : (ch == 2 ? cs2 : cs3));
-              c.x += o.x, c.y += o.y, c.z += o.z, c.w += o.w;
+            if constexpr (MODE == 3) csum.x += o.x, csum.y += o.y, csum.z += o.z, csum.w += o.w;
+          }
+          if constexpr (MODE == 3) {
+            // lanes l, l+8, l+16, l+24 own the same four columns (different rows)
+#pragma unroll
+            for (int o = 8; o < 32; o <<= 1) {
+              csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o);
+              csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
+              csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o);
+              csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
+            }
+            if (lane < 8) {
+              float* c = cs_smem + ct + cc4;
+              atomicAdd(c, csum.x), atomicAdd(c + 1, csum.y), atomicAdd(c + 2, csum.z), atomicAdd(c + 3, csum.w);
             }
           }
         }
@@ -647,23 +661,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       mbar_arrive(acc_empty(ab));
     }
     if constexpr (MODE == 3) {
-      // lanes l, l+8, l+16, l+24 own the same four columns (different rows): fold them, one atomic set per warp
-#pragma unroll
-      for (int ch = 0; ch < CH; ++ch) {
-        float4 v = ch == 0 ? cs0 : (ch == 1 ? cs1 : (ch == 2 ? cs2 : cs3));
-#pragma unroll
-        for (int o = 8; o < 32; o <<= 1) {
-          v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
-          v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
-          v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
-          v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
-        }
-        const int c0 = (half * CH + ch) * 32;
-        if (lane < 8 && c0 < a.N) {
-          float* o = a.colsum_out + c0 + cc4;
-          atomicAdd(o, v.x), atomicAdd(o + 1, v.y), atomicAdd(o + 2, v.z), atomicAdd(o + 3, v.w);
-        }
-      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps
+      const int c = threadIdx.x - 64;
+      if (c < BN && c < a.N) atomicAdd(a.colsum_out + c, cs_smem[c]);
     }
   }
   tcgen05_fence_before();
