@@ -489,6 +489,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             mbar_arrive_expect_tx(full(s), Cfg::STAGE);
             tma_load_4d(st, &tm_a, full(s), ks * SUBK, a.slab_row_off[sl] + t0, b, a.slab_idx[sl]);
             tma_load_2d(st + SUB_A, &tm_b, full(s), (sl * a.ksub + ks) * SUBK, grp * BN);
+            if (BN == 256) TR(it, 0);
           }
       }
     }
@@ -503,6 +504,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (int kk = 0; kk < ksteps; ++kk, ++it) {
           const int s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
           mbar_wait(full(s), ph);
+          if (BN == 256) TR(it, 1);
           tcgen05_fence_after();
           const uint32_t st = base + s * Cfg::STAGE;
 #pragma unroll
@@ -512,6 +514,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           umma_commit(empty(s));
         }
         umma_commit(acc_full(ab));
+        if (BN == 256) TR(j, 2);
       }
     }
   } else {
@@ -528,6 +531,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int grp = (MODE == 0 || MODE == 3) ? tile % a.ngroups : 0, rt = (MODE == 0 || MODE == 3) ? tile / a.ngroups : tile;
       const int b = rt / a.tiles_per_seq, t0 = (rt % a.tiles_per_seq) * TM + q * 32;
       mbar_wait(acc_full(ab), aph);
+      if (BN == 256 && threadIdx.x == 64) TR(j, 3);
       tcgen05_fence_after();
 #pragma unroll 1
       for (int ch = 0; ch < CH; ++ch) {
@@ -659,6 +663,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       }
       tcgen05_fence_before();
       mbar_arrive(acc_empty(ab));
+      if (BN == 256 && threadIdx.x == 64) TR(j, 4);
     }
     if constexpr (MODE == 3) {
       asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps
