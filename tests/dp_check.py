@@ -18,6 +18,18 @@ B, W = 4, 700
 rng = np.random.default_rng(5)
 xs = rng.integers(0, 256, (3, B * world, W + 1)).astype(np.int32)
 for prec in ("fp32", "tf32"):
+    # (0) first step from identical parameters: all-reduced mean gradient == global-batch gradient up to rounding
+    n1 = make_net(cfg, w); n1.set_precision(prec); n1.data_parallel = True; n1.update_laerning_rate(1e-3)
+    x = torch.from_numpy(xs[0, rank * B:(rank + 1) * B]).cuda()
+    n1.train_step(x[:, :W].contiguous(), x[:, 1:].contiguous())
+    r1 = make_net(cfg, w); r1.set_precision(prec); r1.update_laerning_rate(1e-3)
+    x = torch.from_numpy(xs[0]).cuda()
+    r1.train_step(x[:, :W].contiguous(), x[:, 1:].contiguous())
+    g0 = (n1._grads - r1._grads).abs().max().item() / r1._grads.abs().max().item()
+    if rank == 0:
+        print("%s: first-step gradient, dp mean vs global batch: rel max diff %.3e" % (prec, g0), flush=True)
+    assert g0 < (1e-5 if prec == "fp32" else 2e-2), g0
+    del n1, r1
     net = make_net(cfg, w); net.set_precision(prec); net.data_parallel = True; net.update_laerning_rate(1e-3)
     for s in range(3):
         x = torch.from_numpy(xs[s, rank * B:(rank + 1) * B]).cuda()
@@ -28,11 +40,17 @@ for prec in ("fp32", "tf32"):
         x = torch.from_numpy(xs[s]).cuda()
         ref.train_step(x[:, :W].contiguous(), x[:, 1:].contiguous())
     diff = (net._params - ref._params).abs().max().item()
+    # the gradient buffer of the LAST step (all-reduced sum, scaled by 1/world and by the clip factor inside
+    # wn_clip_adam_step) must equal the global-batch one (parameters differ slightly by then: loose bound)
+    gd = (net._grads - ref._grads).abs().max().item() / max(ref._grads.abs().max().item(), 1e-30)
     if rank == 0:
-        print("%s: replicas identical=%s  max|dp - single|=%.3e" % (prec, ok, diff), flush=True)
-    # TF32: atomics + different batch split change rounding; Adam(lr=1e-3) turns tiny gradient differences into +-lr moves
-    # fp32: all-reduce summation order differs from the single-process atomics order (6e-5 seen at 8 ranks)
-    assert ok and diff < (2e-4 if prec == "fp32" else 5e-3), (ok, diff)
+        print("%s: replicas identical=%s  max|dp - single| params=%.3e  last-step gradient rel=%.3e" % (prec, ok, diff, gd),
+              flush=True)
+    # Parameters after 3 Adam steps: Adam divides by sqrt(v), so an element whose gradient is a small difference of
+    # large terms (relative rounding noise of 10 % between two summation orders: atomics, all-reduce, batch split) moves
+    # by a different fraction of lr = 1e-3 in each run.  Seen: fp32 1e-4 .. 3.4e-4 at 2 ranks, TF32 2e-3.
+    assert ok and diff < (1e-3 if prec == "fp32" else 5e-3), (ok, diff)
+    assert gd < (5e-3 if prec == "fp32" else 5e-2), gd
 dist.destroy_process_group()
 if rank == 0:
     print("DP CHECK OK")
