@@ -1266,7 +1266,7 @@ tc_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 // dafg is read from HBM once (the MN-major copy of the rows the dx GEMM just loaded comes from L2) instead of once per
 // kernel; the weight-gradient accumulator stays in TMEM for the CTA's whole range and is reduced at the end.
 struct DxwArgs {
-  const float* rsd;        // dout of the layer above, [rows][64]
+  const float* rsd;        // dout of the layer above, [rows][64]; null for the top layer
   float* Y;                // new dout, [rows][64]
   float* dWf;              // (o, c, tap) with row stride 128: rows [0, 64) of the accumulator
   float* dWg;              // rows [64, 128)
@@ -1441,7 +1441,8 @@ tc_dxw_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
         const int t = min(t0 + jj * 4 + rsub, a.rows_out - 1);
-        r4[jj] = *reinterpret_cast<const float4*>(a.rsd + ((int64_t)b * a.rows_out + t) * 64 + col);
+        r4[jj] = a.rsd ? *reinterpret_cast<const float4*>(a.rsd + ((int64_t)b * a.rows_out + t) * 64 + col)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);   // top layer: nothing flows in from above
       }
       mbar_wait(acc_full(ab), aph);
       tcgen05_fence_after();
@@ -2222,7 +2223,7 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
     // (with the fused dx + dW1 kernel there are two kernels per layer: gate forwards, dxw backwards)
     float* dwf = grads + ly.wf.w_off;
     float* dwg = grads + ly.wg.w_off;
-    const bool fuse_dxw = dout != nullptr && R == 64 && G == 64 && h->cfg.residual_filter_width == 2 &&
+    const bool fuse_dxw = R == 64 && G == 64 && h->cfg.residual_filter_width == 2 &&
                           (((uintptr_t)dwf | (uintptr_t)dwg) & 15) == 0 && getenv("WN_NO_DXW_FUSE") == nullptr;
     const int dir = serp ? (fuse_dxw ? 0 : (l & 1)) : 0, ndir = serp ? !dir : 0;
     const float* dzs = ws + t.dzs + (int64_t)l * P * G;
