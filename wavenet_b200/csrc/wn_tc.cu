@@ -1140,8 +1140,10 @@ tc_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           tma_load_4d(st, &tm_a, full(s), ks * SUBK, t0, b, 0);
           tma_load_2d(st + SUB_A, &tm_b, full(s), ks * SUBK, 0);
         }
+        TR(j, 0);
         // MN-major copies of the same rows for the weight gradient (single buffer: freed by the MMA warp)
         mbar_wait(mn_empty, (j & 1) ^ 1);
+        TR(j, 1);
         mbar_arrive_expect_tx(mn_full, 4 * SUB_A);
         tma_load_4d(base + GB_MN + 0 * SUB_A, &tm_a_mn, mn_full, 0, t0, b, 0);
         tma_load_4d(base + GB_MN + 1 * SUB_A, &tm_a_mn, mn_full, SUBK, t0, b, 0);
@@ -1157,6 +1159,7 @@ tc_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       for (int j = 0; j < n_local; ++j) {
         const int ab = j & 1, aph = (j >> 1) & 1;
         mbar_wait(acc_empty(ab), aph ^ 1);
+        TR(j, 2);
         tcgen05_fence_after();
         for (int kk = 0; kk < 2; ++kk, ++it) {
           const int s = it % GB_STAGES, ph = (it / GB_STAGES) & 1;
@@ -1170,13 +1173,16 @@ tc_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           umma_commit(empty(s));
         }
         umma_commit(acc_full(ab));
+        TR(j, 3);
         mbar_wait(mn_full, j & 1);
+        TR(j, 4);
         tcgen05_fence_after();
 #pragma unroll
         for (int k8 = 0; k8 < TM / 8; ++k8)
           umma_tf32(tmem + 128, umma_desc_mn_sw128_32b(base + GB_MN + k8 * 1024, SUB_A, 512),
                     umma_desc_mn_sw128_32b(base + GB_MN + 4 * SUB_A + k8 * 1024, SUB_A, 512), idesc_mn, (j | k8) > 0);
         umma_commit(mn_empty);
+        TR(j, 5);
       }
       umma_commit(wg_full);
     }
@@ -1199,7 +1205,9 @@ tc_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         z4[jj] = *reinterpret_cast<const float4*>(a.z + orow * 64 + col);
         sg4[jj] = load_sg4(a.sg, orow * a.sg_ld + col, a.sg_half);
       }
+      if (threadIdx.x == 64) TR(j, 8);
       mbar_wait(acc_full(ab), aph);
+      if (threadIdx.x == 64) TR(j, 9);
       tcgen05_fence_after();
       uint32_t v[32];
       tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * 64 + c0, v);
@@ -1233,6 +1241,7 @@ tc_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         *reinterpret_cast<float4*>(drow + 64 + col) = dg;
       }
       __syncwarp();
+      if (threadIdx.x == 64) TR(j, 10);
     }
     if (n_local > 0 && q < 2) {
       // dWp rows (projection output channels) live in TMEM lanes 0..63
