@@ -4,7 +4,7 @@
  (2) they match a single-process run on the concatenated global batch (gradient mean == global-batch gradient)."""
 import os, sys
 import numpy as np, torch, torch.distributed as dist
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import wavenet_oracle as O
 from tests.util import make_cfg, make_net
 from wavenet_b200.dist import assert_replicas_equal

@@ -1,6 +1,6 @@
 """Small end-to-end exercise for compute-sanitizer (manual): fp32 + tf32 train step, generator v1/v2/v3."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from oracle import wavenet_oracle as O
 from tests.util import make_cfg, make_net

@@ -2,7 +2,7 @@
 SIMT backward), and gradient error vs the oracle when the targets are learnable (structured) instead of random."""
 import sys, os
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import wavenet_oracle as O
 from tests.util import make_cfg, make_net, rel_err
 from wavenet_b200 import _lib

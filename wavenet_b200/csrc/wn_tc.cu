@@ -160,7 +160,7 @@ constexpr int L_STG = L_BAR + 256;            // 8 epilogue warps x 2 KB store-t
 constexpr int L_SMEM = L_STG + 8 * 2048;
 constexpr int L_THREADS = 64 + 256;           // producer warp, MMA warp, 8 epilogue warps
 
-// Developer trace (make EXTRA=-DWN_LAYER_TRACE, tests/trace_layer.py): clock64 stamps of CTA 0's pipeline events.
+// Developer trace (make EXTRA=-DWN_LAYER_TRACE, tests/dev/trace_layer.py): clock64 stamps of CTA 0's pipeline events.
 #ifdef WN_LAYER_TRACE
 __device__ long long g_trace[64 * 32];
 #define TR(j, e) do { if (blockIdx.x == 0 && (j) < 64) g_trace[(j) * 32 + (e)] = clock64(); } while (0)
