@@ -15,6 +15,7 @@
 #include "wn_tc.cuh"
 
 static const int GT_HOST = 512;   // consumer threads per CTA (must equal GT below)
+static const int V4_CS_HOST = 8;  // CTAs per cluster of the v4 generator (must equal V4_CS below)
 
 struct GenLayerOff {
   int64_t wa, ba, wb, bb, ring;  // offsets (floats) into the state buffer
@@ -36,6 +37,8 @@ struct GenLayout {
   int64_t chunks_dev = 0;   // GenChunk[] streaming schedule
   int64_t chunks3_dev = 0;  // GenChunk[] schedule of the packed (v3) weights
   int64_t wpk = 0;          // packed weights (v3)
+  int64_t wpk4 = 0;         // per-cluster-rank packed weight slices (v4)
+  int64_t wpk4_rank = 0;    // floats per rank
   int64_t total = 0;
   int maxw = 0;             // widest vector anywhere (for smem sizing)
 };
@@ -62,6 +65,7 @@ struct wn_gen {
   std::vector<GenChunk> chunks3;      // schedule over the packed weights
   struct Pack3 { int64_t src, dst; int K, N, chunkK, mode; };
   std::vector<Pack3> packs3;
+  bool v4_ok = false;                 // config-C shape and few enough streams: one 8-CTA cluster per stream
 };
 
 namespace {
@@ -74,6 +78,7 @@ constexpr int MAX_CHUNKS = 512;     // schedule entries kept in shared memory
 
 // barrier among the GT consumer threads only (the producer warp never joins)
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void csync4() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // v4: 256 consumer threads
 
 // consumer-side view of the weight ring
 struct StreamCtx {
@@ -1026,6 +1031,377 @@ int launch_gen_v3(const GenArgs& a, cudaStream_t s) {
   return WN_OK;
 }
 
+// =============================================================================================
+// Generator v4: ONE STREAM PER 8-CTA CLUSTER (latency path: batch 1 .. sm_count/8 streams).
+// At batch 1 the v3 kernel is bound by what one SM can pull from L2 (5 MB of weights per audio sample).  Here the
+// eight CTAs of a cluster split every matvec by OUTPUT rows -- each streams only its 1/8 slice of the packed weights
+// (604 KB per sample) -- and exchange the 64-float activations through distributed shared memory: a thread that
+// finishes an output sends it to all eight CTAs with st.async (a remote store that completes 4 bytes on the destination's
+// mbarrier); consumers wait for the byte count.  Two exchanges per layer (z, x) + one per head conv.
+// Sampling and the embedding of the next sample are computed redundantly by every CTA (same logits, same counter RNG),
+// so no broadcast of the sample is needed.
+constexpr int V4_CS = 8;                  // CTAs per cluster
+constexpr int V4_T = 256;                 // consumer threads per CTA (+ one producer warp)
+constexpr int V4_STAGE_BYTES = 32768;     // one chunk per stage: a layer's WA|WB slice (18 KB) or a head slice (32 KB)
+constexpr int V4_STAGES = 4;
+constexpr int V4_WA_F = 2 * 256 * 4;      // floats of a packed WA slice: [q 2][thread 256] float4
+constexpr int V4_WB_F = 4 * 160 * 4;      // WB slice: [q 4][thread 160] float4
+constexpr int V4_WH_F = 8 * 256 * 4;      // head slice: [q 8][thread 256] float4
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+// remote store whose completion is signalled on the DESTINATION CTA's mbarrier (complete_tx of 4 bytes): no separate
+// arrive and no release round trip per peer -- eight fire-and-forget messages per value
+__device__ __forceinline__ void st_async_f32(uint32_t addr, float v, uint32_t bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr),
+               "r"(__float_as_uint(v)), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// value v of this CTA's output `idx` into buffer `buf` (shared-memory address, same offset in every CTA) of all CTAs;
+// each destination's barrier counts the bytes
+__device__ __forceinline__ void bcast_value(uint32_t buf, int idx, float v, uint32_t bar) {
+#pragma unroll
+  for (uint32_t r = 0; r < V4_CS; ++r) st_async_f32(map_to_cta(buf + 4u * (uint32_t)idx, r), v, map_to_cta(bar, r));
+}
+// one thread per CTA opens the phase (expects `bytes` from the cluster), everybody waits for it
+__device__ __forceinline__ void exchange_wait(uint32_t bar, uint32_t parity, uint32_t bytes, int tid) {
+  if (tid == 0) tc::mbar_arrive_expect_tx(bar, bytes);
+  tc::mbar_wait(bar, parity);
+}
+
+__global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_kernel_v4(GenArgs a) {
+  extern __shared__ float sm[];
+  const GenLayout& L = a.lay;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rank = (int)cluster_rank();
+  const int stream = blockIdx.x / V4_CS;
+  constexpr int R = 64, G = 64, Q = 256;
+  float* xv = sm;                       // [64]   layer input (all channels, filled by the exchange)
+  float* zv = xv + 64;                  // [2][64]  double-buffered by layer parity (skip-only threads read z without
+                                        //          sending anything afterwards, so the next z must not land on top of it)
+  float* hA = zv + 128;                 // [256]
+  float* hB = hA + 256;                 // [256]
+  float* xpast = hB + 256;              // [L][64]
+  float* hbias = xpast + L.L * 64;      // [n_head][256]
+  uint8_t* ring_g = reinterpret_cast<uint8_t*>(hbias + L.n_head * 256);
+  ring_g += (128 - (tc::smem_u32(ring_g) & 127)) & 127;
+  __shared__ __align__(8) uint64_t s_bars[2 * V4_STAGES + 4];
+  __shared__ GenLayerOff s_layers[128];
+  __shared__ float s_redv[V4_T / 32];
+  __shared__ int s_redi[V4_T / 32];
+  __shared__ int s_sample;
+  const uint32_t full0 = tc::smem_u32(&s_bars[0]), empty0 = tc::smem_u32(&s_bars[V4_STAGES]);
+  // exchange barriers.  Consecutive exchanges never use the same barrier (z, x alternate per layer, the head alternates
+  // hbar0/hbar1): a peer that is one exchange ahead then completes its bytes on a barrier whose previous phase is over
+  // in every CTA, so byte counts of different phases cannot mix.
+  const uint32_t zbar = tc::smem_u32(&s_bars[2 * V4_STAGES]), xbar = zbar + 8, hbar0 = zbar + 16, hbar1 = zbar + 24;
+  const uint32_t xv_s = tc::smem_u32(xv), zv_s = tc::smem_u32(zv), hA_s = tc::smem_u32(hA), hB_s = tc::smem_u32(hB);
+  float* st = a.state;
+  if (tid == 0) {
+    for (int i = 0; i < V4_STAGES; ++i) {
+      tc::mbar_init(full0 + 8 * i, 1);
+      tc::mbar_init(empty0 + 8 * i, V4_T / 32);
+    }
+    tc::mbar_init(zbar, 1);             // phases are opened by tid 0 with the expected byte count
+    tc::mbar_init(xbar, 1);
+    tc::mbar_init(hbar0, 1);
+    tc::mbar_init(hbar1, 1);
+    tc::fence_barrier_init();
+  }
+  for (int i = tid; i < L.L; i += blockDim.x) s_layers[i] = a.layers[i];
+  for (int i = tid; i < L.n_head * 256; i += blockDim.x) hbias[i] = L.has_hb ? st[L.hb[i / 256] + (i % 256)] : 0.f;
+  float* cur_logits = st + L.cur_logits;
+  for (int i = tid; i < Q; i += blockDim.x) hA[i] = cur_logits[(int64_t)stream * Q + i];
+  __syncthreads();
+  cluster_sync_all();                   // every CTA's barriers exist before anybody arrives on them
+  const int n_chunks = L.L + L.n_head;
+  if (tid >= V4_T) {
+    if (tid == V4_T) {                  // producer: this rank's slices of every step, in consumption order
+      const uint8_t* wbase = reinterpret_cast<const uint8_t*>(st + L.wpk4 + (int64_t)rank * L.wpk4_rank);
+      const uint32_t ring_s = tc::smem_u32(ring_g);
+      uint32_t it = 0;
+      for (int step = 0; step < a.n_steps; ++step) {
+        uint64_t off = 0;
+        for (int c = 0; c < n_chunks; ++c, ++it) {
+          const uint32_t bytes = (c < L.L ? (V4_WA_F + V4_WB_F) : V4_WH_F) * 4;
+          const uint32_t stage = it % V4_STAGES;
+          tc::mbar_wait(empty0 + 8 * stage, ((it / V4_STAGES) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(full0 + 8 * stage, bytes);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           ring_s + stage * V4_STAGE_BYTES),
+                       "l"(reinterpret_cast<uint64_t>(wbase + off)), "r"(bytes), "r"(full0 + 8 * stage)
+                       : "memory");
+          off += bytes;
+        }
+      }
+    }
+    __syncwarp();
+    cluster_sync_all();                 // matches the consumers' final cluster barrier
+    return;
+  }
+  int32_t* idx_hist = (int32_t*)(st + L.idx_hist);
+  const int kc1 = L.kc - 1;             // 0 or 1 previous samples feed the causal (embedding) layer
+  int prev_q = kc1 > 0 ? idx_hist[(int64_t)stream * kc1 + kc1 - 1] : -1;
+  float* lg = hA;
+  uint32_t it = 0, zph = 0, xph = 0, hph[2] = {0, 0}, zsel = 0;
+  // phase A roles: warp w -> gate channel 8*rank + w; lanes 0..15 a_f, 16..31 a_g; K slice = lane & 15 (8 rows)
+  // phase B roles: thread t < 160 -> output t >> 2 (0..7 residual channel 8*rank+o, 8..39 skip channel 32*rank+o-8), K slice t & 3
+  // head roles   : output tid >> 3 (32*rank + o), K slice tid & 7 (32 rows)
+  const int ksA = lane & 15;
+  const int oB = tid >> 2, ksB = tid & 3;
+  const int oH = tid >> 3, ksH = tid & 7;
+
+  for (int step = 0; step < a.n_steps; ++step) {
+    const int64_t t = a.t0 + step;
+    // ---- 1. sample (every CTA computes the same value) ----
+    if (!a.sample_first) {
+      if (tid == 0) s_sample = a.forced[stream];
+    } else {
+      float bv = lg[tid];
+      int bi = tid;
+      if (a.mode == WN_GEN_SAMPLE) bv += gumbel(a.seed, (uint64_t)stream, (uint64_t)t, (uint32_t)tid);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) {
+          bv = ov;
+          bi = oi;
+        }
+      }
+      if (lane == 0) {
+        s_redv[warp] = bv;
+        s_redi[warp] = bi;
+      }
+      csync4();
+      if (tid == 0) {
+        for (int w = 1; w < V4_T / 32; ++w)
+          if (s_redv[w] > bv || (s_redv[w] == bv && s_redi[w] < bi)) {
+            bv = s_redv[w];
+            bi = s_redi[w];
+          }
+        s_sample = bi;
+        if (a.out && rank == 0) a.out[(int64_t)stream * a.n_steps + step] = bi;
+      }
+    }
+    // ---- 2. past taps of every layer (rings live in global memory; written at least one step ago) ----
+    for (int i = tid; i < L.L * 16; i += V4_T) {
+      const int l = i >> 4, v4 = i & 15;
+      const GenLayerOff& ly = s_layers[l];
+      const int len = ly.ring_len;
+      const int64_t tau = t - ly.dilation;
+      const int slot = (int)(((tau % len) + len) % len);
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(st + ly.ring + ((int64_t)stream * len + slot) * R) + v4);
+      *reinterpret_cast<float4*>(xpast + l * 64 + v4 * 4) = v;
+    }
+    csync4();                           // s_sample visible
+    if (tid < R) {
+      const float* emb = st + L.emb;
+      float v = L.has_cb ? st[L.emb_b + tid] : 0.f;
+      const int q_new = s_sample;
+      if (kc1 > 0 && prev_q >= 0) v += emb[((int64_t)0 * Q + prev_q) * R + tid];
+      v += emb[((int64_t)kc1 * Q + q_new) * R + tid];
+      xv[tid] = v;
+    }
+    prev_q = s_sample;
+    csync4();
+    // ---- 3. residual layers ----
+    float skr = 0.f;                    // skip-sum channel 32*rank + oB - 8 (threads with ksB == 0, oB >= 8)
+    for (int l = 0; l < L.L; ++l, ++it) {
+      const GenLayerOff& ly = s_layers[l];
+      const int len = ly.ring_len;
+      const uint32_t stage = it % V4_STAGES;
+      tc::mbar_wait(full0 + 8 * stage, (it / V4_STAGES) & 1);
+      const float4* wst = reinterpret_cast<const float4*>(ring_g + stage * V4_STAGE_BYTES);
+      {
+        const float* xin = ksA < 8 ? xpast + l * 64 + ksA * 8 : xv + (ksA - 8) * 8;
+        const float4 w0 = wst[tid], w1 = wst[256 + tid];
+        const float4 x0 = *reinterpret_cast<const float4*>(xin), x1 = *reinterpret_cast<const float4*>(xin + 4);
+        float acc = w0.x * x0.x;
+        acc = fmaf(w0.y, x0.y, acc), acc = fmaf(w0.z, x0.z, acc), acc = fmaf(w0.w, x0.w, acc);
+        acc = fmaf(w1.x, x1.x, acc), acc = fmaf(w1.y, x1.y, acc), acc = fmaf(w1.z, x1.z, acc), acc = fmaf(w1.w, x1.w, acc);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+        const float other = __shfl_xor_sync(0xffffffffu, acc, 16);
+        if (lane == 0) {
+          const int ch = 8 * rank + warp;
+          float f = acc, gg = other;
+          if (ly.has_ba) {
+            f += st[ly.ba + ch];
+            gg += st[ly.ba + G + ch];
+          }
+          bcast_value(zv_s + zsel * 256, ch, tanhf(f) * (1.f / (1.f + expf(-gg))), zbar);   // wavenet.py:351
+        }
+      }
+      exchange_wait(zbar, zph, 64 * 4, tid);
+      zph ^= 1;
+      // this CTA's slice of x[t] into the ring (roll, faster_wavenet.py:90-91).  The slot is the one every CTA read as
+      // x[t-d] at the top of the step: writing it only after the z exchange orders the write behind all those reads.
+      if (tid < 8) st[ly.ring + ((int64_t)stream * len + (int)(t % len)) * R + 8 * rank + tid] = xv[8 * rank + tid];
+      if (tid < 160) {
+        const float4* wb = wst + V4_WA_F / 4;
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w = wb[q * 160 + tid];
+          const float4 z = *reinterpret_cast<const float4*>(zv + zsel * 64 + ksB * 16 + q * 4);
+          acc = fmaf(w.x, z.x, acc), acc = fmaf(w.y, z.y, acc), acc = fmaf(w.z, z.z, acc), acc = fmaf(w.w, z.w, acc);
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (ksB == 0) {
+          if (oB < 8) {
+            const int ch = 8 * rank + oB;
+            const float bb = ly.has_bb ? st[ly.bb + ch] : 0.f;
+            bcast_value(xv_s, ch, xv[ch] + acc + bb, xbar);                    // output = projection + x, wavenet.py:354
+          } else {
+            const float bb = ly.has_bb ? st[ly.bb + R + 32 * rank + oB - 8] : 0.f;
+            skr += acc + bb;                                                   // faster_wavenet.py:100
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(empty0 + 8 * stage);
+      exchange_wait(xbar, xph, 64 * 4, tid);
+      xph ^= 1;
+      zsel ^= 1;
+    }
+    // ---- 4. head (faster_wavenet.py:105-113: ELU on incremental steps; ReLU variant) ----
+    int hsel = 0;
+    if (tid < 160 && ksB == 0 && oB >= 8) bcast_value(hB_s, 32 * rank + oB - 8, head_act(skr, a.head_elu), hbar0);
+    exchange_wait(hbar0, hph[0], 256 * 4, tid);
+    hph[0] ^= 1;
+    hsel = 1;
+    float* hin = hB;
+    float* hout = hA;
+    uint32_t hout_s = hA_s, hin_s = hB_s;
+    for (int hi = 0; hi < L.n_head; ++hi, ++it) {
+      const uint32_t stage = it % V4_STAGES;
+      tc::mbar_wait(full0 + 8 * stage, (it / V4_STAGES) & 1);
+      const float4* wst = reinterpret_cast<const float4*>(ring_g + stage * V4_STAGE_BYTES);
+      float acc = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 w = wst[q * 256 + tid];
+        const float4 x = *reinterpret_cast<const float4*>(hin + ksH * 32 + q * 4);
+        acc = fmaf(w.x, x.x, acc), acc = fmaf(w.y, x.y, acc), acc = fmaf(w.z, x.z, acc), acc = fmaf(w.w, x.w, acc);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      const bool last = hi == L.n_head - 1;
+      if (ksH == 0) {
+        const int o = 32 * rank + oH;
+        float v = acc + hbias[hi * 256 + o];
+        if (!last) v = head_act(v, a.head_elu);
+        bcast_value(hout_s, o, v, hsel ? hbar1 : hbar0);
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(empty0 + 8 * stage);
+      exchange_wait(hsel ? hbar1 : hbar0, hph[hsel], 256 * 4, tid);
+      hph[hsel] ^= 1;
+      hsel ^= 1;
+      float* tmp = hin;
+      hin = hout;
+      hout = tmp;
+      const uint32_t ts = hin_s;
+      hin_s = hout_s;
+      hout_s = ts;
+    }
+    lg = hin;   // logits for the next sample
+  }
+  // ---- epilogue (rank 0 publishes the stream's state) ----
+  if (rank == 0) {
+    for (int q = tid; q < Q; q += V4_T) cur_logits[(int64_t)stream * Q + q] = lg[q];
+    if (kc1 > 0 && tid == 0) idx_hist[(int64_t)stream * kc1 + kc1 - 1] = prev_q;
+    if (a.probs) {
+      if (!a.apply_softmax) {
+        for (int q = tid; q < Q; q += V4_T) a.probs[(int64_t)stream * Q + q] = lg[q];
+      } else {
+        float m = lg[tid];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) s_redv[warp] = m;
+        csync4();
+        m = s_redv[0];
+        for (int w = 1; w < V4_T / 32; ++w) m = fmaxf(m, s_redv[w]);
+        csync4();
+        float sum = expf(lg[tid] - m);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) s_redv[warp] = sum;
+        csync4();
+        sum = 0.f;
+        for (int w = 0; w < V4_T / 32; ++w) sum += s_redv[w];
+        a.probs[(int64_t)stream * Q + tid] = expf(lg[tid] - m) / sum;
+      }
+    }
+  }
+  cluster_sync_all();   // nobody leaves while a peer may still store into its shared memory
+}
+
+// dst[rank][...] <- src [K][N] (generator layout), cut into the per-rank, per-thread order gen_kernel_v4 reads:
+// mode 1: WA (K = 128, N = 128 = a_f | a_g), mode 2: WB (K = 64, N = 320 = residual | skip), mode 3: head (K = N = 256).
+__global__ void gen_pack_v4(const float* __restrict__ src, float* __restrict__ dst, int64_t rank_stride, int K, int N,
+                            int mode) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= K * N) return;
+  const int k = idx / N, n = idx % N, comp = k & 3;
+  int r, f4;
+  if (mode == 1) {
+    const int ch = n & 63, half = n >> 6;
+    r = ch >> 3;
+    const int t = ((ch & 7) * 2 + half) * 16 + (k >> 3);
+    f4 = ((k & 7) >> 2) * 256 + t;
+  } else if (mode == 2) {
+    int o;
+    if (n < 64) {
+      r = n >> 3;
+      o = n & 7;
+    } else {
+      r = (n - 64) >> 5;
+      o = 8 + ((n - 64) & 31);
+    }
+    const int t = o * 4 + (k >> 4);
+    f4 = ((k & 15) >> 2) * 160 + t;
+  } else {
+    r = n >> 5;
+    const int t = (n & 31) * 8 + (k >> 5);
+    f4 = ((k & 31) >> 2) * 256 + t;
+  }
+  dst[(int64_t)r * rank_stride + (int64_t)f4 * 4 + comp] = src[idx];
+}
+
+size_t gen_smem_bytes_v4(const GenLayout& L) {
+  const size_t f = 64 + 128 + 256 + 256 + (size_t)L.L * 64 + (size_t)L.n_head * 256 + 64;
+  return f * sizeof(float) + V4_STAGES * V4_STAGE_BYTES + 128;
+}
+
+int launch_gen_v4(const GenArgs& a, cudaStream_t s) {
+  const size_t smem = gen_smem_bytes_v4(a.lay);
+  static bool attr = false;
+  if (!attr) {
+    WN_CHECK_CUDA(cudaFuncSetAttribute(gen_kernel_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  gen_kernel_v4<<<a.lay.n * V4_CS, V4_T + 32, smem, s>>>(a);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
 size_t gen_smem_bytes(const GenLayout& L, int NS, bool stream) {
   const size_t maxw = L.maxw;
   size_t f = NS * maxw                               // xv
@@ -1058,6 +1434,10 @@ int pick_ns(const wn_gen* g) {
 
 int run_gen(wn_gen* g, GenArgs& a, cudaStream_t s) {
   const int ns = pick_ns(g);
+  if (g->v4_ok) {
+    const char* e = getenv("WN_GEN_V4");
+    if (!e || atoi(e) != 0) return launch_gen_v4(a, s);
+  }
   if (g->v3_ok) {
     int ns3 = ns;
     if (const char* e = getenv("WN_GEN_NS")) ns3 = atoi(e);
@@ -1203,6 +1583,14 @@ extern "C" int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen**
     if (g->chunks3.size() > 512) g->v3_ok = false;
     L.chunks3_dev = take((int64_t)(sizeof(GenChunk) * g->chunks3.size() + 3) / 4 + 4);
   }
+  // v4 (one 8-CTA cluster per stream): the v3 shape with 64 residual channels and 256-wide head inputs, few streams
+  g->v4_ok = g->v3_ok && L.R == 64 && L.k == 2 && L.kc <= 2 && n_streams * V4_CS_HOST <= h->sm_count;
+  for (int i = 0; i < L.n_head && g->v4_ok; ++i) g->v4_ok = L.head_ch[i] == 256;
+  for (int l = 0; l < L.L && g->v4_ok; ++l) g->v4_ok = g->layers[l].ring_len > 0;
+  if (g->v4_ok) {
+    L.wpk4_rank = (int64_t)L.L * (2 * 256 * 4 + 4 * 160 * 4) + (int64_t)L.n_head * (8 * 256 * 4);
+    L.wpk4 = take(L.wpk4_rank * V4_CS_HOST);
+  }
   L.maxw = (maxw + 3) / 4 * 4;
   L.total = off;
   *out = g;
@@ -1305,6 +1693,20 @@ extern "C" int wn_gen_prime(wn_gen* g, const float* params, const int32_t* windo
     }
     WN_CHECK_CUDA(cudaMemcpyAsync(S + L.chunks3_dev, g->chunks3.data(), sizeof(GenChunk) * g->chunks3.size(),
                                   cudaMemcpyHostToDevice, s));
+  }
+  if (g->v4_ok) {
+    int64_t o4 = 0;
+    for (int l = 0; l < L.L; ++l) {
+      gen_pack_v4<<<nb(128 * 128), 256, 0, s>>>(S + g->layers[l].wa, S + L.wpk4 + o4, L.wpk4_rank, 128, 128, 1);
+      o4 += V4_WA_F;
+      gen_pack_v4<<<nb(64 * 320), 256, 0, s>>>(S + g->layers[l].wb, S + L.wpk4 + o4, L.wpk4_rank, 64, 320, 2);
+      o4 += V4_WB_F;
+    }
+    for (int i = 0; i < L.n_head; ++i) {
+      gen_pack_v4<<<nb(256 * 256), 256, 0, s>>>(S + L.hw[i], S + L.wpk4 + o4, L.wpk4_rank, 256, 256, 3);
+      o4 += V4_WH_F;
+    }
+    WN_CHECK_LAUNCH();
   }
   g->primed = true;
   g->t = Win;
