@@ -1,0 +1,26 @@
+"""Developer trace of gen_kernel_v4 (not a test).  Needs `make -C wavenet_b200/csrc clean all EXTRA=-DWN_LAYER_TRACE`."""
+import sys, os, ctypes
+sys.path.insert(0, '/root/repo')
+import numpy as np, torch
+from oracle import wavenet_oracle as O
+from bench import config_c
+from wavenet_b200 import _lib
+from wavenet_b200.faster_wavenet import FasterWaveNet
+net = FasterWaveNet(config_c(), seed=0)
+net.set_weights(O.init_weights(O.config_C(), np.random.default_rng(1234), np.float32))
+net.to_gpu(0)
+window = np.random.default_rng(0).integers(0, 256, (1, net.input_width)).astype(np.int32)
+net.generate(window, 20, mode="sample", seed=0)
+torch.cuda.synchronize()
+buf = np.zeros(64 * 8, dtype=np.int64)
+fn = ctypes.CDLL(_lib.LIB_PATH).wn_debug_gen_trace
+fn.argtypes = [ctypes.c_void_p]; fn.restype = ctypes.c_int
+assert fn(buf.ctypes.data) == 0
+tr = buf.reshape(64, 8)
+t0 = tr[41][0]
+print("step start -> layers start:", tr[41][1] - t0)
+for l in (0, 1, 2, 10, 11, 28, 29):
+    r = tr[l]
+    print("layer %2d: start %6d | weights wait %4d | phase A + send %4d | z wait %4d | phase B + send %4d | x wait %4d" %
+          (l, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4]))
+print("layers total:", tr[40][0] - tr[41][1], " head:", tr[40][1] - tr[40][0], " step:", tr[40][1] - t0)

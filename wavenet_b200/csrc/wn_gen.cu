@@ -1080,6 +1080,13 @@ __device__ __forceinline__ void exchange_wait(uint32_t bar, uint32_t parity, uin
   tc::mbar_wait(bar, parity);
 }
 
+// Developer trace (make EXTRA=-DWN_LAYER_TRACE, tests/dev/trace_gen.py): clock64 stamps of CTA 0 / thread 0 in step 2
+#ifdef WN_LAYER_TRACE
+__device__ long long g_trace_gen[64 * 8];
+#define TRG(l, e) do { if (blockIdx.x == 0 && tid == 0 && step == 2 && (l) < 64) g_trace_gen[(l) * 8 + (e)] = clock64(); } while (0)
+#else
+#define TRG(l, e) do { } while (0)
+#endif
 __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_kernel_v4(GenArgs a) {
   extern __shared__ float sm[];
   const GenLayout& L = a.lay;
@@ -1165,6 +1172,7 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
   for (int step = 0; step < a.n_steps; ++step) {
     const int64_t t = a.t0 + step;
     // ---- 1. sample (every CTA computes the same value) ----
+    TRG(41, 0);
     if (!a.sample_first) {
       if (tid == 0) s_sample = a.forced[stream];
     } else {
@@ -1217,12 +1225,15 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
     prev_q = s_sample;
     csync4();
     // ---- 3. residual layers ----
+    TRG(41, 1);
     float skr = 0.f;                    // skip-sum channel 32*rank + oB - 8 (threads with ksB == 0, oB >= 8)
     for (int l = 0; l < L.L; ++l, ++it) {
       const GenLayerOff& ly = s_layers[l];
       const int len = ly.ring_len;
       const uint32_t stage = it % V4_STAGES;
+      TRG(l, 0);
       tc::mbar_wait(full0 + 8 * stage, (it / V4_STAGES) & 1);
+      TRG(l, 1);
       const float4* wst = reinterpret_cast<const float4*>(ring_g + stage * V4_STAGE_BYTES);
       {
         const float* xin = ksA < 8 ? xpast + l * 64 + ksA * 8 : xv + (ksA - 8) * 8;
@@ -1246,7 +1257,9 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
           bcast_value(zv_s + zsel * 256, ch, tanhf(f) * (1.f / (1.f + expf(-gg))), zbar);   // wavenet.py:351
         }
       }
+      TRG(l, 2);
       exchange_wait(zbar, zph, 64 * 4, tid);
+      TRG(l, 3);
       zph ^= 1;
       // this CTA's slice of x[t] into the ring (roll, faster_wavenet.py:90-91).  The slot is the one every CTA read as
       // x[t-d] at the top of the step: writing it only after the z exchange orders the write behind all those reads.
@@ -1275,11 +1288,14 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
       }
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(empty0 + 8 * stage);
+      TRG(l, 4);
       exchange_wait(xbar, xph, 64 * 4, tid);
+      TRG(l, 5);
       xph ^= 1;
       zsel ^= 1;
     }
     // ---- 4. head (faster_wavenet.py:105-113: ELU on incremental steps; ReLU variant) ----
+    TRG(40, 0);
     int hsel = 0;
     if (tid < 160 && ksB == 0 && oB >= 8) bcast_value(hB_s, 32 * rank + oB - 8, head_act(skr, a.head_elu), hbar0);
     exchange_wait(hbar0, hph[0], 256 * 4, tid);
@@ -1322,6 +1338,7 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
       hout_s = ts;
     }
     lg = hin;   // logits for the next sample
+    TRG(40, 1);
   }
   // ---- epilogue (rank 0 publishes the stream's state) ----
   if (rank == 0) {
@@ -1597,6 +1614,11 @@ extern "C" int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen**
   return WN_OK;
 }
 
+#ifdef WN_LAYER_TRACE
+extern "C" int wn_debug_gen_trace(long long* out) {
+  return cudaMemcpyFromSymbol(out, g_trace_gen, sizeof(long long) * 64 * 8) == cudaSuccess ? 0 : -1;
+}
+#endif
 extern "C" int wn_gen_destroy(wn_gen* g) {
   delete g;
   return WN_OK;
