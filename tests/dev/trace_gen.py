@@ -12,15 +12,15 @@ net.to_gpu(0)
 window = np.random.default_rng(0).integers(0, 256, (1, net.input_width)).astype(np.int32)
 net.generate(window, 20, mode="sample", seed=0)
 torch.cuda.synchronize()
-buf = np.zeros(64 * 8, dtype=np.int64)
+buf = np.zeros(64 * 16, dtype=np.int64)
 fn = ctypes.CDLL(_lib.LIB_PATH).wn_debug_gen_trace
 fn.argtypes = [ctypes.c_void_p]; fn.restype = ctypes.c_int
 assert fn(buf.ctypes.data) == 0
-tr = buf.reshape(64, 8)
+tr = buf.reshape(64, 16)
 t0 = tr[41][0]
 print("step start -> layers start:", tr[41][1] - t0)
 for l in (0, 1, 2, 10, 11, 28, 29):
     r = tr[l]
     print("layer %2d: start %6d | weights wait %4d | phase A + send %4d | z wait %4d | phase B + send %4d | x wait %4d" %
-          (l, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4]))
+          (l, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4]), "| B: ring store %d, dot %d, shuffles %d, bias+residual %d, send %d" % (r[8] - r[3], r[9] - r[8], r[10] - r[9], r[6] - r[10], r[7] - r[6]))
 print("layers total:", tr[40][0] - tr[41][1], " head:", tr[40][1] - tr[40][0], " step:", tr[40][1] - t0)

@@ -1082,8 +1082,8 @@ __device__ __forceinline__ void exchange_wait(uint32_t bar, uint32_t parity, uin
 
 // Developer trace (make EXTRA=-DWN_LAYER_TRACE, tests/dev/trace_gen.py): clock64 stamps of CTA 0 / thread 0 in step 2
 #ifdef WN_LAYER_TRACE
-__device__ long long g_trace_gen[64 * 8];
-#define TRG(l, e) do { if (blockIdx.x == 0 && tid == 0 && step == 2 && (l) < 64) g_trace_gen[(l) * 8 + (e)] = clock64(); } while (0)
+__device__ long long g_trace_gen[64 * 16];
+#define TRG(l, e) do { if (blockIdx.x == 0 && tid == 0 && step == 2 && (l) < 64) g_trace_gen[(l) * 16 + (e)] = clock64(); } while (0)
 #else
 #define TRG(l, e) do { } while (0)
 #endif
@@ -1108,6 +1108,8 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
   __shared__ float s_redv[V4_T / 32];
   __shared__ int s_redi[V4_T / 32];
   __shared__ int s_sample;
+  __shared__ int s_pos[128];            // ring slot of time t per layer (t mod ring_len), advanced once per step: no 64-bit
+                                        // modulo on the per-layer critical path
   const uint32_t full0 = tc::smem_u32(&s_bars[0]), empty0 = tc::smem_u32(&s_bars[V4_STAGES]);
   // exchange barriers.  Consecutive exchanges never use the same barrier (z, x alternate per layer, the head alternates
   // hbar0/hbar1): a peer that is one exchange ahead then completes its bytes on a barrier whose previous phase is over
@@ -1126,7 +1128,10 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
     tc::mbar_init(hbar1, 1);
     tc::fence_barrier_init();
   }
-  for (int i = tid; i < L.L; i += blockDim.x) s_layers[i] = a.layers[i];
+  for (int i = tid; i < L.L; i += blockDim.x) {
+    s_layers[i] = a.layers[i];
+    s_pos[i] = (int)(a.t0 % a.layers[i].ring_len);
+  }
   for (int i = tid; i < L.n_head * 256; i += blockDim.x) hbias[i] = L.has_hb ? st[L.hb[i / 256] + (i % 256)] : 0.f;
   float* cur_logits = st + L.cur_logits;
   for (int i = tid; i < Q; i += blockDim.x) hA[i] = cur_logits[(int64_t)stream * Q + i];
@@ -1207,10 +1212,8 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
     for (int i = tid; i < L.L * 16; i += V4_T) {
       const int l = i >> 4, v4 = i & 15;
       const GenLayerOff& ly = s_layers[l];
-      const int len = ly.ring_len;
-      const int64_t tau = t - ly.dilation;
-      const int slot = (int)(((tau % len) + len) % len);
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(st + ly.ring + ((int64_t)stream * len + slot) * R) + v4);
+      const int len = ly.ring_len;      // == dilation (k = 2): x[t - d] sits in the slot x[t] is about to take
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(st + ly.ring + ((int64_t)stream * len + s_pos[l]) * R) + v4);
       *reinterpret_cast<float4*>(xpast + l * 64 + v4 * 4) = v;
     }
     csync4();                           // s_sample visible
@@ -1228,8 +1231,11 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
     TRG(41, 1);
     float skr = 0.f;                    // skip-sum channel 32*rank + oB - 8 (threads with ksB == 0, oB >= 8)
     for (int l = 0; l < L.L; ++l, ++it) {
+      // layer constants into registers before the weights wait (shared-memory loads off the critical path)
       const GenLayerOff& ly = s_layers[l];
-      const int len = ly.ring_len;
+      const int64_t ring_slot = ly.ring + ((int64_t)stream * ly.ring_len + s_pos[l]) * R;
+      const bool has_ba = ly.has_ba != 0, has_bb = ly.has_bb != 0;
+      const int64_t ba_off = ly.ba, bb_off = ly.bb;
       const uint32_t stage = it % V4_STAGES;
       TRG(l, 0);
       tc::mbar_wait(full0 + 8 * stage, (it / V4_STAGES) & 1);
@@ -1239,9 +1245,10 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
         const float* xin = ksA < 8 ? xpast + l * 64 + ksA * 8 : xv + (ksA - 8) * 8;
         const float4 w0 = wst[tid], w1 = wst[256 + tid];
         const float4 x0 = *reinterpret_cast<const float4*>(xin), x1 = *reinterpret_cast<const float4*>(xin + 4);
-        float acc = w0.x * x0.x;
+        float acc = w0.x * x0.x, acc1 = w1.x * x1.x;    // two chains: the reduction below is latency-bound
         acc = fmaf(w0.y, x0.y, acc), acc = fmaf(w0.z, x0.z, acc), acc = fmaf(w0.w, x0.w, acc);
-        acc = fmaf(w1.x, x1.x, acc), acc = fmaf(w1.y, x1.y, acc), acc = fmaf(w1.z, x1.z, acc), acc = fmaf(w1.w, x1.w, acc);
+        acc1 = fmaf(w1.y, x1.y, acc1), acc1 = fmaf(w1.z, x1.z, acc1), acc1 = fmaf(w1.w, x1.w, acc1);
+        acc += acc1;
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
@@ -1250,9 +1257,9 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
         if (lane == 0) {
           const int ch = 8 * rank + warp;
           float f = acc, gg = other;
-          if (ly.has_ba) {
-            f += st[ly.ba + ch];
-            gg += st[ly.ba + G + ch];
+          if (has_ba) {
+            f += st[ba_off + ch];
+            gg += st[ba_off + G + ch];
           }
           bcast_value(zv_s + zsel * 256, ch, tanhf(f) * (1.f / (1.f + expf(-gg))), zbar);   // wavenet.py:351
         }
@@ -1261,33 +1268,41 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
       exchange_wait(zbar, zph, 64 * 4, tid);
       TRG(l, 3);
       zph ^= 1;
-      // this CTA's slice of x[t] into the ring (roll, faster_wavenet.py:90-91).  The slot is the one every CTA read as
-      // x[t-d] at the top of the step: writing it only after the z exchange orders the write behind all those reads.
-      if (tid < 8) st[ly.ring + ((int64_t)stream * len + (int)(t % len)) * R + 8 * rank + tid] = xv[8 * rank + tid];
+      const float xring = tid < 8 ? xv[8 * rank + tid] : 0.f;   // read before this CTA's own x_out lands on top of it
+      TRG(l, 8);
       if (tid < 160) {
         const float4* wb = wst + V4_WA_F / 4;
-        float acc = 0.f;
+        float a4[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 4; ++q) {                   // four independent chains
           const float4 w = wb[q * 160 + tid];
           const float4 z = *reinterpret_cast<const float4*>(zv + zsel * 64 + ksB * 16 + q * 4);
-          acc = fmaf(w.x, z.x, acc), acc = fmaf(w.y, z.y, acc), acc = fmaf(w.z, z.z, acc), acc = fmaf(w.w, z.w, acc);
+          a4[q] = w.x * z.x;
+          a4[q] = fmaf(w.y, z.y, a4[q]), a4[q] = fmaf(w.z, z.z, a4[q]), a4[q] = fmaf(w.w, z.w, a4[q]);
         }
+        float acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+        TRG(l, 9);
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        TRG(l, 10);
         if (ksB == 0) {
           if (oB < 8) {
             const int ch = 8 * rank + oB;
-            const float bb = ly.has_bb ? st[ly.bb + ch] : 0.f;
+            const float bb = has_bb ? st[bb_off + ch] : 0.f;
+            TRG(l, 6);
             bcast_value(xv_s, ch, xv[ch] + acc + bb, xbar);                    // output = projection + x, wavenet.py:354
+            TRG(l, 7);
           } else {
-            const float bb = ly.has_bb ? st[ly.bb + R + 32 * rank + oB - 8] : 0.f;
+            const float bb = has_bb ? st[bb_off + R + 32 * rank + oB - 8] : 0.f;
             skr += acc + bb;                                                   // faster_wavenet.py:100
           }
         }
       }
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(empty0 + 8 * stage);
+      // this CTA's slice of x[t] into the ring (roll, faster_wavenet.py:90-91).  The slot is the one every CTA read as
+      // x[t-d] at the top of the step: this point is behind the z exchange, hence behind all those reads.
+      if (tid < 8) st[ring_slot + 8 * rank + tid] = xring;
       TRG(l, 4);
       exchange_wait(xbar, xph, 64 * 4, tid);
       TRG(l, 5);
@@ -1338,6 +1353,10 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
       hout_s = ts;
     }
     lg = hin;   // logits for the next sample
+    if (tid < L.L) {                    // every thread is past this step's ring accesses (the head exchanges came after)
+      const int p = s_pos[tid] + 1;
+      s_pos[tid] = p == s_layers[tid].ring_len ? 0 : p;
+    }
     TRG(40, 1);
   }
   // ---- epilogue (rank 0 publishes the stream's state) ----
@@ -1616,7 +1635,7 @@ extern "C" int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen**
 
 #ifdef WN_LAYER_TRACE
 extern "C" int wn_debug_gen_trace(long long* out) {
-  return cudaMemcpyFromSymbol(out, g_trace_gen, sizeof(long long) * 64 * 8) == cudaSuccess ? 0 : -1;
+  return cudaMemcpyFromSymbol(out, g_trace_gen, sizeof(long long) * 64 * 16) == cudaSuccess ? 0 : -1;
 }
 #endif
 extern "C" int wn_gen_destroy(wn_gen* g) {
