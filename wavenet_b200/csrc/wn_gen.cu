@@ -1426,6 +1426,32 @@ size_t gen_smem_bytes_v4(const GenLayout& L) {
   return f * sizeof(float) + V4_STAGES * V4_STAGE_BYTES + 128;
 }
 
+// how many 8-CTA clusters of gen_kernel_v4 can be resident at once (they must all be: the kernel is persistent over
+// every audio sample, a second wave would only start when the first has finished)
+int gen_v4_max_streams(const GenLayout& L) {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  const size_t smem = gen_smem_bytes_v4(L);
+  if (cudaFuncSetAttribute(gen_kernel_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return cached = 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(V4_CS * 32);
+  cfg.blockDim = dim3(V4_T + 32);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = V4_CS;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, gen_kernel_v4, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  return cached = n;
+}
+
 int launch_gen_v4(const GenArgs& a, cudaStream_t s) {
   const size_t smem = gen_smem_bytes_v4(a.lay);
   static bool attr = false;
@@ -1470,7 +1496,7 @@ int pick_ns(const wn_gen* g) {
 
 int run_gen(wn_gen* g, GenArgs& a, cudaStream_t s) {
   const int ns = pick_ns(g);
-  if (g->v4_ok) {
+  if (g->v4_ok && g->lay.n <= gen_v4_max_streams(g->lay)) {
     const char* e = getenv("WN_GEN_V4");
     if (!e || atoi(e) != 0) return launch_gen_v4(a, s);
   }
