@@ -387,14 +387,19 @@ def main():
             total_streams = n * world if n_total > 1 else 1
             us = 1e3 * gms / steps
             sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
-            n_ctas = -(-n // (1 if n <= 148 else 2))
+            clustered = n <= 15          # gen_kernel_v4: one 8-CTA cluster per stream while all clusters are co-resident
+            n_ctas = 8 * n if clustered else -(-n // (1 if n <= 148 else 2))
+            per_cta = 1270272 * 4 / 8 if clustered else 1270272 * 4   # bytes of packed fp32 weights per CTA per step
             gen["batch_%d" % n_total] = {
                 "samples_per_s": total_streams * steps / (gms / 1e3), "streams": total_streams, "steps": steps,
                 "us_per_step": us, "cycles_per_sample_per_stream": us * sm_mhz,
-                # every CTA streams the 5.08 MB fp32 weight set once per step through its cp.async.bulk ring
-                "weight_stream_gbs_per_sm": 1270272 * 4 / (us * 1e-6) / 1e9,
-                "weight_stream_gbs_all_ctas": n_ctas * world * 1270272 * 4 / (us * 1e-6) / 1e9,
-                "bound": "dependency-chain latency (30 layers x 2 block barriers + head per sample)"}
+                "kernel": "gen_kernel_v4 (8-CTA cluster per stream, output-split matvecs, st.async exchanges)" if clustered
+                          else "gen_kernel_v3 (one CTA per 1-2 streams)",
+                # every CTA streams its share of the 5.08 MB fp32 weight set once per step through its cp.async.bulk ring
+                "weight_stream_gbs_per_sm": per_cta / (us * 1e-6) / 1e9,
+                "weight_stream_gbs_all_ctas": n_ctas * world * per_cta / (us * 1e-6) / 1e9,
+                "bound": ("dependency-chain latency (30 layers x 2 cluster exchanges + head per sample)" if clustered else
+                          "dependency-chain latency (30 layers x 2 block barriers + head per sample)")}
         line["fast_gen"] = gen
 
     # ---- BASELINE config 1 shape on the GPU: reference default network (train_audio/model.py:24-43), one train.py
