@@ -1037,15 +1037,16 @@ int launch_gen_v3(const GenArgs& a, cudaStream_t s) {
 // eight CTAs of a cluster split every matvec by OUTPUT rows -- each streams only its 1/8 slice of the packed weights
 // (604 KB per sample) -- and exchange the 64-float activations through distributed shared memory: a thread that
 // finishes an output sends it to all eight CTAs with st.async (a remote store that completes 4 bytes on the destination's
-// mbarrier); consumers wait for the byte count.  Two exchanges per layer (z, x) + one per head conv.
+// mbarrier); consumers wait for the byte count.  ONE exchange per layer (z) + one per head conv: the residual update
+// x += Wp z is computed redundantly by every CTA from the full z (16 KB more weights per layer, but no second exchange).
 // Sampling and the embedding of the next sample are computed redundantly by every CTA (same logits, same counter RNG),
 // so no broadcast of the sample is needed.
 constexpr int V4_CS = 8;                  // CTAs per cluster
 constexpr int V4_T = 256;                 // consumer threads per CTA (+ one producer warp)
-constexpr int V4_STAGE_BYTES = 32768;     // one chunk per stage: a layer's WA|WB slice (18 KB) or a head slice (32 KB)
+constexpr int V4_STAGE_BYTES = 32768;     // one chunk per stage: a layer's WA|WB slice or a head slice (32 KB each)
 constexpr int V4_STAGES = 4;
 constexpr int V4_WA_F = 2 * 256 * 4;      // floats of a packed WA slice: [q 2][thread 256] float4
-constexpr int V4_WB_F = 4 * 160 * 4;      // WB slice: [q 4][thread 160] float4
+constexpr int V4_WB_F = 8 * 192 * 4;      // WB slice: ALL 64 residual rows + this rank's 32 skip rows: [q 8][thread 192] float4
 constexpr int V4_WH_F = 8 * 256 * 4;      // head slice: [q 8][thread 256] float4
 
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -1111,10 +1112,10 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
   __shared__ int s_pos[128];            // ring slot of time t per layer (t mod ring_len), advanced once per step: no 64-bit
                                         // modulo on the per-layer critical path
   const uint32_t full0 = tc::smem_u32(&s_bars[0]), empty0 = tc::smem_u32(&s_bars[V4_STAGES]);
-  // exchange barriers.  Consecutive exchanges never use the same barrier (z, x alternate per layer, the head alternates
+  // exchange barriers.  Consecutive exchanges never use the same barrier (the layers alternate zbar0/zbar1, the head
   // hbar0/hbar1): a peer that is one exchange ahead then completes its bytes on a barrier whose previous phase is over
   // in every CTA, so byte counts of different phases cannot mix.
-  const uint32_t zbar = tc::smem_u32(&s_bars[2 * V4_STAGES]), xbar = zbar + 8, hbar0 = zbar + 16, hbar1 = zbar + 24;
+  const uint32_t zbar0 = tc::smem_u32(&s_bars[2 * V4_STAGES]), zbar1 = zbar0 + 8, hbar0 = zbar0 + 16, hbar1 = zbar0 + 24;
   const uint32_t xv_s = tc::smem_u32(xv), zv_s = tc::smem_u32(zv), hA_s = tc::smem_u32(hA), hB_s = tc::smem_u32(hB);
   float* st = a.state;
   if (tid == 0) {
@@ -1122,8 +1123,8 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
       tc::mbar_init(full0 + 8 * i, 1);
       tc::mbar_init(empty0 + 8 * i, V4_T / 32);
     }
-    tc::mbar_init(zbar, 1);             // phases are opened by tid 0 with the expected byte count
-    tc::mbar_init(xbar, 1);
+    tc::mbar_init(zbar0, 1);            // phases are opened by tid 0 with the expected byte count
+    tc::mbar_init(zbar1, 1);
     tc::mbar_init(hbar0, 1);
     tc::mbar_init(hbar1, 1);
     tc::fence_barrier_init();
@@ -1146,7 +1147,7 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
       for (int step = 0; step < a.n_steps; ++step) {
         uint64_t off = 0;
         for (int c = 0; c < n_chunks; ++c, ++it) {
-          const uint32_t bytes = (c < L.L ? (V4_WA_F + V4_WB_F) : V4_WH_F) * 4;
+          const uint32_t bytes = (c < L.L ? (V4_WA_F + V4_WB_F) : V4_WH_F) * 4;   // 32 KB either way
           const uint32_t stage = it % V4_STAGES;
           tc::mbar_wait(empty0 + 8 * stage, ((it / V4_STAGES) & 1) ^ 1);
           tc::mbar_arrive_expect_tx(full0 + 8 * stage, bytes);
@@ -1166,12 +1167,13 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
   const int kc1 = L.kc - 1;             // 0 or 1 previous samples feed the causal (embedding) layer
   int prev_q = kc1 > 0 ? idx_hist[(int64_t)stream * kc1 + kc1 - 1] : -1;
   float* lg = hA;
-  uint32_t it = 0, zph = 0, xph = 0, hph[2] = {0, 0}, zsel = 0;
+  uint32_t it = 0, zph[2] = {0, 0}, hph[2] = {0, 0}, zsel = 0;
   // phase A roles: warp w -> gate channel 8*rank + w; lanes 0..15 a_f, 16..31 a_g; K slice = lane & 15 (8 rows)
-  // phase B roles: thread t < 160 -> output t >> 2 (0..7 residual channel 8*rank+o, 8..39 skip channel 32*rank+o-8), K slice t & 3
+  // phase B roles: thread t < 192 -> output t >> 1 (0..63 residual channel o -- every CTA computes all of them --,
+  //                64..95 skip channel 32*rank + o - 64), K half t & 1
   // head roles   : output tid >> 3 (32*rank + o), K slice tid & 7 (32 rows)
   const int ksA = lane & 15;
-  const int oB = tid >> 2, ksB = tid & 3;
+  const int oB = tid >> 1, ksB = tid & 1;
   const int oH = tid >> 3, ksH = tid & 7;
 
   for (int step = 0; step < a.n_steps; ++step) {
@@ -1229,7 +1231,7 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
     csync4();
     // ---- 3. residual layers ----
     TRG(41, 1);
-    float skr = 0.f;                    // skip-sum channel 32*rank + oB - 8 (threads with ksB == 0, oB >= 8)
+    float skr = 0.f;                    // skip-sum channel 32*rank + oB - 64 (threads with ksB == 0, oB >= 64)
     for (int l = 0; l < L.L; ++l, ++it) {
       // layer constants into registers before the weights wait (shared-memory loads off the critical path)
       const GenLayerOff& ly = s_layers[l];
@@ -1261,39 +1263,32 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
             f += st[ba_off + ch];
             gg += st[ba_off + G + ch];
           }
-          bcast_value(zv_s + zsel * 256, ch, tanhf(f) * (1.f / (1.f + expf(-gg))), zbar);   // wavenet.py:351
+          bcast_value(zv_s + zsel * 256, ch, tanhf(f) * (1.f / (1.f + expf(-gg))), zsel ? zbar1 : zbar0);   // wavenet.py:351
         }
       }
+      const float xring = tid < 8 ? xv[8 * rank + tid] : 0.f;   // this CTA's ring slice, read before xv is updated below
       TRG(l, 2);
-      exchange_wait(zbar, zph, 64 * 4, tid);
+      exchange_wait(zsel ? zbar1 : zbar0, zph[zsel], 64 * 4, tid);
       TRG(l, 3);
-      zph ^= 1;
-      const float xring = tid < 8 ? xv[8 * rank + tid] : 0.f;   // read before this CTA's own x_out lands on top of it
-      TRG(l, 8);
-      if (tid < 160) {
+      zph[zsel] ^= 1;
+      if (tid < 192) {
         const float4* wb = wst + V4_WA_F / 4;
-        float a4[4];
+        float a4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {                   // four independent chains
-          const float4 w = wb[q * 160 + tid];
-          const float4 z = *reinterpret_cast<const float4*>(zv + zsel * 64 + ksB * 16 + q * 4);
-          a4[q] = w.x * z.x;
-          a4[q] = fmaf(w.y, z.y, a4[q]), a4[q] = fmaf(w.z, z.z, a4[q]), a4[q] = fmaf(w.w, z.w, a4[q]);
+        for (int q = 0; q < 8; ++q) {                   // four independent chains
+          const float4 w = wb[q * 192 + tid];
+          const float4 z = *reinterpret_cast<const float4*>(zv + zsel * 64 + ksB * 32 + q * 4);
+          a4[q & 3] = fmaf(w.x, z.x, a4[q & 3]), a4[q & 3] = fmaf(w.y, z.y, a4[q & 3]);
+          a4[q & 3] = fmaf(w.z, z.z, a4[q & 3]), a4[q & 3] = fmaf(w.w, z.w, a4[q & 3]);
         }
         float acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
-        TRG(l, 9);
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        TRG(l, 10);
         if (ksB == 0) {
-          if (oB < 8) {
-            const int ch = 8 * rank + oB;
-            const float bb = has_bb ? st[bb_off + ch] : 0.f;
-            TRG(l, 6);
-            bcast_value(xv_s, ch, xv[ch] + acc + bb, xbar);                    // output = projection + x, wavenet.py:354
-            TRG(l, 7);
+          if (oB < 64) {
+            const float bb = has_bb ? st[bb_off + oB] : 0.f;
+            xv[oB] += acc + bb;                                                // output = projection + x, wavenet.py:354
           } else {
-            const float bb = has_bb ? st[bb_off + R + 32 * rank + oB - 8] : 0.f;
+            const float bb = has_bb ? st[bb_off + R + 32 * rank + oB - 64] : 0.f;
             skr += acc + bb;                                                   // faster_wavenet.py:100
           }
         }
@@ -1304,15 +1299,14 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
       // x[t-d] at the top of the step: this point is behind the z exchange, hence behind all those reads.
       if (tid < 8) st[ring_slot + 8 * rank + tid] = xring;
       TRG(l, 4);
-      exchange_wait(xbar, xph, 64 * 4, tid);
+      csync4();                           // the new x (identical in every CTA) is complete
       TRG(l, 5);
-      xph ^= 1;
       zsel ^= 1;
     }
     // ---- 4. head (faster_wavenet.py:105-113: ELU on incremental steps; ReLU variant) ----
     TRG(40, 0);
     int hsel = 0;
-    if (tid < 160 && ksB == 0 && oB >= 8) bcast_value(hB_s, 32 * rank + oB - 8, head_act(skr, a.head_elu), hbar0);
+    if (tid < 192 && ksB == 0 && oB >= 64) bcast_value(hB_s, 32 * rank + oB - 64, head_act(skr, a.head_elu), hbar0);
     exchange_wait(hbar0, hph[0], 256 * 4, tid);
     hph[0] ^= 1;
     hsel = 1;
@@ -1390,7 +1384,7 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
 }
 
 // dst[rank][...] <- src [K][N] (generator layout), cut into the per-rank, per-thread order gen_kernel_v4 reads:
-// mode 1: WA (K = 128, N = 128 = a_f | a_g), mode 2: WB (K = 64, N = 320 = residual | skip), mode 3: head (K = N = 256).
+// mode 1: WA (K = 128, N = 128 = a_f | a_g), mode 2: WB (K = 64, N = 320 = residual (all ranks) | skip), mode 3: head.
 __global__ void gen_pack_v4(const float* __restrict__ src, float* __restrict__ dst, int64_t rank_stride, int K, int N,
                             int mode) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1403,16 +1397,15 @@ __global__ void gen_pack_v4(const float* __restrict__ src, float* __restrict__ d
     const int t = ((ch & 7) * 2 + half) * 16 + (k >> 3);
     f4 = ((k & 7) >> 2) * 256 + t;
   } else if (mode == 2) {
-    int o;
+    // residual rows (n < 64) go to EVERY rank (each CTA updates the whole x), skip rows to their owner
+    const int o = n < 64 ? n : 64 + ((n - 64) & 31);
+    const int t = o * 2 + (k >> 5);
+    f4 = ((k & 31) >> 2) * 192 + t;
     if (n < 64) {
-      r = n >> 3;
-      o = n & 7;
-    } else {
-      r = (n - 64) >> 5;
-      o = 8 + ((n - 64) & 31);
+      for (int rr = 0; rr < 8; ++rr) dst[(int64_t)rr * rank_stride + (int64_t)f4 * 4 + comp] = src[idx];
+      return;
     }
-    const int t = o * 4 + (k >> 4);
-    f4 = ((k & 15) >> 2) * 160 + t;
+    r = (n - 64) >> 5;
   } else {
     r = n >> 5;
     const int t = (n & 31) * 8 + (k >> 5);
@@ -1650,7 +1643,7 @@ extern "C" int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen**
   for (int i = 0; i < L.n_head && g->v4_ok; ++i) g->v4_ok = L.head_ch[i] == 256;
   for (int l = 0; l < L.L && g->v4_ok; ++l) g->v4_ok = g->layers[l].ring_len > 0;
   if (g->v4_ok) {
-    L.wpk4_rank = (int64_t)L.L * (2 * 256 * 4 + 4 * 160 * 4) + (int64_t)L.n_head * (8 * 256 * 4);
+    L.wpk4_rank = (int64_t)L.L * (2 * 256 * 4 + 8 * 192 * 4) + (int64_t)L.n_head * (8 * 256 * 4);
     L.wpk4 = take(L.wpk4_rank * V4_CS_HOST);
   }
   L.maxw = (maxw + 3) / 4 * 4;
