@@ -389,7 +389,7 @@ def main():
             sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
             clustered = n <= 15          # gen_kernel_v4: one 8-CTA cluster per stream while all clusters are co-resident
             n_ctas = 8 * n if clustered else -(-n // (1 if n <= 148 else 2))
-            per_cta = 1270272 * 4 / 8 if clustered else 1270272 * 4   # bytes of packed fp32 weights per CTA per step
+            per_cta = 32 * 32768 if clustered else 1270272 * 4   # bytes of packed fp32 weights per CTA per step
             gen["batch_%d" % n_total] = {
                 "samples_per_s": total_streams * steps / (gms / 1e3), "streams": total_streams, "steps": steps,
                 "us_per_step": us, "cycles_per_sample_per_stream": us * sm_mhz,
@@ -398,7 +398,7 @@ def main():
                 # every CTA streams its share of the 5.08 MB fp32 weight set once per step through its cp.async.bulk ring
                 "weight_stream_gbs_per_sm": per_cta / (us * 1e-6) / 1e9,
                 "weight_stream_gbs_all_ctas": n_ctas * world * per_cta / (us * 1e-6) / 1e9,
-                "bound": ("dependency-chain latency (30 layers x 2 cluster exchanges + head per sample)" if clustered else
+                "bound": ("dependency-chain latency (30 layers x 1 cluster exchange + head per sample)" if clustered else
                           "dependency-chain latency (30 layers x 2 block barriers + head per sample)")}
         line["fast_gen"] = gen
 

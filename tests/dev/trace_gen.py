@@ -21,6 +21,6 @@ t0 = tr[41][0]
 print("step start -> layers start:", tr[41][1] - t0)
 for l in (0, 1, 2, 10, 11, 28, 29):
     r = tr[l]
-    print("layer %2d: start %6d | weights wait %4d | phase A + send %4d | z wait %4d | phase B + send %4d | x wait %4d" %
-          (l, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4]), "| B: ring store %d, dot %d, shuffles %d, bias+residual %d, send %d" % (r[8] - r[3], r[9] - r[8], r[10] - r[9], r[6] - r[10], r[7] - r[6]))
+    print("layer %2d: start %6d | weights wait %4d | phase A + send %4d | z wait %4d | phase B (x update, skip) %4d | block barrier %4d" %
+          (l, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4]))
 print("layers total:", tr[40][0] - tr[41][1], " head:", tr[40][1] - tr[40][0], " step:", tr[40][1] - t0)
