@@ -359,6 +359,42 @@ def test_streamed_generator_many_streams(n):
     assert bad_streams <= 0.01, bad_streams
 
 
+@pytest.mark.parametrize("n", [1, 5, 13])
+def test_cluster_generator_matches_single_cta_kernel_and_continues(n):
+    """gen_kernel_v4 (one 8-CTA cluster per stream, up to 15 streams) vs gen_kernel_v3 on the same weights: identical
+    greedy sequences; three consecutive wn_gen_run calls continue the state exactly like one long call."""
+    import os
+    from wavenet_b200 import _lib
+    from wavenet_b200._lib import check
+    from wavenet_b200.wavenet import _ptr, _stream
+    cfg = make_cfg("C")
+    w = O.init_weights(cfg, np.random.default_rng(7), np.float32)
+
+    def run(parts, v4):
+        if v4:
+            os.environ.pop("WN_GEN_V4", None)
+        else:
+            os.environ["WN_GEN_V4"] = "0"
+        try:
+            net = make_net(cfg, w, faster=True)
+            window = np.random.default_rng(3).integers(0, 256, (n, O.input_width(cfg))).astype(np.int32)
+            net.prime(window)
+            outs = []
+            for steps in parts:
+                out = torch.empty((n, steps), dtype=torch.int32, device="cuda")
+                check(net._libh.wn_gen_run(net._gen, _ptr(net._params), steps, _lib.WN_GEN_GREEDY, 0, _ptr(out), _stream()))
+                outs.append(out.cpu().numpy())
+            return np.concatenate(outs, axis=1)
+        finally:
+            os.environ.pop("WN_GEN_V4", None)
+
+    a = run([240], True)
+    b = run([77, 63, 100], True)
+    c = run([240], False)
+    assert np.array_equal(a, b)
+    assert np.array_equal(a, c)
+
+
 def test_device_crop_batch_matches_reference_create_batch():
     """train_audio/train.py:14-22 restated vs wn_crop_batch with the same np.random stream."""
     rng = np.random.default_rng(0)
