@@ -1255,15 +1255,17 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
         acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-        const float other = __shfl_xor_sync(0xffffffffu, acc, 16);
-        if (lane == 0) {
-          const int ch = 8 * rank + warp;
-          float f = acc, gg = other;
-          if (has_ba) {
-            f += st[ba_off + ch];
-            gg += st[ba_off + G + ch];
-          }
-          bcast_value(zv_s + zsel * 256, ch, tanhf(f) * (1.f / (1.f + expf(-gg))), zsel ? zbar1 : zbar0);   // wavenet.py:351
+        // lanes 0..15 hold a_f, lanes 16..31 a_g.  z = tanh(a_f) * sigmoid(a_g) (wavenet.py:351) with
+        // sigmoid(g) = 0.5 + 0.5 tanh(g/2): both halves then run the SAME tanhf at the same time instead of tanhf
+        // followed by expf and a division on one thread; lanes 0..7 each send the result to one CTA.
+        const int ch = 8 * rank + warp;
+        float v = lane < 16 ? acc : 0.5f * acc;
+        if (has_ba) v += lane < 16 ? st[ba_off + ch] : 0.5f * st[ba_off + G + ch];
+        const float th = tanhf(v);
+        const float zval = __shfl_sync(0xffffffffu, th, 0) * (0.5f + 0.5f * __shfl_sync(0xffffffffu, th, 16));
+        if (lane < V4_CS) {
+          const uint32_t zb = zsel ? zbar1 : zbar0;
+          st_async_f32(map_to_cta(zv_s + zsel * 256 + 4u * (uint32_t)ch, (uint32_t)lane), zval, map_to_cta(zb, (uint32_t)lane));
         }
       }
       const float xring = tid < 8 ? xv[8 * rank + tid] : 0.f;   // this CTA's ring slice, read before xv is updated below
