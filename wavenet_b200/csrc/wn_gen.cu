@@ -1069,12 +1069,6 @@ __device__ __forceinline__ void st_async_f32(uint32_t addr, float v, uint32_t ba
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// value v of this CTA's output `idx` into buffer `buf` (shared-memory address, same offset in every CTA) of all CTAs;
-// each destination's barrier counts the bytes
-__device__ __forceinline__ void bcast_value(uint32_t buf, int idx, float v, uint32_t bar) {
-#pragma unroll
-  for (uint32_t r = 0; r < V4_CS; ++r) st_async_f32(map_to_cta(buf + 4u * (uint32_t)idx, r), v, map_to_cta(bar, r));
-}
 // one thread per CTA opens the phase (expects `bytes` from the cluster), everybody waits for it
 __device__ __forceinline__ void exchange_wait(uint32_t bar, uint32_t parity, uint32_t bytes, int tid) {
   if (tid == 0) tc::mbar_arrive_expect_tx(bar, bytes);
@@ -1308,7 +1302,16 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
     // ---- 4. head (faster_wavenet.py:105-113: ELU on incremental steps; ReLU variant) ----
     TRG(40, 0);
     int hsel = 0;
-    if (tid < 192 && ksB == 0 && oB >= 64) bcast_value(hB_s, 32 * rank + oB - 64, head_act(skr, a.head_elu), hbar0);
+    if (tid < 192) {                    // the two lanes of a skip group send to four CTAs each
+      const float hv = head_act(__shfl_sync(0xffffffffu, skr, lane & ~1), a.head_elu);
+      if (oB >= 64) {
+#pragma unroll
+        for (uint32_t r = 0; r < 4; ++r) {
+          const uint32_t dst = 4u * (uint32_t)ksB + r;
+          st_async_f32(map_to_cta(hB_s + 4u * (uint32_t)(32 * rank + oB - 64), dst), hv, map_to_cta(hbar0, dst));
+        }
+      }
+    }
     exchange_wait(hbar0, hph[0], 256 * 4, tid);
     hph[0] ^= 1;
     hsel = 1;
@@ -1330,11 +1333,11 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
       acc += __shfl_xor_sync(0xffffffffu, acc, 4);
       const bool last = hi == L.n_head - 1;
-      if (ksH == 0) {
+      {                                 // every lane of the 8-lane group holds the sum: lane ks sends to CTA ks
         const int o = 32 * rank + oH;
         float v = acc + hbias[hi * 256 + o];
         if (!last) v = head_act(v, a.head_elu);
-        bcast_value(hout_s, o, v, hsel ? hbar1 : hbar0);
+        st_async_f32(map_to_cta(hout_s + 4u * (uint32_t)o, (uint32_t)ksH), v, map_to_cta(hsel ? hbar1 : hbar0, (uint32_t)ksH));
       }
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(empty0 + 8 * stage);
