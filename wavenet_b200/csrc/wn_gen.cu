@@ -1070,9 +1070,25 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // one thread per CTA opens the phase (expects `bytes` from the cluster), everybody waits for it
+// The wait acquires at CLUSTER scope: besides the st.async payload it orders this CTA's later reads of the global rings
+// behind the ring stores the peers made before they sent (store -> block barrier -> st.async/complete_tx -> this wait).
 __device__ __forceinline__ void exchange_wait(uint32_t bar, uint32_t parity, uint32_t bytes, int tid) {
   if (tid == 0) tc::mbar_arrive_expect_tx(bar, bytes);
-  tc::mbar_wait(bar, parity);
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++spins > (1u << 24)) {
+      printf("wavenet_b200: generator v4 exchange timeout (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
 }
 
 // Developer trace (make EXTRA=-DWN_LAYER_TRACE, tests/dev/trace_gen.py): clock64 stamps of CTA 0 / thread 0 in step 2
