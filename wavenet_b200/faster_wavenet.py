@@ -8,6 +8,10 @@ Differences from the reference that a caller can observe, all deliberate:
   * n independent streams are accepted (the reference hard-codes batch index 0,
     wavenet.py:286,290,354);
   * `generate()` runs the whole train_audio/generate.py:24-43 loop on the device.
+
+Kernel choice is made by the library (wn_gen.cu): up to 15 streams of the 64/256-channel shape run one 8-CTA
+cluster per stream (latency path), more streams one CTA per one or two streams; any other shape uses the generic
+kernels.  Arithmetic is exact fp32 in every variant.
 """
 import ctypes as C
 
