@@ -175,8 +175,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from oracle import wavenet_oracle as O
-    from wavenet_b200 import _lib
+    from wavenet_b200 import _lib                      # the product arm never touches oracle/ (only cpu_train_sample does)
     from wavenet_b200.wavenet import WaveNet, _ptr, _stream
     from wavenet_b200.faster_wavenet import FasterWaveNet
 
@@ -190,9 +189,7 @@ def main():
 
     B, W = args.batch, args.width
     params = config_c()
-    w = O.init_weights(O.config_C(), np.random.default_rng(1234), np.float32)
-    net = FasterWaveNet(params, seed=0)
-    net.set_weights(w)
+    net = FasterWaveNet(params, seed=1234)             # the facade's own initialiser (LeCunNormal, bias 0, wavenet.py:379-455)
     net.to_gpu(local_rank)
     net.set_precision(args.precision)
     net.data_parallel = world > 1
@@ -339,7 +336,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": eff_prec,
-        "data": "synthetic mu-law indices default_rng(rank), random-init LeCunNormal weights default_rng(1234)",
+        "data": "synthetic mu-law indices default_rng(rank), random-init LeCunNormal weights (facade initialiser, seed 1234)",
         "config": {"workload": "config C (30 layers d=1..512 x3, 64 residual / 256 skip, head 256-256-256), "
                                "%d x %d samples per GPU, full-width teacher-forced train step" % (B, W),
                    "global_batch": B * world, "width": W, "parallelism": "dp%d" % world,
