@@ -79,6 +79,9 @@ typedef void* wn_stream_t;   /* cudaStream_t */
 /* arithmetic of the GEMM-shaped kernels */
 #define WN_PREC_FP32 0   /* SIMT FFMA, exact fp32: the parity path (1e-4 logits) */
 #define WN_PREC_TF32 1   /* tcgen05 kind::tf32, fp32 accumulate in TMEM: the fast path (1e-2 logits) */
+#define WN_PREC_F16X2 2  /* tcgen05 kind::f16 on split operands (v = hi + lo, two fp16 planes, three MMAs per product,
+                          * fp32 accumulate in TMEM): fp32-grade tensor-core path (1e-4 logits, 1e-3 gradients);
+                          * channel counts must be multiples of 64, otherwise the SIMT fp32 kernels run */
 
 const char* wn_last_error(void);
 int wn_version(void);
@@ -91,6 +94,10 @@ int64_t wn_launch_count_add(int64_t n);
  * hyper-parameters (Params.check, wavenet.py:167-173) and builds the layout. */
 int wn_create(const wn_config* cfg, wn_handle** out);
 int wn_destroy(wn_handle* h);
+/* Re-reads the CURRENT CUDA device into the handle (SM count for the persistent grids) -- the counterpart of
+ * cuda.get_device(n).use() + chain.to_gpu() (train_audio/model.py:57-59).  WN_EARCH unless the device is sm_100;
+ * wn_create performs the same check when a device is visible. */
+int wn_set_device_info(wn_handle* h);
 int wn_set_precision(wn_handle* h, int prec);
 int wn_get_precision(const wn_handle* h);
 /* 1 when the residual stack of this network runs on the tcgen05 path under the current precision */

@@ -1,0 +1,136 @@
+"""The CUDA path against outputs of the REFERENCE'S OWN SOURCE.
+
+tests/golden/ref_*.npz hold what /root/reference/{wavenet,faster_wavenet}.py compute when executed (make_ref_golden.py:
+py2->py3 transform + NumPy Chainer stand-in; float32 like Chainer).  Gates are the north star's: logits <= 1e-4 max-abs,
+gradients <= 1e-3 relative, identical greedy sequences; they are applied to the exact-fp32 SIMT path AND to the fp16x2
+tensor-core path.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import wavenet_oracle as O
+from tests.util import digest, digest_err, make_cfg, make_net, rel_err, weights_from_seed
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def load(name):
+    with np.load(os.path.join(GOLD, name)) as f:
+        return {k: f[k] for k in f.files}
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16x2"])
+@pytest.mark.parametrize("tag,name", [("tiny_k2", "tiny_k2"), ("tiny_k3_bias", "tiny_k3_bias"), ("odd", "odd"),
+                                      ("C_small", "C_small"), ("C_small_full", "C_small"), ("B", "B")])
+def test_train_step_matches_executed_reference(tag, name, prec):
+    """train_audio/train.py:62-80 through the reference-named methods: block outputs, logits, loss, loss.backward()
+    gradients and one backprop() step (clip + Adam) vs the executed reference."""
+    gd = load("ref_train_%s.npz" % tag)
+    cfg = make_cfg(name)
+    w = weights_from_seed(cfg, int(gd["seed"]), float(gd["bias_scale"]))
+    T, tpos, full = int(gd["T"]), gd["tpos"], bool(gd["full"])
+    net = make_net(cfg, w)
+    net.set_precision(prec)
+    if prec == "fp16x2" and name in ("C_small", "B"):
+        assert net._libh.wn_tc_active(net._h) == 1, "the tcgen05 path must be the one that runs"
+    net.update_laerning_rate(1e-3)
+    x = gd["x"]
+    out = net.forward_causal_block(x)
+    assert np.abs(out.data.cpu().numpy()[:, :, 0, :][:, :, tpos] - gd["causal"]).max() < 2e-5
+    out, skip = net.forward_residual_block(out)
+    assert np.abs(out.data.cpu().numpy()[:, :, 0, :][:, :, tpos] - gd["out"]).max() < 2e-5
+    assert np.abs(skip.data.cpu().numpy()[:, :, 0, :][:, :, tpos] - gd["sum_skip"]).max() < 2e-5
+    W = x.shape[1]
+    if W - T >= 1:
+        skip = net.slice_1d(skip, W - T)
+    logits = net.forward_softmax_block(skip, apply_softmax=False)
+    assert np.abs(logits.data.cpu().numpy()[:, :, 0, :] - gd["logits"]).max() < 1e-4
+    loss = net.cross_entropy(logits, gd["target"])
+    assert abs(float(loss.data) - float(gd["loss"])) < 1e-5
+    net.backward()
+    g = net.get_grads()
+    bad = {}
+    for k in w:
+        want = gd["g:" + k]
+        if full:
+            if np.abs(want).max() == 0:
+                assert np.abs(g[k]).max() == 0, k
+            elif rel_err(g[k], want) >= 1e-3:
+                bad[k] = rel_err(g[k], want)
+        else:
+            if want[0] == 0:
+                assert np.abs(g[k]).max() == 0, k
+            elif digest_err(digest(k, g[k]), want) >= 1e-3:
+                bad[k] = digest_err(digest(k, g[k]), want)
+    assert not bad, bad
+    net.update()
+    w2 = net.get_weights()
+    for k in w:
+        if full:
+            assert np.abs(w2[k] - gd["u:" + k]).max() < 2e-5, k
+        else:
+            assert digest_err(digest(k, w2[k].astype(np.float64) - w[k]), gd["u:" + k]) < 1e-2, k
+
+
+@pytest.mark.parametrize("tag,name", [("tiny_k2", "tiny_k2"), ("tiny_k3_bias", "tiny_k3_bias"), ("C_small", "C_small")])
+def test_fast_generation_matches_executed_reference(tag, name):
+    """generate.py:24-43 (greedy) through FasterWaveNet: the device loop reproduces the sample sequence of the executed
+    faster_wavenet.py (ReLU head on the priming call, ELU afterwards), and the reference-style _forward_one_step calls
+    reproduce its per-step probabilities."""
+    gd = load("ref_gen_%s.npz" % tag)
+    cfg = make_cfg(name)
+    w = weights_from_seed(cfg, int(gd["seed"]), float(gd["bias_scale"]))
+    steps = gd["probs_fast"].shape[0]
+    net = make_net(cfg, w, faster=True, head_act="reference")
+    got = net.generate(gd["window"], steps, mode="greedy").cpu().numpy()
+    assert np.array_equal(got[0], gd["samples_fast"])
+    net2 = make_net(cfg, w, faster=True, head_act="reference")
+    Q, Win = cfg.quantization_steps, O.input_width(cfg)
+    audio = gd["window"][0].copy()
+    for s in range(steps):
+        onehot = O.onehot_pixel_image(audio[-Win:].reshape(1, -1), Q)
+        p = net2._forward_one_step(onehot, apply_softmax=True, as_numpy=True)[0, :, 0, -1]
+        assert np.abs(p - gd["probs_fast"][s]).max() < 1e-5, s
+        audio = np.append(audio, [np.argmax(p)])
+    assert np.array_equal(audio[Win:], gd["samples_fast"])
+    # slow path (forward_one_step over the whole window each sample, ReLU head): last-column probabilities
+    net3 = make_net(cfg, w)
+    audio = gd["window"][0].copy()
+    for s in range(min(steps, 8)):
+        probs = net3.forward_one_step(audio[-Win:].reshape(1, -1), apply_softmax=True, as_numpy=True)
+        assert np.abs(probs[0, :, 0, -1] - gd["probs_slow"][s]).max() < 1e-5, s
+        audio = np.append(audio, [np.argmax(probs[0, :, 0, -1])])
+
+
+def test_mulaw_files_match_executed_reference(tmp_path):
+    """data.load_audio_file / save_audio_file of the product on the same WAVs (host NumPy like the reference), and the
+    device quantiser on the normalised stereo signal: bit for bit."""
+    from scipy.io import wavfile
+    from wavenet_b200 import _lib, data as PD
+    from wavenet_b200.wavenet import _ptr, _stream
+    gd = load("ref_mulaw.npz")
+    wavfile.write(str(tmp_path / "s.wav"), 16000, gd["stereo"])
+    wavfile.write(str(tmp_path / "m.wav"), 16000, gd["mono"])
+    q, sr = PD.load_audio_file(str(tmp_path / "s.wav"))
+    assert sr == int(gd["sr"]) and np.array_equal(q, gd["q_stereo"])
+    q, _ = PD.load_audio_file(str(tmp_path / "m.wav"))
+    assert np.array_equal(q, gd["q_mono"])
+    with np.errstate(all="ignore"):
+        PD.save_audio_file(str(tmp_path / "o.wav"), np.arange(256, dtype=np.int32), 256, format="16bit_pcm", sampling_rate=16000)
+    sr2, pcm = wavfile.read(str(tmp_path / "o.wav"))
+    assert sr2 == int(gd["sr_out"]) and np.array_equal(pcm, gd["pcm_all"])
+    # device quantiser (wn_mulaw_encode) on the normalised signal == the reference's classes before the silence trim
+    lib = _lib.load()
+    sig = gd["stereo"][:, 0].astype(float) / (1 << 15)
+    sd = torch.from_numpy(sig).cuda()
+    qd = torch.empty(sig.size, dtype=torch.int32, device="cuda")
+    _lib.check(lib.wn_mulaw_encode(_ptr(sd), sig.size, 256, _ptr(qd), _stream()))
+    from oracle import data_oracle as D
+    assert np.array_equal(qd.cpu().numpy(), D.mulaw_quantize(sig))
+    assert np.array_equal(D.trim_silence(qd.cpu().numpy()), gd["q_stereo"])

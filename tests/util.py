@@ -50,3 +50,26 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def weights_from_seed(cfg, seed, bias_scale=0.0):
+    """float32 weights the reference-executed fixtures (tests/golden/make_ref_golden.py) were generated with."""
+    w = O.init_weights(cfg, np.random.default_rng(seed), np.float64, bias_scale=bias_scale)
+    return {k: v.astype(np.float32) for k, v in w.items()}
+
+
+def digest(name, a, head=64):
+    """Compact fingerprint of a tensor: [L2 norm, three seeded random projections, first `head` values] in float64.
+    The projections use unit-variance vectors drawn from a generator seeded by the tensor's NAME, so any party can
+    recompute them; compare with digest_close()."""
+    import zlib
+    a = np.asarray(a, dtype=np.float64).reshape(-1)
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    proj = [float(a @ rng.standard_normal(a.size)) for _ in range(3)]
+    return np.concatenate([[np.linalg.norm(a)], proj, a[:head]])
+
+
+def digest_err(got, want):
+    """Relative error of a digest: every entry is measured against the tensor's norm (entry 0)."""
+    scale = max(abs(float(want[0])), 1e-30)
+    return float(np.abs(np.asarray(got) - np.asarray(want)).max() / scale)

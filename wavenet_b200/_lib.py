@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("WN_LIB_PATH") or os.path.join(_HERE, "libwavenet_b200.so")   # override: A/B builds
 
 WN_MAX_CAUSAL, WN_MAX_LAYERS, WN_MAX_HEAD, WN_NAME_LEN = 8, 32, 8, 64
-WN_PREC_FP32, WN_PREC_TF32 = 0, 1
+WN_PREC_FP32, WN_PREC_TF32, WN_PREC_F16X2 = 0, 1, 2
 WN_GEN_GREEDY, WN_GEN_SAMPLE = 0, 1
 
 
@@ -56,6 +56,7 @@ SIGNATURES = {
     "wn_launch_count_add": (_L, [_L]),
     "wn_create": (_I, [C.POINTER(wn_config), C.POINTER(_P)]),
     "wn_destroy": (_I, [_P]),
+    "wn_set_device_info": (_I, [_P]),
     "wn_set_precision": (_I, [_P, _I]),
     "wn_get_precision": (_I, [_P]),
     "wn_tc_active": (_I, [_P]),

@@ -130,13 +130,34 @@ extern "C" int wn_create(const wn_config* c, wn_handle** out) {
     snprintf(buf, sizeof(buf), "softmax_%d", i);
     add_conv(h, buf, c->softmax_channels[i + 1], c->softmax_channels[i], 1, 1, !c->softmax_no_bias, &h->head[i]);
   }
-  int dev = 0;
-  if (cudaGetDevice(&dev) == cudaSuccess) {
-    int sm = 0;
-    if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sm > 0) h->sm_count = sm;
+  // a handle may be created on a host without a GPU (layout queries only); when a device is visible it must be sm_100
+  const int rc = wn_set_device_info(h);
+  if (rc == WN_EARCH) {
+    delete h;
+    return rc;
   }
   cudaGetLastError();
   *out = h;
+  return WN_OK;
+}
+
+extern "C" int wn_set_device_info(wn_handle* h) {
+  WN_REQUIRE(h, WN_EINVAL, "null handle");
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    wn_set_error("no CUDA device is visible");
+    return WN_ECUDA;
+  }
+  int major = 0, sm = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    cudaGetLastError();
+    wn_set_error("cannot query the compute capability of device %d", dev);
+    return WN_ECUDA;
+  }
+  WN_REQUIRE(major == 10, WN_EARCH, "device %d has compute capability %d.x; libwavenet_b200.so holds sm_100a code only", dev,
+             major);
+  if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sm > 0) h->sm_count = sm;
   return WN_OK;
 }
 
@@ -147,7 +168,7 @@ extern "C" int wn_destroy(wn_handle* h) {
 
 extern "C" int wn_set_precision(wn_handle* h, int prec) {
   WN_REQUIRE(h, WN_EINVAL, "null handle");
-  WN_REQUIRE(prec == WN_PREC_FP32 || prec == WN_PREC_TF32, WN_EINVAL, "unknown precision %d", prec);
+  WN_REQUIRE(prec == WN_PREC_FP32 || prec == WN_PREC_TF32 || prec == WN_PREC_F16X2, WN_EINVAL, "unknown precision %d", prec);
   h->prec = prec;
   return WN_OK;
 }
@@ -317,6 +338,7 @@ extern "C" int wn_forward_causal_block(wn_handle* h, const float* params, const 
     WN_CHECK_CUDA(cudaMemcpyAsync(out, WS(t.x[0]), sizeof(float) * t.P * h->R, cudaMemcpyDeviceToDevice, s));
   h->x_idx = x;
   h->causal_from_idx = true;
+  h->x0_split = false;
   h->phase = PH_CAUSAL;
   return WN_OK;
 }
@@ -370,9 +392,27 @@ extern "C" int wn_forward_residual_block(wn_handle* h, const float* params, cons
   if (in) {
     WN_CHECK_CUDA(cudaMemcpyAsync(WS(t.x[0]), in, sizeof(float) * t.P * h->R, cudaMemcpyDeviceToDevice, s));
     h->causal_from_idx = false;
+    h->x0_split = false;
   } else {
     WN_REQUIRE(h->phase >= PH_CAUSAL, WN_ESTATE, "forward_residual_block: no causal output on the tape");
   }
+  const int L = (int)h->layers.size();
+  if (h->prec == WN_PREC_F16X2 && tcs_supported(h)) {
+    // split-fp16 tensor-core path: MMA operands on the tape are [hi | lo] fp16 rows of the same byte size
+    if (!h->x0_split) WN_TRY(tcs_split_rows_inplace(WS(t.x[0]), h->R, t.P, tcs_act_scale(), s));
+    h->x0_split = true;
+    WN_TRY(tcs_forward_residual(h, params, s));
+    h->tape_has_tfsg = false;
+    h->tape_tc = true;
+    h->tape_split = true;
+    if (out) WN_TRY(tcs_unsplit_rows(WS(t.x[L]), out, h->R, t.P, 1.f / tcs_act_scale(), s));
+    if (sum_skip) WN_TRY(tcs_unsplit_rows(WS(t.skip), sum_skip, h->S, t.P, 1.f / tcs_act_scale(), s));
+    h->head_external = false;
+    h->phase = PH_RESIDUAL;
+    return WN_OK;
+  }
+  WN_REQUIRE(!h->x0_split, WN_ESTATE, "forward_residual_block: the causal output on the tape was converted by the fp16x2 path");
+  h->tape_split = false;
   if (h->prec == WN_PREC_TF32 && tc_layer_supported(h)) {
     WN_TRY(tc_forward_residual(h, params, s));
     h->tape_has_tfsg = false;      // tensor-core tapes keep (z, sigmoid) only; the SIMT backward would recompute
@@ -383,7 +423,6 @@ extern "C" int wn_forward_residual_block(wn_handle* h, const float* params, cons
     h->tape_tc = false;
     h->skip_is_relu = false;
   }
-  const int L = (int)h->layers.size();
   if (out) WN_CHECK_CUDA(cudaMemcpyAsync(out, WS(t.x[L]), sizeof(float) * t.P * h->R, cudaMemcpyDeviceToDevice, s));
   if (sum_skip)
     WN_CHECK_CUDA(cudaMemcpyAsync(sum_skip, WS(t.skip), sizeof(float) * t.P * h->S, cudaMemcpyDeviceToDevice, s));
@@ -400,8 +439,13 @@ extern "C" int wn_forward_softmax_block(wn_handle* h, const float* params, const
   const Tape& t = h->tape;
   WN_REQUIRE(T >= 1 && T <= t.W, WN_EINVAL, "softmax block width %d outside 1..%d", T, t.W);
   const int64_t rows = (int64_t)t.B * T;
+  const bool split_head = h->prec == WN_PREC_F16X2 && tcs_supported(h) && (in || h->tape_split);
+  WN_REQUIRE(in || split_head || !h->tape_split, WN_ESTATE, "forward_softmax_block: the tape was written by the fp16x2 path");
   if (in) {  // external (already sliced) input: kept compact at the start of the skip buffer
-    WN_CHECK_CUDA(cudaMemcpyAsync(WS(t.skip), in, sizeof(float) * rows * h->S, cudaMemcpyDeviceToDevice, s));
+    if (split_head)
+      WN_TRY(tcs_import_head_input(h, in, T, s));   // ReLU + hi/lo split on the way in
+    else
+      WN_CHECK_CUDA(cudaMemcpyAsync(WS(t.skip), in, sizeof(float) * rows * h->S, cudaMemcpyDeviceToDevice, s));
     h->head_external = true;
   } else {
     WN_REQUIRE(h->phase >= PH_RESIDUAL, WN_ESTATE, "forward_softmax_block: no skip sum on the tape");
@@ -409,9 +453,13 @@ extern "C" int wn_forward_softmax_block(wn_handle* h, const float* params, const
   }
   h->T = T;
   const int nh = (int)h->head.size();
-  const bool tc_head = h->prec == WN_PREC_TF32 && tc_head_supported(h) && h->S % 32 == 0;
-  if (tc_head) WN_TRY(tc_forward_head(h, params, T, h->head_external, s));
+  const bool tc_head = split_head || (h->prec == WN_PREC_TF32 && tc_head_supported(h) && h->S % 32 == 0);
+  if (split_head)
+    WN_TRY(tcs_forward_head(h, params, T, h->head_external, s));
+  else if (tc_head)
+    WN_TRY(tc_forward_head(h, params, T, h->head_external, s));
   h->head_tc = tc_head;
+  h->head_split = split_head;
   for (int i = 0; i < nh && !tc_head; ++i) {  // ReLU -> 1x1 conv per head layer (wavenet.py:587-590)
     const ConvParam& cp = h->head[i];
     GemmArgs g = base_gemm(rows, T);
@@ -455,6 +503,14 @@ extern "C" int wn_cross_entropy(wn_handle* h, const int32_t* target, float* loss
   const int64_t rows = (int64_t)t.B * h->T;
   WN_TRY(simt_cross_entropy(WS(t.hbuf.back()), target, rows, h->Q, (double*)WS(t.loss_acc), loss, WS(t.dlogits),
                             WS(t.ce_colsum), &h->ce_colsum_valid, h->sm_count, s));
+  if (h->head_split) {
+    // the split backward keeps every gradient tensor in fp16 planes: scale dlogits (<= 1/rows in magnitude) by a power of
+    // two into [8, 16) so that the whole gradient stream sits in the fp16 normal range; weight-gradient reductions undo it
+    int k = 3;
+    while (((int64_t)1 << (k - 3)) < rows) ++k;
+    h->gscale = ldexpf(1.f, k);
+    WN_TRY(tcs_scale_split_dlogits(h, h->T, h->gscale, s));
+  }
   h->phase = PH_LOSS;
   return WN_OK;
 }
@@ -527,6 +583,14 @@ extern "C" int wn_backward(wn_handle* h, const float* params, float* grads, wn_s
   const int64_t P = t.P, rows = (int64_t)t.B * T;
   const int nh = (int)h->head.size();
   WN_CHECK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * h->flat_size, s));
+  if (h->head_split) {
+    WN_REQUIRE(h->prec == WN_PREC_F16X2 && (h->tape_split || h->head_external), WN_ESTATE,
+               "backward: the tape was written by the fp16x2 path; keep that precision selected");
+    WN_TRY(tcs_backward(h, params, grads, s));
+    if (h->head_external) return WN_OK;
+    return causal_backward(h, params, grads, h->bwd_dout, s);
+  }
+  WN_REQUIRE(!h->tape_split, WN_ESTATE, "backward: the tape was written by the fp16x2 path; keep that precision selected");
   if (h->prec == WN_PREC_TF32 && h->tape_tc && h->head_tc && h->save_gates) {
     WN_TRY(tc_backward(h, params, grads, s));
     if (h->head_external) return WN_OK;
@@ -718,7 +782,9 @@ extern "C" int wn_forward_loss(wn_handle* h, const float* params, const int32_t*
 }
 
 extern "C" int wn_tc_active(const wn_handle* h) {
-  return h && h->prec == WN_PREC_TF32 && tc_layer_supported(h) ? 1 : 0;
+  if (!h) return 0;
+  if (h->prec == WN_PREC_F16X2) return tcs_supported(h) ? 1 : 0;
+  return h->prec == WN_PREC_TF32 && tc_layer_supported(h) ? 1 : 0;
 }
 
 extern "C" int64_t wn_optim_scratch_bytes(const wn_handle* h) { return h ? 256 : WN_EINVAL; }

@@ -114,6 +114,11 @@ struct wn_handle {
   bool skip_is_relu = false;
   bool save_gates = true;          // tensor-core forward also stores tanh | sigmoid (needed by backward)
   const float* bwd_dout = nullptr; // gradient w.r.t. the causal output after the residual backward
+  // split-fp16 path (wn_tcs.cu): MMA operands on the tape are [hi | lo] fp16 rows
+  bool tape_split = false;         // x / z / skip on the tape are split rows (written by tcs_forward_residual)
+  bool head_split = false;         // head activations + dlogits are split rows (tcs_forward_head)
+  bool x0_split = false;           // x[0] has already been converted in place
+  float gscale = 1.f;              // power-of-two scale of every gradient tensor of the split backward
   bool ce_colsum_valid = false;    // tape.ce_colsum matches tape.dlogits (set by wn_cross_entropy)
 };
 
@@ -196,3 +201,14 @@ int tc_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s)
 int simt_colsum(const float* a, int64_t rows, int C, float* out, cudaStream_t s);
 int simt_gate_backward_zs(const float* z, const float* sg, int sg_half, const float* dz, float* dafg, int64_t P, int W, int G, int zp,
                           cudaStream_t s);
+
+// ---- tcgen05 split-fp16 kernels (wn_tcs.cu): fp32-grade arithmetic, three kind::f16 MMAs per product ----------
+bool tcs_supported(const wn_handle* h);
+float tcs_act_scale();   // power-of-two scale carried by every stored activation of the split tape
+int tcs_split_rows_inplace(float* x, int C, int64_t rows, float scale, cudaStream_t s);
+int tcs_unsplit_rows(const float* src_split, float* dst, int C, int64_t rows, float scale, cudaStream_t s);
+int tcs_import_head_input(wn_handle* h, const float* in, int T, cudaStream_t s);
+int tcs_forward_residual(wn_handle* h, const float* params, cudaStream_t s);
+int tcs_forward_head(wn_handle* h, const float* params, int T, bool external, cudaStream_t s);
+int tcs_scale_split_dlogits(wn_handle* h, int T, float gscale, cudaStream_t s);
+int tcs_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s);

@@ -339,10 +339,10 @@ __global__ void gate_backward_zs_kernel(const float* __restrict__ z, const float
   }
   const float4 d = *reinterpret_cast<const float4*>(dz + p * G + g4);
   float4 df, dg;
-  df.x = d.x * (s.x - zz.x * zz.x / s.x), dg.x = d.x * zz.x * (1.f - s.x);
-  df.y = d.y * (s.y - zz.y * zz.y / s.y), dg.y = d.y * zz.y * (1.f - s.y);
-  df.z = d.z * (s.z - zz.z * zz.z / s.z), dg.z = d.z * zz.z * (1.f - s.z);
-  df.w = d.w * (s.w - zz.w * zz.w / s.w), dg.w = d.w * zz.w * (1.f - s.w);
+  df.x = d.x * (s.x > 0.f ? s.x - zz.x * zz.x / s.x : 0.f), dg.x = d.x * zz.x * (1.f - s.x);
+  df.y = d.y * (s.y > 0.f ? s.y - zz.y * zz.y / s.y : 0.f), dg.y = d.y * zz.y * (1.f - s.y);
+  df.z = d.z * (s.z > 0.f ? s.z - zz.z * zz.z / s.z : 0.f), dg.z = d.z * zz.z * (1.f - s.z);
+  df.w = d.w * (s.w > 0.f ? s.w - zz.w * zz.w / s.w : 0.f), dg.w = d.w * zz.w * (1.f - s.w);
   if (t < zp) df = dg = make_float4(0.f, 0.f, 0.f, 0.f);
   *reinterpret_cast<float4*>(dafg + p * 2 * G + g4) = df;
   *reinterpret_cast<float4*>(dafg + p * 2 * G + G + g4) = dg;

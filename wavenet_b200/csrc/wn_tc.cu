@@ -118,6 +118,10 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return y;
 }
 
+// sigmoid * (1 - tanh^2) rebuilt from z = tanh * sigmoid and the stored sigmoid.  A saturated gate stores sigmoid == 0
+// (fp16 flushes below ~3e-8) while z may still be a tiny non-zero: the derivative is 0 there, not z*z/0.
+__device__ __forceinline__ float gate_dtanh(float z, float sg) { return sg > 0.f ? sg - __fdividef(z * z, sg) : 0.f; }
+
 // Coalesced store of a 32-row x 32-column fp32 block held row-per-lane (lane r owns row r): the block goes
 // through a 2 KB per-warp XOR-swizzled staging buffer, 16 rows at a time, so that every STG.128 covers four
 // complete 128-byte rows instead of 32 partial sectors.
@@ -590,10 +594,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             const float4 z = z4[jj], sg = sg4[jj];
             const float live = t >= a.gate_zp ? 1.f : 0.f;
             float4 df, dg;
-            df.x = live * o.x * (sg.x - __fdividef(z.x * z.x, sg.x)), dg.x = live * o.x * z.x * (1.f - sg.x);
-            df.y = live * o.y * (sg.y - __fdividef(z.y * z.y, sg.y)), dg.y = live * o.y * z.y * (1.f - sg.y);
-            df.z = live * o.z * (sg.z - __fdividef(z.z * z.z, sg.z)), dg.z = live * o.z * z.z * (1.f - sg.z);
-            df.w = live * o.w * (sg.w - __fdividef(z.w * z.w, sg.w)), dg.w = live * o.w * z.w * (1.f - sg.w);
+            df.x = live * o.x * gate_dtanh(z.x, sg.x), dg.x = live * o.x * z.x * (1.f - sg.x);
+            df.y = live * o.y * gate_dtanh(z.y, sg.y), dg.y = live * o.y * z.y * (1.f - sg.y);
+            df.z = live * o.z * gate_dtanh(z.z, sg.z), dg.z = live * o.z * z.z * (1.f - sg.z);
+            df.w = live * o.w * gate_dtanh(z.w, sg.w), dg.w = live * o.w * z.w * (1.f - sg.w);
             float* drow = a.gate_dafg + orow * (2 * a.N);
             *reinterpret_cast<float4*>(drow + col) = df;
             *reinterpret_cast<float4*>(drow + a.N + col) = dg;
@@ -1232,10 +1236,10 @@ tc_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         const float4 z = z4[jj], sg = sg4[jj];
         const float live = t >= a.zp ? 1.f : 0.f;
         float4 df, dg;
-        df.x = live * o.x * (sg.x - __fdividef(z.x * z.x, sg.x)), dg.x = live * o.x * z.x * (1.f - sg.x);
-        df.y = live * o.y * (sg.y - __fdividef(z.y * z.y, sg.y)), dg.y = live * o.y * z.y * (1.f - sg.y);
-        df.z = live * o.z * (sg.z - __fdividef(z.z * z.z, sg.z)), dg.z = live * o.z * z.z * (1.f - sg.z);
-        df.w = live * o.w * (sg.w - __fdividef(z.w * z.w, sg.w)), dg.w = live * o.w * z.w * (1.f - sg.w);
+        df.x = live * o.x * gate_dtanh(z.x, sg.x), dg.x = live * o.x * z.x * (1.f - sg.x);
+        df.y = live * o.y * gate_dtanh(z.y, sg.y), dg.y = live * o.y * z.y * (1.f - sg.y);
+        df.z = live * o.z * gate_dtanh(z.z, sg.z), dg.z = live * o.z * z.z * (1.f - sg.z);
+        df.w = live * o.w * gate_dtanh(z.w, sg.w), dg.w = live * o.w * z.w * (1.f - sg.w);
         float* drow = a.dafg + orow * 128;
         *reinterpret_cast<float4*>(drow + col) = df;
         *reinterpret_cast<float4*>(drow + 64 + col) = dg;

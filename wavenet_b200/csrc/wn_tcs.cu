@@ -1,0 +1,1802 @@
+// Split-fp16 tensor-core path (WN_PREC_F16X2): fp32-grade arithmetic on tcgen05.
+//
+// The reference computes in fp32 end to end (Chainer fp32, wavenet.py:515-519).  A single tensor-core pass in
+// tf32/fp16 keeps 11 significand bits per operand, which misses the 1e-4 logit / 1e-3 gradient gates.  Here every
+// MMA operand is held as TWO fp16 planes, v = hi + lo with hi = fp16(v), lo = fp16(v - hi) (22 significand bits),
+// and every product is three kind::f16 MMAs into the same TMEM accumulator:
+//     A.B  ~=  A_hi.B_hi + A_hi.B_lo + A_lo.B_hi          (the dropped A_lo.B_lo term is 2^-24 relative)
+// A "split row" [hi(C) | lo(C)] is 4C bytes -- exactly the bytes of the fp32 row it replaces -- so HBM traffic,
+// shared-memory footprint and the TMA tiling equal the tf32 path's; only the MMA count is 1.5x (kind::f16 runs at
+// twice the tf32 rate).  Because both planes are plain fp16 [rows x 128 B] tiles, ONE shared-memory image serves as the
+// K-major operand of a data GEMM and as the MN-major operand of the weight-gradient GEMM.
+// Power-of-two scales keep both planes inside the fp16 NORMAL range (a subnormal lo plane would cap the precision at
+// 2^-25 absolute instead of 2^-24 relative): stored activations carry ACT_SCALE, prepared weights W_SCALE, gradient
+// tensors h->gscale (chosen from B*T by wn_cross_entropy).  Every epilogue / reduction multiplies the accumulator by the
+// reciprocal product (exact), so the scales never show outside this file.
+//
+//  tcs_layer_kernel : one residual layer (wavenet.py:358-368, dilated conv of :294-342 in closed form) per launch
+//  tcs_gemm_kernel  : Y = epi(sum_slab A_slab . W^T)   (skip sum, head, data gradients, gate derivative epilogue)
+//  tcs_wgrad_kernel : dW = dY^T . X                    (all weight gradients)
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "wn_common.h"
+#include "wn_tc.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int TM = 128;          // positions per tile (UMMA M)
+constexpr int KB = 64;           // fp16 elements per 128-byte swizzle row
+constexpr int SUB = TM * 128;    // bytes of a [128 x 64] fp16 sub-tile
+constexpr int NTHREADS = 64 + 256;   // producer warp, MMA warp, 8 epilogue warps
+constexpr int MAX_SLABS = 32;
+constexpr float ACT_SCALE = 8.f;       // x, z, skip, head activations: |v| up to 8188 representable
+constexpr float W_SCALE = 16.f;        // weights: |w| up to 4094 representable; lo planes are normal down to |w| = 0.016
+constexpr float INV_ACT = 1.f / ACT_SCALE, INV_W = 1.f / W_SCALE, INV_ACT_W = 1.f / (ACT_SCALE * W_SCALE);
+
+// Instruction descriptor for kind::f16 with fp16 operands, fp32 accumulate (cute InstrDescriptor: c_format [4,6) = 1,
+// a_format [7,10) = 0 (F16), b_format [10,13) = 0, a_major bit 15, b_major bit 16, n>>3 [17,23), m>>4 [24,29)).
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+constexpr uint32_t IDESC_MN_MAJOR = (1u << 15) | (1u << 16);
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// MN-major fp16 operand, SWIZZLE_128B (cute canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): 64
+// contiguous M/N elements per 128-byte row, 8 K rows per 1024-byte group; LBO = bytes between 64-element M/N atoms,
+// SBO = bytes between 8-row K groups.
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// three MMAs of one K=16 step of a split product (A planes ah/al, B planes bh/bl)
+__device__ __forceinline__ void umma_split(uint32_t d_tmem, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl, uint32_t idesc,
+                                           uint32_t accumulate) {
+  umma_f16(d_tmem, ah, bh, idesc, accumulate);
+  umma_f16(d_tmem, ah, bl, idesc, 1u);
+  umma_f16(d_tmem, al, bh, idesc, 1u);
+}
+
+// ---- hi/lo split of fp32 values ---------------------------------------------------------------
+__device__ __forceinline__ __half2 bits_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+
+// {a, b} -> packed fp16x2 (a in the low half), round to nearest, saturating to +-65504 instead of inf
+__device__ __forceinline__ uint32_t pack_h2_sat(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_h2_sat(a, b);
+  const float2 f = __half22float2(bits_h2(hi));
+  lo = pack_h2_sat(a - f.x, b - f.y);
+}
+__device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
+  split2(v.x, v.y, hi.x, lo.x);
+  split2(v.z, v.w, hi.y, lo.y);
+}
+__device__ __forceinline__ float4 join4(const uint2& hi, const uint2& lo) {
+  const float2 h0 = __half22float2(bits_h2(hi.x)), h1 = __half22float2(bits_h2(hi.y));
+  const float2 l0 = __half22float2(bits_h2(lo.x)), l1 = __half22float2(bits_h2(lo.y));
+  return make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+}
+// value(row, col..col+3) of a split tensor whose rows are [hi(C) | lo(C)]
+__device__ __forceinline__ float4 load_split4(const __half* base, int64_t row, int C, int col) {
+  const __half* p = base + row * (2 * (int64_t)C) + col;
+  return join4(*reinterpret_cast<const uint2*>(p), *reinterpret_cast<const uint2*>(p + C));
+}
+__device__ __forceinline__ float4 scale4(const float4& v, float s) { return make_float4(v.x * s, v.y * s, v.z * s, v.w * s); }
+__device__ __forceinline__ void store_split4(__half* base, int64_t row, int C, int col, const float4& v) {
+  uint2 hi, lo;
+  split4(v, hi, lo);
+  __half* p = base + row * (2 * (int64_t)C) + col;
+  *reinterpret_cast<uint2*>(p) = hi;
+  *reinterpret_cast<uint2*>(p + C) = lo;
+}
+
+// fp32-grade gate nonlinearities (expf with full argument reduction; absolute error ~1e-7)
+__device__ __forceinline__ float tanh_acc(float x) { return 1.f - __fdividef(2.f, expf(2.f * x) + 1.f); }
+__device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.f, 1.f + expf(-x)); }
+
+// gate derivative from (z = tanh * sg, sg):  da_f = dz * sg * (1 - tanh^2) = dz * (sg - z^2 / sg),
+// da_g = dz * tanh * sg * (1 - sg) = dz * z * (1 - sg).  A saturated gate (sg == 0, hence z == 0) has zero derivative.
+__device__ __forceinline__ void gate_deriv(float dz, float z, float sg, float live, float& df, float& dg) {
+  const float r = sg > 1e-30f ? sg - __fdividef(z * z, sg) : 0.f;
+  df = live * dz * r;
+  dg = live * dz * z * (1.f - sg);
+}
+
+// ------------------------------------------------------------------------------------------
+// weight preparation: split K-major matrices [N][hi(K) | lo(K)] the MMAs consume directly
+//   w1[l][n][tap*R + c]   = (n < G ? Wf : Wg)[n % G][c][tap]      n in [0, 2G)
+//   w2[l][r][g]           = Wp[r][g]
+//   ws[s][l*G + g]        = Ws_l[s][g]
+//   w1t[l][c][slab*2G + n] (slab 0 = current tap), wpt[l][g][r], wst[l*G + g][s]: the transposes for the data gradients
+struct TcsTabEntry {
+  int64_t wf, wg, wp, ws;
+};
+
+__device__ __forceinline__ void put_split(__half* mat, int64_t row, int K, int k, float v) {
+  v *= W_SCALE;
+  uint32_t hi, lo;
+  split2(v, 0.f, hi, lo);          // saturating: a weight beyond the representable range is clamped, never inf / NaN
+  mat[row * 2 * K + k] = __ushort_as_half((unsigned short)(hi & 0xffffu));
+  mat[row * 2 * K + K + k] = __ushort_as_half((unsigned short)(lo & 0xffffu));
+}
+
+__global__ void tcs_prep_kernel(const float* __restrict__ params, const TcsTabEntry* __restrict__ tab, __half* __restrict__ w1,
+                                __half* __restrict__ w2, __half* __restrict__ wsc, __half* __restrict__ w1t,
+                                __half* __restrict__ wpt, __half* __restrict__ wst, int L, int R, int G, int S, int k) {
+  const int l = blockIdx.y;
+  const TcsTabEntry e = tab[l];
+  const int n1 = 2 * G * k * R, n2 = R * G, n3 = S * G;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2 + n3; i += gridDim.x * blockDim.x) {
+    if (i < n1) {
+      const int n = i / (k * R), kk = i % (k * R);
+      const int tap = kk / R, c = kk % R;
+      const float* src = n < G ? params + e.wf : params + e.wg;
+      const float v = src[((int64_t)(n % G) * R + c) * k + tap];
+      put_split(w1 + (int64_t)l * 2 * n1, n, k * R, kk, v);
+      const int slab = (k - 1) - tap;
+      put_split(w1t + (int64_t)l * 2 * n1, c, k * 2 * G, slab * 2 * G + n, v);
+    } else if (i < n1 + n2) {
+      const int j = i - n1;
+      const float v = params[e.wp + j];
+      const int r = j / G, g = j % G;
+      put_split(w2 + (int64_t)l * 2 * n2, r, G, g, v);
+      put_split(wpt + (int64_t)l * 2 * n2, g, R, r, v);
+    } else {
+      const int j = i - n1 - n2;
+      const int sidx = j / G, g = j % G;
+      const float v = params[e.ws + j];
+      put_split(wsc, sidx, L * G, l * G + g, v);
+      put_split(wst, (int64_t)l * G + g, S, sidx, v);
+    }
+  }
+}
+
+// dst[o][hi(I) | lo(I)] = src[o][i]   and   dstT[i][hi(O) | lo(O)] = src[o][i]
+__global__ void tcs_split_weight_kernel(const float* __restrict__ src, __half* __restrict__ dst, __half* __restrict__ dstT, int O,
+                                        int I) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)O * I) return;
+  const int o = (int)(idx / I), i = (int)(idx % I);
+  const float v = src[idx];
+  put_split(dst, o, I, i, v);
+  put_split(dstT, i, O, o, v);
+}
+
+// ---- row-format converters (fp32 <-> split); one thread per (row, 4 channels) -----------------
+// dst row r = scale * [relu](src row (seq * rows_per_seq_in + row_off + t)), r = seq * rows_per_seq + t.
+// In place (dst == src, identity row mapping) is allowed when blockDim.x is a multiple of C/4: a block then owns
+// whole rows and the barrier separates every load of a row from the stores that overwrite it.
+__global__ void tcs_rows_to_split_kernel(const float* src, int rows_per_seq_in, int row_off, __half* dst, int C, int rows_per_seq,
+                                         int64_t rows, int relu, float scale) {
+  const int c4 = C / 4;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i < rows * c4;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  int64_t row = 0;
+  int cc = 0;
+  if (active) {
+    row = i / c4;
+    cc = (int)(i % c4);
+    const int64_t seq = row / rows_per_seq;
+    const int t = (int)(row % rows_per_seq);
+    v = *(reinterpret_cast<const float4*>(src + ((seq * rows_per_seq_in + row_off + t) * (int64_t)C)) + cc);
+  }
+  __syncthreads();
+  if (active) {
+    if (relu) v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+    v.x *= scale, v.y *= scale, v.z *= scale, v.w *= scale;
+    store_split4(dst, row, C, cc * 4, v);
+  }
+}
+
+__global__ void tcs_split_to_rows_kernel(const __half* __restrict__ src, float* __restrict__ dst, int C, int64_t rows, float scale) {
+  const int c4 = C / 4;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * c4) return;
+  const int64_t row = i / c4;
+  const int cc = (int)(i % c4);
+  float4 v = load_split4(src, row, C, cc * 4);
+  v.x *= scale, v.y *= scale, v.z *= scale, v.w *= scale;
+  *(reinterpret_cast<float4*>(dst + row * C) + cc) = v;
+}
+
+// in-place ReLU of split rows (wavenet.py:588); the sign of hi + lo is the sign of hi unless hi == 0
+__global__ void tcs_relu_split_rows_kernel(__half* a, int C, int rows_per_seq_in, int row_off, int rows_per_seq, int64_t rows) {
+  const int c4 = C / 4;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * c4) return;
+  const int64_t row = i / c4;
+  const int cc = (int)(i % c4);
+  const int64_t seq = row / rows_per_seq;
+  const int t = (int)(row % rows_per_seq);
+  const int64_t r = seq * rows_per_seq_in + row_off + t;
+  float4 v = load_split4(a, r, C, cc * 4);
+  v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+  store_split4(a, r, C, cc * 4, v);
+}
+
+// column sums of a split tensor (bias gradients): out[c] += scale * sum_rows a[row][c]
+__global__ void tcs_colsum_kernel(const __half* __restrict__ a, int64_t rows, int C, float scale, float* __restrict__ out) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  __shared__ float red[8][33];
+  float s = 0.f;
+  if (c < C)
+    for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < rows; r += (int64_t)gridDim.y * 8)
+      s += __half2float(a[r * 2 * C + c]) + __half2float(a[r * 2 * C + C + c]);
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int i = 1; i < 8; ++i) s += red[i][threadIdx.x];
+    atomicAdd(out + c, s * scale);
+  }
+}
+
+// generic-shape gate (wavenet.py:360): afg [a_f | a_g] fp32 is overwritten with [tanh | sigmoid]; z leaves in split format
+__global__ void tcs_gate_forward_kernel(float* __restrict__ afg, __half* __restrict__ z, int64_t P, int G) {
+  const int gv = G >> 2;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * gv) return;
+  const int64_t p = i / gv;
+  const int g4 = (int)(i - p * gv) * 4;
+  float* row = afg + p * 2 * G;
+  const float4 af = *reinterpret_cast<const float4*>(row + g4), ag = *reinterpret_cast<const float4*>(row + G + g4);
+  const float4 tf = make_float4(tanhf(af.x), tanhf(af.y), tanhf(af.z), tanhf(af.w));
+  const float4 sg = make_float4(1.f / (1.f + expf(-ag.x)), 1.f / (1.f + expf(-ag.y)), 1.f / (1.f + expf(-ag.z)),
+                                1.f / (1.f + expf(-ag.w)));
+  *reinterpret_cast<float4*>(row + g4) = tf;
+  *reinterpret_cast<float4*>(row + G + g4) = sg;
+  store_split4(z, p, G, g4, make_float4(ACT_SCALE * tf.x * sg.x, ACT_SCALE * tf.y * sg.y, ACT_SCALE * tf.z * sg.z, ACT_SCALE * tf.w * sg.w));
+}
+
+// gate derivative of the TOP layer (no gradient arrives through the residual branch): dz = dzs_l
+__global__ void tcs_gate_backward_top_kernel(const __half* __restrict__ z, const float* __restrict__ sg, int sg_ld,
+                                             const float* __restrict__ dz, __half* __restrict__ dafg, int64_t P, int W, int G,
+                                             int zp) {
+  const int gv = G >> 2;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * gv) return;
+  const int64_t p = i / gv;
+  const int g4 = (int)(i - p * gv) * 4;
+  const float live = (int)(p % W) >= zp ? 1.f : 0.f;
+  const float4 zz = scale4(load_split4(z, p, G, g4), INV_ACT);
+  const float4 s = *reinterpret_cast<const float4*>(sg + p * sg_ld + g4);
+  const float4 d = *reinterpret_cast<const float4*>(dz + p * G + g4);
+  float4 df, dg;
+  gate_deriv(d.x, zz.x, s.x, live, df.x, dg.x);
+  gate_deriv(d.y, zz.y, s.y, live, df.y, dg.y);
+  gate_deriv(d.z, zz.z, s.z, live, df.z, dg.z);
+  gate_deriv(d.w, zz.w, s.w, live, df.w, dg.w);
+  store_split4(dafg, p, 2 * G, g4, df);
+  store_split4(dafg, p, 2 * G, G + g4, dg);
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused residual layer, R = G = 64, k = 2.  Shared memory (same footprint as the tf32 kernel):
+//   B1: W1 split, sub-tiles [128 n x 64 k] indexed (tap, plane)      4 x 16 KB
+//   B2: Wp split, sub-tiles [64 r x 64 g] indexed (plane)            2 x  8 KB
+//   A : 2 stages x 4 sub-tiles: x(t-d) hi, x(t-d) lo, x(t) hi, x(t) lo; z (hi, lo) then overwrites sub-tiles 0,1 as
+//       the A operand of GEMM 2 and the source of its bulk store; the fp32 sigmoid overwrites sub-tiles 2,3 once the
+//       residual is in registers
+struct SLayerArgs {
+  __half* x_out;           // split [B][W][hi 64 | lo 64]
+  int W, d, zp, tiles_per_seq, num_tiles;
+  int reverse;
+};
+
+constexpr int SL_B1 = 0;
+constexpr int SL_B2 = 65536;
+constexpr int SL_A = 81920;
+constexpr int SL_BAR = SL_A + 2 * 65536;
+constexpr int SL_STG = SL_BAR + 256;           // 8 epilogue warps x 2 KB
+constexpr int SL_SMEM = SL_STG + 8 * 2048;
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+tcs_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
+                 const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_z,
+                 const __grid_constant__ CUtensorMap tm_sg, const SLayerArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + SL_BAR;
+  const uint32_t b_full = bar0;
+  auto a_full = [&](int s) { return bar0 + 8 + 8 * s; };
+  auto d1_full = [&](int s) { return bar0 + 40 + 8 * s; };
+  auto z_full = [&](int s) { return bar0 + 56 + 8 * s; };
+  auto d2_full = [&](int s) { return bar0 + 72 + 8 * s; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + SL_BAR + 128);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(b_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(d1_full(s), 1);
+      mbar_init(z_full(s), 256);
+      mbar_init(d2_full(s), 1);
+    }
+    fence_barrier_init();
+    prefetch_tmap(&tm_x);
+    prefetch_tmap(&tm_w1);
+    prefetch_tmap(&tm_w2);
+    prefetch_tmap(&tm_z);
+    prefetch_tmap(&tm_sg);
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32((const void*)tmem_slot));
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int n_local = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_of = [&](int j) {
+    const int i = (int)blockIdx.x + j * (int)gridDim.x;
+    return a.reverse ? a.num_tiles - 1 - i : i;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(b_full, 81920);
+      // x rows are [hi 64 | lo 64] halves: plane p starts at element p*64.  W1 rows are [hi 128 | lo 128].
+      for (int tap = 0; tap < 2; ++tap)
+        for (int p = 0; p < 2; ++p) tma_load_2d(base + SL_B1 + (tap * 2 + p) * SUB, &tm_w1, b_full, p * 128 + tap * KB, 0);
+      for (int p = 0; p < 2; ++p) tma_load_2d(base + SL_B2 + p * 8192, &tm_w2, b_full, p * KB, 0);
+      for (int j = 0; j <= n_local; ++j) {
+        const int s = j & 1;
+        const uint32_t as = base + SL_A + s * 65536;
+        if (j >= 2) {
+          mbar_wait(d2_full(s), ((j - 2) >> 1) & 1);
+          bulk_wait_group_read0();
+        }
+        if (j < n_local) {
+          const int tile = tile_of(j);
+          const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM;
+          mbar_arrive_expect_tx(a_full(s), 65536);
+          tma_load_4d(as + 0 * SUB, &tm_x, a_full(s), 0, t0 - a.d, b, 0);
+          tma_load_4d(as + 1 * SUB, &tm_x, a_full(s), KB, t0 - a.d, b, 0);
+          tma_load_4d(as + 2 * SUB, &tm_x, a_full(s), 0, t0, b, 0);
+          tma_load_4d(as + 3 * SUB, &tm_x, a_full(s), KB, t0, b, 0);
+          if (j + 2 < n_local) {
+            const int tp = tile_of(j + 2);
+            const int bp = tp / a.tiles_per_seq, tp0 = (tp % a.tiles_per_seq) * TM;
+            tma_prefetch_4d(&tm_x, 0, tp0, bp, 0);
+            tma_prefetch_4d(&tm_x, KB, tp0, bp, 0);
+          }
+        }
+        if (j >= 1) {
+          const int jj = j - 1, s1 = jj & 1, tile = tile_of(jj);
+          const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM;
+          const uint32_t zs = base + SL_A + s1 * 65536;
+          mbar_wait(z_full(s1), (jj >> 1) & 1);
+          tma_store_4d(&tm_z, zs + 0 * SUB, 0, t0, b, 0);      // z hi plane
+          tma_store_4d(&tm_z, zs + 1 * SUB, KB, t0, b, 0);     // z lo plane
+          tma_store_4d(&tm_sg, zs + 2 * SUB, 0, t0, b, 0);     // sigmoid fp32, channels 0..31
+          tma_store_4d(&tm_sg, zs + 3 * SUB, 32, t0, b, 0);    // channels 32..63
+          bulk_commit_group();
+        }
+      }
+      bulk_wait_group0();
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = idesc_f16(128, 128);
+      mbar_wait(b_full, 0);
+      for (int j1 = 0; j1 < n_local; ++j1) {
+        const int s = j1 & 1;
+        if (j1 >= 2) mbar_wait(z_full(s), ((j1 - 2) >> 1) & 1);
+        mbar_wait(a_full(s), (j1 >> 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t as = base + SL_A + s * 65536;
+        // The tensor core accumulates with round-toward-zero: every MMA step loses ~half an ulp OF THE ACCUMULATOR.  The
+        // cross terms (hi.lo, lo.hi) are 2^-11 of the result, so they go first, while the accumulator is still small; only
+        // the hi.hi steps then run at full magnitude (8 truncating steps instead of 24).
+#pragma unroll
+        for (int tap = 0; tap < 2; ++tap)
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint32_t ao = as + tap * 2 * SUB + k4 * 32, bo = base + SL_B1 + tap * 2 * SUB + k4 * 32;
+            umma_f16(tmem + s * 128, umma_desc_k_sw128(ao), umma_desc_k_sw128(bo + SUB), idesc1, (tap | k4) > 0);
+            umma_f16(tmem + s * 128, umma_desc_k_sw128(ao + SUB), umma_desc_k_sw128(bo), idesc1, 1u);
+          }
+#pragma unroll
+        for (int tap = 0; tap < 2; ++tap)
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint32_t ao = as + tap * 2 * SUB + k4 * 32, bo = base + SL_B1 + tap * 2 * SUB + k4 * 32;
+            umma_f16(tmem + s * 128, umma_desc_k_sw128(ao), umma_desc_k_sw128(bo), idesc1, 1u);
+          }
+        umma_commit(d1_full(s));
+      }
+    }
+  } else {
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;     // which 32 of the 64 channels this warp handles
+    const int row = q * 32 + lane;
+    uint8_t* stg = gbase + SL_STG + (warp - 2) * 2048;
+    if (threadIdx.x == 64) mbar_wait(b_full, 0);
+    for (int j = 0; j < n_local; ++j) {
+      const int tile = tile_of(j);
+      const int s = j & 1, ph = (j >> 1) & 1;
+      const int b = tile / a.tiles_per_seq, t = (tile % a.tiles_per_seq) * TM + row;
+      const bool valid = t < a.W;
+      uint8_t* as_g = gbase + SL_A + s * 65536;
+      const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+      // ---- epilogue 1: gate ----
+      mbar_wait(d1_full(s), ph);
+      tcgen05_fence_after();
+      uint32_t f[32], g[32];
+      tmem_ld32(trow + s * 128 + half * 32, f);
+      tmem_ld32(trow + s * 128 + 64 + half * 32, g);
+      // residual ACT_SCALE * x(t) = hi + lo of this thread's row and channels, into registers
+      float xr[32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 hv = *reinterpret_cast<const uint4*>(as_g + 2 * SUB + sw128_off(row, half * 4 + c));
+        const uint4 lv = *reinterpret_cast<const uint4*>(as_g + 3 * SUB + sw128_off(row, half * 4 + c));
+        const float4 v0 = join4(make_uint2(hv.x, hv.y), make_uint2(lv.x, lv.y));
+        const float4 v1 = join4(make_uint2(hv.z, hv.w), make_uint2(lv.z, lv.w));
+        xr[8 * c + 0] = v0.x, xr[8 * c + 1] = v0.y, xr[8 * c + 2] = v0.z, xr[8 * c + 3] = v0.w;
+        xr[8 * c + 4] = v1.x, xr[8 * c + 5] = v1.y, xr[8 * c + 6] = v1.z, xr[8 * c + 7] = v1.w;
+      }
+      tmem_ld_wait();
+      // the sigmoid tiles below overwrite whole rows of sub-tiles 2 / 3, which hold x(t) of BOTH channel halves: the
+      // partner warp (same rows, other half) must have taken its residual first
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      const bool live = valid && t >= a.zp;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float af = __uint_as_float(f[i]) * INV_ACT_W, ag = __uint_as_float(g[i]) * INV_ACT_W;
+        const float tf = tanh_acc(af), sg = sigmoid_acc(ag);
+        g[i] = __float_as_uint(live ? sg : 0.5f);          // masked rows look like tanh(0) | sigmoid(0)
+        f[i] = __float_as_uint(live ? ACT_SCALE * tf * sg : 0.f);   // z is stored with ACT_SCALE
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {   // z planes: 8 channels per 16-byte chunk
+        uint4 hv, lv;
+        split2(__uint_as_float(f[8 * c + 0]), __uint_as_float(f[8 * c + 1]), hv.x, lv.x);
+        split2(__uint_as_float(f[8 * c + 2]), __uint_as_float(f[8 * c + 3]), hv.y, lv.y);
+        split2(__uint_as_float(f[8 * c + 4]), __uint_as_float(f[8 * c + 5]), hv.z, lv.z);
+        split2(__uint_as_float(f[8 * c + 6]), __uint_as_float(f[8 * c + 7]), hv.w, lv.w);
+        *reinterpret_cast<uint4*>(as_g + 0 * SUB + sw128_off(row, half * 4 + c)) = hv;
+        *reinterpret_cast<uint4*>(as_g + 1 * SUB + sw128_off(row, half * 4 + c)) = lv;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c)   // sigmoid fp32: 32 channels of this half = one 128-byte row of sub-tile 2 + half
+        *reinterpret_cast<uint4*>(as_g + (2 + half) * SUB + sw128_off(row, c)) =
+            make_uint4(g[4 * c], g[4 * c + 1], g[4 * c + 2], g[4 * c + 3]);
+      fence_proxy_async();
+      tcgen05_fence_before();
+      mbar_arrive(z_full(s));
+      if (threadIdx.x == 64) {
+        // one epilogue thread issues GEMM 2 as soon as every row of z is in shared memory
+        constexpr uint32_t idesc2 = idesc_f16(128, 64);
+        mbar_wait(z_full(s), ph);
+        tcgen05_fence_after();
+        const uint32_t as = base + SL_A + s * 65536;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {   // cross terms first (see GEMM 1)
+          const uint32_t ao = as + k4 * 32, bo = base + SL_B2 + k4 * 32;
+          umma_f16(tmem + 256 + s * 64, umma_desc_k_sw128(ao), umma_desc_k_sw128(bo + 8192), idesc2, k4 > 0);
+          umma_f16(tmem + 256 + s * 64, umma_desc_k_sw128(ao + SUB), umma_desc_k_sw128(bo), idesc2, 1u);
+        }
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const uint32_t ao = as + k4 * 32, bo = base + SL_B2 + k4 * 32;
+          umma_f16(tmem + 256 + s * 64, umma_desc_k_sw128(ao), umma_desc_k_sw128(bo), idesc2, 1u);
+        }
+        umma_commit(d2_full(s));
+      }
+      __syncwarp();
+      // ---- epilogue 2: projection + residual ----
+      mbar_wait(d2_full(s), ph);
+      tcgen05_fence_after();
+      tmem_ld32(trow + 256 + s * 64 + half * 32, g);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      // x_out rows are [hi 64 | lo 64]: this warp owns channels [half*32, half*32+32) of 32 rows.  Stage 16 rows at a
+      // time as [hi 64 B | lo 64 B] so that every 16-byte store instruction covers whole 64-byte segments.
+      {
+        const int t_w0 = (tile % a.tiles_per_seq) * TM + q * 32;
+        __half* gblock = a.x_out + ((int64_t)b * a.W + t_w0) * 128 + half * 32;
+        const int rows_valid = a.W - t_w0;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          if ((lane >> 4) == hh) {
+            const int r = lane & 15;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint4 hv, lv;
+              split2(fmaf(__uint_as_float(g[8 * c + 0]), INV_W, xr[8 * c + 0]), fmaf(__uint_as_float(g[8 * c + 1]), INV_W, xr[8 * c + 1]), hv.x, lv.x);
+              split2(fmaf(__uint_as_float(g[8 * c + 2]), INV_W, xr[8 * c + 2]), fmaf(__uint_as_float(g[8 * c + 3]), INV_W, xr[8 * c + 3]), hv.y, lv.y);
+              split2(fmaf(__uint_as_float(g[8 * c + 4]), INV_W, xr[8 * c + 4]), fmaf(__uint_as_float(g[8 * c + 5]), INV_W, xr[8 * c + 5]), hv.z, lv.z);
+              split2(fmaf(__uint_as_float(g[8 * c + 6]), INV_W, xr[8 * c + 6]), fmaf(__uint_as_float(g[8 * c + 7]), INV_W, xr[8 * c + 7]), hv.w, lv.w);
+              *reinterpret_cast<uint4*>(stg + r * 128 + ((c ^ (r & 7)) << 4)) = hv;
+              *reinterpret_cast<uint4*>(stg + r * 128 + (((4 + c) ^ (r & 7)) << 4)) = lv;
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int rr = jj * 4 + (lane >> 3), ch = lane & 7;
+            const int rowi = hh * 16 + rr;
+            const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
+            // chunk 0..3: hi plane, 4..7: lo plane (64 halves further)
+            if (rowi < rows_valid)
+              *reinterpret_cast<uint4*>(gblock + (int64_t)rowi * 128 + (ch >> 2) * 64 + (ch & 3) * 8) = val;
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
+// Y[(b,t)][n] = epi( sum_slab  A[slab_idx][b][t + slab_row_off][:] . W[n][slab*K ...] ), both operands split.
+// The ring holds plane-stages [A_p 128x64 | B_p BNx64]; K block kb uses two consecutive stages (hi, lo).
+struct SGemmArgs {
+  void* Y;                 // fp32 [rows][ldy] or split [rows][hi(ldy) | lo(ldy)]
+  int ldy, out_split;
+  const float* bias;       // [N] or null
+  int N;                   // valid output columns
+  int relu;
+  float acc_scale;         // multiplies the accumulator (undoes the operand scales)
+  float out_scale;         // multiplies the final result before it is stored (ACT_SCALE for stored activations)
+  float rsd_scale;         // multiplies the residual after loading
+  const void* Rsd;         // residual added to the result (same rows as Y): fp32 [rows][ldr] or split [rows][2*ldr]
+  int ldr, rsd_split;
+  const __half* mask;      // split tensor: result zeroed where mask[(b, mask_row_off + t)][n] <= 0, or null
+  int ldm, mask_rows_in, mask_row_off;
+  int rows_out;
+  int nslab, kblk;         // K = nslab * kblk * 64
+  int a_plane;             // elements between the hi and lo planes of an A row
+  int b_plane;             // elements between the planes of a W row (= total K)
+  int slab_row_off[MAX_SLABS];
+  int slab_idx[MAX_SLABS];
+  int tiles_per_seq, num_tiles, ngroups;
+  int y_slab_cols;         // >0 (fp32 output only): column block c goes to Y + (c / y_slab_cols) * y_slab_stride
+  int64_t y_slab_stride;
+  // gate-backward epilogue (MODE 1, N == G): acc + Rsd is dz; writes da_f | da_g into the split tensor gate_dafg
+  const float* gate_sg;    // [rows][gate_sg_ld] fp32 sigmoid
+  const __half* gate_z;    // split [rows][2N]
+  __half* gate_dafg;       // split [rows][2 * 2N]
+  int gate_zp, gate_sg_ld;
+  int zero_rows_below;
+  int reverse;
+  int flush;               // MODE 4: accumulate K blocks in registers (forward GEMMs; no mask / y_slab / colsum)
+  float* colsum_out;       // MODE 3: += colsum_scale * column sums of the stored result
+  float colsum_scale;
+};
+
+template <int BN>
+struct SGemmCfg {
+  static constexpr int STAGE = SUB + BN * 128;
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int BAR = STAGES * STAGE;
+  static constexpr int STG = BAR + 256;
+  static constexpr int SMEM = STG + 8 * 4096 + 1024 + 1024;
+};
+
+// MODE: 0 generic epilogue, 1 dz + gate derivative, 3 generic + column sums, 4 FLUSH (forward GEMMs): every 64-channel K
+// block is accumulated from zero in TMEM and ADDED TO REGISTERS by the epilogue warps in fp32 round-to-nearest -- the
+// tensor core truncates its accumulator toward zero at every MMA step, which costs ~1e-5 relative on a K = 1920
+// contraction (measured, tests/dev/check_rz.py: 9.7e-6 in one pass, 4.8e-7 flushed per block, 1.7e-6 for an fp32 SGEMM).
+template <int BN, int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const SGemmArgs a) {
+  using Cfg = SGemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + Cfg::BAR;
+  auto full = [&](int s) { return bar0 + 8 * s; };
+  auto empty = [&](int s) { return bar0 + 64 + 8 * s; };
+  auto acc_full = [&](int s) { return bar0 + 128 + 8 * s; };
+  auto acc_empty = [&](int s) { return bar0 + 144 + 8 * s; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + Cfg::BAR + 192);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), 256);
+    }
+    fence_barrier_init();
+    prefetch_tmap(&tm_a);
+    prefetch_tmap(&tm_b);
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32((const void*)tmem_slot));
+  if constexpr (MODE == 3) {
+    if (threadIdx.x < BN) reinterpret_cast<float*>(gbase + Cfg::STG + 8 * 4096)[threadIdx.x] = 0.f;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int n_local = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int kblocks = a.nslab * a.kblk;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int j = 0; j < n_local; ++j) {
+        const int tile = a.reverse ? a.num_tiles - 1 - ((int)blockIdx.x + j * (int)gridDim.x) : (int)blockIdx.x + j * (int)gridDim.x;
+        const int grp = tile % a.ngroups, rt = tile / a.ngroups;
+        const int b = rt / a.tiles_per_seq, t0 = (rt % a.tiles_per_seq) * TM;
+        for (int sl = 0; sl < a.nslab; ++sl)
+          for (int kc = 0; kc < a.kblk; ++kc)
+            for (int p = 0; p < 2; ++p, ++it) {
+              const int s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
+              mbar_wait(empty(s), ph ^ 1);
+              const uint32_t st = base + s * Cfg::STAGE;
+              mbar_arrive_expect_tx(full(s), Cfg::STAGE);
+              tma_load_4d(st, &tm_a, full(s), p * a.a_plane + kc * KB, a.slab_row_off[sl] + t0, b, a.slab_idx[sl]);
+              tma_load_2d(st + SUB, &tm_b, full(s), p * a.b_plane + (sl * a.kblk + kc) * KB, grp * BN);
+            }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_f16(128, BN);
+      int it = 0;
+      if constexpr (MODE == 4) {
+        int c = 0;   // K blocks issued so far: block c accumulates (from zero) into TMEM buffer c & 1
+        for (int j = 0; j < n_local; ++j)
+          for (int kb = 0; kb < kblocks; ++kb, it += 2, ++c) {
+            const int ab = c & 1, aph = (c >> 1) & 1;
+            const int s0 = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
+            const uint32_t sh = base + s0 * Cfg::STAGE, sl = sh + Cfg::STAGE;
+            mbar_wait(acc_empty(ab), aph ^ 1);
+            mbar_wait(full(s0), ph);
+            mbar_wait(full(s0 + 1), ph);
+            tcgen05_fence_after();
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {   // cross terms while the accumulator is small, hi.hi last
+              umma_f16(tmem + ab * BN, umma_desc_k_sw128(sh + k4 * 32), umma_desc_k_sw128(sl + SUB + k4 * 32), idesc, k4 > 0);
+              umma_f16(tmem + ab * BN, umma_desc_k_sw128(sl + k4 * 32), umma_desc_k_sw128(sh + SUB + k4 * 32), idesc, 1u);
+            }
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              umma_f16(tmem + ab * BN, umma_desc_k_sw128(sh + k4 * 32), umma_desc_k_sw128(sh + SUB + k4 * 32), idesc, 1u);
+            umma_commit(empty(s0));
+            umma_commit(empty(s0 + 1));
+            umma_commit(acc_full(ab));
+          }
+      }
+      for (int j = 0; MODE != 4 && j < n_local; ++j) {
+        const int ab = j & 1, aph = (j >> 1) & 1;
+        mbar_wait(acc_empty(ab), aph ^ 1);
+        tcgen05_fence_after();
+        for (int kb = 0; kb < kblocks; ++kb, it += 2) {
+          const int s0 = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;   // STAGES is even: s0 + 1 is the lo stage
+          const uint32_t sh = base + s0 * Cfg::STAGE, sl = sh + Cfg::STAGE;
+          mbar_wait(full(s0), ph);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma_f16(tmem + ab * BN, umma_desc_k_sw128(sh + k4 * 32), umma_desc_k_sw128(sh + SUB + k4 * 32), idesc, (kb | k4) > 0);
+          mbar_wait(full(s0 + 1), ph);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            umma_f16(tmem + ab * BN, umma_desc_k_sw128(sh + k4 * 32), umma_desc_k_sw128(sl + SUB + k4 * 32), idesc, 1u);
+            umma_f16(tmem + ab * BN, umma_desc_k_sw128(sl + k4 * 32), umma_desc_k_sw128(sh + SUB + k4 * 32), idesc, 1u);
+          }
+          umma_commit(empty(s0));
+          umma_commit(empty(s0 + 1));
+        }
+        umma_commit(acc_full(ab));
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    constexpr int CH = BN / 64;   // 32-column chunks per warp
+    uint8_t* stg = gbase + Cfg::STG + (warp - 2) * 4096;   // [32 rows][128 B], 16-byte chunks XOR-swizzled by row
+    const int cc4 = (lane & 7) * 4;
+    const int rsub = lane >> 3;
+    float* cs_smem = reinterpret_cast<float*>(gbase + Cfg::STG + 8 * 4096);
+    if constexpr (MODE == 4) {
+      int c = 0;
+      for (int j = 0; j < n_local; ++j) {
+        const int tile = a.reverse ? a.num_tiles - 1 - ((int)blockIdx.x + j * (int)gridDim.x) : (int)blockIdx.x + j * (int)gridDim.x;
+        const int grp = tile % a.ngroups, rt = tile / a.ngroups;
+        const int b = rt / a.tiles_per_seq, t0 = (rt % a.tiles_per_seq) * TM + q * 32;
+        float acc[CH][32];
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[ch][i] = 0.f;
+        for (int kb = 0; kb < kblocks; ++kb, ++c) {
+          const int ab = c & 1, aph = (c >> 1) & 1;
+          mbar_wait(acc_full(ab), aph);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int ch = 0; ch < CH; ++ch) {
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * BN + (half * CH + ch) * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[ch][i] += __uint_as_float(v[i]);
+          }
+          tcgen05_fence_before();
+          mbar_arrive(acc_empty(ab));
+        }
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) {
+          const int ct = (half * CH + ch) * 32;
+          const int c0 = grp * BN + ct;
+          if (c0 >= a.N) continue;
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc)
+            *reinterpret_cast<float4*>(stg + lane * 128 + ((cc ^ (lane & 7)) << 4)) =
+                make_float4(acc[ch][4 * cc], acc[ch][4 * cc + 1], acc[ch][4 * cc + 2], acc[ch][4 * cc + 3]);
+          __syncwarp();
+          const int col = c0 + cc4;
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.bias) bb = *reinterpret_cast<const float4*>(a.bias + col);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int rr = jj * 4 + rsub;
+            const int t = t0 + rr;
+            if (t >= a.rows_out) continue;
+            const int64_t orow = (int64_t)b * a.rows_out + t;
+            float4 o = scale4(*reinterpret_cast<const float4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4)), a.acc_scale);
+            o.x += bb.x, o.y += bb.y, o.z += bb.z, o.w += bb.w;
+            if (a.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+            if (t < a.zero_rows_below) o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.Rsd) {
+              const float4 r = a.rsd_split ? load_split4(reinterpret_cast<const __half*>(a.Rsd), orow, a.ldr, col)
+                                           : *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.Rsd) + orow * a.ldr + col);
+              o.x = fmaf(r.x, a.rsd_scale, o.x), o.y = fmaf(r.y, a.rsd_scale, o.y);
+              o.z = fmaf(r.z, a.rsd_scale, o.z), o.w = fmaf(r.w, a.rsd_scale, o.w);
+            }
+            if (a.out_split)
+              store_split4(reinterpret_cast<__half*>(a.Y), orow, a.ldy, col, scale4(o, a.out_scale));
+            else
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.Y) + orow * a.ldy + col) = o;
+          }
+          __syncwarp();
+        }
+      }
+    }
+    for (int j = 0; MODE != 4 && j < n_local; ++j) {
+      const int tile = a.reverse ? a.num_tiles - 1 - ((int)blockIdx.x + j * (int)gridDim.x) : (int)blockIdx.x + j * (int)gridDim.x;
+      const int ab = j & 1, aph = (j >> 1) & 1;
+      const int grp = tile % a.ngroups, rt = tile / a.ngroups;
+      const int b = rt / a.tiles_per_seq, t0 = (rt % a.tiles_per_seq) * TM + q * 32;
+      mbar_wait(acc_full(ab), aph);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < CH; ++ch) {
+        const int ct = (half * CH + ch) * 32;          // column inside the TMEM tile
+        const int c0 = grp * BN + ct;                  // output column
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * BN + ct, v);
+        tmem_ld_wait();
+        if (c0 >= a.N) continue;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+              make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        __syncwarp();
+        const int col = c0 + cc4;
+        if constexpr (MODE == 1) {
+          float4 r4[8], z4[8], sg4[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int t = min(t0 + jj * 4 + rsub, a.rows_out - 1);
+            const int64_t orow = (int64_t)b * a.rows_out + t;
+            r4[jj] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.Rsd) + orow * a.ldr + col);
+            z4[jj] = load_split4(a.gate_z, orow, a.N, col);
+            sg4[jj] = *reinterpret_cast<const float4*>(a.gate_sg + orow * a.gate_sg_ld + col);
+          }
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int rr = jj * 4 + rsub;
+            const int t = t0 + rr;
+            if (t >= a.rows_out) continue;
+            const int64_t orow = (int64_t)b * a.rows_out + t;
+            float4 o = scale4(*reinterpret_cast<const float4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4)), a.acc_scale);
+            o.x += r4[jj].x, o.y += r4[jj].y, o.z += r4[jj].z, o.w += r4[jj].w;
+            const float4 z = scale4(z4[jj], INV_ACT), sg = sg4[jj];
+            const float live = t >= a.gate_zp ? 1.f : 0.f;
+            float4 df, dg;
+            gate_deriv(o.x, z.x, sg.x, live, df.x, dg.x);
+            gate_deriv(o.y, z.y, sg.y, live, df.y, dg.y);
+            gate_deriv(o.z, z.z, sg.z, live, df.z, dg.z);
+            gate_deriv(o.w, z.w, sg.w, live, df.w, dg.w);
+            store_split4(a.gate_dafg, orow, 2 * a.N, col, df);
+            store_split4(a.gate_dafg, orow, 2 * a.N, a.N + col, dg);
+          }
+        } else {
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.bias) bb = *reinterpret_cast<const float4*>(a.bias + col);
+          float4 r4[8], x4[8];
+          float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int t = min(t0 + jj * 4 + rsub, a.rows_out - 1);
+            const int64_t orow = (int64_t)b * a.rows_out + t;
+            if (a.Rsd) {
+              if (a.rsd_split)
+                r4[jj] = load_split4(reinterpret_cast<const __half*>(a.Rsd), orow, a.ldr, col);
+              else
+                r4[jj] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.Rsd) + orow * a.ldr + col);
+            }
+            if (a.mask) x4[jj] = load_split4(a.mask, (int64_t)b * a.mask_rows_in + a.mask_row_off + t, a.ldm, col);
+          }
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int rr = jj * 4 + rsub;
+            const int t = t0 + rr;
+            if (t >= a.rows_out) continue;
+            const int64_t orow = (int64_t)b * a.rows_out + t;
+            float4 o = scale4(*reinterpret_cast<const float4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4)), a.acc_scale);
+            o.x += bb.x, o.y += bb.y, o.z += bb.z, o.w += bb.w;
+            if (a.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+            if (t < a.zero_rows_below) o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.Rsd) {
+              o.x = fmaf(r4[jj].x, a.rsd_scale, o.x), o.y = fmaf(r4[jj].y, a.rsd_scale, o.y);
+              o.z = fmaf(r4[jj].z, a.rsd_scale, o.z), o.w = fmaf(r4[jj].w, a.rsd_scale, o.w);
+            }
+            if (a.mask) {
+              o.x = x4[jj].x > 0.f ? o.x : 0.f;
+              o.y = x4[jj].y > 0.f ? o.y : 0.f;
+              o.z = x4[jj].z > 0.f ? o.z : 0.f;
+              o.w = x4[jj].w > 0.f ? o.w : 0.f;
+            }
+            if (a.out_split) {
+              store_split4(reinterpret_cast<__half*>(a.Y), orow, a.ldy, col, scale4(o, a.out_scale));
+            } else {
+              float* ybase = reinterpret_cast<float*>(a.Y);
+              int ycol = col;
+              if (a.y_slab_cols > 0) {
+                ybase += (int64_t)(c0 / a.y_slab_cols) * a.y_slab_stride;
+                ycol = col % a.y_slab_cols;
+              }
+              *reinterpret_cast<float4*>(ybase + orow * a.ldy + ycol) = o;
+            }
+            if constexpr (MODE == 3) csum.x += o.x, csum.y += o.y, csum.z += o.z, csum.w += o.w;
+          }
+          if constexpr (MODE == 3) {
+#pragma unroll
+            for (int o = 8; o < 32; o <<= 1) {
+              csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o);
+              csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
+              csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o);
+              csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
+            }
+            if (lane < 8) {
+              float* c = cs_smem + ct + cc4;
+              atomicAdd(c, csum.x), atomicAdd(c + 1, csum.y), atomicAdd(c + 2, csum.z), atomicAdd(c + 3, csum.w);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tcgen05_fence_before();
+      mbar_arrive(acc_empty(ab));
+    }
+    if constexpr (MODE == 3) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps
+      const int c = threadIdx.x - 64;
+      if (c < BN && c < a.N) atomicAdd(a.colsum_out + c, cs_smem[c] * a.colsum_scale);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
+// Weight gradient: D[128*MH x NB] = sum over positions  dY[p][a_c0 + m] * X_slab[p + off_slab][c], both operands split and
+// MN-major (the reduction dimension -- positions -- is the row index of both tensors in memory).  TMA deposits
+// [KC positions x 64 channels] sub-tiles; one K=16 MMA step consumes two 8-row swizzle groups (SBO 1024 B), 64-channel
+// atoms are one sub-tile apart (LBO).
+struct SWgradArgs {
+  int rows_it, num_seq;
+  int a_row_off, a_c0, a_plane;   // dY: first channel, elements between its planes
+  int nb_slab, nb_sub;            // X slabs (taps or layers) and 64-channel sub-tiles per slab
+  int b_plane;                    // elements between the planes of an X row
+  int b_row_off[4];
+  int ngroups;
+  int b_slab_idx[8][4];
+  float* dW0[8][4];
+  float* dW1[4];
+  int m_split, m_valid;
+  int64_t sn, sk;
+  int chunks_per_seq, num_chunks;
+  int reverse, run, red_mode;
+  float scale;                    // 1 / gscale
+};
+
+template <int NB, int MH>
+struct SWgradCfg {
+  static constexpr int KC = 32;                          // positions per pipeline stage
+  static constexpr int SUBW = KC * 128;                  // bytes of a [KC x 64] sub-tile
+  static constexpr int NSUB = 2 * MH + NB / 64;          // sub-tiles per plane
+  static constexpr int STAGE = 2 * NSUB * SUBW;
+  static constexpr int STAGES = (192 * 1024) / STAGE > 6 ? 6 : (192 * 1024) / STAGE;
+  static constexpr int BAR = STAGES * STAGE;
+  static constexpr int SMEM = BAR + 256 + 1024;
+  static constexpr int TMEM_COLS = MH * NB > 256 ? 512 : (MH * NB > 128 ? 256 : (MH * NB > 64 ? 128 : 64));
+};
+
+template <int NB, int MH>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tcs_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const SWgradArgs a) {
+  using Cfg = SWgradCfg<NB, MH>;
+  constexpr int KC = Cfg::KC, SUBW = Cfg::SUBW, NSUB = Cfg::NSUB;
+  static_assert(Cfg::STAGES * Cfg::STAGE >= 8 * 8192, "epilogue staging needs 64 KB of ring memory");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + Cfg::BAR;
+  auto full = [&](int s) { return bar0 + 8 * s; };
+  auto empty = [&](int s) { return bar0 + 64 + 8 * s; };
+  const uint32_t acc_full = bar0 + 128;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + Cfg::BAR + 192);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tm_a);
+    prefetch_tmap(&tm_b);
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32((const void*)tmem_slot));
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int grp = (int)blockIdx.x % a.ngroups, nrange = (int)gridDim.x / a.ngroups;
+  const int WG_RUN = a.run;
+  const int r0 = (int)blockIdx.x / a.ngroups;
+  int n_local, c_begin = 0;
+  if (WG_RUN > 0) {
+    const int nruns = (a.num_chunks + WG_RUN - 1) / WG_RUN;
+    const int my_runs = r0 < nruns ? (nruns - r0 + nrange - 1) / nrange : 0;
+    n_local = my_runs * WG_RUN;
+    if (my_runs > 0 && r0 + (my_runs - 1) * nrange == nruns - 1) n_local -= nruns * WG_RUN - a.num_chunks;
+  } else {
+    const int per = (a.num_chunks + nrange - 1) / nrange;
+    c_begin = r0 * per;
+    n_local = max(0, min(a.num_chunks, c_begin + per) - c_begin);
+  }
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < n_local; ++it) {
+        const int fwd = WG_RUN > 0 ? (r0 + (it / WG_RUN) * nrange) * WG_RUN + it % WG_RUN : c_begin + it;
+        const int chunk = a.reverse ? a.num_chunks - 1 - fwd : fwd;
+        const int b = chunk / a.chunks_per_seq, t0 = (chunk % a.chunks_per_seq) * KC;
+        const int s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
+        mbar_wait(empty(s), ph ^ 1);
+        const uint32_t st = base + s * Cfg::STAGE;
+        mbar_arrive_expect_tx(full(s), Cfg::STAGE);
+        for (int p = 0; p < 2; ++p) {
+          const uint32_t sp = st + p * NSUB * SUBW;
+#pragma unroll
+          for (int i = 0; i < 2 * MH; ++i)
+            tma_load_4d(sp + i * SUBW, &tm_a, full(s), p * a.a_plane + a.a_c0 + i * KB, a.a_row_off + t0, b, 0);
+          for (int sl = 0; sl < a.nb_slab; ++sl)
+            for (int i = 0; i < a.nb_sub; ++i)
+              tma_load_4d(sp + (2 * MH + sl * a.nb_sub + i) * SUBW, &tm_b, full(s), p * a.b_plane + i * KB, a.b_row_off[sl] + t0, b,
+                          max(a.b_slab_idx[grp][sl], 0));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_local > 0) {
+      constexpr uint32_t idesc = idesc_f16(128, NB) | IDESC_MN_MAJOR;
+      constexpr uint32_t lbo = SUBW, sbo = 1024, kstep = 2048;
+      for (int it = 0; it < n_local; ++it) {
+        const int s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
+        mbar_wait(full(s), ph);
+        tcgen05_fence_after();
+        const uint32_t sh = base + s * Cfg::STAGE, sl = sh + NSUB * SUBW;
+#pragma unroll
+        for (int k16 = 0; k16 < KC / 16; ++k16) {
+          const uint64_t bh = desc_mn_sw128(sh + 2 * MH * SUBW + k16 * kstep, lbo, sbo);
+          const uint64_t bl = desc_mn_sw128(sl + 2 * MH * SUBW + k16 * kstep, lbo, sbo);
+#pragma unroll
+          for (int mh = 0; mh < MH; ++mh)
+            umma_split(tmem + mh * NB, desc_mn_sw128(sh + 2 * mh * SUBW + k16 * kstep, lbo, sbo),
+                       desc_mn_sw128(sl + 2 * mh * SUBW + k16 * kstep, lbo, sbo), bh, bl, idesc, (it | k16) > 0);
+        }
+        umma_commit(empty(s));
+      }
+      umma_commit(acc_full);
+    }
+  } else if (n_local > 0) {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    constexpr int CH = NB / 64;
+    mbar_wait(acc_full, 0);
+    tcgen05_fence_after();
+    const int nb = a.nb_sub * 64;   // channels per slab
+    const float sc = a.scale;
+    uint8_t* stg = gbase + (warp - 2) * 8192;   // every MMA has retired: the ring is free
+    auto row_ptr = [&](int m, int sl) {
+      return m < a.m_split ? a.dW0[grp][sl] + (int64_t)m * a.sn : a.dW1[sl] + (int64_t)(m - a.m_split) * a.sn;
+    };
+    if (a.red_mode == 2) {
+      // two taps interleaved in memory (sk == 2, dW[1] == dW[0] + 1): this warp owns channels [cw, cw+32) of both taps
+#pragma unroll 1
+      for (int mh = 0; mh < MH; ++mh) {
+#pragma unroll 1
+        for (int ch = 0; ch < nb / 64; ++ch) {
+          const int cw = (half * (nb / 64) + ch) * 32;
+          uint32_t v0[32], v1[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + mh * NB + cw, v0);
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + mh * NB + nb + cw, v1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            *reinterpret_cast<uint4*>(stg + lane * 256 + ((k ^ (lane & 7)) << 4)) =
+                make_uint4(v0[2 * k], v1[2 * k], v0[2 * k + 1], v1[2 * k + 1]);
+          __syncwarp();
+#pragma unroll 4
+          for (int jj = 0; jj < 16; ++jj) {
+            const int rr = jj * 2 + (lane >> 4), kk = lane & 15;
+            const int m = mh * 128 + q * 32 + rr;
+            float4 o = *reinterpret_cast<const float4*>(stg + rr * 256 + ((kk ^ (rr & 7)) << 4));
+            o.x *= sc, o.y *= sc, o.z *= sc, o.w *= sc;
+            if (m < a.m_valid) red_add_v4(row_ptr(m, 0) + (int64_t)cw * 2 + kk * 4, o);
+          }
+          __syncwarp();
+        }
+      }
+    } else if (a.red_mode == 1) {
+#pragma unroll 1
+      for (int mh = 0; mh < MH; ++mh) {
+#pragma unroll 1
+        for (int ch = 0; ch < CH; ++ch) {
+          const int c0 = (half * CH + ch) * 32;
+          uint32_t v[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + mh * NB + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          __syncwarp();
+          const int sl = c0 / nb, cbase = c0 % nb;
+          const bool slab_ok = a.b_slab_idx[grp][sl] >= 0;
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int rr = jj * 4 + (lane >> 3), kk = lane & 7;
+            const int m = mh * 128 + q * 32 + rr;
+            float4 o = *reinterpret_cast<const float4*>(stg + rr * 128 + ((kk ^ (rr & 7)) << 4));
+            o.x *= sc, o.y *= sc, o.z *= sc, o.w *= sc;
+            if (m < a.m_valid && slab_ok) red_add_v4(row_ptr(m, sl) + cbase + kk * 4, o);
+          }
+          __syncwarp();
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int mh = 0; mh < MH; ++mh) {
+        const int m = mh * 128 + q * 32 + lane;
+#pragma unroll 1
+        for (int ch = 0; ch < CH; ++ch) {
+          const int c0 = (half * CH + ch) * 32;
+          uint32_t v[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + mh * NB + c0, v);
+          tmem_ld_wait();
+          const int sl = c0 / nb, cbase = c0 % nb;
+          if (m < a.m_valid && a.b_slab_idx[grp][sl] >= 0) {
+            float* wrow = row_ptr(m, sl);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(wrow + (int64_t)(cbase + i) * a.sk, __uint_as_float(v[i]) * sc);
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// fp16 tensor [d3][d2][d1][d0] (d0 contiguous, strides in elements), box [1][1][box1][64], SWIZZLE_128B, zero fill
+int map_h4d(CUtensorMap* m, const __half* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint64_t s1, uint64_t s2,
+            uint64_t s3, uint32_t box1) {
+  EncodeTiledFn enc = get_encode();
+  WN_REQUIRE(enc, WN_ECUDA, "cuTensorMapEncodeTiled is unavailable");
+  cuuint64_t dims[4] = {d0, d1, d2, d3};
+  cuuint64_t strides[3] = {s1 * 2, s2 * 2, s3 * 2};
+  cuuint32_t box[4] = {KB, box1, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  WN_REQUIRE(r == CUDA_SUCCESS, WN_ECUDA, "cuTensorMapEncodeTiled(f16 4d) failed: %d", (int)r);
+  return WN_OK;
+}
+
+int map_h2d(CUtensorMap* m, const __half* ptr, uint64_t d0, uint64_t d1, uint64_t s1, uint32_t box1) {
+  EncodeTiledFn enc = get_encode();
+  WN_REQUIRE(enc, WN_ECUDA, "cuTensorMapEncodeTiled is unavailable");
+  cuuint64_t dims[2] = {d0, d1};
+  cuuint64_t strides[1] = {s1 * 2};
+  cuuint32_t box[2] = {KB, box1};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  WN_REQUIRE(r == CUDA_SUCCESS, WN_ECUDA, "cuTensorMapEncodeTiled(f16 2d) failed: %d", (int)r);
+  return WN_OK;
+}
+
+// fp32 tensor, box [1][1][box1][32] (the sigmoid store of the fused layer kernel)
+int map_f4d(CUtensorMap* m, const float* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2, uint32_t box1) {
+  EncodeTiledFn enc = get_encode();
+  WN_REQUIRE(enc, WN_ECUDA, "cuTensorMapEncodeTiled is unavailable");
+  cuuint64_t dims[4] = {d0, d1, d2, 1};
+  cuuint64_t strides[3] = {s1 * 4, s2 * 4, s2 * d2 * 4};
+  cuuint32_t box[4] = {32, box1, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  WN_REQUIRE(r == CUDA_SUCCESS, WN_ECUDA, "cuTensorMapEncodeTiled(f32 4d) failed: %d", (int)r);
+  return WN_OK;
+}
+
+template <int BN, int MODE>
+int launch_sgemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const SGemmArgs& g, int sm_count, cudaStream_t s) {
+  using Cfg = SGemmCfg<BN>;
+  static bool attr = false;
+  if (!attr) {
+    WN_CHECK_CUDA(cudaFuncSetAttribute(tcs_gemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr = true;
+  }
+  const int grid = g.num_tiles < sm_count ? g.num_tiles : sm_count;
+  tcs_gemm_kernel<BN, MODE><<<grid, NTHREADS, Cfg::SMEM, s>>>(ta, tb, g);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+template <int BN>
+int launch_sgemm(const CUtensorMap& ta, const CUtensorMap& tb, const SGemmArgs& g, int sm_count, cudaStream_t s) {
+  if (g.gate_sg) return launch_sgemm_mode<BN, 1>(ta, tb, g, sm_count, s);
+  if (g.flush) return launch_sgemm_mode<BN, 4>(ta, tb, g, sm_count, s);
+  if (g.colsum_out && g.ngroups == 1) return launch_sgemm_mode<BN, 3>(ta, tb, g, sm_count, s);
+  return launch_sgemm_mode<BN, 0>(ta, tb, g, sm_count, s);
+}
+
+template <int NB, int MH>
+int launch_swgrad(const CUtensorMap& ta, const CUtensorMap& tb, const SWgradArgs& g, int sm_count, cudaStream_t s) {
+  using Cfg = SWgradCfg<NB, MH>;
+  static bool attr = false;
+  if (!attr) {
+    WN_CHECK_CUDA(cudaFuncSetAttribute(tcs_wgrad_kernel<NB, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr = true;
+  }
+  int grid = g.num_chunks * g.ngroups < sm_count ? g.num_chunks * g.ngroups : sm_count;
+  grid -= grid % g.ngroups;
+  tcs_wgrad_kernel<NB, MH><<<grid, NTHREADS, Cfg::SMEM, s>>>(ta, tb, g);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+// One split operand of a slab GEMM: rows of sequence b are A[slab][b][row_off + t][hi(C) | lo(C)]
+struct SOperand {
+  const __half* ptr;
+  int C;            // channels per row (row = 2C halves)
+  int rows_in;      // rows per sequence in memory
+  int num_seq;
+  int nslab;
+  int64_t slab_stride;   // in halves
+};
+
+struct SEpilogue {
+  const float* bias = nullptr;
+  int relu = 0;
+  float acc_scale = 1.f, out_scale = 1.f, rsd_scale = 1.f;
+  const void* Rsd = nullptr;
+  int ldr = 0, rsd_split = 0;
+  const __half* mask = nullptr;
+  int ldm = 0, mask_rows_in = 0, mask_row_off = 0;
+  int y_slab_cols = 0;
+  int64_t y_slab_stride = 0;
+  const float* gate_sg = nullptr;
+  const __half* gate_z = nullptr;
+  __half* gate_dafg = nullptr;
+  int gate_zp = 0, gate_sg_ld = 0;
+  int zero_rows_below = 0;
+  int reverse = 0;
+  int flush = 0;
+  float* colsum_out = nullptr;
+  float colsum_scale = 1.f;
+};
+
+inline __half* HP(float* p) { return reinterpret_cast<__half*>(p); }
+inline const __half* HP(const float* p) { return reinterpret_cast<const __half*>(p); }
+
+// Y[(b, t)][0..N) = epi( sum_s A[slab_idx[s]][b][t + row_off[s]][0..K) . Wt[:, s*K ..]^T ); Wt is split [N][2 * ns*K]
+int tcs_gemm(const wn_handle* h, const SOperand& A, int ns, const int* slab_idx, const int* row_off, int rows_out,
+             const __half* Wt, int N, const SEpilogue& e, void* Y, int ldy, int out_split, cudaStream_t s) {
+  const bool plain = !e.gate_sg && !e.Rsd && !e.mask;
+  WN_REQUIRE(A.C % KB == 0 && N % 64 == 0 && (N <= 256 || plain) && ns <= MAX_SLABS && (e.y_slab_cols == 0 || !out_split),
+             WN_EINVAL, "tcs_gemm: unsupported shape K=%d N=%d slabs=%d", A.C, N, ns);
+  CUtensorMap ta, tb;
+  const int64_t rowe = 2 * (int64_t)A.C;
+  const int64_t sstride = A.nslab > 1 ? A.slab_stride : (int64_t)A.rows_in * A.num_seq * rowe;
+  WN_TRY(map_h4d(&ta, A.ptr, rowe, A.rows_in, A.num_seq, A.nslab, rowe, (uint64_t)A.rows_in * rowe, sstride, TM));
+  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  const int64_t Ktot = (int64_t)ns * A.C;
+  WN_TRY(map_h2d(&tb, Wt, 2 * Ktot, N, 2 * Ktot, BN));
+  SGemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.Y = Y;
+  g.ldy = ldy;
+  g.out_split = out_split;
+  g.bias = e.bias;
+  g.N = N;
+  g.relu = e.relu;
+  g.acc_scale = e.acc_scale;
+  g.out_scale = e.out_scale;
+  g.rsd_scale = e.rsd_scale;
+  g.Rsd = e.Rsd;
+  g.ldr = e.ldr;
+  g.rsd_split = e.rsd_split;
+  g.mask = e.mask;
+  g.ldm = e.ldm;
+  g.mask_rows_in = e.mask_rows_in;
+  g.mask_row_off = e.mask_row_off;
+  g.y_slab_cols = e.y_slab_cols;
+  g.y_slab_stride = e.y_slab_stride;
+  g.gate_sg = e.gate_sg;
+  g.gate_z = e.gate_z;
+  g.gate_dafg = e.gate_dafg;
+  g.gate_zp = e.gate_zp;
+  g.gate_sg_ld = e.gate_sg_ld ? e.gate_sg_ld : N;
+  g.zero_rows_below = e.zero_rows_below;
+  g.reverse = e.reverse;
+  g.flush = e.flush && !e.gate_sg && !e.mask && !e.colsum_out && e.y_slab_cols == 0;
+  g.colsum_out = e.colsum_out;
+  g.colsum_scale = e.colsum_scale;
+  g.rows_out = rows_out;
+  g.nslab = ns;
+  g.kblk = A.C / KB;
+  g.a_plane = A.C;
+  g.b_plane = (int)Ktot;
+  for (int i = 0; i < ns; ++i) {
+    g.slab_row_off[i] = row_off ? row_off[i] : 0;
+    g.slab_idx[i] = slab_idx ? slab_idx[i] : 0;
+  }
+  g.tiles_per_seq = (rows_out + TM - 1) / TM;
+  g.ngroups = (N + BN - 1) / BN;
+  g.num_tiles = g.tiles_per_seq * A.num_seq * g.ngroups;
+  if (BN == 64) return launch_sgemm<64>(ta, tb, g, h->sm_count, s);
+  if (BN == 128) return launch_sgemm<128>(ta, tb, g, h->sm_count, s);
+  return launch_sgemm<256>(ta, tb, g, h->sm_count, s);
+}
+
+// dW[slab](m, c) += scale * sum_{b,t} dY[b][a_row_off + t][a_c0 + m] * X[slab_idx[s]][b][b_row_off[s] + t][c]
+int tcs_wgrad(const wn_handle* h, const SOperand& dY, int a_row_off, int a_c0, int m_valid, const SOperand& X, int nb_slab,
+              const int* b_row_off, const int* b_slab_idx, float* const* dW0, float* const* dW1, int m_split, int rows_it,
+              int64_t sn, int64_t sk, float scale, cudaStream_t s, int ngroups = 1, int reverse = 0) {
+  const int NB = nb_slab * X.C;
+  WN_REQUIRE(X.C % KB == 0 && dY.C % KB == 0 && a_c0 % KB == 0 && (NB == 64 || NB == 128 || NB == 256) && nb_slab <= 4 &&
+                 m_valid <= 256 && ngroups >= 1 && ngroups <= 8 && (ngroups == 1 || !dW1),
+             WN_EINVAL, "tcs_wgrad: unsupported shape X.C=%d slabs=%d M=%d groups=%d", X.C, nb_slab, m_valid, ngroups);
+  const int MH = m_valid > 128 ? 2 : 1;
+  // (the TMA boxes of dY cover 128*MH channels from a_c0; boxes past channel dY.C fetch lo-plane data or zeros into
+  // accumulator rows >= m_valid, which the epilogue never stores)
+  constexpr int WG_KC = 32;
+  CUtensorMap ta, tb;
+  const int64_t rowa = 2 * (int64_t)dY.C, rowx = 2 * (int64_t)X.C;
+  WN_TRY(map_h4d(&ta, dY.ptr, rowa, dY.rows_in, dY.num_seq, 1, rowa, (uint64_t)dY.rows_in * rowa,
+                 (uint64_t)dY.rows_in * dY.num_seq * rowa, WG_KC));
+  const int64_t xstride = X.nslab > 1 ? X.slab_stride : (int64_t)X.rows_in * X.num_seq * rowx;
+  WN_TRY(map_h4d(&tb, X.ptr, rowx, X.rows_in, X.num_seq, X.nslab, rowx, (uint64_t)X.rows_in * rowx, xstride, WG_KC));
+  SWgradArgs g;
+  memset(&g, 0, sizeof(g));
+  g.rows_it = rows_it;
+  g.num_seq = dY.num_seq;
+  g.a_row_off = a_row_off;
+  g.a_c0 = a_c0;
+  g.a_plane = dY.C;
+  g.nb_slab = nb_slab;
+  g.nb_sub = X.C / KB;
+  g.b_plane = X.C;
+  g.ngroups = ngroups;
+  g.reverse = reverse;
+  g.scale = scale;
+  {
+    static const int run_env = getenv("WN_WG_RUN") ? atoi(getenv("WN_WG_RUN")) : 8;
+    g.run = run_env;
+  }
+  bool aligned = sn % 4 == 0;
+  for (int i = 0; i < nb_slab; ++i) {
+    g.b_row_off[i] = b_row_off[i];
+    g.dW1[i] = dW1 ? dW1[i] : nullptr;
+    if (g.dW1[i]) aligned = aligned && ((uintptr_t)g.dW1[i] & 15) == 0;
+    for (int gr = 0; gr < ngroups; ++gr) {
+      g.b_slab_idx[gr][i] = b_slab_idx ? b_slab_idx[gr * nb_slab + i] : 0;
+      g.dW0[gr][i] = dW0[gr * nb_slab + i];
+      if (g.b_slab_idx[gr][i] >= 0) aligned = aligned && ((uintptr_t)g.dW0[gr][i] & 15) == 0;
+    }
+  }
+  g.m_split = m_split;
+  g.m_valid = m_valid;
+  g.sn = sn;
+  g.sk = sk;
+  g.chunks_per_seq = (rows_it + WG_KC - 1) / WG_KC;
+  g.num_chunks = g.chunks_per_seq * dY.num_seq;
+  {
+    const bool taps2 = ngroups == 1 && nb_slab == 2 && sk == 2 && X.C % 64 == 0 && g.dW0[0][1] == g.dW0[0][0] + 1 &&
+                       (!g.dW1[0] || g.dW1[1] == g.dW1[0] + 1) && sn % 4 == 0 && ((uintptr_t)g.dW0[0][0] & 15) == 0 &&
+                       (!g.dW1[0] || ((uintptr_t)g.dW1[0] & 15) == 0);
+    g.red_mode = (sk == 1 && aligned) ? 1 : (taps2 ? 2 : 0);
+  }
+  if (MH == 1) {
+    if (NB == 64) return launch_swgrad<64, 1>(ta, tb, g, h->sm_count, s);
+    if (NB == 128) return launch_swgrad<128, 1>(ta, tb, g, h->sm_count, s);
+    return launch_swgrad<256, 1>(ta, tb, g, h->sm_count, s);
+  }
+  if (NB == 64) return launch_swgrad<64, 2>(ta, tb, g, h->sm_count, s);
+  if (NB == 128) return launch_swgrad<128, 2>(ta, tb, g, h->sm_count, s);
+  return launch_swgrad<256, 2>(ta, tb, g, h->sm_count, s);
+}
+
+inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+bool fused_shape(const wn_handle* h) {
+  if (h->R != 64 || h->cfg.residual_filter_width != 2) return false;
+  for (const ResLayer& l : h->layers)
+    if (l.G != 64) return false;
+  return true;
+}
+
+int tcs_prepare_weights(wn_handle* h, const float* params, cudaStream_t s) {
+  const Tape& t = h->tape;
+  const int L = (int)h->layers.size();
+  if (!h->tc_tab_uploaded) {
+    std::vector<TcsTabEntry> tab(L);
+    for (int l = 0; l < L; ++l) {
+      tab[l].wf = h->layers[l].wf.w_off;
+      tab[l].wg = h->layers[l].wg.w_off;
+      tab[l].wp = h->layers[l].proj.w_off;
+      tab[l].ws = h->layers[l].skip.w_off;
+    }
+    WN_CHECK_CUDA(cudaMemcpyAsync(h->ws + t.tc_tab, tab.data(), sizeof(TcsTabEntry) * L, cudaMemcpyHostToDevice, s));
+    WN_CHECK_CUDA(cudaStreamSynchronize(s));   // tab is a stack temporary
+    h->tc_tab_uploaded = true;
+  }
+  dim3 grid(16, L);
+  tcs_prep_kernel<<<grid, 256, 0, s>>>(params, (const TcsTabEntry*)(h->ws + t.tc_tab), HP(h->ws + t.tc_w1), HP(h->ws + t.tc_w2),
+                                       HP(h->ws + t.tc_ws), HP(h->ws + t.tc_w1t), HP(h->ws + t.tc_wpt), HP(h->ws + t.tc_wst), L,
+                                       h->R, h->layers[0].G, h->S, 2);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+int tcs_layer_launch(wn_handle* h, int l, cudaStream_t s) {
+  const Tape& t = h->tape;
+  const int tiles_per_seq = (t.W + TM - 1) / TM;
+  const int num_tiles = tiles_per_seq * t.B;
+  const int grid = num_tiles < h->sm_count ? num_tiles : h->sm_count;
+  const ResLayer& ly = h->layers[l];
+  CUtensorMap tx, tw1, tw2, tz, tsg;
+  WN_TRY(map_h4d(&tx, HP(h->ws + t.x[l]), 128, t.W, t.B, 1, 128, (uint64_t)t.W * 128, (uint64_t)t.P * 128, TM));
+  WN_TRY(map_h4d(&tz, HP(h->ws + t.z[l]), 128, t.W, t.B, 1, 128, (uint64_t)t.W * 128, (uint64_t)t.P * 128, TM));
+  WN_TRY(map_f4d(&tsg, h->ws + t.tfsg[l], 64, t.W, t.B, 64, (uint64_t)t.W * 64, TM));
+  WN_TRY(map_h2d(&tw1, HP(h->ws + t.tc_w1) + (int64_t)l * 2 * 128 * 128, 256, 128, 256, 128));
+  WN_TRY(map_h2d(&tw2, HP(h->ws + t.tc_w2) + (int64_t)l * 2 * 64 * 64, 128, 64, 128, 64));
+  SLayerArgs a;
+  a.x_out = HP(h->ws + t.x[l + 1]);
+  a.W = t.W;
+  a.d = ly.dilation;
+  a.zp = wn_zero_prefix(t.W, ly.dilation, 2);
+  a.tiles_per_seq = tiles_per_seq;
+  a.num_tiles = num_tiles;
+  a.reverse = getenv("WN_NO_SERP") ? 0 : (l & 1);
+  static bool attr = false;
+  if (!attr) {
+    WN_CHECK_CUDA(cudaFuncSetAttribute(tcs_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM + 1024));
+    attr = true;
+  }
+  tcs_layer_kernel<<<grid, NTHREADS, SL_SMEM + 1024, s>>>(tx, tw1, tw2, tz, tsg, a);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+int tcs_skip_gemm(wn_handle* h, cudaStream_t s) {
+  const Tape& t = h->tape;
+  const int L = (int)h->layers.size();
+  const int G = h->layers[0].G;
+  const int64_t zstride = L > 1 ? t.z[1] - t.z[0] : 0;   // floats
+  for (int l = 1; l < L; ++l)
+    WN_REQUIRE(t.z[l] - t.z[l - 1] == zstride, WN_EINVAL, "z slabs are not equally spaced");
+  int idx[MAX_SLABS], off[MAX_SLABS];
+  for (int l = 0; l < L; ++l) {
+    idx[l] = l;
+    off[l] = 0;
+  }
+  SOperand A{HP(h->ws + t.z[0]), G, t.W, t.B, L, 2 * zstride};
+  SEpilogue e;
+  e.relu = h->fuse_head_relu;        // fused train path: the head's first ReLU (wavenet.py:588) rides on this epilogue
+  e.acc_scale = INV_ACT_W;
+  e.out_scale = ACT_SCALE;
+  e.flush = 1;
+  h->skip_is_relu = h->fuse_head_relu != 0;
+  return tcs_gemm(h, A, L, idx, off, t.W, HP(h->ws + t.tc_ws), h->S, e, h->ws + t.skip, h->S, 1, s);
+}
+
+}  // namespace
+
+// ---- entry points used by wn_api.cu -----------------------------------------------------------------------------
+// Networks whose channel counts are multiples of 64 (one 128-byte row of fp16 per 64 channels): the fused layer kernel
+// for R = G = 64 (BASELINE config C), slab GEMMs + SIMT gate otherwise (e.g. the reference default R256/G128).
+float tcs_act_scale() { return ACT_SCALE; }
+
+bool tcs_supported(const wn_handle* h) {
+  if (h->cfg.residual_filter_width != 2 || h->R % 64 != 0 || h->R > 256 || h->S % 64 != 0 || h->S > 256) return false;
+  const int G = h->layers[0].G;
+  if (G % 64 != 0 || 2 * G > 256 || (int)h->layers.size() > MAX_SLABS) return false;
+  for (const ResLayer& l : h->layers)
+    if (l.G != G || l.wf.b_off >= 0 || l.proj.b_off >= 0 || l.skip.b_off >= 0) return false;
+  for (const ConvParam& c : h->head)
+    if (c.in_ch % 64 != 0 || c.in_ch > 256 || c.out_ch % 64 != 0 || c.out_ch > 256) return false;
+  return get_encode() != nullptr;
+}
+
+// fp32 rows -> split rows in place, scaled (x[0] written by the embedding kernel; dlogits written by the CE kernel)
+int tcs_split_rows_inplace(float* x, int C, int64_t rows, float scale, cudaStream_t s) {
+  const int c4 = C / 4;
+  WN_REQUIRE(C % 4 == 0 && c4 <= 1024 && rows < (1LL << 30), WN_EINVAL, "tcs_split_rows_inplace: bad shape C=%d", C);
+  int bs = 256 - 256 % c4;      // whole rows per block (see the kernel)
+  if (bs < c4) bs = c4;
+  tcs_rows_to_split_kernel<<<nblk(rows * c4, bs), bs, 0, s>>>(x, 1 << 30, 0, HP(x), C, 1 << 30, rows, 0, scale);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+int tcs_unsplit_rows(const float* src_split, float* dst, int C, int64_t rows, float scale, cudaStream_t s) {
+  tcs_split_to_rows_kernel<<<nblk(rows * (C / 4), 256), 256, 0, s>>>(HP(src_split), dst, C, rows, scale);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+// external fp32 head input [B*T][S] -> ReLU -> split rows at the start of the skip buffer
+int tcs_import_head_input(wn_handle* h, const float* in, int T, cudaStream_t s) {
+  const Tape& t = h->tape;
+  const int64_t rows = (int64_t)t.B * T;
+  tcs_rows_to_split_kernel<<<nblk(rows * (h->S / 4), 256), 256, 0, s>>>(in, T, 0, HP(h->ws + t.skip), h->S, T, rows, 1, ACT_SCALE);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+int tcs_forward_residual(wn_handle* h, const float* params, cudaStream_t s) {
+  const Tape& t = h->tape;
+  const int L = (int)h->layers.size();
+  WN_TRY(tcs_prepare_weights(h, params, s));
+  if (fused_shape(h)) {
+    for (int l = 0; l < L; ++l) WN_TRY(tcs_layer_launch(h, l, s));
+    h->tape_gates_zs = true;     // tape keeps (z split, sigmoid fp32 with row stride G)
+  } else {
+    const int R = h->R, G = h->layers[0].G;
+    for (int l = 0; l < L; ++l) {
+      const ResLayer& ly = h->layers[l];
+      SOperand X{HP(h->ws + t.x[l]), R, t.W, t.B, 1, 0};
+      const int sidx[2] = {0, 0};
+      const int roff[2] = {-ly.dilation, 0};
+      SEpilogue e;
+      e.zero_rows_below = wn_zero_prefix(t.W, ly.dilation, 2);
+      e.acc_scale = INV_ACT_W;
+      e.flush = 1;
+      WN_TRY(tcs_gemm(h, X, 2, sidx, roff, t.W, HP(h->ws + t.tc_w1) + (int64_t)l * 2 * (2 * G * 2 * R), 2 * G, e,
+                      h->ws + t.tfsg[l], 2 * G, 0, s));
+      tcs_gate_forward_kernel<<<nblk(t.P * (G / 4), 256), 256, 0, s>>>(h->ws + t.tfsg[l], HP(h->ws + t.z[l]), t.P, G);
+      WN_CHECK_LAUNCH();
+      SOperand Z{HP(h->ws + t.z[l]), G, t.W, t.B, 1, 0};
+      const int zero = 0;
+      SEpilogue e2;
+      e2.Rsd = h->ws + t.x[l];
+      e2.ldr = R;
+      e2.rsd_split = 1;
+      e2.acc_scale = INV_ACT_W;
+      e2.rsd_scale = INV_ACT;
+      e2.out_scale = ACT_SCALE;
+      e2.flush = 1;
+      WN_TRY(tcs_gemm(h, Z, 1, nullptr, &zero, t.W, HP(h->ws + t.tc_w2) + (int64_t)l * 2 * R * G, R, e2, h->ws + t.x[l + 1], R, 1,
+                      s));
+    }
+    h->tape_gates_zs = false;    // tape keeps (tanh | sigmoid) fp32 with row stride 2G, z split
+  }
+  return tcs_skip_gemm(h, s);
+}
+
+// ReLU -> 1x1 conv per head layer (wavenet.py:587-590).  Stored activations are post-ReLU split rows; the last conv
+// writes fp32 logits.
+int tcs_forward_head(wn_handle* h, const float* params, int T, bool external, cudaStream_t s) {
+  const Tape& t = h->tape;
+  const int nh = (int)h->head.size();
+  const int64_t rows = (int64_t)t.B * T;
+  const int rows_in0 = external ? T : t.W, off0 = external ? 0 : t.W - T;
+  if (!h->skip_is_relu && !external) {
+    tcs_relu_split_rows_kernel<<<nblk(rows * (h->S / 4), 256), 256, 0, s>>>(HP(h->ws + t.skip), h->S, rows_in0, off0, T, rows);
+    WN_CHECK_LAUNCH();
+  }
+  for (int i = 0; i < nh; ++i) {
+    const ConvParam& cp = h->head[i];
+    const int64_t n = (int64_t)cp.out_ch * cp.in_ch;
+    tcs_split_weight_kernel<<<nblk(n, 256), 256, 0, s>>>(params + cp.w_off, HP(h->ws + t.tc_wh[i]), HP(h->ws + t.tc_wht[i]),
+                                                       cp.out_ch, cp.in_ch);
+    WN_CHECK_LAUNCH();
+    const bool last = i == nh - 1;
+    SOperand A{i == 0 ? HP(h->ws + t.skip) : HP(h->ws + t.hbuf[i - 1]), cp.in_ch, i == 0 ? rows_in0 : T, t.B, 1, 0};
+    const int off = i == 0 ? off0 : 0;
+    SEpilogue e;
+    e.bias = cp.b_off >= 0 ? params + cp.b_off : nullptr;
+    e.relu = last ? 0 : 1;
+    e.acc_scale = INV_ACT_W;
+    e.out_scale = last ? 1.f : ACT_SCALE;
+    e.flush = 1;
+    WN_TRY(tcs_gemm(h, A, 1, nullptr, &off, T, HP(h->ws + t.tc_wh[i]), cp.out_ch, e, h->ws + t.hbuf[i], cp.out_ch, last ? 0 : 1, s));
+  }
+  return WN_OK;
+}
+
+// Backward of head + residual stack; requires a tape written by tcs_forward_residual and tcs_forward_head and dlogits in
+// split format scaled by h->gscale.
+int tcs_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s) {
+  const Tape& t = h->tape;
+  const int T = h->T, W = t.W, B = t.B;
+  const int64_t P = t.P;
+  const int nh = (int)h->head.size();
+  const int L = (int)h->layers.size();
+  const int R = h->R, G = h->layers[0].G, S = h->S;
+  float* ws = h->ws;
+  const float inv = 1.f / h->gscale;          // gradient tensors carry gscale
+  const float inv_wg = inv * INV_ACT;         // weight gradients: dY (gscale) x activation (ACT_SCALE)
+  const int zero = 0;
+  // ---- head ----
+  const __half* d = HP(ws + t.dlogits);
+  int tog = 0;
+  bool bias_done = false;
+  for (int i = nh - 1; i >= 0; --i) {
+    const ConvParam& cp = h->head[i];
+    const bool first = i == 0;
+    const int rin = first ? (h->head_external ? T : W) : T;
+    const int aoff = first ? (h->head_external ? 0 : W - T) : 0;
+    const __half* Ain = first ? HP(ws + t.skip) : HP(ws + t.hbuf[i - 1]);
+    SOperand dY{d, cp.out_ch, T, B, 1, 0};
+    SOperand X{Ain, cp.in_ch, rin, B, 1, 0};
+    for (int m0 = 0; m0 < cp.out_ch; m0 += 256) {
+      const int mv = cp.out_ch - m0 < 256 ? cp.out_ch - m0 : 256;
+      float* dw = grads + cp.w_off + (int64_t)m0 * cp.in_ch;
+      WN_TRY(tcs_wgrad(h, dY, 0, m0, mv, X, 1, &aoff, nullptr, &dw, nullptr, 256, T, cp.in_ch, 1, inv_wg, s));
+    }
+    if (cp.b_off >= 0 && !bias_done) {
+      if (i == nh - 1 && h->ce_colsum_valid) {
+        WN_TRY(simt_add_vec(ws + t.ce_colsum, grads + cp.b_off, cp.out_ch, s));   // unscaled column sums from the CE kernel
+      } else {
+        dim3 grid(nblk(cp.out_ch, 32), 64), block(32, 8);
+        tcs_colsum_kernel<<<grid, block, 0, s>>>(d, (int64_t)B * T, cp.out_ch, inv, grads + cp.b_off);
+        WN_CHECK_LAUNCH();
+      }
+    }
+    bias_done = false;
+    if (first && h->head_external) return WN_OK;
+    // d_prev = (d . W) masked by the stored (post-ReLU) input
+    SEpilogue e;
+    e.acc_scale = INV_W;
+    e.mask = Ain;
+    e.ldm = cp.in_ch;
+    e.mask_rows_in = rin;
+    e.mask_row_off = aoff;
+    if (i > 0 && h->head[i - 1].b_off >= 0) {
+      e.colsum_out = grads + h->head[i - 1].b_off;
+      e.colsum_scale = inv;
+      bias_done = true;
+    }
+    WN_TRY(tcs_gemm(h, dY, 1, nullptr, &zero, T, HP(ws + t.tc_wht[i]), cp.in_ch, e, ws + t.dh[tog], cp.in_ch, 1, s));
+    d = HP(ws + t.dh[tog]);
+    tog ^= 1;
+  }
+  const __half* dskip = d;   // split [B*T][S]
+  SOperand DS{dskip, S, T, B, 1, 0};
+  const int wt = W - T, nwt = -(W - T);
+  const int64_t zstride = L > 1 ? t.z[1] - t.z[0] : (int64_t)P * G;   // floats
+  // ---- skip path for ALL layers at once ----
+  //  dzs[l] = dskip . Ws_l  (fp32 slabs, read by the gate epilogues only): one GEMM with N = L*G in 256-column groups
+  {
+    SEpilogue e;
+    e.y_slab_cols = G;
+    e.y_slab_stride = (int64_t)P * G;
+    e.acc_scale = INV_W;
+    WN_TRY(tcs_gemm(h, DS, 1, nullptr, &nwt, W, HP(ws + t.tc_wst), L * G, e, ws + t.dzs, G, 0, s));
+  }
+  //  dWs_l = dskip^T . z_l : groups of nl layers per CTA group (dskip read from HBM once)
+  {
+    int nl = 256 / G;
+    if (nl > 4) nl = 4;
+    const int ngr_all = (L + nl - 1) / nl;
+    SOperand Z{HP(ws + t.z[0]), G, W, B, L, 2 * zstride};
+    for (int g0 = 0; g0 < ngr_all; g0 += 8) {
+      const int ngr = ngr_all - g0 < 8 ? ngr_all - g0 : 8;
+      int boff[4], bidx[32];
+      float* dws[32];
+      for (int j = 0; j < nl; ++j) boff[j] = wt;
+      for (int gr = 0; gr < ngr; ++gr)
+        for (int j = 0; j < nl; ++j) {
+          const int l = (g0 + gr) * nl + j;
+          bidx[gr * nl + j] = l < L ? l : -1;
+          dws[gr * nl + j] = l < L ? grads + h->layers[l].skip.w_off : nullptr;
+        }
+      for (int m0 = 0; m0 < S; m0 += 256) {
+        const int mv = S - m0 < 256 ? S - m0 : 256;
+        float* dws_m[32];
+        for (int i = 0; i < ngr * nl; ++i) dws_m[i] = dws[i] ? dws[i] + (int64_t)m0 * G : nullptr;
+        WN_TRY(tcs_wgrad(h, DS, 0, m0, mv, Z, nl, boff, bidx, dws_m, nullptr, 256, T, G, 1, inv_wg, s, ngr));
+      }
+    }
+  }
+  // ---- residual layers ----
+  const bool serp = getenv("WN_NO_SERP") == nullptr;
+  int dt = 0;
+  const __half* dout = nullptr;
+  for (int l = L - 1; l >= 0; --l) {
+    const ResLayer& ly = h->layers[l];
+    const int zp = wn_zero_prefix(W, ly.dilation, 2);
+    const int dir = serp ? (l & 1) : 0, ndir = serp ? !dir : 0;
+    const float* dzs = ws + t.dzs + (int64_t)l * P * G;
+    const float* sg = h->tape_gates_zs ? ws + t.tfsg[l] : ws + t.tfsg[l] + G;
+    const int sg_ld = h->tape_gates_zs ? G : 2 * G;
+    SOperand Z{HP(ws + t.z[l]), G, W, B, 1, 0};
+    __half* dafg = HP(ws + t.dafg);
+    if (dout) {
+      // dz = dout . Wp + dzs_l, gate derivative fused into the epilogue -> dafg
+      SOperand DO{dout, R, W, B, 1, 0};
+      SEpilogue e;
+      e.Rsd = dzs;
+      e.ldr = G;
+      e.acc_scale = INV_W;
+      e.gate_sg = sg;
+      e.gate_sg_ld = sg_ld;
+      e.gate_z = HP(ws + t.z[l]);
+      e.gate_dafg = dafg;
+      e.gate_zp = zp;
+      e.reverse = dir;
+      WN_TRY(tcs_gemm(h, DO, 1, nullptr, &zero, W, HP(ws + t.tc_wpt) + (int64_t)l * 2 * G * R, G, e, nullptr, G, 0, s));
+      // dWp += dout^T . z
+      for (int m0 = 0; m0 < R; m0 += 256) {
+        const int mv = R - m0 < 256 ? R - m0 : 256;
+        float* dw = grads + ly.proj.w_off + (int64_t)m0 * G;
+        WN_TRY(tcs_wgrad(h, DO, 0, m0, mv, Z, 1, &zero, nullptr, &dw, nullptr, 256, W, G, 1, inv_wg, s, 1, ndir));
+      }
+    } else {
+      tcs_gate_backward_top_kernel<<<nblk(P * (G / 4), 256), 256, 0, s>>>(HP(ws + t.z[l]), sg, sg_ld, dzs, dafg, P, W, G, zp);
+      WN_CHECK_LAUNCH();
+    }
+    SOperand DA{dafg, 2 * G, W, B, 1, 0};
+    {
+      // dW_{f,g}(o, c, tap) += da[t][o] * x[t - (1-tap) d][c]; both taps share a launch while 2R fits one N tile
+      SOperand X{HP(ws + t.x[l]), R, W, B, 1, 0};
+      if (2 * R <= 256) {
+        const int boff[2] = {-ly.dilation, 0};
+        float* d0[2];
+        float* d1[2];
+        for (int tap = 0; tap < 2; ++tap) {
+          d0[tap] = grads + ly.wf.w_off + tap;
+          d1[tap] = grads + ly.wg.w_off + tap;
+        }
+        // rows [0, G) of da are da_f, rows [G, 2G) da_g
+        WN_TRY(tcs_wgrad(h, DA, 0, 0, 2 * G, X, 2, boff, nullptr, d0, d1, G, W, 2 * R, 2, inv_wg, s, 1, dir));
+      } else {
+        for (int tap = 0; tap < 2; ++tap) {
+          const int boff = tap == 0 ? -ly.dilation : 0;
+          float* d0 = grads + ly.wf.w_off + tap;
+          float* d1 = grads + ly.wg.w_off + tap;
+          WN_TRY(tcs_wgrad(h, DA, 0, 0, 2 * G, X, 1, &boff, nullptr, &d0, &d1, G, W, 2 * R, 2, inv_wg, s, 1, dir));
+        }
+      }
+    }
+    {
+      // dx[t] = dout[t] + da[t] . W1(tap 1) + da[t + d] . W1(tap 0)
+      __half* dnew = HP(ws + t.dout[dt]);
+      const int roff[2] = {0, ly.dilation};
+      const int sidx[2] = {0, 0};
+      SEpilogue e;
+      e.Rsd = dout;
+      e.ldr = R;
+      e.rsd_split = 1;
+      e.acc_scale = INV_W;
+      e.reverse = ndir;
+      WN_TRY(tcs_gemm(h, DA, 2, sidx, roff, W, HP(ws + t.tc_w1t) + (int64_t)l * 2 * (R * 4 * G), R, e, dnew, R, 1, s));
+      dout = dnew;
+      dt ^= 1;
+    }
+  }
+  // gradient w.r.t. the causal output, back to unscaled fp32 rows for the SIMT embedding / causal-stack backward
+  float* dfin = ws + t.dout[dt];
+  WN_TRY(tcs_unsplit_rows(reinterpret_cast<const float*>(dout), dfin, R, P, inv, s));
+  h->bwd_dout = dfin;
+  return WN_OK;
+}
+
+// dlogits fp32 [B*T][Q] (written by the CE kernel) -> split rows scaled by gscale, in place
+int tcs_scale_split_dlogits(wn_handle* h, int T, float gscale, cudaStream_t s) {
+  const Tape& t = h->tape;
+  return tcs_split_rows_inplace(h->ws + t.dlogits, h->Q, (int64_t)t.B * T, gscale, s);
+}
+
+// ---- developer hooks (tests/dev/check_tcs_kernels.py): the two generic split kernels on caller-provided split tensors ----
+extern "C" int wn_tcs_debug_gemm(wn_handle* h, const void* a_split, int C, int rows_in, int num_seq, int ns, int row_off0,
+                                 int row_off1, int rows_out, const void* w_split, int N, const void* rsd_split, const void* mask_split,
+                                 int relu, void* y, int out_split, void* stream) {
+  WN_REQUIRE(h && a_split && w_split && y && ns >= 1 && ns <= 2, WN_EINVAL, "wn_tcs_debug_gemm: bad argument");
+  SOperand A{reinterpret_cast<const __half*>(a_split), C, rows_in, num_seq, 1, 0};
+  const int sidx[2] = {0, 0};
+  const int roff[2] = {row_off0, row_off1};
+  SEpilogue e;
+  e.relu = relu;
+  if (rsd_split) {
+    e.Rsd = rsd_split;
+    e.ldr = N;
+    e.rsd_split = 1;
+  }
+  if (mask_split) {
+    e.mask = reinterpret_cast<const __half*>(mask_split);
+    e.ldm = N;
+    e.mask_rows_in = rows_out;
+  }
+  return tcs_gemm(h, A, ns, sidx, roff, rows_out, reinterpret_cast<const __half*>(w_split), N, e, y, N, out_split, (cudaStream_t)stream);
+}
+
+extern "C" int wn_tcs_debug_wgrad(wn_handle* h, const void* dy_split, int M, const void* x_split, int C, int rows, int num_seq,
+                                  int x_row_off, float scale, float* dW, void* stream) {
+  WN_REQUIRE(h && dy_split && x_split && dW && M <= 256, WN_EINVAL, "wn_tcs_debug_wgrad: bad argument");
+  SOperand dY{reinterpret_cast<const __half*>(dy_split), M, rows, num_seq, 1, 0};
+  SOperand X{reinterpret_cast<const __half*>(x_split), C, rows, num_seq, 1, 0};
+  return tcs_wgrad(h, dY, 0, 0, M, X, 1, &x_row_off, nullptr, &dW, nullptr, 256, rows, C, 1, scale, (cudaStream_t)stream);
+}

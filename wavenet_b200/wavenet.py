@@ -184,6 +184,7 @@ class WaveNet(object):
         self._ws = None
         self._ws_key = None
         self._keep = {}
+        self._graphs = {}
         self.data_parallel = False
         self.create_network(seed)
         self.setup_optimizer()
@@ -280,7 +281,15 @@ class WaveNet(object):
         if not torch.cuda.is_available():
             raise Exception("wavenet_b200 has no CPU path: a CUDA device (sm_100a) is required")
         dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        # the C ABI launches on the CURRENT device's stream (like chain.to_gpu() after cuda.get_device(n).use(),
+        # train_audio/model.py:57-59): make the selected device current and re-create the handle there so that
+        # sm_count and every launch belong to it
+        torch.cuda.set_device(dev)
+        if self._device is not None and self._device != dev:
+            self._ws, self._ws_key = None, None
+        self._graphs = {}
         self._device = dev
+        check(self._libh.wn_set_device_info(self._h))
         self._params = self._params.to(dev)
         self._grads = torch.zeros_like(self._params)
         self._m = torch.zeros_like(self._params) if self._m is None else self._m.to(dev)
@@ -295,8 +304,11 @@ class WaveNet(object):
         return bool(torch.cuda.is_available() and self._gpu)
 
     def set_precision(self, name):
-        """'fp32' (SIMT, parity path) or 'tf32' (tcgen05 fast path)."""
-        check(self._libh.wn_set_precision(self._h, {"fp32": _lib.WN_PREC_FP32, "tf32": _lib.WN_PREC_TF32}[name]))
+        """'fp32' (SIMT FFMA, exact), 'fp16x2' (tcgen05 on split fp16 operands: fp32-grade, meets the 1e-4 logit /
+        1e-3 gradient gates) or 'tf32' (single-pass tcgen05, 1e-2 logits)."""
+        check(self._libh.wn_set_precision(self._h, {"fp32": _lib.WN_PREC_FP32, "tf32": _lib.WN_PREC_TF32,
+                                                    "fp16x2": _lib.WN_PREC_F16X2}[name]))
+        self._graphs = {}          # a captured step replays the kernels of the precision it was recorded under
 
     def _need_gpu(self):
         if not self.gpu_enabled:
@@ -310,6 +322,7 @@ class WaveNet(object):
             self._ws = None
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self._device)
         check(self._libh.wn_bind_workspace(self._h, _ptr(self._ws), nbytes, B, W))
+        self._graphs = {}          # captured steps hold TMA descriptors / offsets of the previous binding
         self._ws_key = (B, W)
         self._B, self._W = B, W
 
@@ -504,8 +517,14 @@ class WaveNet(object):
         to launch eagerly."""
         self._need_gpu()
         B, W = x_idx.shape
-        self._bind(B, W)
         T = W if train_width is None else train_width
+        if x_idx.dtype != torch.int32 or target.dtype != torch.int32:
+            raise Exception("train_step expects int32 device tensors")
+        if tuple(target.shape) != (B, T):
+            raise Exception("raw_network_output.width != target.width")
+        if torch.cuda.current_device() != self._device.index:
+            torch.cuda.set_device(self._device)
+        self._bind(B, W)
         key = (B, W, T, int(self._libh.wn_get_precision(self._h)))
         if not getattr(self, "use_cuda_graph", True):
             self._keep["idx"], self._keep["tgt"] = x_idx, target
