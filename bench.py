@@ -2,13 +2,19 @@
 """Benchmark of the musyoku/wavenet hot paths on B200 (see BASELINE.json / SURVEY.md 8d).
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU arithmetic (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU code path
 
-A "step" is one train.py step of the 30-layer config-C network on a synthetic mu-law batch
-of 32 x 16000 samples per GPU: forward + cross-entropy + backward + (NCCL all-reduce when
-N > 1) + gradient clipping + Adam.  `value` is whole-job audio samples/s with the batch
-resident in HBM; `e2e` is the same step driven through the public Python API from pinned
+A "step" is one train.py step of the 30-layer config-C network on a synthetic mu-law batch of 32 x 16000 samples per
+GPU: forward + cross-entropy + backward + (NCCL all-reduce when N > 1) + gradient clipping + Adam.  `value` is whole-job
+audio samples/s with the batch resident in HBM; `e2e` is the same step driven through the public Python API from pinned
 host buffers (H2D of samples/targets, D2H of the loss inside the timed region).
+
+The headline runs in the fp16x2 precision mode (tcgen05 on split fp16 operands, fp32-grade: the mode that meets the 1e-4
+logit / 1e-3 gradient gates); `precision_modes` reports the single-pass tf32 mode and the exact-fp32 SIMT mode next to it.
+
+The reference arm executes the REFERENCE'S OWN SOURCE (oracle/_ref: mechanical py2->py3 transform of
+/root/reference/*.py, NumPy stand-in for the Chainer primitives -- im2col + tensordot like Chainer's CPU path) on the
+host cores; when oracle/_ref is absent it falls back to the NumPy oracle port.
 """
 import argparse
 import json
@@ -29,6 +35,8 @@ LAYER_FLOP_PER_POS = 2 * (128 * 128 + 64 * 64 + 256 * 64)   # one residual layer
 B_PER_GPU, WIDTH = 32, 16000
 METRIC = "train audio samples/s (config C 30-layer, fwd+loss+bwd+clip+Adam)"
 UNIT = "samples/s"
+DTYPE_NAMES = {"fp16x2": "f16x2 (split fp16 operands hi+lo on tcgen05, fp32 accumulate; fp32-grade)",
+               "tf32": "tf32", "fp32": "f32"}
 
 
 def config_c():
@@ -38,6 +46,16 @@ def config_c():
     p.residual_conv_channels = [64] * 10
     p.residual_num_blocks = 3
     p.softmax_conv_channels = [256, 256, 256]
+    return p
+
+
+def config_b():
+    from wavenet_b200.wavenet import Params
+    p = Params()                       # reference default network, train_audio/model.py:24-43
+    p.causal_conv_channels = [256]
+    p.residual_conv_channels = [128] * 8
+    p.residual_num_blocks = 1
+    p.softmax_conv_channels = [256, 256]
     return p
 
 
@@ -98,27 +116,109 @@ def synth_batch(rank, B, W):
     return np.ascontiguousarray(x[:, :W]), np.ascontiguousarray(x[:, 1:])
 
 
-# --------------------------------------------------------------------------------------
-def cpu_train_sample(threads, B=1, W=16000, reps=2):
-    """One train step of config C on the CPU oracle (the reference's arithmetic restated in
-    NumPy: one-hot input, pad copies, im2col+tensordot convs forward; einsum backward; clip+Adam)."""
+# ---- CPU legs: the reference's own code path on the host cores ------------------------------------------
+_CFG_KEYS = ["quantization_steps", "causal_conv_no_bias", "causal_conv_filter_width", "causal_conv_channels",
+             "residual_conv_dilation_no_bias", "residual_conv_projection_no_bias", "residual_conv_filter_width",
+             "residual_conv_channels", "residual_num_blocks", "softmax_conv_no_bias", "softmax_conv_channels",
+             "weight_decay", "momentum", "gradient_clipping"]
+
+
+def load_reference():
+    """(R, RF, RD) = the executed reference modules, or None when oracle/_ref is unavailable."""
+    try:
+        from oracle.ref_build import import_reference
+        return import_reference()
+    except Exception:
+        return None
+
+
+def _ref_params(R, cfg):
+    p = R.Params()
+    for k in _CFG_KEYS:
+        setattr(p, k, getattr(cfg, k))
+    return p
+
+
+class CpuTrainer(object):
+    """One train.py:58-80 step (one-hot -> forward blocks -> slice -> cross_entropy -> backprop) on the host CPU:
+    through the executed reference source when available (kind "reference"), else the NumPy oracle port."""
+
+    def __init__(self, which, B, W, train_width):
+        from oracle import wavenet_oracle as O
+        self.O, self.B, self.W, self.tw = O, B, W, train_width
+        self.cfg = O.config_C() if which == "C" else O.config_B()
+        self.x, self.tgt = synth_batch(0, B, W)
+        self.tgt = np.ascontiguousarray(self.tgt[:, W - train_width:])
+        self.ref = load_reference()
+        if self.ref is not None:
+            R, RF, RD = self.ref
+            np.random.seed(1234)
+            self.net = R.WaveNet(_ref_params(R, self.cfg))       # Chainer default init (LeCunNormal), wavenet.py:379-455
+            self.net.update_laerning_rate(1e-3)
+            self.kind = "reference"
+        else:
+            self.w = O.init_weights(self.cfg, np.random.default_rng(1234), np.float32)
+            self.st = O.new_adam_state(self.w)
+            self.kind = "port"
+
+    def step(self):
+        if self.ref is not None:
+            R, RF, RD = self.ref
+            net, W, tw = self.net, self.W, self.tw
+            onehot = RD.onehot_pixel_image(self.x, quantization_steps=256)
+            out = net.forward_causal_block(onehot)
+            out, skip = net.forward_residual_block(out)
+            if W - tw >= 1:
+                skip = net.slice_1d(skip, W - tw)
+            y = net.forward_softmax_block(skip, apply_softmax=False)
+            loss = net.cross_entropy(y, self.tgt)
+            net.backprop(loss)
+            return float(loss.data)
+        O = self.O
+        fw = O.forward_loss(self.cfg, self.w, self.x, self.tgt, train_width=self.tw, dtype=np.float32)
+        g = O.backward(self.cfg, fw)
+        O.clip_and_adam(self.cfg, self.w, g, self.st, lr=1e-3)
+        return float(fw["loss"])
+
+    def describe(self, what):
+        impl = ("the reference's own wavenet.py executed on the host (oracle/_ref: py2->py3 transform, NumPy stand-in for the "
+                "Chainer primitives: im2col + tensordot convs, define-by-run backward, clip + Adam)" if self.kind == "reference"
+                else "NumPy oracle port (oracle/_ref unavailable)")
+        return "%s; %s; BLAS threads = all host cores" % (what, impl)
+
+
+def cpu_generation_sample(n_steps=60):
+    """faster_wavenet.py incremental steps at config C on the host (rolled windows, ELU head over the whole window, H2D-free):
+    time per step after the priming call."""
     from oracle import wavenet_oracle as O
     cfg = O.config_C()
-    w = O.init_weights(cfg, np.random.default_rng(1234), np.float32)
-    st = O.new_adam_state(w)
-    x, tgt = synth_batch(0, B, W)
-    best = None
-    for _ in range(reps + 1):          # first pass is warm-up
-        t0 = time.perf_counter()
-        O.forward_literal(cfg, w, O.onehot_pixel_image(x, 256))           # reference-shaped forward (timed)
-        t1 = time.perf_counter()
-        fw = O.forward_loss(cfg, w, x, tgt, dtype=np.float32)               # tape for the manual backward (untimed)
-        t2 = time.perf_counter()
-        g = O.backward(cfg, fw)
-        O.clip_and_adam(cfg, w, g, st, lr=1e-3)
-        dt = (t1 - t0) + (time.perf_counter() - t2)
-        best = dt if best is None else min(best, dt)
-    return B * W / best, best
+    Win = O.input_width(cfg)
+    ref = load_reference()
+    audio = np.full((Win,), 127, dtype=np.int32)
+    if ref is not None:
+        R, RF, RD = ref
+        np.random.seed(1234)
+        net = RF.FasterWaveNet(_ref_params(R, cfg))
+        fn = lambda a: net._forward_one_step(RD.onehot_pixel_image(a[-Win:].reshape(1, -1), 256), apply_softmax=True,
+                                             as_numpy=True)[0, :, 0, -1]
+        kind = "reference"
+    else:
+        lit = O.LiteralFastGenerator(cfg, O.init_weights(cfg, np.random.default_rng(1234), np.float32), np.float32)
+        fn = lambda a: lit._forward_one_step(O.onehot_pixel_image(a[-Win:].reshape(1, -1), 256), apply_softmax=True)[0, :, 0, -1]
+        kind = "port"
+    t0 = time.perf_counter()
+    p = fn(audio)
+    audio = np.append(audio, [int(np.argmax(p))])
+    prime_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        p = fn(audio)
+        audio = np.append(audio, [int(np.argmax(p))])
+    per = (time.perf_counter() - t0) / n_steps
+    return {"value": 1.0 / per, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": kind,
+            "sample": "%d incremental _forward_one_step calls at config C after the priming call (%.2f s), batch 1; "
+                      "16000 samples would take %.0f s at this rate (extrapolated)" % (n_steps, prime_s, 16000 * per),
+            "s_per_sample": per}
 
 
 def run_reference(args):
@@ -127,17 +227,11 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     B, W = 1, 8192
+    tr = CpuTrainer("C", B, W, W)
     times = []
-    from oracle import wavenet_oracle as O
-    cfg = O.config_C()
-    w = O.init_weights(cfg, np.random.default_rng(1234), np.float32)
-    st = O.new_adam_state(w)
-    x, tgt = synth_batch(0, B, W)
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        fw = O.forward_loss(cfg, w, x, tgt, dtype=np.float32)
-        g = O.backward(cfg, fw)
-        O.clip_and_adam(cfg, w, g, st, lr=1e-3)
+        tr.step()
         if i >= args.warmup:
             times.append(time.perf_counter() - t0)
     ms = 1e3 * float(np.mean(times))
@@ -146,10 +240,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic mu-law indices, random-init weights",
-        "config": {"workload": "config C train step on a bounded CPU sample of %d x %d samples" % (B, W)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d x %d samples per step, NumPy oracle (Chainer is not installable here), "
-                                   "BLAS threads = all host cores" % (B, W)},
+        "config": {"workload": "config C (30 layers d=1..512 x3, 64 residual / 256 skip, head 256-256-256) train step on a bounded "
+                               "CPU sample of %d x %d samples per step (the GPU arm steps 32 x 16000 per GPU; samples/s normalises)"
+                               % (B, W)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": tr.kind,
+                         "sample": tr.describe("%d x %d samples per step" % (B, W))},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -162,12 +257,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--precision", default="fp16x2", choices=["fp16x2", "tf32", "fp32"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="sequences per GPU")
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--no-gen", action="store_true", help="skip the generation side metrics")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
-    ap.add_argument("--gen-steps", type=int, default=4000)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
+    ap.add_argument("--no-modes", action="store_true", help="skip the other precision modes")
+    ap.add_argument("--gen-steps", type=int, default=16000)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -175,7 +271,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from wavenet_b200 import _lib                      # the product arm never touches oracle/ (only cpu_train_sample does)
+    from wavenet_b200 import _lib                      # the product arm never touches oracle/ (only the CPU legs do)
     from wavenet_b200.wavenet import WaveNet, _ptr, _stream
     from wavenet_b200.faster_wavenet import FasterWaveNet
 
@@ -229,7 +325,8 @@ def main():
     launches = int(lib.wn_launch_count(1))
     clocks = sampler.stop() if rank == 0 else None
     value = B * W * world / (ms / 1e3)
-    eff_prec = "tf32" if (args.precision == "tf32" and lib.wn_tc_active(net._h)) else "f32"
+    tc = bool(lib.wn_tc_active(net._h))
+    eff_prec = args.precision if tc else "fp32"
 
     # ---- e2e: host buffers through the public API -------------------------------------
     xp, tp = torch.from_numpy(x_h).pin_memory(), torch.from_numpy(t_h).pin_memory()
@@ -269,18 +366,58 @@ def main():
     res_ms = timed(residual_only, args.steps)
     peaks = measured_peaks()
     n_layers = 30
-    tc_active = eff_prec == "tf32"
-    if tc_active:
-        # dominant kernel of the step by time share: the fused gate-backward kernel (dz GEMM + gate derivative + dWp,
-        # 29 launches per step), timed alone with CUDA events on the launching stream; the fused forward layer kernel
-        # (30 launches) is reported next to it
-        def read_traffic(name):
-            tpath = os.path.join(ROOT, "profiles", name)
-            if os.path.isfile(tpath):
-                with open(tpath) as f:
-                    return json.load(f).get("dram_bytes_per_launch")
-            return None
+
+    def stored_traffic(name):
+        """DRAM bytes per launch from a committed `ncu --set full` capture (profiles/): a STORED figure, not measured in this
+        run -- the run itself measures `achieved` with CUDA events."""
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.isfile(tpath):
+            with open(tpath) as f:
+                return json.load(f).get("dram_bytes_per_launch"), "stored ncu capture profiles/" + name
+        return None, None
+
+    roofline_layer = roofline_tensor = None
+    if eff_prec == "fp16x2":
+        # dominant kernel family of the step: the fused residual-layer kernels; the forward one is timed alone here
+        def layers_only():
+            for l in range(n_layers):
+                _lib.check(lib.wn_tcs_layer_forward(net._h, l, _stream()))
+        layers_only()
+        lay_ms = timed(layers_only, args.steps) / n_layers
+        # split rows are 4 B per channel: read x(t) once (x(t-d) re-read hits L2), write x_out, z and the fp32 sigmoid
+        bytes_per_pos = 4 * 64 * 4
+        alg_bytes = bytes_per_pos * B * W
+        achieved = alg_bytes / (lay_ms / 1e3) / 1e9
+        traffic, tsrc = stored_traffic("r02_ncu_tcs_layer_kernel.json")
+        layer_flops = 2 * (128 * 128 + 64 * 64) * B * W
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": tsrc,
+                    "kernel": "tcs_layer_kernel (fused residual layer forward, fp16x2), %.1f us per launch, 30 per step"
+                              % (1e3 * lay_ms),
+                    "algorithmic_bytes_per_launch": alg_bytes,
+                    "peak_source": "%s HBM copy bandwidth" % peaks["source"],
+                    "tensor": {"achieved_tflops_algorithmic": layer_flops / (lay_ms / 1e3) / 1e12,
+                               "executed_mma_tflops": 3 * layer_flops / (lay_ms / 1e3) / 1e12,
+                               "peak_tflops": peaks["bf16_sustained"],
+                               "note": "three kind::f16 MMAs per product (hi.hi + hi.lo + lo.hi); per-layer GEMMs (K=128/64) are "
+                                       "HBM-bound, see DESIGN.md section 5"},
+                    "residual_stack_forward_ms": res_ms}
+
+        def skip_only():
+            _lib.check(lib.wn_tcs_skip_gemm(net._h, _stream()))
+        skip_only()
+        skip_ms = timed(skip_only, args.steps)
+        skip_flops = 2 * 64 * n_layers * 256 * B * W
+        skip_tf = skip_flops / (skip_ms / 1e3) / 1e12
+        roofline_tensor = {"bound": "tensor", "achieved": 3 * skip_tf, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                           "frac": 3 * skip_tf / peaks["bf16_burst"], "algorithmic_tflops": skip_tf,
+                           "kernel": "tcs_gemm_kernel<256,4> skip sum (K=1920, N=256, K blocks flushed to registers), %.1f us per launch"
+                                     % (1e3 * skip_ms),
+                           "peak_source": "%s bf16 burst figure (cuBLAS); achieved counts the three executed fp16 MMAs per product"
+                                          % peaks["source"]}
+    elif eff_prec == "tf32":
         scratch = torch.zeros_like(net._grads)
+
         def gates_only():
             for l in range(n_layers - 1):
                 _lib.check(lib.wn_tc_gate_backward_layer(net._h, l, _ptr(scratch), _stream()))
@@ -288,45 +425,39 @@ def main():
         gate_ms = timed(gates_only, args.steps) / (n_layers - 1)
         gate_bytes = (3 * 64 * 4 + 64 * 2 + 128 * 4) * B * W    # read dout, dzs, z (fp32) + sigmoid (fp16); write dafg
         gate_achieved = gate_bytes / (gate_ms / 1e3) / 1e9
+
         def layers_only():
             for l in range(n_layers):
                 _lib.check(lib.wn_tc_layer_forward(net._h, l, _stream()))
         layers_only()
         lay_ms = timed(layers_only, args.steps) / n_layers
-        bytes_per_pos = 3 * 64 * 4 + 64 * 2   # read x(t) once, write x_out, z (fp32) and sigmoid (fp16); x(t-d) re-read hits L2
+        bytes_per_pos = 3 * 64 * 4 + 64 * 2
         alg_bytes = bytes_per_pos * B * W
         achieved = alg_bytes / (lay_ms / 1e3) / 1e9
-        traffic = read_traffic("r01_ncu_tc_layer_kernel.json")
-        # second kernel family: the skip-sum GEMM (K = 64 x 30 layers, N = 256) is the tensor-bound one
-        def skip_only():
-            _lib.check(lib.wn_tc_skip_gemm(net._h, _stream()))
-        skip_only()
-        skip_ms = timed(skip_only, args.steps)
-        skip_flops = 2 * 64 * n_layers * 256 * B * W
-        skip_tf = skip_flops / (skip_ms / 1e3) / 1e12
-        layer_flops = 2 * (128 * 128 + 64 * 64) * B * W
+        traffic, tsrc = stored_traffic("r01_ncu_tc_gate_bwd_kernel.json")
         gate_flops = 2 * (64 * 64 + 64 * 64) * B * W
         roofline = {"bound": "hbm", "achieved": gate_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": gate_achieved / peaks["hbm_gbs"], "traffic": read_traffic("r01_ncu_tc_gate_bwd_kernel.json"),
+                    "frac": gate_achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": tsrc,
                     "kernel": "tc_gate_bwd_kernel (dz GEMM + gate derivative + dWp, one residual layer), %.1f us per launch"
                               % (1e3 * gate_ms),
                     "algorithmic_bytes_per_launch": gate_bytes,
                     "peak_source": "%s HBM copy bandwidth" % peaks["source"],
-                    "tensor": {"achieved_tflops": gate_flops / (gate_ms / 1e3) / 1e12,
-                               "peak_tflops": peaks["bf16_sustained"] / 2.0,
-                               "note": "kind::tf32 peak taken as half of the measured bf16 sustained figure; "
-                                       "per-layer GEMMs (K=128/64) are HBM-bound, see DESIGN.md section 5"}}
+                    "tensor": {"achieved_tflops": gate_flops / (gate_ms / 1e3) / 1e12, "peak_tflops": peaks["bf16_sustained"] / 2.0}}
+        ltraffic, ltsrc = stored_traffic("r01_ncu_tc_layer_kernel.json")
         roofline_layer = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+                          "frac": achieved / peaks["hbm_gbs"], "traffic": ltraffic, "traffic_source": ltsrc,
                           "kernel": "tc_layer_kernel (fused residual layer forward), %.1f us per launch" % (1e3 * lay_ms),
-                          "algorithmic_bytes_per_launch": alg_bytes,
-                          "tensor_achieved_tflops": layer_flops / (lay_ms / 1e3) / 1e12,
-                          "residual_stack_forward_ms": res_ms}
+                          "algorithmic_bytes_per_launch": alg_bytes, "residual_stack_forward_ms": res_ms}
+
+        def skip_only():
+            _lib.check(lib.wn_tc_skip_gemm(net._h, _stream()))
+        skip_only()
+        skip_ms = timed(skip_only, args.steps)
+        skip_tf = 2 * 64 * n_layers * 256 * B * W / (skip_ms / 1e3) / 1e12
         roofline_tensor = {"bound": "tensor", "achieved": skip_tf, "peak": peaks["bf16_burst"] / 2.0, "unit": "TFLOP/s",
-                           "frac": skip_tf / (peaks["bf16_burst"] / 2.0), "frac_of_nominal_tf32_1100": skip_tf / 1100.0,
+                           "frac": skip_tf / (peaks["bf16_burst"] / 2.0),
                            "kernel": "tc_gemm_kernel<256> skip sum (K=1920, N=256), %.1f us per launch" % (1e3 * skip_ms),
-                           "peak_source": "kind::tf32 taken as half of the %s bf16 burst figure (cuBLAS); nominal dense "
-                                          "TF32 is 1.1 PFLOP/s" % peaks["source"]}
+                           "peak_source": "kind::tf32 taken as half of the %s bf16 burst figure (cuBLAS)" % peaks["source"]}
     else:
         achieved = LAYER_FLOP_PER_POS * n_layers * B * W / (res_ms / 1e3) / 1e12
         roofline = {"bound": "tensor", "achieved": achieved, "peak": 72.0, "unit": "TFLOP/s", "frac": achieved / 72.0,
@@ -335,21 +466,37 @@ def main():
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": eff_prec,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_NAMES[eff_prec],
         "data": "synthetic mu-law indices default_rng(rank), random-init LeCunNormal weights (facade initialiser, seed 1234)",
         "config": {"workload": "config C (30 layers d=1..512 x3, 64 residual / 256 skip, head 256-256-256), "
                                "%d x %d samples per GPU, full-width teacher-forced train step" % (B, W),
-                   "global_batch": B * world, "width": W, "parallelism": "dp%d" % world,
+                   "global_batch": B * world, "width": W, "parallelism": "dp%d" % world, "precision_mode": eff_prec,
                    "l2": "working set (activation tape ~20 GB) is far larger than the 126 MB L2; no explicit flush"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(x_h.nbytes + t_h.nbytes),
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-        "roofline_layer": roofline_layer if tc_active else None,
-        "roofline_tensor": roofline_tensor if tc_active else None,
+        "roofline_layer": roofline_layer, "roofline_tensor": roofline_tensor,
         "train_tflops": 3 * FWD_FLOP_PER_POS * B * W * world / (ms / 1e3) / 1e12,
         "fwd_loss": {"ms": fwd_ms, "samples_per_s": B * W * world / (fwd_ms / 1e3),
                      "tflops": FWD_FLOP_PER_POS * B * W * world / (fwd_ms / 1e3) / 1e12},
     }
+
+    # ---- the other precision modes on the same step (N == 1): parity class next to speed -------------------
+    if world == 1 and not args.no_modes:
+        modes = {eff_prec: {"ms_per_step": ms, "samples_per_s": value}}
+        for other, nsteps in (("fp16x2", args.steps), ("tf32", args.steps), ("fp32", 2)):
+            if other in modes:
+                continue
+            net.set_precision(other)
+            for _ in range(2):
+                step()
+            oms = timed(step, nsteps)
+            modes[other] = {"ms_per_step": oms, "samples_per_s": B * W / (oms / 1e3)}
+        net.set_precision(args.precision)
+        modes["fp16x2"]["parity"] = "logits <= 1e-4, gradients <= 1e-3 vs the reference (tests/test_gpu_fp16x2.py, test_gpu_reference.py)"
+        modes["tf32"]["parity"] = "logits <= 1e-2 with argmax agreement; gradients ~4e-2 (single-pass tensor cores)"
+        modes["fp32"]["parity"] = "exact fp32 SIMT FFMA: logits <= 1e-4, gradients <= 1e-3"
+        line["precision_modes"] = modes
 
     # ---- generation side metrics (BASELINE configs 3 and 4), N streams sharded, no collective ---
     if not args.no_gen:
@@ -369,7 +516,10 @@ def main():
 
             def run():
                 _lib.check(lib.wn_gen_run(net._gen, _ptr(net._params), steps, _lib.WN_GEN_SAMPLE, 0, _ptr(out), _stream()))
+            net.prime(window)
             run()
+            torch.cuda.synchronize()
+            net.prime(window)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -392,23 +542,19 @@ def main():
                 "us_per_step": us, "cycles_per_sample_per_stream": us * sm_mhz,
                 "kernel": "gen_kernel_v4 (8-CTA cluster per stream, output-split matvecs, st.async exchanges)" if clustered
                           else "gen_kernel_v3 (one CTA per 1-2 streams)",
-                # every CTA streams its share of the 5.08 MB fp32 weight set once per step through its cp.async.bulk ring
                 "weight_stream_gbs_per_sm": per_cta / (us * 1e-6) / 1e9,
                 "weight_stream_gbs_all_ctas": n_ctas * world * per_cta / (us * 1e-6) / 1e9,
                 "bound": ("dependency-chain latency (30 layers x 1 cluster exchange + head per sample)" if clustered else
                           "dependency-chain latency (30 layers x 2 block barriers + head per sample)")}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            gen["cpu_baseline"] = cpu_generation_sample()
+            gen["batch_1"]["vs_cpu_reference"] = gen["batch_1"]["samples_per_s"] / gen["cpu_baseline"]["value"]
         line["fast_gen"] = gen
 
-    # ---- BASELINE config 1 shape on the GPU: reference default network (train_audio/model.py:24-43), one train.py
-    # step on a 1 s 16 kHz clip, batch 1 (the CPU leg below times the same arithmetic on the host) ----
+    # ---- BASELINE config 1 shape: reference default network (train_audio/model.py:24-43), one train.py step on a 1 s 16 kHz
+    # clip, batch 1 -- on the GPU and (CPU leg) through the reference's own code on the host ----
     if rank == 0 and world == 1:
-        from wavenet_b200.wavenet import Params
-        pb = Params()
-        pb.causal_conv_channels = [256]
-        pb.residual_conv_channels = [128] * 8
-        pb.residual_num_blocks = 1
-        pb.softmax_conv_channels = [256, 256]
-        netb = WaveNet(pb, seed=0)
+        netb = WaveNet(config_b(), seed=0)
         netb.to_gpu(local_rank)
         netb.set_precision(args.precision)
         netb.update_laerning_rate(1e-3)
@@ -420,19 +566,33 @@ def main():
         for _ in range(3):
             stepb()
         msb = timed(stepb, 10)
-        line["config1_reference_default_net"] = {
-            "workload": "R256/G128 x 8 layers, batch 1 x 16000, train_width 15743, fwd+bwd+clip+Adam",
-            "ms_per_step": msb, "samples_per_s": 16000 / (msb / 1e3),
-            "tc_active": bool(lib.wn_tc_active(netb._h)), "tflops": 3 * 3276800 * 16000 / (msb / 1e3) / 1e12}
+        c1 = {"workload": "R256/G128 x 8 layers, batch 1 x 16000, train_width 15743, fwd+bwd+clip+Adam",
+              "ms_per_step": msb, "samples_per_s": 16000 / (msb / 1e3), "tc_active": bool(lib.wn_tc_active(netb._h)),
+              "precision_mode": args.precision, "tflops": 3 * 3276800 * 16000 / (msb / 1e3) / 1e12}
         del netb
+        if not args.no_cpu:
+            trb = CpuTrainer("B", 1, 16000, tw)
+            trb.step()
+            t0 = time.perf_counter()
+            trb.step()
+            sb = time.perf_counter() - t0
+            c1["cpu_baseline"] = {"value": 16000 / sb, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": trb.kind,
+                                  "sample": trb.describe("one full config-1 step (1 x 16000, train_width 15743) after one warm-up, %.1f s" % sb)}
+            c1["vs_cpu_reference"] = c1["samples_per_s"] / c1["cpu_baseline"]["value"]
+        line["config1_reference_default_net"] = c1
 
-    # ---- CPU baseline (rank 0, N == 1 only) -----------------------------------------------------
+    # ---- CPU baseline of the headline workload (rank 0, N == 1 only) -----------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
-        v, secs = cpu_train_sample(threads)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "best of 2 config-C train steps on 1 x 16000 samples (%.1f s each), NumPy oracle in "
-                                          "reference-literal mode, BLAS threads = all host cores" % secs}
+        tr = CpuTrainer("C", 1, 8192, 8192)
+        tr.step()
+        best = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            tr.step()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        line["cpu_baseline"] = {"value": 8192 / best, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": tr.kind,
+                                "sample": tr.describe("best of 2 config-C train steps on 1 x 8192 samples (%.1f s each) after one warm-up" % best)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

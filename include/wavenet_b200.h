@@ -162,6 +162,17 @@ int wn_tc_skip_gemm(wn_handle* h, wn_stream_t s);
  * preceding TF32 wn_backward left on the tape; grads_scratch (flat-size floats) receives the dWp accumulation. */
 int wn_tc_gate_backward_layer(wn_handle* h, int layer, float* grads_scratch, wn_stream_t s);
 
+/* Same hooks for the fp16x2 path (need a preceding fp16x2 wn_forward_residual_block). */
+int wn_tcs_layer_forward(wn_handle* h, int layer, wn_stream_t s);
+int wn_tcs_skip_gemm(wn_handle* h, wn_stream_t s);
+/* Developer hooks (tests/dev/check_tcs_kernels.py): the generic fp16x2 GEMM / weight-gradient kernels on caller-made
+ * split tensors ([rows][hi(C) | lo(C)] fp16). */
+int wn_tcs_debug_gemm(wn_handle* h, const void* a_split, int C, int rows_in, int num_seq, int ns, int row_off0, int row_off1,
+                      int rows_out, const void* w_split, int N, const void* rsd_split, const void* mask_split, int relu,
+                      void* y, int out_split, wn_stream_t s);
+int wn_tcs_debug_wgrad(wn_handle* h, const void* dy_split, int M, const void* x_split, int C, int rows, int num_seq,
+                       int x_row_off, float scale, float* dW, wn_stream_t s);
+
 /* ---- incremental generation (faster_wavenet.py) ----------------------------
  * n_streams independent utterances (the reference hard-codes one, wavenet.py:286).
  * head_act: 0 = ReLU always; 1 = reference (ReLU on the priming call,
@@ -181,6 +192,9 @@ int wn_gen_prime(wn_gen* g, const float* params, const int32_t* window, float* p
  * probs[n][Q] = last-column softmax (logits when !apply_softmax). */
 int wn_gen_step(wn_gen* g, const float* params, const int32_t* x_new, int apply_softmax, float* probs,
                 wn_stream_t s);
+/* logits[n][Q] of the NEXT sample as the last priming call / step left them (before softmax): the last column of what
+ * the reference returns from _forward_one_step(apply_softmax=False), faster_wavenet.py:50-63. */
+int wn_gen_logits(wn_gen* g, float* logits, wn_stream_t s);
 /* The whole generate.py:24-43 loop on device: draws the first sample from the
  * priming distribution already stored by wn_gen_prime, then n_steps-1
  * incremental steps, each feeding its own sample back.  out[n][n_steps]. */

@@ -76,8 +76,14 @@ def build(verbose=True):
 
 
 def import_reference():
-    """Returns the transformed reference modules (wavenet, faster_wavenet, data) running on the chainer stand-in."""
-    out = build(verbose=False)
+    """Returns the transformed reference modules (wavenet, faster_wavenet, data) running on the chainer stand-in.
+    Rebuilds oracle/_ref/ when /root/reference is present; otherwise (GPU box) uses the files that travelled with the tree."""
+    if os.path.isdir(REF):
+        out = build(verbose=False)
+    elif all(os.path.isfile(os.path.join(OUT, n)) for n in ("wavenet.py", "faster_wavenet.py", "data.py")):
+        out = OUT
+    else:
+        raise RuntimeError("oracle/_ref/ is empty and %s does not exist: run oracle/ref_build.py in the build container" % REF)
     shim = os.path.join(HERE, "chainer_shim")
     for p in (shim, out):
         if p not in sys.path:

@@ -27,18 +27,20 @@ def generate_audio(sampling_rate=48000, generate_sec=1, remove_silence_frames=Fa
     n_steps = int(sampling_rate * generate_sec) - 1
 
     start_time = time.time()
-    if args.fast:
+    if args.fast and not remove_silence_frames:
         window = generated_quantized_audio.reshape((1, -1))
         mode = "greedy" if args.greedy else "sample"
         seed = 0 if args.seed is None else args.seed
         samples = wavenet.generate(window, n_steps, mode=mode, seed=seed).cpu().numpy()[0]
-        if remove_silence_frames:
-            samples = samples[samples != 127]
         generated_quantized_audio = np.append(generated_quantized_audio, samples, axis=0)
     else:
+        # per-sample loop of generate.py:24-43.  remove_silence_frames drops a generated 127 from the signal, so the next
+        # call sees the SAME window (and the fast path feeds its last sample again, generate.py:40-43 + faster_wavenet.py:
+        # 65-78): that data-dependent feedback stays on the host loop, one incremental step per call.
+        step_fn = wavenet._forward_one_step if args.fast else wavenet.forward_one_step
         for time_step in range(1, n_steps + 1):
             padded_quantized_x_batch = generated_quantized_audio[-input_width:].reshape((1, -1))
-            softmax = wavenet.forward_one_step(padded_quantized_x_batch, apply_softmax=True, as_numpy=True)
+            softmax = step_fn(padded_quantized_x_batch, apply_softmax=True, as_numpy=True)
             softmax = softmax[0, :, 0, -1].astype(np.float64)
             softmax /= softmax.sum()
             if args.greedy:

@@ -48,7 +48,7 @@ def train_audio(filename, batch_size=16, train_width=16, repeat=1000):
     signals = np.insert(signals, 0, np.full((input_width,), 127, dtype=np.int32), axis=0)
 
     import torch
-    signals_dev = torch.from_numpy(np.ascontiguousarray(signals, dtype=np.int32)).cuda()   # resident for the whole file
+    signals_dev = torch.from_numpy(np.ascontiguousarray(signals, dtype=np.int32)).to(wavenet._device)   # resident for the whole file
     for batch_index in range(0, repeat):
         # same np.random stream as create_batch (train.py:15); the gather itself runs on the device
         indecis = np.random.randint(0, signals.size - train_width - input_width - 1, size=batch_size)

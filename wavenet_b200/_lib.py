@@ -78,6 +78,10 @@ SIGNATURES = {
     "wn_tc_layer_forward": (_I, [_P, _I, _P]),
     "wn_tc_skip_gemm": (_I, [_P, _P]),
     "wn_tc_gate_backward_layer": (_I, [_P, _I, _P, _P]),
+    "wn_tcs_layer_forward": (_I, [_P, _I, _P]),
+    "wn_tcs_skip_gemm": (_I, [_P, _P]),
+    "wn_tcs_debug_gemm": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _I, _P]),
+    "wn_tcs_debug_wgrad": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _F, _P, _P]),
     "wn_optim_scratch_bytes": (_L, [_P]),
     "wn_clip_adam_step": (_I, [_P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _F, _F, _F, _P, _P, _P]),
     "wn_gen_create": (_I, [_P, _I, _I, C.POINTER(_P)]),
@@ -86,6 +90,7 @@ SIGNATURES = {
     "wn_gen_bind_state": (_I, [_P, _P, _L]),
     "wn_gen_prime": (_I, [_P, _P, _P, _P, _P]),
     "wn_gen_step": (_I, [_P, _P, _P, _I, _P, _P]),
+    "wn_gen_logits": (_I, [_P, _P, _P]),
     "wn_gen_run": (_I, [_P, _P, _I, _I, C.c_uint64, _P, _P]),
     "wn_crop_batch": (_I, [_P, _L, _P, _I, _I, _I, _P, _P, _P]),
     "wn_onehot_to_index": (_I, [_P, _I, _I, _I, _P, _P]),

@@ -1443,9 +1443,13 @@ size_t gen_smem_bytes_v4(const GenLayout& L) {
 // how many 8-CTA clusters of gen_kernel_v4 can be resident at once (they must all be: the kernel is persistent over
 // every audio sample, a second wave would only start when the first has finished)
 int gen_v4_max_streams(const GenLayout& L) {
+  // cached per shared-memory size: the footprint depends on the number of layers / head convs of THIS network (a process
+  // may hold several networks, e.g. the test suite)
   static int cached = -1;
-  if (cached >= 0) return cached;
+  static size_t cached_smem = 0;
   const size_t smem = gen_smem_bytes_v4(L);
+  if (cached >= 0 && cached_smem == smem) return cached;
+  cached_smem = smem;
   if (cudaFuncSetAttribute(gen_kernel_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return cached = 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(V4_CS * 32);
@@ -1468,10 +1472,10 @@ int gen_v4_max_streams(const GenLayout& L) {
 
 int launch_gen_v4(const GenArgs& a, cudaStream_t s) {
   const size_t smem = gen_smem_bytes_v4(a.lay);
-  static bool attr = false;
-  if (!attr) {
+  static size_t attr_smem = 0;       // the opt-in limit must cover the largest network launched so far
+  if (smem > attr_smem) {
     WN_CHECK_CUDA(cudaFuncSetAttribute(gen_kernel_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
+    attr_smem = smem;
   }
   gen_kernel_v4<<<a.lay.n * V4_CS, V4_T + 32, smem, s>>>(a);
   WN_CHECK_LAUNCH();
@@ -1821,6 +1825,17 @@ extern "C" int wn_gen_step(wn_gen* g, const float* params, const int32_t* x_new,
   WN_TRY(run_gen(g, a, (cudaStream_t)st));
   g->t += 1;
   g->steps_done += 1;
+  return WN_OK;
+}
+
+// logits of the NEXT sample as left by the last priming call / step (before softmax): what the reference returns from
+// _forward_one_step(apply_softmax=False) (faster_wavenet.py:50-63, last column)
+extern "C" int wn_gen_logits(wn_gen* g, float* logits, wn_stream_t st) {
+  WN_REQUIRE(g && logits, WN_EINVAL, "null argument");
+  WN_REQUIRE(g->primed, WN_ESTATE, "wn_gen_logits: call wn_gen_prime first");
+  const GenLayout& L = g->lay;
+  WN_CHECK_CUDA(cudaMemcpyAsync(logits, g->state + L.cur_logits, sizeof(float) * L.n * L.Q, cudaMemcpyDeviceToDevice,
+                                (cudaStream_t)st));
   return WN_OK;
 }
 

@@ -1130,6 +1130,399 @@ tcs_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------
+// Backward of one residual layer's gate + projection for the fused shape (R = G = 64), one pass over the tile:
+//   dz   = dout . Wp + dzs_l                       (K-major GEMM, N = 64)
+//   dafg = gate derivative of dz (z, sigmoid)      (epilogue; z comes from the shared-memory tile)
+//   dWp += dout^T . z                              (MN-major GEMM over the same 128 rows, TMEM-resident accumulator)
+// In the split format the [128 positions x 64 channels] fp16 tiles of dout serve BOTH as the K-major A operand of the dz
+// GEMM and as the MN-major A operand of the dWp GEMM (same bytes, same 128-byte swizzle), so dout and z are read from
+// HBM exactly once and nothing is re-fetched through L2.
+struct SGateBwdArgs {
+  const float* dzs;        // fp32 [rows][64], carries gscale
+  const float* sg;         // fp32 [rows][sg_ld]
+  __half* dafg;            // split [rows][hi 128 | lo 128], carries gscale
+  float* dWp;              // [64 r][64 g]
+  int sg_ld, zp;
+  int rows_out, tiles_per_seq, num_tiles;
+  int reverse;
+  float wscale;            // 1 / (gscale * ACT_SCALE)
+};
+constexpr int SG_W = 0;                         // Wp^T split: hi [64 g x 64 r] 8 KB, lo 8 KB
+constexpr int SG_ST = 16384;                    // 2 stages x {dout hi, dout lo, z hi, z lo}
+constexpr int SG_ZERO = SG_ST + 2 * 65536;      // 16 KB of zeros: M atom 1 of the dWp MMA (channels 64..127)
+constexpr int SG_BAR = SG_ZERO + SUB;
+constexpr int SG_SMEM = SG_BAR + 256;
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+tcs_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_dout, const __grid_constant__ CUtensorMap tm_z,
+                    const __grid_constant__ CUtensorMap tm_w, const SGateBwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + SG_BAR;
+  const uint32_t w_full = bar0, wg_full = bar0 + 8;
+  auto full = [&](int s) { return bar0 + 16 + 8 * s; };
+  auto empty = [&](int s) { return bar0 + 32 + 8 * s; };
+  auto acc_full = [&](int s) { return bar0 + 48 + 8 * s; };
+  auto acc_empty = [&](int s) { return bar0 + 64 + 8 * s; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + SG_BAR + 128);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(w_full, 1);
+    mbar_init(wg_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 257);       // the MMA commit + 256 epilogue threads (they read z from the stage)
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), 256);
+    }
+    fence_barrier_init();
+    prefetch_tmap(&tm_dout);
+    prefetch_tmap(&tm_z);
+    prefetch_tmap(&tm_w);
+  }
+  for (int i = threadIdx.x; i < SUB / 16; i += blockDim.x) reinterpret_cast<uint4*>(gbase + SG_ZERO)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  if (warp == 1) tmem_alloc<256>(smem_u32((const void*)tmem_slot));
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int n_local = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_of = [&](int j) {
+    const int i = (int)blockIdx.x + j * (int)gridDim.x;
+    return a.reverse ? a.num_tiles - 1 - i : i;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, 16384);
+      tma_load_2d(base + SG_W, &tm_w, w_full, 0, 0);
+      tma_load_2d(base + SG_W + 8192, &tm_w, w_full, KB, 0);
+      for (int j = 0; j < n_local; ++j) {
+        const int tile = tile_of(j);
+        const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM;
+        const int s = j & 1, ph = (j >> 1) & 1;
+        mbar_wait(empty(s), ph ^ 1);
+        const uint32_t st = base + SG_ST + s * 65536;
+        mbar_arrive_expect_tx(full(s), 65536);
+        tma_load_4d(st + 0 * SUB, &tm_dout, full(s), 0, t0, b, 0);
+        tma_load_4d(st + 1 * SUB, &tm_dout, full(s), KB, t0, b, 0);
+        tma_load_4d(st + 2 * SUB, &tm_z, full(s), 0, t0, b, 0);
+        tma_load_4d(st + 3 * SUB, &tm_z, full(s), KB, t0, b, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_local > 0) {
+      constexpr uint32_t idesc = idesc_f16(128, 64);
+      constexpr uint32_t idesc_mn = idesc_f16(128, 64) | IDESC_MN_MAJOR;
+      mbar_wait(w_full, 0);
+      for (int j = 0; j < n_local; ++j) {
+        const int s = j & 1, ph = (j >> 1) & 1;
+        mbar_wait(acc_empty(s), ph ^ 1);
+        mbar_wait(full(s), ph);
+        tcgen05_fence_after();
+        const uint32_t st = base + SG_ST + s * 65536, wb = base + SG_W;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {   // cross terms first (round-toward-zero accumulation, see tcs_layer_kernel)
+          umma_f16(tmem + s * 64, umma_desc_k_sw128(st + k4 * 32), umma_desc_k_sw128(wb + 8192 + k4 * 32), idesc, k4 > 0);
+          umma_f16(tmem + s * 64, umma_desc_k_sw128(st + SUB + k4 * 32), umma_desc_k_sw128(wb + k4 * 32), idesc, 1u);
+        }
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+          umma_f16(tmem + s * 64, umma_desc_k_sw128(st + k4 * 32), umma_desc_k_sw128(wb + k4 * 32), idesc, 1u);
+        umma_commit(acc_full(s));
+        // dWp[r][g] += sum_pos dout[pos][r] * z[pos][g]: A = dout tile read MN-major (atom 1 = zeros), B = z tile MN-major
+        const uint32_t zero = base + SG_ZERO;
+#pragma unroll
+        for (int k16 = 0; k16 < TM / 16; ++k16) {
+          const uint64_t ah = desc_mn_sw128(st + k16 * 2048, zero - st, 1024);
+          const uint64_t al = desc_mn_sw128(st + SUB + k16 * 2048, zero - (st + SUB), 1024);
+          const uint64_t bh = desc_mn_sw128(st + 2 * SUB + k16 * 2048, SUB, 1024);
+          const uint64_t bl = desc_mn_sw128(st + 3 * SUB + k16 * 2048, SUB, 1024);
+          umma_f16(tmem + 128, ah, bl, idesc_mn, (j | k16) > 0);
+          umma_f16(tmem + 128, al, bh, idesc_mn, 1u);
+          umma_f16(tmem + 128, ah, bh, idesc_mn, 1u);
+        }
+        umma_commit(empty(s));
+      }
+      umma_commit(wg_full);
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    for (int j = 0; j < n_local; ++j) {
+      const int tile = tile_of(j);
+      const int s = j & 1, ph = (j >> 1) & 1;
+      const int b = tile / a.tiles_per_seq, t = (tile % a.tiles_per_seq) * TM + row;
+      const bool valid = t < a.rows_out;
+      const int64_t orow = (int64_t)b * a.rows_out + min(t, a.rows_out - 1);
+      const float live = t >= a.zp ? 1.f : 0.f;
+      const uint8_t* st = gbase + SG_ST + s * 65536;
+      // the epilogue inputs that do not depend on the accumulator: issue their loads before waiting for it
+      float4 d4[8], s4[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        d4[i] = *reinterpret_cast<const float4*>(a.dzs + orow * 64 + half * 32 + i * 4);
+        s4[i] = *reinterpret_cast<const float4*>(a.sg + orow * a.sg_ld + half * 32 + i * 4);
+      }
+      mbar_wait(full(s), ph);               // z tile visible to this thread's generic loads
+      mbar_wait(acc_full(s), ph);
+      tcgen05_fence_after();
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + s * 64 + half * 32, v);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      mbar_arrive(acc_empty(s));
+      __half* drow = a.dafg + orow * 256 + half * 32;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 zh = *reinterpret_cast<const uint4*>(st + 2 * SUB + sw128_off(row, half * 4 + c));
+        const uint4 zl = *reinterpret_cast<const uint4*>(st + 3 * SUB + sw128_off(row, half * 4 + c));
+        const float4 z0 = scale4(join4(make_uint2(zh.x, zh.y), make_uint2(zl.x, zl.y)), INV_ACT);
+        const float4 z1 = scale4(join4(make_uint2(zh.z, zh.w), make_uint2(zl.z, zl.w)), INV_ACT);
+        const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+        const float dd[8] = {d4[2 * c].x, d4[2 * c].y, d4[2 * c].z, d4[2 * c].w, d4[2 * c + 1].x, d4[2 * c + 1].y, d4[2 * c + 1].z, d4[2 * c + 1].w};
+        const float ss[8] = {s4[2 * c].x, s4[2 * c].y, s4[2 * c].z, s4[2 * c].w, s4[2 * c + 1].x, s4[2 * c + 1].y, s4[2 * c + 1].z, s4[2 * c + 1].w};
+        float df[8], dg[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gate_deriv(fmaf(__uint_as_float(v[8 * c + i]), INV_W, dd[i]), zz[i], ss[i], live, df[i], dg[i]);
+        uint4 fh, fl, gh, gl;
+        split2(df[0], df[1], fh.x, fl.x), split2(df[2], df[3], fh.y, fl.y), split2(df[4], df[5], fh.z, fl.z), split2(df[6], df[7], fh.w, fl.w);
+        split2(dg[0], dg[1], gh.x, gl.x), split2(dg[2], dg[3], gh.y, gl.y), split2(dg[4], dg[5], gh.z, gl.z), split2(dg[6], dg[7], gh.w, gl.w);
+        if (valid) {
+          *reinterpret_cast<uint4*>(drow + c * 8) = fh;            // da_f hi
+          *reinterpret_cast<uint4*>(drow + 64 + c * 8) = gh;       // da_g hi
+          *reinterpret_cast<uint4*>(drow + 128 + c * 8) = fl;      // da_f lo
+          *reinterpret_cast<uint4*>(drow + 192 + c * 8) = gl;      // da_g lo
+        }
+      }
+      mbar_arrive(empty(s));                // done reading z from the stage
+    }
+    if (n_local > 0 && q < 2) {
+      // dWp rows (projection output channels r) live in TMEM lanes 0..63, columns = g
+      mbar_wait(wg_full, 0);
+      tcgen05_fence_after();
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 128 + half * 32, v);
+      tmem_ld_wait();
+      float* wrow = a.dWp + (int64_t)row * 64 + half * 32;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        red_add_v4(wrow + 4 * i, make_float4(__uint_as_float(v[4 * i]) * a.wscale, __uint_as_float(v[4 * i + 1]) * a.wscale,
+                                             __uint_as_float(v[4 * i + 2]) * a.wscale, __uint_as_float(v[4 * i + 3]) * a.wscale));
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward of one residual layer's dilated conv for the fused shape (R = G = 64, two taps), one pass over dafg:
+//   dx[t]  = dout[t] + dafg[t] . W1(tap 1) + dafg[t+d] . W1(tap 0)       (K-major GEMM, K = 2 x 128, N = 64)
+//   dW_f/g(o, c, tap) += sum_t dafg[t][o] * x[t - (1-tap) d][c]             (MN-major GEMM over the same rows)
+// The ring streams "units" (row slab 0/1, gate half f/g): A = [128 positions x 64 channels] hi + lo planes of dafg,
+// B = the matching [64 c x 64 k] block of W1^T.  The slab-0 units double as the MN-major A operand of the weight
+// gradient (M atom 0 = the unit's 64 gate channels, atom 1 = zeros; one accumulator per gate half), B = [x(t-d) | x(t)].
+struct SDxwArgs {
+  const __half* rsd;       // dout of the layer above, split [rows][hi 64 | lo 64]; null for the top layer
+  __half* Y;               // new dout, split
+  float* dWf;              // (o, c, tap) with row stride 128
+  float* dWg;
+  int d;
+  int rows_out, tiles_per_seq, num_tiles;
+  int reverse;
+  float wscale;            // 1 / (gscale * ACT_SCALE)
+};
+constexpr int SD_STAGE = 2 * SUB + 2 * 8192;    // A hi, A lo [128 x 64], B hi, B lo [64 x 64]
+constexpr int SD_STAGES = 3;
+constexpr int SD_X = SD_STAGES * SD_STAGE;      // x(t-d) hi | x(t) hi | x(t-d) lo | x(t) lo
+constexpr int SD_ZERO = SD_X + 4 * SUB;
+constexpr int SD_BAR = SD_ZERO + SUB;
+constexpr int SD_SMEM = SD_BAR + 256;
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant__ CUtensorMap tm_w,
+               const __grid_constant__ CUtensorMap tm_x, const SDxwArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + SD_BAR;
+  auto full = [&](int s) { return bar0 + 8 * s; };
+  auto empty = [&](int s) { return bar0 + 32 + 8 * s; };
+  auto acc_full = [&](int s) { return bar0 + 64 + 8 * s; };
+  auto acc_empty = [&](int s) { return bar0 + 80 + 8 * s; };
+  const uint32_t x_full = bar0 + 96, x_empty = bar0 + 104, wg_full = bar0 + 112;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + SD_BAR + 128);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SD_STAGES; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), 256);
+    }
+    mbar_init(x_full, 1);
+    mbar_init(x_empty, 1);
+    mbar_init(wg_full, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tm_da);
+    prefetch_tmap(&tm_w);
+    prefetch_tmap(&tm_x);
+  }
+  for (int i = threadIdx.x; i < SUB / 16; i += blockDim.x) reinterpret_cast<uint4*>(gbase + SD_ZERO)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  if (warp == 1) tmem_alloc<512>(smem_u32((const void*)tmem_slot));
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int n_local = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_of = [&](int j) {
+    const int i = (int)blockIdx.x + j * (int)gridDim.x;
+    return a.reverse ? a.num_tiles - 1 - i : i;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int j = 0; j < n_local; ++j) {
+        const int tile = tile_of(j);
+        const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM;
+        mbar_wait(x_empty, (j & 1) ^ 1);
+        const uint32_t xs = base + SD_X;
+        mbar_arrive_expect_tx(x_full, 4 * SUB);
+        tma_load_4d(xs + 0 * SUB, &tm_x, x_full, 0, t0 - a.d, b, 0);
+        tma_load_4d(xs + 1 * SUB, &tm_x, x_full, 0, t0, b, 0);
+        tma_load_4d(xs + 2 * SUB, &tm_x, x_full, KB, t0 - a.d, b, 0);
+        tma_load_4d(xs + 3 * SUB, &tm_x, x_full, KB, t0, b, 0);
+        for (int u = 0; u < 4; ++u, ++it) {
+          const int sl = u >> 1, ch = u & 1;
+          const int s = it % SD_STAGES, ph = (it / SD_STAGES) & 1;
+          mbar_wait(empty(s), ph ^ 1);
+          const uint32_t st = base + s * SD_STAGE;
+          mbar_arrive_expect_tx(full(s), SD_STAGE);
+          tma_load_4d(st, &tm_da, full(s), ch * KB, t0 + sl * a.d, b, 0);                 // dafg hi plane, gate half ch
+          tma_load_4d(st + SUB, &tm_da, full(s), 128 + ch * KB, t0 + sl * a.d, b, 0);     // lo plane
+          tma_load_2d(st + 2 * SUB, &tm_w, full(s), sl * 128 + ch * KB, 0);               // W1^T[c][slab*128 + n] hi
+          tma_load_2d(st + 2 * SUB + 8192, &tm_w, full(s), 256 + sl * 128 + ch * KB, 0);  // lo
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_local > 0) {
+      constexpr uint32_t idesc = idesc_f16(128, 64);
+      constexpr uint32_t idesc_mn = idesc_f16(128, 128) | IDESC_MN_MAJOR;
+      const uint32_t zero = base + SD_ZERO, xs = base + SD_X;
+      int it = 0;
+      for (int j = 0; j < n_local; ++j) {
+        const int ab = j & 1, aph = (j >> 1) & 1;
+        for (int u = 0; u < 4; ++u, ++it) {
+          const int s = it % SD_STAGES, ph = (it / SD_STAGES) & 1;
+          if (u == 0) {
+            mbar_wait(acc_empty(ab), aph ^ 1);
+            mbar_wait(x_full, j & 1);
+          }
+          mbar_wait(full(s), ph);
+          tcgen05_fence_after();
+          const uint32_t st = base + s * SD_STAGE, wb = st + 2 * SUB;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            umma_f16(tmem + ab * 64, umma_desc_k_sw128(st + k4 * 32), umma_desc_k_sw128(wb + 8192 + k4 * 32), idesc, (u | k4) > 0);
+            umma_f16(tmem + ab * 64, umma_desc_k_sw128(st + SUB + k4 * 32), umma_desc_k_sw128(wb + k4 * 32), idesc, 1u);
+          }
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma_f16(tmem + ab * 64, umma_desc_k_sw128(st + k4 * 32), umma_desc_k_sw128(wb + k4 * 32), idesc, 1u);
+          if (u < 2) {
+            // weight gradient of gate half u: accumulator columns [128 + u*128, +128) = (tap, c)
+#pragma unroll
+            for (int k16 = 0; k16 < TM / 16; ++k16) {
+              const uint64_t ah = desc_mn_sw128(st + k16 * 2048, zero - st, 1024);
+              const uint64_t al = desc_mn_sw128(st + SUB + k16 * 2048, zero - (st + SUB), 1024);
+              const uint64_t bh = desc_mn_sw128(xs + k16 * 2048, SUB, 1024);
+              const uint64_t bl = desc_mn_sw128(xs + 2 * SUB + k16 * 2048, SUB, 1024);
+              umma_f16(tmem + 128 + u * 128, ah, bl, idesc_mn, (j | k16) > 0);
+              umma_f16(tmem + 128 + u * 128, al, bh, idesc_mn, 1u);
+              umma_f16(tmem + 128 + u * 128, ah, bh, idesc_mn, 1u);
+            }
+          }
+          umma_commit(empty(s));
+          if (u == 1) umma_commit(x_empty);
+          if (u == 3) umma_commit(acc_full(ab));
+        }
+      }
+      umma_commit(wg_full);
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    for (int j = 0; j < n_local; ++j) {
+      const int tile = tile_of(j);
+      const int ab = j & 1, aph = (j >> 1) & 1;
+      const int b = tile / a.tiles_per_seq, t = (tile % a.tiles_per_seq) * TM + row;
+      const bool valid = t < a.rows_out;
+      const int64_t orow = (int64_t)b * a.rows_out + min(t, a.rows_out - 1);
+      uint4 rh[4], rl[4];      // residual gradient (split): independent of the accumulator, loaded before waiting for it
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (a.rsd) {
+          rh[c] = *reinterpret_cast<const uint4*>(a.rsd + orow * 128 + half * 32 + c * 8);
+          rl[c] = *reinterpret_cast<const uint4*>(a.rsd + orow * 128 + 64 + half * 32 + c * 8);
+        } else {
+          rh[c] = rl[c] = make_uint4(0u, 0u, 0u, 0u);   // top layer: nothing flows in from above
+        }
+      }
+      mbar_wait(acc_full(ab), aph);
+      tcgen05_fence_after();
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * 64 + half * 32, v);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      mbar_arrive(acc_empty(ab));
+      __half* yrow = a.Y + orow * 128 + half * 32;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 r0 = join4(make_uint2(rh[c].x, rh[c].y), make_uint2(rl[c].x, rl[c].y));
+        const float4 r1 = join4(make_uint2(rh[c].z, rh[c].w), make_uint2(rl[c].z, rl[c].w));
+        uint4 oh, ol;
+        split2(fmaf(__uint_as_float(v[8 * c + 0]), INV_W, r0.x), fmaf(__uint_as_float(v[8 * c + 1]), INV_W, r0.y), oh.x, ol.x);
+        split2(fmaf(__uint_as_float(v[8 * c + 2]), INV_W, r0.z), fmaf(__uint_as_float(v[8 * c + 3]), INV_W, r0.w), oh.y, ol.y);
+        split2(fmaf(__uint_as_float(v[8 * c + 4]), INV_W, r1.x), fmaf(__uint_as_float(v[8 * c + 5]), INV_W, r1.y), oh.z, ol.z);
+        split2(fmaf(__uint_as_float(v[8 * c + 6]), INV_W, r1.z), fmaf(__uint_as_float(v[8 * c + 7]), INV_W, r1.w), oh.w, ol.w);
+        if (valid) {
+          *reinterpret_cast<uint4*>(yrow + c * 8) = oh;
+          *reinterpret_cast<uint4*>(yrow + 64 + c * 8) = ol;
+        }
+      }
+    }
+    if (n_local > 0 && q < 2) {
+      // dW_f / dW_g: TMEM lanes 0..63 = gate channel o, columns tap*64 + c; the gradient layout is (o, c, tap)
+      mbar_wait(wg_full, 0);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int gate = 0; gate < 2; ++gate) {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 128 + gate * 128 + half * 32, v0);        // tap 0, channels half*32..
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 128 + gate * 128 + 64 + half * 32, v1);   // tap 1
+        tmem_ld_wait();
+        float* wrow = (gate == 0 ? a.dWf : a.dWg) + (int64_t)row * 128 + half * 64;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          red_add_v4(wrow + 4 * i, make_float4(__uint_as_float(v0[2 * i]) * a.wscale, __uint_as_float(v1[2 * i]) * a.wscale,
+                                               __uint_as_float(v0[2 * i + 1]) * a.wscale, __uint_as_float(v1[2 * i + 1]) * a.wscale));
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1385,6 +1778,69 @@ int tcs_wgrad(const wn_handle* h, const SOperand& dY, int a_row_off, int a_c0, i
   if (NB == 64) return launch_swgrad<64, 2>(ta, tb, g, h->sm_count, s);
   if (NB == 128) return launch_swgrad<128, 2>(ta, tb, g, h->sm_count, s);
   return launch_swgrad<256, 2>(ta, tb, g, h->sm_count, s);
+}
+
+// dz GEMM + gate derivative + dWp in one pass (fused shape R = G = 64); dWp must be 16-byte aligned
+int tcs_gate_bwd(const wn_handle* h, const __half* dout, const __half* wpt, const float* dzs, const __half* z, const float* sg,
+                 int sg_ld, __half* dafg, float* dWp, int zp, int rows, int num_seq, int reverse, float wscale, cudaStream_t s) {
+  CUtensorMap td, tz, tw;
+  const uint64_t seq = (uint64_t)rows * 128, all = seq * num_seq;
+  WN_TRY(map_h4d(&td, dout, 128, rows, num_seq, 1, 128, seq, all, TM));
+  WN_TRY(map_h4d(&tz, z, 128, rows, num_seq, 1, 128, seq, all, TM));
+  WN_TRY(map_h2d(&tw, wpt, 128, 64, 128, 64));
+  SGateBwdArgs g;
+  memset(&g, 0, sizeof(g));
+  g.dzs = dzs;
+  g.sg = sg;
+  g.sg_ld = sg_ld;
+  g.dafg = dafg;
+  g.dWp = dWp;
+  g.zp = zp;
+  g.reverse = reverse;
+  g.wscale = wscale;
+  g.rows_out = rows;
+  g.tiles_per_seq = (rows + TM - 1) / TM;
+  g.num_tiles = g.tiles_per_seq * num_seq;
+  static bool attr = false;
+  if (!attr) {
+    WN_CHECK_CUDA(cudaFuncSetAttribute(tcs_gate_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SG_SMEM + 1024));
+    attr = true;
+  }
+  const int grid = g.num_tiles < h->sm_count ? g.num_tiles : h->sm_count;
+  tcs_gate_bwd_kernel<<<grid, NTHREADS, SG_SMEM + 1024, s>>>(td, tz, tw, g);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+// dx GEMM + dW_f/dW_g in one pass over dafg (fused shape R = G = 64, two taps); gradient pointers 16-byte aligned
+int tcs_dxw(const wn_handle* h, const __half* dafg, const __half* w1t, const __half* rsd, const __half* x, __half* Y, float* dWf,
+            float* dWg, int d, int rows, int num_seq, int reverse, float wscale, cudaStream_t s) {
+  CUtensorMap ta, tw, tx;
+  const uint64_t seqa = (uint64_t)rows * 256, alla = seqa * num_seq, seqx = (uint64_t)rows * 128, allx = seqx * num_seq;
+  WN_TRY(map_h4d(&ta, dafg, 256, rows, num_seq, 1, 256, seqa, alla, TM));
+  WN_TRY(map_h2d(&tw, w1t, 512, 64, 512, 64));
+  WN_TRY(map_h4d(&tx, x, 128, rows, num_seq, 1, 128, seqx, allx, TM));
+  SDxwArgs g;
+  memset(&g, 0, sizeof(g));
+  g.rsd = rsd;
+  g.Y = Y;
+  g.dWf = dWf;
+  g.dWg = dWg;
+  g.d = d;
+  g.reverse = reverse;
+  g.wscale = wscale;
+  g.rows_out = rows;
+  g.tiles_per_seq = (rows + TM - 1) / TM;
+  g.num_tiles = g.tiles_per_seq * num_seq;
+  static bool attr = false;
+  if (!attr) {
+    WN_CHECK_CUDA(cudaFuncSetAttribute(tcs_dxw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_SMEM + 1024));
+    attr = true;
+  }
+  const int grid = g.num_tiles < h->sm_count ? g.num_tiles : h->sm_count;
+  tcs_dxw_kernel<<<grid, NTHREADS, SD_SMEM + 1024, s>>>(ta, tw, tx, g);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
 }
 
 inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
@@ -1694,7 +2150,16 @@ int tcs_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s
     const int sg_ld = h->tape_gates_zs ? G : 2 * G;
     SOperand Z{HP(ws + t.z[l]), G, W, B, 1, 0};
     __half* dafg = HP(ws + t.dafg);
-    if (dout) {
+    float* dwp = grads + ly.proj.w_off;
+    float* dwf = grads + ly.wf.w_off;
+    float* dwg = grads + ly.wg.w_off;
+    const bool fused = fused_shape(h) && (((uintptr_t)dwp | (uintptr_t)dwf | (uintptr_t)dwg) & 15) == 0 &&
+                       getenv("WN_NO_BWD_FUSE") == nullptr;
+    if (dout && fused) {
+      // fused: gate forwards, dxw backwards (serpentine hand-off through L2)
+      WN_TRY(tcs_gate_bwd(h, dout, HP(ws + t.tc_wpt) + (int64_t)l * 2 * G * R, dzs, HP(ws + t.z[l]), sg, sg_ld, dafg, dwp, zp, W, B,
+                          serp ? 0 : 0, inv_wg, s));
+    } else if (dout) {
       // dz = dout . Wp + dzs_l, gate derivative fused into the epilogue -> dafg
       SOperand DO{dout, R, W, B, 1, 0};
       SEpilogue e;
@@ -1719,6 +2184,14 @@ int tcs_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s
       WN_CHECK_LAUNCH();
     }
     SOperand DA{dafg, 2 * G, W, B, 1, 0};
+    if (fused) {
+      __half* dnew = HP(ws + t.dout[dt]);
+      WN_TRY(tcs_dxw(h, dafg, HP(ws + t.tc_w1t) + (int64_t)l * 2 * (R * 4 * G), dout, HP(ws + t.x[l]), dnew, dwf, dwg, ly.dilation, W,
+                     B, serp ? 1 : 0, inv_wg, s));
+      dout = dnew;
+      dt ^= 1;
+      continue;
+    }
     {
       // dW_{f,g}(o, c, tap) += da[t][o] * x[t - (1-tap) d][c]; both taps share a launch while 2R fits one N tile
       SOperand X{HP(ws + t.x[l]), R, W, B, 1, 0};
@@ -1799,4 +2272,16 @@ extern "C" int wn_tcs_debug_wgrad(wn_handle* h, const void* dy_split, int M, con
   SOperand dY{reinterpret_cast<const __half*>(dy_split), M, rows, num_seq, 1, 0};
   SOperand X{reinterpret_cast<const __half*>(x_split), C, rows, num_seq, 1, 0};
   return tcs_wgrad(h, dY, 0, 0, M, X, 1, &x_row_off, nullptr, &dW, nullptr, 256, rows, C, 1, scale, (cudaStream_t)stream);
+}
+
+// Profiling hooks (bench.py roofline): ONE launch of the fused fp16x2 residual-layer kernel / of the skip GEMM on the bound
+// tape; require a preceding fp16x2 wn_forward_residual_block (weights prepared, x[l] in split format).
+extern "C" int wn_tcs_layer_forward(wn_handle* h, int layer, void* stream) {
+  WN_REQUIRE(h && h->ws && h->tape_split && fused_shape(h), WN_ESTATE, "wn_tcs_layer_forward: run an fp16x2 forward of the fused shape first");
+  WN_REQUIRE(layer >= 0 && layer < (int)h->layers.size(), WN_EINVAL, "bad layer index");
+  return tcs_layer_launch(h, layer, (cudaStream_t)stream);
+}
+extern "C" int wn_tcs_skip_gemm(wn_handle* h, void* stream) {
+  WN_REQUIRE(h && h->ws && h->tape_split, WN_ESTATE, "wn_tcs_skip_gemm: run an fp16x2 forward first");
+  return tcs_skip_gemm(h, (cudaStream_t)stream);
 }

@@ -3,6 +3,8 @@ the one-hot image.  The arithmetic is NumPy on the host exactly as in the
 reference (it runs once per file, outside the hot path); wn_mulaw_encode/decode
 in the C ABI are the on-device variants for resident signals.
 """
+import warnings
+
 import numpy as np
 from scipy.io import wavfile
 
@@ -25,6 +27,9 @@ def quantize_signal(signal, quantization_steps=256, format="16bit_pcm"):
     max = _fmt_max(format)
     if np.issubdtype(signal.dtype, np.integer):
         # data.py:17 under Python 2: `signal /= max` on an integer array is floor division
+        warnings.warn("mono integer PCM: the reference divides the int array in place (Python-2 floor division, data.py:8-17), "
+                      "which collapses the signal to classes {0, 127}; kept for parity -- convert the file to stereo or "
+                      "float PCM to train on real audio", RuntimeWarning, stacklevel=2)
         signal = np.floor_divide(signal.astype(np.int64), max).astype(signal.dtype)
     else:
         signal = signal / max

@@ -86,8 +86,8 @@ class FasterWaveNet(WaveNet):
         self._need_gpu()
         if not hasattr(self, "prev_causal_outputs") or self.prev_causal_outputs is None:
             probs = self.prime(x_batch_data)
-            if not apply_softmax:
-                probs = torch.log(probs)   # log-probabilities: logits up to the per-row constant
+            if not apply_softmax:          # the raw head output of the priming pass (faster_wavenet.py:51-52 -> :17-22)
+                check(self._libh.wn_gen_logits(self._gen, _ptr(probs), _stream()))
         else:
             idx = self._to_indices(x_batch_data)
             probs = self.step(idx[:, -1], apply_softmax)
