@@ -556,6 +556,37 @@ tcs_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
+// ---- 256-bit global accesses (sm_100): one full 32-byte sector per lane and instruction -------------------
+__device__ __forceinline__ void ld256(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void st256(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// 16 consecutive channels of a split row (hi plane at p, lo plane at p + C) -> fp32
+__device__ __forceinline__ void load_split16(const __half* p, int C, float (&o)[16]) {
+  uint32_t h[8], l[8];
+  ld256(p, h);
+  ld256(p + C, l);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 a = __half22float2(bits_h2(h[i])), b = __half22float2(bits_h2(l[i]));
+    o[2 * i] = a.x + b.x;
+    o[2 * i + 1] = a.y + b.y;
+  }
+}
+__device__ __forceinline__ void store_split16(__half* p, int C, const float (&o)[16]) {
+  uint32_t h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split2(o[2 * i], o[2 * i + 1], h[i], l[i]);
+  st256(p, h);
+  st256(p + C, l);
+}
+
 // ------------------------------------------------------------------------------------------
 // Y[(b,t)][n] = epi( sum_slab  A[slab_idx][b][t + slab_row_off][:] . W[n][slab*K ...] ), both operands split.
 // The ring holds plane-stages [A_p 128x64 | B_p BNx64]; K block kb uses two consecutive stages (hi, lo).
@@ -602,7 +633,101 @@ struct SGemmCfg {
   static constexpr int SMEM = STG + 8 * 4096 + 1024 + 1024;
 };
 
-// MODE: 0 generic epilogue, 1 dz + gate derivative, 3 generic + column sums, 4 FLUSH (forward GEMMs): every 64-channel K
+// Row-per-lane epilogue of 32 output columns [c0, c0 + 32): lane = TMEM lane = output row, so the thread owns 128 contiguous
+// bytes of its row in every tensor it touches and moves them with 256-bit accesses (one full sector per lane and
+// instruction; no shared-memory transpose, no cross-lane traffic except the optional column sums).
+__device__ __forceinline__ void epi_row32(const SGemmArgs& a, const float (&v)[32], int c0, int t, int64_t orow, int b, float* cs_chunk,
+                                          int lane) {
+  const bool valid = t < a.rows_out;
+  const float relu_floor = a.relu ? 0.f : -INFINITY;
+  const bool zero_row = t < a.zero_rows_below;
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int col = c0 + hh * 16;
+    float o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = v[hh * 16 + i] * a.acc_scale;
+    if (a.bias) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + col) + i);
+        o[4 * i] += bb.x, o[4 * i + 1] += bb.y, o[4 * i + 2] += bb.z, o[4 * i + 3] += bb.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = zero_row ? 0.f : fmaxf(o[i], relu_floor);
+    if (a.Rsd) {
+      float r[16];
+      if (a.rsd_split) {
+        load_split16(reinterpret_cast<const __half*>(a.Rsd) + orow * (2 * (int64_t)a.ldr) + col, a.ldr, r);
+      } else {
+        uint32_t u[8];
+        const float* rp = reinterpret_cast<const float*>(a.Rsd) + orow * a.ldr + col;
+        ld256(rp, u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
+        ld256(rp + 8, u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[8 + i] = __uint_as_float(u[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = fmaf(r[i], a.rsd_scale, o[i]);
+    }
+    if (a.mask) {
+      float m[16];
+      const int64_t mrow = (int64_t)b * a.mask_rows_in + a.mask_row_off + min(t, a.rows_out - 1);
+      load_split16(a.mask + mrow * (2 * (int64_t)a.ldm) + col, a.ldm, m);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = m[i] > 0.f ? o[i] : 0.f;
+    }
+    if (cs_chunk) {
+      // column sums over the 32 rows of this warp: butterfly that halves the live values at every step; after four steps
+      // lane l holds column (l >> 1) & 15 summed over the 16 lanes that share bit 0 with it, the last step adds the two halves
+      float s[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s[i] = valid ? o[i] : 0.f;
+#pragma unroll
+      for (int w = 8; w >= 1; w >>= 1) {
+        const bool upper = (lane & (w << 1)) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i < w) {
+            const float send = upper ? s[i] : s[i + w];
+            const float keep = upper ? s[i + w] : s[i];
+            s[i] = keep + __shfl_xor_sync(0xffffffffu, send, w << 1);
+          }
+        }
+      }
+      s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+      if ((lane & 1) == 0) atomicAdd(cs_chunk + hh * 16 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1), s[0]);
+    }
+    if (valid) {
+      if (a.out_split) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] *= a.out_scale;
+        store_split16(reinterpret_cast<__half*>(a.Y) + orow * (2 * (int64_t)a.ldy) + col, a.ldy, o);
+      } else {
+        float* yp = reinterpret_cast<float*>(a.Y);
+        int ycol = col;
+        if (a.y_slab_cols > 0) {
+          yp += (int64_t)(col / a.y_slab_cols) * a.y_slab_stride;
+          ycol = col % a.y_slab_cols;
+        }
+        yp += orow * a.ldy + ycol;
+        uint32_t u[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u[i] = __float_as_uint(o[i]);
+        st256(yp, u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u[i] = __float_as_uint(o[8 + i]);
+        st256(yp + 8, u);
+      }
+    }
+  }
+}
+
+// MODE: 1 dz + gate derivative (generic shapes; staged, coalesced epilogue), 5 row-per-lane epilogue (bias / ReLU / zero
+// prefix / residual / ReLU mask / column sums, fp32 or split output), 4 = 5 + FLUSH (forward GEMMs): every 64-channel K
 // block is accumulated from zero in TMEM and ADDED TO REGISTERS by the epilogue warps in fp32 round-to-nearest -- the
 // tensor core truncates its accumulator toward zero at every MMA step, which costs ~1e-5 relative on a K = 1920
 // contraction (measured, tests/dev/check_rz.py: 9.7e-6 in one pass, 4.8e-7 flushed per block, 1.7e-6 for an fp32 SGEMM).
@@ -634,7 +759,7 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     prefetch_tmap(&tm_b);
   }
   if (warp == 1) tmem_alloc<512>(smem_u32((const void*)tmem_slot));
-  if constexpr (MODE == 3) {
+  if constexpr (MODE == 5) {
     if (threadIdx.x < BN) reinterpret_cast<float*>(gbase + Cfg::STG + 8 * 4096)[threadIdx.x] = 0.f;
   }
   tcgen05_fence_before();
@@ -749,45 +874,47 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           tcgen05_fence_before();
           mbar_arrive(acc_empty(ab));
         }
+        const int t = t0 + lane;
+        const int64_t orow = (int64_t)b * a.rows_out + min(t, a.rows_out - 1);
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch) {
-          const int ct = (half * CH + ch) * 32;
-          const int c0 = grp * BN + ct;
-          if (c0 >= a.N) continue;
-#pragma unroll
-          for (int cc = 0; cc < 8; ++cc)
-            *reinterpret_cast<float4*>(stg + lane * 128 + ((cc ^ (lane & 7)) << 4)) =
-                make_float4(acc[ch][4 * cc], acc[ch][4 * cc + 1], acc[ch][4 * cc + 2], acc[ch][4 * cc + 3]);
-          __syncwarp();
-          const int col = c0 + cc4;
-          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (a.bias) bb = *reinterpret_cast<const float4*>(a.bias + col);
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const int rr = jj * 4 + rsub;
-            const int t = t0 + rr;
-            if (t >= a.rows_out) continue;
-            const int64_t orow = (int64_t)b * a.rows_out + t;
-            float4 o = scale4(*reinterpret_cast<const float4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4)), a.acc_scale);
-            o.x += bb.x, o.y += bb.y, o.z += bb.z, o.w += bb.w;
-            if (a.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
-            if (t < a.zero_rows_below) o = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.Rsd) {
-              const float4 r = a.rsd_split ? load_split4(reinterpret_cast<const __half*>(a.Rsd), orow, a.ldr, col)
-                                           : *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.Rsd) + orow * a.ldr + col);
-              o.x = fmaf(r.x, a.rsd_scale, o.x), o.y = fmaf(r.y, a.rsd_scale, o.y);
-              o.z = fmaf(r.z, a.rsd_scale, o.z), o.w = fmaf(r.w, a.rsd_scale, o.w);
-            }
-            if (a.out_split)
-              store_split4(reinterpret_cast<__half*>(a.Y), orow, a.ldy, col, scale4(o, a.out_scale));
-            else
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.Y) + orow * a.ldy + col) = o;
-          }
-          __syncwarp();
+          const int c0 = grp * BN + (half * CH + ch) * 32;
+          if (c0 < a.N) epi_row32(a, acc[ch], c0, t, orow, b, nullptr, lane);
         }
       }
     }
-    for (int j = 0; MODE != 4 && j < n_local; ++j) {
+    if constexpr (MODE == 5) {
+      for (int j = 0; j < n_local; ++j) {
+        const int tile = a.reverse ? a.num_tiles - 1 - ((int)blockIdx.x + j * (int)gridDim.x) : (int)blockIdx.x + j * (int)gridDim.x;
+        const int ab = j & 1, aph = (j >> 1) & 1;
+        const int grp = tile % a.ngroups, rt = tile / a.ngroups;
+        const int b = rt / a.tiles_per_seq, t = (rt % a.tiles_per_seq) * TM + q * 32 + lane;
+        const int64_t orow = (int64_t)b * a.rows_out + min(t, a.rows_out - 1);
+        mbar_wait(acc_full(ab), aph);
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int ch = 0; ch < CH; ++ch) {
+          const int ct = (half * CH + ch) * 32;
+          const int c0 = grp * BN + ct;
+          uint32_t v[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * BN + ct, v);
+          tmem_ld_wait();
+          if (c0 >= a.N) continue;
+          float o[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i]);
+          epi_row32(a, o, c0, t, orow, b, a.colsum_out ? cs_smem + ct : nullptr, lane);
+        }
+        tcgen05_fence_before();
+        mbar_arrive(acc_empty(ab));
+      }
+      if (a.colsum_out) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps
+        const int c = threadIdx.x - 64;
+        if (c < BN && c < a.N) atomicAdd(a.colsum_out + c, cs_smem[c] * a.colsum_scale);
+      }
+    }
+    for (int j = 0; MODE == 1 && j < n_local; ++j) {
       const int tile = a.reverse ? a.num_tiles - 1 - ((int)blockIdx.x + j * (int)gridDim.x) : (int)blockIdx.x + j * (int)gridDim.x;
       const int ab = j & 1, aph = (j >> 1) & 1;
       const int grp = tile % a.ngroups, rt = tile / a.ngroups;
@@ -836,79 +963,11 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             store_split4(a.gate_dafg, orow, 2 * a.N, col, df);
             store_split4(a.gate_dafg, orow, 2 * a.N, a.N + col, dg);
           }
-        } else {
-          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (a.bias) bb = *reinterpret_cast<const float4*>(a.bias + col);
-          float4 r4[8], x4[8];
-          float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const int t = min(t0 + jj * 4 + rsub, a.rows_out - 1);
-            const int64_t orow = (int64_t)b * a.rows_out + t;
-            if (a.Rsd) {
-              if (a.rsd_split)
-                r4[jj] = load_split4(reinterpret_cast<const __half*>(a.Rsd), orow, a.ldr, col);
-              else
-                r4[jj] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.Rsd) + orow * a.ldr + col);
-            }
-            if (a.mask) x4[jj] = load_split4(a.mask, (int64_t)b * a.mask_rows_in + a.mask_row_off + t, a.ldm, col);
-          }
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const int rr = jj * 4 + rsub;
-            const int t = t0 + rr;
-            if (t >= a.rows_out) continue;
-            const int64_t orow = (int64_t)b * a.rows_out + t;
-            float4 o = scale4(*reinterpret_cast<const float4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4)), a.acc_scale);
-            o.x += bb.x, o.y += bb.y, o.z += bb.z, o.w += bb.w;
-            if (a.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
-            if (t < a.zero_rows_below) o = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.Rsd) {
-              o.x = fmaf(r4[jj].x, a.rsd_scale, o.x), o.y = fmaf(r4[jj].y, a.rsd_scale, o.y);
-              o.z = fmaf(r4[jj].z, a.rsd_scale, o.z), o.w = fmaf(r4[jj].w, a.rsd_scale, o.w);
-            }
-            if (a.mask) {
-              o.x = x4[jj].x > 0.f ? o.x : 0.f;
-              o.y = x4[jj].y > 0.f ? o.y : 0.f;
-              o.z = x4[jj].z > 0.f ? o.z : 0.f;
-              o.w = x4[jj].w > 0.f ? o.w : 0.f;
-            }
-            if (a.out_split) {
-              store_split4(reinterpret_cast<__half*>(a.Y), orow, a.ldy, col, scale4(o, a.out_scale));
-            } else {
-              float* ybase = reinterpret_cast<float*>(a.Y);
-              int ycol = col;
-              if (a.y_slab_cols > 0) {
-                ybase += (int64_t)(c0 / a.y_slab_cols) * a.y_slab_stride;
-                ycol = col % a.y_slab_cols;
-              }
-              *reinterpret_cast<float4*>(ybase + orow * a.ldy + ycol) = o;
-            }
-            if constexpr (MODE == 3) csum.x += o.x, csum.y += o.y, csum.z += o.z, csum.w += o.w;
-          }
-          if constexpr (MODE == 3) {
-#pragma unroll
-            for (int o = 8; o < 32; o <<= 1) {
-              csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o);
-              csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
-              csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o);
-              csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
-            }
-            if (lane < 8) {
-              float* c = cs_smem + ct + cc4;
-              atomicAdd(c, csum.x), atomicAdd(c + 1, csum.y), atomicAdd(c + 2, csum.z), atomicAdd(c + 3, csum.w);
-            }
-          }
         }
         __syncwarp();
       }
       tcgen05_fence_before();
       mbar_arrive(acc_empty(ab));
-    }
-    if constexpr (MODE == 3) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps
-      const int c = threadIdx.x - 64;
-      if (c < BN && c < a.N) atomicAdd(a.colsum_out + c, cs_smem[c] * a.colsum_scale);
     }
   }
   tcgen05_fence_before();
@@ -1599,8 +1658,7 @@ template <int BN>
 int launch_sgemm(const CUtensorMap& ta, const CUtensorMap& tb, const SGemmArgs& g, int sm_count, cudaStream_t s) {
   if (g.gate_sg) return launch_sgemm_mode<BN, 1>(ta, tb, g, sm_count, s);
   if (g.flush) return launch_sgemm_mode<BN, 4>(ta, tb, g, sm_count, s);
-  if (g.colsum_out && g.ngroups == 1) return launch_sgemm_mode<BN, 3>(ta, tb, g, sm_count, s);
-  return launch_sgemm_mode<BN, 0>(ta, tb, g, sm_count, s);
+  return launch_sgemm_mode<BN, 5>(ta, tb, g, sm_count, s);
 }
 
 template <int NB, int MH>
@@ -1647,6 +1705,7 @@ struct SEpilogue {
   int flush = 0;
   float* colsum_out = nullptr;
   float colsum_scale = 1.f;
+  bool ngroups_ok_for_colsum(int N, int BN) const { return N <= BN; }   // the per-CTA column-sum table covers one column group
 };
 
 inline __half* HP(float* p) { return reinterpret_cast<__half*>(p); }
@@ -1692,8 +1751,8 @@ int tcs_gemm(const wn_handle* h, const SOperand& A, int ns, const int* slab_idx,
   g.gate_sg_ld = e.gate_sg_ld ? e.gate_sg_ld : N;
   g.zero_rows_below = e.zero_rows_below;
   g.reverse = e.reverse;
-  g.flush = e.flush && !e.gate_sg && !e.mask && !e.colsum_out && e.y_slab_cols == 0;
-  g.colsum_out = e.colsum_out;
+  g.flush = e.flush && !e.gate_sg && !e.colsum_out;
+  g.colsum_out = e.ngroups_ok_for_colsum(N, BN) ? e.colsum_out : nullptr;
   g.colsum_scale = e.colsum_scale;
   g.rows_out = rows_out;
   g.nslab = ns;
