@@ -501,16 +501,19 @@ extern "C" int wn_cross_entropy(wn_handle* h, const int32_t* target, float* loss
   cudaStream_t s = (cudaStream_t)st;
   const Tape& t = h->tape;
   const int64_t rows = (int64_t)t.B * h->T;
-  WN_TRY(simt_cross_entropy(WS(t.hbuf.back()), target, rows, h->Q, (double*)WS(t.loss_acc), loss, WS(t.dlogits),
-                            WS(t.ce_colsum), &h->ce_colsum_valid, h->sm_count, s));
+  // the split backward keeps every gradient tensor in fp16 planes: dlogits (<= 1/rows in magnitude) are scaled by a power of
+  // two into [8, 16) so that the whole gradient stream sits in the fp16 normal range; weight-gradient reductions undo it
+  float gscale = 0.f;
   if (h->head_split) {
-    // the split backward keeps every gradient tensor in fp16 planes: scale dlogits (<= 1/rows in magnitude) by a power of
-    // two into [8, 16) so that the whole gradient stream sits in the fp16 normal range; weight-gradient reductions undo it
     int k = 3;
     while (((int64_t)1 << (k - 3)) < rows) ++k;
-    h->gscale = ldexpf(1.f, k);
-    WN_TRY(tcs_scale_split_dlogits(h, h->T, h->gscale, s));
+    gscale = ldexpf(1.f, k);
+    h->gscale = gscale;
   }
+  bool split_written = false;
+  WN_TRY(simt_cross_entropy(WS(t.hbuf.back()), target, rows, h->Q, (double*)WS(t.loss_acc), loss, WS(t.dlogits),
+                            WS(t.ce_colsum), &h->ce_colsum_valid, h->sm_count, s, gscale, &split_written));
+  if (h->head_split && !split_written) WN_TRY(tcs_scale_split_dlogits(h, h->T, h->gscale, s));   // generic Q: convert in place
   h->phase = PH_LOSS;
   return WN_OK;
 }

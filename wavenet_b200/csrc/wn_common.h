@@ -182,7 +182,8 @@ int simt_gate_backward(const float* tfsg, const float* dz, float* dafg, int64_t 
                        cudaStream_t s);
 int simt_softmax_rows(const float* in, float* out, int64_t rows, int Q, cudaStream_t s);
 int simt_cross_entropy(const float* logits, const int32_t* target, int64_t rows, int Q, double* acc, float* loss,
-                       float* dlogits, float* colsum, bool* colsum_written, int sm_count, cudaStream_t s);
+                       float* dlogits, float* colsum, bool* colsum_written, int sm_count, cudaStream_t s,
+                       float split_scale = 0.f, bool* split_written = nullptr);
 int simt_add_vec(const float* src, float* dst, int n, cudaStream_t s);
 int simt_onehot_to_index(const float* onehot, int B, int Q, int W, int32_t* idx, cudaStream_t s);
 

@@ -543,7 +543,9 @@ int simt_softmax_rows(const float* in, float* out, int64_t rows, int Q, cudaStre
 __global__ void __launch_bounds__(256) cross_entropy256_kernel(const float* __restrict__ logits,
                                                                const int32_t* __restrict__ target, int64_t rows,
                                                                double* __restrict__ acc, float* __restrict__ dlogits,
-                                                               float* __restrict__ colsum) {
+                                                               float* __restrict__ colsum, float split_scale) {
+  // split_scale > 0: dlogits leave as split fp16 rows [hi 256 | lo 256] scaled by split_scale (the fp16x2 backward's operand
+  // format, wn_tcs.cu) -- the same 1 KB per row as the fp32 row they replace
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   __shared__ double part[8];
   __shared__ float cs[8][256];
@@ -580,9 +582,26 @@ __global__ void __launch_bounds__(256) cross_entropy256_kernel(const float* __re
       c[i] += e[i];
     }
     xt = warp_sum(xt);
-    float4* o = reinterpret_cast<float4*>(dlogits + row * 256);
-    o[lane] = make_float4(e[0], e[1], e[2], e[3]);
-    o[32 + lane] = make_float4(e[4], e[5], e[6], e[7]);
+    if (split_scale > 0.f) {
+      __half* hrow = reinterpret_cast<__half*>(dlogits) + row * 512;
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        uint2 hi, lo;
+        const float v0 = e[4 * part] * split_scale, v1 = e[4 * part + 1] * split_scale, v2 = e[4 * part + 2] * split_scale,
+                    v3 = e[4 * part + 3] * split_scale;
+        const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y), l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
+        hi.x = *reinterpret_cast<const uint32_t*>(&h01), hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+        lo.x = *reinterpret_cast<const uint32_t*>(&l01), lo.y = *reinterpret_cast<const uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(hrow + part * 128 + lane * 4) = hi;
+        *reinterpret_cast<uint2*>(hrow + 256 + part * 128 + lane * 4) = lo;
+      }
+    } else {
+      float4* o = reinterpret_cast<float4*>(dlogits + row * 256);
+      o[lane] = make_float4(e[0], e[1], e[2], e[3]);
+      o[32 + lane] = make_float4(e[4], e[5], e[6], e[7]);
+    }
     if (lane == 0) my += (double)(m + logf(sum)) - (double)xt;
   }
 #pragma unroll
@@ -612,15 +631,17 @@ int simt_add_vec(const float* src, float* dst, int n, cudaStream_t s) {
 }
 
 int simt_cross_entropy(const float* logits, const int32_t* target, int64_t rows, int Q, double* acc, float* loss,
-                       float* dlogits, float* colsum, bool* colsum_written, int sm_count, cudaStream_t s) {
+                       float* dlogits, float* colsum, bool* colsum_written, int sm_count, cudaStream_t s, float split_scale,
+                       bool* split_written) {
   WN_CHECK_CUDA(cudaMemsetAsync(acc, 0, 2 * sizeof(double), s));
   const bool fast = Q == 256 && colsum && (((uintptr_t)logits | (uintptr_t)dlogits) & 15) == 0;
   if (colsum_written) *colsum_written = fast;
+  if (split_written) *split_written = fast && split_scale > 0.f;   // the generic kernel always writes fp32 rows
   if (fast) {
     WN_CHECK_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * 256, s));
     const int64_t want = blocks_for(rows, 8);
     const int grid = (int)(want < (int64_t)sm_count * 8 ? want : (int64_t)sm_count * 8);
-    cross_entropy256_kernel<<<grid, 256, 0, s>>>(logits, target, rows, acc, dlogits, colsum);
+    cross_entropy256_kernel<<<grid, 256, 0, s>>>(logits, target, rows, acc, dlogits, colsum, split_scale);
   } else {
     cross_entropy_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(logits, target, rows, Q, acc, dlogits);
   }

@@ -114,6 +114,83 @@ __device__ __forceinline__ void store_split4(__half* base, int64_t row, int C, i
   *reinterpret_cast<uint2*>(p + C) = lo;
 }
 
+// ---- 256-bit global accesses (sm_100): one full 32-byte sector per lane and instruction -------------------
+__device__ __forceinline__ void ld256(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void st256(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// 16 consecutive channels of a split row (hi plane at p, lo plane at p + C) -> fp32
+__device__ __forceinline__ void load_split16(const __half* p, int C, float (&o)[16]) {
+  uint32_t h[8], l[8];
+  ld256(p, h);
+  ld256(p + C, l);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 a = __half22float2(bits_h2(h[i])), b = __half22float2(bits_h2(l[i]));
+    o[2 * i] = a.x + b.x;
+    o[2 * i + 1] = a.y + b.y;
+  }
+}
+__device__ __forceinline__ void store_split16(__half* p, int C, const float (&o)[16]) {
+  uint32_t h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split2(o[2 * i], o[2 * i + 1], h[i], l[i]);
+  st256(p, h);
+  st256(p + C, l);
+}
+
+// ------------------------------------------------------------------------------------------
+// Y[(b,t)][n] = epi( sum_slab  A[slab_idx][b][t + slab_row_off][:] . W[n][slab*K ...] ), both operands split.
+// The ring holds plane-stages [A_p 128x64 | B_p BNx64]; K block kb uses two consecutive stages (hi, lo).
+struct SGemmArgs {
+  void* Y;                 // fp32 [rows][ldy] or split [rows][hi(ldy) | lo(ldy)]
+  int ldy, out_split;
+  const float* bias;       // [N] or null
+  int N;                   // valid output columns
+  int relu;
+  float acc_scale;         // multiplies the accumulator (undoes the operand scales)
+  float out_scale;         // multiplies the final result before it is stored (ACT_SCALE for stored activations)
+  float rsd_scale;         // multiplies the residual after loading
+  const void* Rsd;         // residual added to the result (same rows as Y): fp32 [rows][ldr] or split [rows][2*ldr]
+  int ldr, rsd_split;
+  const __half* mask;      // split tensor: result zeroed where mask[(b, mask_row_off + t)][n] <= 0, or null
+  int ldm, mask_rows_in, mask_row_off;
+  int rows_out;
+  int nslab, kblk;         // K = nslab * kblk * 64
+  int a_plane;             // elements between the hi and lo planes of an A row
+  int b_plane;             // elements between the planes of a W row (= total K)
+  int slab_row_off[MAX_SLABS];
+  int slab_idx[MAX_SLABS];
+  int tiles_per_seq, num_tiles, ngroups;
+  int y_slab_cols;         // >0 (fp32 output only): column block c goes to Y + (c / y_slab_cols) * y_slab_stride
+  int64_t y_slab_stride;
+  // gate-backward epilogue (MODE 1, N == G): acc + Rsd is dz; writes da_f | da_g into the split tensor gate_dafg
+  const float* gate_sg;    // [rows][gate_sg_ld] fp32 sigmoid
+  const __half* gate_z;    // split [rows][2N]
+  __half* gate_dafg;       // split [rows][2 * 2N]
+  int gate_zp, gate_sg_ld;
+  int zero_rows_below;
+  int reverse;
+  int flush;               // MODE 4: accumulate K blocks in registers (forward GEMMs; no mask / y_slab / colsum)
+  float* colsum_out;       // MODE 3: += colsum_scale * column sums of the stored result
+  float colsum_scale;
+};
+
+template <int BN>
+struct SGemmCfg {
+  static constexpr int STAGE = SUB + BN * 128;
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int BAR = STAGES * STAGE;
+  static constexpr int STG = BAR + 256;
+  static constexpr int SMEM = STG + 8 * 4096 + 1024 + 1024;
+};
+
 // fp32-grade gate nonlinearities (expf with full argument reduction; absolute error ~1e-7)
 __device__ __forceinline__ float tanh_acc(float x) { return 1.f - __fdividef(2.f, expf(2.f * x) + 1.f); }
 __device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.f, 1.f + expf(-x)); }
@@ -311,8 +388,7 @@ constexpr int SL_B1 = 0;
 constexpr int SL_B2 = 65536;
 constexpr int SL_A = 81920;
 constexpr int SL_BAR = SL_A + 2 * 65536;
-constexpr int SL_STG = SL_BAR + 256;           // 8 epilogue warps x 2 KB
-constexpr int SL_SMEM = SL_STG + 8 * 2048;
+constexpr int SL_SMEM = SL_BAR + 256;
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 tcs_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
@@ -434,7 +510,6 @@ tcs_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const int q = warp & 3;               // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;     // which 32 of the 64 channels this warp handles
     const int row = q * 32 + lane;
-    uint8_t* stg = gbase + SL_STG + (warp - 2) * 2048;
     if (threadIdx.x == 64) mbar_wait(b_full, 0);
     for (int j = 0; j < n_local; ++j) {
       const int tile = tile_of(j);
@@ -515,38 +590,19 @@ tcs_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       tmem_ld32(trow + 256 + s * 64 + half * 32, g);
       tmem_ld_wait();
       tcgen05_fence_before();
-      // x_out rows are [hi 64 | lo 64]: this warp owns channels [half*32, half*32+32) of 32 rows.  Stage 16 rows at a
-      // time as [hi 64 B | lo 64 B] so that every 16-byte store instruction covers whole 64-byte segments.
-      {
-        const int t_w0 = (tile % a.tiles_per_seq) * TM + q * 32;
-        __half* gblock = a.x_out + ((int64_t)b * a.W + t_w0) * 128 + half * 32;
-        const int rows_valid = a.W - t_w0;
+      // x_out rows are [hi 64 | lo 64] halves: the thread owns channels [half*32, +32) of its row = 64 contiguous bytes in
+      // each plane, written with two 256-bit stores per plane (full sectors, no staging)
+      if (valid) {
+        __half* xrow = a.x_out + ((int64_t)b * a.W + t) * 128 + half * 32;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          if ((lane >> 4) == hh) {
-            const int r = lane & 15;
+          uint32_t hv[8], lv[8];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint4 hv, lv;
-              split2(fmaf(__uint_as_float(g[8 * c + 0]), INV_W, xr[8 * c + 0]), fmaf(__uint_as_float(g[8 * c + 1]), INV_W, xr[8 * c + 1]), hv.x, lv.x);
-              split2(fmaf(__uint_as_float(g[8 * c + 2]), INV_W, xr[8 * c + 2]), fmaf(__uint_as_float(g[8 * c + 3]), INV_W, xr[8 * c + 3]), hv.y, lv.y);
-              split2(fmaf(__uint_as_float(g[8 * c + 4]), INV_W, xr[8 * c + 4]), fmaf(__uint_as_float(g[8 * c + 5]), INV_W, xr[8 * c + 5]), hv.z, lv.z);
-              split2(fmaf(__uint_as_float(g[8 * c + 6]), INV_W, xr[8 * c + 6]), fmaf(__uint_as_float(g[8 * c + 7]), INV_W, xr[8 * c + 7]), hv.w, lv.w);
-              *reinterpret_cast<uint4*>(stg + r * 128 + ((c ^ (r & 7)) << 4)) = hv;
-              *reinterpret_cast<uint4*>(stg + r * 128 + (((4 + c) ^ (r & 7)) << 4)) = lv;
-            }
-          }
-          __syncwarp();
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int rr = jj * 4 + (lane >> 3), ch = lane & 7;
-            const int rowi = hh * 16 + rr;
-            const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
-            // chunk 0..3: hi plane, 4..7: lo plane (64 halves further)
-            if (rowi < rows_valid)
-              *reinterpret_cast<uint4*>(gblock + (int64_t)rowi * 128 + (ch >> 2) * 64 + (ch & 3) * 8) = val;
-          }
-          __syncwarp();
+          for (int i = 0; i < 8; ++i)
+            split2(fmaf(__uint_as_float(g[hh * 16 + 2 * i]), INV_W, xr[hh * 16 + 2 * i]),
+                   fmaf(__uint_as_float(g[hh * 16 + 2 * i + 1]), INV_W, xr[hh * 16 + 2 * i + 1]), hv[i], lv[i]);
+          st256(xrow + hh * 16, hv);
+          st256(xrow + 64 + hh * 16, lv);
         }
       }
     }
@@ -555,83 +611,6 @@ tcs_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   __syncthreads();
   if (warp == 1) tmem_dealloc<512>(tmem);
 }
-
-// ---- 256-bit global accesses (sm_100): one full 32-byte sector per lane and instruction -------------------
-__device__ __forceinline__ void ld256(const void* p, uint32_t (&r)[8]) {
-  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "l"(p));
-}
-__device__ __forceinline__ void st256(void* p, const uint32_t (&r)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
-               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-// 16 consecutive channels of a split row (hi plane at p, lo plane at p + C) -> fp32
-__device__ __forceinline__ void load_split16(const __half* p, int C, float (&o)[16]) {
-  uint32_t h[8], l[8];
-  ld256(p, h);
-  ld256(p + C, l);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float2 a = __half22float2(bits_h2(h[i])), b = __half22float2(bits_h2(l[i]));
-    o[2 * i] = a.x + b.x;
-    o[2 * i + 1] = a.y + b.y;
-  }
-}
-__device__ __forceinline__ void store_split16(__half* p, int C, const float (&o)[16]) {
-  uint32_t h[8], l[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) split2(o[2 * i], o[2 * i + 1], h[i], l[i]);
-  st256(p, h);
-  st256(p + C, l);
-}
-
-// ------------------------------------------------------------------------------------------
-// Y[(b,t)][n] = epi( sum_slab  A[slab_idx][b][t + slab_row_off][:] . W[n][slab*K ...] ), both operands split.
-// The ring holds plane-stages [A_p 128x64 | B_p BNx64]; K block kb uses two consecutive stages (hi, lo).
-struct SGemmArgs {
-  void* Y;                 // fp32 [rows][ldy] or split [rows][hi(ldy) | lo(ldy)]
-  int ldy, out_split;
-  const float* bias;       // [N] or null
-  int N;                   // valid output columns
-  int relu;
-  float acc_scale;         // multiplies the accumulator (undoes the operand scales)
-  float out_scale;         // multiplies the final result before it is stored (ACT_SCALE for stored activations)
-  float rsd_scale;         // multiplies the residual after loading
-  const void* Rsd;         // residual added to the result (same rows as Y): fp32 [rows][ldr] or split [rows][2*ldr]
-  int ldr, rsd_split;
-  const __half* mask;      // split tensor: result zeroed where mask[(b, mask_row_off + t)][n] <= 0, or null
-  int ldm, mask_rows_in, mask_row_off;
-  int rows_out;
-  int nslab, kblk;         // K = nslab * kblk * 64
-  int a_plane;             // elements between the hi and lo planes of an A row
-  int b_plane;             // elements between the planes of a W row (= total K)
-  int slab_row_off[MAX_SLABS];
-  int slab_idx[MAX_SLABS];
-  int tiles_per_seq, num_tiles, ngroups;
-  int y_slab_cols;         // >0 (fp32 output only): column block c goes to Y + (c / y_slab_cols) * y_slab_stride
-  int64_t y_slab_stride;
-  // gate-backward epilogue (MODE 1, N == G): acc + Rsd is dz; writes da_f | da_g into the split tensor gate_dafg
-  const float* gate_sg;    // [rows][gate_sg_ld] fp32 sigmoid
-  const __half* gate_z;    // split [rows][2N]
-  __half* gate_dafg;       // split [rows][2 * 2N]
-  int gate_zp, gate_sg_ld;
-  int zero_rows_below;
-  int reverse;
-  int flush;               // MODE 4: accumulate K blocks in registers (forward GEMMs; no mask / y_slab / colsum)
-  float* colsum_out;       // MODE 3: += colsum_scale * column sums of the stored result
-  float colsum_scale;
-};
-
-template <int BN>
-struct SGemmCfg {
-  static constexpr int STAGE = SUB + BN * 128;
-  static constexpr int STAGES = BN == 256 ? 4 : 6;
-  static constexpr int BAR = STAGES * STAGE;
-  static constexpr int STG = BAR + 256;
-  static constexpr int SMEM = STG + 8 * 4096 + 1024 + 1024;
-};
 
 // Row-per-lane epilogue of 32 output columns [c0, c0 + 32): lane = TMEM lane = output row, so the thread owns 128 contiguous
 // bytes of its row in every tensor it touches and moves them with 256-bit accesses (one full sector per lane and
@@ -1319,11 +1298,11 @@ tcs_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_dout, const __grid_co
       const float live = t >= a.zp ? 1.f : 0.f;
       const uint8_t* st = gbase + SG_ST + s * 65536;
       // the epilogue inputs that do not depend on the accumulator: issue their loads before waiting for it
-      float4 d4[8], s4[8];
+      uint32_t d8[4][8], s8[4][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        d4[i] = *reinterpret_cast<const float4*>(a.dzs + orow * 64 + half * 32 + i * 4);
-        s4[i] = *reinterpret_cast<const float4*>(a.sg + orow * a.sg_ld + half * 32 + i * 4);
+      for (int i = 0; i < 4; ++i) {
+        ld256(a.dzs + orow * 64 + half * 32 + i * 8, d8[i]);
+        ld256(a.sg + orow * a.sg_ld + half * 32 + i * 8, s8[i]);
       }
       mbar_wait(full(s), ph);               // z tile visible to this thread's generic loads
       mbar_wait(acc_full(s), ph);
@@ -1334,6 +1313,7 @@ tcs_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_dout, const __grid_co
       tcgen05_fence_before();
       mbar_arrive(acc_empty(s));
       __half* drow = a.dafg + orow * 256 + half * 32;
+      uint32_t fh[8], fl[8], gh[8], gl[8];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint4 zh = *reinterpret_cast<const uint4*>(st + 2 * SUB + sw128_off(row, half * 4 + c));
@@ -1341,19 +1321,22 @@ tcs_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_dout, const __grid_co
         const float4 z0 = scale4(join4(make_uint2(zh.x, zh.y), make_uint2(zl.x, zl.y)), INV_ACT);
         const float4 z1 = scale4(join4(make_uint2(zh.z, zh.w), make_uint2(zl.z, zl.w)), INV_ACT);
         const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
-        const float dd[8] = {d4[2 * c].x, d4[2 * c].y, d4[2 * c].z, d4[2 * c].w, d4[2 * c + 1].x, d4[2 * c + 1].y, d4[2 * c + 1].z, d4[2 * c + 1].w};
-        const float ss[8] = {s4[2 * c].x, s4[2 * c].y, s4[2 * c].z, s4[2 * c].w, s4[2 * c + 1].x, s4[2 * c + 1].y, s4[2 * c + 1].z, s4[2 * c + 1].w};
         float df[8], dg[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) gate_deriv(fmaf(__uint_as_float(v[8 * c + i]), INV_W, dd[i]), zz[i], ss[i], live, df[i], dg[i]);
-        uint4 fh, fl, gh, gl;
-        split2(df[0], df[1], fh.x, fl.x), split2(df[2], df[3], fh.y, fl.y), split2(df[4], df[5], fh.z, fl.z), split2(df[6], df[7], fh.w, fl.w);
-        split2(dg[0], dg[1], gh.x, gl.x), split2(dg[2], dg[3], gh.y, gl.y), split2(dg[4], dg[5], gh.z, gl.z), split2(dg[6], dg[7], gh.w, gl.w);
-        if (valid) {
-          *reinterpret_cast<uint4*>(drow + c * 8) = fh;            // da_f hi
-          *reinterpret_cast<uint4*>(drow + 64 + c * 8) = gh;       // da_g hi
-          *reinterpret_cast<uint4*>(drow + 128 + c * 8) = fl;      // da_f lo
-          *reinterpret_cast<uint4*>(drow + 192 + c * 8) = gl;      // da_g lo
+        for (int i = 0; i < 8; ++i)
+          gate_deriv(fmaf(__uint_as_float(v[8 * c + i]), INV_W, __uint_as_float(d8[c][i])), zz[i], __uint_as_float(s8[c][i]), live,
+                     df[i], dg[i]);
+        const int k = (c & 1) * 4;
+        split2(df[0], df[1], fh[k], fl[k]), split2(df[2], df[3], fh[k + 1], fl[k + 1]);
+        split2(df[4], df[5], fh[k + 2], fl[k + 2]), split2(df[6], df[7], fh[k + 3], fl[k + 3]);
+        split2(dg[0], dg[1], gh[k], gl[k]), split2(dg[2], dg[3], gh[k + 1], gl[k + 1]);
+        split2(dg[4], dg[5], gh[k + 2], gl[k + 2]), split2(dg[6], dg[7], gh[k + 3], gl[k + 3]);
+        if ((c & 1) && valid) {     // 16 channels per plane = one 256-bit store each
+          const int o16 = (c >> 1) * 16;
+          st256(drow + o16, fh);            // da_f hi
+          st256(drow + 64 + o16, gh);       // da_g hi
+          st256(drow + 128 + o16, fl);      // da_f lo
+          st256(drow + 192 + o16, gl);      // da_g lo
         }
       }
       mbar_arrive(empty(s));                // done reading z from the stage
@@ -1525,14 +1508,15 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
       const int b = tile / a.tiles_per_seq, t = (tile % a.tiles_per_seq) * TM + row;
       const bool valid = t < a.rows_out;
       const int64_t orow = (int64_t)b * a.rows_out + min(t, a.rows_out - 1);
-      uint4 rh[4], rl[4];      // residual gradient (split): independent of the accumulator, loaded before waiting for it
+      uint32_t rh[2][8], rl[2][8];   // residual gradient (split): independent of the accumulator, loaded before waiting for it
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         if (a.rsd) {
-          rh[c] = *reinterpret_cast<const uint4*>(a.rsd + orow * 128 + half * 32 + c * 8);
-          rl[c] = *reinterpret_cast<const uint4*>(a.rsd + orow * 128 + 64 + half * 32 + c * 8);
+          ld256(a.rsd + orow * 128 + half * 32 + c * 16, rh[c]);
+          ld256(a.rsd + orow * 128 + 64 + half * 32 + c * 16, rl[c]);
         } else {
-          rh[c] = rl[c] = make_uint4(0u, 0u, 0u, 0u);   // top layer: nothing flows in from above
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rh[c][i] = rl[c][i] = 0u;   // top layer: nothing flows in from above
         }
       }
       mbar_wait(acc_full(ab), aph);
@@ -1544,17 +1528,17 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
       mbar_arrive(acc_empty(ab));
       __half* yrow = a.Y + orow * 128 + half * 32;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float4 r0 = join4(make_uint2(rh[c].x, rh[c].y), make_uint2(rl[c].x, rl[c].y));
-        const float4 r1 = join4(make_uint2(rh[c].z, rh[c].w), make_uint2(rl[c].z, rl[c].w));
-        uint4 oh, ol;
-        split2(fmaf(__uint_as_float(v[8 * c + 0]), INV_W, r0.x), fmaf(__uint_as_float(v[8 * c + 1]), INV_W, r0.y), oh.x, ol.x);
-        split2(fmaf(__uint_as_float(v[8 * c + 2]), INV_W, r0.z), fmaf(__uint_as_float(v[8 * c + 3]), INV_W, r0.w), oh.y, ol.y);
-        split2(fmaf(__uint_as_float(v[8 * c + 4]), INV_W, r1.x), fmaf(__uint_as_float(v[8 * c + 5]), INV_W, r1.y), oh.z, ol.z);
-        split2(fmaf(__uint_as_float(v[8 * c + 6]), INV_W, r1.z), fmaf(__uint_as_float(v[8 * c + 7]), INV_W, r1.w), oh.w, ol.w);
+      for (int c = 0; c < 2; ++c) {
+        uint32_t oh[8], ol[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 rhi = __half22float2(bits_h2(rh[c][i])), rlo = __half22float2(bits_h2(rl[c][i]));
+          split2(fmaf(__uint_as_float(v[c * 16 + 2 * i]), INV_W, rhi.x + rlo.x),
+                 fmaf(__uint_as_float(v[c * 16 + 2 * i + 1]), INV_W, rhi.y + rlo.y), oh[i], ol[i]);
+        }
         if (valid) {
-          *reinterpret_cast<uint4*>(yrow + c * 8) = oh;
-          *reinterpret_cast<uint4*>(yrow + 64 + c * 8) = ol;
+          st256(yrow + c * 16, oh);
+          st256(yrow + 64 + c * 16, ol);
         }
       }
     }
