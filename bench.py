@@ -288,7 +288,9 @@ def main():
     net = FasterWaveNet(params, seed=1234)             # the facade's own initialiser (LeCunNormal, bias 0, wavenet.py:379-455)
     net.to_gpu(local_rank)
     net.set_precision(args.precision)
-    net.data_parallel = world > 1
+    if world > 1:
+        from wavenet_b200.dist import init_comm
+        init_comm(net)                                 # NCCL communicator inside libwavenet_b200.so (wn_comm_init)
     net.update_laerning_rate(1e-3)
     x_h, t_h = synth_batch(rank, B, W)
     x_d = torch.from_numpy(x_h).cuda()

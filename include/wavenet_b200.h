@@ -154,6 +154,19 @@ int wn_clip_adam_step(wn_handle* h, float* params, float* grads, float* m, float
                       float beta2, float eps, float weight_decay, float clip, float grad_scale, void* scratch,
                       float* norm_out, wn_stream_t s);
 
+/* ---- data-parallel training (the reference is single-device) ---------------------------------------
+ * The batch of train_audio/train.py:58-80 is sharded over one process per GPU; the only exchange step is ONE sum
+ * all-reduce of the flat gradient buffer between wn_backward and wn_clip_adam_step(grad_scale = 1/world), so the clip
+ * hook acts on the averaged gradient like wavenet.py:477-480.  NCCL (libnccl.so.2, resolved at run time) lives behind
+ * these calls: rank 0 makes a 128-byte id (host memory), the caller ships it to the other ranks, every rank calls
+ * wn_comm_init with the device it trains on current. */
+int wn_comm_available(void);                                   /* 1 when libnccl.so.2 could be loaded */
+int wn_comm_unique_id(char* id_out_host /* [128] */);
+int wn_comm_init(wn_handle* h, const char* id_host /* [128] */, int rank, int world);
+int wn_comm_world(const wn_handle* h);
+int wn_allreduce_grads(wn_handle* h, float* grads, wn_stream_t s);   /* in-place sum over ranks; no-op without a communicator */
+int wn_comm_destroy(wn_handle* h);
+
 /* Profiling hooks used by bench.py's roofline leg: ONE launch of the fused residual-layer kernel (layer l)
  * or of the skip-sum GEMM on the bound tape; need a preceding TF32 wn_forward_residual_block. */
 int wn_tc_layer_forward(wn_handle* h, int layer, wn_stream_t s);

@@ -1,0 +1,89 @@
+"""Two-rank data-parallel training on real GPUs through the C-ABI communicator (wn_comm_init / wn_allreduce_grads).
+Skipped on a single-GPU box.  Each rank runs the CUDA path on its shard; checks:
+  * the all-reduced mean gradient equals the gradient of the global batch computed on one GPU (<= 1e-5 relative),
+  * after three replicated clip + Adam steps the parameters of both ranks are bit-identical."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from oracle import wavenet_oracle as O
+from tests.util import make_cfg, make_net, rel_err
+from wavenet_b200.dist import init_comm, shard_range, assert_replicas_equal
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("gloo")                      # only ships the 128-byte NCCL id and the verdicts
+prec = sys.argv[1]
+cfg = make_cfg("C_small")
+w = O.init_weights(cfg, np.random.default_rng(0), np.float64)
+rng = np.random.default_rng(1)
+B, W = 6, 700
+x = rng.integers(0, 256, (B, W)).astype(np.int32)
+t = rng.integers(0, 256, (B, W)).astype(np.int32)
+b0, b1 = shard_range(B, world, rank)
+dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+net = make_net(cfg, w)
+net.set_precision(prec)
+net.update_laerning_rate(1e-3)
+net.use_cuda_graph = False
+init_comm(net)
+assert net._libh.wn_comm_world(net._h) == world
+# gradient of the shard, all-reduced inside the library
+net._bind(b1 - b0, W)
+net._fwd_bwd(dev(x[b0:b1]), dev(t[b0:b1]), W)
+from wavenet_b200._lib import check
+from wavenet_b200.wavenet import _ptr, _stream
+check(net._libh.wn_allreduce_grads(net._h, _ptr(net._grads), _stream()))
+g_dp = {k: v / world for k, v in net.get_grads().items()}
+ok = True
+if rank == 0:
+    ref = make_net(cfg, w)
+    ref.set_precision(prec)
+    ref._bind(B, W)
+    ref._fwd_bwd(dev(x), dev(t), W)
+    g_full = ref.get_grads()
+    worst = max(rel_err(g_dp[k], v) for k, v in g_full.items() if np.abs(v).max() > 0)
+    print("worst rel err DP vs global batch: %%.2e" %% worst, flush=True)
+    ok = worst < 1e-5
+    del ref
+# three replicated steps; parameters must stay bit-identical
+for step in range(3):
+    net.train_step(dev(x[b0:b1]), dev(t[b0:b1]))
+same = assert_replicas_equal(net._params.cpu(), atol=0.0)
+flag = torch.tensor([1 if (ok and same) else 0])
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("DP_OK" if flag.item() == 1 else "DP_FAIL same=%%s ok=%%s" %% (same, ok), flush=True)
+dist.destroy_process_group()
+'''
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("prec", ["fp16x2", "fp32"])
+def test_two_rank_dp_gradient_equals_global_batch(prec, tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "dp_worker.py"
+    script.write_text(WORKER % ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), str(script), prec]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert "DP_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

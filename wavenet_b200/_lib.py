@@ -82,6 +82,12 @@ SIGNATURES = {
     "wn_tcs_skip_gemm": (_I, [_P, _P]),
     "wn_tcs_debug_gemm": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _I, _P]),
     "wn_tcs_debug_wgrad": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _F, _P, _P]),
+    "wn_comm_available": (_I, []),
+    "wn_comm_unique_id": (_I, [C.c_char_p]),
+    "wn_comm_init": (_I, [_P, C.c_char_p, _I, _I]),
+    "wn_comm_world": (_I, [_P]),
+    "wn_allreduce_grads": (_I, [_P, _P, _P]),
+    "wn_comm_destroy": (_I, [_P]),
     "wn_optim_scratch_bytes": (_L, [_P]),
     "wn_clip_adam_step": (_I, [_P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _F, _F, _F, _P, _P, _P]),
     "wn_gen_create": (_I, [_P, _I, _I, C.POINTER(_P)]),

@@ -162,6 +162,7 @@ extern "C" int wn_set_device_info(wn_handle* h) {
 }
 
 extern "C" int wn_destroy(wn_handle* h) {
+  if (h && h->comm) wn_comm_destroy(h);
   delete h;
   return WN_OK;
 }

@@ -119,6 +119,9 @@ struct wn_handle {
   bool head_split = false;         // head activations + dlogits are split rows (tcs_forward_head)
   bool x0_split = false;           // x[0] has already been converted in place
   float gscale = 1.f;              // power-of-two scale of every gradient tensor of the split backward
+  // data-parallel communicator (wn_comm.cu): an ncclComm_t owned by the handle
+  void* comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
   bool ce_colsum_valid = false;    // tape.ce_colsum matches tape.dlogits (set by wn_cross_entropy)
 };
 

@@ -69,6 +69,13 @@ __device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t smem_addr, uint32_t l
   return d;
 }
 
+// One mbarrier arrival per WARP: hundreds of threads arriving on the same shared-memory word serialise (an arrive is an
+// atomic); bar.warp.sync orders every lane's earlier shared-memory / TMEM accesses before lane 0's releasing arrive.
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
 // three MMAs of one K=16 step of a split product (A planes ah/al, B planes bh/bl)
 __device__ __forceinline__ void umma_split(uint32_t d_tmem, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl, uint32_t idesc,
                                            uint32_t accumulate) {
@@ -389,8 +396,17 @@ constexpr int SL_B2 = 65536;
 constexpr int SL_A = 81920;
 constexpr int SL_BAR = SL_A + 2 * 65536;
 constexpr int SL_SMEM = SL_BAR + 256;
+constexpr int SL_THREADS = 64 + 512;           // producer warp, MMA warp, 16 epilogue warps
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+// Developer trace (make EXTRA=-DWN_LAYER_TRACE, tests/dev/trace_tcs_layer.py): clock64 stamps of CTA 0's pipeline events.
+#ifdef WN_LAYER_TRACE
+__device__ long long g_trace_s[64 * 32];
+#define TRS(j, e) do { if (blockIdx.x == 0 && (j) < 64) g_trace_s[(j) * 32 + (e)] = clock64(); } while (0)
+#else
+#define TRS(j, e) do { } while (0)
+#endif
+
+__global__ void __launch_bounds__(SL_THREADS, 1)
 tcs_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
                  const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_z,
                  const __grid_constant__ CUtensorMap tm_sg, const SLayerArgs a) {
@@ -411,7 +427,7 @@ tcs_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     for (int s = 0; s < 2; ++s) {
       mbar_init(a_full(s), 1);
       mbar_init(d1_full(s), 1);
-      mbar_init(z_full(s), 256);
+      mbar_init(z_full(s), 16);        // one arrival per epilogue warp
       mbar_init(d2_full(s), 1);
     }
     fence_barrier_init();
@@ -444,7 +460,9 @@ tcs_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const uint32_t as = base + SL_A + s * 65536;
         if (j >= 2) {
           mbar_wait(d2_full(s), ((j - 2) >> 1) & 1);
+          TRS(j, 0);
           bulk_wait_group_read0();
+          TRS(j, 1);
         }
         if (j < n_local) {
           const int tile = tile_of(j);
@@ -454,6 +472,7 @@ tcs_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           tma_load_4d(as + 1 * SUB, &tm_x, a_full(s), KB, t0 - a.d, b, 0);
           tma_load_4d(as + 2 * SUB, &tm_x, a_full(s), 0, t0, b, 0);
           tma_load_4d(as + 3 * SUB, &tm_x, a_full(s), KB, t0, b, 0);
+          TRS(j, 2);
           if (j + 2 < n_local) {
             const int tp = tile_of(j + 2);
             const int bp = tp / a.tiles_per_seq, tp0 = (tp % a.tiles_per_seq) * TM;
@@ -466,6 +485,7 @@ tcs_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM;
           const uint32_t zs = base + SL_A + s1 * 65536;
           mbar_wait(z_full(s1), (jj >> 1) & 1);
+          TRS(j, 3);
           tma_store_4d(&tm_z, zs + 0 * SUB, 0, t0, b, 0);      // z hi plane
           tma_store_4d(&tm_z, zs + 1 * SUB, KB, t0, b, 0);     // z lo plane
           tma_store_4d(&tm_sg, zs + 2 * SUB, 0, t0, b, 0);     // sigmoid fp32, channels 0..31
@@ -483,6 +503,7 @@ tcs_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const int s = j1 & 1;
         if (j1 >= 2) mbar_wait(z_full(s), ((j1 - 2) >> 1) & 1);
         mbar_wait(a_full(s), (j1 >> 1) & 1);
+        TRS(j1, 4);
         tcgen05_fence_after();
         const uint32_t as = base + SL_A + s * 65536;
         // The tensor core accumulates with round-toward-zero: every MMA step loses ~half an ulp OF THE ACCUMULATOR.  The
@@ -504,11 +525,15 @@ tcs_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             umma_f16(tmem + s * 128, umma_desc_k_sw128(ao), umma_desc_k_sw128(bo), idesc1, 1u);
           }
         umma_commit(d1_full(s));
+        TRS(j1, 5);
       }
     }
   } else {
+    // 16 epilogue warps: the gate epilogue is a long dependent chain per element (two exponentials, two reciprocals, the
+    // hi/lo splits), so it is bound by instruction latency, not by issue slots -- four warps per scheduler hide it
+    // (ncu, 8 warps: 0.21 IPC per warp, 42 % issue utilisation, tile period 9.1 k cycles against an HBM floor of 5.7 k)
     const int q = warp & 3;               // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;     // which 32 of the 64 channels this warp handles
+    const int part = (warp - 2) >> 2;     // which 16 of the 64 channels this warp handles
     const int row = q * 32 + lane;
     if (threadIdx.x == 64) mbar_wait(b_full, 0);
     for (int j = 0; j < n_local; ++j) {
@@ -520,54 +545,57 @@ tcs_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
       // ---- epilogue 1: gate ----
       mbar_wait(d1_full(s), ph);
+      if (threadIdx.x == 64) TRS(j, 8);
       tcgen05_fence_after();
-      uint32_t f[32], g[32];
-      tmem_ld32(trow + s * 128 + half * 32, f);
-      tmem_ld32(trow + s * 128 + 64 + half * 32, g);
+      uint32_t f[16], g[16];
+      tmem_ld16(trow + s * 128 + part * 16, f);
+      tmem_ld16(trow + s * 128 + 64 + part * 16, g);
       // residual ACT_SCALE * x(t) = hi + lo of this thread's row and channels, into registers
-      float xr[32];
+      float xr[16];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint4 hv = *reinterpret_cast<const uint4*>(as_g + 2 * SUB + sw128_off(row, half * 4 + c));
-        const uint4 lv = *reinterpret_cast<const uint4*>(as_g + 3 * SUB + sw128_off(row, half * 4 + c));
+      for (int c = 0; c < 2; ++c) {
+        const uint4 hv = *reinterpret_cast<const uint4*>(as_g + 2 * SUB + sw128_off(row, part * 2 + c));
+        const uint4 lv = *reinterpret_cast<const uint4*>(as_g + 3 * SUB + sw128_off(row, part * 2 + c));
         const float4 v0 = join4(make_uint2(hv.x, hv.y), make_uint2(lv.x, lv.y));
         const float4 v1 = join4(make_uint2(hv.z, hv.w), make_uint2(lv.z, lv.w));
         xr[8 * c + 0] = v0.x, xr[8 * c + 1] = v0.y, xr[8 * c + 2] = v0.z, xr[8 * c + 3] = v0.w;
         xr[8 * c + 4] = v1.x, xr[8 * c + 5] = v1.y, xr[8 * c + 6] = v1.z, xr[8 * c + 7] = v1.w;
       }
       tmem_ld_wait();
-      // the sigmoid tiles below overwrite whole rows of sub-tiles 2 / 3, which hold x(t) of BOTH channel halves: the
-      // partner warp (same rows, other half) must have taken its residual first
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      // the sigmoid tiles below overwrite whole rows of sub-tiles 2 / 3, which hold x(t) of ALL channels: the three partner
+      // warps (same rows, other channels) must have taken their residuals first
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
       const bool live = valid && t >= a.zp;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
+      for (int i = 0; i < 16; ++i) {
         const float af = __uint_as_float(f[i]) * INV_ACT_W, ag = __uint_as_float(g[i]) * INV_ACT_W;
         const float tf = tanh_acc(af), sg = sigmoid_acc(ag);
         g[i] = __float_as_uint(live ? sg : 0.5f);          // masked rows look like tanh(0) | sigmoid(0)
         f[i] = __float_as_uint(live ? ACT_SCALE * tf * sg : 0.f);   // z is stored with ACT_SCALE
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {   // z planes: 8 channels per 16-byte chunk
+      for (int c = 0; c < 2; ++c) {   // z planes: 8 channels per 16-byte chunk
         uint4 hv, lv;
         split2(__uint_as_float(f[8 * c + 0]), __uint_as_float(f[8 * c + 1]), hv.x, lv.x);
         split2(__uint_as_float(f[8 * c + 2]), __uint_as_float(f[8 * c + 3]), hv.y, lv.y);
         split2(__uint_as_float(f[8 * c + 4]), __uint_as_float(f[8 * c + 5]), hv.z, lv.z);
         split2(__uint_as_float(f[8 * c + 6]), __uint_as_float(f[8 * c + 7]), hv.w, lv.w);
-        *reinterpret_cast<uint4*>(as_g + 0 * SUB + sw128_off(row, half * 4 + c)) = hv;
-        *reinterpret_cast<uint4*>(as_g + 1 * SUB + sw128_off(row, half * 4 + c)) = lv;
+        *reinterpret_cast<uint4*>(as_g + 0 * SUB + sw128_off(row, part * 2 + c)) = hv;
+        *reinterpret_cast<uint4*>(as_g + 1 * SUB + sw128_off(row, part * 2 + c)) = lv;
       }
 #pragma unroll
-      for (int c = 0; c < 8; ++c)   // sigmoid fp32: 32 channels of this half = one 128-byte row of sub-tile 2 + half
-        *reinterpret_cast<uint4*>(as_g + (2 + half) * SUB + sw128_off(row, c)) =
+      for (int c = 0; c < 4; ++c)   // sigmoid fp32: channels [part*16, +16) = four chunks of the 128-byte row of sub-tile 2 + part/2
+        *reinterpret_cast<uint4*>(as_g + (2 + (part >> 1)) * SUB + sw128_off(row, (part & 1) * 4 + c)) =
             make_uint4(g[4 * c], g[4 * c + 1], g[4 * c + 2], g[4 * c + 3]);
       fence_proxy_async();
       tcgen05_fence_before();
-      mbar_arrive(z_full(s));
+      warp_arrive(z_full(s), lane);
+      if (threadIdx.x == 64) TRS(j, 9);
       if (threadIdx.x == 64) {
         // one epilogue thread issues GEMM 2 as soon as every row of z is in shared memory
         constexpr uint32_t idesc2 = idesc_f16(128, 64);
         mbar_wait(z_full(s), ph);
+        TRS(j, 6);
         tcgen05_fence_after();
         const uint32_t as = base + SL_A + s * 65536;
 #pragma unroll
@@ -586,25 +614,23 @@ tcs_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       __syncwarp();
       // ---- epilogue 2: projection + residual ----
       mbar_wait(d2_full(s), ph);
+      if (threadIdx.x == 64) TRS(j, 10);
       tcgen05_fence_after();
-      tmem_ld32(trow + 256 + s * 64 + half * 32, g);
+      tmem_ld16(trow + 256 + s * 64 + part * 16, g);
       tmem_ld_wait();
       tcgen05_fence_before();
-      // x_out rows are [hi 64 | lo 64] halves: the thread owns channels [half*32, +32) of its row = 64 contiguous bytes in
-      // each plane, written with two 256-bit stores per plane (full sectors, no staging)
+      // x_out rows are [hi 64 | lo 64] halves: the thread owns channels [part*16, +16) of its row = 32 contiguous bytes in
+      // each plane = one 256-bit store per plane (a full sector, no staging)
       if (valid) {
-        __half* xrow = a.x_out + ((int64_t)b * a.W + t) * 128 + half * 32;
+        __half* xrow = a.x_out + ((int64_t)b * a.W + t) * 128 + part * 16;
+        uint32_t hv[8], lv[8];
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t hv[8], lv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            split2(fmaf(__uint_as_float(g[hh * 16 + 2 * i]), INV_W, xr[hh * 16 + 2 * i]),
-                   fmaf(__uint_as_float(g[hh * 16 + 2 * i + 1]), INV_W, xr[hh * 16 + 2 * i + 1]), hv[i], lv[i]);
-          st256(xrow + hh * 16, hv);
-          st256(xrow + 64 + hh * 16, lv);
-        }
+        for (int i = 0; i < 8; ++i)
+          split2(fmaf(__uint_as_float(g[2 * i]), INV_W, xr[2 * i]), fmaf(__uint_as_float(g[2 * i + 1]), INV_W, xr[2 * i + 1]), hv[i], lv[i]);
+        st256(xrow, hv);
+        st256(xrow + 64, lv);
       }
+      if (threadIdx.x == 64) TRS(j, 11);
     }
   }
   tcgen05_fence_before();
@@ -731,7 +757,7 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full(s), 1);
-      mbar_init(acc_empty(s), 256);
+      mbar_init(acc_empty(s), 8);      // one arrival per epilogue warp
     }
     fence_barrier_init();
     prefetch_tmap(&tm_a);
@@ -851,7 +877,7 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             for (int i = 0; i < 32; ++i) acc[ch][i] += __uint_as_float(v[i]);
           }
           tcgen05_fence_before();
-          mbar_arrive(acc_empty(ab));
+          warp_arrive(acc_empty(ab), lane);
         }
         const int t = t0 + lane;
         const int64_t orow = (int64_t)b * a.rows_out + min(t, a.rows_out - 1);
@@ -885,7 +911,7 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           epi_row32(a, o, c0, t, orow, b, a.colsum_out ? cs_smem + ct : nullptr, lane);
         }
         tcgen05_fence_before();
-        mbar_arrive(acc_empty(ab));
+        warp_arrive(acc_empty(ab), lane);
       }
       if (a.colsum_out) {
         asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps
@@ -946,7 +972,7 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         __syncwarp();
       }
       tcgen05_fence_before();
-      mbar_arrive(acc_empty(ab));
+      warp_arrive(acc_empty(ab), lane);
     }
   }
   tcgen05_fence_before();
@@ -1210,9 +1236,9 @@ tcs_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_dout, const __grid_co
     mbar_init(wg_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(full(s), 1);
-      mbar_init(empty(s), 257);       // the MMA commit + 256 epilogue threads (they read z from the stage)
+      mbar_init(empty(s), 9);         // the MMA commit + 8 epilogue warps (they read z from the stage)
       mbar_init(acc_full(s), 1);
-      mbar_init(acc_empty(s), 256);
+      mbar_init(acc_empty(s), 8);      // one arrival per epilogue warp
     }
     fence_barrier_init();
     prefetch_tmap(&tm_dout);
@@ -1311,7 +1337,7 @@ tcs_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_dout, const __grid_co
       tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + s * 64 + half * 32, v);
       tmem_ld_wait();
       tcgen05_fence_before();
-      mbar_arrive(acc_empty(s));
+      warp_arrive(acc_empty(s), lane);
       __half* drow = a.dafg + orow * 256 + half * 32;
       uint32_t fh[8], fl[8], gh[8], gl[8];
 #pragma unroll
@@ -1339,7 +1365,7 @@ tcs_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_dout, const __grid_co
           st256(drow + 192 + o16, gl);      // da_g lo
         }
       }
-      mbar_arrive(empty(s));                // done reading z from the stage
+      warp_arrive(empty(s), lane);          // done reading z from the stage
     }
     if (n_local > 0 && q < 2) {
       // dWp rows (projection output channels r) live in TMEM lanes 0..63, columns = g
@@ -1405,7 +1431,7 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full(s), 1);
-      mbar_init(acc_empty(s), 256);
+      mbar_init(acc_empty(s), 8);      // one arrival per epilogue warp
     }
     mbar_init(x_full, 1);
     mbar_init(x_empty, 1);
@@ -1525,7 +1551,7 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
       tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * 64 + half * 32, v);
       tmem_ld_wait();
       tcgen05_fence_before();
-      mbar_arrive(acc_empty(ab));
+      warp_arrive(acc_empty(ab), lane);
       __half* yrow = a.Y + orow * 128 + half * 32;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -1943,7 +1969,7 @@ int tcs_layer_launch(wn_handle* h, int l, cudaStream_t s) {
     WN_CHECK_CUDA(cudaFuncSetAttribute(tcs_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM + 1024));
     attr = true;
   }
-  tcs_layer_kernel<<<grid, NTHREADS, SL_SMEM + 1024, s>>>(tx, tw1, tw2, tz, tsg, a);
+  tcs_layer_kernel<<<grid, SL_THREADS, SL_SMEM + 1024, s>>>(tx, tw1, tw2, tz, tsg, a);
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
@@ -2328,3 +2354,9 @@ extern "C" int wn_tcs_skip_gemm(wn_handle* h, void* stream) {
   WN_REQUIRE(h && h->ws && h->tape_split, WN_ESTATE, "wn_tcs_skip_gemm: run an fp16x2 forward first");
   return tcs_skip_gemm(h, (cudaStream_t)stream);
 }
+
+#ifdef WN_LAYER_TRACE
+extern "C" int wn_debug_tcs_trace(long long* out) {
+  return cudaMemcpyFromSymbol(out, g_trace_s, sizeof(long long) * 64 * 32) == cudaSuccess ? 0 : -1;
+}
+#endif

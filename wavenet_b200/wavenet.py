@@ -477,7 +477,14 @@ class WaveNet(object):
     def update(self):
         """Hooks + Adam (wavenet.py:477-480, Chainer GradientMethod.update)."""
         p, opt = self.params, self.optimizer
-        grad_scale = allreduce_sum_(self._grads) if self.data_parallel else 1.0
+        grad_scale = 1.0
+        if self.data_parallel:
+            world = int(self._libh.wn_comm_world(self._h))
+            if world > 1:        # communicator behind the C ABI (dist.init_comm): NCCL all-reduce on the caller's stream
+                check(self._libh.wn_allreduce_grads(self._h, _ptr(self._grads), _stream()))
+                grad_scale = 1.0 / world
+            else:                # no communicator in the library: torch.distributed (host-side tests)
+                grad_scale = allreduce_sum_(self._grads)
         opt.t += 1
         check(self._libh.wn_clip_adam_step(self._h, _ptr(self._params), _ptr(self._grads), _ptr(self._m), _ptr(self._v),
                                            opt.t, opt.alpha, opt.beta1, opt.beta2, opt.eps, float(p.weight_decay),
