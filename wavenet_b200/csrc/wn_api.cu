@@ -780,6 +780,32 @@ extern "C" int wn_forward_loss(wn_handle* h, const float* params, const int32_t*
   int rc = wn_forward_residual_block(h, params, nullptr, nullptr, nullptr, st);
   h->fuse_head_relu = 0;
   WN_TRY(rc);
+  if (target && h->prec == WN_PREC_F16X2 && h->tape_split && h->Q == 256) {
+    // fp16x2 path: the last head conv carries the softmax cross-entropy in its epilogue (wavenet.py:590 + 597-617 in one
+    // kernel): the logits never reach HBM unless logits_opt asks for them, and no separate loss kernel runs
+    WN_REQUIRE(loss, WN_EINVAL, "null loss pointer");
+    const int64_t rows = (int64_t)h->tape.B * T;
+    int k = 3;
+    while (((int64_t)1 << (k - 3)) < rows) ++k;
+    h->gscale = ldexpf(1.f, k);
+    h->fuse_ce_target = target;
+    h->fuse_ce_logits = logits_opt;
+    h->ce_fused_done = false;
+    rc = wn_forward_softmax_block(h, params, nullptr, T, 0, nullptr, st);
+    h->fuse_ce_target = nullptr;
+    h->fuse_ce_logits = nullptr;
+    WN_TRY(rc);
+    if (h->ce_fused_done) {
+      WN_TRY(simt_loss_finalize((const double*)(h->ws + h->tape.loss_acc), rows, loss, (cudaStream_t)st));
+      h->ce_colsum_valid = false;      // the bias gradient of the last conv comes from a column-sum pass over dlogits
+      h->phase = PH_LOSS;
+      return WN_OK;
+    }
+    if (logits_opt)
+      WN_CHECK_CUDA(cudaMemcpyAsync(logits_opt, h->ws + h->tape.hbuf.back(), sizeof(float) * rows * h->Q, cudaMemcpyDeviceToDevice,
+                                    (cudaStream_t)st));
+    return wn_cross_entropy(h, target, loss, st);
+  }
   WN_TRY(wn_forward_softmax_block(h, params, nullptr, T, 0, logits_opt, st));
   if (target) WN_TRY(wn_cross_entropy(h, target, loss, st));
   return WN_OK;

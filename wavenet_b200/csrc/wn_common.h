@@ -119,6 +119,9 @@ struct wn_handle {
   bool head_split = false;         // head activations + dlogits are split rows (tcs_forward_head)
   bool x0_split = false;           // x[0] has already been converted in place
   float gscale = 1.f;              // power-of-two scale of every gradient tensor of the split backward
+  const int32_t* fuse_ce_target = nullptr;   // set by wn_forward_loss: the head's last conv runs the cross-entropy epilogue
+  float* fuse_ce_logits = nullptr;           //   optional fp32 logits output of that fused kernel
+  bool ce_fused_done = false;
   // data-parallel communicator (wn_comm.cu): an ncclComm_t owned by the handle
   void* comm = nullptr;
   int comm_rank = 0, comm_world = 1;
@@ -188,6 +191,7 @@ int simt_cross_entropy(const float* logits, const int32_t* target, int64_t rows,
                        float* dlogits, float* colsum, bool* colsum_written, int sm_count, cudaStream_t s,
                        float split_scale = 0.f, bool* split_written = nullptr);
 int simt_add_vec(const float* src, float* dst, int n, cudaStream_t s);
+int simt_loss_finalize(const double* acc, int64_t rows, float* loss, cudaStream_t s);
 int simt_onehot_to_index(const float* onehot, int B, int Q, int W, int32_t* idx, cudaStream_t s);
 
 // ---- optimiser (wn_optim.cu) ---------------------------------------------------

@@ -651,6 +651,12 @@ int simt_cross_entropy(const float* logits, const int32_t* target, int64_t rows,
   return WN_OK;
 }
 
+int simt_loss_finalize(const double* acc, int64_t rows, float* loss, cudaStream_t s) {
+  loss_finalize_kernel<<<1, 1, 0, s>>>(acc, rows, loss);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
 int simt_onehot_to_index(const float* onehot, int B, int Q, int W, int32_t* idx, cudaStream_t s) {
   onehot_to_index_kernel<<<blocks_for((int64_t)B * W, 256), 256, 0, s>>>(onehot, B, Q, W, idx);
   WN_CHECK_LAUNCH();

@@ -185,8 +185,13 @@ struct SGemmArgs {
   int zero_rows_below;
   int reverse;
   int flush;               // MODE 4: accumulate K blocks in registers (forward GEMMs; no mask / y_slab / colsum)
-  float* colsum_out;       // MODE 3: += colsum_scale * column sums of the stored result
+  float* colsum_out;       // MODE 5: += colsum_scale * column sums of the stored result
   float colsum_scale;
+  // MODE 6 (last head conv fused with softmax cross-entropy; N == 256): Y (optional) receives the fp32 logits
+  const int32_t* ce_target;   // [rows]
+  double* ce_acc;             // += sum over rows of (logsumexp - logit[target])
+  __half* ce_dlogits;         // split [rows][hi 256 | lo 256] = (softmax - onehot) * ce_invn * ce_gscale
+  float ce_invn, ce_gscale;
 };
 
 template <int BN>
@@ -887,6 +892,99 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           if (c0 < a.N) epi_row32(a, acc[ch], c0, t, orow, b, nullptr, lane);
         }
       }
+    }
+    if constexpr (MODE == 6) {
+      // Last head conv fused with softmax cross-entropy (wavenet.py:590 + 597-617): the logits of a row live in the
+      // registers of TWO threads (this warp's 128 columns, the partner warp's other 128), so the row maximum and the
+      // exp-sum are exchanged through shared memory; the loss and dlogits (split fp16, scaled by gscale -- the operand format
+      // of the backward GEMMs) leave from here.  The logits themselves are only written on request.
+      static_assert(MODE != 6 || BN == 256, "the fused CE epilogue needs the whole 256-class row in one tile");
+      float* xmax = reinterpret_cast<float*>(stg);                 // this warp's 4 KB staging block: [32 rows] max | sum | tgt logit
+      float* pmax = reinterpret_cast<float*>(gbase + Cfg::STG + (((warp - 2) ^ 4)) * 4096);   // partner warp (same rows, other half)
+      double loss_part = 0.0;
+      const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+      const int cbase = half * CH * 32;
+      for (int j = 0; j < n_local; ++j) {
+        const int tile = a.reverse ? a.num_tiles - 1 - ((int)blockIdx.x + j * (int)gridDim.x) : (int)blockIdx.x + j * (int)gridDim.x;
+        const int ab = j & 1, aph = (j >> 1) & 1;
+        const int b = tile / a.tiles_per_seq, t = (tile % a.tiles_per_seq) * TM + q * 32 + lane;
+        const bool valid = t < a.rows_out;
+        const int64_t orow = (int64_t)b * a.rows_out + min(t, a.rows_out - 1);
+        const int tg = a.ce_target[orow];
+        mbar_wait(acc_full(ab), aph);
+        tcgen05_fence_after();
+        // the accumulator stays in TMEM and is read three times (max, exp-sum, gradient): no 128-register row copy
+        float m = -INFINITY, xt = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < CH; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(trow + ab * BN + cbase + ch * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float l = fmaf(__uint_as_float(v[i]), a.acc_scale, a.bias ? __ldg(a.bias + cbase + ch * 32 + i) : 0.f);
+            m = fmaxf(m, l);
+            if (cbase + ch * 32 + i == tg) xt = l;
+          }
+        }
+        xmax[lane] = m;
+        xmax[64 + lane] = xt;
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        m = fmaxf(m, pmax[lane]);
+        xt += pmax[64 + lane];
+        float sum = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < CH; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(trow + ab * BN + cbase + ch * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            sum += expf(fmaf(__uint_as_float(v[i]), a.acc_scale, a.bias ? __ldg(a.bias + cbase + ch * 32 + i) : 0.f) - m);
+        }
+        xmax[32 + lane] = sum;
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        sum += pmax[32 + lane];
+        if (valid && half == 0) loss_part += (double)(m + logf(sum)) - (double)xt;
+        const float inv = 1.f / sum, gk = a.ce_invn * a.ce_gscale;
+        __half* drow = a.ce_dlogits + orow * (2 * (int64_t)BN) + cbase;
+        float* yp = a.Y ? reinterpret_cast<float*>(a.Y) + orow * a.ldy + cbase : nullptr;
+#pragma unroll 1
+        for (int ch = 0; ch < CH; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(trow + ab * BN + cbase + ch * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            float d[16];
+            uint32_t u[8];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int col = cbase + ch * 32 + hh * 16 + i;
+              const float l = fmaf(__uint_as_float(v[hh * 16 + i]), a.acc_scale, a.bias ? __ldg(a.bias + col) : 0.f);
+              v[hh * 16 + i] = __float_as_uint(l);
+              d[i] = (expf(l - m) * inv - (col == tg ? 1.f : 0.f)) * gk;
+            }
+            if (valid) {
+              store_split16(drow + ch * 32 + hh * 16, BN, d);
+              if (yp) {     // logits on request
+#pragma unroll
+                for (int i = 0; i < 8; ++i) u[i] = v[hh * 16 + i];
+                st256(yp + ch * 32 + hh * 16, u);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) u[i] = v[hh * 16 + 8 + i];
+                st256(yp + ch * 32 + hh * 16 + 8, u);
+              }
+            }
+          }
+        }
+        tcgen05_fence_before();
+        warp_arrive(acc_empty(ab), lane);
+      }
+      // loss: one double atomic per warp
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) loss_part += __shfl_xor_sync(0xffffffffu, loss_part, o);
+      if (lane == 0 && half == 0) atomicAdd(a.ce_acc, loss_part);
     }
     if constexpr (MODE == 5) {
       for (int j = 0; j < n_local; ++j) {
@@ -1667,6 +1765,11 @@ int launch_sgemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const SGemmA
 template <int BN>
 int launch_sgemm(const CUtensorMap& ta, const CUtensorMap& tb, const SGemmArgs& g, int sm_count, cudaStream_t s) {
   if (g.gate_sg) return launch_sgemm_mode<BN, 1>(ta, tb, g, sm_count, s);
+  if (g.ce_target) {
+    if constexpr (BN == 256) return launch_sgemm_mode<256, 6>(ta, tb, g, sm_count, s);
+    wn_set_error("fused cross-entropy epilogue needs 256 classes");
+    return WN_EINVAL;
+  }
   if (g.flush) return launch_sgemm_mode<BN, 4>(ta, tb, g, sm_count, s);
   return launch_sgemm_mode<BN, 5>(ta, tb, g, sm_count, s);
 }
@@ -1715,6 +1818,10 @@ struct SEpilogue {
   int flush = 0;
   float* colsum_out = nullptr;
   float colsum_scale = 1.f;
+  const int32_t* ce_target = nullptr;
+  double* ce_acc = nullptr;
+  __half* ce_dlogits = nullptr;
+  float ce_invn = 0.f, ce_gscale = 1.f;
   bool ngroups_ok_for_colsum(int N, int BN) const { return N <= BN; }   // the per-CTA column-sum table covers one column group
 };
 
@@ -1763,6 +1870,11 @@ int tcs_gemm(const wn_handle* h, const SOperand& A, int ns, const int* slab_idx,
   g.reverse = e.reverse;
   g.flush = e.flush && !e.gate_sg && !e.colsum_out;
   g.colsum_out = e.ngroups_ok_for_colsum(N, BN) ? e.colsum_out : nullptr;
+  g.ce_target = e.ce_target;
+  g.ce_acc = e.ce_acc;
+  g.ce_dlogits = e.ce_dlogits;
+  g.ce_invn = e.ce_invn;
+  g.ce_gscale = e.ce_gscale;
   g.colsum_scale = e.colsum_scale;
   g.rows_out = rows_out;
   g.nslab = ns;
@@ -2106,6 +2218,18 @@ int tcs_forward_head(wn_handle* h, const float* params, int T, bool external, cu
     e.acc_scale = INV_ACT_W;
     e.out_scale = last ? 1.f : ACT_SCALE;
     e.flush = 1;
+    if (last && h->fuse_ce_target && cp.out_ch == 256) {
+      // wn_forward_loss: softmax cross-entropy rides on this GEMM's epilogue; logits are only written on request
+      e.ce_target = h->fuse_ce_target;
+      e.ce_acc = (double*)(h->ws + t.loss_acc);
+      e.ce_dlogits = HP(h->ws + t.dlogits);
+      e.ce_invn = 1.f / (float)rows;
+      e.ce_gscale = h->gscale;
+      WN_CHECK_CUDA(cudaMemsetAsync(e.ce_acc, 0, 2 * sizeof(double), s));
+      WN_TRY(tcs_gemm(h, A, 1, nullptr, &off, T, HP(h->ws + t.tc_wh[i]), cp.out_ch, e, h->fuse_ce_logits, cp.out_ch, 0, s));
+      h->ce_fused_done = true;
+      continue;
+    }
     WN_TRY(tcs_gemm(h, A, 1, nullptr, &off, T, HP(h->ws + t.tc_wh[i]), cp.out_ch, e, h->ws + t.hbuf[i], cp.out_ch, last ? 0 : 1, s));
   }
   return WN_OK;
