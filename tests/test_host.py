@@ -151,3 +151,23 @@ def test_checkpoint_roundtrip_on_host(tmp_path):
     wa, wb = a.get_weights(), b.get_weights()
     for k in wa:
         assert np.array_equal(wa[k], wb[k])
+
+
+def test_hdf5_checkpoint_layout_matches_chainer_serializer(tmp_path):
+    """wavenet.py:619-639: when h5py is available the checkpoint is also written / read in the layout
+    chainer.serializers.save_hdf5 produces (group per link, datasets W / b; optimizer t + per-parameter m / v)."""
+    h5py = pytest.importorskip("h5py")
+    from wavenet_b200.wavenet import WaveNet
+    from tests.util import to_product_params
+    cfg = make_cfg("tiny_k3_bias")
+    net = WaveNet(to_product_params(cfg), seed=3)
+    net.save(str(tmp_path))
+    with h5py.File(str(tmp_path / "wavenet.model"), "r") as f:
+        assert set(f["causal_0"].keys()) == {"W", "b"}
+        assert f["residual_0_block_1_wf/W"].shape == (2, 5, 3, 1)
+    os.remove(str(tmp_path / "wavenet.model.npz"))
+    os.remove(str(tmp_path / "wavenet.opt.npz"))
+    net2 = WaveNet(to_product_params(cfg), seed=4)
+    net2.load(str(tmp_path))
+    for k, v in net.get_weights().items():
+        assert np.array_equal(net2.get_weights()[k], v), k

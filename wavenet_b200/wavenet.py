@@ -574,37 +574,77 @@ class WaveNet(object):
         self.update()
         return self._loss
 
-    # ---- checkpoint (wavenet.py:619-639), stored as .npz under the reference link names ------
+    # ---- checkpoint (wavenet.py:619-639) --------------------------------------------------------------------------
+    # Stored as .npz under the reference link names; when h5py is importable the reference's own files are written and
+    # read as well: `wavenet.model` / `wavenet.opt` in the layout chainer.serializers.save_hdf5 produces for the chain
+    # registered at wavenet.py:461-472 (group "<link name>", datasets "W" / "b"; optimizer: "t", "epoch" and per-parameter
+    # groups "<link name>/W" with the Adam moments "m", "v"), so weights trained with the Chainer reference load here.
+    @staticmethod
+    def _h5py():
+        try:
+            import h5py
+            return h5py
+        except Exception:
+            return None
+
     def save(self, model_dir="./"):
         try:
             os.mkdir(model_dir)
         except Exception:
             pass
-        np.savez(model_dir + "/wavenet.model.npz", **self.get_weights())
+        weights = self.get_weights()
+        np.savez(model_dir + "/wavenet.model.npz", **weights)
         opt = {"t": np.int64(self.optimizer.t)}
+        moments = {}
         if self._m is not None:
             m, v = self._m.detach().cpu().numpy(), self._v.detach().cpu().numpy()
             for name, (off, n, shape) in self.layout.items():
-                opt[name + "/m"] = m[off:off + n].reshape(shape)
-                opt[name + "/v"] = v[off:off + n].reshape(shape)
+                moments[name] = (m[off:off + n].reshape(shape), v[off:off + n].reshape(shape))
+                opt[name + "/m"], opt[name + "/v"] = moments[name]
         np.savez(model_dir + "/wavenet.opt.npz", **opt)
+        h5py = self._h5py()
+        if h5py is not None:
+            with h5py.File(model_dir + "/wavenet.model", "w") as f:
+                for name, arr in weights.items():            # "causal_0/W" -> group causal_0, dataset W
+                    f.create_dataset(name, data=arr)
+            with h5py.File(model_dir + "/wavenet.opt", "w") as f:
+                f.create_dataset("t", data=np.int32(self.optimizer.t))
+                f.create_dataset("epoch", data=np.int32(0))
+                for name, (mm, vv) in moments.items():
+                    f.create_dataset(name + "/m", data=mm)
+                    f.create_dataset(name + "/v", data=vv)
+
+    def _set_moments(self, get):
+        dev = self._params.device
+        m = torch.zeros(self.flat_size, dtype=torch.float32)
+        v = torch.zeros(self.flat_size, dtype=torch.float32)
+        for name, (off, n, shape) in self.layout.items():
+            mv = get(name)
+            if mv is not None:
+                m[off:off + n] = torch.from_numpy(np.asarray(mv[0], dtype=np.float32).reshape(-1))
+                v[off:off + n] = torch.from_numpy(np.asarray(mv[1], dtype=np.float32).reshape(-1))
+        self._m, self._v = m.to(dev), v.to(dev)
 
     def load(self, model_dir="./"):
+        h5py = self._h5py()
         filename = model_dir + "/wavenet.model.npz"
         if os.path.isfile(filename):
             print("loading", filename, "...")
             with np.load(filename) as f:
                 self.set_weights({k: f[k] for k in f.files})
+        elif h5py is not None and os.path.isfile(model_dir + "/wavenet.model"):
+            print("loading", model_dir + "/wavenet.model", "...")
+            with h5py.File(model_dir + "/wavenet.model", "r") as f:
+                self.set_weights({name: np.asarray(f[name]) for name in self.layout if name in f})
         filename = model_dir + "/wavenet.opt.npz"
         if os.path.isfile(filename):
             print("loading", filename, "...")
             with np.load(filename) as f:
                 self.optimizer.t = int(f["t"])
-                dev = self._params.device
-                m = torch.zeros(self.flat_size, dtype=torch.float32)
-                v = torch.zeros(self.flat_size, dtype=torch.float32)
-                for name, (off, n, shape) in self.layout.items():
-                    if name + "/m" in f.files:
-                        m[off:off + n] = torch.from_numpy(f[name + "/m"].reshape(-1))
-                        v[off:off + n] = torch.from_numpy(f[name + "/v"].reshape(-1))
-                self._m, self._v = m.to(dev), v.to(dev)
+                self._set_moments(lambda name: (f[name + "/m"], f[name + "/v"]) if name + "/m" in f.files else None)
+        elif h5py is not None and os.path.isfile(model_dir + "/wavenet.opt"):
+            print("loading", model_dir + "/wavenet.opt", "...")
+            with h5py.File(model_dir + "/wavenet.opt", "r") as f:
+                self.optimizer.t = int(np.asarray(f["t"]))
+                self._set_moments(lambda name: (np.asarray(f[name + "/m"]), np.asarray(f[name + "/v"]))
+                                  if name + "/m" in f else None)
