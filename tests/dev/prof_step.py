@@ -1,5 +1,5 @@
 import sys, os
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from oracle import wavenet_oracle as O
 from bench import config_c, synth_batch
@@ -7,7 +7,7 @@ from wavenet_b200.faster_wavenet import FasterWaveNet
 B, W = 32, 16000
 net = FasterWaveNet(config_c(), seed=0)
 net.set_weights(O.init_weights(O.config_C(), np.random.default_rng(1234), np.float32))
-net.to_gpu(0); net.set_precision("tf32"); net.update_laerning_rate(1e-3)
+net.to_gpu(0); net.set_precision(sys.argv[2] if len(sys.argv) > 2 else "fp16x2"); net.update_laerning_rate(1e-3)
 x, t = synth_batch(0, B, W)
 xd, td = torch.from_numpy(x).cuda(), torch.from_numpy(t).cuda()
 for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
