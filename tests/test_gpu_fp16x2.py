@@ -67,6 +67,25 @@ def test_fp16x2_matches_oracle(name, B, W, T, tc):
     check_grads(net.get_grads(), g_ref)
 
 
+@pytest.mark.parametrize("name,B,W,T", [("C_small", 2, 1000, 1000), ("C", 1, 4200, 1129), ("C", 3, 2171, 977), ("B", 1, 600, 343)])
+def test_fp16x2_fused_train_step_gradients_match_oracle(name, B, W, T):
+    """The path train_step() runs (wn_forward_loss: head ReLU fused into the skip GEMM, softmax cross-entropy fused into the
+    last head conv, dlogits / dskip / dzs / dafg kept as ONE fp16 plane, 16-bit fixed-point sigmoid tape): loss and every
+    gradient against the fp64 oracle at the north star's gates."""
+    cfg = make_cfg(name)
+    w = O.init_weights(cfg, np.random.default_rng(1234), np.float64)
+    x = np.random.default_rng(0).integers(0, 256, (B, W)).astype(np.int32)
+    tgt = np.random.default_rng(1).integers(0, 256, (B, T)).astype(np.int32)
+    fw = O.forward_loss(cfg, w, x, tgt, train_width=T, dtype=np.float64)
+    g_ref = O.backward(cfg, fw)
+    net = make_net(cfg, w)
+    net.set_precision("fp16x2")
+    net._bind(B, W)
+    net._fwd_bwd(dev(x), dev(tgt), T)
+    assert abs(float(net._loss[0]) - float(fw["loss"])) < 1e-5
+    check_grads(net.get_grads(), g_ref)
+
+
 def test_fp16x2_block_outputs():
     """forward_causal_block / forward_residual_block / forward_softmax_block one by one (localises a failing kernel),
     including foreign numpy inputs to the later blocks."""
@@ -91,25 +110,38 @@ def test_fp16x2_block_outputs():
 
 
 def test_fp16x2_adam_steps_match_oracle():
+    """Three train steps (wavenet.py:515-519 + Chainer-2 hooks/Adam).  Two separate claims:
+    (1) gradient parity at every step of the trajectory: loss within 1e-5, every gradient within 1e-3 of the fp64 oracle AT THE
+        PRODUCT'S CURRENT WEIGHTS;
+    (2) optimiser parity: the oracle's clip + Adam applied to the product's OWN gradients reproduces the product's weights to
+        fp32 rounding.
+    (A max-abs comparison of two free-running trajectories is not a meaningful gate for any path inside the 1e-3 gradient
+    tolerance: Adam's first steps move every weight by ~lr * sign(g), so the few elements whose gradient is smaller than the
+    tolerated error flip by 2 lr, and with random targets the next gradient then differs by percents --
+    tests/dev/quant_sensitivity.py and the simulation in DESIGN.md section 3.)"""
     cfg = make_cfg("C_small")
     rng = np.random.default_rng(8)
     w = O.init_weights(cfg, rng, np.float64)
     net = make_net(cfg, w)
     net.set_precision("fp16x2")
     net.update_laerning_rate(1e-3)
-    w_ref = {k: v.copy() for k, v in w.items()}
+    w_ref = {k: v.astype(np.float32).astype(np.float64) for k, v in w.items()}
     st = O.new_adam_state(w_ref)
     for step in range(3):
         x = rng.integers(0, 256, (2, 300)).astype(np.int32)
         tgt = rng.integers(0, 256, (2, 173)).astype(np.int32)
         fw = O.forward_loss(cfg, w_ref, x, tgt, train_width=173, dtype=np.float64)
-        g_ref = O.backward(cfg, fw)
-        O.clip_and_adam(cfg, w_ref, g_ref, st, lr=1e-3)
-        loss = net.train_step(dev(x), dev(tgt), train_width=173)
-        assert abs(float(loss[0]) - float(fw["loss"])) < 1e-4
-    w_got = net.get_weights()
-    for k in w_ref:
-        assert np.abs(w_got[k] - w_ref[k]).max() < 5e-5, k
+        logits, loss = run_train_step(net, x, tgt, 173)
+        assert abs(float(loss.data) - float(fw["loss"])) < 1e-5
+        net.backward()
+        g = net.get_grads()
+        check_grads(g, O.backward(cfg, fw))
+        O.clip_and_adam(cfg, w_ref, {k: v.astype(np.float64) for k, v in g.items()}, st, lr=1e-3)
+        net.update()
+        w_got = net.get_weights()
+        for k in w_ref:
+            assert np.abs(w_got[k] - w_ref[k]).max() < 2e-6, (step, k)
+        w_ref = {k: v.astype(np.float64) for k, v in w_got.items()}     # continue from the product's fp32 weights
 
 
 def test_fp16x2_full_size_agrees_with_fp32_path():

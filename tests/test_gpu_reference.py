@@ -71,11 +71,23 @@ def test_train_step_matches_executed_reference(tag, name, prec):
     assert not bad, bad
     net.update()
     w2 = net.get_weights()
+    if prec == "fp32":
+        for k in w:
+            if full:
+                assert np.abs(w2[k] - gd["u:" + k]).max() < 2e-5, k
+            else:
+                assert digest_err(digest(k, w2[k].astype(np.float64) - w[k]), gd["u:" + k]) < 1e-2, k
+        return
+    # fp16x2 (gradients inside the 1e-3 gate, not bit-close): Adam's first step moves every weight by lr * sign(g), so an
+    # element whose gradient is smaller than the tolerated gradient error may legitimately land 2 lr away from the
+    # reference's.  Optimiser parity is therefore checked on the product's OWN gradients (the oracle's clip + Adam is pinned to
+    # the executed reference in tests/test_reference_pin.py), and against the reference's weights statistically.
+    w_own = {k: v.astype(np.float64) for k, v in w.items()}
+    O.clip_and_adam(cfg, w_own, {k: v.astype(np.float64) for k, v in g.items()}, O.new_adam_state(w_own), lr=1e-3)
     for k in w:
+        assert np.abs(w2[k] - w_own[k]).max() < 2e-6, k
         if full:
-            assert np.abs(w2[k] - gd["u:" + k]).max() < 2e-5, k
-        else:
-            assert digest_err(digest(k, w2[k].astype(np.float64) - w[k]), gd["u:" + k]) < 1e-2, k
+            assert (np.abs(w2[k] - gd["u:" + k]) < 2e-5).mean() > 0.98, k
 
 
 @pytest.mark.parametrize("tag,name", [("tiny_k2", "tiny_k2"), ("tiny_k3_bias", "tiny_k3_bias"), ("C_small", "C_small")])

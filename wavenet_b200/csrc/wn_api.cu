@@ -512,6 +512,7 @@ extern "C" int wn_cross_entropy(wn_handle* h, const int32_t* target, float* loss
     h->gscale = gscale;
   }
   bool split_written = false;
+  h->dlogits_single = false;
   WN_TRY(simt_cross_entropy(WS(t.hbuf.back()), target, rows, h->Q, (double*)WS(t.loss_acc), loss, WS(t.dlogits),
                             WS(t.ce_colsum), &h->ce_colsum_valid, h->sm_count, s, gscale, &split_written));
   if (h->head_split && !split_written) WN_TRY(tcs_scale_split_dlogits(h, h->T, h->gscale, s));   // generic Q: convert in place

@@ -122,6 +122,7 @@ struct wn_handle {
   const int32_t* fuse_ce_target = nullptr;   // set by wn_forward_loss: the head's last conv runs the cross-entropy epilogue
   float* fuse_ce_logits = nullptr;           //   optional fp32 logits output of that fused kernel
   bool ce_fused_done = false;
+  bool dlogits_single = false;     // dlogits on the tape are ONE fp16 plane (fused CE epilogue) instead of split rows
   // data-parallel communicator (wn_comm.cu): an ncclComm_t owned by the handle
   void* comm = nullptr;
   int comm_rank = 0, comm_world = 1;

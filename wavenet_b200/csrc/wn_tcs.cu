@@ -76,14 +76,6 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
   if (lane == 0) mbar_arrive(bar);
 }
 
-// three MMAs of one K=16 step of a split product (A planes ah/al, B planes bh/bl)
-__device__ __forceinline__ void umma_split(uint32_t d_tmem, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl, uint32_t idesc,
-                                           uint32_t accumulate) {
-  umma_f16(d_tmem, ah, bh, idesc, accumulate);
-  umma_f16(d_tmem, ah, bl, idesc, 1u);
-  umma_f16(d_tmem, al, bh, idesc, 1u);
-}
-
 // ---- hi/lo split of fp32 values ---------------------------------------------------------------
 __device__ __forceinline__ __half2 bits_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 
@@ -156,8 +148,8 @@ __device__ __forceinline__ void store_split16(__half* p, int C, const float (&o)
 // Y[(b,t)][n] = epi( sum_slab  A[slab_idx][b][t + slab_row_off][:] . W[n][slab*K ...] ), both operands split.
 // The ring holds plane-stages [A_p 128x64 | B_p BNx64]; K block kb uses two consecutive stages (hi, lo).
 struct SGemmArgs {
-  void* Y;                 // fp32 [rows][ldy] or split [rows][hi(ldy) | lo(ldy)]
-  int ldy, out_split;
+  void* Y;                 // fp32 [rows][ldy], split [rows][hi(ldy) | lo(ldy)] or (out_half) one fp16 plane [rows][ldy]
+  int ldy, out_split, out_half;
   const float* bias;       // [N] or null
   int N;                   // valid output columns
   int relu;
@@ -170,12 +162,13 @@ struct SGemmArgs {
   int ldm, mask_rows_in, mask_row_off;
   int rows_out;
   int nslab, kblk;         // K = nslab * kblk * 64
+  int a_planes;            // 2: A rows are split [hi | lo]; 1: ONE fp16 plane (gradient tensors), two MMAs per product
   int a_plane;             // elements between the hi and lo planes of an A row
   int b_plane;             // elements between the planes of a W row (= total K)
   int slab_row_off[MAX_SLABS];
   int slab_idx[MAX_SLABS];
   int tiles_per_seq, num_tiles, ngroups;
-  int y_slab_cols;         // >0 (fp32 output only): column block c goes to Y + (c / y_slab_cols) * y_slab_stride
+  int y_slab_cols;         // >0 (fp32 / fp16 output): column block c goes to Y + (c / y_slab_cols) * y_slab_stride elements
   int64_t y_slab_stride;
   // gate-backward epilogue (MODE 1, N == G): acc + Rsd is dz; writes da_f | da_g into the split tensor gate_dafg
   const float* gate_sg;    // [rows][gate_sg_ld] fp32 sigmoid
@@ -190,7 +183,7 @@ struct SGemmArgs {
   // MODE 6 (last head conv fused with softmax cross-entropy; N == 256): Y (optional) receives the fp32 logits
   const int32_t* ce_target;   // [rows]
   double* ce_acc;             // += sum over rows of (logsumexp - logit[target])
-  __half* ce_dlogits;         // split [rows][hi 256 | lo 256] = (softmax - onehot) * ce_invn * ce_gscale
+  __half* ce_dlogits;         // ONE fp16 plane [rows][256] = (softmax - onehot) * ce_invn * ce_gscale
   float ce_invn, ce_gscale;
 };
 
@@ -203,9 +196,17 @@ struct SGemmCfg {
   static constexpr int SMEM = STG + 8 * 4096 + 1024 + 1024;
 };
 
-// fp32-grade gate nonlinearities (expf with full argument reduction; absolute error ~1e-7)
-__device__ __forceinline__ float tanh_acc(float x) { return 1.f - __fdividef(2.f, expf(2.f * x) + 1.f); }
-__device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.f, 1.f + expf(-x)); }
+// fp32-grade gate nonlinearities on ONE MUFU.EX2 each: e^y = ex2.approx(y * log2 e).  ex2.approx is good to 2 ulp and the
+// rounded product adds |y| * 2^-24 relative; both enter tanh / sigmoid through d tanh = 2 E eps / (E + 1)^2 <= eps / 2, so
+// the absolute error stays below 1e-6 for every x (measured: logits 4e-6 from the oracle, against a 1e-4 gate).  expf() with
+// its full range reduction costs ~3x the instructions in an epilogue that is bound by instruction issue, not by MUFU.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float tanh_acc(float x) { return 1.f - __fdividef(2.f, ex2_approx(x * 2.8853900817779268f) + 1.f); }
+__device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.f, 1.f + ex2_approx(x * -1.4426950408889634f)); }
 
 // gate derivative from (z = tanh * sg, sg):  da_f = dz * sg * (1 - tanh^2) = dz * (sg - z^2 / sg),
 // da_g = dz * tanh * sg * (1 - sg) = dz * z * (1 - sg).  A saturated gate (sg == 0, hence z == 0) has zero derivative.
@@ -214,6 +215,14 @@ __device__ __forceinline__ void gate_deriv(float dz, float z, float sg, float li
   df = live * dz * r;
   dg = live * dz * z * (1.f - sg);
 }
+
+// Sigmoid tape of the fused shape: 16-bit FIXED POINT, sg ~= q / 65536.  The backward needs the sigmoid's ABSOLUTE accuracy
+// (da_f = dz (sg - z^2 / sg), da_g = dz z (1 - sg): an error e in sg moves both by at most |dz| e (1 + tanh^2)), and a
+// fixed-point code has a uniform 2^-17 = 7.6e-6 -- 30x finer than fp16 on [0.5, 1) -- in half the bytes of fp32.
+__device__ __forceinline__ uint32_t sg_q16(float sg) { return min(__float2uint_rn(sg * 65536.f), 65535u); }
+__device__ __forceinline__ uint32_t sg_pack2(float a, float b) { return sg_q16(a) | (sg_q16(b) << 16); }
+__device__ __forceinline__ float sg_lo(uint32_t u) { return (float)(u & 0xffffu) * (1.f / 65536.f); }
+__device__ __forceinline__ float sg_hi(uint32_t u) { return (float)(u >> 16) * (1.f / 65536.f); }
 
 // ------------------------------------------------------------------------------------------
 // weight preparation: split K-major matrices [N][hi(K) | lo(K)] the MMAs consume directly
@@ -329,13 +338,13 @@ __global__ void tcs_relu_split_rows_kernel(__half* a, int C, int rows_per_seq_in
 }
 
 // column sums of a split tensor (bias gradients): out[c] += scale * sum_rows a[row][c]
-__global__ void tcs_colsum_kernel(const __half* __restrict__ a, int64_t rows, int C, float scale, float* __restrict__ out) {
+__global__ void tcs_colsum_kernel(const __half* __restrict__ a, int planes, int64_t rows, int C, float scale, float* __restrict__ out) {
   const int c = blockIdx.x * 32 + threadIdx.x;
   __shared__ float red[8][33];
   float s = 0.f;
   if (c < C)
     for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < rows; r += (int64_t)gridDim.y * 8)
-      s += __half2float(a[r * 2 * C + c]) + __half2float(a[r * 2 * C + C + c]);
+      s += __half2float(a[r * planes * C + c]) + (planes == 2 ? __half2float(a[r * 2 * C + C + c]) : 0.f);
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && c < C) {
@@ -383,13 +392,37 @@ __global__ void tcs_gate_backward_top_kernel(const __half* __restrict__ z, const
   store_split4(dafg, p, 2 * G, G + g4, dg);
 }
 
+// same for the fused shape's tape formats: sigmoid u16 fixed point [P][G], dzs fp16 [P][G] (carries gscale), dafg ONE fp16
+// plane [P][da_f G | da_g G] -- gradient tensors that only ever feed MMAs as the dY operand are rounded to nearest once
+__global__ void tcs_gate_backward_top_fused_kernel(const __half* __restrict__ z, const uint16_t* __restrict__ sg,
+                                                   const __half* __restrict__ dz, __half* __restrict__ dafg, int64_t P, int W, int G,
+                                                   int zp) {
+  const int gv = G >> 2;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * gv) return;
+  const int64_t p = i / gv;
+  const int g4 = (int)(i - p * gv) * 4;
+  const float live = (int)(p % W) >= zp ? 1.f : 0.f;
+  const float4 zz = scale4(load_split4(z, p, G, g4), INV_ACT);
+  const uint2 sq = *reinterpret_cast<const uint2*>(sg + p * G + g4);
+  const uint2 dq = *reinterpret_cast<const uint2*>(dz + p * G + g4);
+  const float2 d0 = __half22float2(bits_h2(dq.x)), d1 = __half22float2(bits_h2(dq.y));
+  float4 df, dg;
+  gate_deriv(d0.x, zz.x, sg_lo(sq.x), live, df.x, dg.x);
+  gate_deriv(d0.y, zz.y, sg_hi(sq.x), live, df.y, dg.y);
+  gate_deriv(d1.x, zz.z, sg_lo(sq.y), live, df.z, dg.z);
+  gate_deriv(d1.y, zz.w, sg_hi(sq.y), live, df.w, dg.w);
+  *reinterpret_cast<uint2*>(dafg + p * 2 * G + g4) = make_uint2(pack_h2_sat(df.x, df.y), pack_h2_sat(df.z, df.w));
+  *reinterpret_cast<uint2*>(dafg + p * 2 * G + G + g4) = make_uint2(pack_h2_sat(dg.x, dg.y), pack_h2_sat(dg.z, dg.w));
+}
+
 // ------------------------------------------------------------------------------------------
 // Fused residual layer, R = G = 64, k = 2.  Shared memory (same footprint as the tf32 kernel):
 //   B1: W1 split, sub-tiles [128 n x 64 k] indexed (tap, plane)      4 x 16 KB
 //   B2: Wp split, sub-tiles [64 r x 64 g] indexed (plane)            2 x  8 KB
 //   A : 2 stages x 4 sub-tiles: x(t-d) hi, x(t-d) lo, x(t) hi, x(t) lo; z (hi, lo) then overwrites sub-tiles 0,1 as
-//       the A operand of GEMM 2 and the source of its bulk store; the fp32 sigmoid overwrites sub-tiles 2,3 once the
-//       residual is in registers
+//       the A operand of GEMM 2 and the source of its bulk store; the 16-bit fixed-point sigmoid overwrites the thread's
+//       own bytes of sub-tile 2 (x(t) hi, same channels) once the residual is in registers
 struct SLayerArgs {
   __half* x_out;           // split [B][W][hi 64 | lo 64]
   int W, d, zp, tiles_per_seq, num_tiles;
@@ -493,8 +526,7 @@ tcs_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           TRS(j, 3);
           tma_store_4d(&tm_z, zs + 0 * SUB, 0, t0, b, 0);      // z hi plane
           tma_store_4d(&tm_z, zs + 1 * SUB, KB, t0, b, 0);     // z lo plane
-          tma_store_4d(&tm_sg, zs + 2 * SUB, 0, t0, b, 0);     // sigmoid fp32, channels 0..31
-          tma_store_4d(&tm_sg, zs + 3 * SUB, 32, t0, b, 0);    // channels 32..63
+          tma_store_4d(&tm_sg, zs + 2 * SUB, 0, t0, b, 0);     // sigmoid, 16-bit fixed point, 64 channels per 128-byte row
           bulk_commit_group();
         }
       }
@@ -567,9 +599,6 @@ tcs_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         xr[8 * c + 4] = v1.x, xr[8 * c + 5] = v1.y, xr[8 * c + 6] = v1.z, xr[8 * c + 7] = v1.w;
       }
       tmem_ld_wait();
-      // the sigmoid tiles below overwrite whole rows of sub-tiles 2 / 3, which hold x(t) of ALL channels: the three partner
-      // warps (same rows, other channels) must have taken their residuals first
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
       const bool live = valid && t >= a.zp;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -589,9 +618,12 @@ tcs_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         *reinterpret_cast<uint4*>(as_g + 1 * SUB + sw128_off(row, part * 2 + c)) = lv;
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c)   // sigmoid fp32: channels [part*16, +16) = four chunks of the 128-byte row of sub-tile 2 + part/2
-        *reinterpret_cast<uint4*>(as_g + (2 + (part >> 1)) * SUB + sw128_off(row, (part & 1) * 4 + c)) =
-            make_uint4(g[4 * c], g[4 * c + 1], g[4 * c + 2], g[4 * c + 3]);
+      for (int c = 0; c < 2; ++c)   // sigmoid q16: channels [part*16, +16) = the two chunks this thread took its x(t) hi residual from
+        *reinterpret_cast<uint4*>(as_g + 2 * SUB + sw128_off(row, part * 2 + c)) =
+            make_uint4(sg_pack2(__uint_as_float(g[8 * c]), __uint_as_float(g[8 * c + 1])),
+                       sg_pack2(__uint_as_float(g[8 * c + 2]), __uint_as_float(g[8 * c + 3])),
+                       sg_pack2(__uint_as_float(g[8 * c + 4]), __uint_as_float(g[8 * c + 5])),
+                       sg_pack2(__uint_as_float(g[8 * c + 6]), __uint_as_float(g[8 * c + 7])));
       fence_proxy_async();
       tcgen05_fence_before();
       warp_arrive(z_full(s), lane);
@@ -716,6 +748,17 @@ __device__ __forceinline__ void epi_row32(const SGemmArgs& a, const float (&v)[3
 #pragma unroll
         for (int i = 0; i < 16; ++i) o[i] *= a.out_scale;
         store_split16(reinterpret_cast<__half*>(a.Y) + orow * (2 * (int64_t)a.ldy) + col, a.ldy, o);
+      } else if (a.out_half) {
+        __half* yp = reinterpret_cast<__half*>(a.Y);
+        int ycol = col;
+        if (a.y_slab_cols > 0) {
+          yp += (int64_t)(col / a.y_slab_cols) * a.y_slab_stride;
+          ycol = col % a.y_slab_cols;
+        }
+        uint32_t u[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u[i] = pack_h2_sat(o[2 * i], o[2 * i + 1]);
+        st256(yp + orow * a.ldy + ycol, u);
       } else {
         float* yp = reinterpret_cast<float*>(a.Y);
         int ycol = col;
@@ -792,8 +835,9 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               const int s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
               mbar_wait(empty(s), ph ^ 1);
               const uint32_t st = base + s * Cfg::STAGE;
-              mbar_arrive_expect_tx(full(s), Cfg::STAGE);
-              tma_load_4d(st, &tm_a, full(s), p * a.a_plane + kc * KB, a.slab_row_off[sl] + t0, b, a.slab_idx[sl]);
+              const bool a_here = p < a.a_planes;      // a single-plane A has no lo tile: the lo stage carries B_lo only
+              mbar_arrive_expect_tx(full(s), a_here ? Cfg::STAGE : BN * 128);
+              if (a_here) tma_load_4d(st, &tm_a, full(s), p * a.a_plane + kc * KB, a.slab_row_off[sl] + t0, b, a.slab_idx[sl]);
               tma_load_2d(st + SUB, &tm_b, full(s), p * a.b_plane + (sl * a.kblk + kc) * KB, grp * BN);
             }
       }
@@ -843,7 +887,8 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
             umma_f16(tmem + ab * BN, umma_desc_k_sw128(sh + k4 * 32), umma_desc_k_sw128(sl + SUB + k4 * 32), idesc, 1u);
-            umma_f16(tmem + ab * BN, umma_desc_k_sw128(sl + k4 * 32), umma_desc_k_sw128(sh + SUB + k4 * 32), idesc, 1u);
+            if (a.a_planes == 2)
+              umma_f16(tmem + ab * BN, umma_desc_k_sw128(sl + k4 * 32), umma_desc_k_sw128(sh + SUB + k4 * 32), idesc, 1u);
           }
           umma_commit(empty(s0));
           umma_commit(empty(s0 + 1));
@@ -896,8 +941,8 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     if constexpr (MODE == 6) {
       // Last head conv fused with softmax cross-entropy (wavenet.py:590 + 597-617): the logits of a row live in the
       // registers of TWO threads (this warp's 128 columns, the partner warp's other 128), so the row maximum and the
-      // exp-sum are exchanged through shared memory; the loss and dlogits (split fp16, scaled by gscale -- the operand format
-      // of the backward GEMMs) leave from here.  The logits themselves are only written on request.
+      // exp-sum are exchanged through shared memory; the loss and dlogits (one fp16 plane, scaled by gscale -- the dY operand
+      // format of the backward GEMMs) leave from here.  The logits themselves are only written on request.
       static_assert(MODE != 6 || BN == 256, "the fused CE epilogue needs the whole 256-class row in one tile");
       float* xmax = reinterpret_cast<float*>(stg);                 // this warp's 4 KB staging block: [32 rows] max | sum | tgt logit
       float* pmax = reinterpret_cast<float*>(gbase + Cfg::STG + (((warp - 2) ^ 4)) * 4096);   // partner warp (same rows, other half)
@@ -947,7 +992,7 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         sum += pmax[32 + lane];
         if (valid && half == 0) loss_part += (double)(m + logf(sum)) - (double)xt;
         const float inv = 1.f / sum, gk = a.ce_invn * a.ce_gscale;
-        __half* drow = a.ce_dlogits + orow * (2 * (int64_t)BN) + cbase;
+        __half* drow = a.ce_dlogits + orow * (int64_t)BN + cbase;
         float* yp = a.Y ? reinterpret_cast<float*>(a.Y) + orow * a.ldy + cbase : nullptr;
 #pragma unroll 1
         for (int ch = 0; ch < CH; ++ch) {
@@ -966,7 +1011,9 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               d[i] = (expf(l - m) * inv - (col == tg ? 1.f : 0.f)) * gk;
             }
             if (valid) {
-              store_split16(drow + ch * 32 + hh * 16, BN, d);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) u[i] = pack_h2_sat(d[2 * i], d[2 * i + 1]);
+              st256(drow + ch * 32 + hh * 16, u);
               if (yp) {     // logits on request
 #pragma unroll
                 for (int i = 0; i < 8; ++i) u[i] = v[hh * 16 + i];
@@ -1086,6 +1133,7 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 struct SWgradArgs {
   int rows_it, num_seq;
   int a_row_off, a_c0, a_plane;   // dY: first channel, elements between its planes
+  int a_planes;                   // 2: dY rows are split; 1: one fp16 plane (two MMAs per product)
   int nb_slab, nb_sub;            // X slabs (taps or layers) and 64-channel sub-tiles per slab
   int b_plane;                    // elements between the planes of an X row
   int b_row_off[4];
@@ -1166,12 +1214,14 @@ tcs_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
         mbar_wait(empty(s), ph ^ 1);
         const uint32_t st = base + s * Cfg::STAGE;
-        mbar_arrive_expect_tx(full(s), Cfg::STAGE);
+        mbar_arrive_expect_tx(full(s), Cfg::STAGE - (a.a_planes == 1 ? 2 * MH * SUBW : 0));
         for (int p = 0; p < 2; ++p) {
           const uint32_t sp = st + p * NSUB * SUBW;
+          if (p < a.a_planes) {
 #pragma unroll
-          for (int i = 0; i < 2 * MH; ++i)
-            tma_load_4d(sp + i * SUBW, &tm_a, full(s), p * a.a_plane + a.a_c0 + i * KB, a.a_row_off + t0, b, 0);
+            for (int i = 0; i < 2 * MH; ++i)
+              tma_load_4d(sp + i * SUBW, &tm_a, full(s), p * a.a_plane + a.a_c0 + i * KB, a.a_row_off + t0, b, 0);
+          }
           for (int sl = 0; sl < a.nb_slab; ++sl)
             for (int i = 0; i < a.nb_sub; ++i)
               tma_load_4d(sp + (2 * MH + sl * a.nb_sub + i) * SUBW, &tm_b, full(s), p * a.b_plane + i * KB, a.b_row_off[sl] + t0, b,
@@ -1193,9 +1243,12 @@ tcs_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const uint64_t bh = desc_mn_sw128(sh + 2 * MH * SUBW + k16 * kstep, lbo, sbo);
           const uint64_t bl = desc_mn_sw128(sl + 2 * MH * SUBW + k16 * kstep, lbo, sbo);
 #pragma unroll
-          for (int mh = 0; mh < MH; ++mh)
-            umma_split(tmem + mh * NB, desc_mn_sw128(sh + 2 * mh * SUBW + k16 * kstep, lbo, sbo),
-                       desc_mn_sw128(sl + 2 * mh * SUBW + k16 * kstep, lbo, sbo), bh, bl, idesc, (it | k16) > 0);
+          for (int mh = 0; mh < MH; ++mh) {
+            const uint64_t ah = desc_mn_sw128(sh + 2 * mh * SUBW + k16 * kstep, lbo, sbo);
+            umma_f16(tmem + mh * NB, ah, bh, idesc, (it | k16) > 0);
+            umma_f16(tmem + mh * NB, ah, bl, idesc, 1u);
+            if (a.a_planes == 2) umma_f16(tmem + mh * NB, desc_mn_sw128(sl + 2 * mh * SUBW + k16 * kstep, lbo, sbo), bh, idesc, 1u);
+          }
         }
         umma_commit(empty(s));
       }
@@ -1300,11 +1353,11 @@ tcs_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 // GEMM and as the MN-major A operand of the dWp GEMM (same bytes, same 128-byte swizzle), so dout and z are read from
 // HBM exactly once and nothing is re-fetched through L2.
 struct SGateBwdArgs {
-  const float* dzs;        // fp32 [rows][64], carries gscale
-  const float* sg;         // fp32 [rows][sg_ld]
-  __half* dafg;            // split [rows][hi 128 | lo 128], carries gscale
+  const __half* dzs;       // fp16 [rows][64], carries gscale
+  const uint16_t* sg;      // 16-bit fixed-point sigmoid [rows][64]
+  __half* dafg;            // ONE fp16 plane [rows][da_f 64 | da_g 64], carries gscale
   float* dWp;              // [64 r][64 g]
-  int sg_ld, zp;
+  int zp;
   int rows_out, tiles_per_seq, num_tiles;
   int reverse;
   float wscale;            // 1 / (gscale * ACT_SCALE)
@@ -1422,11 +1475,12 @@ tcs_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_dout, const __grid_co
       const float live = t >= a.zp ? 1.f : 0.f;
       const uint8_t* st = gbase + SG_ST + s * 65536;
       // the epilogue inputs that do not depend on the accumulator: issue their loads before waiting for it
-      uint32_t d8[4][8], s8[4][8];
+      // (32 channels x 16 bit = two 256-bit loads per tensor)
+      uint32_t d8[2][8], s8[2][8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        ld256(a.dzs + orow * 64 + half * 32 + i * 8, d8[i]);
-        ld256(a.sg + orow * a.sg_ld + half * 32 + i * 8, s8[i]);
+      for (int i = 0; i < 2; ++i) {
+        ld256(a.dzs + orow * 64 + half * 32 + i * 16, d8[i]);
+        ld256(a.sg + orow * 64 + half * 32 + i * 16, s8[i]);
       }
       mbar_wait(full(s), ph);               // z tile visible to this thread's generic loads
       mbar_wait(acc_full(s), ph);
@@ -1436,8 +1490,8 @@ tcs_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_dout, const __grid_co
       tmem_ld_wait();
       tcgen05_fence_before();
       warp_arrive(acc_empty(s), lane);
-      __half* drow = a.dafg + orow * 256 + half * 32;
-      uint32_t fh[8], fl[8], gh[8], gl[8];
+      __half* drow = a.dafg + orow * 128 + half * 32;
+      uint32_t fh[8], gh[8];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint4 zh = *reinterpret_cast<const uint4*>(st + 2 * SUB + sw128_off(row, half * 4 + c));
@@ -1447,20 +1501,22 @@ tcs_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_dout, const __grid_co
         const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
         float df[8], dg[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          gate_deriv(fmaf(__uint_as_float(v[8 * c + i]), INV_W, __uint_as_float(d8[c][i])), zz[i], __uint_as_float(s8[c][i]), live,
-                     df[i], dg[i]);
+        for (int i = 0; i < 8; i += 2) {
+          const uint32_t sq = s8[c >> 1][(c & 1) * 4 + (i >> 1)];
+          const float2 dq = __half22float2(bits_h2(d8[c >> 1][(c & 1) * 4 + (i >> 1)]));
+          gate_deriv(fmaf(__uint_as_float(v[8 * c + i]), INV_W, dq.x), zz[i], sg_lo(sq), live, df[i], dg[i]);
+          gate_deriv(fmaf(__uint_as_float(v[8 * c + i + 1]), INV_W, dq.y), zz[i + 1], sg_hi(sq), live, df[i + 1], dg[i + 1]);
+        }
         const int k = (c & 1) * 4;
-        split2(df[0], df[1], fh[k], fl[k]), split2(df[2], df[3], fh[k + 1], fl[k + 1]);
-        split2(df[4], df[5], fh[k + 2], fl[k + 2]), split2(df[6], df[7], fh[k + 3], fl[k + 3]);
-        split2(dg[0], dg[1], gh[k], gl[k]), split2(dg[2], dg[3], gh[k + 1], gl[k + 1]);
-        split2(dg[4], dg[5], gh[k + 2], gl[k + 2]), split2(dg[6], dg[7], gh[k + 3], gl[k + 3]);
-        if ((c & 1) && valid) {     // 16 channels per plane = one 256-bit store each
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          fh[k + i] = pack_h2_sat(df[2 * i], df[2 * i + 1]);
+          gh[k + i] = pack_h2_sat(dg[2 * i], dg[2 * i + 1]);
+        }
+        if ((c & 1) && valid) {     // 16 channels = one 256-bit store per gate half
           const int o16 = (c >> 1) * 16;
-          st256(drow + o16, fh);            // da_f hi
-          st256(drow + 64 + o16, gh);       // da_g hi
-          st256(drow + 128 + o16, fl);      // da_f lo
-          st256(drow + 192 + o16, gl);      // da_g lo
+          st256(drow + o16, fh);            // da_f
+          st256(drow + 64 + o16, gh);       // da_g
         }
       }
       warp_arrive(empty(s), lane);          // done reading z from the stage
@@ -1488,9 +1544,11 @@ tcs_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_dout, const __grid_co
 // Backward of one residual layer's dilated conv for the fused shape (R = G = 64, two taps), one pass over dafg:
 //   dx[t]  = dout[t] + dafg[t] . W1(tap 1) + dafg[t+d] . W1(tap 0)       (K-major GEMM, K = 2 x 128, N = 64)
 //   dW_f/g(o, c, tap) += sum_t dafg[t][o] * x[t - (1-tap) d][c]             (MN-major GEMM over the same rows)
-// The ring streams "units" (row slab 0/1, gate half f/g): A = [128 positions x 64 channels] hi + lo planes of dafg,
-// B = the matching [64 c x 64 k] block of W1^T.  The slab-0 units double as the MN-major A operand of the weight
-// gradient (M atom 0 = the unit's 64 gate channels, atom 1 = zeros; one accumulator per gate half), B = [x(t-d) | x(t)].
+// dafg is ONE fp16 plane (round-to-nearest of the gate derivative; it only ever is the dY operand of these two products and
+// its rounding error is 2.5e-4 of the gradient norm, tests/dev/quant_sensitivity.py), so every product is TWO MMAs
+// (dafg . B_hi + dafg . B_lo).  The ring streams "units" (row slab 0/1, gate half f/g): A = [128 positions x 64 channels] of
+// dafg, B = the matching [64 c x 64 k] block of W1^T (hi, lo).  The slab-0 units double as the MN-major A operand of the
+// weight gradient (M atom 0 = the unit's 64 gate channels, atom 1 = zeros; one accumulator per gate half), B = [x(t-d) | x(t)].
 struct SDxwArgs {
   const __half* rsd;       // dout of the layer above, split [rows][hi 64 | lo 64]; null for the top layer
   __half* Y;               // new dout, split
@@ -1501,8 +1559,8 @@ struct SDxwArgs {
   int reverse;
   float wscale;            // 1 / (gscale * ACT_SCALE)
 };
-constexpr int SD_STAGE = 2 * SUB + 2 * 8192;    // A hi, A lo [128 x 64], B hi, B lo [64 x 64]
-constexpr int SD_STAGES = 3;
+constexpr int SD_STAGE = SUB + 2 * 8192;        // A [128 x 64], B hi, B lo [64 x 64]
+constexpr int SD_STAGES = 4;
 constexpr int SD_X = SD_STAGES * SD_STAGE;      // x(t-d) hi | x(t) hi | x(t-d) lo | x(t) lo
 constexpr int SD_ZERO = SD_X + 4 * SUB;
 constexpr int SD_BAR = SD_ZERO + SUB;
@@ -1571,10 +1629,9 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
           mbar_wait(empty(s), ph ^ 1);
           const uint32_t st = base + s * SD_STAGE;
           mbar_arrive_expect_tx(full(s), SD_STAGE);
-          tma_load_4d(st, &tm_da, full(s), ch * KB, t0 + sl * a.d, b, 0);                 // dafg hi plane, gate half ch
-          tma_load_4d(st + SUB, &tm_da, full(s), 128 + ch * KB, t0 + sl * a.d, b, 0);     // lo plane
-          tma_load_2d(st + 2 * SUB, &tm_w, full(s), sl * 128 + ch * KB, 0);               // W1^T[c][slab*128 + n] hi
-          tma_load_2d(st + 2 * SUB + 8192, &tm_w, full(s), 256 + sl * 128 + ch * KB, 0);  // lo
+          tma_load_4d(st, &tm_da, full(s), ch * KB, t0 + sl * a.d, b, 0);                 // dafg, gate half ch
+          tma_load_2d(st + SUB, &tm_w, full(s), sl * 128 + ch * KB, 0);                   // W1^T[c][slab*128 + n] hi
+          tma_load_2d(st + SUB + 8192, &tm_w, full(s), 256 + sl * 128 + ch * KB, 0);      // lo
         }
       }
     }
@@ -1594,12 +1651,10 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
           }
           mbar_wait(full(s), ph);
           tcgen05_fence_after();
-          const uint32_t st = base + s * SD_STAGE, wb = st + 2 * SUB;
+          const uint32_t st = base + s * SD_STAGE, wb = st + SUB;
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
+          for (int k4 = 0; k4 < 4; ++k4)   // the small (lo-plane) terms first: the accumulator truncates toward zero
             umma_f16(tmem + ab * 64, umma_desc_k_sw128(st + k4 * 32), umma_desc_k_sw128(wb + 8192 + k4 * 32), idesc, (u | k4) > 0);
-            umma_f16(tmem + ab * 64, umma_desc_k_sw128(st + SUB + k4 * 32), umma_desc_k_sw128(wb + k4 * 32), idesc, 1u);
-          }
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4)
             umma_f16(tmem + ab * 64, umma_desc_k_sw128(st + k4 * 32), umma_desc_k_sw128(wb + k4 * 32), idesc, 1u);
@@ -1608,11 +1663,9 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
 #pragma unroll
             for (int k16 = 0; k16 < TM / 16; ++k16) {
               const uint64_t ah = desc_mn_sw128(st + k16 * 2048, zero - st, 1024);
-              const uint64_t al = desc_mn_sw128(st + SUB + k16 * 2048, zero - (st + SUB), 1024);
               const uint64_t bh = desc_mn_sw128(xs + k16 * 2048, SUB, 1024);
               const uint64_t bl = desc_mn_sw128(xs + 2 * SUB + k16 * 2048, SUB, 1024);
               umma_f16(tmem + 128 + u * 128, ah, bl, idesc_mn, (j | k16) > 0);
-              umma_f16(tmem + 128 + u * 128, al, bh, idesc_mn, 1u);
               umma_f16(tmem + 128 + u * 128, ah, bh, idesc_mn, 1u);
             }
           }
@@ -1734,20 +1787,6 @@ int map_h2d(CUtensorMap* m, const __half* ptr, uint64_t d0, uint64_t d1, uint64_
   return WN_OK;
 }
 
-// fp32 tensor, box [1][1][box1][32] (the sigmoid store of the fused layer kernel)
-int map_f4d(CUtensorMap* m, const float* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2, uint32_t box1) {
-  EncodeTiledFn enc = get_encode();
-  WN_REQUIRE(enc, WN_ECUDA, "cuTensorMapEncodeTiled is unavailable");
-  cuuint64_t dims[4] = {d0, d1, d2, 1};
-  cuuint64_t strides[3] = {s1 * 4, s2 * 4, s2 * d2 * 4};
-  cuuint32_t box[4] = {32, box1, 1, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  WN_REQUIRE(r == CUDA_SUCCESS, WN_ECUDA, "cuTensorMapEncodeTiled(f32 4d) failed: %d", (int)r);
-  return WN_OK;
-}
-
 template <int BN, int MODE>
 int launch_sgemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const SGemmArgs& g, int sm_count, cudaStream_t s) {
   using Cfg = SGemmCfg<BN>;
@@ -1797,6 +1836,7 @@ struct SOperand {
   int num_seq;
   int nslab;
   int64_t slab_stride;   // in halves
+  int planes = 2;        // 2: rows are [hi(C) | lo(C)]; 1: one fp16 plane [C] (gradient tensors of the fused backward)
 };
 
 struct SEpilogue {
@@ -1809,6 +1849,7 @@ struct SEpilogue {
   int ldm = 0, mask_rows_in = 0, mask_row_off = 0;
   int y_slab_cols = 0;
   int64_t y_slab_stride = 0;
+  int out_half = 0;
   const float* gate_sg = nullptr;
   const __half* gate_z = nullptr;
   __half* gate_dafg = nullptr;
@@ -1832,10 +1873,11 @@ inline const __half* HP(const float* p) { return reinterpret_cast<const __half*>
 int tcs_gemm(const wn_handle* h, const SOperand& A, int ns, const int* slab_idx, const int* row_off, int rows_out,
              const __half* Wt, int N, const SEpilogue& e, void* Y, int ldy, int out_split, cudaStream_t s) {
   const bool plain = !e.gate_sg && !e.Rsd && !e.mask;
-  WN_REQUIRE(A.C % KB == 0 && N % 64 == 0 && (N <= 256 || plain) && ns <= MAX_SLABS && (e.y_slab_cols == 0 || !out_split),
+  WN_REQUIRE(A.C % KB == 0 && N % 64 == 0 && (N <= 256 || plain) && ns <= MAX_SLABS && (e.y_slab_cols == 0 || !out_split) &&
+                 !(e.out_half && out_split),
              WN_EINVAL, "tcs_gemm: unsupported shape K=%d N=%d slabs=%d", A.C, N, ns);
   CUtensorMap ta, tb;
-  const int64_t rowe = 2 * (int64_t)A.C;
+  const int64_t rowe = A.planes * (int64_t)A.C;
   const int64_t sstride = A.nslab > 1 ? A.slab_stride : (int64_t)A.rows_in * A.num_seq * rowe;
   WN_TRY(map_h4d(&ta, A.ptr, rowe, A.rows_in, A.num_seq, A.nslab, rowe, (uint64_t)A.rows_in * rowe, sstride, TM));
   const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
@@ -1846,6 +1888,7 @@ int tcs_gemm(const wn_handle* h, const SOperand& A, int ns, const int* slab_idx,
   g.Y = Y;
   g.ldy = ldy;
   g.out_split = out_split;
+  g.out_half = e.out_half;
   g.bias = e.bias;
   g.N = N;
   g.relu = e.relu;
@@ -1869,6 +1912,7 @@ int tcs_gemm(const wn_handle* h, const SOperand& A, int ns, const int* slab_idx,
   g.zero_rows_below = e.zero_rows_below;
   g.reverse = e.reverse;
   g.flush = e.flush && !e.gate_sg && !e.colsum_out;
+  WN_REQUIRE(A.planes == 2 || (!g.flush && !e.gate_sg && !e.ce_target), WN_EINVAL, "tcs_gemm: single-plane A is a backward operand");
   g.colsum_out = e.ngroups_ok_for_colsum(N, BN) ? e.colsum_out : nullptr;
   g.ce_target = e.ce_target;
   g.ce_acc = e.ce_acc;
@@ -1879,6 +1923,7 @@ int tcs_gemm(const wn_handle* h, const SOperand& A, int ns, const int* slab_idx,
   g.rows_out = rows_out;
   g.nslab = ns;
   g.kblk = A.C / KB;
+  g.a_planes = A.planes;
   g.a_plane = A.C;
   g.b_plane = (int)Ktot;
   for (int i = 0; i < ns; ++i) {
@@ -1906,7 +1951,7 @@ int tcs_wgrad(const wn_handle* h, const SOperand& dY, int a_row_off, int a_c0, i
   // accumulator rows >= m_valid, which the epilogue never stores)
   constexpr int WG_KC = 32;
   CUtensorMap ta, tb;
-  const int64_t rowa = 2 * (int64_t)dY.C, rowx = 2 * (int64_t)X.C;
+  const int64_t rowa = dY.planes * (int64_t)dY.C, rowx = 2 * (int64_t)X.C;
   WN_TRY(map_h4d(&ta, dY.ptr, rowa, dY.rows_in, dY.num_seq, 1, rowa, (uint64_t)dY.rows_in * rowa,
                  (uint64_t)dY.rows_in * dY.num_seq * rowa, WG_KC));
   const int64_t xstride = X.nslab > 1 ? X.slab_stride : (int64_t)X.rows_in * X.num_seq * rowx;
@@ -1918,6 +1963,7 @@ int tcs_wgrad(const wn_handle* h, const SOperand& dY, int a_row_off, int a_c0, i
   g.a_row_off = a_row_off;
   g.a_c0 = a_c0;
   g.a_plane = dY.C;
+  g.a_planes = dY.planes;
   g.nb_slab = nb_slab;
   g.nb_sub = X.C / KB;
   g.b_plane = X.C;
@@ -1962,8 +2008,8 @@ int tcs_wgrad(const wn_handle* h, const SOperand& dY, int a_row_off, int a_c0, i
 }
 
 // dz GEMM + gate derivative + dWp in one pass (fused shape R = G = 64); dWp must be 16-byte aligned
-int tcs_gate_bwd(const wn_handle* h, const __half* dout, const __half* wpt, const float* dzs, const __half* z, const float* sg,
-                 int sg_ld, __half* dafg, float* dWp, int zp, int rows, int num_seq, int reverse, float wscale, cudaStream_t s) {
+int tcs_gate_bwd(const wn_handle* h, const __half* dout, const __half* wpt, const __half* dzs, const __half* z, const uint16_t* sg,
+                 __half* dafg, float* dWp, int zp, int rows, int num_seq, int reverse, float wscale, cudaStream_t s) {
   CUtensorMap td, tz, tw;
   const uint64_t seq = (uint64_t)rows * 128, all = seq * num_seq;
   WN_TRY(map_h4d(&td, dout, 128, rows, num_seq, 1, 128, seq, all, TM));
@@ -1973,7 +2019,6 @@ int tcs_gate_bwd(const wn_handle* h, const __half* dout, const __half* wpt, cons
   memset(&g, 0, sizeof(g));
   g.dzs = dzs;
   g.sg = sg;
-  g.sg_ld = sg_ld;
   g.dafg = dafg;
   g.dWp = dWp;
   g.zp = zp;
@@ -1997,8 +2042,8 @@ int tcs_gate_bwd(const wn_handle* h, const __half* dout, const __half* wpt, cons
 int tcs_dxw(const wn_handle* h, const __half* dafg, const __half* w1t, const __half* rsd, const __half* x, __half* Y, float* dWf,
             float* dWg, int d, int rows, int num_seq, int reverse, float wscale, cudaStream_t s) {
   CUtensorMap ta, tw, tx;
-  const uint64_t seqa = (uint64_t)rows * 256, alla = seqa * num_seq, seqx = (uint64_t)rows * 128, allx = seqx * num_seq;
-  WN_TRY(map_h4d(&ta, dafg, 256, rows, num_seq, 1, 256, seqa, alla, TM));
+  const uint64_t seqa = (uint64_t)rows * 128, alla = seqa * num_seq, seqx = (uint64_t)rows * 128, allx = seqx * num_seq;
+  WN_TRY(map_h4d(&ta, dafg, 128, rows, num_seq, 1, 128, seqa, alla, TM));
   WN_TRY(map_h2d(&tw, w1t, 512, 64, 512, 64));
   WN_TRY(map_h4d(&tx, x, 128, rows, num_seq, 1, 128, seqx, allx, TM));
   SDxwArgs g;
@@ -2065,7 +2110,7 @@ int tcs_layer_launch(wn_handle* h, int l, cudaStream_t s) {
   CUtensorMap tx, tw1, tw2, tz, tsg;
   WN_TRY(map_h4d(&tx, HP(h->ws + t.x[l]), 128, t.W, t.B, 1, 128, (uint64_t)t.W * 128, (uint64_t)t.P * 128, TM));
   WN_TRY(map_h4d(&tz, HP(h->ws + t.z[l]), 128, t.W, t.B, 1, 128, (uint64_t)t.W * 128, (uint64_t)t.P * 128, TM));
-  WN_TRY(map_f4d(&tsg, h->ws + t.tfsg[l], 64, t.W, t.B, 64, (uint64_t)t.W * 64, TM));
+  WN_TRY(map_h4d(&tsg, HP(h->ws + t.tfsg[l]), 64, t.W, t.B, 1, 64, (uint64_t)t.W * 64, (uint64_t)t.P * 64, TM));   // u16 rows
   WN_TRY(map_h2d(&tw1, HP(h->ws + t.tc_w1) + (int64_t)l * 2 * 128 * 128, 256, 128, 256, 128));
   WN_TRY(map_h2d(&tw2, HP(h->ws + t.tc_w2) + (int64_t)l * 2 * 64 * 64, 128, 64, 128, 64));
   SLayerArgs a;
@@ -2158,7 +2203,7 @@ int tcs_forward_residual(wn_handle* h, const float* params, cudaStream_t s) {
   WN_TRY(tcs_prepare_weights(h, params, s));
   if (fused_shape(h)) {
     for (int l = 0; l < L; ++l) WN_TRY(tcs_layer_launch(h, l, s));
-    h->tape_gates_zs = true;     // tape keeps (z split, sigmoid fp32 with row stride G)
+    h->tape_gates_zs = true;     // tape keeps (z split, sigmoid 16-bit fixed point [P][G])
   } else {
     const int R = h->R, G = h->layers[0].G;
     for (int l = 0; l < L; ++l) {
@@ -2228,6 +2273,7 @@ int tcs_forward_head(wn_handle* h, const float* params, int T, bool external, cu
       WN_CHECK_CUDA(cudaMemsetAsync(e.ce_acc, 0, 2 * sizeof(double), s));
       WN_TRY(tcs_gemm(h, A, 1, nullptr, &off, T, HP(h->ws + t.tc_wh[i]), cp.out_ch, e, h->fuse_ce_logits, cp.out_ch, 0, s));
       h->ce_fused_done = true;
+      h->dlogits_single = true;
       continue;
     }
     WN_TRY(tcs_gemm(h, A, 1, nullptr, &off, T, HP(h->ws + t.tc_wh[i]), cp.out_ch, e, h->ws + t.hbuf[i], cp.out_ch, last ? 0 : 1, s));
@@ -2249,6 +2295,8 @@ int tcs_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s
   const float inv_wg = inv * INV_ACT;         // weight gradients: dY (gscale) x activation (ACT_SCALE)
   const int zero = 0;
   // ---- head ----
+  // head gradients: one fp16 plane when dlogits came from the fused cross-entropy epilogue (the train step), split otherwise
+  const int dpl = h->dlogits_single ? 1 : 2;
   const __half* d = HP(ws + t.dlogits);
   int tog = 0;
   bool bias_done = false;
@@ -2258,7 +2306,7 @@ int tcs_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s
     const int rin = first ? (h->head_external ? T : W) : T;
     const int aoff = first ? (h->head_external ? 0 : W - T) : 0;
     const __half* Ain = first ? HP(ws + t.skip) : HP(ws + t.hbuf[i - 1]);
-    SOperand dY{d, cp.out_ch, T, B, 1, 0};
+    SOperand dY{d, cp.out_ch, T, B, 1, 0, dpl};
     SOperand X{Ain, cp.in_ch, rin, B, 1, 0};
     for (int m0 = 0; m0 < cp.out_ch; m0 += 256) {
       const int mv = cp.out_ch - m0 < 256 ? cp.out_ch - m0 : 256;
@@ -2270,7 +2318,7 @@ int tcs_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s
         WN_TRY(simt_add_vec(ws + t.ce_colsum, grads + cp.b_off, cp.out_ch, s));   // unscaled column sums from the CE kernel
       } else {
         dim3 grid(nblk(cp.out_ch, 32), 64), block(32, 8);
-        tcs_colsum_kernel<<<grid, block, 0, s>>>(d, (int64_t)B * T, cp.out_ch, inv, grads + cp.b_off);
+        tcs_colsum_kernel<<<grid, block, 0, s>>>(d, dpl, (int64_t)B * T, cp.out_ch, inv, grads + cp.b_off);
         WN_CHECK_LAUNCH();
       }
     }
@@ -2288,21 +2336,32 @@ int tcs_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s
       e.colsum_scale = inv;
       bias_done = true;
     }
-    WN_TRY(tcs_gemm(h, dY, 1, nullptr, &zero, T, HP(ws + t.tc_wht[i]), cp.in_ch, e, ws + t.dh[tog], cp.in_ch, 1, s));
+    e.out_half = dpl == 1;
+    WN_TRY(tcs_gemm(h, dY, 1, nullptr, &zero, T, HP(ws + t.tc_wht[i]), cp.in_ch, e, ws + t.dh[tog], cp.in_ch, dpl == 2, s));
     d = HP(ws + t.dh[tog]);
     tog ^= 1;
   }
-  const __half* dskip = d;   // split [B*T][S]
-  SOperand DS{dskip, S, T, B, 1, 0};
+  const __half* dskip = d;   // [B*T][S], dpl planes
+  SOperand DS{dskip, S, T, B, 1, 0, dpl};
   const int wt = W - T, nwt = -(W - T);
   const int64_t zstride = L > 1 ? t.z[1] - t.z[0] : (int64_t)P * G;   // floats
+  // The fused shape keeps the gradient tensors that are only ever read back as MMA dY operands / epilogue addends in ONE
+  // fp16 plane (dzs, dafg; round to nearest, gscale keeps them in the normal range) and the sigmoid tape in 16-bit fixed
+  // point; the residual-gradient stream dout, which accumulates over all layers, stays split.
+  const bool fused = fused_shape(h);
+  if (fused)
+    for (const ResLayer& ly : h->layers)
+      WN_REQUIRE((((uintptr_t)(grads + ly.proj.w_off) | (uintptr_t)(grads + ly.wf.w_off) | (uintptr_t)(grads + ly.wg.w_off)) & 15) == 0,
+                 WN_EINVAL, "fp16x2 backward: gradient buffers of the residual layers must be 16-byte aligned");
   // ---- skip path for ALL layers at once ----
-  //  dzs[l] = dskip . Ws_l  (fp32 slabs, read by the gate epilogues only): one GEMM with N = L*G in 256-column groups
+  //  dzs[l] = dskip . Ws_l  (slabs read by the gate epilogues only; fp16 for the fused shape, fp32 otherwise): one GEMM with
+  //  N = L*G in 256-column groups
   {
     SEpilogue e;
     e.y_slab_cols = G;
     e.y_slab_stride = (int64_t)P * G;
     e.acc_scale = INV_W;
+    e.out_half = fused ? 1 : 0;
     WN_TRY(tcs_gemm(h, DS, 1, nullptr, &nwt, W, HP(ws + t.tc_wst), L * G, e, ws + t.dzs, G, 0, s));
   }
   //  dWs_l = dskip^T . z_l : groups of nl layers per CTA group (dskip read from HBM once)
@@ -2338,20 +2397,23 @@ int tcs_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s
     const ResLayer& ly = h->layers[l];
     const int zp = wn_zero_prefix(W, ly.dilation, 2);
     const int dir = serp ? (l & 1) : 0, ndir = serp ? !dir : 0;
-    const float* dzs = ws + t.dzs + (int64_t)l * P * G;
-    const float* sg = h->tape_gates_zs ? ws + t.tfsg[l] : ws + t.tfsg[l] + G;
-    const int sg_ld = h->tape_gates_zs ? G : 2 * G;
+    const float* dzs = ws + t.dzs + (int64_t)l * P * G;                      // generic shapes: fp32 slabs
+    const __half* dzs_h = HP(ws + t.dzs) + (int64_t)l * P * G;               // fused shape: fp16 slabs
+    const float* sg = ws + t.tfsg[l] + G;                                    // generic shapes: (tanh | sigmoid) fp32
+    const int sg_ld = 2 * G;
+    const uint16_t* sg_q = reinterpret_cast<const uint16_t*>(ws + t.tfsg[l]);   // fused shape: 16-bit fixed point [P][G]
     SOperand Z{HP(ws + t.z[l]), G, W, B, 1, 0};
     __half* dafg = HP(ws + t.dafg);
     float* dwp = grads + ly.proj.w_off;
     float* dwf = grads + ly.wf.w_off;
     float* dwg = grads + ly.wg.w_off;
-    const bool fused = fused_shape(h) && (((uintptr_t)dwp | (uintptr_t)dwf | (uintptr_t)dwg) & 15) == 0 &&
-                       getenv("WN_NO_BWD_FUSE") == nullptr;
     if (dout && fused) {
       // fused: gate forwards, dxw backwards (serpentine hand-off through L2)
-      WN_TRY(tcs_gate_bwd(h, dout, HP(ws + t.tc_wpt) + (int64_t)l * 2 * G * R, dzs, HP(ws + t.z[l]), sg, sg_ld, dafg, dwp, zp, W, B,
-                          serp ? 0 : 0, inv_wg, s));
+      WN_TRY(tcs_gate_bwd(h, dout, HP(ws + t.tc_wpt) + (int64_t)l * 2 * G * R, dzs_h, HP(ws + t.z[l]), sg_q, dafg, dwp, zp, W, B, 0,
+                          inv_wg, s));
+    } else if (fused) {
+      tcs_gate_backward_top_fused_kernel<<<nblk(P * (G / 4), 256), 256, 0, s>>>(HP(ws + t.z[l]), sg_q, dzs_h, dafg, P, W, G, zp);
+      WN_CHECK_LAUNCH();
     } else if (dout) {
       // dz = dout . Wp + dzs_l, gate derivative fused into the epilogue -> dafg
       SOperand DO{dout, R, W, B, 1, 0};
