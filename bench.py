@@ -386,11 +386,12 @@ def main():
                 _lib.check(lib.wn_tcs_layer_forward(net._h, l, _stream()))
         layers_only()
         lay_ms = timed(layers_only, args.steps) / n_layers
-        # split rows are 4 B per channel: read x(t) once (x(t-d) re-read hits L2), write x_out, z and the fp32 sigmoid
-        bytes_per_pos = 4 * 64 * 4
+        # split rows are 4 B per channel: read x(t) once (x(t-d) re-read hits L2), write x_out and z (split) and the 16-bit
+        # fixed-point sigmoid tape
+        bytes_per_pos = 3 * 64 * 4 + 64 * 2
         alg_bytes = bytes_per_pos * B * W
         achieved = alg_bytes / (lay_ms / 1e3) / 1e9
-        traffic, tsrc = stored_traffic("r02_ncu_tcs_layer_kernel.json")
+        traffic, tsrc = stored_traffic("r02_ncu_tcs_layer_kernel_final.json")
         layer_flops = 2 * (128 * 128 + 64 * 64) * B * W
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": tsrc,
@@ -504,8 +505,12 @@ def main():
     if not args.no_gen:
         gen = {}
         Win = net.input_width
-        for n_total in (1, 256):
-            n = max(1, n_total // world) if n_total > 1 else 1
+        # batch_256 shards 256 streams over the ranks (BASELINE config 4, strong scaling: 256 / N streams per GPU);
+        # batch_256_per_gpu (N > 1 only) keeps 256 streams on EVERY GPU (weak scaling, the units-per-rank-fixed reading of 5)
+        cases = [("batch_1", 1, 1), ("batch_256", 256, max(1, 256 // world))]
+        if world > 1:
+            cases.append(("batch_256_per_gpu", 256 * world, 256))
+        for key, n_total, n in cases:
             if n_total == 1 and rank != 0:
                 continue
             if n_total == 1:
@@ -539,8 +544,9 @@ def main():
             clustered = n <= 15          # gen_kernel_v4: one 8-CTA cluster per stream while all clusters are co-resident
             n_ctas = 8 * n if clustered else -(-n // (1 if n <= 148 else 2))
             per_cta = 32 * 32768 if clustered else 1270272 * 4   # bytes of packed fp32 weights per CTA per step
-            gen["batch_%d" % n_total] = {
-                "samples_per_s": total_streams * steps / (gms / 1e3), "streams": total_streams, "steps": steps,
+            gen[key] = {
+                "samples_per_s": total_streams * steps / (gms / 1e3), "streams": total_streams, "streams_per_gpu": n,
+                "scaling": "weak" if key == "batch_256_per_gpu" else ("strong" if n_total > 1 else "single stream"), "steps": steps,
                 "us_per_step": us, "cycles_per_sample_per_stream": us * sm_mhz,
                 "kernel": "gen_kernel_v4 (8-CTA cluster per stream, output-split matvecs, st.async exchanges)" if clustered
                           else "gen_kernel_v3 (one CTA per 1-2 streams)",

@@ -205,8 +205,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float tanh_acc(float x) { return 1.f - __fdividef(2.f, ex2_approx(x * 2.8853900817779268f) + 1.f); }
-__device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.f, 1.f + ex2_approx(x * -1.4426950408889634f)); }
+// The gate with ONE reciprocal: with E1 = e^(2 a_f), E2 = e^(-a_g), r = 1 / ((E1 + 1)(1 + E2)):
+//   sigmoid(a_g) = (E1 + 1) r,   tanh(a_f) sigmoid(a_g) = (E1 - 1) r        (three MUFU ops per gate element instead of four).
+// E1 and E2 are capped at 1e13 (tanh is 1 - 2e-13, sigmoid 1e-13 there), so the product stays below 1e26; `scale` undoes
+// the operand scales of the accumulator and is folded into the exponent multipliers.
+__device__ __forceinline__ void gate_acc(float af, float ag, float scale, float& z, float& sg) {
+  const float e1 = fminf(ex2_approx(af * (scale * 2.8853900817779268f)), 1e13f);
+  const float e2 = fminf(ex2_approx(ag * (scale * -1.4426950408889634f)), 1e13f);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((e1 + 1.f) * (1.f + e2)));
+  sg = (e1 + 1.f) * r;
+  z = (e1 - 1.f) * r;
+}
 
 // gate derivative from (z = tanh * sg, sg):  da_f = dz * sg * (1 - tanh^2) = dz * (sg - z^2 / sg),
 // da_g = dz * tanh * sg * (1 - sg) = dz * z * (1 - sg).  A saturated gate (sg == 0, hence z == 0) has zero derivative.
@@ -216,13 +226,21 @@ __device__ __forceinline__ void gate_deriv(float dz, float z, float sg, float li
   dg = live * dz * z * (1.f - sg);
 }
 
-// Sigmoid tape of the fused shape: 16-bit FIXED POINT, sg ~= q / 65536.  The backward needs the sigmoid's ABSOLUTE accuracy
+// Sigmoid tape of the fused shape: 16-bit FIXED POINT, sg ~= q / 65535.  The backward needs the sigmoid's ABSOLUTE accuracy
 // (da_f = dz (sg - z^2 / sg), da_g = dz z (1 - sg): an error e in sg moves both by at most |dz| e (1 + tanh^2)), and a
 // fixed-point code has a uniform 2^-17 = 7.6e-6 -- 30x finer than fp16 on [0.5, 1) -- in half the bytes of fp32.
-__device__ __forceinline__ uint32_t sg_q16(float sg) { return min(__float2uint_rn(sg * 65536.f), 65535u); }
-__device__ __forceinline__ uint32_t sg_pack2(float a, float b) { return sg_q16(a) | (sg_q16(b) << 16); }
-__device__ __forceinline__ float sg_lo(uint32_t u) { return (float)(u & 0xffffu) * (1.f / 65536.f); }
-__device__ __forceinline__ float sg_hi(uint32_t u) { return (float)(u >> 16) * (1.f / 65536.f); }
+// Both directions go through the 2^23 trick (an fp32 in [2^23, 2^24) has its integer part in the low mantissa bits, and
+// the add rounds to nearest) so that neither F2I nor I2F -- quarter-rate XU-pipe instructions, like MUFU -- is needed.
+__device__ __forceinline__ uint32_t sg_pack2(float a, float b) {
+  // q = round(sg * 65535) sits in the low 16 mantissa bits of sg * 65535 + 2^23; one byte permute packs two of them
+  return __byte_perm(__float_as_uint(fmaf(a, 65535.f, 8388608.f)), __float_as_uint(fmaf(b, 65535.f, 8388608.f)), 0x5410);
+}
+__device__ __forceinline__ float sg_lo(uint32_t u) {
+  return (__uint_as_float(0x4b000000u | (u & 0xffffu)) - 8388608.f) * (1.f / 65535.f);
+}
+__device__ __forceinline__ float sg_hi(uint32_t u) {
+  return (__uint_as_float(0x4b000000u | (u >> 16)) - 8388608.f) * (1.f / 65535.f);
+}
 
 // ------------------------------------------------------------------------------------------
 // weight preparation: split K-major matrices [N][hi(K) | lo(K)] the MMAs consume directly
@@ -534,140 +552,170 @@ tcs_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc1 = idesc_f16(128, 128);
+      // One thread issues BOTH GEMMs and polls for whichever is ready: GEMM 1 of tile n1 (operands loaded, accumulator
+      // buffer drained by the gate epilogue of tile n1 - 2) or GEMM 2 of tile n2 (every row of z in shared memory).  Neither
+      // ever waits behind the other's barrier (an MMA thread blocked on the next tile's load used to stall the epilogue).
+      constexpr uint32_t idesc1 = idesc_f16(128, 128), idesc2 = idesc_f16(128, 64);
       mbar_wait(b_full, 0);
-      for (int j1 = 0; j1 < n_local; ++j1) {
-        const int s = j1 & 1;
-        if (j1 >= 2) mbar_wait(z_full(s), ((j1 - 2) >> 1) & 1);
-        mbar_wait(a_full(s), (j1 >> 1) & 1);
-        TRS(j1, 4);
-        tcgen05_fence_after();
-        const uint32_t as = base + SL_A + s * 65536;
-        // The tensor core accumulates with round-toward-zero: every MMA step loses ~half an ulp OF THE ACCUMULATOR.  The
-        // cross terms (hi.lo, lo.hi) are 2^-11 of the result, so they go first, while the accumulator is still small; only
-        // the hi.hi steps then run at full magnitude (8 truncating steps instead of 24).
+      int n1 = 0, n2 = 0;
+      uint32_t spins = 0;
+      while (n2 < n_local) {
+        bool did = false;
+        if (n1 < n_local) {
+          const int s = n1 & 1;
+          if (mbar_try_wait(a_full(s), (n1 >> 1) & 1) && (n1 < 2 || mbar_try_wait(z_full(s), ((n1 - 2) >> 1) & 1))) {
+            TRS(n1, 4);
+            tcgen05_fence_after();
+            const uint32_t as = base + SL_A + s * 65536;
+            // The tensor core accumulates with round-toward-zero: every MMA step loses ~half an ulp OF THE ACCUMULATOR.  The
+            // cross terms (hi.lo, lo.hi) are 2^-11 of the result, so they go first, while the accumulator is still small;
+            // only the hi.hi steps then run at full magnitude (8 truncating steps instead of 24).
 #pragma unroll
-        for (int tap = 0; tap < 2; ++tap)
+            for (int tap = 0; tap < 2; ++tap)
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const uint32_t ao = as + tap * 2 * SUB + k4 * 32, bo = base + SL_B1 + tap * 2 * SUB + k4 * 32;
-            umma_f16(tmem + s * 128, umma_desc_k_sw128(ao), umma_desc_k_sw128(bo + SUB), idesc1, (tap | k4) > 0);
-            umma_f16(tmem + s * 128, umma_desc_k_sw128(ao + SUB), umma_desc_k_sw128(bo), idesc1, 1u);
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const uint32_t ao = as + tap * 2 * SUB + k4 * 32, bo = base + SL_B1 + tap * 2 * SUB + k4 * 32;
+                umma_f16(tmem + s * 128, umma_desc_k_sw128(ao), umma_desc_k_sw128(bo + SUB), idesc1, (tap | k4) > 0);
+                umma_f16(tmem + s * 128, umma_desc_k_sw128(ao + SUB), umma_desc_k_sw128(bo), idesc1, 1u);
+              }
+#pragma unroll
+            for (int tap = 0; tap < 2; ++tap)
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const uint32_t ao = as + tap * 2 * SUB + k4 * 32, bo = base + SL_B1 + tap * 2 * SUB + k4 * 32;
+                umma_f16(tmem + s * 128, umma_desc_k_sw128(ao), umma_desc_k_sw128(bo), idesc1, 1u);
+              }
+            umma_commit(d1_full(s));
+            TRS(n1, 5);
+            ++n1;
+            did = true;
           }
+        }
+        if (n2 < n1) {
+          const int s = n2 & 1;
+          if (mbar_try_wait(z_full(s), (n2 >> 1) & 1)) {
+            TRS(n2, 6);
+            tcgen05_fence_after();
+            const uint32_t as = base + SL_A + s * 65536;
 #pragma unroll
-        for (int tap = 0; tap < 2; ++tap)
+            for (int k4 = 0; k4 < 4; ++k4) {   // cross terms first (see GEMM 1)
+              const uint32_t ao = as + k4 * 32, bo = base + SL_B2 + k4 * 32;
+              umma_f16(tmem + 256 + s * 64, umma_desc_k_sw128(ao), umma_desc_k_sw128(bo + 8192), idesc2, k4 > 0);
+              umma_f16(tmem + 256 + s * 64, umma_desc_k_sw128(ao + SUB), umma_desc_k_sw128(bo), idesc2, 1u);
+            }
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const uint32_t ao = as + tap * 2 * SUB + k4 * 32, bo = base + SL_B1 + tap * 2 * SUB + k4 * 32;
-            umma_f16(tmem + s * 128, umma_desc_k_sw128(ao), umma_desc_k_sw128(bo), idesc1, 1u);
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint32_t ao = as + k4 * 32, bo = base + SL_B2 + k4 * 32;
+              umma_f16(tmem + 256 + s * 64, umma_desc_k_sw128(ao), umma_desc_k_sw128(bo), idesc2, 1u);
+            }
+            umma_commit(d2_full(s));
+            ++n2;
+            did = true;
           }
-        umma_commit(d1_full(s));
-        TRS(j1, 5);
+        }
+        if (did) {
+          spins = 0;
+        } else if (++spins > (1u << 26)) {
+          printf("wavenet_b200: tcs_layer_kernel MMA thread timeout (block %d, n1 %d, n2 %d)\n", (int)blockIdx.x, n1, n2);
+          __trap();
+        }
       }
     }
   } else {
-    // 16 epilogue warps: the gate epilogue is a long dependent chain per element (two exponentials, two reciprocals, the
-    // hi/lo splits), so it is bound by instruction latency, not by issue slots -- four warps per scheduler hide it
-    // (ncu, 8 warps: 0.21 IPC per warp, 42 % issue utilisation, tile period 9.1 k cycles against an HBM floor of 5.7 k)
+    // 16 epilogue warps (four per scheduler: the gate epilogue is a long dependent chain per element).  The two epilogues of
+    // a tile are SKEWED by one tile: gate epilogue of tile j, then the projection epilogue of tile j - 1 -- GEMM 2 of tile
+    // j - 1 (issued when the slowest warp delivered its z rows, ~1.3 k cycles of tensor-core latency) has long finished by
+    // then, so no warp ever sits waiting for it (trace before: 2.2 k of a 7.5 k cycle tile period were that wait).
     const int q = warp & 3;               // TMEM lane quarter this warp may access
     const int part = (warp - 2) >> 2;     // which 16 of the 64 channels this warp handles
     const int row = q * 32 + lane;
-    if (threadIdx.x == 64) mbar_wait(b_full, 0);
-    for (int j = 0; j < n_local; ++j) {
-      const int tile = tile_of(j);
-      const int s = j & 1, ph = (j >> 1) & 1;
-      const int b = tile / a.tiles_per_seq, t = (tile % a.tiles_per_seq) * TM + row;
-      const bool valid = t < a.W;
-      uint8_t* as_g = gbase + SL_A + s * 65536;
-      const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-      // ---- epilogue 1: gate ----
-      mbar_wait(d1_full(s), ph);
-      if (threadIdx.x == 64) TRS(j, 8);
-      tcgen05_fence_after();
-      uint32_t f[16], g[16];
-      tmem_ld16(trow + s * 128 + part * 16, f);
-      tmem_ld16(trow + s * 128 + 64 + part * 16, g);
-      // residual ACT_SCALE * x(t) = hi + lo of this thread's row and channels, into registers
-      float xr[16];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const uint4 hv = *reinterpret_cast<const uint4*>(as_g + 2 * SUB + sw128_off(row, part * 2 + c));
-        const uint4 lv = *reinterpret_cast<const uint4*>(as_g + 3 * SUB + sw128_off(row, part * 2 + c));
-        const float4 v0 = join4(make_uint2(hv.x, hv.y), make_uint2(lv.x, lv.y));
-        const float4 v1 = join4(make_uint2(hv.z, hv.w), make_uint2(lv.z, lv.w));
-        xr[8 * c + 0] = v0.x, xr[8 * c + 1] = v0.y, xr[8 * c + 2] = v0.z, xr[8 * c + 3] = v0.w;
-        xr[8 * c + 4] = v1.x, xr[8 * c + 5] = v1.y, xr[8 * c + 6] = v1.z, xr[8 * c + 7] = v1.w;
-      }
-      tmem_ld_wait();
-      const bool live = valid && t >= a.zp;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float af = __uint_as_float(f[i]) * INV_ACT_W, ag = __uint_as_float(g[i]) * INV_ACT_W;
-        const float tf = tanh_acc(af), sg = sigmoid_acc(ag);
-        g[i] = __float_as_uint(live ? sg : 0.5f);          // masked rows look like tanh(0) | sigmoid(0)
-        f[i] = __float_as_uint(live ? ACT_SCALE * tf * sg : 0.f);   // z is stored with ACT_SCALE
-      }
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {   // z planes: 8 channels per 16-byte chunk
-        uint4 hv, lv;
-        split2(__uint_as_float(f[8 * c + 0]), __uint_as_float(f[8 * c + 1]), hv.x, lv.x);
-        split2(__uint_as_float(f[8 * c + 2]), __uint_as_float(f[8 * c + 3]), hv.y, lv.y);
-        split2(__uint_as_float(f[8 * c + 4]), __uint_as_float(f[8 * c + 5]), hv.z, lv.z);
-        split2(__uint_as_float(f[8 * c + 6]), __uint_as_float(f[8 * c + 7]), hv.w, lv.w);
-        *reinterpret_cast<uint4*>(as_g + 0 * SUB + sw128_off(row, part * 2 + c)) = hv;
-        *reinterpret_cast<uint4*>(as_g + 1 * SUB + sw128_off(row, part * 2 + c)) = lv;
-      }
-#pragma unroll
-      for (int c = 0; c < 2; ++c)   // sigmoid q16: channels [part*16, +16) = the two chunks this thread took its x(t) hi residual from
-        *reinterpret_cast<uint4*>(as_g + 2 * SUB + sw128_off(row, part * 2 + c)) =
-            make_uint4(sg_pack2(__uint_as_float(g[8 * c]), __uint_as_float(g[8 * c + 1])),
-                       sg_pack2(__uint_as_float(g[8 * c + 2]), __uint_as_float(g[8 * c + 3])),
-                       sg_pack2(__uint_as_float(g[8 * c + 4]), __uint_as_float(g[8 * c + 5])),
-                       sg_pack2(__uint_as_float(g[8 * c + 6]), __uint_as_float(g[8 * c + 7])));
-      fence_proxy_async();
-      tcgen05_fence_before();
-      warp_arrive(z_full(s), lane);
-      if (threadIdx.x == 64) TRS(j, 9);
-      if (threadIdx.x == 64) {
-        // one epilogue thread issues GEMM 2 as soon as every row of z is in shared memory
-        constexpr uint32_t idesc2 = idesc_f16(128, 64);
-        mbar_wait(z_full(s), ph);
-        TRS(j, 6);
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    float xr[16];                         // residual ACT_SCALE * x(t) of the tile whose projection epilogue is pending
+    for (int j = 0; j <= n_local; ++j) {
+      float xn[16];
+      if (j < n_local) {
+        // ---- epilogue 1: gate ----
+        const int tile = tile_of(j);
+        const int s = j & 1, ph = (j >> 1) & 1;
+        const int t = (tile % a.tiles_per_seq) * TM + row;
+        uint8_t* as_g = gbase + SL_A + s * 65536;
+        mbar_wait(d1_full(s), ph);
+        if (threadIdx.x == 64) TRS(j, 8);
         tcgen05_fence_after();
-        const uint32_t as = base + SL_A + s * 65536;
+        uint32_t f[16], g[16];
+        tmem_ld16(trow + s * 128 + part * 16, f);
+        tmem_ld16(trow + s * 128 + 64 + part * 16, g);
+        // residual = hi + lo of this thread's row and channels, into registers
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {   // cross terms first (see GEMM 1)
-          const uint32_t ao = as + k4 * 32, bo = base + SL_B2 + k4 * 32;
-          umma_f16(tmem + 256 + s * 64, umma_desc_k_sw128(ao), umma_desc_k_sw128(bo + 8192), idesc2, k4 > 0);
-          umma_f16(tmem + 256 + s * 64, umma_desc_k_sw128(ao + SUB), umma_desc_k_sw128(bo), idesc2, 1u);
+        for (int c = 0; c < 2; ++c) {
+          const uint4 hv = *reinterpret_cast<const uint4*>(as_g + 2 * SUB + sw128_off(row, part * 2 + c));
+          const uint4 lv = *reinterpret_cast<const uint4*>(as_g + 3 * SUB + sw128_off(row, part * 2 + c));
+          const float4 v0 = join4(make_uint2(hv.x, hv.y), make_uint2(lv.x, lv.y));
+          const float4 v1 = join4(make_uint2(hv.z, hv.w), make_uint2(lv.z, lv.w));
+          xn[8 * c + 0] = v0.x, xn[8 * c + 1] = v0.y, xn[8 * c + 2] = v0.z, xn[8 * c + 3] = v0.w;
+          xn[8 * c + 4] = v1.x, xn[8 * c + 5] = v1.y, xn[8 * c + 6] = v1.z, xn[8 * c + 7] = v1.w;
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float zz, sg;
+          gate_acc(__uint_as_float(f[i]), __uint_as_float(g[i]), INV_ACT_W, zz, sg);
+          g[i] = __float_as_uint(sg);
+          f[i] = __float_as_uint(ACT_SCALE * zz);            // z is stored with ACT_SCALE
+        }
+        if (!(t < a.W && t >= a.zp)) {                       // zero-prefix / out-of-range rows look like tanh(0) | sigmoid(0)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = 0u, g[i] = 0x3f000000u;
         }
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          const uint32_t ao = as + k4 * 32, bo = base + SL_B2 + k4 * 32;
-          umma_f16(tmem + 256 + s * 64, umma_desc_k_sw128(ao), umma_desc_k_sw128(bo), idesc2, 1u);
+        for (int c = 0; c < 2; ++c) {   // z planes: 8 channels per 16-byte chunk
+          uint4 hv, lv;
+          split2(__uint_as_float(f[8 * c + 0]), __uint_as_float(f[8 * c + 1]), hv.x, lv.x);
+          split2(__uint_as_float(f[8 * c + 2]), __uint_as_float(f[8 * c + 3]), hv.y, lv.y);
+          split2(__uint_as_float(f[8 * c + 4]), __uint_as_float(f[8 * c + 5]), hv.z, lv.z);
+          split2(__uint_as_float(f[8 * c + 6]), __uint_as_float(f[8 * c + 7]), hv.w, lv.w);
+          *reinterpret_cast<uint4*>(as_g + 0 * SUB + sw128_off(row, part * 2 + c)) = hv;
+          *reinterpret_cast<uint4*>(as_g + 1 * SUB + sw128_off(row, part * 2 + c)) = lv;
         }
-        umma_commit(d2_full(s));
-      }
-      __syncwarp();
-      // ---- epilogue 2: projection + residual ----
-      mbar_wait(d2_full(s), ph);
-      if (threadIdx.x == 64) TRS(j, 10);
-      tcgen05_fence_after();
-      tmem_ld16(trow + 256 + s * 64 + part * 16, g);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      // x_out rows are [hi 64 | lo 64] halves: the thread owns channels [part*16, +16) of its row = 32 contiguous bytes in
-      // each plane = one 256-bit store per plane (a full sector, no staging)
-      if (valid) {
-        __half* xrow = a.x_out + ((int64_t)b * a.W + t) * 128 + part * 16;
-        uint32_t hv[8], lv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          split2(fmaf(__uint_as_float(g[2 * i]), INV_W, xr[2 * i]), fmaf(__uint_as_float(g[2 * i + 1]), INV_W, xr[2 * i + 1]), hv[i], lv[i]);
-        st256(xrow, hv);
-        st256(xrow + 64, lv);
+        for (int c = 0; c < 2; ++c)   // sigmoid q16: channels [part*16, +16) = the two chunks this thread took its x(t) hi residual from
+          *reinterpret_cast<uint4*>(as_g + 2 * SUB + sw128_off(row, part * 2 + c)) =
+              make_uint4(sg_pack2(__uint_as_float(g[8 * c]), __uint_as_float(g[8 * c + 1])),
+                         sg_pack2(__uint_as_float(g[8 * c + 2]), __uint_as_float(g[8 * c + 3])),
+                         sg_pack2(__uint_as_float(g[8 * c + 4]), __uint_as_float(g[8 * c + 5])),
+                         sg_pack2(__uint_as_float(g[8 * c + 6]), __uint_as_float(g[8 * c + 7])));
+        fence_proxy_async();
+        tcgen05_fence_before();
+        warp_arrive(z_full(s), lane);
+        if (threadIdx.x == 64) TRS(j, 9);
       }
-      if (threadIdx.x == 64) TRS(j, 11);
+      if (j >= 1) {
+        // ---- epilogue 2 of the PREVIOUS tile: projection + residual ----
+        const int jj = j - 1, tile = tile_of(jj);
+        const int s = jj & 1, ph = (jj >> 1) & 1;
+        const int b = tile / a.tiles_per_seq, t = (tile % a.tiles_per_seq) * TM + row;
+        mbar_wait(d2_full(s), ph);
+        if (threadIdx.x == 64) TRS(jj, 10);
+        tcgen05_fence_after();
+        uint32_t g[16];
+        tmem_ld16(trow + 256 + s * 64 + part * 16, g);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        // x_out rows are [hi 64 | lo 64] halves: the thread owns channels [part*16, +16) of its row = 32 contiguous bytes
+        // in each plane = one 256-bit store per plane (a full sector, no staging)
+        if (t < a.W) {
+          __half* xrow = a.x_out + ((int64_t)b * a.W + t) * 128 + part * 16;
+          uint32_t hv[8], lv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            split2(fmaf(__uint_as_float(g[2 * i]), INV_W, xr[2 * i]), fmaf(__uint_as_float(g[2 * i + 1]), INV_W, xr[2 * i + 1]), hv[i], lv[i]);
+          st256(xrow, hv);
+          st256(xrow + 64, lv);
+        }
+        if (threadIdx.x == 64) TRS(jj, 11);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) xr[i] = xn[i];
     }
   }
   tcgen05_fence_before();
@@ -1547,8 +1595,10 @@ tcs_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_dout, const __grid_co
 // dafg is ONE fp16 plane (round-to-nearest of the gate derivative; it only ever is the dY operand of these two products and
 // its rounding error is 2.5e-4 of the gradient norm, tests/dev/quant_sensitivity.py), so every product is TWO MMAs
 // (dafg . B_hi + dafg . B_lo).  The ring streams "units" (row slab 0/1, gate half f/g): A = [128 positions x 64 channels] of
-// dafg, B = the matching [64 c x 64 k] block of W1^T (hi, lo).  The slab-0 units double as the MN-major A operand of the
-// weight gradient (M atom 0 = the unit's 64 gate channels, atom 1 = zeros; one accumulator per gate half), B = [x(t-d) | x(t)].
+// dafg, B = the matching [64 c x 64 k] block of W1^T (hi, lo).  The two slab-0 units (da_f, da_g of the tile's own rows) sit
+// in ring stages 2 and 3 and TOGETHER are the MN-major A operand of the weight gradient (M atom 0 = the 64 f channels,
+// atom 1 = the 64 g channels, LBO = one ring stage): one M = 128 MMA per K step fills all 128 accumulator lanes (with one gate
+// half per MMA and a zero tile as the other atom the tensor pipe did twice the work), B = [x(t-d) | x(t)].
 struct SDxwArgs {
   const __half* rsd;       // dout of the layer above, split [rows][hi 64 | lo 64]; null for the top layer
   __half* Y;               // new dout, split
@@ -1561,9 +1611,9 @@ struct SDxwArgs {
 };
 constexpr int SD_STAGE = SUB + 2 * 8192;        // A [128 x 64], B hi, B lo [64 x 64]
 constexpr int SD_STAGES = 4;
+static_assert(SD_STAGES == 4, "a tile's four units must land in fixed stages (unit u in stage u)");
 constexpr int SD_X = SD_STAGES * SD_STAGE;      // x(t-d) hi | x(t) hi | x(t-d) lo | x(t) lo
-constexpr int SD_ZERO = SD_X + 4 * SUB;
-constexpr int SD_BAR = SD_ZERO + SUB;
+constexpr int SD_BAR = SD_X + 4 * SUB;
 constexpr int SD_SMEM = SD_BAR + 256;
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -1597,9 +1647,7 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
     prefetch_tmap(&tm_w);
     prefetch_tmap(&tm_x);
   }
-  for (int i = threadIdx.x; i < SUB / 16; i += blockDim.x) reinterpret_cast<uint4*>(gbase + SD_ZERO)[i] = make_uint4(0u, 0u, 0u, 0u);
-  fence_proxy_async();
-  if (warp == 1) tmem_alloc<512>(smem_u32((const void*)tmem_slot));
+  if (warp == 1) tmem_alloc<256>(smem_u32((const void*)tmem_slot));
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -1616,15 +1664,30 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
       for (int j = 0; j < n_local; ++j) {
         const int tile = tile_of(j);
         const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM;
-        mbar_wait(x_empty, (j & 1) ^ 1);
-        const uint32_t xs = base + SD_X;
-        mbar_arrive_expect_tx(x_full, 4 * SUB);
-        tma_load_4d(xs + 0 * SUB, &tm_x, x_full, 0, t0 - a.d, b, 0);
-        tma_load_4d(xs + 1 * SUB, &tm_x, x_full, 0, t0, b, 0);
-        tma_load_4d(xs + 2 * SUB, &tm_x, x_full, KB, t0 - a.d, b, 0);
-        tma_load_4d(xs + 3 * SUB, &tm_x, x_full, KB, t0, b, 0);
+        // Unit order: the two slab-1 units (dx only) first, the slab-0 units (dx + weight gradient) last -- the single x
+        // buffer is released by the previous tile's LAST unit, so its reload (issued here after the first two unit loads,
+        // rows already pulled into L2 one tile ahead) has two units of MMA work to hide behind.
+        if (j + 1 < n_local) {
+          const int tn = tile_of(j + 1);
+          const int bn = tn / a.tiles_per_seq, tn0 = (tn % a.tiles_per_seq) * TM;
+          tma_prefetch_4d(&tm_x, 0, tn0, bn, 0);
+          tma_prefetch_4d(&tm_x, KB, tn0, bn, 0);
+          if (a.d >= TM && tn0 >= a.d) {
+            tma_prefetch_4d(&tm_x, 0, tn0 - a.d, bn, 0);
+            tma_prefetch_4d(&tm_x, KB, tn0 - a.d, bn, 0);
+          }
+        }
         for (int u = 0; u < 4; ++u, ++it) {
-          const int sl = u >> 1, ch = u & 1;
+          if (u == 2) {
+            mbar_wait(x_empty, (j & 1) ^ 1);
+            const uint32_t xs = base + SD_X;
+            mbar_arrive_expect_tx(x_full, 4 * SUB);
+            tma_load_4d(xs + 0 * SUB, &tm_x, x_full, 0, t0 - a.d, b, 0);
+            tma_load_4d(xs + 1 * SUB, &tm_x, x_full, 0, t0, b, 0);
+            tma_load_4d(xs + 2 * SUB, &tm_x, x_full, KB, t0 - a.d, b, 0);
+            tma_load_4d(xs + 3 * SUB, &tm_x, x_full, KB, t0, b, 0);
+          }
+          const int sl = u < 2 ? 1 : 0, ch = u & 1;
           const int s = it % SD_STAGES, ph = (it / SD_STAGES) & 1;
           mbar_wait(empty(s), ph ^ 1);
           const uint32_t st = base + s * SD_STAGE;
@@ -1639,16 +1702,14 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
     if (lane == 0 && n_local > 0) {
       constexpr uint32_t idesc = idesc_f16(128, 64);
       constexpr uint32_t idesc_mn = idesc_f16(128, 128) | IDESC_MN_MAJOR;
-      const uint32_t zero = base + SD_ZERO, xs = base + SD_X;
+      const uint32_t xs = base + SD_X;
       int it = 0;
       for (int j = 0; j < n_local; ++j) {
         const int ab = j & 1, aph = (j >> 1) & 1;
         for (int u = 0; u < 4; ++u, ++it) {
           const int s = it % SD_STAGES, ph = (it / SD_STAGES) & 1;
-          if (u == 0) {
-            mbar_wait(acc_empty(ab), aph ^ 1);
-            mbar_wait(x_full, j & 1);
-          }
+          if (u == 0) mbar_wait(acc_empty(ab), aph ^ 1);
+          if (u == 2) mbar_wait(x_full, j & 1);
           mbar_wait(full(s), ph);
           tcgen05_fence_after();
           const uint32_t st = base + s * SD_STAGE, wb = st + SUB;
@@ -1658,20 +1719,25 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4)
             umma_f16(tmem + ab * 64, umma_desc_k_sw128(st + k4 * 32), umma_desc_k_sw128(wb + k4 * 32), idesc, 1u);
-          if (u < 2) {
-            // weight gradient of gate half u: accumulator columns [128 + u*128, +128) = (tap, c)
+          if (u == 3) {
+            // weight gradient of both gate halves: A atoms = the da_f tile (stage 2) and the da_g tile (this stage);
+            // accumulator lanes = (f | g) channel, columns [128, 256) = (tap, c)
+            const uint32_t sf = st - SD_STAGE;
 #pragma unroll
             for (int k16 = 0; k16 < TM / 16; ++k16) {
-              const uint64_t ah = desc_mn_sw128(st + k16 * 2048, zero - st, 1024);
+              const uint64_t ah = desc_mn_sw128(sf + k16 * 2048, SD_STAGE, 1024);
               const uint64_t bh = desc_mn_sw128(xs + k16 * 2048, SUB, 1024);
               const uint64_t bl = desc_mn_sw128(xs + 2 * SUB + k16 * 2048, SUB, 1024);
-              umma_f16(tmem + 128 + u * 128, ah, bl, idesc_mn, (j | k16) > 0);
-              umma_f16(tmem + 128 + u * 128, ah, bh, idesc_mn, 1u);
+              umma_f16(tmem + 128, ah, bl, idesc_mn, (j | k16) > 0);
+              umma_f16(tmem + 128, ah, bh, idesc_mn, 1u);
             }
+            umma_commit(empty(s - 1));        // the da_f stage was held for the weight-gradient MMAs
+            umma_commit(empty(s));
+            umma_commit(x_empty);
+            umma_commit(acc_full(ab));
+          } else if (u != 2) {
+            umma_commit(empty(s));
           }
-          umma_commit(empty(s));
-          if (u == 1) umma_commit(x_empty);
-          if (u == 3) umma_commit(acc_full(ab));
         }
       }
       umma_commit(wg_full);
@@ -1719,27 +1785,25 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
         }
       }
     }
-    if (n_local > 0 && q < 2) {
-      // dW_f / dW_g: TMEM lanes 0..63 = gate channel o, columns tap*64 + c; the gradient layout is (o, c, tap)
+    if (n_local > 0) {
+      // dW_f / dW_g: TMEM lanes 0..63 = f gate channel o, lanes 64..127 = g gate channel o, columns tap*64 + c; the
+      // gradient layout is (o, c, tap)
       mbar_wait(wg_full, 0);
       tcgen05_fence_after();
-#pragma unroll 1
-      for (int gate = 0; gate < 2; ++gate) {
-        uint32_t v0[32], v1[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 128 + gate * 128 + half * 32, v0);        // tap 0, channels half*32..
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 128 + gate * 128 + 64 + half * 32, v1);   // tap 1
-        tmem_ld_wait();
-        float* wrow = (gate == 0 ? a.dWf : a.dWg) + (int64_t)row * 128 + half * 64;
+      uint32_t v0[32], v1[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 128 + half * 32, v0);        // tap 0, channels half*32..
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 128 + 64 + half * 32, v1);   // tap 1
+      tmem_ld_wait();
+      float* wrow = (q < 2 ? a.dWf : a.dWg) + (int64_t)(row & 63) * 128 + half * 64;
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          red_add_v4(wrow + 4 * i, make_float4(__uint_as_float(v0[2 * i]) * a.wscale, __uint_as_float(v1[2 * i]) * a.wscale,
-                                               __uint_as_float(v0[2 * i + 1]) * a.wscale, __uint_as_float(v1[2 * i + 1]) * a.wscale));
-      }
+      for (int i = 0; i < 16; ++i)
+        red_add_v4(wrow + 4 * i, make_float4(__uint_as_float(v0[2 * i]) * a.wscale, __uint_as_float(v1[2 * i]) * a.wscale,
+                                             __uint_as_float(v0[2 * i + 1]) * a.wscale, __uint_as_float(v1[2 * i + 1]) * a.wscale));
     }
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem);
+  if (warp == 1) tmem_dealloc<256>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------
