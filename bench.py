@@ -484,6 +484,19 @@ def main():
                      "tflops": FWD_FLOP_PER_POS * B * W * world / (fwd_ms / 1e3) / 1e12},
     }
 
+    # ---- strong scaling (BASELINE config 5): GLOBAL batch 256 x 16000 at every N -- 256 / (32 N) micro-batches of 32 per rank
+    # with gradient accumulation, then ONE all-reduce + clip + Adam; the all-reduce is amortised over 8 micro-batches at N = 1
+    # and over one at N = 8 ---------------------------------------------------------------------------------------------
+    if B * world <= 256 and 256 % (B * world) == 0 and W == WIDTH:
+        k = 256 // (B * world)
+        mbs = [(x_d, t_d)] * k
+        net.train_step_accumulated(mbs)
+        sms = timed(lambda: net.train_step_accumulated(mbs), 2)
+        line["strong_scaling"] = {"global_batch": 256, "width": W, "micro_batches_per_rank": k, "ms_per_step": sms,
+                                  "samples_per_s": 256 * W / (sms / 1e3), "scaling": "strong",
+                                  "note": "one optimiser step = k x (forward + loss + backward) + gradient accumulation + "
+                                          "one all-reduce + clip + Adam"}
+
     # ---- the other precision modes on the same step (N == 1): parity class next to speed -------------------
     if world == 1 and not args.no_modes:
         modes = {eff_prec: {"ms_per_step": ms, "samples_per_s": value}}

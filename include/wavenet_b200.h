@@ -142,6 +142,11 @@ int wn_backward(wn_handle* h, const float* params, float* grads, wn_stream_t s);
  * (wavenet.py:556-563,597): all phases above back to back. */
 int wn_forward_loss(wn_handle* h, const float* params, const int32_t* x, const int32_t* target, int T, float* loss,
                     float* logits_opt, wn_stream_t s);
+/* Gradient accumulation over micro-batches (a global batch larger than one tape, e.g. BASELINE config 5's 256 x 16000 on
+ * one GPU): acc[i] += grads[i] over the flat layout.  wn_backward always starts from zeros (Chainer cleargrads,
+ * wavenet.py:516), so the caller adds each micro-batch's gradient to its accumulator and hands the accumulator to
+ * wn_clip_adam_step with grad_scale = 1 / (micro_batches * world). */
+int wn_accumulate_grads(wn_handle* h, const float* grads, float* acc, wn_stream_t s);
 
 /* optimizer.update hooks + Adam (wavenet.py:175-199,477-480 and Chainer-2
  * Adam selected at wavenet.py:83): [g += wd*p] -> global L2 norm -> clip ->

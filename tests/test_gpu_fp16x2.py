@@ -273,3 +273,37 @@ def test_tf32_fast_mode_tracks_fp32_grade_training_on_a_learnable_signal():
         g1, g2 = flat_grad(weights, "fp16x2", x, t), flat_grad(weights, "tf32", x, t)
         cos = g1 @ g2 / (np.linalg.norm(g1) * np.linalg.norm(g2))
         assert cos > 0.995, cos
+
+
+def test_gradient_accumulation_over_micro_batches_equals_the_big_batch():
+    """train_step_accumulated (wn_accumulate_grads): the summed gradient of two micro-batches of 2 sequences, divided by
+    two, is the gradient of the batch of 4 (mean over all positions), and ONE clip + Adam step follows on it."""
+    cfg = make_cfg("C_small")
+    w = O.init_weights(cfg, np.random.default_rng(3), np.float64)
+    rng = np.random.default_rng(4)
+    x = rng.integers(0, 256, (4, 600)).astype(np.int32)
+    t = rng.integers(0, 256, (4, 600)).astype(np.int32)
+    big = make_net(cfg, w)
+    big.set_precision("fp16x2")
+    big._bind(4, 600)
+    big._fwd_bwd(dev(x), dev(t), 600)
+    g_big = big.get_grads()
+    net = make_net(cfg, w)
+    net.set_precision("fp16x2")
+    net.update_laerning_rate(1e-3)
+    loss = net.train_step_accumulated([(dev(x[:2]), dev(t[:2])), (dev(x[2:]), dev(t[2:]))])
+    assert abs(float(loss[0]) - float(big._loss[0])) < 1e-5
+    # update() left the accumulator as the gradient Adam consumed: (sum / 2) * clip rate (in place, like Chainer's hooks)
+    norm, clip = float(net._norm[0]), float(cfg.gradient_clipping)
+    rate = min(1.0, clip / norm) if clip > 0 and norm > 0 else 1.0
+    flat = net._gacc.detach().cpu().numpy() / rate
+    for name, (off, n, shape) in net.layout.items():
+        if np.abs(g_big[name]).max() > 0:
+            assert rel_err(flat[off:off + n].reshape(shape), g_big[name]) < 1e-3, name
+    # the update consumed the accumulated gradient: oracle clip + Adam on it reproduces the weights
+    w_ref = {k: v.astype(np.float32).astype(np.float64) for k, v in w.items()}
+    g_acc = {name: flat[off:off + n].reshape(shape).astype(np.float64) for name, (off, n, shape) in net.layout.items()}
+    O.clip_and_adam(cfg, w_ref, g_acc, O.new_adam_state(w_ref), lr=1e-3)
+    w_got = net.get_weights()
+    for k in w_ref:
+        assert np.abs(w_got[k] - w_ref[k]).max() < 2e-6, k

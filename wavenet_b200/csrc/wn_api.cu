@@ -578,6 +578,11 @@ static int causal_backward(wn_handle* h, const float* params, float* grads, cons
                              t.B, W, c0.out_ch, h->Q, c.causal_filter_width, s);
 }
 
+extern "C" int wn_accumulate_grads(wn_handle* h, const float* grads, float* acc, wn_stream_t st) {
+  WN_REQUIRE(h && grads && acc, WN_EINVAL, "null argument");
+  return simt_add_vec(grads, acc, (int)h->flat_size, (cudaStream_t)st);
+}
+
 extern "C" int wn_backward(wn_handle* h, const float* params, float* grads, wn_stream_t st) {
   WN_REQUIRE(h && params && grads, WN_EINVAL, "null argument");
   WN_REQUIRE(h->phase == PH_LOSS, WN_ESTATE, "backward: run forward and cross_entropy first");

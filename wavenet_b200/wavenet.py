@@ -181,6 +181,7 @@ class WaveNet(object):
         self._gpu = False
         self._device = None
         self._grads = None
+        self._gacc = None
         self._ws = None
         self._ws_key = None
         self._keep = {}
@@ -296,6 +297,7 @@ class WaveNet(object):
         self._v = torch.zeros_like(self._params) if self._v is None else self._v.to(dev)
         self._scratch = torch.zeros(int(self._libh.wn_optim_scratch_bytes(self._h)), dtype=torch.uint8, device=dev)
         self._loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._gacc = None
         self._norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self._gpu = True
 
@@ -474,19 +476,23 @@ class WaveNet(object):
         """loss.backward(): fills the flat gradient buffer (no update)."""
         check(self._libh.wn_backward(self._h, _ptr(self._params), _ptr(self._grads), _stream()))
 
-    def update(self):
-        """Hooks + Adam (wavenet.py:477-480, Chainer GradientMethod.update)."""
+    def update(self, grads=None, micro_batches=1):
+        """Hooks + Adam (wavenet.py:477-480, Chainer GradientMethod.update).  `grads`: another flat gradient buffer (the
+        accumulator of train_step_accumulated) holding the SUM over `micro_batches` micro-batch gradients."""
         p, opt = self.params, self.optimizer
         grad_scale = 1.0
+        if grads is None:
+            grads = self._grads
         if self.data_parallel:
             world = int(self._libh.wn_comm_world(self._h))
             if world > 1:        # communicator behind the C ABI (dist.init_comm): NCCL all-reduce on the caller's stream
-                check(self._libh.wn_allreduce_grads(self._h, _ptr(self._grads), _stream()))
+                check(self._libh.wn_allreduce_grads(self._h, _ptr(grads), _stream()))
                 grad_scale = 1.0 / world
             else:                # no communicator in the library: torch.distributed (host-side tests)
-                grad_scale = allreduce_sum_(self._grads)
+                grad_scale = allreduce_sum_(grads)
+        grad_scale /= micro_batches
         opt.t += 1
-        check(self._libh.wn_clip_adam_step(self._h, _ptr(self._params), _ptr(self._grads), _ptr(self._m), _ptr(self._v),
+        check(self._libh.wn_clip_adam_step(self._h, _ptr(self._params), _ptr(grads), _ptr(self._m), _ptr(self._v),
                                            opt.t, opt.alpha, opt.beta1, opt.beta2, opt.eps, float(p.weight_decay),
                                            float(p.gradient_clipping), grad_scale, _ptr(self._scratch),
                                            _ptr(self._norm), _stream()))
@@ -515,7 +521,24 @@ class WaveNet(object):
                                          None, _stream()))
         self.backward()
 
-    def train_step(self, x_idx, target, train_width=None):
+    def train_step_accumulated(self, micro_batches, train_width=None):
+        """One optimiser step over a global batch that is processed as several micro-batches [(x_idx, target), ...] of the
+        same shape (BASELINE config 5 on fewer than 8 GPUs: 256 x 16000 does not fit one tape): every micro-batch runs the
+        captured forward + loss + backward, its gradient is added to an accumulator (wn_accumulate_grads), and ONE
+        all-reduce + clip + Adam follows on the mean gradient.  Returns the mean loss (device tensor)."""
+        if self._gacc is None or self._gacc.shape != self._grads.shape:
+            self._gacc = torch.zeros_like(self._grads)
+            self._lacc = torch.zeros_like(self._loss)
+        self._gacc.zero_()
+        self._lacc.zero_()
+        for x_idx, target in micro_batches:
+            self.train_step(x_idx, target, train_width, _update=False)
+            check(self._libh.wn_accumulate_grads(self._h, _ptr(self._grads), _ptr(self._gacc), _stream()))
+            self._lacc += self._loss
+        self.update(self._gacc, len(micro_batches))
+        return self._lacc / len(micro_batches)
+
+    def train_step(self, x_idx, target, train_width=None, _update=True):
         """One fused train.py:58-80 step on int32 device tensors; returns the loss tensor (no sync).
 
         The ~200 launches of forward + loss + backward are captured once per (B, W, T) shape into a CUDA graph
@@ -560,7 +583,8 @@ class WaveNet(object):
                     torch.cuda.synchronize()
                 self._graphs = {key: (graph, sx, st)}     # one shape at a time (the tape is re-bound on shape change)
                 if graph is None:
-                    self.update()
+                    if _update:
+                        self.update()
                     return self._loss
                 g = self._graphs[key]
             graph, sx, st = g
@@ -571,7 +595,8 @@ class WaveNet(object):
                 st.copy_(target, non_blocking=True)
                 graph.replay()
                 self._libh.wn_launch_count_add(self._graph_launches)
-        self.update()
+        if _update:
+            self.update()
         return self._loss
 
     # ---- checkpoint (wavenet.py:619-639) --------------------------------------------------------------------------
