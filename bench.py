@@ -555,18 +555,22 @@ def main():
             us = 1e3 * gms / steps
             sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
             clustered = n <= 15          # gen_kernel_v4: one 8-CTA cluster per stream while all clusters are co-resident
-            n_ctas = 8 * n if clustered else -(-n // (1 if n <= 148 else 2))
-            per_cta = 32 * 32768 if clustered else 1270272 * 4   # bytes of packed fp32 weights per CTA per step
+            many = False                 # gen_kernel_v5 (16 streams per 8-CTA cluster) is opt-in (WN_GEN_V5=1): slower than v3 today
+            n_ctas = 8 * n if clustered else (8 * -(-n // 16) if many else -(-n // (1 if n <= 148 else 2)))
+            per_cta = 33 * 32768 if (clustered or many) else 1270272 * 4   # bytes of packed fp32 weights per CTA per step
             gen[key] = {
                 "samples_per_s": total_streams * steps / (gms / 1e3), "streams": total_streams, "streams_per_gpu": n,
                 "scaling": "weak" if key == "batch_256_per_gpu" else ("strong" if n_total > 1 else "single stream"), "steps": steps,
                 "us_per_step": us, "cycles_per_sample_per_stream": us * sm_mhz,
                 "kernel": "gen_kernel_v4 (8-CTA cluster per stream, output-split matvecs, st.async exchanges)" if clustered
-                          else "gen_kernel_v3 (one CTA per 1-2 streams)",
+                          else ("gen_kernel_v5 (16 streams per 8-CTA cluster: weights in registers swept over the streams, "
+                                "transposing-butterfly reductions, st.async exchanges)" if many
+                                else "gen_kernel_v3 (one CTA per 1-2 streams)"),
                 "weight_stream_gbs_per_sm": per_cta / (us * 1e-6) / 1e9,
                 "weight_stream_gbs_all_ctas": n_ctas * world * per_cta / (us * 1e-6) / 1e9,
                 "bound": ("dependency-chain latency (30 layers x 1 cluster exchange + head per sample)" if clustered else
-                          "dependency-chain latency (30 layers x 2 block barriers + head per sample)")}
+                          ("FP32 FMA issue + one cluster exchange per layer (per CTA and step: 16 streams x 155 k MACs)" if many
+                           else "dependency-chain latency (30 layers x 2 block barriers + head per sample)"))}
         if rank == 0 and world == 1 and not args.no_cpu:
             gen["cpu_baseline"] = cpu_generation_sample()
             gen["batch_1"]["vs_cpu_reference"] = gen["batch_1"]["samples_per_s"] / gen["cpu_baseline"]["value"]

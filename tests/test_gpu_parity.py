@@ -394,6 +394,47 @@ def test_cluster_generator_matches_single_cta_kernel_and_continues(n):
     assert np.array_equal(a, c)
 
 
+@pytest.mark.parametrize("n", [16, 20, 37])
+def test_many_stream_cluster_generator(n):
+    """gen_kernel_v5 (opt-in; 16 streams per 8-CTA cluster; a last, partially filled cluster at n = 20 and 37) at config-C depth:
+    greedy sequences against the fp64 ring oracle and against the single-CTA kernel, continuation across wn_gen_run calls,
+    and independence of the streams (a shard of the streams generates what it generates inside the full set)."""
+    import os
+    from wavenet_b200 import _lib
+    from wavenet_b200._lib import check
+    from wavenet_b200.wavenet import _ptr, _stream
+    cfg = make_cfg("C")
+    w = O.init_weights(cfg, np.random.default_rng(7), np.float64)
+    window = np.random.default_rng(3).integers(0, 256, (n, O.input_width(cfg))).astype(np.int32)
+
+    def run(win, parts, v5):
+        os.environ["WN_GEN_V5"] = "1" if v5 else "0"        # the many-stream cluster kernel is opt-in (slower than v3 today)
+        try:
+            net = make_net(cfg, w, faster=True, head_act="reference")
+            net.prime(win)
+            outs = []
+            for steps in parts:
+                out = torch.empty((win.shape[0], steps), dtype=torch.int32, device="cuda")
+                check(net._libh.wn_gen_run(net._gen, _ptr(net._params), steps, _lib.WN_GEN_GREEDY, 0, _ptr(out), _stream()))
+                outs.append(out.cpu().numpy())
+            return np.concatenate(outs, axis=1)
+        finally:
+            os.environ.pop("WN_GEN_V5", None)
+
+    steps = 60
+    a = run(window, [steps], True)
+    want = O.RingGenerator(cfg, w, n, head_act="reference", dtype=np.float64).generate_greedy(window, steps)
+    # fp32 vs fp64 may flip an arg-max on a near tie (the stream then diverges): at most one stream
+    assert (a != want).any(axis=1).sum() <= 1, (a != want).any(axis=1)
+    b = run(window, [17, 30, 13], True)
+    assert np.array_equal(a, b)
+    c = run(window, [steps], False)                     # single-CTA kernel, same fp32 weights
+    assert (a != c).any(axis=1).sum() <= 1
+    lo, hi = 3, min(n, 19)                              # a shard that straddles the first cluster boundary when n > 16
+    d = run(window[lo:hi], [steps], True)
+    assert np.array_equal(d, a[lo:hi])
+
+
 def test_device_crop_batch_matches_reference_create_batch():
     """train_audio/train.py:14-22 restated vs wn_crop_batch with the same np.random stream."""
     rng = np.random.default_rng(0)

@@ -65,7 +65,8 @@ struct wn_gen {
   std::vector<GenChunk> chunks3;      // schedule over the packed weights
   struct Pack3 { int64_t src, dst; int K, N, chunkK, mode; };
   std::vector<Pack3> packs3;
-  bool v4_ok = false;                 // config-C shape and few enough streams: one 8-CTA cluster per stream
+  bool v4_ok = false;                 // config-C shape: the cluster generators' packed weight slices exist (v4: one 8-CTA
+                                      // cluster per stream while they are all co-resident; v5: 16 streams per cluster)
 };
 
 namespace {
@@ -1404,6 +1405,437 @@ __global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_k
   cluster_sync_all();   // nobody leaves while a peer may still store into its shared memory
 }
 
+// ------------------------------------------------------------------------------------------
+// gen_kernel_v5: MANY streams on the cluster layout of v4 -- one 8-CTA cluster per V5_NS = 16 streams.
+// v3 gives every CTA whole streams, so every SM pulls all 5 MB of weights through its shared memory each step (128 CTAs x
+// 5 MB = 7.9 TB/s of L2 -> SMEM traffic at 256 streams, 82 us per step).  Here the eight CTAs of a cluster split every
+// matrix by output rows exactly like v4 (same packed slices, 1 MB per CTA and step), keep each thread's weights in
+// REGISTERS and sweep them over the cluster's 16 streams.  Differences from v4:
+//  * exchanged activations are CHANNEL-major [channel][stream], so a CTA's slice of an exchange (its 8 gate channels or
+//    32 head outputs x 16 streams) is one contiguous block: it is staged in local shared memory and sent with ONE
+//    cp.async.bulk per destination CTA (shared::cta -> shared::cluster, complete_tx on the destination's mbarrier) -- 8
+//    bulk copies per CTA and exchange.  (Per-value st.async as in v4 costs ~9 cycles per 4-byte message: 47 k messages
+//    per step and CTA made the first version of this kernel 222 us per step.)
+//  * phase A: a thread accumulates its K slice for all 16 streams, then a TRANSPOSING butterfly (15 shuffles instead of
+//    16 x 4) leaves lane j of each half-warp with the complete sum of stream j -> ONE tanhf per lane serves 16 streams;
+//  * the x(t-d) taps are prefetched three layers ahead into a 4-layer shared-memory ring (the all-layer table of v4 would
+//    need 123 KB for 16 streams);
+//  * sampling is warp-parallel over streams (warp w finishes the arg-max of streams 2w, 2w+1).
+constexpr int V5_NS = 16;
+constexpr int V5_XP = 4;                   // layers of x(t-d) taps resident in shared memory
+
+__device__ __forceinline__ void bulk_copy_to_cta(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(V4_CS, 1, 1) __launch_bounds__(V4_T + 32) gen_kernel_v5(GenArgs a) {
+  extern __shared__ float sm[];
+  const GenLayout& L = a.lay;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rank = (int)cluster_rank();
+  const int stream0 = (blockIdx.x / V4_CS) * V5_NS;
+  const int ns = min(V5_NS, L.n - stream0);          // live streams of this cluster (the same in its eight CTAs); dead ones
+                                                     // compute on mirrored inputs and are never stored
+  constexpr int R = 64, G = 64, Q = 256, NS = V5_NS;
+  float* xv = sm;                            // [NS][64]      layer input of every stream (local)
+  float* zv = xv + NS * 64;                  // [2][64][NS]   gate outputs, channel-major, double-buffered by layer parity
+  float* hA = zv + 2 * 64 * NS;              // [256][NS]     head activations / logits, channel-major
+  float* hB = hA + 256 * NS;                 // [256][NS]
+  float* xpast = hB + 256 * NS;              // [V5_XP][NS][64]
+  float* stg = xpast + V5_XP * NS * 64;      // [2][32][NS]   this CTA's slice of an exchange (source of the bulk copies)
+  float* hbias = stg + 2 * 32 * NS;          // [n_head][256]
+  uint8_t* ring_g = reinterpret_cast<uint8_t*>(hbias + L.n_head * 256);
+  ring_g += (128 - (tc::smem_u32(ring_g) & 127)) & 127;
+  __shared__ __align__(8) uint64_t s_bars[2 * V4_STAGES + 4];
+  __shared__ GenLayerOff s_layers[128];
+  __shared__ float s_redv[NS][V4_T / 32];
+  __shared__ int s_redi[NS][V4_T / 32];
+  __shared__ int s_sample[NS], s_prev[NS];
+  __shared__ int s_pos[128];
+  const uint32_t full0 = tc::smem_u32(&s_bars[0]), empty0 = tc::smem_u32(&s_bars[V4_STAGES]);
+  const uint32_t zbar0 = tc::smem_u32(&s_bars[2 * V4_STAGES]), zbar1 = zbar0 + 8, hbar0 = zbar0 + 16, hbar1 = zbar0 + 24;
+  const uint32_t zv_s = tc::smem_u32(zv), hA_s = tc::smem_u32(hA), hB_s = tc::smem_u32(hB), stg_s = tc::smem_u32(stg);
+  float* st = a.state;
+  if (tid == 0) {
+    for (int i = 0; i < V4_STAGES; ++i) {
+      tc::mbar_init(full0 + 8 * i, 1);
+      tc::mbar_init(empty0 + 8 * i, V4_T / 32);
+    }
+    tc::mbar_init(zbar0, 1);
+    tc::mbar_init(zbar1, 1);
+    tc::mbar_init(hbar0, 1);
+    tc::mbar_init(hbar1, 1);
+    tc::fence_barrier_init();
+  }
+  for (int i = tid; i < L.L; i += blockDim.x) {
+    s_layers[i] = a.layers[i];
+    s_pos[i] = (int)(a.t0 % a.layers[i].ring_len);
+  }
+  for (int i = tid; i < L.n_head * 256; i += blockDim.x) hbias[i] = L.has_hb ? st[L.hb[i / 256] + (i % 256)] : 0.f;
+  float* cur_logits = st + L.cur_logits;
+  for (int i = tid; i < NS * Q; i += blockDim.x) {
+    const int q = i % Q, s = i / Q;
+    hA[q * NS + s] = cur_logits[(int64_t)(stream0 + min(s, ns - 1)) * Q + q];
+  }
+  int32_t* idx_hist = (int32_t*)(st + L.idx_hist);
+  const int kc1 = L.kc - 1;
+  if (tid < NS) s_prev[tid] = kc1 > 0 ? idx_hist[(int64_t)(stream0 + min(tid, ns - 1)) * kc1 + kc1 - 1] : -1;
+  __syncthreads();
+  cluster_sync_all();
+  const int n_chunks = L.L + L.n_head;
+  if (tid >= V4_T) {
+    if (tid == V4_T) {                       // producer: identical to v4 (this rank's packed slices, every step)
+      const uint8_t* wbase = reinterpret_cast<const uint8_t*>(st + L.wpk4 + (int64_t)rank * L.wpk4_rank);
+      const uint32_t ring_s = tc::smem_u32(ring_g);
+      uint32_t it = 0;
+      for (int step = 0; step < a.n_steps; ++step) {
+        uint64_t off = 0;
+        for (int c = 0; c < n_chunks; ++c, ++it) {
+          const uint32_t bytes = (c < L.L ? (V4_WA_F + V4_WB_F) : V4_WH_F) * 4;
+          const uint32_t stage = it % V4_STAGES;
+          tc::mbar_wait(empty0 + 8 * stage, ((it / V4_STAGES) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(full0 + 8 * stage, bytes);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           ring_s + stage * V4_STAGE_BYTES),
+                       "l"(reinterpret_cast<uint64_t>(wbase + off)), "r"(bytes), "r"(full0 + 8 * stage)
+                       : "memory");
+          off += bytes;
+        }
+      }
+    }
+    __syncwarp();
+    cluster_sync_all();
+    return;
+  }
+  float* lg = hA;
+  uint32_t it = 0, zph[2] = {0, 0}, hph[2] = {0, 0}, zsel = 0, xsel = 0;
+  // phase A roles: warp w -> gate channel 8*rank + w; lanes 0..15 a_f, 16..31 a_g; K slice = lane & 15 (8 rows); after the
+  //                transposing reduction lane j of each half owns stream j
+  // phase B roles: thread t < 192 -> output t >> 1 (0..63 residual channel -- every CTA computes all --, 64..95 skip channel
+  //                32*rank + o - 64), K half t & 1
+  // head roles   : output tid >> 3 (32*rank + o), K slice tid & 7 (32 rows); after the reduction lane ks owns streams 2ks, 2ks+1
+  const int ksA = lane & 15, jA = lane & 15;
+  const int oB = tid >> 1, ksB = tid & 1;
+  const int oH = tid >> 3, ksH = tid & 7;
+  const int ps = tid >> 4, pv = tid & 15;    // x(t-d) prefetch: stream ps, float4 pv of the 64 channels
+  const int psc = min(ps, ns - 1);
+  auto past_ptr = [&](int l) {
+    const GenLayerOff& ly = s_layers[l];
+    return reinterpret_cast<const float4*>(st + ly.ring + ((int64_t)(stream0 + psc) * ly.ring_len + s_pos[l]) * R) + pv;
+  };
+  // this CTA's staged slice (rows x NS floats) -> the same rows of `dst_local` in every CTA of the cluster; one thread per
+  // destination.  The staging buffer alternates between consecutive exchanges: a copy out of it has landed everywhere before
+  // the exchange after next can start (peers send exchange e+1 only after they received all of e).
+  auto send_slice = [&](uint32_t dst_local, int rows, uint32_t bar_local) {
+    tc::fence_proxy_async();                 // staged values (generic stores) -> visible to the bulk-copy engine
+    csync4();
+    if (tid < V4_CS)
+      bulk_copy_to_cta(map_to_cta(dst_local, (uint32_t)tid), stg_s + xsel * (32 * NS * 4), (uint32_t)(rows * NS * 4),
+                       map_to_cta(bar_local, (uint32_t)tid));
+    xsel ^= 1;
+  };
+
+  for (int step = 0; step < a.n_steps; ++step) {
+    const int64_t t = a.t0 + step;
+    TRG(41, 0);
+    // ---- 1. sample: thread q holds logit q of every stream; warp-level arg-max per stream, then warp w finishes streams 2w
+    //         and 2w+1 (every CTA of the cluster computes the same values) ----
+    if (!a.sample_first) {
+      if (tid < NS) s_sample[tid] = a.forced[stream0 + min(tid, ns - 1)];
+    } else {
+      float lv[NS];
+#pragma unroll
+      for (int g4 = 0; g4 < NS / 4; ++g4) {
+        const float4 v = *reinterpret_cast<const float4*>(lg + tid * NS + g4 * 4);
+        lv[4 * g4] = v.x, lv[4 * g4 + 1] = v.y, lv[4 * g4 + 2] = v.z, lv[4 * g4 + 3] = v.w;
+      }
+#pragma unroll 4
+      for (int s = 0; s < NS; ++s) {
+        float bv = lv[s];
+        int bi = tid;
+        if (a.mode == WN_GEN_SAMPLE) bv += gumbel(a.seed, (uint64_t)(stream0 + s), (uint64_t)t, (uint32_t)tid);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) {
+            bv = ov;
+            bi = oi;
+          }
+        }
+        if (lane == 0) {
+          s_redv[s][warp] = bv;
+          s_redi[s][warp] = bi;
+        }
+      }
+      csync4();
+      if (lane < 2) {
+        const int s = 2 * warp + lane;
+        float bv = s_redv[s][0];
+        int bi = s_redi[s][0];
+        for (int w = 1; w < V4_T / 32; ++w)
+          if (s_redv[s][w] > bv || (s_redv[s][w] == bv && s_redi[s][w] < bi)) {
+            bv = s_redv[s][w];
+            bi = s_redi[s][w];
+          }
+        s_sample[s] = bi;
+        if (a.out && rank == 0 && s < ns) a.out[(int64_t)(stream0 + s) * a.n_steps + step] = bi;
+      }
+    }
+    // ---- 2. x(t-d) taps of the first three layers (written at least one step ago) ----
+    {
+      const float4 p0 = __ldcg(past_ptr(0));
+      const float4 p1 = L.L > 1 ? __ldcg(past_ptr(1)) : p0;
+      const float4 p2 = L.L > 2 ? __ldcg(past_ptr(2)) : p0;
+      *reinterpret_cast<float4*>(xpast + (0 * NS + ps) * 64 + pv * 4) = p0;
+      *reinterpret_cast<float4*>(xpast + (1 * NS + ps) * 64 + pv * 4) = p1;
+      *reinterpret_cast<float4*>(xpast + (2 * NS + ps) * 64 + pv * 4) = p2;
+    }
+    csync4();                                // s_sample visible
+    {
+      const float* emb = st + L.emb;
+      const int c = tid & 63;
+      const float bias = L.has_cb ? st[L.emb_b + c] : 0.f;
+      for (int s = tid >> 6; s < NS; s += 4) {
+        const int q_new = s_sample[s], q_old = s_prev[s];
+        float v = bias;
+        if (kc1 > 0 && q_old >= 0) v += emb[((int64_t)0 * Q + q_old) * R + c];
+        v += emb[((int64_t)kc1 * Q + q_new) * R + c];
+        xv[s * 64 + c] = v;
+      }
+    }
+    csync4();
+    if (tid < NS) s_prev[tid] = s_sample[tid];
+    // ---- 3. residual layers ----
+    TRG(41, 1);
+    float skr[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) skr[s] = 0.f;
+    for (int l = 0; l < L.L; ++l, ++it) {
+      const GenLayerOff& ly = s_layers[l];
+      const bool has_ba = ly.has_ba != 0, has_bb = ly.has_bb != 0;
+      const int64_t ba_off = ly.ba, bb_off = ly.bb;
+      const uint32_t stage = it % V4_STAGES;
+      // prefetch the taps of layer l + 3 (its ring slot is overwritten only when that layer runs)
+      const bool pf = l + 3 < L.L;
+      float4 pnext = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pf) pnext = __ldcg(past_ptr(l + 3));
+      // this CTA's slice of x[t] for the ring (8 channels x 16 streams), read before phase B updates xv
+      const int rs = tid >> 3, rc = tid & 7;
+      const float xring = tid < 8 * NS ? xv[rs * 64 + 8 * rank + rc] : 0.f;
+      const int64_t ring_slot = ly.ring + ((int64_t)(stream0 + min(rs, ns - 1)) * ly.ring_len + s_pos[l]) * R;
+      TRG(l, 0);
+      tc::mbar_wait(full0 + 8 * stage, (it / V4_STAGES) & 1);
+      TRG(l, 1);
+      const float4* wst = reinterpret_cast<const float4*>(ring_g + stage * V4_STAGE_BYTES);
+      const uint32_t zb = zsel ? zbar1 : zbar0;
+      {
+        const float4 w0 = wst[tid], w1 = wst[256 + tid];
+        const float* xin = ksA < 8 ? xpast + ((l & (V5_XP - 1)) * NS) * 64 + ksA * 8 : xv + (ksA - 8) * 8;
+        float v[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const float4 x0 = *reinterpret_cast<const float4*>(xin + s * 64), x1 = *reinterpret_cast<const float4*>(xin + s * 64 + 4);
+          float acc = w0.x * x0.x, acc1 = w1.x * x1.x;
+          acc = fmaf(w0.y, x0.y, acc), acc = fmaf(w0.z, x0.z, acc), acc = fmaf(w0.w, x0.w, acc);
+          acc1 = fmaf(w1.y, x1.y, acc1), acc1 = fmaf(w1.z, x1.z, acc1), acc1 = fmaf(w1.w, x1.w, acc1);
+          v[s] = acc + acc1;
+        }
+        // transposing butterfly over the 16 lanes of a half-warp: every step halves the live values; lane j ends with the
+        // sum of stream j
+#pragma unroll
+        for (int w = 8; w >= 1; w >>= 1) {
+          const bool upper = (lane & w) != 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (i < w) {
+              const float send = upper ? v[i] : v[i + w];
+              const float keep = upper ? v[i + w] : v[i];
+              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+            }
+          }
+        }
+        const int ch = 8 * rank + warp;
+        float g = lane < 16 ? v[0] : 0.5f * v[0];
+        if (has_ba) g += lane < 16 ? st[ba_off + ch] : 0.5f * st[ba_off + G + ch];
+        const float th = tanhf(g);
+        const float zval = th * (0.5f + 0.5f * __shfl_down_sync(0xffffffffu, th, 16));   // lanes 0..15: stream jA
+        if (lane < 16) stg[(xsel * 32 + warp) * NS + jA] = zval;
+      }
+      TRG(l, 6);
+      send_slice(zv_s + 4u * (uint32_t)((zsel * 64 + 8 * rank) * NS), 8, zb);
+      TRG(l, 2);
+      exchange_wait(zb, zph[zsel], (uint32_t)(64 * NS * 4), tid);
+      TRG(l, 3);
+      zph[zsel] ^= 1;
+      if (tid < 192) {
+        const float4* wb = wst + V4_WA_F / 4;
+        const float* zk = zv + (zsel * 64 + ksB * 32) * NS;
+        float acc[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) acc[s] = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 w = wb[q * 192 + tid];
+          const float wk[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int g4 = 0; g4 < NS / 4; ++g4) {
+              const float4 z = *reinterpret_cast<const float4*>(zk + (q * 4 + c) * NS + g4 * 4);
+              acc[4 * g4] = fmaf(wk[c], z.x, acc[4 * g4]), acc[4 * g4 + 1] = fmaf(wk[c], z.y, acc[4 * g4 + 1]);
+              acc[4 * g4 + 2] = fmaf(wk[c], z.z, acc[4 * g4 + 2]), acc[4 * g4 + 3] = fmaf(wk[c], z.w, acc[4 * g4 + 3]);
+            }
+          }
+        }
+        const float bb = has_bb ? st[bb_off + (oB < 64 ? oB : R + 32 * rank + oB - 64)] : 0.f;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], 1) + bb;
+        if (oB < 64) {
+          if (ksB == 0) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) xv[s * 64 + oB] += acc[s];      // output = projection + x, wavenet.py:354
+          }
+        } else {
+#pragma unroll
+          for (int s = 0; s < NS; ++s) skr[s] += acc[s];                 // faster_wavenet.py:100 (both lanes of the pair hold it)
+        }
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(empty0 + 8 * stage);
+      // ring roll (faster_wavenet.py:90-91): the slot is the one read as x[t-d] >= 3 layers ago by every CTA
+      if (tid < 8 * NS && rs < ns) st[ring_slot + 8 * rank + rc] = xring;
+      if (pf) *reinterpret_cast<float4*>(xpast + (((l + 3) & (V5_XP - 1)) * NS + ps) * 64 + pv * 4) = pnext;
+      TRG(l, 4);
+      csync4();
+      TRG(l, 5);
+      zsel ^= 1;
+    }
+    // ---- 4. head ----
+    TRG(40, 0);
+    int hsel = 0;
+    if (tid >= 128 && tid < 192) {           // skip sums: lane ksB of a pair stages streams 8 ksB .. 8 ksB + 7
+      float* row = stg + (xsel * 32 + oB - 64) * NS + ksB * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float v0 = ksB ? skr[8 + i] : skr[i];
+        row[i] = head_act(v0, a.head_elu);
+      }
+    }
+    send_slice(hB_s + 4u * (uint32_t)(32 * rank * NS), 32, hbar0);
+    exchange_wait(hbar0, hph[0], (uint32_t)(256 * NS * 4), tid);
+    hph[0] ^= 1;
+    hsel = 1;
+    float* hin = hB;
+    float* hout = hA;
+    uint32_t hout_s = hA_s, hin_s = hB_s;
+    for (int hi = 0; hi < L.n_head; ++hi, ++it) {
+      const uint32_t stage = it % V4_STAGES;
+      tc::mbar_wait(full0 + 8 * stage, (it / V4_STAGES) & 1);
+      const float4* wst = reinterpret_cast<const float4*>(ring_g + stage * V4_STAGE_BYTES);
+      const bool last = hi == L.n_head - 1;
+      const float hb = hbias[hi * 256 + 32 * rank + oH];
+      const uint32_t hbar = hsel ? hbar1 : hbar0;
+      const float* xk = hin + (ksH * 32) * NS;
+      float v[NS];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) v[s] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 w = wst[q * 256 + tid];
+        const float wk[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int g4 = 0; g4 < NS / 4; ++g4) {
+            const float4 x = *reinterpret_cast<const float4*>(xk + (q * 4 + c) * NS + g4 * 4);
+            v[4 * g4] = fmaf(wk[c], x.x, v[4 * g4]), v[4 * g4 + 1] = fmaf(wk[c], x.y, v[4 * g4 + 1]);
+            v[4 * g4 + 2] = fmaf(wk[c], x.z, v[4 * g4 + 2]), v[4 * g4 + 3] = fmaf(wk[c], x.w, v[4 * g4 + 3]);
+          }
+        }
+      }
+      // transposing butterfly over the 8 K-slice lanes: 16 -> 8 -> 4 -> 2 live values; lane ks ends with streams 2ks, 2ks+1
+#pragma unroll
+      for (int w = 4, half = 8; w >= 1; w >>= 1, half >>= 1) {
+        const bool upper = (lane & w) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i < half) {
+            const float send = upper ? v[i] : v[i + half];
+            const float keep = upper ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+          }
+        }
+      }
+      float o0 = v[0] + hb, o1 = v[1] + hb;
+      if (!last) o0 = head_act(o0, a.head_elu), o1 = head_act(o1, a.head_elu);
+      *reinterpret_cast<float2*>(stg + (xsel * 32 + oH) * NS + 2 * ksH) = make_float2(o0, o1);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(empty0 + 8 * stage);
+      send_slice(hout_s + 4u * (uint32_t)(32 * rank * NS), 32, hbar);
+      exchange_wait(hbar, hph[hsel], (uint32_t)(256 * NS * 4), tid);
+      hph[hsel] ^= 1;
+      hsel ^= 1;
+      float* tmp = hin;
+      hin = hout;
+      hout = tmp;
+      const uint32_t ts = hin_s;
+      hin_s = hout_s;
+      hout_s = ts;
+    }
+    lg = hin;
+    if (tid < L.L) {
+      const int p = s_pos[tid] + 1;
+      s_pos[tid] = p == s_layers[tid].ring_len ? 0 : p;
+    }
+    csync4();                                // s_pos settled before the next step's tap addresses
+    TRG(40, 1);
+  }
+  // ---- epilogue (rank 0 publishes the streams' state) ----
+  if (rank == 0) {
+    for (int i = tid; i < ns * Q; i += V4_T) {
+      const int q = i % Q, s = i / Q;
+      cur_logits[(int64_t)(stream0 + s) * Q + q] = lg[q * NS + s];
+    }
+    if (kc1 > 0 && tid < ns) idx_hist[(int64_t)(stream0 + tid) * kc1 + kc1 - 1] = s_prev[tid];
+    if (a.probs) {
+      for (int s = 0; s < ns; ++s) {
+        float* pr = a.probs + (int64_t)(stream0 + s) * Q;
+        const float mine = lg[tid * NS + s];
+        if (!a.apply_softmax) {
+          pr[tid] = mine;
+        } else {
+          float m = mine;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          if (lane == 0) s_redv[0][warp] = m;
+          csync4();
+          m = s_redv[0][0];
+          for (int w = 1; w < V4_T / 32; ++w) m = fmaxf(m, s_redv[0][w]);
+          csync4();
+          float sum = expf(mine - m);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          if (lane == 0) s_redv[0][warp] = sum;
+          csync4();
+          sum = 0.f;
+          for (int w = 0; w < V4_T / 32; ++w) sum += s_redv[0][w];
+          pr[tid] = expf(mine - m) / sum;
+          csync4();
+        }
+      }
+    }
+  }
+  cluster_sync_all();
+}
+
+size_t gen_smem_bytes_v5(const GenLayout& L) {
+  const size_t f = (size_t)V5_NS * (64 + 128 + 256 + 256 + V5_XP * 64 + 64) + (size_t)L.n_head * 256 + 64;
+  return f * sizeof(float) + V4_STAGES * V4_STAGE_BYTES + 128;
+}
+
 // dst[rank][...] <- src [K][N] (generator layout), cut into the per-rank, per-thread order gen_kernel_v4 reads:
 // mode 1: WA (K = 128, N = 128 = a_f | a_g), mode 2: WB (K = 64, N = 320 = residual (all ranks) | skip), mode 3: head.
 __global__ void gen_pack_v4(const float* __restrict__ src, float* __restrict__ dst, int64_t rank_stride, int K, int N,
@@ -1482,6 +1914,50 @@ int launch_gen_v4(const GenArgs& a, cudaStream_t s) {
   return WN_OK;
 }
 
+// co-resident 8-CTA clusters of gen_kernel_v5 (16 streams each)
+int gen_v5_max_clusters(const GenLayout& L) {
+  static int cached = -1;
+  static size_t cached_smem = 0;
+  const size_t smem = gen_smem_bytes_v5(L);
+  if (cached >= 0 && cached_smem == smem) return cached;
+  cached_smem = smem;
+  if (smem > 227 * 1024 ||
+      cudaFuncSetAttribute(gen_kernel_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return cached = 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(V4_CS * 32);
+  cfg.blockDim = dim3(V4_T + 32);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = V4_CS;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, gen_kernel_v5, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  return cached = n;
+}
+
+int launch_gen_v5(const GenArgs& a, cudaStream_t s) {
+  const size_t smem = gen_smem_bytes_v5(a.lay);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    WN_CHECK_CUDA(cudaFuncSetAttribute(gen_kernel_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  const int clusters = (a.lay.n + V5_NS - 1) / V5_NS;
+  gen_kernel_v5<<<clusters * V4_CS, V4_T + 32, smem, s>>>(a);
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
 size_t gen_smem_bytes(const GenLayout& L, int NS, bool stream) {
   const size_t maxw = L.maxw;
   size_t f = NS * maxw                               // xv
@@ -1517,6 +1993,13 @@ int run_gen(wn_gen* g, GenArgs& a, cudaStream_t s) {
   if (g->v4_ok && g->lay.n <= gen_v4_max_streams(g->lay)) {
     const char* e = getenv("WN_GEN_V4");
     if (!e || atoi(e) != 0) return launch_gen_v4(a, s);
+  }
+  // gen_kernel_v5 (16 streams per cluster) is OPT-IN: it is correct (tests) but measured 164 us per step against 59 us for
+  // one stream per CTA -- with FP32 SIMT math every FMA needs a shared-memory operand and 16 streams per cluster put ~4 k
+  // shared-memory wavefronts on each layer; kept as the measured record of that design.
+  if (g->v4_ok && g->lay.n >= 2 && (g->lay.n + V5_NS - 1) / V5_NS <= gen_v5_max_clusters(g->lay)) {
+    const char* e = getenv("WN_GEN_V5");
+    if (e && atoi(e) != 0) return launch_gen_v5(a, s);
   }
   if (g->v3_ok) {
     int ns3 = ns;
@@ -1664,7 +2147,7 @@ extern "C" int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen**
     L.chunks3_dev = take((int64_t)(sizeof(GenChunk) * g->chunks3.size() + 3) / 4 + 4);
   }
   // v4 (one 8-CTA cluster per stream): the v3 shape with 64 residual channels and 256-wide head inputs, few streams
-  g->v4_ok = g->v3_ok && L.R == 64 && L.k == 2 && L.kc <= 2 && n_streams * V4_CS_HOST <= h->sm_count;
+  g->v4_ok = g->v3_ok && L.R == 64 && L.k == 2 && L.kc <= 2;
   for (int i = 0; i < L.n_head && g->v4_ok; ++i) g->v4_ok = L.head_ch[i] == 256;
   for (int l = 0; l < L.L && g->v4_ok; ++l) g->v4_ok = g->layers[l].ring_len > 0;
   if (g->v4_ok) {

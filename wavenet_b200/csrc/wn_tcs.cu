@@ -1530,7 +1530,8 @@ tcs_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_dout, const __grid_co
         ld256(a.dzs + orow * 64 + half * 32 + i * 16, d8[i]);
         ld256(a.sg + orow * 64 + half * 32 + i * 16, s8[i]);
       }
-      mbar_wait(full(s), ph);               // z tile visible to this thread's generic loads
+      if (lane == 0) mbar_wait(full(s), ph);   // z tile (written by TMA) visible to this warp's generic loads: one lane
+      __syncwarp();                            // observes the barrier, bar.warp.sync orders the others behind it
       mbar_wait(acc_full(s), ph);
       tcgen05_fence_after();
       uint32_t v[32];
