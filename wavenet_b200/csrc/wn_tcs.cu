@@ -355,19 +355,32 @@ __global__ void tcs_relu_split_rows_kernel(__half* a, int C, int rows_per_seq_in
   store_split4(a, r, C, cc * 4, v);
 }
 
-// column sums of a split tensor (bias gradients): out[c] += scale * sum_rows a[row][c]
+// column sums of a split / single-plane tensor (bias gradients): out[c] += scale * sum_rows a[row][c].  A thread owns two
+// adjacent columns (one half2 per plane and row: a warp reads 128 contiguous bytes), the 8 row-slots of a block stride
+// through the rows; grid.y blocks split the rows.
 __global__ void tcs_colsum_kernel(const __half* __restrict__ a, int planes, int64_t rows, int C, float scale, float* __restrict__ out) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  __shared__ float red[8][33];
-  float s = 0.f;
-  if (c < C)
-    for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < rows; r += (int64_t)gridDim.y * 8)
-      s += __half2float(a[r * planes * C + c]) + (planes == 2 ? __half2float(a[r * 2 * C + C + c]) : 0.f);
-  red[threadIdx.y][threadIdx.x] = s;
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 2;
+  __shared__ float red[8][66];
+  float s0 = 0.f, s1 = 0.f;
+  if (c < C) {
+    const int64_t ld = (int64_t)planes * C;
+#pragma unroll 4
+    for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < rows; r += (int64_t)gridDim.y * 8) {
+      float2 v = __half22float2(*reinterpret_cast<const __half2*>(a + r * ld + c));
+      if (planes == 2) {
+        const float2 l = __half22float2(*reinterpret_cast<const __half2*>(a + r * ld + C + c));
+        v.x += l.x, v.y += l.y;
+      }
+      s0 += v.x, s1 += v.y;
+    }
+  }
+  red[threadIdx.y][2 * threadIdx.x] = s0;
+  red[threadIdx.y][2 * threadIdx.x + 1] = s1;
   __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
-    for (int i = 1; i < 8; ++i) s += red[i][threadIdx.x];
-    atomicAdd(out + c, s * scale);
+  if (threadIdx.y < 2 && c < C) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i][2 * threadIdx.x + threadIdx.y];
+    atomicAdd(out + c + threadIdx.y, s * scale);
   }
 }
 
@@ -2382,7 +2395,8 @@ int tcs_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s
       if (i == nh - 1 && h->ce_colsum_valid) {
         WN_TRY(simt_add_vec(ws + t.ce_colsum, grads + cp.b_off, cp.out_ch, s));   // unscaled column sums from the CE kernel
       } else {
-        dim3 grid(nblk(cp.out_ch, 32), 64), block(32, 8);
+        WN_REQUIRE(cp.out_ch % 2 == 0, WN_EINVAL, "tcs_colsum: odd channel count");
+        dim3 grid(nblk(cp.out_ch, 64), 4 * h->sm_count / (int)nblk(cp.out_ch, 64) + 1), block(32, 8);
         tcs_colsum_kernel<<<grid, block, 0, s>>>(d, dpl, (int64_t)B * T, cp.out_ch, inv, grads + cp.b_off);
         WN_CHECK_LAUNCH();
       }
