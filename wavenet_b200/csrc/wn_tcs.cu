@@ -177,7 +177,8 @@ struct SGemmArgs {
   int gate_zp, gate_sg_ld;
   int zero_rows_below;
   int reverse;
-  int flush;               // MODE 4: accumulate K blocks in registers (forward GEMMs; no mask / y_slab / colsum)
+  int flush;               // MODE 4 (forward GEMMs; no mask / y_slab / colsum): > 0 = K blocks per flush group -- every group
+                           // accumulates from zero in TMEM and is ADDED TO REGISTERS by the epilogue (fp32, round to nearest)
   float* colsum_out;       // MODE 5: += colsum_scale * column sums of the stored result
   float colsum_scale;
   // MODE 6 (last head conv fused with softmax cross-entropy; N == 256): Y (optional) receives the fp32 logits
@@ -908,19 +909,22 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       constexpr uint32_t idesc = idesc_f16(128, BN);
       int it = 0;
       if constexpr (MODE == 4) {
-        int c = 0;   // K blocks issued so far: block c accumulates (from zero) into TMEM buffer c & 1
+        // flush group c (a.flush consecutive K blocks) accumulates from zero into TMEM buffer c & 1
+        const int fl = a.flush;
+        int c = 0;
         for (int j = 0; j < n_local; ++j)
-          for (int kb = 0; kb < kblocks; ++kb, it += 2, ++c) {
+          for (int kb = 0; kb < kblocks; ++kb, it += 2) {
             const int ab = c & 1, aph = (c >> 1) & 1;
             const int s0 = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
             const uint32_t sh = base + s0 * Cfg::STAGE, sl = sh + Cfg::STAGE;
-            mbar_wait(acc_empty(ab), aph ^ 1);
+            const bool first = kb % fl == 0, last = kb % fl == fl - 1;
+            if (first) mbar_wait(acc_empty(ab), aph ^ 1);
             mbar_wait(full(s0), ph);
             mbar_wait(full(s0 + 1), ph);
             tcgen05_fence_after();
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {   // cross terms while the accumulator is small, hi.hi last
-              umma_f16(tmem + ab * BN, umma_desc_k_sw128(sh + k4 * 32), umma_desc_k_sw128(sl + SUB + k4 * 32), idesc, k4 > 0);
+              umma_f16(tmem + ab * BN, umma_desc_k_sw128(sh + k4 * 32), umma_desc_k_sw128(sl + SUB + k4 * 32), idesc, !first || k4 > 0);
               umma_f16(tmem + ab * BN, umma_desc_k_sw128(sl + k4 * 32), umma_desc_k_sw128(sh + SUB + k4 * 32), idesc, 1u);
             }
 #pragma unroll
@@ -928,7 +932,10 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               umma_f16(tmem + ab * BN, umma_desc_k_sw128(sh + k4 * 32), umma_desc_k_sw128(sh + SUB + k4 * 32), idesc, 1u);
             umma_commit(empty(s0));
             umma_commit(empty(s0 + 1));
-            umma_commit(acc_full(ab));
+            if (last) {
+              umma_commit(acc_full(ab));
+              ++c;
+            }
           }
       }
       for (int j = 0; MODE != 4 && j < n_local; ++j) {
@@ -975,7 +982,7 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         for (int ch = 0; ch < CH; ++ch)
 #pragma unroll
           for (int i = 0; i < 32; ++i) acc[ch][i] = 0.f;
-        for (int kb = 0; kb < kblocks; ++kb, ++c) {
+        for (int kb = 0; kb < kblocks; kb += a.flush, ++c) {
           const int ab = c & 1, aph = (c >> 1) & 1;
           mbar_wait(acc_full(ab), aph);
           tcgen05_fence_after();
@@ -1623,10 +1630,16 @@ struct SDxwArgs {
   int reverse;
   float wscale;            // 1 / (gscale * ACT_SCALE)
 };
-constexpr int SD_STAGE = SUB + 2 * 8192;        // A [128 x 64], B hi, B lo [64 x 64]
+// Shared-memory bandwidth (128 B/clk: TMA writes + MMA operand reads) is what bounds this kernel, so (1) W1^T (64 KB) is
+// RESIDENT instead of travelling with every unit, (2) the hi and lo planes of a B operand are adjacent and consumed by ONE
+// MMA of twice the N (dafg . [W_hi | W_lo] -> two 64-column halves the epilogue adds; dafg^T . [x_hi | x_lo] -> N = 256), so
+// every A tile is read once per K step instead of twice: 352 KB of shared-memory traffic per tile instead of 512 KB.
+constexpr int SD_W = 0;                         // W1^T resident: unit (slab, gate half) -> [hi 64 c x 64 k | lo] 16 KB
+constexpr int SD_RING = 4 * 16384;
+constexpr int SD_STAGE = SUB;                   // A [128 x 64] of dafg
 constexpr int SD_STAGES = 4;
 static_assert(SD_STAGES == 4, "a tile's four units must land in fixed stages (unit u in stage u)");
-constexpr int SD_X = SD_STAGES * SD_STAGE;      // x(t-d) hi | x(t) hi | x(t-d) lo | x(t) lo
+constexpr int SD_X = SD_RING + SD_STAGES * SD_STAGE;   // x(t-d) hi | x(t) hi | x(t-d) lo | x(t) lo
 constexpr int SD_BAR = SD_X + 4 * SUB;
 constexpr int SD_SMEM = SD_BAR + 256;
 
@@ -1641,7 +1654,7 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
   auto empty = [&](int s) { return bar0 + 32 + 8 * s; };
   auto acc_full = [&](int s) { return bar0 + 64 + 8 * s; };
   auto acc_empty = [&](int s) { return bar0 + 80 + 8 * s; };
-  const uint32_t x_full = bar0 + 96, x_empty = bar0 + 104, wg_full = bar0 + 112;
+  const uint32_t x_full = bar0 + 96, x_empty = bar0 + 104, wg_full = bar0 + 112, w_full = bar0 + 120;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + SD_BAR + 128);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -1656,12 +1669,13 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
     mbar_init(x_full, 1);
     mbar_init(x_empty, 1);
     mbar_init(wg_full, 1);
+    mbar_init(w_full, 1);
     fence_barrier_init();
     prefetch_tmap(&tm_da);
     prefetch_tmap(&tm_w);
     prefetch_tmap(&tm_x);
   }
-  if (warp == 1) tmem_alloc<256>(smem_u32((const void*)tmem_slot));
+  if (warp == 1) tmem_alloc<512>(smem_u32((const void*)tmem_slot));
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -1675,6 +1689,12 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
+      mbar_arrive_expect_tx(w_full, 4 * 16384);
+      for (int u = 0; u < 4; ++u) {        // unit u = (slab u < 2 ? 1 : 0, gate half u & 1): W1^T[c][slab*128 + n], hi then lo
+        const int sl = u < 2 ? 1 : 0, ch = u & 1;
+        tma_load_2d(base + SD_W + u * 16384, &tm_w, w_full, sl * 128 + ch * KB, 0);
+        tma_load_2d(base + SD_W + u * 16384 + 8192, &tm_w, w_full, 256 + sl * 128 + ch * KB, 0);
+      }
       for (int j = 0; j < n_local; ++j) {
         const int tile = tile_of(j);
         const int b = tile / a.tiles_per_seq, t0 = (tile % a.tiles_per_seq) * TM;
@@ -1693,7 +1713,9 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
         }
         for (int u = 0; u < 4; ++u, ++it) {
           if (u == 2) {
+            TRS(j, 12);
             mbar_wait(x_empty, (j & 1) ^ 1);
+            TRS(j, 13);
             const uint32_t xs = base + SD_X;
             mbar_arrive_expect_tx(x_full, 4 * SUB);
             tma_load_4d(xs + 0 * SUB, &tm_x, x_full, 0, t0 - a.d, b, 0);
@@ -1704,51 +1726,50 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
           const int sl = u < 2 ? 1 : 0, ch = u & 1;
           const int s = it % SD_STAGES, ph = (it / SD_STAGES) & 1;
           mbar_wait(empty(s), ph ^ 1);
-          const uint32_t st = base + s * SD_STAGE;
+          TRS(j, u);                        // producer: stage free, load of unit u issued
+          const uint32_t st = base + SD_RING + s * SD_STAGE;
           mbar_arrive_expect_tx(full(s), SD_STAGE);
           tma_load_4d(st, &tm_da, full(s), ch * KB, t0 + sl * a.d, b, 0);                 // dafg, gate half ch
-          tma_load_2d(st + SUB, &tm_w, full(s), sl * 128 + ch * KB, 0);                   // W1^T[c][slab*128 + n] hi
-          tma_load_2d(st + SUB + 8192, &tm_w, full(s), 256 + sl * 128 + ch * KB, 0);      // lo
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && n_local > 0) {
-      constexpr uint32_t idesc = idesc_f16(128, 64);
-      constexpr uint32_t idesc_mn = idesc_f16(128, 128) | IDESC_MN_MAJOR;
+      constexpr uint32_t idesc = idesc_f16(128, 128);                      // N = [W_hi 64 | W_lo 64]
+      constexpr uint32_t idesc_mn = idesc_f16(128, 256) | IDESC_MN_MAJOR;   // N = [x(t-d) hi | x(t) hi | x(t-d) lo | x(t) lo]
       const uint32_t xs = base + SD_X;
+      mbar_wait(w_full, 0);
       int it = 0;
       for (int j = 0; j < n_local; ++j) {
         const int ab = j & 1, aph = (j >> 1) & 1;
         for (int u = 0; u < 4; ++u, ++it) {
           const int s = it % SD_STAGES, ph = (it / SD_STAGES) & 1;
           if (u == 0) mbar_wait(acc_empty(ab), aph ^ 1);
-          if (u == 2) mbar_wait(x_full, j & 1);
+          if (u == 2) {
+            TRS(j, 14);
+            mbar_wait(x_full, j & 1);
+            TRS(j, 15);
+          }
           mbar_wait(full(s), ph);
+          TRS(j, 4 + u);                    // MMA thread: unit u loaded
           tcgen05_fence_after();
-          const uint32_t st = base + s * SD_STAGE, wb = st + SUB;
+          const uint32_t st = base + SD_RING + s * SD_STAGE, wb = base + SD_W + u * 16384;
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)   // the small (lo-plane) terms first: the accumulator truncates toward zero
-            umma_f16(tmem + ab * 64, umma_desc_k_sw128(st + k4 * 32), umma_desc_k_sw128(wb + 8192 + k4 * 32), idesc, (u | k4) > 0);
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)
-            umma_f16(tmem + ab * 64, umma_desc_k_sw128(st + k4 * 32), umma_desc_k_sw128(wb + k4 * 32), idesc, 1u);
+          for (int k4 = 0; k4 < 4; ++k4)   // columns [0, 64): dafg . W_hi, [64, 128): dafg . W_lo (separate fp32 accumulators)
+            umma_f16(tmem + ab * 128, umma_desc_k_sw128(st + k4 * 32), umma_desc_k_sw128(wb + k4 * 32), idesc, (u | k4) > 0);
           if (u == 3) {
             // weight gradient of both gate halves: A atoms = the da_f tile (stage 2) and the da_g tile (this stage);
-            // accumulator lanes = (f | g) channel, columns [128, 256) = (tap, c)
+            // accumulator lanes = (f | g) channel, columns 256 + [plane 2][tap 2][c 64]
             const uint32_t sf = st - SD_STAGE;
 #pragma unroll
-            for (int k16 = 0; k16 < TM / 16; ++k16) {
-              const uint64_t ah = desc_mn_sw128(sf + k16 * 2048, SD_STAGE, 1024);
-              const uint64_t bh = desc_mn_sw128(xs + k16 * 2048, SUB, 1024);
-              const uint64_t bl = desc_mn_sw128(xs + 2 * SUB + k16 * 2048, SUB, 1024);
-              umma_f16(tmem + 128, ah, bl, idesc_mn, (j | k16) > 0);
-              umma_f16(tmem + 128, ah, bh, idesc_mn, 1u);
-            }
+            for (int k16 = 0; k16 < TM / 16; ++k16)
+              umma_f16(tmem + 256, desc_mn_sw128(sf + k16 * 2048, SD_STAGE, 1024), desc_mn_sw128(xs + k16 * 2048, SUB, 1024), idesc_mn,
+                       (j | k16) > 0);
             umma_commit(empty(s - 1));        // the da_f stage was held for the weight-gradient MMAs
             umma_commit(empty(s));
             umma_commit(x_empty);
             umma_commit(acc_full(ab));
+            TRS(j, 8);                      // MMA thread: whole tile issued
           } else if (u != 2) {
             umma_commit(empty(s));
           }
@@ -1777,12 +1798,16 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
         }
       }
       mbar_wait(acc_full(ab), aph);
+      if (threadIdx.x == 64) TRS(j, 9);     // epilogue: accumulator ready
       tcgen05_fence_after();
-      uint32_t v[32];
-      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * 64 + half * 32, v);
+      uint32_t v[32], vl[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * 128 + half * 32, v);
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * 128 + 64 + half * 32, vl);
       tmem_ld_wait();
       tcgen05_fence_before();
       warp_arrive(acc_empty(ab), lane);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(vl[i]));
       __half* yrow = a.Y + orow * 128 + half * 32;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -1798,6 +1823,7 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
           st256(yrow + 64 + c * 16, ol);
         }
       }
+      if (threadIdx.x == 64) TRS(j, 10);    // epilogue: tile stored
     }
     if (n_local > 0) {
       // dW_f / dW_g: TMEM lanes 0..63 = f gate channel o, lanes 64..127 = g gate channel o, columns tap*64 + c; the
@@ -1805,9 +1831,19 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
       mbar_wait(wg_full, 0);
       tcgen05_fence_after();
       uint32_t v0[32], v1[32];
-      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 128 + half * 32, v0);        // tap 0, channels half*32..
-      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 128 + 64 + half * 32, v1);   // tap 1
-      tmem_ld_wait();
+      {
+        uint32_t t0[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 256 + half * 32, v0);              // tap 0, x hi plane, channels half*32..
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 256 + 128 + half * 32, t0);        // tap 0, x lo plane
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v0[i] = __float_as_uint(__uint_as_float(v0[i]) + __uint_as_float(t0[i]));
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 256 + 64 + half * 32, v1);         // tap 1
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 256 + 192 + half * 32, t0);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v1[i] = __float_as_uint(__uint_as_float(v1[i]) + __uint_as_float(t0[i]));
+      }
       float* wrow = (q < 2 ? a.dWf : a.dWg) + (int64_t)(row & 63) * 128 + half * 64;
 #pragma unroll
       for (int i = 0; i < 16; ++i)
@@ -1817,7 +1853,7 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<256>(tmem);
+  if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1990,6 +2026,10 @@ int tcs_gemm(const wn_handle* h, const SOperand& A, int ns, const int* slab_idx,
   g.zero_rows_below = e.zero_rows_below;
   g.reverse = e.reverse;
   g.flush = e.flush && !e.gate_sg && !e.colsum_out;
+  // Two K blocks (128 channels) per flush group when the block count is even: reading a 128 x 256 fp32 accumulator out of
+  // TMEM takes 2048 cycles (64 B/clk) against 1536 cycles of MMAs per K block, so one flush per block made the tensor pipe
+  // wait for tcgen05.ld; the truncating accumulation over 128 instead of 64 channels costs < 1e-6 relative
+  if (g.flush && (ns * (A.C / KB)) % 2 == 0) g.flush = 2;
   WN_REQUIRE(A.planes == 2 || (!g.flush && !e.gate_sg && !e.ce_target), WN_EINVAL, "tcs_gemm: single-plane A is a backward operand");
   g.colsum_out = e.ngroups_ok_for_colsum(N, BN) ? e.colsum_out : nullptr;
   g.ce_target = e.ce_target;
