@@ -1432,8 +1432,7 @@ struct SGateBwdArgs {
 };
 constexpr int SG_W = 0;                         // Wp^T split: hi [64 g x 64 r] 8 KB, lo 8 KB
 constexpr int SG_ST = 16384;                    // 2 stages x {dout hi, dout lo, z hi, z lo}
-constexpr int SG_ZERO = SG_ST + 2 * 65536;      // 16 KB of zeros: M atom 1 of the dWp MMA (channels 64..127)
-constexpr int SG_BAR = SG_ZERO + SUB;
+constexpr int SG_BAR = SG_ST + 2 * 65536;
 constexpr int SG_SMEM = SG_BAR + 256;
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -1464,9 +1463,7 @@ tcs_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_dout, const __grid_co
     prefetch_tmap(&tm_z);
     prefetch_tmap(&tm_w);
   }
-  for (int i = threadIdx.x; i < SUB / 16; i += blockDim.x) reinterpret_cast<uint4*>(gbase + SG_ZERO)[i] = make_uint4(0u, 0u, 0u, 0u);
-  fence_proxy_async();
-  if (warp == 1) tmem_alloc<256>(smem_u32((const void*)tmem_slot));
+  if (warp == 1) tmem_alloc<512>(smem_u32((const void*)tmem_slot));
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -1497,8 +1494,13 @@ tcs_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_dout, const __grid_co
     }
   } else if (warp == 1) {
     if (lane == 0 && n_local > 0) {
-      constexpr uint32_t idesc = idesc_f16(128, 64);
-      constexpr uint32_t idesc_mn = idesc_f16(128, 64) | IDESC_MN_MAJOR;
+      // Adjacent hi | lo planes are consumed as ONE operand of twice the size (shared-memory operand reads, not the tensor
+      // pipe, are what these small-K MMAs cost): dz = dout_lo . [Wp_hi | Wp_lo] + dout_hi . [Wp_hi | Wp_lo] leaves the hi
+      // and lo products in two 64-column halves the epilogue adds; dWp = [dout_hi | dout_lo]^T . [z_hi | z_lo] puts all four
+      // plane products into one M = 128, N = 128 accumulator (lanes 0..63 dout_hi, 64..127 dout_lo) -- one MMA per K step
+      // where three half-empty ones (M atom 1 was a zero tile) ran before.
+      constexpr uint32_t idesc = idesc_f16(128, 128);
+      constexpr uint32_t idesc_mn = idesc_f16(128, 128) | IDESC_MN_MAJOR;
       mbar_wait(w_full, 0);
       for (int j = 0; j < n_local; ++j) {
         const int s = j & 1, ph = (j >> 1) & 1;
@@ -1507,26 +1509,18 @@ tcs_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_dout, const __grid_co
         tcgen05_fence_after();
         const uint32_t st = base + SG_ST + s * 65536, wb = base + SG_W;
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {   // cross terms first (round-toward-zero accumulation, see tcs_layer_kernel)
-          umma_f16(tmem + s * 64, umma_desc_k_sw128(st + k4 * 32), umma_desc_k_sw128(wb + 8192 + k4 * 32), idesc, k4 > 0);
-          umma_f16(tmem + s * 64, umma_desc_k_sw128(st + SUB + k4 * 32), umma_desc_k_sw128(wb + k4 * 32), idesc, 1u);
-        }
+        for (int k4 = 0; k4 < 4; ++k4)     // the small (dout_lo) products first: the accumulator truncates toward zero
+          umma_f16(tmem + s * 128, umma_desc_k_sw128(st + SUB + k4 * 32), umma_desc_k_sw128(wb + k4 * 32), idesc, k4 > 0);
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4)
-          umma_f16(tmem + s * 64, umma_desc_k_sw128(st + k4 * 32), umma_desc_k_sw128(wb + k4 * 32), idesc, 1u);
+          umma_f16(tmem + s * 128, umma_desc_k_sw128(st + k4 * 32), umma_desc_k_sw128(wb + k4 * 32), idesc, 1u);
         umma_commit(acc_full(s));
-        // dWp[r][g] += sum_pos dout[pos][r] * z[pos][g]: A = dout tile read MN-major (atom 1 = zeros), B = z tile MN-major
-        const uint32_t zero = base + SG_ZERO;
+        // dWp[r][g] += sum_pos dout[pos][r] * z[pos][g]: A = [dout_hi | dout_lo] tiles read MN-major (two M atoms), B = [z_hi |
+        // z_lo] tiles MN-major (two N atoms)
 #pragma unroll
-        for (int k16 = 0; k16 < TM / 16; ++k16) {
-          const uint64_t ah = desc_mn_sw128(st + k16 * 2048, zero - st, 1024);
-          const uint64_t al = desc_mn_sw128(st + SUB + k16 * 2048, zero - (st + SUB), 1024);
-          const uint64_t bh = desc_mn_sw128(st + 2 * SUB + k16 * 2048, SUB, 1024);
-          const uint64_t bl = desc_mn_sw128(st + 3 * SUB + k16 * 2048, SUB, 1024);
-          umma_f16(tmem + 128, ah, bl, idesc_mn, (j | k16) > 0);
-          umma_f16(tmem + 128, al, bh, idesc_mn, 1u);
-          umma_f16(tmem + 128, ah, bh, idesc_mn, 1u);
-        }
+        for (int k16 = 0; k16 < TM / 16; ++k16)
+          umma_f16(tmem + 256, desc_mn_sw128(st + k16 * 2048, SUB, 1024), desc_mn_sw128(st + 2 * SUB + k16 * 2048, SUB, 1024),
+                   idesc_mn, (j | k16) > 0);
         umma_commit(empty(s));
       }
       umma_commit(wg_full);
@@ -1555,10 +1549,16 @@ tcs_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_dout, const __grid_co
       mbar_wait(acc_full(s), ph);
       tcgen05_fence_after();
       uint32_t v[32];
-      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + s * 64 + half * 32, v);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      warp_arrive(acc_empty(s), lane);
+      {
+        uint32_t vl[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + s * 128 + half * 32, v);        // dout . Wp_hi
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + s * 128 + 64 + half * 32, vl);  // dout . Wp_lo
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        warp_arrive(acc_empty(s), lane);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(vl[i]));
+      }
       __half* drow = a.dafg + orow * 128 + half * 32;
       uint32_t fh[8], gh[8];
 #pragma unroll
@@ -1590,14 +1590,21 @@ tcs_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_dout, const __grid_co
       }
       warp_arrive(empty(s), lane);          // done reading z from the stage
     }
-    if (n_local > 0 && q < 2) {
-      // dWp rows (projection output channels r) live in TMEM lanes 0..63, columns = g
+    if (n_local > 0) {
+      // dWp rows (projection output channels r): TMEM lanes r (dout_hi products) and 64 + r (dout_lo products), columns g
+      // (z_hi) and 64 + g (z_lo); every lane quarter reduces its share into dWp
       mbar_wait(wg_full, 0);
       tcgen05_fence_after();
       uint32_t v[32];
-      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 128 + half * 32, v);
-      tmem_ld_wait();
-      float* wrow = a.dWp + (int64_t)row * 64 + half * 32;
+      {
+        uint32_t vl[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 256 + half * 32, v);
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 256 + 64 + half * 32, vl);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(vl[i]));
+      }
+      float* wrow = a.dWp + (int64_t)(row & 63) * 64 + half * 32;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         red_add_v4(wrow + 4 * i, make_float4(__uint_as_float(v[4 * i]) * a.wscale, __uint_as_float(v[4 * i + 1]) * a.wscale,
@@ -1606,7 +1613,7 @@ tcs_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_dout, const __grid_co
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<256>(tmem);
+  if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------
