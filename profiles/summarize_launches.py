@@ -1,6 +1,6 @@
 """Per-kernel table from an ncu launch list (`ncu --metrics gpu__time_duration.sum[,dram__bytes_read.sum,dram__bytes_write.sum]
 --clock-control none --csv`).  usage: python profiles/summarize_launches.py launches.csv [first_launch] [n_launches]
-(default: the last half of the launches = the second of two captured steps)"""
+(default: the last captured train step)"""
 import collections
 import csv
 import sys
@@ -24,7 +24,9 @@ def main():
     if len(sys.argv) > 3:
         data = data[int(sys.argv[2]):int(sys.argv[2]) + int(sys.argv[3])]
     else:
-        data = data[len(data) // 2:]
+        # default: the LAST train step = from the last weight-preparation launch (tcs_prep_kernel / tc_prep_kernel) on
+        prep = [i for i, d in enumerate(data) if "prep_kernel" in d["name"] and "embed" not in d["name"]]
+        data = data[prep[-1]:] if prep else data[len(data) // 2:]
     agg = collections.OrderedDict()
     for d in data:
         k = d["name"].split("(")[0].replace("void ", "").replace("<unnamed>::", "")[:52]
