@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import wavenet_oracle as O
-from tests.util import make_cfg, make_net, rel_err
+from tests.util import grads_vs_oracle, make_cfg, make_net, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -32,7 +32,8 @@ def run_train_step(net, x, tgt, T):
     return logits, loss
 
 
-def check_grads(g, g_ref, tol=GRAD_TOL):
+def check_grads(g, g_ref, tol=GRAD_TOL, cfg=None, fw=None):
+    """Every gradient within tol (relative L2); with cfg / fw the comparison is ReLU-kink aware (tests/util.py)."""
     bad = {}
     for k, v in g_ref.items():
         if np.abs(v).max() == 0:
@@ -40,6 +41,11 @@ def check_grads(g, g_ref, tol=GRAD_TOL):
                 bad[k] = "nonzero"
         elif not rel_err(g[k], v) < tol:
             bad[k] = "%.2e" % rel_err(g[k], v)
+    if bad and fw is not None:
+        worst, flipped, errs = grads_vs_oracle(cfg, fw, g)
+        if worst < tol:
+            return
+        bad = {k: "%.2e" % e for k, e in errs.items() if not e < tol}
     assert not bad, bad
 
 
@@ -64,7 +70,7 @@ def test_fp16x2_matches_oracle(name, B, W, T, tc):
     assert np.abs(got - fw["logits"]).max() < LOGIT_TOL
     assert abs(float(loss.data) - float(fw["loss"])) < 1e-5
     net.backward()
-    check_grads(net.get_grads(), g_ref)
+    check_grads(net.get_grads(), g_ref, cfg=cfg, fw=fw)
 
 
 @pytest.mark.parametrize("name,B,W,T", [("C_small", 2, 1000, 1000), ("C", 1, 4200, 1129), ("C", 3, 2171, 977), ("B", 1, 600, 343)])
@@ -83,7 +89,7 @@ def test_fp16x2_fused_train_step_gradients_match_oracle(name, B, W, T):
     net._bind(B, W)
     net._fwd_bwd(dev(x), dev(tgt), T)
     assert abs(float(net._loss[0]) - float(fw["loss"])) < 1e-5
-    check_grads(net.get_grads(), g_ref)
+    check_grads(net.get_grads(), g_ref, cfg=cfg, fw=fw)
 
 
 def test_fp16x2_block_outputs():
@@ -135,7 +141,7 @@ def test_fp16x2_adam_steps_match_oracle():
         assert abs(float(loss.data) - float(fw["loss"])) < 1e-5
         net.backward()
         g = net.get_grads()
-        check_grads(g, O.backward(cfg, fw))
+        check_grads(g, O.backward(cfg, fw), cfg=cfg, fw=fw)
         O.clip_and_adam(cfg, w_ref, {k: v.astype(np.float64) for k, v in g.items()}, st, lr=1e-3)
         net.update()
         w_got = net.get_weights()

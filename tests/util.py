@@ -82,3 +82,41 @@ def digest_err(got, want):
     e_proj = float(np.sqrt(np.mean(d[1:1 + NPROJ] ** 2)))
     e_rest = float(np.abs(np.concatenate([d[:1], d[1 + NPROJ:]])).max())
     return max(e_proj, e_rest) / scale
+
+
+def grad_errors(g, g_ref):
+    """Per-tensor relative L2 errors (tensors whose reference gradient is exactly zero must be exactly zero: error inf)."""
+    out = {}
+    for k, v in g_ref.items():
+        if np.abs(v).max() == 0:
+            out[k] = 0.0 if np.abs(g[k]).max() == 0 else float("inf")
+        else:
+            out[k] = rel_err(g[k], v)
+    return out
+
+
+def grads_vs_oracle(cfg, fw, g, eps=3e-6, max_kinks=4):
+    """Worst per-tensor gradient error against the fp64 oracle, ReLU-kink aware.
+
+    The head's ReLUs (wavenet.py:588) are not differentiable at 0: a pre-activation within the forward tolerance of zero
+    (|v| < eps; with ~5e5 ReLU inputs per case the smallest one is typically ~5e-7) may legitimately fall on the other side in
+    fp32 arithmetic -- the Chainer fp32 reference does the same against an fp64 run -- and ONE flipped mask moves every
+    upstream gradient by ~1/sqrt(#active elements) ~ 2e-3.  The product is therefore compared with the oracle's gradient for
+    the best assignment of signs to those (at most max_kinks) near-zero pre-activations; everything else is untouched.
+    Returns (worst error, number of flipped kinks, dict of per-tensor errors)."""
+    import itertools
+    errs = grad_errors(g, O.backward(cfg, fw))
+    best = (max(errs.values()), 0, errs)
+    kinks = [(i, int(j)) for i, h in enumerate(fw["h_cache"]) for j in np.flatnonzero(np.abs(h) < eps)]
+    if not kinks or len(kinks) > max_kinks:
+        return best
+    for r in range(1, len(kinks) + 1):
+        for subset in itertools.combinations(kinks, r):
+            fw2 = dict(fw)
+            fw2["h_cache"] = [h.copy() for h in fw["h_cache"]]
+            for i, j in subset:
+                fw2["h_cache"][i].flat[j] = -fw2["h_cache"][i].flat[j]
+            e2 = grad_errors(g, O.backward(cfg, fw2))
+            if max(e2.values()) < best[0]:
+                best = (max(e2.values()), r, e2)
+    return best
