@@ -673,7 +673,11 @@ tcs_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float zz, sg;
+#ifndef WN_DIAG_NOGATE
           gate_acc(__uint_as_float(f[i]), __uint_as_float(g[i]), INV_ACT_W, zz, sg);
+#else
+          zz = __uint_as_float(f[i]) * 1e-6f, sg = __uint_as_float(g[i]) * 1e-6f + 0.5f;   // timing diagnostic: no MUFU
+#endif
           g[i] = __float_as_uint(sg);
           f[i] = __float_as_uint(ACT_SCALE * zz);            // z is stored with ACT_SCALE
         }
@@ -723,8 +727,12 @@ tcs_layer_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             split2(fmaf(__uint_as_float(g[2 * i]), INV_W, xr[2 * i]), fmaf(__uint_as_float(g[2 * i + 1]), INV_W, xr[2 * i + 1]), hv[i], lv[i]);
+#ifndef WN_DIAG_NOSTORE
           st256(xrow, hv);
           st256(xrow + 64, lv);
+#else
+          if (hv[0] == 0x12345678u && lv[7] == 0x9abcdef0u) st256(xrow, hv);   // timing diagnostic: keep the math, drop the stores
+#endif
         }
         if (threadIdx.x == 64) TRS(jj, 11);
       }
