@@ -433,6 +433,8 @@ def test_many_stream_cluster_generator(n):
     lo, hi = 3, min(n, 19)                              # a shard that straddles the first cluster boundary when n > 16
     d = run(window[lo:hi], [steps], True)
     assert np.array_equal(d, a[lo:hi])
+    e = run(window[lo:hi], [steps], False)              # the default kernels: sharded streams == the same streams unsharded
+    assert np.array_equal(e, c[lo:hi])
 
 
 def test_device_crop_batch_matches_reference_create_batch():
