@@ -142,6 +142,14 @@ int wn_backward(wn_handle* h, const float* params, float* grads, wn_stream_t s);
  * (wavenet.py:556-563,597): all phases above back to back. */
 int wn_forward_loss(wn_handle* h, const float* params, const int32_t* x, const int32_t* target, int T, float* loss,
                     float* logits_opt, wn_stream_t s);
+/* Deterministic training (bit-reproducible gradients and weights run to run): every CTA of the weight-gradient kernels adds into
+ * its own copy of the flat gradient buffer with plain stores, wn_backward sums the copies in a fixed order, bias column sums
+ * and the optimiser's norm use fixed-order reductions, the embedding gradient runs as a tensor-core weight gradient.  Covers the
+ * fused fp16x2 shape (R = G = 64, k = 2, one bias-free causal layer: BASELINE config C); scratch: wn_det_scratch_bytes() device
+ * bytes owned by the caller for as long as the mode is on (~150 x the flat buffer).  The reported loss still sums per-warp
+ * partials with double-precision atomics.  The reference (Chainer/cuDNN) makes no such promise. */
+int64_t wn_det_scratch_bytes(const wn_handle* h);
+int wn_set_deterministic(wn_handle* h, int on, void* scratch);
 /* Gradient accumulation over micro-batches (a global batch larger than one tape, e.g. BASELINE config 5's 256 x 16000 on
  * one GPU): acc[i] += grads[i] over the flat layout.  wn_backward always starts from zeros (Chainer cleargrads,
  * wavenet.py:516), so the caller adds each micro-batch's gradient to its accumulator and hands the accumulator to

@@ -313,3 +313,52 @@ def test_gradient_accumulation_over_micro_batches_equals_the_big_batch():
     w_got = net.get_weights()
     for k in w_ref:
         assert np.abs(w_got[k] - w_ref[k]).max() < 2e-6, k
+
+
+def test_deterministic_mode_is_bit_reproducible_and_matches_the_atomic_mode():
+    """wn_set_deterministic: per-CTA gradient slabs summed in slab order, fixed-order column sums / optimiser norm, embedding
+    gradient as a tensor-core weight gradient.  Two independent runs of three train steps give bit-identical gradients and
+    weights; the gradients agree with the default (atomic) mode to fp32 rounding and meet the oracle gates."""
+    cfg = make_cfg("C_small")
+    w = O.init_weights(cfg, np.random.default_rng(12), np.float64)
+    rng = np.random.default_rng(13)
+    xs = [rng.integers(0, 256, (3, 700)).astype(np.int32) for _ in range(3)]
+    ts = [rng.integers(0, 256, (3, 700)).astype(np.int32) for _ in range(3)]
+
+    def run(det):
+        net = make_net(cfg, w)
+        net.set_precision("fp16x2")
+        net.update_laerning_rate(1e-3)
+        if det:
+            net.set_deterministic(True)
+        grads = []
+        for x, t in zip(xs, ts):
+            net.train_step(dev(x), dev(t))
+            grads.append(net._grads.detach().cpu().numpy().copy())
+        return grads, net.get_weights(), net
+
+    g1, w1, net1 = run(True)
+    g2, w2, _ = run(True)
+    for a, b in zip(g1, g2):
+        assert np.array_equal(a, b)
+    for k in w1:
+        assert np.array_equal(w1[k], w2[k]), k
+    # first step (same weights in both modes): deterministic == atomic up to summation order; and vs the oracle
+    net = make_net(cfg, w)
+    net.set_precision("fp16x2")
+    net._bind(3, 700)
+    net._fwd_bwd(dev(xs[0]), dev(ts[0]), 700)
+    ga = net.get_grads()
+    net1b = make_net(cfg, w)
+    net1b.set_precision("fp16x2")
+    net1b.set_deterministic(True)
+    net1b._bind(3, 700)
+    net1b._fwd_bwd(dev(xs[0]), dev(ts[0]), 700)
+    gd = net1b.get_grads()
+    for k in ga:
+        if np.abs(ga[k]).max() > 0:
+            assert rel_err(gd[k], ga[k]) < 2e-6, (k, rel_err(gd[k], ga[k]))
+        else:
+            assert np.abs(gd[k]).max() == 0, k
+    fw = O.forward_loss(cfg, w, xs[0], ts[0], train_width=700, dtype=np.float64)
+    check_grads(gd, O.backward(cfg, fw), cfg=cfg, fw=fw)

@@ -63,3 +63,5 @@ if args.gpu_device == -1:
     raise Exception("the B200 backend has no CPU mode (-g -1): the reference's CPU arithmetic lives in oracle/ for tests only")
 wavenet.to_gpu(args.gpu_device)
 wavenet.set_precision(args.precision)
+if getattr(args, "deterministic", False):
+    wavenet.set_deterministic(True)

@@ -578,6 +578,39 @@ static int causal_backward(wn_handle* h, const float* params, float* grads, cons
                              t.B, W, c0.out_ch, h->Q, c.causal_filter_width, s);
 }
 
+// ---- deterministic mode ---------------------------------------------------------------------------------------------------------
+static __global__ void det_reduce_kernel(float* __restrict__ grads, const float* __restrict__ slab, int nslab, int64_t n) {
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (int64_t)gridDim.x * blockDim.x * 4) {
+    float4 a = *reinterpret_cast<const float4*>(grads + i);
+    for (int c = 0; c < nslab; ++c) {             // fixed order: slab 0, 1, 2, ...
+      const float4 v = *reinterpret_cast<const float4*>(slab + (int64_t)c * n + i);
+      a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+    }
+    *reinterpret_cast<float4*>(grads + i) = a;
+  }
+}
+
+extern "C" int64_t wn_det_scratch_bytes(const wn_handle* h) {
+  return h ? ((int64_t)h->sm_count * h->flat_size * (int64_t)sizeof(float) + 4096 * (int64_t)sizeof(double)) : WN_EINVAL;
+}
+
+extern "C" int wn_set_deterministic(wn_handle* h, int on, void* scratch) {
+  WN_REQUIRE(h, WN_EINVAL, "null handle");
+  if (!on) {
+    h->deterministic = false;
+    h->det_slab = nullptr;
+    return WN_OK;
+  }
+  WN_REQUIRE(scratch && ((uintptr_t)scratch & 15) == 0, WN_EINVAL, "wn_set_deterministic: 16-byte aligned scratch of wn_det_scratch_bytes() needed");
+  WN_REQUIRE(h->flat_size % 4 == 0, WN_EINVAL, "wn_set_deterministic: flat size must be a multiple of 4");
+  WN_REQUIRE(tcs_supported(h) && tcs_det_supported(h), WN_EINVAL,
+             "deterministic mode covers the fused fp16x2 shape (R = G = 64, k = 2, one bias-free causal layer)");
+  h->deterministic = true;
+  h->det_slab = (float*)scratch;
+  h->det_nslab = h->sm_count;
+  return WN_OK;
+}
+
 extern "C" int wn_accumulate_grads(wn_handle* h, const float* grads, float* acc, wn_stream_t st) {
   WN_REQUIRE(h && grads && acc, WN_EINVAL, "null argument");
   return simt_add_vec(grads, acc, (int)h->flat_size, (cudaStream_t)st);
@@ -593,6 +626,16 @@ extern "C" int wn_backward(wn_handle* h, const float* params, float* grads, wn_s
   const int64_t P = t.P, rows = (int64_t)t.B * T;
   const int nh = (int)h->head.size();
   WN_CHECK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * h->flat_size, s));
+  if (h->deterministic) {
+    WN_REQUIRE(h->head_split && h->tape_split && !h->head_external && h->prec == WN_PREC_F16X2, WN_ESTATE,
+               "deterministic backward needs a tape written by the fp16x2 forward of the whole network");
+    h->det_grads = grads;
+    WN_CHECK_CUDA(cudaMemsetAsync(h->det_slab, 0, sizeof(float) * h->flat_size * h->det_nslab, s));
+    WN_TRY(tcs_backward(h, params, grads, s));
+    det_reduce_kernel<<<h->sm_count * 4, 256, 0, s>>>(grads, h->det_slab, h->det_nslab, h->flat_size);
+    WN_CHECK_LAUNCH();
+    return WN_OK;
+  }
   if (h->head_split) {
     WN_REQUIRE(h->prec == WN_PREC_F16X2 && (h->tape_split || h->head_external), WN_ESTATE,
                "backward: the tape was written by the fp16x2 path; keep that precision selected");
@@ -830,8 +873,9 @@ extern "C" int wn_clip_adam_step(wn_handle* h, float* params, float* grads, floa
                                  void* scratch, float* norm_out, wn_stream_t st) {
   WN_REQUIRE(h && params && grads && m && v && scratch, WN_EINVAL, "null argument");
   WN_REQUIRE(t >= 1, WN_EINVAL, "Adam step count must be >= 1");
+  double* det_partials = h->deterministic ? reinterpret_cast<double*>(h->det_slab + (int64_t)h->det_nslab * h->flat_size) : nullptr;
   return optim_clip_adam(params, grads, m, v, h->flat_size, t, lr, beta1, beta2, eps, weight_decay, clip, grad_scale,
-                         (double*)scratch, norm_out, h->sm_count, (cudaStream_t)st);
+                         (double*)scratch, norm_out, h->sm_count, (cudaStream_t)st, det_partials);
 }
 
 extern "C" int wn_onehot_to_index(const float* onehot, int B, int Q, int W, int32_t* idx, wn_stream_t s) {

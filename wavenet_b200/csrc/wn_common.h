@@ -123,11 +123,19 @@ struct wn_handle {
   float* fuse_ce_logits = nullptr;           //   optional fp32 logits output of that fused kernel
   bool ce_fused_done = false;
   bool dlogits_single = false;     // dlogits on the tape are ONE fp16 plane (fused CE epilogue) instead of split rows
+  // deterministic mode (wn_set_deterministic): per-CTA gradient slabs, summed in slab order by wn_backward
+  bool deterministic = false;
+  float* det_slab = nullptr;       // [det_nslab][flat_size] floats + [4096] doubles of reduction partials, caller-owned
+  int det_nslab = 0;
+  float* det_grads = nullptr;      // the gradient buffer of the backward pass in flight (slab pointers are rebased from it)
   // data-parallel communicator (wn_comm.cu): an ncclComm_t owned by the handle
   void* comm = nullptr;
   int comm_rank = 0, comm_world = 1;
   bool ce_colsum_valid = false;    // tape.ce_colsum matches tape.dlogits (set by wn_cross_entropy)
 };
+
+inline float* wn_det_ptr(const wn_handle* h, float* p) { return h->deterministic ? h->det_slab + (p - h->det_grads) : p; }
+inline int64_t wn_det_stride(const wn_handle* h) { return h->deterministic ? h->flat_size : 0; }
 
 // ---- SIMT fp32 kernels (wn_simt.cu) ---------------------------------------------
 struct GemmArgs {
@@ -198,7 +206,7 @@ int simt_onehot_to_index(const float* onehot, int B, int Q, int W, int32_t* idx,
 // ---- optimiser (wn_optim.cu) ---------------------------------------------------
 int optim_clip_adam(float* params, float* grads, float* m, float* v, int64_t n, int t, float lr, float beta1,
                     float beta2, float eps, float wd, float clip, float grad_scale, double* scratch, float* norm_out,
-                    int sm_count, cudaStream_t s);
+                    int sm_count, cudaStream_t s, double* det_partials = nullptr);
 
 // ---- tcgen05 TF32 kernels (wn_tc.cu) ---------------------------------------------
 bool tc_layer_supported(const wn_handle* h);
@@ -221,3 +229,4 @@ int tcs_forward_residual(wn_handle* h, const float* params, cudaStream_t s);
 int tcs_forward_head(wn_handle* h, const float* params, int T, bool external, cudaStream_t s);
 int tcs_scale_split_dlogits(wn_handle* h, int T, float gscale, cudaStream_t s);
 int tcs_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s);
+bool tcs_det_supported(const wn_handle* h);   // deterministic mode covers the fused fp16x2 shape with a bias-free single causal layer

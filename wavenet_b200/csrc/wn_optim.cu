@@ -7,7 +7,7 @@
 namespace {
 
 __global__ void sqnorm_kernel(const float* __restrict__ params, float* __restrict__ grads, int64_t n, float wd,
-                              float grad_scale, double* __restrict__ acc) {
+                              float grad_scale, double* __restrict__ acc, double* __restrict__ det_partials) {
   double s = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float g = grads[i] * grad_scale;
@@ -23,8 +23,17 @@ __global__ void sqnorm_kernel(const float* __restrict__ params, float* __restric
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += part[i];
-    atomicAdd(acc, t);
+    if (det_partials)
+      det_partials[blockIdx.x] = t;      // deterministic mode: summed in block order by sqnorm_finalize_kernel
+    else
+      atomicAdd(acc, t);
   }
+}
+
+__global__ void sqnorm_finalize_kernel(const double* __restrict__ partials, int n, double* __restrict__ acc) {
+  double t = 0.0;
+  for (int i = 0; i < n; ++i) t += partials[i];
+  acc[0] = t;
 }
 
 __global__ void clip_adam_kernel(float* __restrict__ params, float* __restrict__ grads, float* __restrict__ m,
@@ -54,13 +63,17 @@ __global__ void clip_adam_kernel(float* __restrict__ params, float* __restrict__
 
 int optim_clip_adam(float* params, float* grads, float* m, float* v, int64_t n, int t, float lr, float beta1,
                     float beta2, float eps, float wd, float clip, float grad_scale, double* scratch, float* norm_out,
-                    int sm_count, cudaStream_t s) {
+                    int sm_count, cudaStream_t s, double* det_partials) {
   WN_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double), s));
   int blocks = (int)((n + 255) / 256);
   if (blocks > sm_count * 8) blocks = sm_count * 8;
   if (blocks < 1) blocks = 1;
-  sqnorm_kernel<<<blocks, 256, 0, s>>>(params, grads, n, wd, grad_scale, scratch);
+  sqnorm_kernel<<<blocks, 256, 0, s>>>(params, grads, n, wd, grad_scale, scratch, det_partials);
   WN_CHECK_LAUNCH();
+  if (det_partials) {
+    sqnorm_finalize_kernel<<<1, 1, 0, s>>>(det_partials, blocks, scratch);
+    WN_CHECK_LAUNCH();
+  }
   const double fix1 = 1.0 - pow((double)beta1, (double)t);
   const double fix2 = 1.0 - pow((double)beta2, (double)t);
   const float step = (float)((double)lr * sqrt(fix2) / fix1);

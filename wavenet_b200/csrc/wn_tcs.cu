@@ -56,6 +56,17 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
       : "memory");
 }
 
+// Deterministic mode (wn_set_deterministic): every CTA adds its weight-gradient contribution into ITS OWN copy ("slab") of the
+// flat gradient buffer with plain stores -- each (CTA, element) pair is written at most once per backward pass -- and one
+// kernel then sums the slabs in slab order.  `det_stride` (floats between slabs, 0 = atomic mode) travels in the kernel
+// arguments; the destination pointers are rebased to slab 0 by the host.
+__device__ __forceinline__ void wg_add_v4(float* p, const float4& v, bool det) {
+  if (det)
+    *reinterpret_cast<float4*>(p) = v;
+  else
+    red_add_v4(p, v);
+}
+
 // MN-major fp16 operand, SWIZZLE_128B (cute canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): 64
 // contiguous M/N elements per 128-byte row, 8 K rows per 1024-byte group; LBO = bytes between 64-element M/N atoms,
 // SBO = bytes between 8-row K groups.
@@ -181,6 +192,7 @@ struct SGemmArgs {
                            // accumulates from zero in TMEM and is ADDED TO REGISTERS by the epilogue (fp32, round to nearest)
   float* colsum_out;       // MODE 5: += colsum_scale * column sums of the stored result
   float colsum_scale;
+  int64_t det_stride;      // deterministic mode: per-warp column-sum tables, fixed-order sum, plain store into the CTA's slab
   // MODE 6 (last head conv fused with softmax cross-entropy; N == 256): Y (optional) receives the fp32 logits
   const int32_t* ce_target;   // [rows]
   double* ce_acc;             // += sum over rows of (logsumexp - logit[target])
@@ -359,7 +371,8 @@ __global__ void tcs_relu_split_rows_kernel(__half* a, int C, int rows_per_seq_in
 // column sums of a split / single-plane tensor (bias gradients): out[c] += scale * sum_rows a[row][c].  A thread owns two
 // adjacent columns (one half2 per plane and row: a warp reads 128 contiguous bytes), the 8 row-slots of a block stride
 // through the rows; grid.y blocks split the rows.
-__global__ void tcs_colsum_kernel(const __half* __restrict__ a, int planes, int64_t rows, int C, float scale, float* __restrict__ out) {
+__global__ void tcs_colsum_kernel(const __half* __restrict__ a, int planes, int64_t rows, int C, float scale, float* __restrict__ out,
+                                  int64_t det_stride) {
   const int c = (blockIdx.x * 32 + threadIdx.x) * 2;
   __shared__ float red[8][66];
   float s0 = 0.f, s1 = 0.f;
@@ -381,7 +394,10 @@ __global__ void tcs_colsum_kernel(const __half* __restrict__ a, int planes, int6
   if (threadIdx.y < 2 && c < C) {
     float s = 0.f;
     for (int i = 0; i < 8; ++i) s += red[i][2 * threadIdx.x + threadIdx.y];
-    atomicAdd(out + c + threadIdx.y, s * scale);
+    if (det_stride)        // deterministic mode: block (x, y) owns slab y (gridDim.y <= number of slabs), plain store
+      out[(int64_t)blockIdx.y * det_stride + c + threadIdx.y] = s * scale;
+    else
+      atomicAdd(out + c + threadIdx.y, s * scale);
   }
 }
 
@@ -884,6 +900,8 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   if (warp == 1) tmem_alloc<512>(smem_u32((const void*)tmem_slot));
   if constexpr (MODE == 5) {
     if (threadIdx.x < BN) reinterpret_cast<float*>(gbase + Cfg::STG + 8 * 4096)[threadIdx.x] = 0.f;
+    if (a.det_stride)      // the eight 4 KB staging blocks (unused by the row-per-lane epilogue) become per-warp tables
+      for (int i = threadIdx.x; i < 8 * 1024; i += blockDim.x) reinterpret_cast<float*>(gbase + Cfg::STG)[i] = 0.f;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -1129,7 +1147,9 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           float o[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i]);
-          epi_row32(a, o, c0, t, orow, b, a.colsum_out ? cs_smem + ct : nullptr, lane);
+          // deterministic mode: a warp's sums go into ITS OWN table (one warp adds in program order); atomic mode: one table
+          float* cs_tab = a.det_stride ? reinterpret_cast<float*>(stg) : cs_smem;
+          epi_row32(a, o, c0, t, orow, b, a.colsum_out ? cs_tab + ct : nullptr, lane);
         }
         tcgen05_fence_before();
         warp_arrive(acc_empty(ab), lane);
@@ -1137,7 +1157,15 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       if (a.colsum_out) {
         asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps
         const int c = threadIdx.x - 64;
-        if (c < BN && c < a.N) atomicAdd(a.colsum_out + c, cs_smem[c] * a.colsum_scale);
+        if (c < BN && c < a.N) {
+          if (a.det_stride) {
+            float sum = 0.f;
+            for (int w = 0; w < 8; ++w) sum += reinterpret_cast<const float*>(gbase + Cfg::STG + w * 4096)[c];
+            a.colsum_out[(int64_t)blockIdx.x * a.det_stride + c] = sum * a.colsum_scale;
+          } else {
+            atomicAdd(a.colsum_out + c, cs_smem[c] * a.colsum_scale);
+          }
+        }
       }
     }
     for (int j = 0; MODE == 1 && j < n_local; ++j) {
@@ -1222,6 +1250,7 @@ struct SWgradArgs {
   int chunks_per_seq, num_chunks;
   int reverse, run, red_mode;
   float scale;                    // 1 / gscale
+  int64_t det_stride;             // deterministic mode: floats between the per-CTA gradient slabs (0 = atomics)
 };
 
 template <int NB, int MH>
@@ -1338,8 +1367,10 @@ tcs_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int nb = a.nb_sub * 64;   // channels per slab
     const float sc = a.scale;
     uint8_t* stg = gbase + (warp - 2) * 8192;   // every MMA has retired: the ring is free
+    const bool det = a.det_stride != 0;
     auto row_ptr = [&](int m, int sl) {
-      return m < a.m_split ? a.dW0[grp][sl] + (int64_t)m * a.sn : a.dW1[sl] + (int64_t)(m - a.m_split) * a.sn;
+      return (m < a.m_split ? a.dW0[grp][sl] + (int64_t)m * a.sn : a.dW1[sl] + (int64_t)(m - a.m_split) * a.sn) +
+             (int64_t)blockIdx.x * a.det_stride;
     };
     if (a.red_mode == 2) {
       // two taps interleaved in memory (sk == 2, dW[1] == dW[0] + 1): this warp owns channels [cw, cw+32) of both taps
@@ -1363,7 +1394,7 @@ tcs_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const int m = mh * 128 + q * 32 + rr;
             float4 o = *reinterpret_cast<const float4*>(stg + rr * 256 + ((kk ^ (rr & 7)) << 4));
             o.x *= sc, o.y *= sc, o.z *= sc, o.w *= sc;
-            if (m < a.m_valid) red_add_v4(row_ptr(m, 0) + (int64_t)cw * 2 + kk * 4, o);
+            if (m < a.m_valid) wg_add_v4(row_ptr(m, 0) + (int64_t)cw * 2 + kk * 4, o, det);
           }
           __syncwarp();
         }
@@ -1390,7 +1421,7 @@ tcs_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const int m = mh * 128 + q * 32 + rr;
             float4 o = *reinterpret_cast<const float4*>(stg + rr * 128 + ((kk ^ (rr & 7)) << 4));
             o.x *= sc, o.y *= sc, o.z *= sc, o.w *= sc;
-            if (m < a.m_valid && slab_ok) red_add_v4(row_ptr(m, sl) + cbase + kk * 4, o);
+            if (m < a.m_valid && slab_ok) wg_add_v4(row_ptr(m, sl) + cbase + kk * 4, o, det);
           }
           __syncwarp();
         }
@@ -1409,7 +1440,12 @@ tcs_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (m < a.m_valid && a.b_slab_idx[grp][sl] >= 0) {
             float* wrow = row_ptr(m, sl);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(wrow + (int64_t)(cbase + i) * a.sk, __uint_as_float(v[i]) * sc);
+            for (int i = 0; i < 32; ++i) {
+              if (det)
+                wrow[(int64_t)(cbase + i) * a.sk] = __uint_as_float(v[i]) * sc;
+              else
+                atomicAdd(wrow + (int64_t)(cbase + i) * a.sk, __uint_as_float(v[i]) * sc);
+            }
           }
         }
       }
@@ -1437,6 +1473,7 @@ struct SGateBwdArgs {
   int rows_out, tiles_per_seq, num_tiles;
   int reverse;
   float wscale;            // 1 / (gscale * ACT_SCALE)
+  int64_t det_stride;      // deterministic mode: floats between the per-CTA gradient slabs (0 = red.global.add)
 };
 constexpr int SG_W = 0;                         // Wp^T split: hi [64 g x 64 r] 8 KB, lo 8 KB
 constexpr int SG_ST = 16384;                    // 2 stages x {dout hi, dout lo, z hi, z lo}
@@ -1612,11 +1649,31 @@ tcs_gate_bwd_kernel(const __grid_constant__ CUtensorMap tm_dout, const __grid_co
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(vl[i]));
       }
-      float* wrow = a.dWp + (int64_t)(row & 63) * 64 + half * 32;
+      float* wrow = a.dWp + (int64_t)blockIdx.x * a.det_stride + (int64_t)(row & 63) * 64 + half * 32;
+      if (a.det_stride) {
+        // deterministic: the dout_lo products (lanes 64..127) go through shared memory (the stage ring is idle now) and are
+        // added by the warp that owns the dout_hi products of the same rows; one plain store per element
+        float* xch = reinterpret_cast<float*>(gbase + SG_ST) + ((q & 1) * 2 + half) * 1024 + lane * 32;
+        if (q >= 2) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        red_add_v4(wrow + 4 * i, make_float4(__uint_as_float(v[4 * i]) * a.wscale, __uint_as_float(v[4 * i + 1]) * a.wscale,
-                                             __uint_as_float(v[4 * i + 2]) * a.wscale, __uint_as_float(v[4 * i + 3]) * a.wscale));
+          for (int i = 0; i < 8; ++i) reinterpret_cast<uint4*>(xch)[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (q < 2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 o = reinterpret_cast<const float4*>(xch)[i];
+            *reinterpret_cast<float4*>(wrow + 4 * i) =
+                make_float4((__uint_as_float(v[4 * i]) + o.x) * a.wscale, (__uint_as_float(v[4 * i + 1]) + o.y) * a.wscale,
+                            (__uint_as_float(v[4 * i + 2]) + o.z) * a.wscale, (__uint_as_float(v[4 * i + 3]) + o.w) * a.wscale);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          red_add_v4(wrow + 4 * i, make_float4(__uint_as_float(v[4 * i]) * a.wscale, __uint_as_float(v[4 * i + 1]) * a.wscale,
+                                               __uint_as_float(v[4 * i + 2]) * a.wscale, __uint_as_float(v[4 * i + 3]) * a.wscale));
+      }
     }
   }
   tcgen05_fence_before();
@@ -1644,6 +1701,7 @@ struct SDxwArgs {
   int rows_out, tiles_per_seq, num_tiles;
   int reverse;
   float wscale;            // 1 / (gscale * ACT_SCALE)
+  int64_t det_stride;      // deterministic mode: floats between the per-CTA gradient slabs (0 = red.global.add)
 };
 // Shared-memory bandwidth (128 B/clk: TMA writes + MMA operand reads) is what bounds this kernel, so (1) W1^T (64 KB) is
 // RESIDENT instead of travelling with every unit, (2) the hi and lo planes of a B operand are adjacent and consumed by ONE
@@ -1859,11 +1917,12 @@ tcs_dxw_kernel(const __grid_constant__ CUtensorMap tm_da, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 32; ++i) v1[i] = __float_as_uint(__uint_as_float(v1[i]) + __uint_as_float(t0[i]));
       }
-      float* wrow = (q < 2 ? a.dWf : a.dWg) + (int64_t)(row & 63) * 128 + half * 64;
+      float* wrow = (q < 2 ? a.dWf : a.dWg) + (int64_t)blockIdx.x * a.det_stride + (int64_t)(row & 63) * 128 + half * 64;
 #pragma unroll
       for (int i = 0; i < 16; ++i)
-        red_add_v4(wrow + 4 * i, make_float4(__uint_as_float(v0[2 * i]) * a.wscale, __uint_as_float(v1[2 * i]) * a.wscale,
-                                             __uint_as_float(v0[2 * i + 1]) * a.wscale, __uint_as_float(v1[2 * i + 1]) * a.wscale));
+        wg_add_v4(wrow + 4 * i, make_float4(__uint_as_float(v0[2 * i]) * a.wscale, __uint_as_float(v1[2 * i]) * a.wscale,
+                                            __uint_as_float(v0[2 * i + 1]) * a.wscale, __uint_as_float(v1[2 * i + 1]) * a.wscale),
+                  a.det_stride != 0);
     }
   }
   tcgen05_fence_before();
@@ -2047,6 +2106,8 @@ int tcs_gemm(const wn_handle* h, const SOperand& A, int ns, const int* slab_idx,
   if (g.flush && (ns * (A.C / KB)) % 2 == 0) g.flush = 2;
   WN_REQUIRE(A.planes == 2 || (!g.flush && !e.gate_sg && !e.ce_target), WN_EINVAL, "tcs_gemm: single-plane A is a backward operand");
   g.colsum_out = e.ngroups_ok_for_colsum(N, BN) ? e.colsum_out : nullptr;
+  if (g.colsum_out) g.colsum_out = wn_det_ptr(h, g.colsum_out);
+  g.det_stride = wn_det_stride(h);
   g.ce_target = e.ce_target;
   g.ce_acc = e.ce_acc;
   g.ce_dlogits = e.ce_dlogits;
@@ -2103,6 +2164,7 @@ int tcs_wgrad(const wn_handle* h, const SOperand& dY, int a_row_off, int a_c0, i
   g.ngroups = ngroups;
   g.reverse = reverse;
   g.scale = scale;
+  g.det_stride = wn_det_stride(h);
   {
     static const int run_env = getenv("WN_WG_RUN") ? atoi(getenv("WN_WG_RUN")) : 8;
     g.run = run_env;
@@ -2110,11 +2172,11 @@ int tcs_wgrad(const wn_handle* h, const SOperand& dY, int a_row_off, int a_c0, i
   bool aligned = sn % 4 == 0;
   for (int i = 0; i < nb_slab; ++i) {
     g.b_row_off[i] = b_row_off[i];
-    g.dW1[i] = dW1 ? dW1[i] : nullptr;
+    g.dW1[i] = dW1 && dW1[i] ? wn_det_ptr(h, dW1[i]) : nullptr;
     if (g.dW1[i]) aligned = aligned && ((uintptr_t)g.dW1[i] & 15) == 0;
     for (int gr = 0; gr < ngroups; ++gr) {
       g.b_slab_idx[gr][i] = b_slab_idx ? b_slab_idx[gr * nb_slab + i] : 0;
-      g.dW0[gr][i] = dW0[gr * nb_slab + i];
+      g.dW0[gr][i] = dW0[gr * nb_slab + i] ? wn_det_ptr(h, dW0[gr * nb_slab + i]) : nullptr;
       if (g.b_slab_idx[gr][i] >= 0) aligned = aligned && ((uintptr_t)g.dW0[gr][i] & 15) == 0;
     }
   }
@@ -2153,7 +2215,8 @@ int tcs_gate_bwd(const wn_handle* h, const __half* dout, const __half* wpt, cons
   g.dzs = dzs;
   g.sg = sg;
   g.dafg = dafg;
-  g.dWp = dWp;
+  g.dWp = wn_det_ptr(h, dWp);
+  g.det_stride = wn_det_stride(h);
   g.zp = zp;
   g.reverse = reverse;
   g.wscale = wscale;
@@ -2183,8 +2246,9 @@ int tcs_dxw(const wn_handle* h, const __half* dafg, const __half* w1t, const __h
   memset(&g, 0, sizeof(g));
   g.rsd = rsd;
   g.Y = Y;
-  g.dWf = dWf;
-  g.dWg = dWg;
+  g.dWf = wn_det_ptr(h, dWf);
+  g.dWg = wn_det_ptr(h, dWg);
+  g.det_stride = wn_det_stride(h);
   g.d = d;
   g.reverse = reverse;
   g.wscale = wscale;
@@ -2414,6 +2478,8 @@ int tcs_forward_head(wn_handle* h, const float* params, int T, bool external, cu
   return WN_OK;
 }
 
+static int tcs_embed_backward_det(wn_handle* h, const __half* dout_split, float* grads, float inv, cudaStream_t s);
+
 // Backward of head + residual stack; requires a tape written by tcs_forward_residual and tcs_forward_head and dlogits in
 // split format scaled by h->gscale.
 int tcs_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s) {
@@ -2452,7 +2518,9 @@ int tcs_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s
       } else {
         WN_REQUIRE(cp.out_ch % 2 == 0, WN_EINVAL, "tcs_colsum: odd channel count");
         dim3 grid(nblk(cp.out_ch, 64), 4 * h->sm_count / (int)nblk(cp.out_ch, 64) + 1), block(32, 8);
-        tcs_colsum_kernel<<<grid, block, 0, s>>>(d, dpl, (int64_t)B * T, cp.out_ch, inv, grads + cp.b_off);
+        if (h->deterministic) grid.y = h->det_nslab;
+        tcs_colsum_kernel<<<grid, block, 0, s>>>(d, dpl, (int64_t)B * T, cp.out_ch, inv, wn_det_ptr(h, grads + cp.b_off),
+                                                 wn_det_stride(h));
         WN_CHECK_LAUNCH();
       }
     }
@@ -2619,10 +2687,50 @@ int tcs_backward(wn_handle* h, const float* params, float* grads, cudaStream_t s
       dt ^= 1;
     }
   }
+  if (h->deterministic) {
+    h->bwd_dout = nullptr;
+    return h->causal_from_idx ? tcs_embed_backward_det(h, dout, grads, inv, s) : WN_OK;
+  }
   // gradient w.r.t. the causal output, back to unscaled fp32 rows for the SIMT embedding / causal-stack backward
   float* dfin = ws + t.dout[dt];
   WN_TRY(tcs_unsplit_rows(reinterpret_cast<const float*>(dout), dfin, R, P, inv, s));
   h->bwd_dout = dfin;
+  return WN_OK;
+}
+
+// ---- deterministic mode: the embedding gradient as a tensor-core weight gradient ---------------------------------------------
+// dWc(r, q, tap) = sum_p [idx[p - (kc-1-tap)] == q] * dout[p][r]  is  onehot^T . dout: the one-hot rows are written as ONE exact
+// fp16 plane and the generic weight-gradient kernel (per-CTA accumulators in TMEM, per-CTA slabs) does the rest -- no
+// shared-memory float atomics, whose order the SIMT scatter kernel cannot fix.
+__global__ void tcs_onehot_rows_kernel(const int32_t* __restrict__ idx, __half* __restrict__ oh, int64_t P, int Q) {
+  const int qv = Q >> 3;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * qv) return;
+  const int64_t p = i / qv;
+  const int q0 = (int)(i - p * qv) * 8;
+  const int k = idx[p] - q0;
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  if (k >= 0 && k < 8) w[k >> 1] = (k & 1) ? 0x3c000000u : 0x00003c00u;   // fp16 1.0 in the upper / lower half
+  *reinterpret_cast<uint4*>(oh + p * Q + q0) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+bool tcs_det_supported(const wn_handle* h) {
+  return fused_shape(h) && h->cfg.n_causal == 1 && h->causal[0].b_off < 0 && h->Q % 64 == 0 && h->Q <= 256 && h->layers.size() >= 2;
+}
+
+static int tcs_embed_backward_det(wn_handle* h, const __half* dout_split, float* grads, float inv, cudaStream_t s) {
+  const Tape& t = h->tape;
+  const int kc = h->cfg.causal_filter_width, Q = h->Q, R = h->R;
+  __half* oh = HP(h->ws + t.dzs);                      // [P][Q] halves: the dzs slabs are dead by now
+  tcs_onehot_rows_kernel<<<nblk(t.P * (Q / 8), 256), 256, 0, s>>>(h->x_idx, oh, t.P, Q);
+  WN_CHECK_LAUNCH();
+  SOperand OH{oh, Q, t.W, t.B, 1, 0, 1};
+  SOperand X{dout_split, R, t.W, t.B, 1, 0};
+  const int zero = 0;
+  for (int tap = 0; tap < kc; ++tap) {
+    float* dw = grads + h->causal[0].w_off + tap;      // element (r, q, tap) at (r * Q + q) * kc + tap
+    WN_TRY(tcs_wgrad(h, OH, -(kc - 1 - tap), 0, Q, X, 1, &zero, nullptr, &dw, nullptr, 256, t.W, kc, (int64_t)Q * kc, inv, s));
+  }
   return WN_OK;
 }
 
