@@ -179,6 +179,15 @@ int wn_comm_init(wn_handle* h, const char* id_host /* [128] */, int rank, int wo
 int wn_comm_world(const wn_handle* h);
 int wn_allreduce_grads(wn_handle* h, float* grads, wn_stream_t s);   /* in-place sum over ranks; no-op without a communicator */
 int wn_comm_destroy(wn_handle* h);
+/* One-shot peer-memory all-reduce fused with the optimiser's first pass (opt-in: WN_FUSED_ALLREDUCE=1 in the environment when
+ * wn_comm_init runs; <= 8 ranks of one node): every rank publishes its gradient in a CUDA-IPC buffer, ONE kernel sums all
+ * buffers in rank order over NVLink peer loads, applies 1/N and the weight-decay hook and accumulates the squared norm; the
+ * clip + Adam kernel follows.  Without the peer path the call is wn_allreduce_grads + wn_clip_adam_step.  grad_scale multiplies
+ * the SUMMED gradient. */
+int wn_comm_peer_enabled(const wn_handle* h);
+int wn_allreduce_clip_adam_step(wn_handle* h, float* params, float* grads, float* m, float* v, int t, float lr, float beta1,
+                                float beta2, float eps, float weight_decay, float clip, float grad_scale, void* scratch,
+                                float* norm_out, wn_stream_t s);
 
 /* Profiling hooks used by bench.py's roofline leg: ONE launch of the fused residual-layer kernel (layer l)
  * or of the skip-sum GEMM on the bound tape; need a preceding TF32 wn_forward_residual_block. */

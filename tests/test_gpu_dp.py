@@ -37,6 +37,8 @@ net = make_net(cfg, w)
 net.set_precision(prec)
 net.update_laerning_rate(1e-3)
 net.use_cuda_graph = False
+if len(sys.argv) > 2 and sys.argv[2] == "det":
+    net.set_deterministic(True)            # bit-reproducible gradients: two separate launches become comparable bit for bit
 init_comm(net)
 assert net._libh.wn_comm_world(net._h) == world
 # gradient of the shard, all-reduced inside the library
@@ -61,6 +63,10 @@ if rank == 0:
 for step in range(3):
     net.train_step(dev(x[b0:b1]), dev(t[b0:b1]))
 same = assert_replicas_equal(net._params.cpu(), atol=0.0)
+if rank == 0:
+    import hashlib
+    print("PEER %%d" %% net._libh.wn_comm_peer_enabled(net._h), flush=True)
+    print("PARAMS_SHA %%s" %% hashlib.sha1(net._params.cpu().numpy().tobytes()).hexdigest(), flush=True)
 flag = torch.tensor([1 if (ok and same) else 0])
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
@@ -77,13 +83,38 @@ def _free_port():
     return p
 
 
+def _run_workers(prec, tmp_path, fused, det=False):
+    script = tmp_path / "dp_worker.py"
+    script.write_text(WORKER % ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), str(script), prec] + (["det"] if det else [])
+    env = dict(os.environ)
+    env["WN_FUSED_ALLREDUCE"] = "1" if fused else "0"
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert "DP_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    peer = int(out.stdout.split("PEER ")[1].split()[0])
+    sha = out.stdout.split("PARAMS_SHA ")[1].split()[0]
+    return peer, sha
+
+
 @pytest.mark.parametrize("prec", ["fp16x2", "fp32"])
 def test_two_rank_dp_gradient_equals_global_batch(prec, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
-    script = tmp_path / "dp_worker.py"
-    script.write_text(WORKER % ROOT)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", str(_free_port()), str(script), prec]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
-    assert "DP_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    peer, _ = _run_workers(prec, tmp_path, fused=False)
+    assert peer == 0
+
+
+def test_fused_peer_allreduce_matches_nccl_path(tmp_path):
+    """WN_FUSED_ALLREDUCE=1: the one-shot peer-memory all-reduce fused with the optimiser's norm pass (CUDA-IPC buffers, P2P
+    loads summed in rank order) trains to the SAME BITS as ncclAllReduce + wn_clip_adam_step (two ranks: a + b == b + a), with
+    bit-identical replicas.  Both runs use the deterministic mode (fixed-order gradient reductions), so two separate launches
+    are comparable bit for bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    peer0, sha0 = _run_workers("fp16x2", tmp_path, fused=False, det=True)
+    peer1, sha1 = _run_workers("fp16x2", tmp_path, fused=True, det=True)
+    assert peer0 == 0
+    if peer1 == 0:
+        pytest.skip("CUDA IPC peer buffers are not available on this box: the library fell back to NCCL")
+    assert sha0 == sha1

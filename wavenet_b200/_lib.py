@@ -88,6 +88,8 @@ SIGNATURES = {
     "wn_comm_world": (_I, [_P]),
     "wn_allreduce_grads": (_I, [_P, _P, _P]),
     "wn_accumulate_grads": (_I, [_P, _P, _P, _P]),
+    "wn_comm_peer_enabled": (_I, [_P]),
+    "wn_allreduce_clip_adam_step": (_I, [_P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _F, _F, _F, _P, _P, _P]),
     "wn_det_scratch_bytes": (_L, [_P]),
     "wn_set_deterministic": (_I, [_P, _I, _P]),
     "wn_comm_destroy": (_I, [_P]),

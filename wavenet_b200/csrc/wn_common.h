@@ -131,6 +131,7 @@ struct wn_handle {
   // data-parallel communicator (wn_comm.cu): an ncclComm_t owned by the handle
   void* comm = nullptr;
   int comm_rank = 0, comm_world = 1;
+  void* peer = nullptr;            // PeerState* (wn_comm.cu): CUDA-IPC exchange buffers of the fused one-shot all-reduce
   bool ce_colsum_valid = false;    // tape.ce_colsum matches tape.dlogits (set by wn_cross_entropy)
 };
 
@@ -207,6 +208,10 @@ int simt_onehot_to_index(const float* onehot, int B, int Q, int W, int32_t* idx,
 int optim_clip_adam(float* params, float* grads, float* m, float* v, int64_t n, int t, float lr, float beta1,
                     float beta2, float eps, float wd, float clip, float grad_scale, double* scratch, float* norm_out,
                     int sm_count, cudaStream_t s, double* det_partials = nullptr);
+// the second half of optim_clip_adam for callers that produced the squared norm themselves (scratch[0], or det_partials[0..n))
+int optim_adam_after_norm(float* params, float* grads, float* m, float* v, int64_t n, int t, float lr, float beta1, float beta2,
+                          float eps, float clip, double* scratch, float* norm_out, int sm_count, cudaStream_t s,
+                          double* det_partials, int det_n);
 
 // ---- tcgen05 TF32 kernels (wn_tc.cu) ---------------------------------------------
 bool tc_layer_supported(const wn_handle* h);

@@ -70,8 +70,18 @@ int optim_clip_adam(float* params, float* grads, float* m, float* v, int64_t n, 
   if (blocks < 1) blocks = 1;
   sqnorm_kernel<<<blocks, 256, 0, s>>>(params, grads, n, wd, grad_scale, scratch, det_partials);
   WN_CHECK_LAUNCH();
+  return optim_adam_after_norm(params, grads, m, v, n, t, lr, beta1, beta2, eps, clip, scratch, norm_out, sm_count, s,
+                               det_partials, blocks);
+}
+
+int optim_adam_after_norm(float* params, float* grads, float* m, float* v, int64_t n, int t, float lr, float beta1, float beta2,
+                          float eps, float clip, double* scratch, float* norm_out, int sm_count, cudaStream_t s,
+                          double* det_partials, int det_n) {
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > sm_count * 8) blocks = sm_count * 8;
+  if (blocks < 1) blocks = 1;
   if (det_partials) {
-    sqnorm_finalize_kernel<<<1, 1, 0, s>>>(det_partials, blocks, scratch);
+    sqnorm_finalize_kernel<<<1, 1, 0, s>>>(det_partials, det_n, scratch);
     WN_CHECK_LAUNCH();
   }
   const double fix1 = 1.0 - pow((double)beta1, (double)t);

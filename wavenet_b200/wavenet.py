@@ -498,11 +498,14 @@ class WaveNet(object):
             grads = self._grads
         if self.data_parallel:
             world = int(self._libh.wn_comm_world(self._h))
-            if world > 1:        # communicator behind the C ABI (dist.init_comm): NCCL all-reduce on the caller's stream
-                check(self._libh.wn_allreduce_grads(self._h, _ptr(grads), _stream()))
-                grad_scale = 1.0 / world
-            else:                # no communicator in the library: torch.distributed (host-side tests)
-                grad_scale = allreduce_sum_(grads)
+            if world > 1:        # communicator behind the C ABI (dist.init_comm): exchange + hooks + Adam in one entry point
+                opt.t += 1       # (NCCL all-reduce, or the fused one-shot peer-memory all-reduce when it is enabled)
+                check(self._libh.wn_allreduce_clip_adam_step(
+                    self._h, _ptr(self._params), _ptr(grads), _ptr(self._m), _ptr(self._v), opt.t, opt.alpha, opt.beta1,
+                    opt.beta2, opt.eps, float(p.weight_decay), float(p.gradient_clipping), 1.0 / (world * micro_batches),
+                    _ptr(self._scratch), _ptr(self._norm), _stream()))
+                return
+            grad_scale = allreduce_sum_(grads)      # no communicator in the library: torch.distributed (host-side tests)
         grad_scale /= micro_batches
         opt.t += 1
         check(self._libh.wn_clip_adam_step(self._h, _ptr(self._params), _ptr(grads), _ptr(self._m), _ptr(self._v),
