@@ -474,6 +474,8 @@ def main():
         "config": {"workload": "config C (30 layers d=1..512 x3, 64 residual / 256 skip, head 256-256-256), "
                                "%d x %d samples per GPU, full-width teacher-forced train step" % (B, W),
                    "global_batch": B * world, "width": W, "parallelism": "dp%d" % world, "precision_mode": eff_prec,
+                   "allreduce": (None if world == 1 else ("fused one-shot peer-memory all-reduce + norm (wn_allreduce_clip_adam_step)"
+                                                          if lib.wn_comm_peer_enabled(net._h) else "ncclAllReduce behind the C ABI")),
                    "l2": "working set (activation tape ~20 GB) is far larger than the 126 MB L2; no explicit flush"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(x_h.nbytes + t_h.nbytes),
                 "d2h_bytes_per_step": 4},
