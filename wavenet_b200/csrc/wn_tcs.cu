@@ -14,7 +14,15 @@
 // tensors h->gscale (chosen from B*T by wn_cross_entropy).  Every epilogue / reduction multiplies the accumulator by the
 // reciprocal product (exact), so the scales never show outside this file.
 //
+// Backward: the residual-gradient stream dout and every forward-tape operand (x, z, weights) stay split; the gradient
+// tensors that are only ever the dY operand of a product (dlogits, dh, dskip, dzs, dafg) are ONE fp16 plane rounded to
+// nearest (two MMAs per product) and the sigmoid tape is 16-bit fixed point -- together 6.5e-4 of the gradient norm against
+// the 1e-3 gate (tests/dev/quant_sensitivity.py).  Where the hi and lo planes of an operand are adjacent in shared memory
+// they are consumed by ONE MMA of twice the N (or M): small-N MMAs are bound by shared-memory operand reads, not by the
+// tensor pipe.
+//
 //  tcs_layer_kernel : one residual layer (wavenet.py:358-368, dilated conv of :294-342 in closed form) per launch
+//  tcs_gate_bwd_kernel / tcs_dxw_kernel : the two fused backward kernels of a residual layer
 //  tcs_gemm_kernel  : Y = epi(sum_slab A_slab . W^T)   (skip sum, head, data gradients, gate derivative epilogue)
 //  tcs_wgrad_kernel : dW = dY^T . X                    (all weight gradients)
 #include <cuda.h>
