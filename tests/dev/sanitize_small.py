@@ -19,11 +19,13 @@ if what in ("all", "train"):
     rng = np.random.default_rng(1)
     x = rng.integers(0, 256, (2, 300)).astype(np.int32)
     t = rng.integers(0, 256, (2, 300)).astype(np.int32)
-    for prec in ("fp16x2", "tf32"):
+    for prec in ("fp16x2", "fp16x2-deterministic", "tf32"):
         net = make_net(cfg, w)
-        net.set_precision(prec)
+        net.set_precision(prec.split("-")[0])
         net.use_cuda_graph = False
         net.update_laerning_rate(1e-3)
+        if prec.endswith("deterministic"):
+            net.set_deterministic(True)
         loss = net.train_step(dev(x), dev(t))
         torch.cuda.synchronize()
         print("train", prec, float(loss[0]), flush=True)
