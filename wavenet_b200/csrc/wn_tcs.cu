@@ -906,6 +906,9 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     prefetch_tmap(&tm_b);
   }
   if (warp == 1) tmem_alloc<512>(smem_u32((const void*)tmem_slot));
+  if constexpr (MODE == 6) {     // the fused CE epilogue reads the bias three times per element: keep it in shared memory
+    if (threadIdx.x < BN) reinterpret_cast<float*>(gbase + Cfg::STG + 8 * 4096)[threadIdx.x] = a.bias ? a.bias[threadIdx.x] : 0.f;
+  }
   if constexpr (MODE == 5) {
     if (threadIdx.x < BN) reinterpret_cast<float*>(gbase + Cfg::STG + 8 * 4096)[threadIdx.x] = 0.f;
     if (a.det_stride)      // the eight 4 KB staging blocks (unused by the row-per-lane epilogue) become per-warp tables
@@ -1069,7 +1072,7 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float l = fmaf(__uint_as_float(v[i]), a.acc_scale, a.bias ? __ldg(a.bias + cbase + ch * 32 + i) : 0.f);
+            const float l = fmaf(__uint_as_float(v[i]), a.acc_scale, cs_smem[cbase + ch * 32 + i]);
             m = fmaxf(m, l);
             if (cbase + ch * 32 + i == tg) xt = l;
           }
@@ -1087,7 +1090,7 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            sum += expf(fmaf(__uint_as_float(v[i]), a.acc_scale, a.bias ? __ldg(a.bias + cbase + ch * 32 + i) : 0.f) - m);
+            sum += ex2_approx((fmaf(__uint_as_float(v[i]), a.acc_scale, cs_smem[cbase + ch * 32 + i]) - m) * 1.4426950408889634f);
         }
         xmax[32 + lane] = sum;
         asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
@@ -1108,9 +1111,9 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int col = cbase + ch * 32 + hh * 16 + i;
-              const float l = fmaf(__uint_as_float(v[hh * 16 + i]), a.acc_scale, a.bias ? __ldg(a.bias + col) : 0.f);
+              const float l = fmaf(__uint_as_float(v[hh * 16 + i]), a.acc_scale, cs_smem[col]);
               v[hh * 16 + i] = __float_as_uint(l);
-              d[i] = (expf(l - m) * inv - (col == tg ? 1.f : 0.f)) * gk;
+              d[i] = (ex2_approx((l - m) * 1.4426950408889634f) * inv - (col == tg ? 1.f : 0.f)) * gk;
             }
             if (valid) {
 #pragma unroll
