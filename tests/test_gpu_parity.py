@@ -435,6 +435,12 @@ def test_many_stream_cluster_generator(n):
     assert np.array_equal(d, a[lo:hi])
     e = run(window[lo:hi], [steps], False)              # the default kernels: sharded streams == the same streams unsharded
     assert np.array_equal(e, c[lo:hi])
+    os.environ["WN_GEN_NS"] = "2"                       # gen_kernel_v3<2>: the two-streams-per-CTA variant the 256-stream runs use
+    try:
+        f = run(window, [steps], False)
+    finally:
+        os.environ.pop("WN_GEN_NS", None)
+    assert (f != want).any(axis=1).sum() <= 1 and (f != c).any(axis=1).sum() <= 1
 
 
 def test_device_crop_batch_matches_reference_create_batch():
