@@ -8,6 +8,7 @@
 // only the last column is computed, sampling happens on device and the loop over
 // audio samples never returns to the host.  Arithmetic is exact fp32 (FFMA) so
 // greedy sequences can match the oracle.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -39,6 +40,10 @@ struct GenLayout {
   int64_t wpk = 0;          // packed weights (v3)
   int64_t wpk4 = 0;         // per-cluster-rank packed weight slices (v4)
   int64_t wpk4_rank = 0;    // floats per rank
+  int64_t wpk6 = 0;         // per-rank fp16 hi|lo B tiles of the tensor-core generator (v6)
+  int64_t wpk6_rank_bytes = 0;
+  int64_t ring6 = 0;        // v6 dilation rings: [cluster][rank][slot][32 KB operand tile]
+  int64_t ring6_cta_bytes = 0;
   int64_t total = 0;
   int maxw = 0;             // widest vector anywhere (for smem sizing)
 };
@@ -67,6 +72,10 @@ struct wn_gen {
   std::vector<Pack3> packs3;
   bool v4_ok = false;                 // config-C shape: the cluster generators' packed weight slices exist (v4: one 8-CTA
                                       // cluster per stream while they are all co-resident; v5: 16 streams per cluster)
+  bool v6_ok = false;                 // tensor-core generator (gen_kernel_v6): config-C shape without biases, >= 16 streams
+  int v6_spc = 128, v6_clusters = 0;  // streams per 8-CTA cluster, clusters
+  bool ring6_valid = false;           // the v6 operand-tile rings hold the current state
+  bool ringf_valid = true;            // the fp32 rings hold the current state
 };
 
 namespace {
@@ -1967,6 +1976,8 @@ int launch_gen_v5(const GenArgs& a, cudaStream_t s) {
   return WN_OK;
 }
 
+#include "wn_gen_mma.cuh"
+
 size_t gen_smem_bytes(const GenLayout& L, int NS, bool stream) {
   const size_t maxw = L.maxw;
   size_t f = NS * maxw                               // xv
@@ -1989,6 +2000,46 @@ int launch_gen(const GenArgs& a, cudaStream_t s) {
   return WN_OK;
 }
 
+// fp32 rings <-> operand-tile rings of gen_kernel_v6 (lazily, whenever the kernel family changes between calls)
+int gen_v6_convert(wn_gen* g, bool to_v6, cudaStream_t s) {
+  const GenLayout& L = g->lay;
+  uint8_t* ring6 = reinterpret_cast<uint8_t*>(g->state + L.ring6);
+  int base = 0;
+  for (int l = 0; l < L.L; ++l) {
+    const GenLayerOff& o = g->layers[l];
+    const int64_t items = (int64_t)g->v6_clusters * o.ring_len * 1024;
+    const unsigned nb = (unsigned)((items + 255) / 256);
+    if (to_v6)
+      gen_ring_to_v6<<<nb, 256, 0, s>>>(g->state + o.ring, ring6, L.ring6_cta_bytes, base, o.ring_len, L.n, g->v6_spc, g->v6_clusters);
+    else
+      gen_ring_from_v6<<<nb, 256, 0, s>>>(g->state + o.ring, ring6, L.ring6_cta_bytes, base, o.ring_len, L.n, g->v6_spc,
+                                          g->v6_clusters);
+    base += o.ring_len;
+  }
+  WN_CHECK_LAUNCH();
+  return WN_OK;
+}
+
+int launch_gen_v6(wn_gen* g, const GenArgs& a, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    WN_CHECK_CUDA(cudaFuncSetAttribute(gen_kernel_v6, cudaFuncAttributeMaxDynamicSharedMemorySize, V6_SMEM + 128));
+    attr_set = true;
+  }
+  if (!g->ring6_valid) WN_TRY(gen_v6_convert(g, true, s));
+  V6Args v;
+  v.wpk = reinterpret_cast<const uint8_t*>(g->state + g->lay.wpk6);
+  v.wpk_rank_bytes = g->lay.wpk6_rank_bytes;
+  v.ring = reinterpret_cast<uint8_t*>(g->state + g->lay.ring6);
+  v.ring_cta_bytes = g->lay.ring6_cta_bytes;
+  v.spc = g->v6_spc;
+  gen_kernel_v6<<<g->v6_clusters * V6_CS, V6_THREADS, V6_SMEM + 128, s>>>(a, v);
+  WN_CHECK_LAUNCH();
+  g->ring6_valid = true;
+  g->ringf_valid = false;
+  return WN_OK;
+}
+
 int pick_ns(const wn_gen* g) {
   // streams per CTA: spread over the SMs first, then stack streams to amortise weight reads
   const int n = g->lay.n, sms = g->h->sm_count;
@@ -1999,6 +2050,16 @@ int pick_ns(const wn_gen* g) {
 
 int run_gen(wn_gen* g, GenArgs& a, cudaStream_t s) {
   const int ns = pick_ns(g);
+  // tensor-core generator: >= 16 streams of the config-C shape, free-running sampling loop (not the one-step API)
+  if (g->v6_ok && a.sample_first && a.n_steps >= 8 && !a.probs) {
+    const char* e = getenv("WN_GEN_V6");
+    if (!e || atoi(e) != 0) return launch_gen_v6(g, a, s);
+  }
+  if (!g->ringf_valid) {                     // the last call ran on the v6 rings: bring the fp32 rings up to date
+    WN_TRY(gen_v6_convert(g, false, s));
+    g->ringf_valid = true;
+  }
+  g->ring6_valid = false;
   if (g->v4_ok && g->lay.n <= gen_v4_max_streams(g->lay)) {
     const char* e = getenv("WN_GEN_V4");
     if (!e || atoi(e) != 0) return launch_gen_v4(a, s);
@@ -2163,6 +2224,25 @@ extern "C" int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen**
     L.wpk4_rank = (int64_t)L.L * (2 * 256 * 4 + 8 * 192 * 4) + (int64_t)L.n_head * (8 * 256 * 4);
     L.wpk4 = take(L.wpk4_rank * V4_CS_HOST);
   }
+  // v6 (streams = MMA M dimension, <= 128 per 8-CTA cluster): the v4 shape with biases in the head only, two head convs
+  g->v6_ok = g->v4_ok && L.n_head == 2 && !L.has_cb && L.L <= 64 && n_streams >= 16;
+  for (int l = 0; l < L.L && g->v6_ok; ++l) g->v6_ok = !g->layers[l].has_ba && !g->layers[l].has_bb;
+  if (g->v6_ok) {
+    int spc = 128;
+    if (const char* e = getenv("WN_GEN_V6_SPC")) spc = atoi(e);
+    if (spc < 8 || spc > 128) spc = 128;
+    g->v6_spc = spc;
+    g->v6_clusters = (n_streams + spc - 1) / spc;
+    if (g->v6_clusters * V4_CS_HOST > h->sm_count) g->v6_ok = false;      // every cluster resident at once
+  }
+  if (g->v6_ok) {
+    int64_t slots = 0;
+    for (int l = 0; l < L.L; ++l) slots += g->layers[l].ring_len;
+    L.wpk6_rank_bytes = (int64_t)(L.L + L.n_head) * 32768;
+    L.wpk6 = take(L.wpk6_rank_bytes * V4_CS_HOST / 4);
+    L.ring6_cta_bytes = slots * 32768;
+    L.ring6 = take(L.ring6_cta_bytes / 4 * V4_CS_HOST * g->v6_clusters);
+  }
   L.maxw = (maxw + 3) / 4 * 4;
   L.total = off;
   *out = g;
@@ -2285,6 +2365,20 @@ extern "C" int wn_gen_prime(wn_gen* g, const float* params, const int32_t* windo
     }
     WN_CHECK_LAUNCH();
   }
+  if (g->v6_ok) {
+    uint8_t* w6 = reinterpret_cast<uint8_t*>(S + L.wpk6);
+    for (int l = 0; l < L.L; ++l) {
+      uint8_t* d = w6 + (int64_t)l * 32768;
+      gen_pack_v6<<<nb(8 * 16 * 32 * 8), 256, 0, s>>>(S + g->layers[l].wa, d, L.wpk6_rank_bytes, 1, 128);
+      gen_pack_v6<<<nb(8 * 8 * 128 * 8), 256, 0, s>>>(S + g->layers[l].wb, d + 8192, L.wpk6_rank_bytes, 2, 320);
+      gen_pack_v6<<<nb(8 * 8 * 64 * 8), 256, 0, s>>>(S + g->layers[l].wb, d + 24576, L.wpk6_rank_bytes, 3, 320);
+    }
+    for (int i = 0; i < L.n_head; ++i)
+      gen_pack_v6<<<nb(8 * 32 * 64 * 8), 256, 0, s>>>(S + L.hw[i], w6 + (int64_t)(L.L + i) * 32768, L.wpk6_rank_bytes, 4, 256);
+    WN_CHECK_LAUNCH();
+  }
+  g->ring6_valid = false;
+  g->ringf_valid = true;
   g->primed = true;
   g->t = Win;
   g->steps_done = 0;

@@ -1,0 +1,615 @@
+// gen_kernel_v6: the MANY-stream generator on the tensor cores (included by wn_gen.cu inside its anonymous namespace).
+//
+// FasterWaveNet._forward_one_step (faster_wavenet.py:50-113) + the sampling loop of train_audio/generate.py:24-43 for up
+// to 128 streams per 8-CTA cluster.  The SIMT generators feed every FMA one operand from shared memory (v3: 5 MB of
+// weights per CTA and step; v5: ~4 k LDS wavefronts per layer), so they stop scaling at one or two streams per SM.  Here
+// the STREAMS are the M dimension of tcgen05.mma (M = 128, one TMEM lane per stream) and the eight CTAs of a cluster split
+// every weight matrix by OUTPUT rows like v4/v5 (1 MB of packed fp16 hi|lo weights per CTA and step, streamed through a
+// cp.async.bulk ring):
+//   gate      D[128 x 16]  = [x(t-d) | x(t)] (K = 128) . Wf/Wg rows of this rank (8 f + 8 g)
+//   project   D[128 x 64]  = z (K = 64) . Wp (all 64 rows, computed redundantly by every CTA: ONE exchange per layer)
+//   skip      D[128 x 32] += z . Ws rows of this rank (accumulates in TMEM, flushed to registers every V6_FLUSH layers
+//                                                     because the tensor core accumulates round-toward-zero)
+//   head      D[128 x 32]  = h (K = 256) . W rows of this rank, twice
+// Arithmetic is the fp16x2 split of the training path (wn_tcs.cu): A.B ~ A_hi.B_hi + A_hi.B_lo + A_lo.B_hi with fp32
+// accumulation; the hi and lo weight planes are adjacent rows of one B tile, so a product is TWO MMAs (A_hi . [B_hi|B_lo]
+// with twice the N, A_lo . B_hi) and the epilogue adds the two column halves.
+// Operand tiles use the NO-SWIZZLE K-major canonical layout (8-row x 16-byte core matrices): tile[k_core][plane][128 rows]
+// [16 B] -- a CTA's slice of an exchanged activation (its 8 gate channels = one k_core, both planes, all 128 streams) is
+// then one contiguous 4 KB block and travels with ONE cp.async.bulk shared::cta -> shared::cluster per destination
+// (complete_tx on the destination's mbarrier, the data path the MMA's async proxy reads without a cross-proxy fence).
+// The dilation rings hold whole operand tiles (x(t) of a layer for all 128 streams, 32 KB): one bulk store per layer and
+// step, one bulk load d steps later, private to each CTA (no cross-CTA ordering of global memory on the chain).
+// Warp roles: 8 epilogue warps (TMEM lane quarter = warp & 3, column half = warp >> 2), one producer thread (weights,
+// ring loads / stores), one MMA-issuing thread.
+
+constexpr int V6_CS = 8;
+constexpr int V6_T = 256;                       // epilogue threads
+constexpr int V6_THREADS = V6_T + 64;           // + producer warp + MMA warp
+constexpr int V6_TILE = 32768;                  // [8 k_cores][2 planes][128 rows][16 B]
+constexpr int V6_CHUNK = 32768;                 // weights of one layer (gate 8 KB | project 16 KB | skip 8 KB) or one head conv
+constexpr int V6_OFF_X = 0;                     // x(t) tile
+constexpr int V6_OFF_XD = V6_TILE;              // 2 x x(t-d) tiles
+constexpr int V6_OFF_Z = 3 * V6_TILE;           // 2 x z tiles
+constexpr int V6_OFF_CAND = 4 * V6_TILE;        // sampling candidates live in z tile 1 (idle between the head and layer 1)
+constexpr int V6_OFF_W = 5 * V6_TILE;           // 2 weight stages
+constexpr int V6_SMEM = 7 * V6_TILE;            // the head's K = 256 tile (128 KB) overlays x | xd | z0
+constexpr int V6_FLUSH = 5;                     // layers per TMEM skip-accumulation group
+constexpr int V6_MAXL = 64;
+constexpr float V6_ACT = 8.f, V6_WSC = 16.f, V6_INV = 1.f / (V6_ACT * V6_WSC);
+constexpr uint32_t V6_TM_GATE = 0, V6_TM_PROJ = 32, V6_TM_SKIP = 160, V6_TM_HEAD = 32;
+
+__host__ __device__ constexpr uint32_t v6_idesc(int M, int N) {   // kind::f16, fp16 operands, fp32 accumulate, K-major A and B
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void v6_umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major operand without swizzle (cute canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte units): LBO = bytes between the
+// two 8-element K chunks of one MMA, SBO = bytes between 8-row groups.
+__device__ __forceinline__ uint64_t v6_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void v6_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t v6_pack(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+__device__ __forceinline__ void v6_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = v6_pack(a, b);
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = v6_pack(a - f.x, b - f.y);
+}
+// eight consecutive channels of one row -> the 16-byte hi chunk and the 16-byte lo chunk (2048 bytes further) of a tile
+__device__ __forceinline__ void v6_store8(uint32_t addr, const float* v, float scale) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v6_split2(v[2 * i] * scale, v[2 * i + 1] * scale, h[i], l[i]);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + 2048), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+}
+// waits that acquire at cluster scope (payload written by a peer's bulk copy / a peer's remote arrive)
+__device__ __forceinline__ void v6_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++spins > (1u << 25)) {
+      printf("wavenet_b200: generator v6 exchange timeout (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void v6_remote_arrive(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void v6_esync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void v6_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void v6_bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(dst)), "r"(src),
+               "r"(bytes)
+               : "memory");
+}
+
+#ifdef WN_LAYER_TRACE
+#define TR6(l, e) do { if (blockIdx.x == 0 && step == 2 && (l) < 64) g_trace_gen[(l) * 16 + (e)] = clock64(); } while (0)
+#else
+#define TR6(l, e) do { } while (0)
+#endif
+
+struct V6Args {
+  const uint8_t* wpk;       // [rank][L + n_head][32 KB]
+  int64_t wpk_rank_bytes;
+  uint8_t* ring;            // [cluster][rank][slot][32 KB]
+  int64_t ring_cta_bytes;
+  int spc;                  // streams per cluster (<= 128)
+};
+
+__global__ void __cluster_dims__(V6_CS, 1, 1) __launch_bounds__(V6_THREADS, 1) gen_kernel_v6(GenArgs a, V6Args v) {
+  extern __shared__ uint8_t sm6_raw[];
+  const GenLayout& L = a.lay;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rank = (int)cluster_rank();
+  const int cluster = blockIdx.x / V6_CS;
+  const int stream0 = cluster * v.spc;
+  const int ns = min(v.spc, L.n - stream0);
+  const int NL = L.L;
+  constexpr int Q = 256, R = 64;
+  uint8_t* smp = sm6_raw + ((128 - (tc::smem_u32(sm6_raw) & 127)) & 127);
+  const uint32_t sb = tc::smem_u32(smp);
+  // barriers
+  enum { B_WF = 0, B_WE = 2, B_XDF = 4, B_XDE = 6, B_XR = 8, B_XF = 9, B_GD = 10, B_ZF = 11, B_PD = 13, B_HF = 14, B_HD = 15,
+         B_HFREE = 16, B_CF = 17, B_N = 18 };
+  __shared__ __align__(8) uint64_t s_bar[B_N];
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_len[V6_MAXL], s_base[V6_MAXL];
+  const uint32_t bar0 = tc::smem_u32(&s_bar[0]);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(BAR(B_WF + i), 1);
+      tc::mbar_init(BAR(B_WE + i), 1);
+      tc::mbar_init(BAR(B_XDF + i), 1);
+      tc::mbar_init(BAR(B_XDE + i), 1);
+      tc::mbar_init(BAR(B_ZF + i), 1);
+    }
+    tc::mbar_init(BAR(B_XR), V6_T / 32);
+    tc::mbar_init(BAR(B_XF), 1);
+    tc::mbar_init(BAR(B_GD), 1);
+    tc::mbar_init(BAR(B_PD), 1);
+    tc::mbar_init(BAR(B_HF), 1);
+    tc::mbar_init(BAR(B_HD), 1);
+    tc::mbar_init(BAR(B_HFREE), V6_CS);
+    tc::mbar_init(BAR(B_CF), 1);
+    tc::fence_barrier_init();
+    int base = 0;
+    for (int l = 0; l < NL; ++l) {
+      s_len[l] = a.layers[l].ring_len;
+      s_base[l] = base;
+      base += a.layers[l].ring_len;
+    }
+  }
+  if (warp == 9) tc::tmem_alloc<256>(tc::smem_u32(&s_tmem));
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem = s_tmem;
+  cluster_sync_all();
+
+  const int n_chunks = NL + 2;
+  const uint8_t* wbase = v.wpk + (int64_t)rank * v.wpk_rank_bytes;
+  uint8_t* ring = v.ring + (int64_t)(cluster * V6_CS + rank) * v.ring_cta_bytes;
+
+  if (warp == 8) {
+    // ================= producer: weights ring, x(t-d) tile loads, x(t) tile stores =================
+    if (lane == 0) {
+      uint32_t n_w[2] = {0, 0};      // loads issued per weight stage
+      uint32_t n_xd[2] = {0, 0};     // loads issued per x(t-d) buffer
+      uint32_t n_xr = 0;             // x tiles seen
+      uint32_t it = 0;
+      auto load_w = [&](int chunk) {
+        const uint32_t st = it & 1;
+        if (n_w[st] > 0) tc::mbar_wait(BAR(B_WE + st), (n_w[st] - 1) & 1);
+        tc::mbar_arrive_expect_tx(BAR(B_WF + st), V6_CHUNK);
+        v6_bulk_g2s(sb + V6_OFF_W + st * V6_CHUNK, wbase + (int64_t)chunk * V6_CHUNK, V6_CHUNK, BAR(B_WF + st));
+        ++n_w[st];
+        ++it;
+      };
+      auto load_xd = [&](int l, int64_t t) {
+        const uint32_t b = l & 1;
+        if (n_xd[b] > 0) tc::mbar_wait(BAR(B_XDE + b), (n_xd[b] - 1) & 1);
+        asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");      // the slot's last store (>= 3 groups ago) has landed
+        tc::mbar_arrive_expect_tx(BAR(B_XDF + b), V6_TILE);
+        const int pos = (int)(t % s_len[l]);
+        v6_bulk_g2s(sb + V6_OFF_XD + b * V6_TILE, ring + (int64_t)(s_base[l] + pos) * V6_TILE, V6_TILE, BAR(B_XDF + b));
+        ++n_xd[b];
+      };
+      load_w(0);
+      load_w(1);
+      load_xd(0, a.t0);
+      if (NL > 1) load_xd(1, a.t0);
+      for (int step = 0; step < a.n_steps; ++step) {
+        const int64_t t = a.t0 + step;
+        for (int l = 0; l < NL; ++l) {
+          const uint32_t b = l & 1;
+          tc::mbar_wait(BAR(B_XR), n_xr & 1);                       // x(t) tile of layer l complete
+          ++n_xr;
+          TR6(l, 10);
+          tc::mbar_wait(BAR(B_XDF + b), (n_xd[b] - 1) & 1);         // its slot has been read: roll the ring (faster_wavenet.py:90-91)
+          TR6(l, 11);
+          v6_bulk_s2g(ring + (int64_t)(s_base[l] + (int)(t % s_len[l])) * V6_TILE, sb + V6_OFF_X, V6_TILE);
+          tc::bulk_commit_group();
+          tc::bulk_wait_group_read0();
+          tc::mbar_arrive(BAR(B_XF));
+          TR6(l, 12);
+          if (l + 2 < NL) load_xd(l + 2, t);
+          TR6(l, 13);
+          load_w((l + 2) % n_chunks);                               // chunk l + 2 of this step (the head's two are NL, NL + 1)
+          TR6(l, 14);
+        }
+        const bool more = step + 1 < a.n_steps;
+        for (int hi = 0; hi < 2; ++hi) {
+          if (more) {
+            load_w(hi);                                             // waits for head conv hi to release its stage
+          } else {
+            const uint32_t st = it & 1;
+            tc::mbar_wait(BAR(B_WE + st), (n_w[st] - 1) & 1);
+            ++it;
+          }
+        }
+        if (more) {                                                 // the head tile overlaid the x(t-d) buffers until now
+          load_xd(0, t + 1);
+          if (NL > 1) load_xd(1, t + 1);
+        }
+      }
+      tc::bulk_wait_group0();
+    }
+  } else if (warp == 9) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      uint32_t n_w = 0, n_xr = 0, n_gate[2] = {0, 0}, n_z[2] = {0, 0}, n_h = 0;
+      constexpr uint32_t ID_G2 = v6_idesc(128, 32), ID_G1 = v6_idesc(128, 16), ID_P2 = v6_idesc(128, 128), ID_P1 = v6_idesc(128, 64),
+                         ID_S2 = v6_idesc(128, 64), ID_S1 = v6_idesc(128, 32);
+      for (int step = 0; step < a.n_steps; ++step) {
+        for (int l = 0; l < NL; ++l, ++n_w) {
+          const uint32_t st = n_w & 1, b = l & 1;
+          const uint32_t wst = sb + V6_OFF_W + st * V6_CHUNK;
+          tc::mbar_wait(BAR(B_WF + st), (n_w >> 1) & 1);
+          TR6(l, 5);
+          tc::mbar_wait(BAR(B_XDF + b), n_gate[b] & 1);
+          ++n_gate[b];
+          TR6(l, 6);
+          tc::mbar_wait(BAR(B_XR), n_xr & 1);
+          ++n_xr;
+          TR6(l, 7);
+          tc::tcgen05_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t at = (ks < 4 ? sb + V6_OFF_XD + b * V6_TILE : sb + V6_OFF_X) + (uint32_t)(ks & 3) * 8192;
+            const uint64_t bd = v6_desc(wst + ks * 1024, 512, 128);
+            v6_umma(tmem + V6_TM_GATE, v6_desc(at, 4096, 128), bd, ID_G2, ks > 0);
+            v6_umma(tmem + V6_TM_GATE, v6_desc(at + 2048, 4096, 128), bd, ID_G1, 1u);
+          }
+          tc::umma_commit(BAR(B_GD));
+          tc::umma_commit(BAR(B_XDE + b));
+          v6_wait_cluster(BAR(B_ZF + b), n_z[b] & 1);
+          ++n_z[b];
+          TR6(l, 8);
+          tc::tcgen05_fence_after();
+          const uint32_t zt = sb + V6_OFF_Z + b * V6_TILE;
+          const uint32_t skip_acc = (l % V6_FLUSH) != 0;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ah = v6_desc(zt + ks * 8192, 4096, 128), al = v6_desc(zt + ks * 8192 + 2048, 4096, 128);
+            const uint64_t bp = v6_desc(wst + 8192 + ks * 4096, 2048, 128), bs = v6_desc(wst + 24576 + ks * 2048, 1024, 128);
+            v6_umma(tmem + V6_TM_PROJ, ah, bp, ID_P2, ks > 0);
+            v6_umma(tmem + V6_TM_PROJ, al, bp, ID_P1, 1u);
+            v6_umma(tmem + V6_TM_SKIP, ah, bs, ID_S2, skip_acc | (ks > 0));
+            v6_umma(tmem + V6_TM_SKIP, al, bs, ID_S1, 1u);
+          }
+          tc::umma_commit(BAR(B_PD));
+          tc::umma_commit(BAR(B_WE + st));
+          TR6(l, 9);
+        }
+        for (int hi = 0; hi < 2; ++hi, ++n_w) {
+          const uint32_t st = n_w & 1;
+          const uint32_t wst = sb + V6_OFF_W + st * V6_CHUNK;
+          tc::mbar_wait(BAR(B_WF + st), (n_w >> 1) & 1);
+          v6_wait_cluster(BAR(B_HF), n_h & 1);
+          ++n_h;
+          tc::tcgen05_fence_after();
+#pragma unroll 4
+          for (int ks = 0; ks < 16; ++ks) {
+            const uint64_t bd = v6_desc(wst + ks * 2048, 1024, 128);
+            v6_umma(tmem + V6_TM_HEAD, v6_desc(sb + ks * 8192, 4096, 128), bd, ID_S2, ks > 0);
+            v6_umma(tmem + V6_TM_HEAD, v6_desc(sb + ks * 8192 + 2048, 4096, 128), bd, ID_S1, 1u);
+          }
+          tc::umma_commit(BAR(B_HD));
+          tc::umma_commit(BAR(B_WE + st));
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warps: stream s = TMEM lane, column half hh =================
+    const int q4 = warp & 3, hh = warp >> 2;
+    const int s = 32 * q4 + lane;
+    const int sg = stream0 + min(s, ns - 1);           // dead lanes mirror the last live stream and are never stored
+    const uint32_t tl = tmem + ((uint32_t)(32 * q4) << 16);
+    const uint32_t row_off = (uint32_t)((s >> 3) * 128 + (s & 7) * 16);
+    float* st = a.state;
+    float* cur_logits = st + L.cur_logits;
+    int32_t* idx_hist = (int32_t*)(st + L.idx_hist);
+    const int kc1 = L.kc - 1;
+    const float* emb = st + L.emb;
+    float lg[16], xr[32], sk[16];
+    {
+      const float4* p = reinterpret_cast<const float4*>(cur_logits + (int64_t)sg * Q + 32 * rank + 16 * hh);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v4 = p[i];
+        lg[4 * i] = v4.x, lg[4 * i + 1] = v4.y, lg[4 * i + 2] = v4.z, lg[4 * i + 3] = v4.w;
+      }
+    }
+    int prev = kc1 > 0 ? idx_hist[(int64_t)sg * kc1 + kc1 - 1] : -1;
+    uint32_t n_gd = 0, n_pd = 0, n_xf = 0, n_hd = 0, n_hfree = 0, n_cf = 0;
+    for (int step = 0; step < a.n_steps; ++step) {
+      const int64_t t = a.t0 + step;
+      TRG(41, 0);
+      // ---- 1. sample (generate.py:38-43): partial arg-max over this thread's 16 classes, candidates to every CTA ----
+      {
+        float bv = -INFINITY;
+        int bi = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int qi = 32 * rank + 16 * hh + i;
+          float vv = lg[i];
+          if (a.mode == WN_GEN_SAMPLE) vv += gumbel(a.seed, (uint64_t)sg, (uint64_t)t, (uint32_t)qi);
+          if (vv > bv) bv = vv, bi = qi;
+        }
+        const uint32_t ca = sb + V6_OFF_CAND + (uint32_t)(((rank * 2 + hh) * 128 + s) * 8);
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(ca), "r"(__float_as_uint(bv)), "r"((uint32_t)bi) : "memory");
+        tc::fence_proxy_async();
+        v6_esync();
+        if (tid < V6_CS) {
+          if (tid == rank)
+            tc::mbar_arrive_expect_tx(BAR(B_CF), (V6_CS - 1) * 2048);
+          else
+            bulk_copy_to_cta(map_to_cta(sb + V6_OFF_CAND + rank * 2048, (uint32_t)tid), sb + V6_OFF_CAND + rank * 2048, 2048,
+                             map_to_cta(BAR(B_CF), (uint32_t)tid));
+        }
+        v6_wait_cluster(BAR(B_CF), n_cf & 1);
+        ++n_cf;
+        bv = -INFINITY, bi = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {               // candidate j covers classes 16 j .. 16 j + 15: ascending, first maximum wins
+          uint32_t cv, ci;
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(cv), "=r"(ci) : "r"(sb + V6_OFF_CAND + (uint32_t)((j * 128 + s) * 8)));
+          const float fv = __uint_as_float(cv);
+          if (fv > bv) bv = fv, bi = (int)ci;
+        }
+        if (a.out && rank == 0 && hh == 0 && s < ns) a.out[(int64_t)(stream0 + s) * a.n_steps + step] = bi;
+        // ---- 2. embedding of the new sample = causal conv of the one-hot pair (wavenet.py:565-570) ----
+        const float4* e1 = reinterpret_cast<const float4*>(emb + ((int64_t)kc1 * Q + bi) * R + 32 * hh);
+        const float4* e0 = reinterpret_cast<const float4*>(emb + ((int64_t)0 * Q + max(prev, 0)) * R + 32 * hh);
+        const bool two = kc1 > 0 && prev >= 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 v1 = __ldg(e1 + i);
+          if (two) {
+            const float4 v0 = __ldg(e0 + i);
+            v1.x += v0.x, v1.y += v0.y, v1.z += v0.z, v1.w += v0.w;
+          }
+          xr[4 * i] = v1.x, xr[4 * i + 1] = v1.y, xr[4 * i + 2] = v1.z, xr[4 * i + 3] = v1.w;
+        }
+        prev = bi;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v6_store8(sb + V6_OFF_X + (uint32_t)(4 * hh + j) * 4096 + row_off, xr + 8 * j, V6_ACT);
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(BAR(B_XR));
+#pragma unroll
+      for (int i = 0; i < 16; ++i) sk[i] = 0.f;
+      TRG(41, 1);
+      // ---- 3. residual layers ----
+      for (int l = 0; l < NL; ++l) {
+        const uint32_t b = l & 1;
+        TRG(l, 0);
+        tc::mbar_wait(BAR(B_GD), n_gd & 1);
+        ++n_gd;
+        tc::tcgen05_fence_after();
+        TRG(l, 1);
+        {
+          uint32_t gh[8], gl[8];
+          v6_ld8(tl + V6_TM_GATE + 8 * hh, gh);
+          v6_ld8(tl + V6_TM_GATE + 16 + 8 * hh, gl);
+          tc::tmem_ld_wait();
+          float zv[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float af = (__uint_as_float(gh[c]) + __uint_as_float(gl[c])) * V6_INV;
+            const float ag = (__uint_as_float(gh[4 + c]) + __uint_as_float(gl[4 + c])) * V6_INV;
+            zv[c] = tanh_ex2(af) * (0.5f + 0.5f * tanh_ex2(0.5f * ag)) * V6_ACT;      // wavenet.py:362-364
+          }
+          uint32_t h0, h1, l0, l1;
+          v6_split2(zv[0], zv[1], h0, l0);
+          v6_split2(zv[2], zv[3], h1, l1);
+          const uint32_t za = sb + V6_OFF_Z + b * V6_TILE + (uint32_t)rank * 4096 + row_off + 8 * hh;
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(za), "r"(h0), "r"(h1) : "memory");
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(za + 2048), "r"(l0), "r"(l1) : "memory");
+        }
+        if (l == NL - 1) {                     // peers answer z of the last layer with head slices that land on the x tile:
+          tc::mbar_wait(BAR(B_XF), n_xf & 1);  // the ring store must have read it first
+          ++n_xf;
+        }
+        tc::fence_proxy_async();
+        v6_esync();
+        if (tid < V6_CS) {
+          const uint32_t zs = sb + V6_OFF_Z + b * V6_TILE + (uint32_t)rank * 4096;
+          if (tid == rank)
+            tc::mbar_arrive_expect_tx(BAR(B_ZF + b), (V6_CS - 1) * 4096);
+          else
+            bulk_copy_to_cta(map_to_cta(zs, (uint32_t)tid), zs, 4096, map_to_cta(BAR(B_ZF + b), (uint32_t)tid));
+        }
+        TRG(l, 2);
+        tc::mbar_wait(BAR(B_PD), n_pd & 1);
+        ++n_pd;
+        tc::tcgen05_fence_after();
+        TRG(l, 3);
+        {
+          uint32_t ph[32], pl[32];
+          tc::tmem_ld32(tl + V6_TM_PROJ + 32 * hh, ph);
+          tc::tmem_ld32(tl + V6_TM_PROJ + 64 + 32 * hh, pl);
+          const bool flush = (l % V6_FLUSH) == V6_FLUSH - 1 || l == NL - 1;
+          if (flush) {
+            uint32_t sh[16], sl[16];
+            tc::tmem_ld16(tl + V6_TM_SKIP + 16 * hh, sh);
+            tc::tmem_ld16(tl + V6_TM_SKIP + 32 + 16 * hh, sl);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sk[i] += (__uint_as_float(sh[i]) + __uint_as_float(sl[i])) * V6_INV;   // faster_wavenet.py:100
+          } else {
+            tc::tmem_ld_wait();
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) xr[i] += (__uint_as_float(ph[i]) + __uint_as_float(pl[i])) * V6_INV;     // wavenet.py:354
+        }
+        if (l + 1 < NL) {
+          tc::mbar_wait(BAR(B_XF), n_xf & 1);
+          ++n_xf;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v6_store8(sb + V6_OFF_X + (uint32_t)(4 * hh + j) * 4096 + row_off, xr + 8 * j, V6_ACT);
+          tc::fence_proxy_async();
+          tc::tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(BAR(B_XR));
+        }
+        TRG(l, 4);
+      }
+      // ---- 4. head (faster_wavenet.py:105-113): activation of the skip sum, two 256 x 256 convs split by output rows ----
+      TRG(40, 0);
+      float hv[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) hv[i] = head_act(sk[i], a.head_elu);
+      for (int hi = 0; hi < 2; ++hi) {
+        const uint32_t hs = sb + (uint32_t)rank * 16384;
+        if (hi == 1) {
+          // every CTA must be done reading the first head tile before anyone overwrites it
+          if (tid < V6_CS) v6_remote_arrive(map_to_cta(BAR(B_HFREE), (uint32_t)tid));
+        }
+        v6_store8(hs + (uint32_t)(2 * hh) * 4096 + row_off, hv, V6_ACT);
+        v6_store8(hs + (uint32_t)(2 * hh + 1) * 4096 + row_off, hv + 8, V6_ACT);
+        tc::fence_proxy_async();
+        tc::tcgen05_fence_before();
+        v6_esync();
+        if (tid < V6_CS) {
+          if (hi == 1) v6_wait_cluster(BAR(B_HFREE), n_hfree & 1);
+          if (tid == rank)
+            tc::mbar_arrive_expect_tx(BAR(B_HF), (V6_CS - 1) * 16384);
+          else
+            bulk_copy_to_cta(map_to_cta(hs, (uint32_t)tid), hs, 16384, map_to_cta(BAR(B_HF), (uint32_t)tid));
+        }
+        if (hi == 1) ++n_hfree;
+        float hb[16];                          // head bias of this thread's 16 outputs (loaded under the MMA wait)
+        {
+          const float4* bp = reinterpret_cast<const float4*>(st + L.hb[hi] + 32 * rank + 16 * hh);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 b4 = L.has_hb ? __ldg(bp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            hb[4 * i] = b4.x, hb[4 * i + 1] = b4.y, hb[4 * i + 2] = b4.z, hb[4 * i + 3] = b4.w;
+          }
+        }
+        tc::mbar_wait(BAR(B_HD), n_hd & 1);
+        ++n_hd;
+        tc::tcgen05_fence_after();
+        uint32_t dh[16], dl[16];
+        tc::tmem_ld16(tl + V6_TM_HEAD + 16 * hh, dh);
+        tc::tmem_ld16(tl + V6_TM_HEAD + 32 + 16 * hh, dl);
+        tc::tmem_ld_wait();
+        if (hi == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            hv[i] = head_act(fmaf(__uint_as_float(dh[i]) + __uint_as_float(dl[i]), V6_INV, hb[i]), a.head_elu);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) lg[i] = fmaf(__uint_as_float(dh[i]) + __uint_as_float(dl[i]), V6_INV, hb[i]);
+        }
+        tc::tcgen05_fence_before();
+      }
+      TRG(40, 1);
+    }
+    // ---- state for the next call: logits of the next sample, last index ----
+    if (s < ns) {
+      float4* p = reinterpret_cast<float4*>(cur_logits + (int64_t)(stream0 + s) * Q + 32 * rank + 16 * hh);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) p[i] = make_float4(lg[4 * i], lg[4 * i + 1], lg[4 * i + 2], lg[4 * i + 3]);
+      if (kc1 > 0 && rank == 0 && hh == 0) idx_hist[(int64_t)(stream0 + s) * kc1 + kc1 - 1] = prev;
+    }
+  }
+  __syncwarp();
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 9) tc::tmem_dealloc<256>(tmem);
+  cluster_sync_all();
+}
+
+// ---- packing: generator-layout fp32 matrices [K][N] -> per-rank fp16 hi|lo B tiles (x V6_WSC) ----
+// mode 1: gate (K = 128, N = 128 = f | g): rows of rank r = plane x [half x (f 4 | g 4)];  mode 2: project (all ranks, rows =
+// plane x 64);  mode 3: skip (src columns 64.., rows = plane x 32);  mode 4: head conv (rows = plane x 32)
+__global__ void gen_pack_v6(const float* __restrict__ src, uint8_t* __restrict__ dst, int64_t rank_bytes, int mode, int ldn) {
+  const int K = mode == 1 ? 128 : (mode == 4 ? 256 : 64);
+  const int rows = mode == 1 ? 32 : (mode == 2 ? 128 : 64);
+  const int total = V6_CS * (K / 8) * rows * 8;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int e = i & 7, row = (i >> 3) % rows, kc = (i / (8 * rows)) % (K / 8), r = i / (8 * rows * (K / 8));
+  const int k = kc * 8 + e;
+  int plane, n;
+  if (mode == 1) {
+    plane = row >> 4;
+    const int j = row & 15, half = j >> 3, jj = j & 7, isg = jj >> 2, c4 = jj & 3;
+    n = (isg ? 64 : 0) + 8 * r + 4 * half + c4;
+  } else if (mode == 2) {
+    plane = row >> 6;
+    n = row & 63;
+  } else if (mode == 3) {
+    plane = row >> 5;
+    n = 64 + 32 * r + (row & 31);
+  } else {
+    plane = row >> 5;
+    n = 32 * r + (row & 31);
+  }
+  const float w = src[(int64_t)k * ldn + n] * V6_WSC;
+  const __half hi = __float2half_rn(w);
+  const __half val = plane ? __float2half_rn(w - __half2float(hi)) : hi;
+  reinterpret_cast<__half*>(dst + (int64_t)r * rank_bytes)[((int64_t)kc * rows + row) * 8 + e] = val;
+}
+
+// fp32 rings [stream][slot][64] -> operand tiles, one copy per CTA of the cluster;  and back (from rank 0's copy)
+__global__ void gen_ring_to_v6(const float* __restrict__ ringf, uint8_t* __restrict__ ring6, int64_t cta_bytes, int slot_base,
+                               int len, int n, int spc, int clusters) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (cluster, slot, row, k_core)
+  if (i >= (int64_t)clusters * len * 128 * 8) return;
+  const int kc = (int)(i & 7), row = (int)((i >> 3) & 127);
+  const int slot = (int)((i >> 10) % len), cl = (int)(i / ((int64_t)len * 1024));
+  const int ns = min(spc, n - cl * spc);
+  const int stream = cl * spc + min(row, ns - 1);
+  const float* p = ringf + ((int64_t)stream * len + slot) * 64 + kc * 8;
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v6_split2(p[2 * j] * V6_ACT, p[2 * j + 1] * V6_ACT, h[j], l[j]);
+  const int64_t off = (int64_t)(slot_base + slot) * V6_TILE + kc * 4096 + (row >> 3) * 128 + (row & 7) * 16;
+  for (int r = 0; r < V6_CS; ++r) {
+    uint8_t* d = ring6 + (int64_t)(cl * V6_CS + r) * cta_bytes + off;
+    *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(d + 2048) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+__global__ void gen_ring_from_v6(float* __restrict__ ringf, const uint8_t* __restrict__ ring6, int64_t cta_bytes, int slot_base,
+                                 int len, int n, int spc, int clusters) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)clusters * len * 128 * 8) return;
+  const int kc = (int)(i & 7), row = (int)((i >> 3) & 127);
+  const int slot = (int)((i >> 10) % len), cl = (int)(i / ((int64_t)len * 1024));
+  const int ns = min(spc, n - cl * spc);
+  if (row >= ns) return;
+  const uint8_t* d = ring6 + (int64_t)(cl * V6_CS) * cta_bytes + (int64_t)(slot_base + slot) * V6_TILE + kc * 4096 +
+                     (row >> 3) * 128 + (row & 7) * 16;
+  const uint4 h = *reinterpret_cast<const uint4*>(d), l = *reinterpret_cast<const uint4*>(d + 2048);
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+  float* p = ringf + ((int64_t)(cl * spc + row) * len + slot) * 64 + kc * 8;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[j])), b = __half22float2(*reinterpret_cast<const __half2*>(&lw[j]));
+    p[2 * j] = (a.x + b.x) * (1.f / V6_ACT);
+    p[2 * j + 1] = (a.y + b.y) * (1.f / V6_ACT);
+  }
+}

@@ -959,6 +959,7 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             mbar_wait(full(s0), ph);
             mbar_wait(full(s0 + 1), ph);
             tcgen05_fence_after();
+#ifndef WN_DIAG_GEMM1          // (timing diagnostic WN_DIAG_GEMM1: only the hi.hi products -- is the kernel bound by its MMAs at all?)
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {   // cross terms while the accumulator is small, hi.hi last
               umma_f16(tmem + ab * BN, umma_desc_k_sw128(sh + k4 * 32), umma_desc_k_sw128(sl + SUB + k4 * 32), idesc, !first || k4 > 0);
@@ -967,6 +968,11 @@ tcs_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4)
               umma_f16(tmem + ab * BN, umma_desc_k_sw128(sh + k4 * 32), umma_desc_k_sw128(sh + SUB + k4 * 32), idesc, 1u);
+#else
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              umma_f16(tmem + ab * BN, umma_desc_k_sw128(sh + k4 * 32), umma_desc_k_sw128(sh + SUB + k4 * 32), idesc, !first || k4 > 0);
+#endif
             umma_commit(empty(s0));
             umma_commit(empty(s0 + 1));
             if (last) {
