@@ -223,6 +223,11 @@ int wn_gen_bind_state(wn_gen* g, void* state, int64_t bytes);
  * Win = wn_input_width(); fills the dilation rings; probs_opt[n][Q] gets the
  * last-column softmax; needs a bound training workspace for (n, Win). */
 int wn_gen_prime(wn_gen* g, const float* params, const int32_t* window, float* probs_opt, wn_stream_t s);
+/* The same for the streams [stream0, stream0 + count) only: window[count][Win], probs_opt[count][Q], a training workspace
+ * bound for (count, Win).  Thousands of streams are primed in slices (the full pass keeps ~130 MB of activations per
+ * stream of BASELINE config C); the generator counts as primed once the slice ending at n_streams has run. */
+int wn_gen_prime_part(wn_gen* g, const float* params, const int32_t* window, int stream0, int count, float* probs_opt,
+                      wn_stream_t s);
 /* One _forward_one_step (faster_wavenet.py:50-63) for new samples x_new[n]:
  * probs[n][Q] = last-column softmax (logits when !apply_softmax). */
 int wn_gen_step(wn_gen* g, const float* params, const int32_t* x_new, int apply_softmax, float* probs,

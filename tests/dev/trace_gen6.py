@@ -33,4 +33,9 @@ for l in (0, 1, 2, 3, 10, 11, 20, 28, 29):
           (l, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3],
            r[5] - r[0], r[6] - r[0], r[7] - r[0], r[8] - r[0], r[9] - r[0],
            r[10] - r[0], r[11] - r[0], r[12] - r[0], r[13] - r[0], r[14] - r[0]))
+print("sampling: candidates ready %d | exchange %d | embedding %d | x0 stored %d" % (tr[42][0] - t0, tr[42][1] - tr[42][0], tr[42][2] - tr[42][1], tr[41][1] - tr[42][2]))
+h0 = tr[40][0]
+print("head: h0 sent %d | conv0 done %d | h1 sent %d | conv1 done %d | end %d" % (tr[43][0] - h0, tr[43][1] - h0, tr[43][2] - h0, tr[43][3] - h0, tr[40][1] - h0))
+print("head detail (rel. head start): conv0: stored %d fenced %d synced %d sent %d | conv1: stored %d fenced %d synced %d hfree %d" % tuple(tr[44][i] - h0 for i in range(8)))
+print("sampling detail (rel. step start): fenced %d synced %d | scan done %d" % (tr[45][0] - t0, tr[45][1] - t0, tr[45][2] - t0))
 print("layers total:", tr[40][0] - tr[41][1], " head:", tr[40][1] - tr[40][0], " step:", tr[40][1] - t0)

@@ -2020,12 +2020,35 @@ int gen_v6_convert(wn_gen* g, bool to_v6, cudaStream_t s) {
   return WN_OK;
 }
 
-int launch_gen_v6(wn_gen* g, const GenArgs& a, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    WN_CHECK_CUDA(cudaFuncSetAttribute(gen_kernel_v6, cudaFuncAttributeMaxDynamicSharedMemorySize, V6_SMEM + 128));
-    attr_set = true;
+// co-resident 8-CTA clusters of gen_kernel_v6 (the kernel is persistent over every audio sample: a second wave of
+// clusters would only start when the first has finished)
+int gen_v6_max_clusters() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  if (cudaFuncSetAttribute(gen_kernel_v6, cudaFuncAttributeMaxDynamicSharedMemorySize, V6_SMEM + 128) != cudaSuccess) {
+    cudaGetLastError();
+    return cached = 0;
   }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(V6_CS * 32);
+  cfg.blockDim = dim3(V6_THREADS);
+  cfg.dynamicSmemBytes = V6_SMEM + 128;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = V6_CS;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, gen_kernel_v6, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  return cached = n;
+}
+
+int launch_gen_v6(wn_gen* g, const GenArgs& a, cudaStream_t s) {
   if (!g->ring6_valid) WN_TRY(gen_v6_convert(g, true, s));
   V6Args v;
   v.wpk = reinterpret_cast<const uint8_t*>(g->state + g->lay.wpk6);
@@ -2225,7 +2248,11 @@ extern "C" int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen**
     L.wpk4 = take(L.wpk4_rank * V4_CS_HOST);
   }
   // v6 (streams = MMA M dimension, <= 128 per 8-CTA cluster): the v4 shape with biases in the head only, two head convs
-  g->v6_ok = g->v4_ok && L.n_head == 2 && !L.has_cb && L.L <= 64 && n_streams >= 16;
+  // It pays from ~500 streams on (measured: 107 us per step for up to 128 streams per cluster against 59 / 82 / 132 us for
+  // 1 / 2 / 4 streams per CTA of gen_kernel_v3); WN_GEN_V6=1 forces it from 16 streams (tests), WN_GEN_V6=0 disables it.
+  const char* e6 = getenv("WN_GEN_V6");
+  const int min6 = e6 && atoi(e6) != 0 ? 16 : 512;
+  g->v6_ok = g->v4_ok && L.n_head == 2 && !L.has_cb && L.L >= 16 && L.L <= 64 && n_streams >= min6 && !(e6 && atoi(e6) == 0);
   for (int l = 0; l < L.L && g->v6_ok; ++l) g->v6_ok = !g->layers[l].has_ba && !g->layers[l].has_bb;
   if (g->v6_ok) {
     int spc = 128;
@@ -2233,7 +2260,7 @@ extern "C" int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen**
     if (spc < 8 || spc > 128) spc = 128;
     g->v6_spc = spc;
     g->v6_clusters = (n_streams + spc - 1) / spc;
-    if (g->v6_clusters * V4_CS_HOST > h->sm_count) g->v6_ok = false;      // every cluster resident at once
+    if (g->v6_clusters > gen_v6_max_clusters()) g->v6_ok = false;         // every cluster resident at once
   }
   if (g->v6_ok) {
     int64_t slots = 0;
@@ -2272,13 +2299,24 @@ extern "C" int wn_gen_bind_state(wn_gen* g, void* state, int64_t bytes) {
 }
 
 extern "C" int wn_gen_prime(wn_gen* g, const float* params, const int32_t* window, float* probs_opt, wn_stream_t st) {
+  WN_REQUIRE(g, WN_EINVAL, "null argument");
+  return wn_gen_prime_part(g, params, window, 0, g->lay.n, probs_opt, st);
+}
+
+// Priming of the streams [stream0, stream0 + count): the full pass needs a training workspace of `count` sequences only, so
+// thousands of streams can be primed in slices (the tape of one stream of config C is ~130 MB).  The generator is primed
+// when the slice that ends at n_streams has run; slices may come in any order before that one.
+extern "C" int wn_gen_prime_part(wn_gen* g, const float* params, const int32_t* window, int stream0, int count, float* probs_opt,
+                                 wn_stream_t st) {
   WN_REQUIRE(g && params && window, WN_EINVAL, "null argument");
   WN_REQUIRE(g->state, WN_ESTATE, "no generator state bound");
   wn_handle* h = g->h;
   const GenLayout& L = g->lay;
   const int Win = wn_input_width(h);
-  WN_REQUIRE(h->ws && h->tape.B == L.n && h->tape.W == Win, WN_ESTATE,
-             "wn_gen_prime: bind a training workspace for (B=%d, W=%d) first", L.n, Win);
+  WN_REQUIRE(stream0 >= 0 && count >= 1 && stream0 + count <= L.n, WN_EINVAL, "stream slice [%d, %d) outside 0..%d", stream0,
+             stream0 + count, L.n);
+  WN_REQUIRE(h->ws && h->tape.B == count && h->tape.W == Win, WN_ESTATE,
+             "wn_gen_prime: bind a training workspace for (B=%d, W=%d) first", count, Win);
   cudaStream_t s = (cudaStream_t)st;
   // full pass over the window (faster_wavenet.py:13-47); the priming head is ReLU (Q2).
   // Generation is always exact fp32 so greedy sequences match the reference arithmetic.
@@ -2291,7 +2329,7 @@ extern "C" int wn_gen_prime(wn_gen* g, const float* params, const int32_t* windo
   WN_TRY(rc);
   float* S = g->state;
   const Tape& t = h->tape;
-  WN_CHECK_CUDA(cudaMemcpyAsync(S + L.cur_logits, h->ws + t.hbuf.back(), sizeof(float) * L.n * L.Q,
+  WN_CHECK_CUDA(cudaMemcpyAsync(S + L.cur_logits + (int64_t)stream0 * L.Q, h->ws + t.hbuf.back(), sizeof(float) * count * L.Q,
                                 cudaMemcpyDeviceToDevice, s));
   auto nb = [](int64_t n) { return (unsigned)((n + 255) / 256); };
   // generator-layout weights
@@ -2307,8 +2345,8 @@ extern "C" int wn_gen_prime(wn_gen* g, const float* params, const int32_t* windo
                                                                                     cp.out_ch, 0);
     gen_copy_bias<<<nb(cp.out_ch), 256, 0, s>>>(cp.b_off >= 0 ? params + cp.b_off : nullptr, S + L.cb[i], cp.out_ch);
     if (L.kc > 1)
-      gen_fill_ring<<<nb((int64_t)L.n * (L.kc - 1) * cp.in_ch), 256, 0, s>>>(h->ws + t.cx[i - 1], S + L.chist[i], L.n,
-                                                                              Win, cp.in_ch, L.kc - 1, 1);
+      gen_fill_ring<<<nb((int64_t)count * (L.kc - 1) * cp.in_ch), 256, 0, s>>>(
+          h->ws + t.cx[i - 1], S + L.chist[i] + (int64_t)stream0 * (L.kc - 1) * cp.in_ch, count, Win, cp.in_ch, L.kc - 1, 1);
   }
   for (int l = 0; l < L.L; ++l) {
     const ResLayer& ly = h->layers[l];
@@ -2325,8 +2363,8 @@ extern "C" int wn_gen_prime(wn_gen* g, const float* params, const int32_t* windo
     gen_copy_bias<<<nb(L.R), 256, 0, s>>>(ly.proj.b_off >= 0 ? params + ly.proj.b_off : nullptr, S + o.bb, L.R);
     gen_copy_bias<<<nb(L.S), 256, 0, s>>>(ly.skip.b_off >= 0 ? params + ly.skip.b_off : nullptr, S + o.bb + L.R, L.S);
     if (o.ring_len > 0)
-      gen_fill_ring<<<nb((int64_t)L.n * o.ring_len * L.R), 256, 0, s>>>(h->ws + t.x[l], S + o.ring, L.n, Win, L.R,
-                                                                         o.ring_len, 0);
+      gen_fill_ring<<<nb((int64_t)count * o.ring_len * L.R), 256, 0, s>>>(
+          h->ws + t.x[l], S + o.ring + (int64_t)stream0 * o.ring_len * L.R, count, Win, L.R, o.ring_len, 0);
   }
   for (int i = 0; i < L.n_head; ++i) {
     const ConvParam& cp = h->head[i];
@@ -2335,8 +2373,8 @@ extern "C" int wn_gen_prime(wn_gen* g, const float* params, const int32_t* windo
     gen_copy_bias<<<nb(cp.out_ch), 256, 0, s>>>(cp.b_off >= 0 ? params + cp.b_off : nullptr, S + L.hb[i], cp.out_ch);
   }
   if (L.kc > 1)
-    gen_fill_idx_hist<<<nb((int64_t)L.n * (L.kc - 1)), 256, 0, s>>>(window, (int32_t*)(S + L.idx_hist), L.n, Win,
-                                                                    L.kc - 1);
+    gen_fill_idx_hist<<<nb((int64_t)count * (L.kc - 1)), 256, 0, s>>>(
+        window, (int32_t*)(S + L.idx_hist) + (int64_t)stream0 * (L.kc - 1), count, Win, L.kc - 1);
   WN_CHECK_LAUNCH();
   WN_CHECK_CUDA(cudaMemcpyAsync(S + L.layers_dev, g->layers.data(), sizeof(GenLayerOff) * L.L, cudaMemcpyHostToDevice,
                                 s));
@@ -2370,8 +2408,7 @@ extern "C" int wn_gen_prime(wn_gen* g, const float* params, const int32_t* windo
     for (int l = 0; l < L.L; ++l) {
       uint8_t* d = w6 + (int64_t)l * 32768;
       gen_pack_v6<<<nb(8 * 16 * 32 * 8), 256, 0, s>>>(S + g->layers[l].wa, d, L.wpk6_rank_bytes, 1, 128);
-      gen_pack_v6<<<nb(8 * 8 * 128 * 8), 256, 0, s>>>(S + g->layers[l].wb, d + 8192, L.wpk6_rank_bytes, 2, 320);
-      gen_pack_v6<<<nb(8 * 8 * 64 * 8), 256, 0, s>>>(S + g->layers[l].wb, d + 24576, L.wpk6_rank_bytes, 3, 320);
+      gen_pack_v6<<<nb(8 * 8 * 192 * 8), 256, 0, s>>>(S + g->layers[l].wb, d + 8192, L.wpk6_rank_bytes, 2, 320);
     }
     for (int i = 0; i < L.n_head; ++i)
       gen_pack_v6<<<nb(8 * 32 * 64 * 8), 256, 0, s>>>(S + L.hw[i], w6 + (int64_t)(L.L + i) * 32768, L.wpk6_rank_bytes, 4, 256);
@@ -2379,7 +2416,7 @@ extern "C" int wn_gen_prime(wn_gen* g, const float* params, const int32_t* windo
   }
   g->ring6_valid = false;
   g->ringf_valid = true;
-  g->primed = true;
+  g->primed = stream0 + count == L.n;
   g->t = Win;
   g->steps_done = 0;
   return WN_OK;

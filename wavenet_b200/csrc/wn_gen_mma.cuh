@@ -37,7 +37,7 @@ constexpr int V6_SMEM = 7 * V6_TILE;            // the head's K = 256 tile (128 
 constexpr int V6_FLUSH = 5;                     // layers per TMEM skip-accumulation group
 constexpr int V6_MAXL = 64;
 constexpr float V6_ACT = 8.f, V6_WSC = 16.f, V6_INV = 1.f / (V6_ACT * V6_WSC);
-constexpr uint32_t V6_TM_GATE = 0, V6_TM_PROJ = 32, V6_TM_SKIP = 160, V6_TM_HEAD = 32;
+constexpr uint32_t V6_TM_GATE = 0, V6_TM_PROJ = 64, V6_TM_SKIP = 128, V6_TM_HEAD = 64;   // gate: 2 x 32 columns (layer parity)
 
 __host__ __device__ constexpr uint32_t v6_idesc(int M, int N) {   // kind::f16, fp16 operands, fp32 accumulate, K-major A and B
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -124,6 +124,15 @@ __device__ __forceinline__ void v6_bulk_s2g(void* dst, uint32_t src, uint32_t by
 #else
 #define TR6(l, e) do { } while (0)
 #endif
+
+// ELU / ReLU of the head on the per-step chain: e^v - 1 through one MUFU.EX2 (absolute error < 2e-7; expm1f is ~40
+// instructions, 16 values per thread and head conv)
+__device__ __forceinline__ float v6_head_act(float v, int elu) {
+  if (!elu) return fmaxf(v, 0.f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v, 0.f) * 1.4426950408889634f));
+  return v > 0.f ? v : e - 1.f;
+}
 
 struct V6Args {
   const uint8_t* wpk;       // [rank][L + n_head][32 KB]
@@ -256,27 +265,41 @@ __global__ void __cluster_dims__(V6_CS, 1, 1) __launch_bounds__(V6_THREADS, 1) g
     // ================= MMA issuer =================
     if (lane == 0) {
       uint32_t n_w = 0, n_xr = 0, n_gate[2] = {0, 0}, n_z[2] = {0, 0}, n_h = 0;
-      constexpr uint32_t ID_G2 = v6_idesc(128, 32), ID_G1 = v6_idesc(128, 16), ID_P2 = v6_idesc(128, 128), ID_P1 = v6_idesc(128, 64),
-                         ID_S2 = v6_idesc(128, 64), ID_S1 = v6_idesc(128, 32);
+      constexpr uint32_t ID_G2 = v6_idesc(128, 32), ID_G1 = v6_idesc(128, 16), 
+                         ID_S2 = v6_idesc(128, 64), ID_S1 = v6_idesc(128, 32), ID_PS = v6_idesc(128, 96);
+      // x(t-d) half of a layer's gate GEMM: independent of the sample in flight, issued one layer ahead into the other
+      // gate accumulator
+      auto gate_early = [&](int l, uint32_t chunk) {
+        const uint32_t st = chunk & 1, b = l & 1;
+        const uint32_t wst = sb + V6_OFF_W + st * V6_CHUNK;
+        tc::mbar_wait(BAR(B_WF + st), (chunk >> 1) & 1);
+        tc::mbar_wait(BAR(B_XDF + b), n_gate[b] & 1);
+        ++n_gate[b];
+        tc::tcgen05_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t at = sb + V6_OFF_XD + b * V6_TILE + (uint32_t)ks * 8192;
+          const uint64_t bd = v6_desc(wst + ks * 1024, 512, 128);
+          v6_umma(tmem + V6_TM_GATE + 32 * b, v6_desc(at, 4096, 128), bd, ID_G2, ks > 0);
+          v6_umma(tmem + V6_TM_GATE + 32 * b, v6_desc(at + 2048, 4096, 128), bd, ID_G1, 1u);
+        }
+      };
       for (int step = 0; step < a.n_steps; ++step) {
         for (int l = 0; l < NL; ++l, ++n_w) {
           const uint32_t st = n_w & 1, b = l & 1;
           const uint32_t wst = sb + V6_OFF_W + st * V6_CHUNK;
-          tc::mbar_wait(BAR(B_WF + st), (n_w >> 1) & 1);
-          TR6(l, 5);
-          tc::mbar_wait(BAR(B_XDF + b), n_gate[b] & 1);
-          ++n_gate[b];
+          if (l == 0) gate_early(0, n_w);
           TR6(l, 6);
           tc::mbar_wait(BAR(B_XR), n_xr & 1);
           ++n_xr;
           TR6(l, 7);
           tc::tcgen05_fence_after();
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t at = (ks < 4 ? sb + V6_OFF_XD + b * V6_TILE : sb + V6_OFF_X) + (uint32_t)(ks & 3) * 8192;
+          for (int ks = 4; ks < 8; ++ks) {
+            const uint32_t at = sb + V6_OFF_X + (uint32_t)(ks & 3) * 8192;
             const uint64_t bd = v6_desc(wst + ks * 1024, 512, 128);
-            v6_umma(tmem + V6_TM_GATE, v6_desc(at, 4096, 128), bd, ID_G2, ks > 0);
-            v6_umma(tmem + V6_TM_GATE, v6_desc(at + 2048, 4096, 128), bd, ID_G1, 1u);
+            v6_umma(tmem + V6_TM_GATE + 32 * b, v6_desc(at, 4096, 128), bd, ID_G2, 1u);
+            v6_umma(tmem + V6_TM_GATE + 32 * b, v6_desc(at + 2048, 4096, 128), bd, ID_G1, 1u);
           }
           tc::umma_commit(BAR(B_GD));
           tc::umma_commit(BAR(B_XDE + b));
@@ -285,19 +308,19 @@ __global__ void __cluster_dims__(V6_CS, 1, 1) __launch_bounds__(V6_THREADS, 1) g
           TR6(l, 8);
           tc::tcgen05_fence_after();
           const uint32_t zt = sb + V6_OFF_Z + b * V6_TILE;
-          const uint32_t skip_acc = (l % V6_FLUSH) != 0;
+          const uint32_t grp_acc = (l % V6_FLUSH) != 0;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
+          for (int ks = 0; ks < 4; ++ks) {           // cross terms first, hi.hi last (the accumulator rounds toward zero)
             const uint64_t ah = v6_desc(zt + ks * 8192, 4096, 128), al = v6_desc(zt + ks * 8192 + 2048, 4096, 128);
-            const uint64_t bp = v6_desc(wst + 8192 + ks * 4096, 2048, 128), bs = v6_desc(wst + 24576 + ks * 2048, 1024, 128);
-            v6_umma(tmem + V6_TM_PROJ, ah, bp, ID_P2, ks > 0);
-            v6_umma(tmem + V6_TM_PROJ, al, bp, ID_P1, 1u);
-            v6_umma(tmem + V6_TM_SKIP, ah, bs, ID_S2, skip_acc | (ks > 0));
-            v6_umma(tmem + V6_TM_SKIP, al, bs, ID_S1, 1u);
+            const uint64_t bh = v6_desc(wst + 8192 + ks * 3072, 1536, 128), bl = v6_desc(wst + 8192 + 12288 + ks * 3072, 1536, 128);
+            v6_umma(tmem + V6_TM_PROJ, ah, bl, ID_PS, grp_acc | (ks > 0));
+            v6_umma(tmem + V6_TM_PROJ, al, bh, ID_PS, 1u);
+            v6_umma(tmem + V6_TM_PROJ, ah, bh, ID_PS, 1u);
           }
           tc::umma_commit(BAR(B_PD));
           tc::umma_commit(BAR(B_WE + st));
           TR6(l, 9);
+          if (l + 1 < NL) gate_early(l + 1, n_w + 1);
         }
         for (int hi = 0; hi < 2; ++hi, ++n_w) {
           const uint32_t st = n_w & 1;
@@ -324,6 +347,9 @@ __global__ void __cluster_dims__(V6_CS, 1, 1) __launch_bounds__(V6_THREADS, 1) g
     const int sg = stream0 + min(s, ns - 1);           // dead lanes mirror the last live stream and are never stored
     const uint32_t tl = tmem + ((uint32_t)(32 * q4) << 16);
     const uint32_t row_off = (uint32_t)((s >> 3) * 128 + (s & 7) * 16);
+    // exchanges: thread j < 7 copies this CTA's slice to rank + 1 + j (rotated, so no destination is everybody's first target:
+    // a DSMEM port moves ~17-21 B/clk), thread 7 opens the local phase
+    const uint32_t dst_rank = (uint32_t)((rank + 1 + tid) & (V6_CS - 1));
     float* st = a.state;
     float* cur_logits = st + L.cur_logits;
     int32_t* idx_hist = (int32_t*)(st + L.idx_hist);
@@ -340,6 +366,13 @@ __global__ void __cluster_dims__(V6_CS, 1, 1) __launch_bounds__(V6_THREADS, 1) g
     }
     int prev = kc1 > 0 ? idx_hist[(int64_t)sg * kc1 + kc1 - 1] : -1;
     uint32_t n_gd = 0, n_pd = 0, n_xf = 0, n_hd = 0, n_hfree = 0, n_cf = 0;
+    // Gumbel noise of the NEXT sampling step: independent of the data, computed one value per layer inside the layer loop's
+    // waits (16 x (3 splitmix64 + 2 logf) per thread would otherwise sit on the per-step chain)
+    const bool noisy = a.mode == WN_GEN_SAMPLE;
+    float gum[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      gum[i] = noisy ? gumbel(a.seed, (uint64_t)sg, (uint64_t)a.t0, (uint32_t)(32 * rank + 16 * hh + i)) : 0.f;
     for (int step = 0; step < a.n_steps; ++step) {
       const int64_t t = a.t0 + step;
       TRG(41, 0);
@@ -350,23 +383,26 @@ __global__ void __cluster_dims__(V6_CS, 1, 1) __launch_bounds__(V6_THREADS, 1) g
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int qi = 32 * rank + 16 * hh + i;
-          float vv = lg[i];
-          if (a.mode == WN_GEN_SAMPLE) vv += gumbel(a.seed, (uint64_t)sg, (uint64_t)t, (uint32_t)qi);
+          const float vv = lg[i] + gum[i];
           if (vv > bv) bv = vv, bi = qi;
         }
         const uint32_t ca = sb + V6_OFF_CAND + (uint32_t)(((rank * 2 + hh) * 128 + s) * 8);
         asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(ca), "r"(__float_as_uint(bv)), "r"((uint32_t)bi) : "memory");
+        TRG(42, 0);
         tc::fence_proxy_async();
+        TRG(45, 0);
         v6_esync();
+        TRG(45, 1);
         if (tid < V6_CS) {
-          if (tid == rank)
+          if (tid == V6_CS - 1)
             tc::mbar_arrive_expect_tx(BAR(B_CF), (V6_CS - 1) * 2048);
           else
-            bulk_copy_to_cta(map_to_cta(sb + V6_OFF_CAND + rank * 2048, (uint32_t)tid), sb + V6_OFF_CAND + rank * 2048, 2048,
-                             map_to_cta(BAR(B_CF), (uint32_t)tid));
+            bulk_copy_to_cta(map_to_cta(sb + V6_OFF_CAND + rank * 2048, dst_rank), sb + V6_OFF_CAND + rank * 2048, 2048,
+                             map_to_cta(BAR(B_CF), dst_rank));
         }
         v6_wait_cluster(BAR(B_CF), n_cf & 1);
         ++n_cf;
+        TRG(42, 1);
         bv = -INFINITY, bi = 0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {               // candidate j covers classes 16 j .. 16 j + 15: ascending, first maximum wins
@@ -375,6 +411,7 @@ __global__ void __cluster_dims__(V6_CS, 1, 1) __launch_bounds__(V6_THREADS, 1) g
           const float fv = __uint_as_float(cv);
           if (fv > bv) bv = fv, bi = (int)ci;
         }
+        TRG(45, 2);
         if (a.out && rank == 0 && hh == 0 && s < ns) a.out[(int64_t)(stream0 + s) * a.n_steps + step] = bi;
         // ---- 2. embedding of the new sample = causal conv of the one-hot pair (wavenet.py:565-570) ----
         const float4* e1 = reinterpret_cast<const float4*>(emb + ((int64_t)kc1 * Q + bi) * R + 32 * hh);
@@ -390,6 +427,7 @@ __global__ void __cluster_dims__(V6_CS, 1, 1) __launch_bounds__(V6_THREADS, 1) g
           xr[4 * i] = v1.x, xr[4 * i + 1] = v1.y, xr[4 * i + 2] = v1.z, xr[4 * i + 3] = v1.w;
         }
         prev = bi;
+        TRG(42, 2);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) v6_store8(sb + V6_OFF_X + (uint32_t)(4 * hh + j) * 4096 + row_off, xr + 8 * j, V6_ACT);
@@ -409,8 +447,8 @@ __global__ void __cluster_dims__(V6_CS, 1, 1) __launch_bounds__(V6_THREADS, 1) g
         TRG(l, 1);
         {
           uint32_t gh[8], gl[8];
-          v6_ld8(tl + V6_TM_GATE + 8 * hh, gh);
-          v6_ld8(tl + V6_TM_GATE + 16 + 8 * hh, gl);
+          v6_ld8(tl + V6_TM_GATE + 32 * b + 8 * hh, gh);
+          v6_ld8(tl + V6_TM_GATE + 32 * b + 16 + 8 * hh, gl);
           tc::tmem_ld_wait();
           float zv[4];
 #pragma unroll
@@ -434,39 +472,49 @@ __global__ void __cluster_dims__(V6_CS, 1, 1) __launch_bounds__(V6_THREADS, 1) g
         v6_esync();
         if (tid < V6_CS) {
           const uint32_t zs = sb + V6_OFF_Z + b * V6_TILE + (uint32_t)rank * 4096;
-          if (tid == rank)
+          if (tid == V6_CS - 1)
             tc::mbar_arrive_expect_tx(BAR(B_ZF + b), (V6_CS - 1) * 4096);
           else
-            bulk_copy_to_cta(map_to_cta(zs, (uint32_t)tid), zs, 4096, map_to_cta(BAR(B_ZF + b), (uint32_t)tid));
+            bulk_copy_to_cta(map_to_cta(zs, dst_rank), zs, 4096, map_to_cta(BAR(B_ZF + b), dst_rank));
         }
         TRG(l, 2);
+        if (noisy && l < 16) {
+          const float g = gumbel(a.seed, (uint64_t)sg, (uint64_t)(t + 1), (uint32_t)(32 * rank + 16 * hh + l));
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (i == l) gum[i] = g;
+        }
         tc::mbar_wait(BAR(B_PD), n_pd & 1);
         ++n_pd;
         tc::tcgen05_fence_after();
         TRG(l, 3);
+        float xn[32];
         {
-          uint32_t ph[32], pl[32];
+          uint32_t ph[32];
           tc::tmem_ld32(tl + V6_TM_PROJ + 32 * hh, ph);
-          tc::tmem_ld32(tl + V6_TM_PROJ + 64 + 32 * hh, pl);
           const bool flush = (l % V6_FLUSH) == V6_FLUSH - 1 || l == NL - 1;
           if (flush) {
-            uint32_t sh[16], sl[16];
+            uint32_t sh[16];
             tc::tmem_ld16(tl + V6_TM_SKIP + 16 * hh, sh);
-            tc::tmem_ld16(tl + V6_TM_SKIP + 32 + 16 * hh, sl);
             tc::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) sk[i] += (__uint_as_float(sh[i]) + __uint_as_float(sl[i])) * V6_INV;   // faster_wavenet.py:100
+            for (int i = 0; i < 16; ++i) sk[i] = fmaf(__uint_as_float(sh[i]), V6_INV, sk[i]);     // faster_wavenet.py:100
           } else {
             tc::tmem_ld_wait();
           }
+          // the projection accumulates in TMEM over a group of V6_FLUSH layers: x = x(group start) + sum (wavenet.py:354)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) xr[i] += (__uint_as_float(ph[i]) + __uint_as_float(pl[i])) * V6_INV;     // wavenet.py:354
+          for (int i = 0; i < 32; ++i) xn[i] = fmaf(__uint_as_float(ph[i]), V6_INV, xr[i]);
+          if (flush) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) xr[i] = xn[i];
+          }
         }
         if (l + 1 < NL) {
           tc::mbar_wait(BAR(B_XF), n_xf & 1);
           ++n_xf;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v6_store8(sb + V6_OFF_X + (uint32_t)(4 * hh + j) * 4096 + row_off, xr + 8 * j, V6_ACT);
+          for (int j = 0; j < 4; ++j) v6_store8(sb + V6_OFF_X + (uint32_t)(4 * hh + j) * 4096 + row_off, xn + 8 * j, V6_ACT);
           tc::fence_proxy_async();
           tc::tcgen05_fence_before();
           __syncwarp();
@@ -478,7 +526,7 @@ __global__ void __cluster_dims__(V6_CS, 1, 1) __launch_bounds__(V6_THREADS, 1) g
       TRG(40, 0);
       float hv[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) hv[i] = head_act(sk[i], a.head_elu);
+      for (int i = 0; i < 16; ++i) hv[i] = v6_head_act(sk[i], a.head_elu);
       for (int hi = 0; hi < 2; ++hi) {
         const uint32_t hs = sb + (uint32_t)rank * 16384;
         if (hi == 1) {
@@ -487,17 +535,22 @@ __global__ void __cluster_dims__(V6_CS, 1, 1) __launch_bounds__(V6_THREADS, 1) g
         }
         v6_store8(hs + (uint32_t)(2 * hh) * 4096 + row_off, hv, V6_ACT);
         v6_store8(hs + (uint32_t)(2 * hh + 1) * 4096 + row_off, hv + 8, V6_ACT);
+        TRG(44, 4 * hi);
         tc::fence_proxy_async();
         tc::tcgen05_fence_before();
+        TRG(44, 4 * hi + 1);
         v6_esync();
+        TRG(44, 4 * hi + 2);
         if (tid < V6_CS) {
           if (hi == 1) v6_wait_cluster(BAR(B_HFREE), n_hfree & 1);
-          if (tid == rank)
+          TRG(44, 4 * hi + 3);
+          if (tid == V6_CS - 1)
             tc::mbar_arrive_expect_tx(BAR(B_HF), (V6_CS - 1) * 16384);
           else
-            bulk_copy_to_cta(map_to_cta(hs, (uint32_t)tid), hs, 16384, map_to_cta(BAR(B_HF), (uint32_t)tid));
+            bulk_copy_to_cta(map_to_cta(hs, dst_rank), hs, 16384, map_to_cta(BAR(B_HF), dst_rank));
         }
         if (hi == 1) ++n_hfree;
+        TRG(43, 2 * hi);
         float hb[16];                          // head bias of this thread's 16 outputs (loaded under the MMA wait)
         {
           const float4* bp = reinterpret_cast<const float4*>(st + L.hb[hi] + 32 * rank + 16 * hh);
@@ -509,6 +562,7 @@ __global__ void __cluster_dims__(V6_CS, 1, 1) __launch_bounds__(V6_THREADS, 1) g
         }
         tc::mbar_wait(BAR(B_HD), n_hd & 1);
         ++n_hd;
+        TRG(43, 2 * hi + 1);
         tc::tcgen05_fence_after();
         uint32_t dh[16], dl[16];
         tc::tmem_ld16(tl + V6_TM_HEAD + 16 * hh, dh);
@@ -517,7 +571,7 @@ __global__ void __cluster_dims__(V6_CS, 1, 1) __launch_bounds__(V6_THREADS, 1) g
         if (hi == 0) {
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            hv[i] = head_act(fmaf(__uint_as_float(dh[i]) + __uint_as_float(dl[i]), V6_INV, hb[i]), a.head_elu);
+            hv[i] = v6_head_act(fmaf(__uint_as_float(dh[i]) + __uint_as_float(dl[i]), V6_INV, hb[i]), a.head_elu);
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) lg[i] = fmaf(__uint_as_float(dh[i]) + __uint_as_float(dl[i]), V6_INV, hb[i]);
@@ -542,35 +596,37 @@ __global__ void __cluster_dims__(V6_CS, 1, 1) __launch_bounds__(V6_THREADS, 1) g
 }
 
 // ---- packing: generator-layout fp32 matrices [K][N] -> per-rank fp16 hi|lo B tiles (x V6_WSC) ----
-// mode 1: gate (K = 128, N = 128 = f | g): rows of rank r = plane x [half x (f 4 | g 4)];  mode 2: project (all ranks, rows =
-// plane x 64);  mode 3: skip (src columns 64.., rows = plane x 32);  mode 4: head conv (rows = plane x 32)
+// mode 1: gate (K = 128, N = 128 = f | g): rows of rank r = plane x [half x (f 4 | g 4)];  mode 2: project (64 rows, every
+// rank) | skip (this rank's 32 rows) as one N = 96 tile per plane;  mode 4: head conv (rows = plane x 32)
 __global__ void gen_pack_v6(const float* __restrict__ src, uint8_t* __restrict__ dst, int64_t rank_bytes, int mode, int ldn) {
   const int K = mode == 1 ? 128 : (mode == 4 ? 256 : 64);
-  const int rows = mode == 1 ? 32 : (mode == 2 ? 128 : 64);
+  const int rows = mode == 1 ? 32 : (mode == 2 ? 192 : 64);
   const int total = V6_CS * (K / 8) * rows * 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int e = i & 7, row = (i >> 3) % rows, kc = (i / (8 * rows)) % (K / 8), r = i / (8 * rows * (K / 8));
   const int k = kc * 8 + e;
   int plane, n;
-  if (mode == 1) {
+  int64_t off;                                 // element offset inside the rank's block
+  if (mode == 1) {                             // [k_core 16][hi 16 | lo 16]
     plane = row >> 4;
     const int j = row & 15, half = j >> 3, jj = j & 7, isg = jj >> 2, c4 = jj & 3;
     n = (isg ? 64 : 0) + 8 * r + 4 * half + c4;
-  } else if (mode == 2) {
-    plane = row >> 6;
-    n = row & 63;
-  } else if (mode == 3) {
-    plane = row >> 5;
-    n = 64 + 32 * r + (row & 31);
-  } else {
+    off = ((int64_t)kc * rows + row) * 8 + e;
+  } else if (mode == 2) {                      // hi block [k_core 8][project 64 | skip 32], then the lo block
+    plane = row / 96;
+    const int j = row % 96;
+    n = j < 64 ? j : 64 + 32 * r + (j - 64);
+    off = (int64_t)plane * (8 * 96 * 8) + ((int64_t)kc * 96 + j) * 8 + e;
+  } else {                                     // head conv: [k_core 32][hi 32 | lo 32]
     plane = row >> 5;
     n = 32 * r + (row & 31);
+    off = ((int64_t)kc * rows + row) * 8 + e;
   }
   const float w = src[(int64_t)k * ldn + n] * V6_WSC;
   const __half hi = __float2half_rn(w);
   const __half val = plane ? __float2half_rn(w - __half2float(hi)) : hi;
-  reinterpret_cast<__half*>(dst + (int64_t)r * rank_bytes)[((int64_t)kc * rows + row) * 8 + e] = val;
+  reinterpret_cast<__half*>(dst + (int64_t)r * rank_bytes)[off] = val;
 }
 
 // fp32 rings [stream][slot][64] -> operand tiles, one copy per CTA of the cluster;  and back (from rank 0's copy)

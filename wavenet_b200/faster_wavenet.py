@@ -25,6 +25,8 @@ from .wavenet import WaveNet, Variable, _ptr, _stream
 class FasterWaveNet(WaveNet):
     """faster_wavenet.py:11-113."""
 
+    PRIME_SLICE = 256                     # streams per priming pass (the pass keeps ~130 MB of activations per config-C stream)
+
     def __init__(self, params, seed=None, head_act="reference"):
         WaveNet.__init__(self, params, seed)
         self.head_act = head_act          # "reference": ReLU on the priming call, ELU afterwards (Q2); "relu"
@@ -65,11 +67,15 @@ class FasterWaveNet(WaveNet):
         n, W = idx.shape
         if W != self.input_width:
             raise Exception("priming window must be input_width = {} samples wide".format(self.input_width))
-        self._bind(n, W)
         self._ensure_gen(n)
         self._keep["idx"] = idx
         probs = torch.empty((n, self.params.quantization_steps), dtype=torch.float32, device=self._device)
-        check(self._libh.wn_gen_prime(self._gen, _ptr(self._params), _ptr(idx), _ptr(probs), _stream()))
+        # the full pass keeps the activation tape of every primed stream: slices of PRIME_SLICE streams bound the workspace
+        for s0 in range(0, n, self.PRIME_SLICE):
+            cnt = min(self.PRIME_SLICE, n - s0)
+            self._bind(cnt, W)
+            check(self._libh.wn_gen_prime_part(self._gen, _ptr(self._params), _ptr(idx[s0:s0 + cnt]), s0, cnt,
+                                               _ptr(probs[s0:s0 + cnt]), _stream()))
         self.prev_causal_outputs = True
         return probs
 
