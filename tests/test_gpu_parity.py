@@ -443,6 +443,62 @@ def test_many_stream_cluster_generator(n):
     assert (f != want).any(axis=1).sum() <= 1 and (f != c).any(axis=1).sum() <= 1
 
 
+@pytest.mark.parametrize("n", [24, 130])
+def test_tensor_core_generator(n):
+    """gen_kernel_v6 (tcgen05 generator: streams are the MMA M dimension, up to 128 per 8-CTA cluster; automatic from 512
+    streams, forced here with WN_GEN_V6=1) at config-C depth: greedy sequences against the fp64 ring oracle and gen_kernel_v3,
+    sampled sequences against gen_kernel_v3 (same counter RNG), continuation across wn_gen_run calls (the state moves between
+    the fp32 rings and the operand-tile rings), a partially filled second cluster (n = 130), sliced priming, and a shard of
+    the streams generating what it generates inside the full set."""
+    import os
+    from wavenet_b200 import _lib
+    from wavenet_b200._lib import check
+    from wavenet_b200.faster_wavenet import FasterWaveNet
+    from wavenet_b200.wavenet import _ptr, _stream
+    cfg = make_cfg("C")
+    w = O.init_weights(cfg, np.random.default_rng(7), np.float64)
+    window = np.random.default_rng(3).integers(0, 256, (n, O.input_width(cfg))).astype(np.int32)
+
+    def run(win, parts, v6, mode=_lib.WN_GEN_GREEDY, step_between=False):
+        os.environ["WN_GEN_V6"] = "1" if v6 else "0"
+        try:
+            net = make_net(cfg, w, faster=True, head_act="reference")
+            net.prime(win)
+            outs = []
+            for i, steps in enumerate(parts):
+                out = torch.empty((win.shape[0], steps), dtype=torch.int32, device="cuda")
+                check(net._libh.wn_gen_run(net._gen, _ptr(net._params), steps, mode, 11, _ptr(out), _stream()))
+                outs.append(out.cpu().numpy())
+            return np.concatenate(outs, axis=1)
+        finally:
+            os.environ.pop("WN_GEN_V6", None)
+
+    steps = 40
+    a = run(window, [steps], True)
+    want = O.RingGenerator(cfg, w, n, head_act="reference", dtype=np.float64).generate_greedy(window, steps)
+    assert (a != want).any(axis=1).sum() <= 1, (a != want).any(axis=1)      # a near tie may flip one arg-max
+    c = run(window, [steps], False)
+    assert (a != c).any(axis=1).sum() <= 1
+    # 9 + 4 + 27: the middle call is too short for v6 (< 8 steps) and runs on gen_kernel_v3 -> both ring conversions
+    b = run(window, [9, 4, 27], True)
+    assert (a != b).any(axis=1).sum() <= 1
+    b2 = run(window, [13, 27], True)
+    assert np.array_equal(a, b2)
+    s6 = run(window, [steps], True, _lib.WN_GEN_SAMPLE)
+    s3 = run(window, [steps], False, _lib.WN_GEN_SAMPLE)
+    assert (s6 != s3).any(axis=1).sum() <= 1
+    lo, hi = 3, min(n, 21)
+    d = run(window[lo:hi], [steps], True)
+    assert np.array_equal(d, a[lo:hi])
+    old = FasterWaveNet.PRIME_SLICE
+    FasterWaveNet.PRIME_SLICE = 16                                           # priming in slices == priming in one pass
+    try:
+        e = run(window, [steps], True)
+    finally:
+        FasterWaveNet.PRIME_SLICE = old
+    assert np.array_equal(e, a)
+
+
 def test_device_crop_batch_matches_reference_create_batch():
     """train_audio/train.py:14-22 restated vs wn_crop_batch with the same np.random stream."""
     rng = np.random.default_rng(0)

@@ -38,6 +38,7 @@ constexpr int V6_FLUSH = 5;                     // layers per TMEM skip-accumula
 constexpr int V6_MAXL = 64;
 constexpr float V6_ACT = 8.f, V6_WSC = 16.f, V6_INV = 1.f / (V6_ACT * V6_WSC);
 constexpr uint32_t V6_TM_GATE = 0, V6_TM_PROJ = 64, V6_TM_SKIP = 128, V6_TM_HEAD = 64;   // gate: 2 x 32 columns (layer parity)
+constexpr uint32_t V6_TM_XH = 160, V6_TM_XL = 192;   // x(t) as the A operand IN TMEM: fp16 pairs, 32 columns per plane
 
 __host__ __device__ constexpr uint32_t v6_idesc(int M, int N) {   // kind::f16, fp16 operands, fp32 accumulate, K-major A and B
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -86,6 +87,51 @@ __device__ __forceinline__ void v6_store8(uint32_t addr, const float* v, float s
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + 2048), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
 }
+// A operand from TENSOR MEMORY (128 lanes x 8 columns of fp16 pairs per K = 16 step): no shared-memory read at all
+__device__ __forceinline__ void v6_umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void v6_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void v6_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 32 channels of one stream -> (1) the TMEM A operand of the gate GEMM, signalled to the MMA thread at once; (2) the
+// shared-memory tile the producer rolls into the dilation ring (off the chain)
+__device__ __forceinline__ void v6_publish_x(const float* x, uint32_t tm_lane, int hh, uint32_t xs, uint32_t bar_xt, uint32_t bar_xr, int lane) {
+  uint32_t h[16], l[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v6_split2(x[2 * i] * V6_ACT, x[2 * i + 1] * V6_ACT, h[i], l[i]);
+  v6_st16(tm_lane + V6_TM_XH + 16 * hh, h);
+  v6_st16(tm_lane + V6_TM_XL + 16 * hh, l);
+  v6_st_wait();
+  tc::tcgen05_fence_before();
+  __syncwarp();
+  if (lane == 0) tc::mbar_arrive(bar_xt);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xs + j * 4096), "r"(h[4 * j]), "r"(h[4 * j + 1]), "r"(h[4 * j + 2]),
+                 "r"(h[4 * j + 3])
+                 : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xs + j * 4096 + 2048), "r"(l[4 * j]), "r"(l[4 * j + 1]), "r"(l[4 * j + 2]),
+                 "r"(l[4 * j + 3])
+                 : "memory");
+  }
+  tc::fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) tc::mbar_arrive(bar_xr);
+}
+
 // waits that acquire at cluster scope (payload written by a peer's bulk copy / a peer's remote arrive)
 __device__ __forceinline__ void v6_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
@@ -156,7 +202,7 @@ __global__ void __cluster_dims__(V6_CS, 1, 1) __launch_bounds__(V6_THREADS, 1) g
   const uint32_t sb = tc::smem_u32(smp);
   // barriers
   enum { B_WF = 0, B_WE = 2, B_XDF = 4, B_XDE = 6, B_XR = 8, B_XF = 9, B_GD = 10, B_ZF = 11, B_PD = 13, B_HF = 14, B_HD = 15,
-         B_HFREE = 16, B_CF = 17, B_N = 18 };
+         B_HFREE = 16, B_CF = 17, B_XT = 18, B_N = 19 };
   __shared__ __align__(8) uint64_t s_bar[B_N];
   __shared__ uint32_t s_tmem;
   __shared__ int s_len[V6_MAXL], s_base[V6_MAXL];
@@ -171,6 +217,7 @@ __global__ void __cluster_dims__(V6_CS, 1, 1) __launch_bounds__(V6_THREADS, 1) g
       tc::mbar_init(BAR(B_ZF + i), 1);
     }
     tc::mbar_init(BAR(B_XR), V6_T / 32);
+    tc::mbar_init(BAR(B_XT), V6_T / 32);
     tc::mbar_init(BAR(B_XF), 1);
     tc::mbar_init(BAR(B_GD), 1);
     tc::mbar_init(BAR(B_PD), 1);
@@ -290,16 +337,15 @@ __global__ void __cluster_dims__(V6_CS, 1, 1) __launch_bounds__(V6_THREADS, 1) g
           const uint32_t wst = sb + V6_OFF_W + st * V6_CHUNK;
           if (l == 0) gate_early(0, n_w);
           TR6(l, 6);
-          tc::mbar_wait(BAR(B_XR), n_xr & 1);
+          tc::mbar_wait(BAR(B_XT), n_xr & 1);
           ++n_xr;
           TR6(l, 7);
           tc::tcgen05_fence_after();
 #pragma unroll
           for (int ks = 4; ks < 8; ++ks) {
-            const uint32_t at = sb + V6_OFF_X + (uint32_t)(ks & 3) * 8192;
             const uint64_t bd = v6_desc(wst + ks * 1024, 512, 128);
-            v6_umma(tmem + V6_TM_GATE + 32 * b, v6_desc(at, 4096, 128), bd, ID_G2, 1u);
-            v6_umma(tmem + V6_TM_GATE + 32 * b, v6_desc(at + 2048, 4096, 128), bd, ID_G1, 1u);
+            v6_umma_ts(tmem + V6_TM_GATE + 32 * b, tmem + V6_TM_XH + 8 * (ks & 3), bd, ID_G2, 1u);
+            v6_umma_ts(tmem + V6_TM_GATE + 32 * b, tmem + V6_TM_XL + 8 * (ks & 3), bd, ID_G1, 1u);
           }
           tc::umma_commit(BAR(B_GD));
           tc::umma_commit(BAR(B_XDE + b));
@@ -417,23 +463,19 @@ __global__ void __cluster_dims__(V6_CS, 1, 1) __launch_bounds__(V6_THREADS, 1) g
         const float4* e1 = reinterpret_cast<const float4*>(emb + ((int64_t)kc1 * Q + bi) * R + 32 * hh);
         const float4* e0 = reinterpret_cast<const float4*>(emb + ((int64_t)0 * Q + max(prev, 0)) * R + 32 * hh);
         const bool two = kc1 > 0 && prev >= 0;
+        float4 v1[8], v0[8];                       // all sixteen loads in flight before the first use
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 v1 = __ldg(e1 + i);
-          if (two) {
-            const float4 v0 = __ldg(e0 + i);
-            v1.x += v0.x, v1.y += v0.y, v1.z += v0.z, v1.w += v0.w;
-          }
-          xr[4 * i] = v1.x, xr[4 * i + 1] = v1.y, xr[4 * i + 2] = v1.z, xr[4 * i + 3] = v1.w;
-        }
+        for (int i = 0; i < 8; ++i) v1[i] = __ldg(e1 + i);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v0[i] = two ? __ldg(e0 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          xr[4 * i] = v1[i].x + v0[i].x, xr[4 * i + 1] = v1[i].y + v0[i].y, xr[4 * i + 2] = v1[i].z + v0[i].z,
+                 xr[4 * i + 3] = v1[i].w + v0[i].w;
         prev = bi;
         TRG(42, 2);
       }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v6_store8(sb + V6_OFF_X + (uint32_t)(4 * hh + j) * 4096 + row_off, xr + 8 * j, V6_ACT);
-      tc::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(BAR(B_XR));
+      v6_publish_x(xr, tl, hh, sb + V6_OFF_X + (uint32_t)(4 * hh) * 4096 + row_off, BAR(B_XT), BAR(B_XR), lane);
 #pragma unroll
       for (int i = 0; i < 16; ++i) sk[i] = 0.f;
       TRG(41, 1);
@@ -513,12 +555,7 @@ __global__ void __cluster_dims__(V6_CS, 1, 1) __launch_bounds__(V6_THREADS, 1) g
         if (l + 1 < NL) {
           tc::mbar_wait(BAR(B_XF), n_xf & 1);
           ++n_xf;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) v6_store8(sb + V6_OFF_X + (uint32_t)(4 * hh + j) * 4096 + row_off, xn + 8 * j, V6_ACT);
-          tc::fence_proxy_async();
-          tc::tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(BAR(B_XR));
+          v6_publish_x(xn, tl, hh, sb + V6_OFF_X + (uint32_t)(4 * hh) * 4096 + row_off, BAR(B_XT), BAR(B_XR), lane);
         }
         TRG(l, 4);
       }
