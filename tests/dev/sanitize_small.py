@@ -38,3 +38,13 @@ if what in ("all", "gen"):
         out = net.generate(win, 6, mode="greedy")
         torch.cuda.synchronize()
         print("gen", tag, out[0].tolist(), flush=True)
+if what in ("gen6",):
+    # gen_kernel_v6 (tensor-core generator): one partially filled cluster, forced below its automatic threshold
+    os.environ["WN_GEN_V6"] = "1"
+    cfg = make_cfg("C")
+    w = O.init_weights(cfg, np.random.default_rng(0), np.float32)
+    net = make_net(cfg, w, faster=True)
+    win = np.random.default_rng(2).integers(0, 256, (20, O.input_width(cfg))).astype(np.int32)
+    out = net.generate(win, 9, mode="sample")
+    torch.cuda.synchronize()
+    print("gen v6 tensor-core", out[0].tolist(), flush=True)
