@@ -73,7 +73,7 @@ struct wn_gen {
   bool v4_ok = false;                 // config-C shape: the cluster generators' packed weight slices exist (v4: one 8-CTA
                                       // cluster per stream while they are all co-resident; v5: 16 streams per cluster)
   bool v6_ok = false;                 // tensor-core generator (gen_kernel_v6): config-C shape without biases, >= 16 streams
-  int v6_spc = 128, v6_clusters = 0;  // streams per 8-CTA cluster, clusters
+  int v6_spc = 128, v6_clusters = 0, v6_cs = 8;  // streams per cluster, clusters, CTAs per cluster (8 or 4)
   bool ring6_valid = false;           // the v6 operand-tile rings hold the current state
   bool ringf_valid = true;            // the fp32 rings hold the current state
 };
@@ -2010,42 +2010,65 @@ int gen_v6_convert(wn_gen* g, bool to_v6, cudaStream_t s) {
     const int64_t items = (int64_t)g->v6_clusters * o.ring_len * 1024;
     const unsigned nb = (unsigned)((items + 255) / 256);
     if (to_v6)
-      gen_ring_to_v6<<<nb, 256, 0, s>>>(g->state + o.ring, ring6, L.ring6_cta_bytes, base, o.ring_len, L.n, g->v6_spc, g->v6_clusters);
+      gen_ring_to_v6<<<nb, 256, 0, s>>>(g->state + o.ring, ring6, L.ring6_cta_bytes, base, o.ring_len, L.n, g->v6_spc, g->v6_clusters,
+                                        g->v6_cs);
     else
       gen_ring_from_v6<<<nb, 256, 0, s>>>(g->state + o.ring, ring6, L.ring6_cta_bytes, base, o.ring_len, L.n, g->v6_spc,
-                                          g->v6_clusters);
+                                          g->v6_clusters, g->v6_cs);
     base += o.ring_len;
   }
   WN_CHECK_LAUNCH();
   return WN_OK;
 }
 
-// co-resident 8-CTA clusters of gen_kernel_v6 (the kernel is persistent over every audio sample: a second wave of
-// clusters would only start when the first has finished)
-int gen_v6_max_clusters() {
+// co-resident clusters of gen_kernel_v6<CS> (the kernel is persistent over every audio sample: a second wave of clusters
+// would only start when the first has finished)
+template <int CS>
+int gen_v6_max_clusters_cs() {
   static int cached = -1;
   if (cached >= 0) return cached;
-  if (cudaFuncSetAttribute(gen_kernel_v6, cudaFuncAttributeMaxDynamicSharedMemorySize, V6_SMEM + 128) != cudaSuccess) {
+  const int smem = V6C<CS>::SMEM + 128;
+  if (cudaFuncSetAttribute(gen_kernel_v6<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
     cudaGetLastError();
     return cached = 0;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(V6_CS * 32);
+  cfg.gridDim = dim3(CS * 64);
   cfg.blockDim = dim3(V6_THREADS);
-  cfg.dynamicSmemBytes = V6_SMEM + 128;
+  cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = V6_CS;
+  at[0].val.clusterDim.x = CS;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, gen_kernel_v6, &cfg) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveClusters(&n, gen_kernel_v6<CS>, &cfg) != cudaSuccess) {
     cudaGetLastError();
     n = 0;
   }
   return cached = n;
+}
+int gen_v6_max_clusters(int cs) { return cs == 4 ? gen_v6_max_clusters_cs<4>() : gen_v6_max_clusters_cs<8>(); }
+
+template <int CS>
+int launch_gen_v6_cs(wn_gen* g, const GenArgs& a, const V6Args& v, cudaStream_t s) {
+  if (gen_v6_max_clusters_cs<CS>() < g->v6_clusters) return WN_ESTATE;   // also sets the shared-memory attribute
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(g->v6_clusters * CS);
+  cfg.blockDim = dim3(V6_THREADS);
+  cfg.dynamicSmemBytes = V6C<CS>::SMEM + 128;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  WN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gen_kernel_v6<CS>, a, v));
+  return WN_OK;
 }
 
 int launch_gen_v6(wn_gen* g, const GenArgs& a, cudaStream_t s) {
@@ -2056,7 +2079,10 @@ int launch_gen_v6(wn_gen* g, const GenArgs& a, cudaStream_t s) {
   v.ring = reinterpret_cast<uint8_t*>(g->state + g->lay.ring6);
   v.ring_cta_bytes = g->lay.ring6_cta_bytes;
   v.spc = g->v6_spc;
-  gen_kernel_v6<<<g->v6_clusters * V6_CS, V6_THREADS, V6_SMEM + 128, s>>>(a, v);
+  if (g->v6_cs == 4)
+    WN_TRY(launch_gen_v6_cs<4>(g, a, v, s));
+  else
+    WN_TRY(launch_gen_v6_cs<8>(g, a, v, s));
   WN_CHECK_LAUNCH();
   g->ring6_valid = true;
   g->ringf_valid = false;
@@ -2260,15 +2286,22 @@ extern "C" int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen**
     if (spc < 8 || spc > 128) spc = 128;
     g->v6_spc = spc;
     g->v6_clusters = (n_streams + spc - 1) / spc;
-    if (g->v6_clusters > gen_v6_max_clusters()) g->v6_ok = false;         // every cluster resident at once
+    // 8-CTA clusters while they are all co-resident (15 on a B200), else 4-CTA clusters (twice the streams per SM, a slightly
+    // longer step); WN_GEN_V6_CS = 4 / 8 pins the choice
+    int cs = g->v6_clusters <= gen_v6_max_clusters(8) ? 8 : 4;
+    if (const char* e = getenv("WN_GEN_V6_CS")) cs = atoi(e) == 4 ? 4 : 8;
+    g->v6_cs = cs;
+    if (g->v6_clusters > gen_v6_max_clusters(cs)) g->v6_ok = false;       // every cluster resident at once
   }
   if (g->v6_ok) {
+    const int cs = g->v6_cs;
     int64_t slots = 0;
     for (int l = 0; l < L.L; ++l) slots += g->layers[l].ring_len;
-    L.wpk6_rank_bytes = (int64_t)(L.L + L.n_head) * 32768;
-    L.wpk6 = take(L.wpk6_rank_bytes * V4_CS_HOST / 4);
+    const int64_t chunk = cs == 4 ? V6C<4>::CHUNK : V6C<8>::CHUNK;
+    L.wpk6_rank_bytes = (int64_t)L.L * chunk + (int64_t)L.n_head * (256 / cs / 32) * 32768;
+    L.wpk6 = take(L.wpk6_rank_bytes * cs / 4);
     L.ring6_cta_bytes = slots * 32768;
-    L.ring6 = take(L.ring6_cta_bytes / 4 * V4_CS_HOST * g->v6_clusters);
+    L.ring6 = take(L.ring6_cta_bytes / 4 * cs * g->v6_clusters);
   }
   L.maxw = (maxw + 3) / 4 * 4;
   L.total = off;
@@ -2405,13 +2438,18 @@ extern "C" int wn_gen_prime_part(wn_gen* g, const float* params, const int32_t* 
   }
   if (g->v6_ok) {
     uint8_t* w6 = reinterpret_cast<uint8_t*>(S + L.wpk6);
+    const int cs = g->v6_cs, gc = 64 / cs, psn = 64 + 256 / cs, nsub = 256 / cs / 32;
+    const int64_t chunk = cs == 4 ? V6C<4>::CHUNK : V6C<8>::CHUNK;
+    const int64_t gbytes = 16 * 4 * gc * 16;
     for (int l = 0; l < L.L; ++l) {
-      uint8_t* d = w6 + (int64_t)l * 32768;
-      gen_pack_v6<<<nb(8 * 16 * 32 * 8), 256, 0, s>>>(S + g->layers[l].wa, d, L.wpk6_rank_bytes, 1, 128);
-      gen_pack_v6<<<nb(8 * 8 * 192 * 8), 256, 0, s>>>(S + g->layers[l].wb, d + 8192, L.wpk6_rank_bytes, 2, 320);
+      uint8_t* d = w6 + (int64_t)l * chunk;
+      gen_pack_v6<<<nb((int64_t)cs * 16 * 4 * gc * 8), 256, 0, s>>>(S + g->layers[l].wa, d, L.wpk6_rank_bytes, 1, 128, cs, 0);
+      gen_pack_v6<<<nb((int64_t)cs * 8 * 2 * psn * 8), 256, 0, s>>>(S + g->layers[l].wb, d + gbytes, L.wpk6_rank_bytes, 2, 320, cs, 0);
     }
     for (int i = 0; i < L.n_head; ++i)
-      gen_pack_v6<<<nb(8 * 32 * 64 * 8), 256, 0, s>>>(S + L.hw[i], w6 + (int64_t)(L.L + i) * 32768, L.wpk6_rank_bytes, 4, 256);
+      for (int j = 0; j < nsub; ++j)
+        gen_pack_v6<<<nb((int64_t)cs * 32 * 64 * 8), 256, 0, s>>>(S + L.hw[i], w6 + (int64_t)L.L * chunk + (int64_t)(i * nsub + j) * 32768,
+                                                                  L.wpk6_rank_bytes, 4, 256, cs, j);
     WN_CHECK_LAUNCH();
   }
   g->ring6_valid = false;
