@@ -525,8 +525,13 @@ def main():
         cases = [("batch_1", 1, 1), ("batch_256", 256, max(1, 256 // world))]
         if world > 1:
             cases.append(("batch_256_per_gpu", 256 * world, 256))
-        # the serving-scale case: 15 clusters x 128 streams per GPU on the tensor-core generator (gen_kernel_v6), weak-scaled
-        cases.append(("batch_1920_per_gpu", 1920 * world, 1920))
+        # the serving-scale cases on the tensor-core generator (gen_kernel_v6), weak-scaled: as many streams per GPU as stay
+        # resident with 8-CTA clusters (15 x 128 = 1920 on a B200) and with 4-CTA clusters (33 x 128 = 4224)
+        cap8, cap4 = int(lib.wn_gen_mma_capacity(8)), int(lib.wn_gen_mma_capacity(4))
+        if cap8 >= 512:
+            cases.append(("many_streams_8cta_per_gpu", cap8 * world, cap8))
+        if cap4 > cap8:
+            cases.append(("many_streams_4cta_per_gpu", cap4 * world, cap4))
         for key, n_total, n in cases:
             if n_total == 1 and rank != 0:
                 continue
@@ -560,22 +565,23 @@ def main():
             sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
             clustered = n <= 15          # gen_kernel_v4: one 8-CTA cluster per stream while all clusters are co-resident
             many = False                 # gen_kernel_v5 (16 streams per 8-CTA cluster) is opt-in (WN_GEN_V5=1): slower than v3 today
-            mma = 512 <= n <= 1920 and os.environ.get("WN_GEN_V6", "1") != "0"   # gen_kernel_v6: automatic from 512 streams
-            n_ctas = 8 * n if clustered else (8 * -(-n // 128) if mma else (8 * -(-n // 16) if many else -(-n // (1 if n <= 148 else 2))))
-            per_cta = 32 * 32768 if mma else (33 * 32768 if (clustered or many) else 1270272 * 4)   # packed weight bytes per CTA per step
+            mma = n >= 512 and os.environ.get("WN_GEN_V6", "1") != "0"   # gen_kernel_v6: automatic from 512 streams
+            mma_cs = 8 if (mma and n <= cap8) else 4                    # 8-CTA clusters while they are all resident, else 4-CTA
+            n_ctas = 8 * n if clustered else (mma_cs * -(-n // 128) if mma else (8 * -(-n // 16) if many else -(-n // (1 if n <= 148 else 2))))
+            per_cta = (8 // mma_cs) * 32 * 32768 if mma else (33 * 32768 if (clustered or many) else 1270272 * 4)   # packed weight bytes per CTA per step
             gen[key] = {
                 "samples_per_s": total_streams * steps / (gms / 1e3), "streams": total_streams, "streams_per_gpu": n,
                 "scaling": "weak" if key.endswith("_per_gpu") else ("strong" if n_total > 1 else "single stream"), "steps": steps,
                 "us_per_step": us, "cycles_per_sample_per_stream": us * sm_mhz,
                 "kernel": "gen_kernel_v4 (8-CTA cluster per stream, output-split matvecs, st.async exchanges)" if clustered
-                          else ("gen_kernel_v6 (tcgen05: streams = MMA M dimension, 128 per 8-CTA cluster, fp16 hi|lo operands, "
-                                "weights split by output rows, z all-gathered with bulk DSMEM copies)" if mma else ("gen_kernel_v5 (16 streams per 8-CTA cluster: weights in registers swept over the streams, "
+                          else ("gen_kernel_v6<%d> (tcgen05: streams = MMA M dimension, 128 per %d-CTA cluster, fp16 hi|lo operands, "
+                                "weights split by output rows, z all-gathered with bulk DSMEM copies)" % (mma_cs, mma_cs) if mma else ("gen_kernel_v5 (16 streams per 8-CTA cluster: weights in registers swept over the streams, "
                                 "transposing-butterfly reductions, st.async exchanges)" if many
                                 else "gen_kernel_v3 (one CTA per 1-2 streams)")),
                 "weight_stream_gbs_per_sm": per_cta / (us * 1e-6) / 1e9,
                 "weight_stream_gbs_all_ctas": n_ctas * world * per_cta / (us * 1e-6) / 1e9,
                 "bound": ("dependency-chain latency (30 layers x 1 cluster exchange + head per sample)" if clustered else
-                          "per layer: DSMEM all-gather of z (28 KB into every CTA at ~17-21 B/clk) + shared-memory A-operand reads of the "
+                          "per layer: DSMEM all-gather of z (24-28 KB into every CTA at ~17-21 B/clk) + shared-memory A-operand reads of the "
                           "MMAs (64 B/clk) + TMEM reads of the epilogues, all on one dependency chain" if mma else
                           ("FP32 FMA issue + one cluster exchange per layer (per CTA and step: 16 streams x 155 k MACs)" if many
                            else "dependency-chain latency (30 layers x 2 block barriers + head per sample)"))}

@@ -443,13 +443,14 @@ def test_many_stream_cluster_generator(n):
     assert (f != want).any(axis=1).sum() <= 1 and (f != c).any(axis=1).sum() <= 1
 
 
-@pytest.mark.parametrize("n", [24, 130])
-def test_tensor_core_generator(n):
+@pytest.mark.parametrize("n,cs", [(24, 8), (130, 8), (130, 4)])
+def test_tensor_core_generator(n, cs):
     """gen_kernel_v6 (tcgen05 generator: streams are the MMA M dimension, up to 128 per 8-CTA cluster; automatic from 512
     streams, forced here with WN_GEN_V6=1) at config-C depth: greedy sequences against the fp64 ring oracle and gen_kernel_v3,
     sampled sequences against gen_kernel_v3 (same counter RNG), continuation across wn_gen_run calls (the state moves between
-    the fp32 rings and the operand-tile rings), a partially filled second cluster (n = 130), sliced priming, and a shard of
-    the streams generating what it generates inside the full set."""
+    the fp32 rings and the operand-tile rings), a partially filled second cluster (n = 130), sliced priming, a shard of the
+    streams generating what it generates inside the full set, both cluster sizes (8 CTAs: up to 1920 resident streams, 4 CTAs:
+    4224), and clusters launched in consecutive waves (what happens beyond the resident capacity)."""
     import os
     from wavenet_b200 import _lib
     from wavenet_b200._lib import check
@@ -459,8 +460,11 @@ def test_tensor_core_generator(n):
     w = O.init_weights(cfg, np.random.default_rng(7), np.float64)
     window = np.random.default_rng(3).integers(0, 256, (n, O.input_width(cfg))).astype(np.int32)
 
-    def run(win, parts, v6, mode=_lib.WN_GEN_GREEDY, step_between=False):
+    def run(win, parts, v6, mode=_lib.WN_GEN_GREEDY, wave=None):
         os.environ["WN_GEN_V6"] = "1" if v6 else "0"
+        os.environ["WN_GEN_V6_CS"] = str(cs)
+        if wave:
+            os.environ["WN_GEN_V6_WAVE"] = str(wave)
         try:
             net = make_net(cfg, w, faster=True, head_act="reference")
             net.prime(win)
@@ -471,7 +475,8 @@ def test_tensor_core_generator(n):
                 outs.append(out.cpu().numpy())
             return np.concatenate(outs, axis=1)
         finally:
-            os.environ.pop("WN_GEN_V6", None)
+            for k in ("WN_GEN_V6", "WN_GEN_V6_CS", "WN_GEN_V6_WAVE"):
+                os.environ.pop(k, None)
 
     steps = 40
     a = run(window, [steps], True)
@@ -497,6 +502,9 @@ def test_tensor_core_generator(n):
     finally:
         FasterWaveNet.PRIME_SLICE = old
     assert np.array_equal(e, a)
+    if n > 128:
+        f = run(window, [steps], True, wave=1)                               # two clusters, one per launch
+        assert np.array_equal(f, a)
 
 
 def test_device_crop_batch_matches_reference_create_batch():

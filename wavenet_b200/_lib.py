@@ -101,6 +101,7 @@ SIGNATURES = {
     "wn_gen_bind_state": (_I, [_P, _P, _L]),
     "wn_gen_prime": (_I, [_P, _P, _P, _P, _P]),
     "wn_gen_prime_part": (_I, [_P, _P, _P, _I, _I, _P, _P]),
+    "wn_gen_mma_capacity": (_I, [_I]),
     "wn_gen_step": (_I, [_P, _P, _P, _I, _P, _P]),
     "wn_gen_logits": (_I, [_P, _P, _P]),
     "wn_gen_run": (_I, [_P, _P, _I, _I, C.c_uint64, _P, _P]),

@@ -2053,10 +2053,9 @@ int gen_v6_max_clusters_cs() {
 int gen_v6_max_clusters(int cs) { return cs == 4 ? gen_v6_max_clusters_cs<4>() : gen_v6_max_clusters_cs<8>(); }
 
 template <int CS>
-int launch_gen_v6_cs(wn_gen* g, const GenArgs& a, const V6Args& v, cudaStream_t s) {
-  if (gen_v6_max_clusters_cs<CS>() < g->v6_clusters) return WN_ESTATE;   // also sets the shared-memory attribute
+int launch_gen_v6_cs(wn_gen* g, const GenArgs& a, const V6Args& v, int n_clusters, cudaStream_t s) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(g->v6_clusters * CS);
+  cfg.gridDim = dim3(n_clusters * CS);
   cfg.blockDim = dim3(V6_THREADS);
   cfg.dynamicSmemBytes = V6C<CS>::SMEM + 128;
   cfg.stream = s;
@@ -2079,11 +2078,21 @@ int launch_gen_v6(wn_gen* g, const GenArgs& a, cudaStream_t s) {
   v.ring = reinterpret_cast<uint8_t*>(g->state + g->lay.ring6);
   v.ring_cta_bytes = g->lay.ring6_cta_bytes;
   v.spc = g->v6_spc;
-  if (g->v6_cs == 4)
-    WN_TRY(launch_gen_v6_cs<4>(g, a, v, s));
-  else
-    WN_TRY(launch_gen_v6_cs<8>(g, a, v, s));
-  WN_CHECK_LAUNCH();
+  // every cluster of a launch must be resident (the kernel is persistent over all audio samples): more clusters than fit
+  // run as consecutive launches over the same samples
+  int wave = gen_v6_max_clusters(g->v6_cs);              // also sets the shared-memory attribute
+  if (const char* e = getenv("WN_GEN_V6_WAVE"))           // developer switch: smaller waves (tests)
+    if (atoi(e) > 0 && atoi(e) < wave) wave = atoi(e);
+  WN_REQUIRE(wave > 0, WN_ESTATE, "gen_kernel_v6 cannot be resident on this device");
+  for (int c0 = 0; c0 < g->v6_clusters; c0 += wave) {
+    const int nc = g->v6_clusters - c0 < wave ? g->v6_clusters - c0 : wave;
+    v.cluster0 = c0;
+    if (g->v6_cs == 4)
+      WN_TRY(launch_gen_v6_cs<4>(g, a, v, nc, s));
+    else
+      WN_TRY(launch_gen_v6_cs<8>(g, a, v, nc, s));
+    WN_CHECK_LAUNCH();
+  }
   g->ring6_valid = true;
   g->ringf_valid = false;
   return WN_OK;
@@ -2291,7 +2300,7 @@ extern "C" int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen**
     int cs = g->v6_clusters <= gen_v6_max_clusters(8) ? 8 : 4;
     if (const char* e = getenv("WN_GEN_V6_CS")) cs = atoi(e) == 4 ? 4 : 8;
     g->v6_cs = cs;
-    if (g->v6_clusters > gen_v6_max_clusters(cs)) g->v6_ok = false;       // every cluster resident at once
+    if (gen_v6_max_clusters(cs) <= 0) g->v6_ok = false;
   }
   if (g->v6_ok) {
     const int cs = g->v6_cs;
@@ -2314,6 +2323,11 @@ extern "C" int wn_debug_gen_trace(long long* out) {
   return cudaMemcpyFromSymbol(out, g_trace_gen, sizeof(long long) * 64 * 16) == cudaSuccess ? 0 : -1;
 }
 #endif
+extern "C" int wn_gen_mma_capacity(int cluster_size) {
+  if (cluster_size != 4 && cluster_size != 8) return WN_EINVAL;
+  return gen_v6_max_clusters(cluster_size) * 128;
+}
+
 extern "C" int wn_gen_destroy(wn_gen* g) {
   delete g;
   return WN_OK;

@@ -214,6 +214,7 @@ struct V6Args {
   uint8_t* ring;            // [cluster][rank][slot][32 KB]
   int64_t ring_cta_bytes;
   int spc;                  // streams per cluster (<= 128)
+  int cluster0;             // first cluster of this launch (more clusters than fit at once run as consecutive launches)
 };
 
 template <int CS>
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) gen_kernel_v6(GenArgs a, V6Args
   const GenLayout& L = a.lay;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rank = (int)cluster_rank();
-  const int cluster = blockIdx.x / CS;
+  const int cluster = blockIdx.x / CS + v.cluster0;
   const int stream0 = cluster * v.spc;
   const int ns = min(v.spc, L.n - stream0);
   const int NL = L.L;
