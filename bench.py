@@ -528,7 +528,7 @@ def main():
         # the serving-scale cases on the tensor-core generator (gen_kernel_v6), weak-scaled: as many streams per GPU as stay
         # resident with 8-CTA clusters (15 x 128 = 1920 on a B200) and with 4-CTA clusters (33 x 128 = 4224)
         cap8, cap4 = int(lib.wn_gen_mma_capacity(8)), int(lib.wn_gen_mma_capacity(4))
-        if cap8 >= 512:
+        if cap8 > 296:
             cases.append(("many_streams_8cta_per_gpu", cap8 * world, cap8))
         if cap4 > cap8:
             cases.append(("many_streams_4cta_per_gpu", cap4 * world, cap4))
@@ -565,7 +565,7 @@ def main():
             sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
             clustered = n <= 15          # gen_kernel_v4: one 8-CTA cluster per stream while all clusters are co-resident
             many = False                 # gen_kernel_v5 (16 streams per 8-CTA cluster) is opt-in (WN_GEN_V5=1): slower than v3 today
-            mma = n >= 512 and os.environ.get("WN_GEN_V6", "1") != "0"   # gen_kernel_v6: automatic from 512 streams
+            mma = n > 296 and os.environ.get("WN_GEN_V6", "1") != "0"   # gen_kernel_v6: automatic beyond 2 x sm_count = 296 streams
             mma_cs = 8 if (mma and n <= cap8) else 4                    # 8-CTA clusters while they are all resident, else 4-CTA
             n_ctas = 8 * n if clustered else (mma_cs * -(-n // 128) if mma else (8 * -(-n // 16) if many else -(-n // (1 if n <= 148 else 2))))
             per_cta = (8 // mma_cs) * 32 * 32768 if mma else (33 * 32768 if (clustered or many) else 1270272 * 4)   # packed weight bytes per CTA per step

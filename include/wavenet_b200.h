@@ -217,7 +217,7 @@ int wn_tcs_debug_wgrad(wn_handle* h, const void* dy_split, int M, const void* x_
 
 int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen** out);
 int wn_gen_destroy(wn_gen* g);
-/* Streams the tensor-core generator (gen_kernel_v6, automatic from 512 streams) keeps resident at once on the current
+/* Streams the tensor-core generator (gen_kernel_v6, automatic beyond 2 x sm_count = 296 streams) keeps resident at once on the current
  * device with clusters of `cluster_size` (4 or 8) CTAs: co-resident clusters x 128.  More streams run as consecutive
  * launches over the same samples.  (B200: 1920 with 8-CTA clusters, 4224 with 4-CTA clusters.) */
 int wn_gen_mma_capacity(int cluster_size);

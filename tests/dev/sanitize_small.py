@@ -38,9 +38,10 @@ if what in ("all", "gen"):
         out = net.generate(win, 6, mode="greedy")
         torch.cuda.synchronize()
         print("gen", tag, out[0].tolist(), flush=True)
-if what in ("gen6",):
+if what in ("gen6", "gen6_4"):
     # gen_kernel_v6 (tensor-core generator): one partially filled cluster, forced below its automatic threshold
     os.environ["WN_GEN_V6"] = "1"
+    os.environ["WN_GEN_V6_CS"] = "4" if what == "gen6_4" else "8"
     cfg = make_cfg("C")
     w = O.init_weights(cfg, np.random.default_rng(0), np.float32)
     net = make_net(cfg, w, faster=True)

@@ -2283,10 +2283,11 @@ extern "C" int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen**
     L.wpk4 = take(L.wpk4_rank * V4_CS_HOST);
   }
   // v6 (streams = MMA M dimension, <= 128 per 8-CTA cluster): the v4 shape with biases in the head only, two head convs
-  // It pays from ~500 streams on (measured: 107 us per step for up to 128 streams per cluster against 59 / 82 / 132 us for
-  // 1 / 2 / 4 streams per CTA of gen_kernel_v3); WN_GEN_V6=1 forces it from 16 streams (tests), WN_GEN_V6=0 disables it.
+  // It pays as soon as gen_kernel_v3 needs four streams per CTA, i.e. beyond 2 x sm_count streams (measured: 107-116 us per
+  // step at any stream count against 59 / 82 / 132 us for 1 / 2 / 4 streams per CTA of gen_kernel_v3); WN_GEN_V6=1 forces it
+  // from 16 streams (tests), WN_GEN_V6=0 disables it.
   const char* e6 = getenv("WN_GEN_V6");
-  const int min6 = e6 && atoi(e6) != 0 ? 16 : 512;
+  const int min6 = e6 && atoi(e6) != 0 ? 16 : 2 * h->sm_count + 1;
   g->v6_ok = g->v4_ok && L.n_head == 2 && !L.has_cb && L.L >= 16 && L.L <= 64 && n_streams >= min6 && !(e6 && atoi(e6) == 0);
   for (int l = 0; l < L.L && g->v6_ok; ++l) g->v6_ok = !g->layers[l].has_ba && !g->layers[l].has_bb;
   if (g->v6_ok) {
