@@ -232,8 +232,10 @@ __global__ void __launch_bounds__(V6_THREADS, 1) gen_kernel_v6(GenArgs a, V6Args
   uint8_t* smp = sm6_raw + ((128 - (tc::smem_u32(sm6_raw) & 127)) & 127);
   const uint32_t sb = tc::smem_u32(smp);
   // barriers
-  enum { B_WF = 0, B_WE = 2, B_XDF = 4, B_XDE = 6, B_XR = 8, B_XF = 9, B_GD = 10, B_ZF = 11, B_PD = 13, B_HF = 14, B_HD = 15,
-         B_HFREE = 16, B_CF = 17, B_XT = 18, B_CFREE = 19, B_N = 20 };
+  // B_ZF: [z buffer 2][K step 4] -- the project + skip GEMM consumes z K step by K step as the slices land;  B_HF: one per
+  // source rank of a head-tile slice
+  enum { B_WF = 0, B_WE = 2, B_XDF = 4, B_XDE = 6, B_XR = 8, B_XF = 9, B_GD = 10, B_PD = 11, B_HD = 12, B_HFREE = 13, B_CF = 14,
+         B_XT = 15, B_CFREE = 16, B_ZF = 17, B_HF = 25, B_N = 33 };
   __shared__ __align__(8) uint64_t s_bar[B_N];
   __shared__ uint32_t s_tmem;
   __shared__ int s_len[V6_MAXL], s_base[V6_MAXL];
@@ -245,14 +247,16 @@ __global__ void __launch_bounds__(V6_THREADS, 1) gen_kernel_v6(GenArgs a, V6Args
       tc::mbar_init(BAR(B_WE + i), 1);
       tc::mbar_init(BAR(B_XDF + i), 1);
       tc::mbar_init(BAR(B_XDE + i), 1);
+    }
+    for (int i = 0; i < 8; ++i) {
       tc::mbar_init(BAR(B_ZF + i), 1);
+      tc::mbar_init(BAR(B_HF + i), 1);
     }
     tc::mbar_init(BAR(B_XR), V6_T / 32);
     tc::mbar_init(BAR(B_XT), V6_T / 32);
     tc::mbar_init(BAR(B_XF), 1);
     tc::mbar_init(BAR(B_GD), 1);
     tc::mbar_init(BAR(B_PD), 1);
-    tc::mbar_init(BAR(B_HF), 1);
     tc::mbar_init(BAR(B_HD), 1);
     tc::mbar_init(BAR(B_HFREE), CS);
     tc::mbar_init(BAR(B_CFREE), CS);
@@ -351,6 +355,29 @@ __global__ void __launch_bounds__(V6_THREADS, 1) gen_kernel_v6(GenArgs a, V6Args
       uint32_t n_w = 0, n_xr = 0, n_gate[2] = {0, 0}, n_z[2] = {0, 0}, n_h = 0;
       constexpr uint32_t ID_G2 = v6_idesc(128, C::G_ROWS), ID_G1 = v6_idesc(128, C::G_ROWS / 2), ID_S2 = v6_idesc(128, 64),
                          ID_S1 = v6_idesc(128, 32), ID_PS = v6_idesc(128, C::PS_N);
+      // Slices of an all-gather arrive from rank - 1, rank - 2, ... (every sender serves rank + 1 first); the own slice is local.
+      // K step ks of the z tile holds the slices of ranks [ks CS / 4, (ks + 1) CS / 4): order the K steps by the arrival of
+      // their last slice.
+      int zorder[4];
+      {
+        int ready[4];
+        for (int ks = 0; ks < 4; ++ks) {
+          int last = 0;
+          for (int m = ks * CS / 4; m < (ks + 1) * CS / 4; ++m) {
+            const int pos = m == rank ? 0 : ((rank - m - 1) & (CS - 1)) + 1;
+            last = pos > last ? pos : last;
+          }
+          ready[ks] = last;
+          zorder[ks] = ks;
+        }
+        for (int i = 0; i < 4; ++i)
+          for (int j = i + 1; j < 4; ++j)
+            if (ready[zorder[j]] < ready[zorder[i]]) {
+              const int tmp = zorder[i];
+              zorder[i] = zorder[j];
+              zorder[j] = tmp;
+            }
+      }
       // x(t-d) half of a layer's gate GEMM: independent of the sample in flight, issued one layer ahead into the other
       // gate accumulator
       auto gate_early = [&](int l, uint32_t chunk) {
@@ -388,21 +415,22 @@ __global__ void __launch_bounds__(V6_THREADS, 1) gen_kernel_v6(GenArgs a, V6Args
             v6_umma_ts(dg, tmem + V6_TM_XL + 8 * (ks & 3), bd, ID_G1, 1u);
           }
           tc::umma_commit(BAR(B_GD));
-          v6_wait_cluster(BAR(B_ZF + b), n_z[b] & 1);
-          ++n_z[b];
-          TR6(l, 8);
-          tc::tcgen05_fence_after();
           const uint32_t zt = sb + C::OFF_Z + b * V6_TILE;
           const uint32_t grp_acc = (l % V6_FLUSH) != 0;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {           // cross terms first, hi.hi last (the accumulator rounds toward zero)
+          for (int i = 0; i < 4; ++i) {              // K steps in the order their z slices land (the DSMEM all-gather is the long pole)
+            const int ks = zorder[i];
+            v6_wait_cluster(BAR(B_ZF + 4 * b + ks), n_z[b] & 1);
+            if (i == 0) TR6(l, 8);
+            tc::tcgen05_fence_after();
             const uint64_t ah = v6_desc(zt + ks * 8192, 4096, 128), al = v6_desc(zt + ks * 8192 + 2048, 4096, 128);
             const uint64_t bh = v6_desc(wst + C::G_BYTES + ks * 2 * C::PS_KS, C::PS_KS, 128);
             const uint64_t bl = v6_desc(wst + C::G_BYTES + C::PS_PLANE + ks * 2 * C::PS_KS, C::PS_KS, 128);
-            v6_umma(tmem + C::TM_PS, ah, bl, ID_PS, grp_acc | (ks > 0));
+            v6_umma(tmem + C::TM_PS, ah, bl, ID_PS, grp_acc | (i > 0));      // cross terms first, hi.hi last (round-toward-zero)
             v6_umma(tmem + C::TM_PS, al, bh, ID_PS, 1u);
             v6_umma(tmem + C::TM_PS, ah, bh, ID_PS, 1u);
           }
+          ++n_z[b];
           tc::umma_commit(BAR(B_PD));
           tc::umma_commit(BAR(B_WE + st));
           TR6(l, 9);
@@ -413,18 +441,22 @@ __global__ void __launch_bounds__(V6_THREADS, 1) gen_kernel_v6(GenArgs a, V6Args
             const uint32_t st = n_w & 1;
             const uint32_t wst = sb + C::OFF_W + st * C::CHUNK;
             tc::mbar_wait(BAR(B_WF + st), (n_w >> 1) & 1);
-            if (j == 0) {
-              v6_wait_cluster(BAR(B_HF), n_h & 1);
+            for (int i = 0; i < CS; ++i) {           // slices in arrival order: own, rank - 1, rank - 2, ...
+              const int src = (rank - i) & (CS - 1);
+              if (j == 0) v6_wait_cluster(BAR(B_HF + src), n_h & 1);
+              tc::tcgen05_fence_after();
+#pragma unroll
+              for (int k = 0; k < C::SKC / 16; ++k) {
+                const int ks = src * (C::SKC / 16) + k;
+                const uint64_t bd = v6_desc(wst + ks * 2048, 1024, 128);
+                v6_umma(tmem + C::TM_HEAD + 64 * j, v6_desc(sb + ks * 8192, 4096, 128), bd, ID_S2, (i | k) > 0);
+                v6_umma(tmem + C::TM_HEAD + 64 * j, v6_desc(sb + ks * 8192 + 2048, 4096, 128), bd, ID_S1, 1u);
+              }
+            }
+            if (j == C::NSUB - 1) {
+              tc::umma_commit(BAR(B_HD));
               ++n_h;
             }
-            tc::tcgen05_fence_after();
-#pragma unroll 4
-            for (int ks = 0; ks < 16; ++ks) {
-              const uint64_t bd = v6_desc(wst + ks * 2048, 1024, 128);
-              v6_umma(tmem + C::TM_HEAD + 64 * j, v6_desc(sb + ks * 8192, 4096, 128), bd, ID_S2, ks > 0);
-              v6_umma(tmem + C::TM_HEAD + 64 * j, v6_desc(sb + ks * 8192 + 2048, 4096, 128), bd, ID_S1, 1u);
-            }
-            if (j == C::NSUB - 1) tc::umma_commit(BAR(B_HD));
             tc::umma_commit(BAR(B_WE + st));
           }
         }
@@ -516,18 +548,35 @@ __global__ void __launch_bounds__(V6_THREADS, 1) gen_kernel_v6(GenArgs a, V6Args
         TRG(45, 2);
         if (a.out && rank == 0 && hh == 0 && s < ns) a.out[(int64_t)(stream0 + s) * a.n_steps + step] = bi;
         // ---- 2. embedding of the new sample = causal conv of the one-hot pair (wavenet.py:565-570) ----
-        const float4* e1 = reinterpret_cast<const float4*>(emb + ((int64_t)kc1 * Q + bi) * R + 32 * hh);
-        const float4* e0 = reinterpret_cast<const float4*>(emb + ((int64_t)0 * Q + max(prev, 0)) * R + 32 * hh);
-        const bool two = kc1 > 0 && prev >= 0;
-        float4 v1[8], v0[8];                       // all sixteen loads in flight before the first use
+        // Every thread needs 2 x 128 B of the embedding table (its stream's half rows of both taps).  Read row-per-lane that is
+        // 32 different lines per load instruction (4 k LSU wavefronts per step and CTA, 7 k cycles); instead eight lanes share
+        // a row (4 full lines per instruction), add the two taps and hand the sums over through the warp's own 4 KB of the
+        // x tile (the bytes this warp overwrites with x(t) right after; nobody else touches them now).
+        {
+          const uint32_t stg = sb + C::OFF_X + (uint32_t)(4 * hh) * 4096 + 512u * (uint32_t)q4;
+          const int kk = lane & 7;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v1[i] = __ldg(e1 + i);
+          for (int it = 0; it < 8; ++it) {
+            const int i = 4 * it + (lane >> 3);                  // stream of this lane group in this round
+            const int bi_i = __shfl_sync(0xffffffffu, bi, i), prev_i = __shfl_sync(0xffffffffu, prev, i);
+            float4 v1 = __ldg(reinterpret_cast<const float4*>(emb + ((int64_t)kc1 * Q + bi_i) * R + 32 * hh) + kk);
+            if (kc1 > 0 && prev_i >= 0) {
+              const float4 v0 = __ldg(reinterpret_cast<const float4*>(emb + (int64_t)prev_i * R + 32 * hh) + kk);
+              v1.x += v0.x, v1.y += v0.y, v1.z += v0.z, v1.w += v0.w;
+            }
+            const uint32_t ad = stg + (uint32_t)(it >> 1) * 4096 + (uint32_t)(it & 1) * 2048 + (uint32_t)(i & 3) * 128 +
+                                (uint32_t)((kk ^ (i & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ad), "f"(v1.x), "f"(v1.y), "f"(v1.z), "f"(v1.w) : "memory");
+          }
+          __syncwarp();
+          const uint32_t rd = stg + (uint32_t)(lane >> 3) * 4096 + (uint32_t)((lane >> 2) & 1) * 2048 + (uint32_t)(lane & 3) * 128;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v0[i] = two ? __ldg(e0 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          xr[4 * i] = v1[i].x + v0[i].x, xr[4 * i + 1] = v1[i].y + v0[i].y, xr[4 * i + 2] = v1[i].z + v0[i].z,
-                 xr[4 * i + 3] = v1[i].w + v0[i].w;
+          for (int k = 0; k < 8; ++k)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(xr[4 * k]), "=f"(xr[4 * k + 1]), "=f"(xr[4 * k + 2]), "=f"(xr[4 * k + 3])
+                         : "r"(rd + (uint32_t)((k ^ (lane & 7)) << 4)));
+          __syncwarp();                                          // all rows read before any lane publishes x(t) over them
+        }
         prev = bi;
         TRG(42, 2);
       }
@@ -577,10 +626,16 @@ __global__ void __launch_bounds__(V6_THREADS, 1) gen_kernel_v6(GenArgs a, V6Args
         v6_esync();
         if (tid < CS) {
           const uint32_t zs = sb + C::OFF_Z + b * V6_TILE + (uint32_t)rank * C::Z_SLICE;
-          if (tid == CS - 1)
-            tc::mbar_arrive_expect_tx(BAR(B_ZF + b), (CS - 1) * C::Z_SLICE);
-          else
-            bulk_copy_to_cta(map_to_cta(zs, dst_rank), zs, C::Z_SLICE, map_to_cta(BAR(B_ZF + b), dst_rank));
+          if (tid < CS - 1)                    // lands on the destination's barrier of the K step this rank's channels belong to
+            bulk_copy_to_cta(map_to_cta(zs, dst_rank), zs, C::Z_SLICE, map_to_cta(BAR(B_ZF + 4 * b + rank * 4 / CS), dst_rank));
+          if (tid < 4) {                       // open the local phase of K step `tid`: its remote slices (the own one is in place)
+            const int own = rank * 4 / CS == tid ? 1 : 0;
+            const uint32_t bytes = (uint32_t)((CS / 4 - own) * C::Z_SLICE);
+            if (bytes)
+              tc::mbar_arrive_expect_tx(BAR(B_ZF + 4 * b + tid), bytes);
+            else
+              tc::mbar_arrive(BAR(B_ZF + 4 * b + tid));
+          }
         }
         TRG(l, 2);
         if (noisy && more && l < 16) {
@@ -644,10 +699,11 @@ __global__ void __launch_bounds__(V6_THREADS, 1) gen_kernel_v6(GenArgs a, V6Args
           // every CTA must be done reading the first head tile before anyone overwrites it
           if (hi == 1) v6_wait_cluster(BAR(B_HFREE), n_hfree & 1);
           TRG(44, 4 * hi + 3);
-          if (tid == CS - 1)
-            tc::mbar_arrive_expect_tx(BAR(B_HF), (CS - 1) * C::H_SLICE);
+          if (tid < CS - 1) bulk_copy_to_cta(map_to_cta(hs, dst_rank), hs, C::H_SLICE, map_to_cta(BAR(B_HF + rank), dst_rank));
+          if (tid == rank)                     // local phase of source rank `tid`
+            tc::mbar_arrive(BAR(B_HF + tid));
           else
-            bulk_copy_to_cta(map_to_cta(hs, dst_rank), hs, C::H_SLICE, map_to_cta(BAR(B_HF), dst_rank));
+            tc::mbar_arrive_expect_tx(BAR(B_HF + tid), C::H_SLICE);
         }
         if (hi == 1) ++n_hfree;
         TRG(43, 2 * hi);
