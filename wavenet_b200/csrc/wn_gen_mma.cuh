@@ -1,27 +1,33 @@
-// gen_kernel_v6: the MANY-stream generator on the tensor cores (included by wn_gen.cu inside its anonymous namespace).
+// gen_kernel_v6<CS>: the MANY-stream generator on the tensor cores (included by wn_gen.cu inside its anonymous namespace).
 //
 // FasterWaveNet._forward_one_step (faster_wavenet.py:50-113) + the sampling loop of train_audio/generate.py:24-43 for up
-// to 128 streams per 8-CTA cluster.  The SIMT generators feed every FMA one operand from shared memory (v3: 5 MB of
-// weights per CTA and step; v5: ~4 k LDS wavefronts per layer), so they stop scaling at one or two streams per SM.  Here
-// the STREAMS are the M dimension of tcgen05.mma (M = 128, one TMEM lane per stream) and the eight CTAs of a cluster split
-// every weight matrix by OUTPUT rows like v4/v5 (1 MB of packed fp16 hi|lo weights per CTA and step, streamed through a
-// cp.async.bulk ring):
-//   gate      D[128 x 16]  = [x(t-d) | x(t)] (K = 128) . Wf/Wg rows of this rank (8 f + 8 g)
-//   project   D[128 x 64]  = z (K = 64) . Wp (all 64 rows, computed redundantly by every CTA: ONE exchange per layer)
-//   skip      D[128 x 32] += z . Ws rows of this rank (accumulates in TMEM, flushed to registers every V6_FLUSH layers
-//                                                     because the tensor core accumulates round-toward-zero)
-//   head      D[128 x 32]  = h (K = 256) . W rows of this rank, twice
+// to 128 streams per cluster of CS = 8 or 4 CTAs.  The SIMT generators feed every FMA one operand from shared memory (v3:
+// 5 MB of weights per CTA and step; v5: ~4 k LDS wavefronts per layer), so they stop scaling at one or two streams per SM.
+// Here the STREAMS are the M dimension of tcgen05.mma (M = 128, one TMEM lane per stream) and the CTAs of a cluster split
+// every weight matrix by OUTPUT rows like v4/v5 (packed fp16 hi|lo B tiles streamed through a 2-stage cp.async.bulk ring:
+// 1 MB per CTA and step with 8 CTAs, 1.5 MB with 4).  Per layer and CTA (CS = 8 / 4):
+//   gate      D[128 x 16 / 32]  = [x(t-d) | x(t)] (K = 128) . Wf/Wg rows of this rank.  The x(t-d) half is issued one layer
+//                                 ahead into the other gate accumulator; the x(t) half takes its A operand FROM TENSOR MEMORY
+//                                 (written by the previous epilogue with tcgen05.st): no shared-memory read on the chain
+//   project   D[128 x 64]       = z (K = 64) . Wp (all 64 rows, computed redundantly by every CTA: ONE exchange per layer)
+//   skip      D[128 x 32 / 64] += z . Ws rows of this rank -- one N = 96 / 128 GEMM with the projection; both accumulate in
+//                                 TMEM over V6_FLUSH layers (the tensor core accumulates round-toward-zero), then move to
+//                                 fp32 registers
+//   head      D[128 x 32]       = h (K = 256) . W rows of this rank, twice (CS = 4: two 32-output sub-chunks per conv)
 // Arithmetic is the fp16x2 split of the training path (wn_tcs.cu): A.B ~ A_hi.B_hi + A_hi.B_lo + A_lo.B_hi with fp32
-// accumulation; the hi and lo weight planes are adjacent rows of one B tile, so a product is TWO MMAs (A_hi . [B_hi|B_lo]
-// with twice the N, A_lo . B_hi) and the epilogue adds the two column halves.
+// accumulation.  For the gate and the head the hi and lo weight planes are adjacent rows of one B tile, so a product is TWO
+// MMAs (A_hi . [B_hi|B_lo] with twice the N, A_lo . B_hi) and the epilogue adds the two column halves; the project + skip
+// GEMM keeps three MMAs into one accumulator (its epilogue is bound by the 64 B/clk TMEM read).
 // Operand tiles use the NO-SWIZZLE K-major canonical layout (8-row x 16-byte core matrices): tile[k_core][plane][128 rows]
-// [16 B] -- a CTA's slice of an exchanged activation (its 8 gate channels = one k_core, both planes, all 128 streams) is
-// then one contiguous 4 KB block and travels with ONE cp.async.bulk shared::cta -> shared::cluster per destination
+// [16 B] -- a CTA's slice of an exchanged activation (its 8 or 16 gate channels = one or two k_cores, both planes, all 128
+// streams) is then one contiguous block and travels with ONE cp.async.bulk shared::cta -> shared::cluster per destination
 // (complete_tx on the destination's mbarrier, the data path the MMA's async proxy reads without a cross-proxy fence).
+// The all-gathers are the long pole (a DSMEM port moves 17-21 B/clk), so consumers are pipelined against them: one barrier
+// per K step of the z tile / per source rank of the head tile, and the MMA thread walks them in arrival order.
 // The dilation rings hold whole operand tiles (x(t) of a layer for all 128 streams, 32 KB): one bulk store per layer and
 // step, one bulk load d steps later, private to each CTA (no cross-CTA ordering of global memory on the chain).
 // Warp roles: 8 epilogue warps (TMEM lane quarter = warp & 3, column half = warp >> 2), one producer thread (weights,
-// ring loads / stores), one MMA-issuing thread.
+// ring loads / stores), one MMA-issuing thread.  Measured: 98 us per step (CS = 8), 101-108 us (CS = 4) at any stream count.
 
 constexpr int V6_T = 256;                       // epilogue threads
 constexpr int V6_THREADS = V6_T + 64;           // + producer warp + MMA warp
