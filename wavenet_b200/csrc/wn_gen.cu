@@ -2302,6 +2302,10 @@ extern "C" int wn_gen_create(wn_handle* h, int n_streams, int head_act, wn_gen**
     if (const char* e = getenv("WN_GEN_V6_CS")) cs = atoi(e) == 4 ? 4 : 8;
     g->v6_cs = cs;
     if (gen_v6_max_clusters(cs) <= 0) g->v6_ok = false;
+    // every CTA keeps its own operand-tile copy of the dilation rings (~100 MB for config C): stay below 48 GB of state
+    int64_t slots6 = 0;
+    for (int l = 0; l < L.L; ++l) slots6 += g->layers[l].ring_len;
+    if (slots6 * 32768 * cs * g->v6_clusters > ((int64_t)48 << 30)) g->v6_ok = false;
   }
   if (g->v6_ok) {
     const int cs = g->v6_cs;
