@@ -560,6 +560,17 @@ def main():
                 t = torch.tensor([gms], device="cuda")
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 gms = float(t[0])
+            # end to end through the public call: host window -> device, priming pass, the sampling loop, samples -> host
+            torch.cuda.synchronize()
+            w0 = time.perf_counter()
+            host_samples = net.generate(window, steps, mode="sample", seed=0).cpu()
+            torch.cuda.synchronize()
+            e2e_s = time.perf_counter() - w0
+            if world > 1 and n_total > 1:
+                t = torch.tensor([e2e_s], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                e2e_s = float(t[0])
+            del host_samples
             total_streams = n * world if n_total > 1 else 1
             us = 1e3 * gms / steps
             sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
@@ -573,6 +584,9 @@ def main():
                 "samples_per_s": total_streams * steps / (gms / 1e3), "streams": total_streams, "streams_per_gpu": n,
                 "scaling": "weak" if key.endswith("_per_gpu") else ("strong" if n_total > 1 else "single stream"), "steps": steps,
                 "us_per_step": us, "cycles_per_sample_per_stream": us * sm_mhz,
+                "e2e": {"samples_per_s": total_streams * steps / e2e_s, "seconds": e2e_s,
+                        "what": "FasterWaveNet.generate(host window): H2D of the window, priming pass, sampling loop, D2H of the samples",
+                        "h2d_bytes": int(window.nbytes), "d2h_bytes": int(n * steps * 4)},
                 "kernel": "gen_kernel_v4 (8-CTA cluster per stream, output-split matvecs, st.async exchanges)" if clustered
                           else ("gen_kernel_v6<%d> (tcgen05: streams = MMA M dimension, 128 per %d-CTA cluster, fp16 hi|lo operands, "
                                 "weights split by output rows, z all-gathered with bulk DSMEM copies)" % (mma_cs, mma_cs) if mma else ("gen_kernel_v5 (16 streams per 8-CTA cluster: weights in registers swept over the streams, "

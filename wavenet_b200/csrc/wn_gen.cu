@@ -127,6 +127,23 @@ __global__ void gen_fill_ring(const float* __restrict__ x, float* __restrict__ r
   ring[((int64_t)sidx * len + slot) * C + c] = v;
 }
 
+// the same from the SPLIT tape of the fp16x2 forward: rows of [hi C | lo C] fp16, both carrying `inv_scale`^-1
+__global__ void gen_fill_ring_split(const __half* __restrict__ x, float* __restrict__ ring, int n, int Win, int C, int len,
+                                    float inv_scale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n * len * C) return;
+  const int c = (int)(i % C);
+  const int j = (int)((i / C) % len);
+  const int sidx = (int)(i / ((int64_t)C * len));
+  const int tau = Win - len + j;
+  float v = 0.f;
+  if (tau >= 0) {
+    const __half* row = x + ((int64_t)sidx * Win + tau) * 2 * C;
+    v = (__half2float(row[c]) + __half2float(row[C + c])) * inv_scale;
+  }
+  ring[((int64_t)sidx * len + ((tau % len) + len) % len) * C + c] = v;
+}
+
 __global__ void gen_fill_idx_hist(const int32_t* __restrict__ window, int32_t* __restrict__ hist, int n, int Win,
                                   int kc1) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2370,10 +2387,15 @@ extern "C" int wn_gen_prime_part(wn_gen* g, const float* params, const int32_t* 
   WN_REQUIRE(h->ws && h->tape.B == count && h->tape.W == Win, WN_ESTATE,
              "wn_gen_prime: bind a training workspace for (B=%d, W=%d) first", count, Win);
   cudaStream_t s = (cudaStream_t)st;
+  const wn_config& c6 = h->cfg;
   // full pass over the window (faster_wavenet.py:13-47); the priming head is ReLU (Q2).
-  // Generation is always exact fp32 so greedy sequences match the reference arithmetic.
+  // The SIMT generators are exact fp32, and so is their priming pass (greedy sequences match the reference arithmetic).
+  // The tensor-core generator computes in split fp16 (fp32-grade) anyway: its priming pass runs on the fp16x2 training
+  // kernels -- 7x faster, which matters when thousands of streams are primed (WN_GEN_TC_PRIME=0: fp32 pass).
+  bool tc_prime = g->v6_ok && c6.n_causal == 1 && tcs_supported(h);
+  if (const char* e = getenv("WN_GEN_TC_PRIME")) tc_prime = tc_prime && atoi(e) != 0;
   const int saved_prec = h->prec;
-  h->prec = WN_PREC_FP32;
+  h->prec = tc_prime ? WN_PREC_F16X2 : WN_PREC_FP32;
   int rc = wn_forward_causal_block(h, params, window, nullptr, st);
   if (rc == WN_OK) rc = wn_forward_residual_block(h, params, nullptr, nullptr, nullptr, st);
   if (rc == WN_OK) rc = wn_forward_softmax_block(h, params, nullptr, 1, 1, probs_opt, st);
@@ -2414,7 +2436,11 @@ extern "C" int wn_gen_prime_part(wn_gen* g, const float* params, const int32_t* 
                                                                 L.R + L.S, L.R);
     gen_copy_bias<<<nb(L.R), 256, 0, s>>>(ly.proj.b_off >= 0 ? params + ly.proj.b_off : nullptr, S + o.bb, L.R);
     gen_copy_bias<<<nb(L.S), 256, 0, s>>>(ly.skip.b_off >= 0 ? params + ly.skip.b_off : nullptr, S + o.bb + L.R, L.S);
-    if (o.ring_len > 0)
+    if (o.ring_len > 0 && tc_prime)
+      gen_fill_ring_split<<<nb((int64_t)count * o.ring_len * L.R), 256, 0, s>>>(
+          reinterpret_cast<const __half*>(h->ws + t.x[l]), S + o.ring + (int64_t)stream0 * o.ring_len * L.R, count, Win, L.R,
+          o.ring_len, 1.f / tcs_act_scale());
+    else if (o.ring_len > 0)
       gen_fill_ring<<<nb((int64_t)count * o.ring_len * L.R), 256, 0, s>>>(
           h->ws + t.x[l], S + o.ring + (int64_t)stream0 * o.ring_len * L.R, count, Win, L.R, o.ring_len, 0);
   }
