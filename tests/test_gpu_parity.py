@@ -507,6 +507,36 @@ def test_tensor_core_generator(n, cs):
         assert np.array_equal(f, a)
 
 
+def test_tensor_core_generator_at_resident_capacity():
+    """gen_kernel_v6 at the size the bench runs it (every co-resident 4-CTA cluster filled: 4224 streams on a B200, automatic
+    kernel choice, fp16x2 priming in slices), through size-independent properties: streams are independent, so (1) streams
+    primed with the same window generate the same greedy samples wherever they sit (other cluster, other lane), (2) a handful
+    of them agree with the exact-fp32 single-CTA kernel run on just those windows, (3) two launches (waves) equal one."""
+    import os
+    from wavenet_b200 import _lib
+    cfg = make_cfg("C")
+    w = O.init_weights(cfg, np.random.default_rng(7), np.float32)
+    n = int(_lib.load().wn_gen_mma_capacity(4))
+    assert n >= 1024
+    base = np.random.default_rng(5).integers(0, 256, (97, O.input_width(cfg))).astype(np.int32)
+    window = base[np.arange(n) % 97]
+    steps = 24
+    got = make_net(cfg, w, faster=True, head_act="reference").generate(window, steps, mode="greedy").cpu().numpy()
+    assert np.array_equal(got, got[:97][np.arange(n) % 97])
+    os.environ["WN_GEN_V6"] = "0"
+    try:
+        ref = make_net(cfg, w, faster=True, head_act="reference").generate(base[:12], steps, mode="greedy").cpu().numpy()
+    finally:
+        os.environ.pop("WN_GEN_V6", None)
+    assert (got[:12] != ref).any(axis=1).sum() <= 1
+    os.environ["WN_GEN_V6_WAVE"] = "20"
+    try:
+        waves = make_net(cfg, w, faster=True, head_act="reference").generate(window, steps, mode="greedy").cpu().numpy()
+    finally:
+        os.environ.pop("WN_GEN_V6_WAVE", None)
+    assert np.array_equal(waves, got)
+
+
 def test_device_crop_batch_matches_reference_create_batch():
     """train_audio/train.py:14-22 restated vs wn_crop_batch with the same np.random stream."""
     rng = np.random.default_rng(0)
