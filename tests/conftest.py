@@ -24,3 +24,19 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _release_gpu_memory(request):
+    """The facade objects hold tens of GB of workspace / generator state and sit in reference cycles: collect them and hand
+    the cached blocks back after every GPU test, so that the suite's footprint is one test's, not the sum of all of them."""
+    yield
+    if "gpu" in request.keywords:
+        import gc
+        gc.collect()
+        try:
+            import torch
+            if torch.cuda.is_available():
+                torch.cuda.empty_cache()
+        except Exception:
+            pass

@@ -521,19 +521,28 @@ def test_tensor_core_generator_at_resident_capacity():
     base = np.random.default_rng(5).integers(0, 256, (97, O.input_width(cfg))).astype(np.int32)
     window = base[np.arange(n) % 97]
     steps = 24
-    got = make_net(cfg, w, faster=True, head_act="reference").generate(window, steps, mode="greedy").cpu().numpy()
+
+    def gen(win, env=None):
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()            # three generators of this size do not fit next to each other (50 GB each)
+        os.environ.update(env or {})
+        try:
+            net = make_net(cfg, w, faster=True, head_act="reference")
+            out = net.generate(win, steps, mode="greedy").cpu().numpy()
+            del net
+            return out
+        finally:
+            for k in (env or {}):
+                os.environ.pop(k, None)
+            gc.collect()
+            torch.cuda.empty_cache()
+
+    got = gen(window)
     assert np.array_equal(got, got[:97][np.arange(n) % 97])
-    os.environ["WN_GEN_V6"] = "0"
-    try:
-        ref = make_net(cfg, w, faster=True, head_act="reference").generate(base[:12], steps, mode="greedy").cpu().numpy()
-    finally:
-        os.environ.pop("WN_GEN_V6", None)
+    ref = gen(base[:12], {"WN_GEN_V6": "0"})
     assert (got[:12] != ref).any(axis=1).sum() <= 1
-    os.environ["WN_GEN_V6_WAVE"] = "20"
-    try:
-        waves = make_net(cfg, w, faster=True, head_act="reference").generate(window, steps, mode="greedy").cpu().numpy()
-    finally:
-        os.environ.pop("WN_GEN_V6_WAVE", None)
+    waves = gen(window, {"WN_GEN_V6_WAVE": "20"})
     assert np.array_equal(waves, got)
 
 
