@@ -595,8 +595,8 @@ def main():
                 "weight_stream_gbs_per_sm": per_cta / (us * 1e-6) / 1e9,
                 "weight_stream_gbs_all_ctas": n_ctas * world * per_cta / (us * 1e-6) / 1e9,
                 "bound": ("dependency-chain latency (30 layers x 1 cluster exchange + head per sample)" if clustered else
-                          "per layer: DSMEM all-gather of z (24-28 KB into every CTA at ~17-21 B/clk) + shared-memory A-operand reads of the "
-                          "MMAs (64 B/clk) + TMEM reads of the epilogues, all on one dependency chain" if mma else
+                          "per layer: DSMEM all-gather of z (24-28 KB into every CTA at ~17-21 B/clk) + chains of tiny MMAs that run at the MMA "
+                          "latency (55-75 cycles each) + TMEM reads of the epilogues (64 B/clk), all on one dependency chain per cluster" if mma else
                           ("FP32 FMA issue + one cluster exchange per layer (per CTA and step: 16 streams x 155 k MACs)" if many
                            else "dependency-chain latency (30 layers x 2 block barriers + head per sample)"))}
         if rank == 0 and world == 1 and not args.no_cpu:
