@@ -670,3 +670,19 @@ def test_tf32_backward_alone_is_tf32_accurate(name, B, W, T):
             assert rel_err(g_tc[k], v) < 1e-2, (k, rel_err(g_tc[k], v))
         else:
             assert np.abs(g_tc[k]).max() == 0, k
+
+
+def test_stale_variable_takes_the_external_input_path():
+    """A Variable returned by forward_causal_block stands for tape contents; after a second causal pass of the same shape the
+    tape holds other data, and the first Variable must go through the external-input path (its .data) instead."""
+    cfg = make_cfg("tiny_k2")
+    w = O.init_weights(cfg, np.random.default_rng(0), np.float64)
+    net = make_net(cfg, w)
+    rng = np.random.default_rng(1)
+    xa, xb = (rng.integers(0, 6, (2, 40)).astype(np.int32) for _ in range(2))
+    ca = net.forward_causal_block(xa)
+    net.forward_causal_block(xb)                       # same shape: replaces the tape behind `ca`
+    out_a, _ = net.forward_residual_block(ca)
+    fresh = make_net(cfg, w)
+    want, _ = fresh.forward_residual_block(fresh.forward_causal_block(xa))
+    assert np.abs(out_a.data.cpu().numpy() - want.data.cpu().numpy()).max() < 1e-6

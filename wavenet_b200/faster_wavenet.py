@@ -71,6 +71,7 @@ class FasterWaveNet(WaveNet):
         self._keep["idx"] = idx
         probs = torch.empty((n, self.params.quantization_steps), dtype=torch.float32, device=self._device)
         # the full pass keeps the activation tape of every primed stream: slices of PRIME_SLICE streams bound the workspace
+        self._tape_gen = getattr(self, "_tape_gen", 0) + 1      # the priming pass rewrites the tape: older Variables are stale
         for s0 in range(0, n, self.PRIME_SLICE):
             cnt = min(self.PRIME_SLICE, n - s0)
             self._bind(cnt, W)

@@ -407,30 +407,39 @@ class WaveNet(object):
         self._keep["idx"] = idx
         out = torch.empty((B, W, self.params.causal_conv_channels[-1]), dtype=torch.float32, device=self._device)
         check(self._libh.wn_forward_causal_block(self._h, _ptr(self._params), _ptr(idx), _ptr(out), _stream()))
-        return Variable(self._as_bc1w(out), tag=("causal", B, W))
+        # the tag names the tape contents this Variable stands for: a later pass of the same shape replaces them, and a
+        # Variable with a stale generation then goes through the external-input path (its .data is a real copy)
+        self._tape_gen = getattr(self, "_tape_gen", 0) + 1
+        return Variable(self._as_bc1w(out), tag=("causal", B, W, self._tape_gen))
 
     def forward_residual_block(self, x_batch):
         self._need_gpu()
         x_batch = self.to_variable(x_batch)
         R, S = self.params.causal_conv_channels[-1], self.params.softmax_conv_channels[0]
-        if x_batch._tag is not None and x_batch._tag[0] == "causal" and self._ws_key == x_batch._tag[1:]:
-            B, W = x_batch._tag[1:]
+        tag = x_batch._tag
+        if (tag is not None and tag[0] == "causal" and self._ws_key == tag[1:3]
+                and tag[3] == getattr(self, "_tape_gen", 0)):
+            B, W = tag[1:3]
             xin = None
         else:
             xin = self._to_bwc(x_batch)
             B, W = xin.shape[0], xin.shape[1]
             self._bind(B, W)
+            self._tape_gen = getattr(self, "_tape_gen", 0) + 1
         out = torch.empty((B, W, R), dtype=torch.float32, device=self._device)
         skip = torch.empty((B, W, S), dtype=torch.float32, device=self._device)
         check(self._libh.wn_forward_residual_block(self._h, _ptr(self._params), _ptr(xin), _ptr(out), _ptr(skip), _stream()))
-        return Variable(self._as_bc1w(out), tag=("out", B, W, W)), Variable(self._as_bc1w(skip), tag=("skip", B, W, W))
+        gen = self._tape_gen
+        return (Variable(self._as_bc1w(out), tag=("out", B, W, W, gen)),
+                Variable(self._as_bc1w(skip), tag=("skip", B, W, W, gen)))
 
     def forward_softmax_block(self, x_batch, apply_softmax=True):
         self._need_gpu()
         x_batch = self.to_variable(x_batch)
         Q = self.params.quantization_steps
         tag = x_batch._tag
-        if tag is not None and tag[0] == "skip" and self._ws_key == tag[1:3]:
+        if (tag is not None and tag[0] == "skip" and self._ws_key == tag[1:3]
+                and tag[4] == getattr(self, "_tape_gen", 0)):
             B, W, T = tag[1], tag[2], tag[3]
             xin = None
         else:
@@ -450,7 +459,7 @@ class WaveNet(object):
         x = self.to_variable(x)
         tag = x._tag
         if tag is not None and tag[0] in ("skip", "out"):
-            tag = (tag[0], tag[1], tag[2], tag[3] - cut)
+            tag = (tag[0], tag[1], tag[2], tag[3] - cut, tag[4])
         else:
             tag = None
         return Variable(x.data[:, :, :, cut:], tag=tag)
@@ -533,6 +542,7 @@ class WaveNet(object):
         return x, t
 
     def _fwd_bwd(self, x_idx, target, T):
+        self._tape_gen = getattr(self, "_tape_gen", 0) + 1      # the fused step rewrites the tape: older Variables are stale
         check(self._libh.wn_forward_loss(self._h, _ptr(self._params), _ptr(x_idx), _ptr(target), T, _ptr(self._loss),
                                          None, _stream()))
         self.backward()
@@ -571,6 +581,7 @@ class WaveNet(object):
         if torch.cuda.current_device() != self._device.index:
             torch.cuda.set_device(self._device)
         self._bind(B, W)
+        self._tape_gen = getattr(self, "_tape_gen", 0) + 1      # the step (eager or replayed) rewrites the tape
         key = (B, W, T, int(self._libh.wn_get_precision(self._h)))
         if not getattr(self, "use_cuda_graph", True):
             self._keep["idx"], self._keep["tgt"] = x_idx, target
